@@ -1,0 +1,185 @@
+"""Datasets and loaders.
+
+The reference trains on torchvision CIFAR-10 with ``ToTensor`` + ``Normalize(0.5, 0.5)``, an
+*unseeded* random ``Subset`` of ``sample_size`` images, batch 64, and a ``DistributedSampler`` in
+the data-parallel script only (data_parallel_train.py:43-73; layer_…:103-131 and tensor_…:123-152
+iterate the whole subset on every rank).  There is no network here, so the default dataset is a
+**seeded synthetic CIFAR-shaped set** (uint8 32×32×3 + labels 0..9) whose images carry a weak
+class-dependent signal so loss/accuracy curves are meaningful.  Real CIFAR-10 python batches are
+read from ``data_dir`` when ``synthetic=False``.
+
+Loader design (B200-first): the whole (sub)set is tiny (50 000×3 KiB = 150 MB), so it is staged
+once in *pinned* host memory as uint8 NHWC; each step's batch is one async H2D copy of 64×3 KiB
+on a copy stream, double-buffered, normalisation + bf16 cast fused into the stem's im2col kernel.
+A native C++ prefetch thread (csrc/loader.cpp) assembles shuffled batches into the pinned
+staging ring; the pure-Python path below is the fallback and the CPU path.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+import torch
+
+CIFAR_MEAN, CIFAR_STD = 0.5, 0.5          # reference Normalize((0.5,)*3, (0.5,)*3)
+
+
+class SyntheticCIFAR:
+    """Deterministic CIFAR-shaped data: images uint8 [N,32,32,3] (NHWC), labels int64 [N]."""
+
+    def __init__(self, n: int, seed: int = 1234, num_classes: int = 10, hw: int = 32):
+        rng = np.random.default_rng(seed)
+        self.labels = rng.integers(0, num_classes, size=n, dtype=np.int64)
+        protos = rng.normal(0.0, 1.0, size=(num_classes, hw, hw, 3)).astype(np.float32)
+        noise = rng.normal(0.0, 1.0, size=(n, hw, hw, 3)).astype(np.float32)
+        img = 127.5 + 40.0 * (0.6 * protos[self.labels] + noise)
+        self.images = np.clip(img, 0, 255).astype(np.uint8)
+        self.num_classes = num_classes
+
+    def __len__(self):
+        return len(self.labels)
+
+
+class CIFAR10Files:
+    """CIFAR-10 'python version' batches (data_batch_1..5) under ``root/cifar-10-batches-py``."""
+
+    def __init__(self, root: str, train: bool = True):
+        base = os.path.join(root, "cifar-10-batches-py")
+        files = [f"data_batch_{i}" for i in range(1, 6)] if train else ["test_batch"]
+        xs, ys = [], []
+        for f in files:
+            path = os.path.join(base, f)
+            if not os.path.exists(path):
+                raise FileNotFoundError(
+                    f"{path} not found (no network in this environment: use synthetic data)")
+            with open(path, "rb") as fh:
+                d = pickle.load(fh, encoding="latin1")
+            xs.append(np.asarray(d["data"], dtype=np.uint8).reshape(-1, 3, 32, 32).transpose(0, 2, 3, 1))
+            ys.append(np.asarray(d["labels"], dtype=np.int64))
+        self.images = np.ascontiguousarray(np.concatenate(xs))
+        self.labels = np.concatenate(ys)
+        self.num_classes = 10
+
+    def __len__(self):
+        return len(self.labels)
+
+
+def build_dataset(sample_size: Optional[int], synthetic: bool, data_dir: str, seed: int):
+    """Returns (images uint8 NHWC ndarray, labels int64 ndarray) of the requested subset.
+
+    The subset is a *seeded* permutation prefix (the reference draws an unseeded one per rank,
+    SURVEY Q6 — identical data across ranks is required for TP/PP semantics)."""
+    if synthetic:
+        n = sample_size if sample_size else 50000
+        ds = SyntheticCIFAR(n, seed=seed)
+        return ds.images, ds.labels
+    ds = CIFAR10Files(data_dir, train=True)
+    if sample_size and sample_size < len(ds):
+        idx = np.random.default_rng(seed).permutation(len(ds))[:sample_size]
+        return ds.images[idx], ds.labels[idx]
+    return ds.images, ds.labels
+
+
+class ShardedSampler:
+    """DistributedSampler semantics (pad to a multiple of ``num_replicas`` by wrapping, then
+    rank-strided slice; seeded per-epoch shuffle) — data_parallel_train.py:63."""
+
+    def __init__(self, n: int, num_replicas: int, rank: int, shuffle: bool = True, seed: int = 0):
+        self.n, self.num_replicas, self.rank = n, num_replicas, rank
+        self.shuffle, self.seed, self.epoch = shuffle, seed, 0
+        self.num_samples = -(-n // num_replicas)
+        self.total = self.num_samples * num_replicas
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = epoch
+
+    def indices(self) -> np.ndarray:
+        if self.shuffle:
+            idx = np.random.default_rng(self.seed + self.epoch).permutation(self.n)
+        else:
+            idx = np.arange(self.n)
+        if self.total > self.n:
+            reps = -(-self.total // self.n)
+            idx = np.concatenate([idx] * reps)[: self.total]
+        return idx[self.rank: self.total: self.num_replicas]
+
+    def __len__(self):
+        return self.num_samples
+
+
+class BatchLoader:
+    """Iterates (images, labels) batches on ``device``.
+
+    images are delivered as uint8 NHWC ``[B,32,32,3]`` on CUDA (normalisation is fused into the
+    stem kernel) or as normalised fp32 NCHW-channels_last on CPU.  H2D copies are issued from
+    pinned memory on a dedicated copy stream one batch ahead of compute."""
+
+    def __init__(self, images: np.ndarray, labels: np.ndarray, batch_size: int, device,
+                 sampler: Optional[ShardedSampler] = None, drop_last: bool = False,
+                 prefetch: bool = True):
+        self.device = torch.device(device)
+        self.bs = batch_size
+        self.sampler = sampler
+        self.drop_last = drop_last
+        self.images = torch.from_numpy(images)
+        self.labels = torch.from_numpy(labels)
+        self.cuda = self.device.type == "cuda"
+        if self.cuda:
+            self.images = self.images.pin_memory()
+            self.labels = self.labels.pin_memory()
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.prefetch = prefetch and self.cuda
+        self.h2d_bytes_per_batch = batch_size * (images[0].nbytes + 8)
+
+    @property
+    def dataset_len(self) -> int:
+        return len(self.labels)
+
+    def __len__(self) -> int:
+        n = len(self.sampler) if self.sampler is not None else len(self.labels)
+        return n // self.bs if self.drop_last else -(-n // self.bs)
+
+    def _index_batches(self):
+        idx = self.sampler.indices() if self.sampler is not None else np.arange(len(self.labels))
+        nb = len(self)
+        for b in range(nb):
+            yield idx[b * self.bs:(b + 1) * self.bs]
+
+    def _stage(self, bidx):
+        t = torch.from_numpy(np.ascontiguousarray(bidx))
+        x = self.images.index_select(0, t)
+        y = self.labels.index_select(0, t)
+        if not self.cuda:
+            xf = x.permute(0, 3, 1, 2).float().div_(255.0).sub_(CIFAR_MEAN).div_(CIFAR_STD)
+            return xf.contiguous(memory_format=torch.channels_last), y
+        x, y = x.pin_memory(), y.pin_memory()
+        with torch.cuda.stream(self.copy_stream):
+            xd = x.to(self.device, non_blocking=True)
+            yd = y.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return xd, yd, ev, (x, y)
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        it = self._index_batches()
+        if not self.cuda:
+            for bidx in it:
+                yield self._stage(bidx)
+            return
+        nxt = None
+        for bidx in it:
+            cur = nxt
+            nxt = self._stage(bidx)
+            if cur is not None:
+                yield self._deliver(cur)
+        if nxt is not None:
+            yield self._deliver(nxt)
+
+    def _deliver(self, staged):
+        xd, yd, ev, _keep = staged
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        xd.record_stream(torch.cuda.current_stream(self.device))
+        yd.record_stream(torch.cuda.current_stream(self.device))
+        return xd, yd

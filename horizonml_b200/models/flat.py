@@ -1,0 +1,147 @@
+"""Flat parameter / gradient storage.
+
+All parameters of a (sub)model live in ONE fp32 master buffer, their gradients in ONE fp32
+gradient buffer laid out **in reverse execution order** (fc, layer4 … conv1 — the order backward
+produces them, SURVEY §2.5 "Backward shapes"), and — for bf16 compute — a bf16 shadow buffer the
+kernels read and the fused Adam kernel refreshes.  Buckets are contiguous slices of the gradient
+buffer, so a bucket all-reduce needs no flatten/unflatten copy (what DDP's reducer does with
+25 MiB buckets, data_parallel_train.py:202) and wgrad kernels write straight into it.
+
+Every parameter's offset is padded to 64 elements so bf16 shadows are 128-byte aligned (TMA global
+address requirement is 16 B; 128 B keeps vector loads and swizzle atoms aligned).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+ALIGN = 64
+
+
+@dataclass
+class Bucket:
+    index: int
+    start: int           # element offset in the flat buffers
+    end: int
+    names: List[str]
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+class FlatParams:
+    def __init__(self, named_params: Sequence[Tuple[str, nn.Parameter]], device, compute_dtype,
+                 bucket_cap_mb: float = 25.0, reverse: bool = True, first_bucket_mb: float = 1.0):
+        named = list(named_params)
+        order = list(reversed(named)) if reverse else named
+        self.names = [n for n, _ in order]
+        self.params = [p for _, p in order]
+        offs, cur = [], 0
+        for p in self.params:
+            offs.append(cur)
+            cur = _round_up(cur + p.numel(), ALIGN)
+        self.offsets = offs
+        self.total = max(cur, ALIGN)
+        self.device = torch.device(device)
+        self.compute_dtype = compute_dtype
+        self.master = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.shadow = (torch.zeros(self.total, dtype=compute_dtype, device=self.device)
+                       if compute_dtype != torch.float32 else None)
+        for p, o in zip(self.params, self.offsets):
+            n = p.numel()
+            src = p.detach()
+            cl = src.dim() == 4
+            # physical order of a channels_last 4-D tensor is [d0, d2, d3, d1]
+            phys = src.permute(0, 2, 3, 1).contiguous().view(-1) if cl else src.contiguous().view(-1)
+            self.master[o:o + n].copy_(phys)
+
+            def view(buf):
+                v = buf[o:o + n]
+                if cl:
+                    d0, d1, d2, d3 = src.shape
+                    return v.view(d0, d2, d3, d1).permute(0, 3, 1, 2)
+                return v.view(src.shape)
+
+            p.data = view(self.master)
+            p.main_grad = view(self.grad)
+            p._acc = False
+            p._flat_range = (o, o + n)
+            if self.shadow is not None:
+                p.shadow = view(self.shadow)
+        self.sync_shadow()
+        self.buckets = self._make_buckets(bucket_cap_mb, first_bucket_mb)
+        self._bucket_of: Dict[int, int] = {}
+        for b in self.buckets:
+            for nme in b.names:
+                self._bucket_of[id(self.params[self.names.index(nme)])] = b.index
+
+    # ------------------------------------------------------------------------------------
+    def _make_buckets(self, cap_mb: float, first_mb: float) -> List[Bucket]:
+        """Greedy contiguous bucketing in gradient-ready order (DDP-style: small first bucket so
+        the first all-reduce starts early, then ``cap_mb`` buckets)."""
+        buckets: List[Bucket] = []
+        cap = int(first_mb * (1 << 20) / 4)
+        start, names = 0, []
+        for i, (nme, p, o) in enumerate(zip(self.names, self.params, self.offsets)):
+            names.append(nme)
+            end = self.offsets[i + 1] if i + 1 < len(self.offsets) else self.total
+            if end - start >= cap or i + 1 == len(self.params):
+                buckets.append(Bucket(len(buckets), start, end, names))
+                start, names = end, []
+                cap = int(cap_mb * (1 << 20) / 4)
+        return buckets
+
+    def bucket_index(self, p) -> int:
+        return self._bucket_of[id(p)]
+
+    def begin_step(self) -> None:
+        """Next gradient write overwrites (no zero-fill pass needed)."""
+        for p in self.params:
+            p._acc = False
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        self.begin_step()
+
+    @torch.no_grad()
+    def sync_shadow(self) -> None:
+        if self.shadow is not None:
+            self.shadow.copy_(self.master)
+
+    def numel(self) -> int:
+        return sum(p.numel() for p in self.params)
+
+    def grad_bytes(self, dtype_bytes: int = 4) -> int:
+        return self.numel() * dtype_bytes
+
+
+class FlatAdam:
+    """Adam over a FlatParams store — one fused kernel per step, fp32 master +
+    moments, bf16 shadow refresh fused in.  Semantics = ``torch.optim.Adam(lr)`` as used by the
+    reference (data_parallel_train.py:205)."""
+
+    def __init__(self, flat: FlatParams, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.flat, self.lr, self.betas, self.eps = flat, lr, betas, eps
+        self.m = torch.zeros_like(flat.master)
+        self.v = torch.zeros_like(flat.master)
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=flat.device)
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0) -> None:
+        from .. import ops
+        f = self.flat
+        ops.adam_step(f.master, f.grad, self.m, self.v, f.shadow, self.step_t, self.lr,
+                      self.betas[0], self.betas[1], self.eps, grad_scale)
+
+    def state_dict(self) -> dict:
+        return {"m": self.m.cpu(), "v": self.v.cpu(), "step": self.step_t.cpu(), "lr": self.lr,
+                "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_t.copy_(sd["step"])
+        self.lr = sd.get("lr", self.lr)

@@ -1,0 +1,147 @@
+"""ResNet-18 built from the fused op set (NHWC / channels_last, bf16 compute on GPU).
+
+Parameter names and shapes are those of ``torchvision.models.resnet18`` (the model every
+reference script instantiates: data_parallel_train.py:198, layer_model_parallel_train.py:30,
+tensor_parallel_train.py:72) so state dicts are interchangeable; the topology is organised as
+the reference's five *atomic blocks* (layer_model_parallel_train.py:37-52):
+
+    [conv1+bn1+relu+maxpool] [layer1] [layer2] [layer3] [layer4+avgpool+flatten+fc]
+
+Differences from the reference: the classifier is ``num_classes``-way (10) in every
+strategy (the layer-parallel script keeps torchvision's 1000-way fc, Q2).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class ConvW(nn.Module):
+    """Holds a conv weight [Cout, Cin, R, S] stored channels_last (physically [Cout,R,S,Cin])."""
+
+    def __init__(self, cin: int, cout: int, k: int, stride: int, pad: int):
+        super().__init__()
+        w = torch.empty(cout, cin, k, k)
+        nn.init.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")   # torchvision init
+        self.weight = nn.Parameter(w.contiguous(memory_format=torch.channels_last))
+        self.stride, self.pad, self.k = stride, pad, k
+        self.cin, self.cout = cin, cout
+
+
+class BNP(nn.Module):
+    """BatchNorm2d parameters/buffers (training-mode batch statistics, momentum 0.1, eps 1e-5)."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.zeros((), dtype=torch.long))
+        self.momentum, self.eps = 0.1, 1e-5
+
+
+def _cba(x, conv: ConvW, bn: BNP, relu: bool, residual=None, training=True):
+    return ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                           stride=conv.stride, pad=conv.pad, relu=relu, residual=residual,
+                           momentum=bn.momentum, eps=bn.eps, training=training)
+
+
+class BasicBlock(nn.Module):
+    def __init__(self, cin: int, cout: int, stride: int):
+        super().__init__()
+        self.conv1 = ConvW(cin, cout, 3, stride, 1)
+        self.bn1 = BNP(cout)
+        self.conv2 = ConvW(cout, cout, 3, 1, 1)
+        self.bn2 = BNP(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential()
+            self.downsample.add_module("0", ConvW(cin, cout, 1, stride, 0))
+            self.downsample.add_module("1", BNP(cout))
+
+    def forward(self, x):
+        t = self.training
+        idt = x
+        if self.downsample is not None:
+            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t)
+        y = _cba(x, self.conv1, self.bn1, relu=True, training=t)
+        return _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t)
+
+
+class Stem(nn.Module):
+    """conv1 7×7/2 + bn1 + relu + maxpool 3×3/2 (atomic block 0)."""
+
+    def __init__(self, parent: "ResNet18"):
+        super().__init__()
+        object.__setattr__(self, "_p", parent)   # parameters live on the parent (torchvision names)
+
+    def forward(self, x):
+        p = self._p
+        y = _cba(x, p.conv1, p.bn1, relu=True, training=p.training)
+        return ops.maxpool3x3s2(y)
+
+
+class ResNet18(nn.Module):
+    LAYERS = [(64, 64, 1), (64, 128, 2), (128, 256, 2), (256, 512, 2)]
+
+    def __init__(self, num_classes: int = 10, class_pad_to: int = 1):
+        super().__init__()
+        self.conv1 = ConvW(3, 64, 7, 2, 3)
+        self.bn1 = BNP(64)
+        for i, (cin, cout, s) in enumerate(self.LAYERS, start=1):
+            setattr(self, f"layer{i}", nn.Sequential(BasicBlock(cin, cout, s), BasicBlock(cout, cout, 1)))
+        self.num_classes = num_classes
+        kpad = int(math.ceil(num_classes / class_pad_to) * class_pad_to)
+        fc = nn.Linear(512, kpad)
+        if kpad != num_classes:
+            with torch.no_grad():
+                fc.weight[num_classes:].zero_()
+                fc.bias[num_classes:].zero_()
+        self.fc = fc
+        self._stem = Stem(self)
+
+    # ---- the reference's five atomic blocks -------------------------------------------------
+    def atomic_blocks(self) -> List[nn.Module]:
+        return [self._stem, self.layer1, self.layer2, self.layer3, self.layer4]
+
+    def block_param_names(self) -> List[List[str]]:
+        groups = [["conv1.", "bn1."], ["layer1."], ["layer2."], ["layer3."], ["layer4.", "fc."]]
+        names = [n for n, _ in self.named_parameters()]
+        return [[n for n in names if any(n.startswith(g) for g in gs)] for gs in groups]
+
+    def features(self, x, first: int = 0, last: int = 4):
+        blocks = self.atomic_blocks()
+        for i in range(first, last + 1):
+            x = blocks[i](x)
+        return x
+
+    def forward(self, x):
+        """images (channels_last activations in compute dtype) → logits [N, num_classes]"""
+        f = self.features(x)
+        return ops.head_logits(f, self.fc.weight, self.fc.bias)[:, : self.num_classes]
+
+    def forward_loss(self, x, labels, loss_scale: float = 1.0, stats_out: Optional[dict] = None):
+        f = self.features(x)
+        return ops.head_loss(f, self.fc.weight, self.fc.bias, labels, loss_scale,
+                             n_valid=self.num_classes, stats_out=stats_out)
+
+
+def resnet18(num_classes: int = 10, seed: Optional[int] = None, class_pad_to: int = 1) -> ResNet18:
+    if seed is not None:
+        g = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+    m = ResNet18(num_classes, class_pad_to)
+    if seed is not None:
+        torch.random.set_rng_state(g)
+    return m
+
+
+def torchvision_state_dict(model: ResNet18) -> dict:
+    """state_dict with plain-contiguous tensors, loadable by torchvision.models.resnet18."""
+    return {k: v.detach().contiguous() for k, v in model.state_dict().items()}

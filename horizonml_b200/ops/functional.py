@@ -1,0 +1,224 @@
+"""Backend-agnostic autograd layer over the fused op set.
+
+Design points
+-------------
+* The unit of fusion is **conv → BatchNorm(batch stats) → [+residual] → [ReLU]**
+  (``conv_bn_act``): on the native backend the conv kernel's epilogue produces the BN
+  partial sums, one elementwise kernel applies BN/residual/ReLU; backward is
+  (reduce, apply, dgrad, wgrad) — see SURVEY §2.5 W4-W6.
+* Weight gradients are **written in place into ``param.main_grad``** (a view of the flat
+  fp32 gradient bucket owned by ``FlatParams``), never materialised as autograd outputs —
+  this is what lets wgrad kernels deposit straight into the all-reduce bucket and lets
+  the DP reducer launch a bucket's all-reduce the moment its last wgrad is enqueued
+  (reference equivalent: DDP reducer hooks fired inside ``loss.backward()``,
+  data_parallel_train.py:118).
+* Parameters are fp32 masters; when the compute dtype is bf16 the kernels read the
+  ``param.shadow`` bf16 copy maintained by the fused Adam kernel.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import torch_backend as _tb
+
+_state = {"backend": "torch", "native": None}
+
+
+def set_backend(name: str) -> None:
+    if name not in ("torch", "native"):
+        raise ValueError(name)
+    if name == "native":
+        from . import native_backend  # noqa: WPS433 (lazy: needs the CUDA extension)
+        _state["native"] = native_backend
+    _state["backend"] = name
+
+
+def get_backend() -> str:
+    return _state["backend"]
+
+
+def _be(t: torch.Tensor):
+    if _state["backend"] == "native" and t.is_cuda:
+        return _state["native"]
+    return _tb
+
+
+# ----------------------------------------------------------------------------------------------
+# parameter helpers
+# ----------------------------------------------------------------------------------------------
+
+def compute_weight(p: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """The tensor kernels should read for parameter ``p`` in compute dtype ``dtype``."""
+    if dtype == p.dtype:
+        return p.detach()
+    sh = getattr(p, "shadow", None)
+    if sh is not None and sh.dtype == dtype:
+        return sh
+    return p.detach().to(dtype)
+
+
+def grad_target(p: torch.Tensor):
+    """(fp32 tensor to write dW into, accumulate?) for parameter ``p``."""
+    mg = getattr(p, "main_grad", None)
+    if mg is not None:
+        return mg, bool(getattr(p, "_acc", False))
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
+    return p.grad, True
+
+
+def grad_written(p: torch.Tensor) -> None:
+    if getattr(p, "main_grad", None) is not None:
+        p._acc = True
+    hook = getattr(p, "_ready_hook", None)
+    if hook is not None:
+        hook(p)
+
+
+def _write_vec_grad(p, g):
+    tgt, acc = grad_target(p)
+    if acc:
+        tgt.add_(g.to(tgt.dtype).view_as(tgt))
+    else:
+        tgt.copy_(g.to(tgt.dtype).view_as(tgt))
+    grad_written(p)
+
+
+# ----------------------------------------------------------------------------------------------
+# conv + BN + (residual) + (ReLU)
+# ----------------------------------------------------------------------------------------------
+
+class _ConvBNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
+                momentum, eps, training):
+        be = _be(x)
+        w = compute_weight(weight, x.dtype)
+        y_raw, sums = be.conv_fwd(x, w, stride, pad, training)
+        out, mean, invstd = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar,
+                                          momentum, eps, residual, relu, training)
+        ctx.save_for_backward(x, y_raw, out, mean, invstd)
+        ctx.params = (weight, gamma, beta)
+        ctx.cfg = (stride, pad, relu, residual is not None, training)
+        ctx.x_needs_grad = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y_raw, out, mean, invstd = ctx.saved_tensors
+        weight, gamma, beta = ctx.params
+        stride, pad, relu, has_res, training = ctx.cfg
+        if not training:
+            raise RuntimeError("conv_bn_act backward requires training=True")
+        be = _be(x)
+        dout = dout.contiguous(memory_format=torch.channels_last)
+        dy, dgamma, dbeta, dres = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(),
+                                                relu, has_res)
+        _write_vec_grad(gamma, dgamma)
+        _write_vec_grad(beta, dbeta)
+        w = compute_weight(weight, x.dtype)
+        tgt, acc = grad_target(weight)
+        be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc)
+        grad_written(weight)
+        dx = be.conv_dgrad(dy, w, x.shape, stride, pad) if ctx.x_needs_grad else None
+        return (dx, None, None, None, dres, None, None, None, None, None, None, None, None)
+
+
+def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True, residual=None,
+                momentum=0.1, eps=1e-5, training=True):
+    if not training or not torch.is_grad_enabled():
+        be = _be(x)
+        y_raw, sums = be.conv_fwd(x, compute_weight(weight, x.dtype), stride, pad, training)
+        out, _, _ = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar,
+                                  momentum, eps, residual, relu, training)
+        return out
+    return _ConvBNAct.apply(x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
+                            momentum, eps, training)
+
+
+# ----------------------------------------------------------------------------------------------
+# max-pool 3×3 / stride 2 / pad 1 (the stem pool; index-free recompute backward)
+# ----------------------------------------------------------------------------------------------
+
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = _be(x).maxpool_fwd(x)
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        return _be(x).maxpool_bwd(dy.contiguous(memory_format=torch.channels_last), x, y)
+
+
+def maxpool3x3s2(x):
+    if not x.requires_grad or not torch.is_grad_enabled():
+        return _be(x).maxpool_fwd(x)
+    return _MaxPool.apply(x)
+
+
+# ----------------------------------------------------------------------------------------------
+# classifier head: avg-pool → FC → softmax-CE (+ accuracy), forward and backward in one kernel
+# ----------------------------------------------------------------------------------------------
+
+class _HeadLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, fc_w, fc_b, labels, loss_scale, n_valid, stats_out):
+        be = _be(feat)
+        tw, accw = grad_target(fc_w)
+        tb, accb = grad_target(fc_b) if fc_b is not None else (None, False)
+        w = fc_w.detach()
+        loss, correct, dfeat, logits = be.head_fwd_bwd(
+            feat, w, fc_b.detach() if fc_b is not None else None, labels, loss_scale, n_valid,
+            tw, tb, accw, feat.requires_grad)
+        ctx.params = (fc_w, fc_b)
+        ctx.save_for_backward(dfeat if dfeat is not None else torch.empty(0))
+        ctx.has_dfeat = dfeat is not None
+        if stats_out is not None:
+            stats_out["correct"] = correct
+            stats_out["logits"] = logits
+        ctx.mark_non_differentiable(correct)
+        return loss, correct
+
+    @staticmethod
+    def backward(ctx, dloss, _dcorrect):
+        # gradients were produced in forward with d(loss)=1 (loss_scale already folded in)
+        fc_w, fc_b = ctx.params
+        grad_written(fc_w)
+        if fc_b is not None:
+            grad_written(fc_b)
+        (dfeat,) = ctx.saved_tensors
+        return (dfeat if ctx.has_dfeat else None), None, None, None, None, None, None
+
+
+def head_loss(feat, fc_w, fc_b, labels, loss_scale: float = 1.0, n_valid: Optional[int] = None,
+              stats_out: Optional[dict] = None):
+    """Returns (loss, correct_count).  ``loss.backward()`` must be seeded with 1 (the default)."""
+    n_valid = fc_w.shape[0] if n_valid is None else n_valid
+    return _HeadLoss.apply(feat, fc_w, fc_b, labels, float(loss_scale), int(n_valid), stats_out)
+
+
+def head_logits(feat, fc_w, fc_b):
+    """Inference-only logits (avg-pool + FC)."""
+    pooled = feat.float().mean(dim=(2, 3))
+    return _be(feat).linear_fwd(pooled, fc_w.detach(), fc_b.detach() if fc_b is not None else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# small utilities shared by trainers
+# ----------------------------------------------------------------------------------------------
+
+def adam_step(master, grad, m, v, shadow, step_t, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
+    _be(master).adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale)
+
+
+def grad_diff_sq(grad, prev):
+    return _be(grad).grad_diff_sq(grad, prev)
+
+
+def stem_prepare(images, mean=0.5, std=0.5, dtype=torch.float32):
+    return _be(images).stem_prepare(images, mean, std, dtype)

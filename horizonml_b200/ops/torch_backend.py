@@ -1,0 +1,187 @@
+"""Pure-PyTorch implementation of the op set.
+
+Two jobs: (1) the numerical oracle every sm_100a kernel is tested against, and (2) the
+CPU/gloo plumbing backend (BASELINE.json config #1).  Signatures are identical to
+``native_backend`` so the autograd layer in ``ops.functional`` is backend-agnostic.
+
+All activations are logical NCHW tensors stored channels_last (physically NHWC); weights are
+logical [Cout, Cin, R, S] stored channels_last (physically [Cout, R, S, Cin]).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t.contiguous()
+
+
+def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
+    y = _cl(F.conv2d(x, w.to(x.dtype), None, stride, pad))
+    if not want_stats:
+        return y, None
+    yf = y.float()
+    sums = torch.stack([yf.sum(dim=(0, 2, 3)), (yf * yf).sum(dim=(0, 2, 3))])
+    return y, sums
+
+
+def bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum: float, eps: float,
+               residual, relu: bool, training: bool):
+    """BatchNorm (batch statistics) + optional residual add + optional ReLU.
+
+    Returns (out, mean, invstd).  ``sums`` (2×C: Σy, Σy²) may come from the conv epilogue."""
+    C = y_raw.shape[1]
+    cnt = y_raw.numel() // C
+    if training:
+        if sums is None:
+            yf = y_raw.float()
+            sums = torch.stack([yf.sum(dim=(0, 2, 3)), (yf * yf).sum(dim=(0, 2, 3))])
+        mean = sums[0] / cnt
+        var = (sums[1] / cnt - mean * mean).clamp_min(0.0)
+        if rmean is not None:
+            with torch.no_grad():
+                unbiased = var * (cnt / max(cnt - 1, 1))
+                rmean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                rvar.mul_(1 - momentum).add_(unbiased, alpha=momentum)
+    else:
+        mean, var = rmean.float(), rvar.float()
+    invstd = torch.rsqrt(var + eps)
+    scale = (gamma.float() * invstd).view(1, C, 1, 1)
+    shift = (beta.float() - mean * gamma.float() * invstd).view(1, C, 1, 1)
+    out = y_raw.float() * scale + shift
+    if residual is not None:
+        out = out + residual.float()
+    if relu:
+        out = out.clamp_min(0.0)
+    return _cl(out.to(y_raw.dtype)), mean, invstd
+
+
+def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: bool):
+    """Backward of bn_act_fwd (training mode). Returns (dy_raw, dgamma, dbeta, dres)."""
+    C = y_raw.shape[1]
+    cnt = y_raw.numel() // C
+    g = dout.float()
+    if relu:
+        g = g * (out > 0).to(g.dtype)
+    dres = _cl(g.to(dout.dtype)) if has_residual else None
+    xhat = (y_raw.float() - mean.view(1, C, 1, 1)) * invstd.view(1, C, 1, 1)
+    dbeta = g.sum(dim=(0, 2, 3))
+    dgamma = (g * xhat).sum(dim=(0, 2, 3))
+    k = (gamma.float() * invstd).view(1, C, 1, 1)
+    dy = k * (g - (dbeta / cnt).view(1, C, 1, 1) - xhat * (dgamma / cnt).view(1, C, 1, 1))
+    return _cl(dy.to(y_raw.dtype)), dgamma, dbeta, dres
+
+
+def conv_dgrad(dy, w, x_shape, stride: int, pad: int):
+    dx, _, _ = torch.ops.aten.convolution_backward(
+        dy, dy.new_empty(x_shape), w.to(dy.dtype), None, [stride, stride], [pad, pad], [1, 1], False,
+        [0, 0], 1, [True, False, False])
+    return _cl(dx)
+
+
+def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, accumulate: bool):
+    """dW written (or accumulated) as fp32 into ``out_grad`` — a view of the flat gradient bucket
+    with the weight's logical shape / channels_last strides."""
+    _, gw, _ = torch.ops.aten.convolution_backward(
+        dy, x, dy.new_empty(w_shape), None, [stride, stride], [pad, pad], [1, 1], False,
+        [0, 0], 1, [False, True, False])
+    gw = gw.float()
+    if accumulate:
+        out_grad.add_(gw)
+    else:
+        out_grad.copy_(gw)
+
+
+def maxpool_fwd(x):
+    return _cl(F.max_pool2d(x, 3, 2, 1))
+
+
+def maxpool_bwd(dy, x, y):
+    # recompute-style backward (no saved indices): route gradient to the arg-max positions
+    xf = x.detach().float().requires_grad_(True)
+    with torch.enable_grad():
+        yy = F.max_pool2d(xf, 3, 2, 1)
+    (dx,) = torch.autograd.grad(yy, xf, dy.float())
+    return _cl(dx.to(x.dtype))
+
+
+def head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale: float, n_valid: int,
+                 dw_out, db_out, accumulate: bool, need_dfeat: bool = True):
+    """global-avg-pool → FC → softmax cross-entropy, forward AND backward in one op.
+
+    feat [N,C,H,W]; fc_w [Kpad, C] (rows ≥ n_valid are padding and masked to −inf);
+    returns (loss_sum/N * loss_scale as 0-d fp32, correct count 0-d fp32, dfeat, logits[N,Kpad])."""
+    N, C, H, W = feat.shape
+    pooled = feat.float().mean(dim=(2, 3))
+    logits = pooled @ fc_w.float().t()
+    if fc_b is not None:
+        logits = logits + fc_b.float()
+    K = logits.shape[1]
+    if n_valid < K:
+        mask = torch.arange(K, device=logits.device) >= n_valid
+        logits = logits.masked_fill(mask, float("-inf"))
+    lse = torch.logsumexp(logits, dim=1)
+    picked = logits.gather(1, labels.view(-1, 1)).squeeze(1)
+    loss = (lse - picked).mean() * loss_scale
+    correct = (logits.argmax(dim=1) == labels).sum().float()
+    p = torch.softmax(logits, dim=1)
+    p = p.scatter_add(1, labels.view(-1, 1), -torch.ones(N, 1, device=p.device, dtype=p.dtype))
+    dlogits = p * (loss_scale / N)
+    dw = dlogits.t() @ pooled
+    if accumulate:
+        dw_out.add_(dw)
+        if db_out is not None:
+            db_out.add_(dlogits.sum(0))
+    else:
+        dw_out.copy_(dw)
+        if db_out is not None:
+            db_out.copy_(dlogits.sum(0))
+    dfeat = None
+    if need_dfeat:
+        dpooled = dlogits @ fc_w.float()
+        dfeat = _cl((dpooled / (H * W)).view(N, C, 1, 1).expand(N, C, H, W).to(feat.dtype))
+    return loss, correct, dfeat, logits
+
+
+def linear_fwd(x2d, w, b):
+    y = x2d.float() @ w.float().t()
+    if b is not None:
+        y = y + b.float()
+    return y
+
+
+def adam_step(master, grad, m, v, shadow, step_t, lr: float, b1: float, b2: float, eps: float,
+              grad_scale: float = 1.0):
+    """Flat fused Adam (torch.optim.Adam semantics, no weight decay / amsgrad).
+    ``step_t`` is a 1-element fp32/int tensor holding the step count (incremented here)."""
+    step_t += 1
+    t = float(step_t.item()) if step_t.device.type == "cpu" else step_t.float()
+    g = grad if grad_scale == 1.0 else grad * grad_scale
+    m.mul_(b1).add_(g, alpha=1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1 = 1 - b1 ** t
+    bc2 = 1 - b2 ** t
+    denom = (v / bc2).sqrt_().add_(eps)
+    master.sub_((m / bc1) / denom * lr)
+    if shadow is not None:
+        shadow.copy_(master)
+
+
+def grad_diff_sq(grad, prev):
+    """Σ (g_t − g_{t−1})², then prev ← g_t  (reference metric, data_parallel_train.py:132-145)."""
+    d = (grad - prev)
+    out = (d * d).sum()
+    prev.copy_(grad)
+    return out
+
+
+def stem_prepare(images, mean: float, std: float, dtype):
+    """uint8/fp32 NCHW images → normalised channels_last activations in the compute dtype."""
+    x = images.float()
+    if images.dtype == torch.uint8:
+        x = x / 255.0
+    x = (x - mean) / std
+    return _cl(x.to(dtype))

@@ -1,0 +1,158 @@
+"""Communication layer.
+
+Reference: ``torch.distributed`` ProcessGroupGloo over TCP loopback, WORLD group only, blocking
+calls only (K1-K12).  Here:
+
+* ``torch.distributed`` (NCCL on GPUs, gloo on CPU) is the bootstrap, the p2p transport for the
+  pipeline and the *measured baseline*;
+* gradient all-reduce on GPUs goes through :class:`PeerAllReduce` — hand-written sm_100a kernels
+  (csrc/comm.cu) that fuse the fp32→bf16 cast and the 1/W scale into a one-shot / two-shot
+  reduction over CUDA-IPC peer buffers, plus an NVLS (``multimem``) variant over a multicast
+  mapping; device-side flag barriers replace the reference's per-step host barrier (K4/K10).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def dist_ready() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def world() -> int:
+    return dist.get_world_size() if dist_ready() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist_ready() else 0
+
+
+# size thresholds (bytes of wire data) for algorithm selection; refined from measurements
+ONESHOT_MAX_BYTES = 1 << 20
+
+
+class GradAllReduce:
+    """In-place *averaging* all-reduce of a slice of the flat fp32 gradient buffer."""
+
+    name = "base"
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist_ready() else 1
+        self.rank = dist.get_rank(group) if dist_ready() else 0
+        self.bytes_per_call: List[int] = []
+
+    def allreduce_avg_(self, t: torch.Tensor) -> None:   # pragma: no cover - interface
+        raise NotImplementedError
+
+    def wire_bytes(self, numel: int) -> int:
+        return numel * 4
+
+
+class TorchDistAllReduce(GradAllReduce):
+    """NCCL / gloo all-reduce (the baseline path; also the CPU plumbing path)."""
+
+    name = "nccl"
+
+    def allreduce_avg_(self, t: torch.Tensor) -> None:
+        if self.world == 1:
+            return
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        t.div_(self.world)
+
+
+class PeerAllReduce(GradAllReduce):
+    """Fused cast/scale + peer-memory all-reduce (csrc/comm.cu).
+
+    ``algo``: oneshot | twoshot | nvls | auto.  ``wire``: bf16 (default, the north-star's fused
+    cast) or fp32 (bit-comparable with a fp32 NCCL all-reduce up to summation order)."""
+
+    name = "peer"
+
+    def __init__(self, max_numel: int, device, group=None, algo: str = "auto", wire: str = "bf16",
+                 max_blocks: int = 32):
+        super().__init__(group)
+        from ..ops import _ext
+        self.C = _ext.load(required=True)
+        self.device = torch.device(device)
+        self.algo, self.wire = algo, wire
+        self.max_numel = int(max_numel)
+        self.max_blocks = max_blocks
+        wire_bytes = 2 if wire == "bf16" else 4
+        self.handle = self.C.PeerComm(self.rank, self.world, self.device.index or 0,
+                                      self.max_numel * wire_bytes, max_blocks)
+        self.has_nvls = False
+        if self.world > 1:
+            mine = torch.tensor(list(self.handle.export_handles()), dtype=torch.uint8)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            # handles are opaque host bytes: exchange through a CPU-side object gather
+            objs: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(objs, bytes(mine.tolist()), group=group)
+            self.handle.import_handles([bytes(o) for o in objs])
+            if algo in ("nvls", "auto"):
+                self.has_nvls = self._try_setup_nvls(group)
+            dist.barrier(group=group)
+        if algo == "nvls" and not self.has_nvls and self.world > 1:
+            raise RuntimeError("NVLS multicast is not available on this system")
+
+    def _try_setup_nvls(self, group) -> bool:
+        """Multicast (NVLS) mapping via torch symmetric memory; kernels are ours."""
+        if os.environ.get("HZ_DISABLE_NVLS", "0") == "1":
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            wire_bytes = 2 if self.wire == "bf16" else 4
+            nbytes = 2 * self.max_numel * wire_bytes
+            buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+            hdl = symm.rendezvous(buf, group=group if group is not None else dist.group.WORLD)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            ok = torch.tensor([1 if mc else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                return False
+            self._symm_buf, self._symm_hdl = buf, hdl
+            self.handle.set_multicast(mc, buf.data_ptr(), nbytes)
+            return True
+        except Exception as e:  # noqa: BLE001
+            if os.environ.get("HZ_DEBUG"):
+                print(f"[comm] NVLS setup failed: {e!r}")
+            return False
+
+    def pick(self, numel: int) -> str:
+        if self.algo != "auto":
+            return self.algo
+        wb = numel * (2 if self.wire == "bf16" else 4)
+        if self.world <= 2 or wb <= ONESHOT_MAX_BYTES:
+            return "oneshot"
+        return "nvls" if self.has_nvls else "twoshot"
+
+    def wire_bytes(self, numel: int) -> int:
+        return numel * (2 if self.wire == "bf16" else 4)
+
+    def allreduce_avg_(self, t: torch.Tensor, algo: Optional[str] = None) -> None:
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_numel
+        a = algo or self.pick(t.numel())
+        self.handle.allreduce(t, a, self.wire == "bf16", 1.0 / self.world)
+
+    def barrier(self) -> None:
+        self.handle.barrier()
+
+
+def make_grad_allreduce(kind: str, max_numel: int, device, group=None, wire: str = "bf16") -> GradAllReduce:
+    dev = torch.device(device)
+    if kind == "auto":
+        kind = "peer-auto" if dev.type == "cuda" else "nccl"
+        try:
+            from ..ops import _ext
+            if dev.type == "cuda" and _ext.load(required=False) is None:
+                kind = "nccl"
+        except Exception:
+            kind = "nccl"
+    if kind == "nccl" or dev.type != "cuda":
+        return TorchDistAllReduce(group)
+    algo = {"peer-auto": "auto"}.get(kind, kind)
+    return PeerAllReduce(max_numel, dev, group, algo=algo, wire=wire)

@@ -1,0 +1,166 @@
+"""Runtime pieces shared by the three trainers: device/dtype/backend resolution, the CUDA-graph
+captured step, device-side metric accumulators, heartbeat + fault-injection hooks."""
+from __future__ import annotations
+
+import os
+import time
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..config import TrainConfig
+
+
+@dataclass
+class Runtime:
+    rank: int
+    world: int
+    device: torch.device
+    dtype: torch.dtype
+    backend: str           # op backend actually in use
+    comm_backend: str
+
+
+def setup_runtime(rank: int, world: int, cfg: TrainConfig, device: str) -> Runtime:
+    from ..launch import init_distributed
+    comm_backend = init_distributed(rank, world, device, cfg.comm)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device == "cuda" else torch.device("cpu")
+    dtype = {"auto": torch.bfloat16 if dev.type == "cuda" else torch.float32,
+             "bf16": torch.bfloat16, "fp32": torch.float32}[cfg.dtype]
+    backend = cfg.backend
+    if backend == "auto":
+        backend = "native" if (dev.type == "cuda" and ops.native_available()) else "torch"
+    if backend == "native" and dev.type != "cuda":
+        raise RuntimeError("--backend native requires a CUDA device")
+    ops.set_backend(backend)
+    if dev.type == "cpu":
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
+    torch.manual_seed(cfg.seed)
+    return Runtime(rank, world, dev, dtype, backend, comm_backend)
+
+
+class DeviceStats:
+    """On-device accumulators: no ``.item()`` in the step loop (the reference syncs three times per
+    step: data_parallel_train.py:126,130,140)."""
+
+    N = 6   # loss_sum, correct, seen, grad_div_sum, grad_div_n, steps
+
+    def __init__(self, device):
+        self.buf = torch.zeros(self.N, dtype=torch.float32, device=device)
+        self.has_prev = torch.zeros((), dtype=torch.float32, device=device)
+
+    def add_step(self, loss, correct, batch: int) -> None:
+        self.buf[0] += loss.detach().float()
+        self.buf[1] += correct.detach().float()
+        self.buf[2] += batch
+        self.buf[5] += 1
+
+    def add_grad_div(self, diff_sq) -> None:
+        self.buf[3] += diff_sq.sqrt() * self.has_prev
+        self.buf[4] += self.has_prev
+        self.has_prev.fill_(1.0)
+
+    def read_and_reset(self, keep_div: bool = True) -> Dict[str, float]:
+        v = self.buf.tolist()
+        out = {"loss_sum": v[0], "correct": v[1], "seen": v[2], "grad_div_sum": v[3],
+               "grad_div_n": v[4], "steps": v[5]}
+        self.buf[:3].zero_()
+        self.buf[5].zero_()
+        if not keep_div:
+            self.buf[3:5].zero_()
+        return out
+
+
+class GraphedStep:
+    """Runs ``fn(images, labels)`` eagerly for ``warmup`` calls, then captures it into a CUDA graph
+    (static input buffers) and replays.  Falls back to eager for off-size batches / CPU."""
+
+    def __init__(self, fn: Callable, device, enabled: bool, warmup: int = 3):
+        self.fn, self.device = fn, torch.device(device)
+        self.enabled = enabled and self.device.type == "cuda"
+        self.warmup = warmup
+        self.calls = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.static_x = self.static_y = None
+        self.shape = None
+        self.capture_error: Optional[str] = None
+
+    def __call__(self, x, y):
+        self.calls += 1
+        if not self.enabled:
+            return self.fn(x, y)
+        if self.graph is not None and tuple(x.shape) == self.shape:
+            self.static_x.copy_(x, non_blocking=True)
+            self.static_y.copy_(y, non_blocking=True)
+            self.graph.replay()
+            return None
+        if self.graph is None and self.calls > self.warmup and self.capture_error is None:
+            try:
+                self._capture(x, y)
+                self.graph.replay()
+                return None
+            except Exception as e:  # noqa: BLE001
+                self.capture_error = repr(e)
+                self.graph = None
+                self.enabled = False
+                if os.environ.get("HZ_STRICT_GRAPH", "0") == "1":
+                    raise
+                print(f"[graph] capture failed, staying eager: {e!r}", flush=True)
+                torch.cuda.synchronize()
+        return self.fn(x, y)
+
+    def _capture(self, x, y):
+        self.static_x = x.clone()
+        self.static_y = y.clone()
+        self.shape = tuple(x.shape)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.fn(self.static_x, self.static_y)
+        self.graph = g
+
+
+class Heartbeat:
+    """Per-rank heartbeat file (failure detection aid; the reference has only timeouts)."""
+
+    def __init__(self, directory: Optional[str], rank: int):
+        self.path = os.path.join(directory, f"heartbeat_rank{rank}.txt") if directory else None
+        if self.path:
+            os.makedirs(directory, exist_ok=True)
+
+    def beat(self, epoch: int, step: int) -> None:
+        if self.path:
+            with open(self.path, "w") as fh:
+                fh.write(f"{time.time():.3f} epoch={epoch} step={step}\n")
+
+
+class FaultInjector:
+    """``--inject_fault rank:step`` — that rank dies at that global step (launcher tear-down test)."""
+
+    def __init__(self, spec: Optional[str], rank: int):
+        self.step = None
+        if spec:
+            r, s = spec.split(":")
+            if int(r) == rank:
+                self.step = int(s)
+
+    def maybe_fail(self, global_step: int) -> None:
+        if self.step is not None and global_step >= self.step:
+            raise RuntimeError(f"injected fault at global step {global_step}")
+
+
+def gpu_mem_mb(device) -> float:
+    if torch.device(device).type != "cuda":
+        return 0.0
+    return torch.cuda.max_memory_allocated(device) / (1 << 20)
+
+
+def allreduce_max_scalar(x: float, device) -> float:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device if torch.device(device).type == "cuda" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

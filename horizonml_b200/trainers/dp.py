@@ -1,0 +1,192 @@
+"""Data-parallel trainer.
+
+Reference call stack: data_parallel_train.py ``worker`` → ``train`` (:76-189, :192-230): per step
+``zero_grad → model(images) → CE → backward (DDP bucket all-reduce) → Adam.step → loss.item() →
+argmax accuracy → grad clone+cat divergence → dist.barrier()``.
+
+B200 step (``DPEngine.step``): one CUDA-graph replay containing
+``stem-im2col(normalise+cast) → 20× [tcgen05 conv(+BN sums) → BN/ReLU/residual] → fused
+FC+CE+accuracy(+its own backward) → 20× [BN-bwd reduce/apply → wgrad (into the bucket) → dgrad] →
+per-bucket fused cast/scale peer all-reduce on the comm stream (overlapped) → fused Adam (+bf16
+shadow refresh) → grad-divergence``; loss/accuracy accumulate on the device and are read once per
+epoch.  No host barrier per step (flag ``--step_barrier`` restores the reference behaviour).
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import checkpoint, ops
+from ..config import TrainConfig
+from ..data import BatchLoader, ShardedSampler, build_dataset
+from ..metrics import EpochRecorder, write_summary
+from ..models.flat import FlatAdam, FlatParams
+from ..models.resnet import resnet18
+from ..parallel.comm import make_grad_allreduce
+from ..parallel.dp import GradReducer
+from .common import (DeviceStats, FaultInjector, GraphedStep, Heartbeat, Runtime, allreduce_max_scalar,
+                     gpu_mem_mb, setup_runtime)
+
+
+def build_model(cfg: TrainConfig, device, class_pad_to: int = 1):
+    if cfg.model == "mobilenet":
+        from ..models.mobilenet import mobilenet_v2
+        return mobilenet_v2(cfg.num_classes, seed=cfg.seed).to(device)
+    return resnet18(cfg.num_classes, seed=cfg.seed, class_pad_to=class_pad_to).to(device)
+
+
+class DPEngine:
+    """Public data-parallel training engine: ``engine.step(images_u8_nhwc, labels)``.
+
+    ``images`` uint8 NHWC on CUDA (normalisation fused into the stem) or normalised fp32 on CPU."""
+
+    def __init__(self, cfg: TrainConfig, rt: Runtime):
+        self.cfg, self.rt = cfg, rt
+        dev = rt.device
+        self.model = build_model(cfg, dev)
+        self.model.train()
+        self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype, cfg.bucket_mb)
+        if rt.world > 1:   # K1: make replicas identical (same seed already does; belt and braces)
+            dist.broadcast(self.flat.master, src=0)
+            for b in self.model.buffers():
+                if b.dtype.is_floating_point:
+                    dist.broadcast(b, src=0)
+            self.flat.sync_shadow()
+        self.opt = FlatAdam(self.flat, lr=cfg.lr)
+        kind = cfg.allreduce
+        self.ar = make_grad_allreduce(kind, self.flat.total, dev) if rt.world > 1 else None
+        self.reducer = GradReducer(self.flat, self.ar, cfg.overlap) if self.ar is not None else None
+        self.stats = DeviceStats(dev)
+        self.prev_grad = torch.zeros_like(self.flat.grad) if cfg.grad_divergence else None
+        self._graphed = GraphedStep(self._step_impl, dev, cfg.cuda_graph)
+        self.global_step = 0
+
+    # one full training step; everything inside is stream-ordered and graph-capturable
+    def _step_impl(self, images, labels) -> None:
+        cfg = self.cfg
+        x = images
+        if x.dtype == torch.uint8:
+            x = ops.stem_prepare(x.permute(0, 3, 1, 2), dtype=self.rt.dtype)
+        self.flat.begin_step()
+        if self.reducer is not None:
+            self.reducer.begin_step()
+        loss, correct = self.model.forward_loss(x, labels)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt.step()
+        self.stats.add_step(loss, correct, labels.shape[0])
+        if self.prev_grad is not None:
+            self.stats.add_grad_div(ops.grad_diff_sq(self.flat.grad, self.prev_grad))
+
+    def step(self, images, labels) -> None:
+        self._graphed(images, labels)
+        self.global_step += 1
+
+    def allreduce_bytes_per_step(self) -> int:
+        if self.reducer is None:
+            return 0
+        return sum(self.ar.wire_bytes(b.end - b.start) for b in self.flat.buckets)
+
+
+def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
+    """Per-rank worker (the reference's ``worker`` + ``train``)."""
+    rt = setup_runtime(rank, world, cfg, device)
+    logs_dir = cfg.resolved_logs_dir()
+    images, labels = build_dataset(cfg.sample_size, cfg.synthetic, cfg.data_dir, cfg.seed)
+    if rank == 0 and not cfg.quiet:
+        print("Worker 0 downloaded the dataset." if not cfg.synthetic else
+              "Worker 0 generated the synthetic dataset.", flush=True)
+    sampler = ShardedSampler(len(labels), world, rank, shuffle=True, seed=cfg.seed)
+    loader = BatchLoader(images, labels, cfg.batch_size, rt.device, sampler)
+    eng = DPEngine(cfg, rt)
+    rec = EpochRecorder("data", rank, logs_dir, cfg.sample_size)
+    hb = Heartbeat(cfg.heartbeat_dir, rank)
+    fault = FaultInjector(cfg.inject_fault, rank)
+    start_epoch = 0
+    if cfg.resume:
+        payload = checkpoint.load(cfg.resume, "dp", eng.model, eng.opt)
+        if payload is not None:
+            start_epoch = payload["epoch"]
+            eng.global_step = payload["global_step"]
+    if not cfg.quiet:
+        print(f"Worker {rank} is starting training...", flush=True)
+    cuda = rt.device.type == "cuda"
+    df = None
+    for epoch in range(start_epoch, cfg.epochs):
+        sampler.set_epoch(epoch)
+        t_epoch = time.time()
+        t0 = time.time()
+        if world > 1:
+            dist.barrier()
+        rec.total_idle += time.time() - t0
+        step_times: List[float] = []
+        ev_start = ev_end = None
+        if cuda:
+            torch.cuda.reset_peak_memory_stats(rt.device)
+            ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev_start.record()
+        nsteps = 0
+        for bi, (x, y) in enumerate(loader):
+            if cfg.max_steps and bi >= cfg.max_steps:
+                break
+            ts = time.time()
+            rec.host.sample()
+            fault.maybe_fail(eng.global_step)
+            eng.step(x, y)
+            if cfg.step_barrier and world > 1:
+                ti = time.time()
+                if cuda:
+                    torch.cuda.synchronize()
+                dist.barrier()
+                rec.total_idle += time.time() - ti
+            step_times.append(time.time() - ts)
+            nsteps += 1
+            if bi % 50 == 0:
+                hb.beat(epoch, eng.global_step)
+        if cuda:
+            ev_end.record()
+            torch.cuda.synchronize()
+            dev_s = ev_start.elapsed_time(ev_end) / 1e3
+        else:
+            dev_s = time.time() - t_epoch
+        s = eng.stats.read_and_reset()
+        epoch_time = time.time() - t_epoch
+        steps = max(int(s["steps"]), 1)
+        loss = s["loss_sum"] / steps
+        acc = 100.0 * s["correct"] / max(s["seen"], 1)
+        if s["grad_div_n"] > 0:
+            rec.grad_divs = [s["grad_div_sum"] / s["grad_div_n"]]
+        # reference split (Q8): compute = forward share, comm = backward+optimizer share of device time
+        rec.total_compute += dev_s * (1.0 / 3.0)
+        rec.total_comm += dev_s * (2.0 / 3.0)
+        dev_s_max = allreduce_max_scalar(dev_s, rt.device)
+        seen_all = s["seen"] * world
+        ar_bytes = eng.allreduce_bytes_per_step()
+        ext = {"images_per_sec": seen_all / dev_s_max if dev_s_max > 0 else 0,
+               "gpu_mem_MB": gpu_mem_mb(rt.device), "steps": nsteps,
+               "nvlink_GBps": (ar_bytes * nsteps / dev_s_max / 1e9) if dev_s_max > 0 else 0}
+        if cuda:
+            step_times = [dev_s / max(nsteps, 1)] * nsteps
+        rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times, ext=ext)
+        if rank == 0 and not cfg.quiet:
+            print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "
+                  f"Time: {epoch_time:.2f}s", flush=True)
+        if cfg.save_dir and rank == 0 and (
+                (cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
+            checkpoint.save(cfg.save_dir, "dp", eng.model, eng.opt, epoch + 1, eng.global_step)
+        if world > 1:
+            dist.barrier()
+    df = rec.frame()
+    if rank == 0:
+        write_summary(logs_dir, f"summary_{cfg.sample_size}.json", {
+            "strategy": "data", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
+            "comm": rt.comm_backend, "allreduce": getattr(eng.ar, "name", None),
+            "graph": eng._graphed.graph is not None, "graph_error": eng._graphed.capture_error,
+            "final": rec.rows[-1] if rec.rows else None})
+    from ..launch import shutdown_distributed
+    shutdown_distributed()
+    return df
