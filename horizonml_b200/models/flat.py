@@ -74,6 +74,7 @@ class FlatParams:
             if self.shadow is not None:
                 p.shadow = view(self.shadow)
         self.sync_shadow()
+        self._attach_autograd_bridge()
         self.buckets = self._make_buckets(bucket_cap_mb, first_bucket_mb)
         self._bucket_of: Dict[int, int] = {}
         for b in self.buckets:
@@ -95,6 +96,27 @@ class FlatParams:
                 start, names = end, []
                 cap = int(cap_mb * (1 << 20) / 4)
         return buckets
+
+    def _attach_autograd_bridge(self) -> None:
+        """Parameters used by plain autograd ops (library models, e.g. MobileNetV2) receive ``.grad``;
+        bridge it into ``main_grad`` so the reducer/optimizer see one storage."""
+        def bridge(p):
+            g = p.grad
+            if g is None:
+                return
+            if getattr(p, "_acc", False):
+                p.main_grad.add_(g.to(torch.float32))
+            else:
+                p.main_grad.copy_(g.to(torch.float32))
+            p.grad = None
+            p._acc = True
+            hook = getattr(p, "_ready_hook", None)
+            if hook is not None:
+                hook(p)
+
+        for p in self.params:
+            if p.requires_grad:
+                p.register_post_accumulate_grad_hook(bridge)
 
     def bucket_index(self, p) -> int:
         return self._bucket_of[id(p)]

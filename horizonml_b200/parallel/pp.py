@@ -1,0 +1,177 @@
+"""Layer (pipeline) parallelism: real 1F1B.
+
+Reference (layer_model_parallel_train.py:172-273): a *forward-only* blocking chain — each stage
+``recv``s a 32-byte shape header + the activation into a fresh leaf tensor, runs its segment and
+``send``s on; only the last stage has a loss/optimizer, no gradient ever travels upstream (Q1).
+
+Here every stage trains: activations go down and gradients come back over ``torch.distributed``
+p2p (NCCL on GPUs — the north-star keeps PP traffic on NCCL p2p; gloo on CPU), shapes are static
+(no header), payloads are in the compute dtype (bf16), and the batch is cut into micro-batches
+scheduled **1F1B** so a stage's p2p for micro-batch *i* overlaps its neighbours' compute.  Sends and
+receives that face each other are issued as one ``batch_isend_irecv`` group (one NCCL group
+kernel), which is what makes the steady state deadlock-free.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def one_f_one_b(stage: int, num_stages: int, num_micro: int) -> List[Tuple[str, int]]:
+    """The 1F1B action list for ``stage``: [('F', i) | ('B', i)].  Used for tests / tracing;
+    ``PipelineRunner`` executes the same order."""
+    warm = min(num_stages - stage - 1, num_micro)
+    acts: List[Tuple[str, int]] = [("F", i) for i in range(warm)]
+    f, b = warm, 0
+    for _ in range(num_micro - warm):
+        acts.append(("F", f)); f += 1
+        acts.append(("B", b)); b += 1
+    while b < num_micro:
+        acts.append(("B", b)); b += 1
+    return acts
+
+
+class P2P:
+    """Static-shape activation/gradient exchange with the neighbouring stages."""
+
+    def __init__(self, stage: int, num_stages: int, group=None):
+        self.stage, self.S, self.group = stage, num_stages, group
+        self.prev = stage - 1 if stage > 0 else None
+        self.next = stage + 1 if stage < num_stages - 1 else None
+        self.bytes_sent = 0
+        self._keep: List = []
+
+    def _run(self, ops_: List[dist.P2POp]):
+        if not ops_:
+            return
+        reqs = dist.batch_isend_irecv(ops_)
+        for r in reqs:
+            r.wait()
+
+    def _send(self, t, peer):
+        self.bytes_sent += t.numel() * t.element_size()
+        self._keep.append(t)
+        return dist.P2POp(dist.isend, t, peer, self.group)
+
+    def _recv(self, t, peer):
+        return dist.P2POp(dist.irecv, t, peer, self.group)
+
+    def exchange(self, send_fwd=None, send_bwd=None, recv_fwd_like=None, recv_bwd_like=None):
+        """Issue up to four p2p ops as ONE group. ``*_like`` = (shape, dtype, device) to receive."""
+        ops_: List[dist.P2POp] = []
+        got_f = got_b = None
+        # payloads travel in their physical NHWC order (a dense contiguous tensor for c10d)
+        def phys(t):
+            return t.detach().contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+
+        def alloc(like):
+            (n, c, h, w), dtype, dev = like
+            return torch.empty((n, h, w, c), dtype=dtype, device=dev)
+
+        if send_fwd is not None and self.next is not None:
+            ops_.append(self._send(phys(send_fwd), self.next))
+        if send_bwd is not None and self.prev is not None:
+            ops_.append(self._send(phys(send_bwd), self.prev))
+        if recv_fwd_like is not None and self.prev is not None:
+            got_f = alloc(recv_fwd_like)
+            ops_.append(self._recv(got_f, self.prev))
+        if recv_bwd_like is not None and self.next is not None:
+            got_b = alloc(recv_bwd_like)
+            ops_.append(self._recv(got_b, self.next))
+        self._run(ops_)
+        return (got_f.permute(0, 3, 1, 2) if got_f is not None else None,
+                got_b.permute(0, 3, 1, 2) if got_b is not None else None)
+
+    def end_step(self):
+        self._keep.clear()
+        b, self.bytes_sent = self.bytes_sent, 0
+        return b
+
+
+class PipelineRunner:
+    """Executes one optimizer step's worth of micro-batches on this stage with the 1F1B order.
+
+    ``fwd_fn(x_or_images, mb_index) -> out`` (for the last stage: returns (loss, correct));
+    stage boundaries are tensors of ``in_shape(mb_size)`` / ``out_shape(mb_size)``."""
+
+    def __init__(self, stage: int, num_stages: int, fwd_fn: Callable, in_shape: Callable,
+                 out_shape: Callable, dtype, device, group=None):
+        self.stage, self.S = stage, num_stages
+        self.first, self.last = stage == 0, stage == num_stages - 1
+        self.fwd_fn, self.in_shape, self.out_shape = fwd_fn, in_shape, out_shape
+        self.dtype, self.device = dtype, device
+        self.p2p = P2P(stage, num_stages, group)
+        self.trace: List[Tuple[str, int]] = []
+
+    def _like_in(self, n):
+        return None if self.first else (self.in_shape(n), self.dtype, self.device)
+
+    def _like_out(self, n):
+        return None if self.last else (self.out_shape(n), self.dtype, self.device)
+
+    def run(self, mb_sizes: Sequence[int], first_inputs: Optional[Sequence] = None):
+        """Returns (sum of micro losses, sum of correct) on the last stage, else (None, None)."""
+        M = len(mb_sizes)
+        warm = min(self.S - self.stage - 1, M)
+        remaining = M - warm
+        inputs: List = []
+        outputs: List = []
+        self.trace = []
+        loss_sum = correct_sum = None
+        f_idx = b_idx = 0
+
+        def do_fwd(x, i):
+            nonlocal loss_sum, correct_sum
+            if not self.first:
+                x.requires_grad_(True)
+            out = self.fwd_fn(x if not self.first else first_inputs[i], i)
+            inputs.append(x)
+            outputs.append(out)
+            self.trace.append(("F", i))
+            if self.last:
+                loss, correct = out
+                loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
+                correct_sum = correct if correct_sum is None else correct_sum + correct
+            return out
+
+        def do_bwd(dout, i):
+            x, out = inputs[i], outputs[i]
+            if self.last:
+                out[0].backward()
+            else:
+                torch.autograd.backward(out, dout)
+            self.trace.append(("B", i))
+            inputs[i] = outputs[i] = None
+            return None if self.first else x.grad
+
+        # ---- warm-up forwards
+        for _ in range(warm):
+            x, _ = self.p2p.exchange(recv_fwd_like=self._like_in(mb_sizes[f_idx]))
+            out = do_fwd(x, f_idx)
+            self.p2p.exchange(send_fwd=None if self.last else out)
+            f_idx += 1
+        x = None
+        if remaining > 0:
+            x, _ = self.p2p.exchange(recv_fwd_like=self._like_in(mb_sizes[f_idx]))
+        # ---- steady state 1F1B
+        for k in range(remaining):
+            out = do_fwd(x, f_idx)
+            f_idx += 1
+            _, dout = self.p2p.exchange(send_fwd=None if self.last else out,
+                                        recv_bwd_like=self._like_out(mb_sizes[b_idx]))
+            dx = do_bwd(dout, b_idx)
+            b_idx += 1
+            if k == remaining - 1:
+                self.p2p.exchange(send_bwd=dx)
+                x = None
+            else:
+                x, _ = self.p2p.exchange(send_bwd=dx, recv_fwd_like=self._like_in(mb_sizes[f_idx]))
+        # ---- cool-down backwards
+        while b_idx < M:
+            _, dout = self.p2p.exchange(recv_bwd_like=self._like_out(mb_sizes[b_idx]))
+            dx = do_bwd(dout, b_idx)
+            self.p2p.exchange(send_bwd=dx)
+            b_idx += 1
+        return loss_sum, correct_sum

@@ -1,0 +1,198 @@
+"""Tensor parallelism.
+
+Reference (tensor_parallel_train.py:27-105): the backbone is replicated, only the 512→10 classifier
+is column-split (``out_features // world_size`` — truncating, Q5), its shards are "all-gathered" by
+``ws`` broadcasts on non-contiguous views (wrong for most rows, Q3), and *every* parameter's gradient
+— sharded ones included — is all-reduced and divided by ``ws`` (Q4).
+
+Here:
+* **classifier**: column-parallel with classes padded to a multiple of ``ws`` (pad logits masked to
+  −inf), logits all-gathered, exact backward (dX = Σ_r dY_r·W_r through an all-reduce);
+* **layer3 / layer4 BasicBlocks** (``--no_tp_conv_split`` disables): conv1 is *column*-parallel
+  (output channels split, BN1 sharded with it), conv2 is *row*-parallel (input channels split, partial
+  sums reduced before the replicated BN2) — the Megatron pattern transplanted to convs: one
+  reduction per block forward (GEMM→reduce) and one per block backward (dgrad→reduce);
+* replicated parameters still get their gradients averaged (the reference's K9 traffic, bucketed
+  instead of 62 blocking calls) so replicas cannot drift; sharded parameters are never averaged.
+
+The reduction points are ``TPComm`` methods; on GPUs they map to the fused sm_100a kernels
+(GEMM+reduce-scatter / all-gather+GEMM over peer memory, csrc/tp_fused.cu) when shapes allow and to
+NCCL otherwise.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .. import ops
+from ..models.resnet import BNP, BasicBlock, ConvW, ResNet18, _cba
+from ..ops.functional import grad_target, grad_written
+
+
+class TPComm:
+    """Reduction / gather points of the tensor-parallel group."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.bytes = 0
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return t
+        self.bytes += t.numel() * t.element_size()
+        if t.dim() == 4:     # c10d wants a dense tensor: reduce the physical NHWC buffer
+            phys = t.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
+            dist.all_reduce(phys, group=self.group)
+            return phys.permute(0, 3, 1, 2)
+        t = t.contiguous()
+        dist.all_reduce(t, group=self.group)
+        return t
+
+    def all_gather_cols(self, local: torch.Tensor) -> torch.Tensor:
+        """[N, k] per rank → [N, k·ws] (rank-major column blocks)."""
+        if self.world == 1:
+            return local
+        self.bytes += local.numel() * local.element_size() * (self.world - 1)
+        parts = [torch.empty_like(local) for _ in range(self.world)]
+        dist.all_gather(parts, local.contiguous(), group=self.group)
+        return torch.cat(parts, dim=1)
+
+    def take_bytes(self) -> int:
+        b, self.bytes = self.bytes, 0
+        return b
+
+
+def padded_classes(num_classes: int, ws: int) -> int:
+    return int(math.ceil(num_classes / ws) * ws)
+
+
+def shard_range(n: int, ws: int, rank: int) -> Tuple[int, int]:
+    assert n % ws == 0, f"{n} not divisible by tensor-parallel size {ws}"
+    k = n // ws
+    return rank * k, (rank + 1) * k
+
+
+class _TPHeadLoss(torch.autograd.Function):
+    """avg-pool → column-parallel FC → all-gather(logits) → softmax-CE, with exact backward."""
+
+    @staticmethod
+    def forward(ctx, feat, w_local, b_local, labels, comm: TPComm, n_valid: int, loss_scale: float):
+        N, C, H, W = feat.shape
+        pooled = feat.float().mean(dim=(2, 3))
+        wl = w_local.detach().float()
+        local = pooled @ wl.t() + b_local.detach().float()
+        logits = comm.all_gather_cols(local)
+        K = logits.shape[1]
+        if n_valid < K:
+            logits = logits.masked_fill(torch.arange(K, device=logits.device) >= n_valid, float("-inf"))
+        lse = torch.logsumexp(logits, dim=1)
+        loss = (lse - logits.gather(1, labels.view(-1, 1)).squeeze(1)).mean() * loss_scale
+        correct = (logits.argmax(1) == labels).sum().float()
+        p = torch.softmax(logits, dim=1)
+        p = p.scatter_add(1, labels.view(-1, 1), -torch.ones(N, 1, device=p.device, dtype=p.dtype))
+        dlogits = p * (loss_scale / N)
+        k = wl.shape[0]
+        dl = dlogits[:, comm.rank * k:(comm.rank + 1) * k]
+        tw, accw = grad_target(w_local)
+        tb, accb = grad_target(b_local)
+        dw, db = dl.t() @ pooled, dl.sum(0)
+        tw.add_(dw) if accw else tw.copy_(dw)
+        tb.add_(db) if accb else tb.copy_(db)
+        dfeat = None
+        if feat.requires_grad:
+            dpooled = comm.all_reduce_sum(dl @ wl)        # Σ_r dY_r · W_r
+            dfeat = (dpooled / (H * W)).view(N, C, 1, 1).expand(N, C, H, W).to(feat.dtype)
+            dfeat = dfeat.contiguous(memory_format=torch.channels_last)
+        ctx.params = (w_local, b_local)
+        ctx.save_for_backward(dfeat if dfeat is not None else torch.empty(0))
+        ctx.has = dfeat is not None
+        ctx.mark_non_differentiable(correct)
+        return loss, correct
+
+    @staticmethod
+    def backward(ctx, dloss, _dc):
+        for p in ctx.params:
+            grad_written(p)
+        (dfeat,) = ctx.saved_tensors
+        return (dfeat if ctx.has else None), None, None, None, None, None, None
+
+
+class TPBasicBlock(nn.Module):
+    """BasicBlock with conv1 column-parallel and conv2 row-parallel (see module docstring)."""
+
+    def __init__(self, dense: BasicBlock, comm: TPComm):
+        super().__init__()
+        ws, r = comm.world, comm.rank
+        cout, cin = dense.conv1.cout, dense.conv1.cin
+        lo, hi = shard_range(cout, ws, r)
+        self.comm = comm
+        self.conv1 = ConvW(cin, hi - lo, 3, dense.conv1.stride, 1)
+        self.bn1 = BNP(hi - lo)
+        self.conv2 = ConvW(hi - lo, cout, 3, 1, 1)
+        self.bn2 = BNP(cout)
+        with torch.no_grad():
+            self.conv1.weight.copy_(dense.conv1.weight[lo:hi])
+            self.bn1.weight.copy_(dense.bn1.weight[lo:hi]); self.bn1.bias.copy_(dense.bn1.bias[lo:hi])
+            self.conv2.weight.copy_(dense.conv2.weight[:, lo:hi])
+            self.bn2.weight.copy_(dense.bn2.weight); self.bn2.bias.copy_(dense.bn2.bias)
+        self.downsample = dense.downsample
+        for p in (self.conv1.weight, self.bn1.weight, self.bn1.bias, self.conv2.weight):
+            p.tp_sharded = True
+
+    def forward(self, x):
+        t = self.training
+        idt = x
+        if self.downsample is not None:
+            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t)
+        c1, b1, c2, b2 = self.conv1, self.bn1, self.conv2, self.bn2
+        y = ops.conv_bn_act(x, c1.weight, b1.weight, b1.bias, b1.running_mean, b1.running_var,
+                            stride=c1.stride, pad=1, relu=True, training=t,
+                            post_dgrad=self.comm.all_reduce_sum)
+        return ops.conv_bn_act(y, c2.weight, b2.weight, b2.bias, b2.running_mean, b2.running_var,
+                               stride=1, pad=1, relu=True, residual=idt, training=t,
+                               post_conv=self.comm.all_reduce_sum)
+
+
+class TensorParallelResNet(nn.Module):
+    """ResNet-18 with a column-parallel classifier and (optionally) channel-parallel layer3/4."""
+
+    def __init__(self, dense: ResNet18, comm: TPComm, conv_split: bool = True):
+        super().__init__()
+        self.comm, self.num_classes = comm, dense.num_classes
+        ws, r = comm.world, comm.rank
+        self.backbone = dense
+        self.conv_split = conv_split and ws > 1
+        if self.conv_split:
+            for lname in ("layer3", "layer4"):
+                layer = getattr(dense, lname)
+                if layer[0].conv1.cout % ws == 0:
+                    setattr(dense, lname, nn.Sequential(*[TPBasicBlock(b, comm) for b in layer]))
+        kpad = padded_classes(dense.num_classes, ws)
+        full_w = torch.zeros(kpad, 512)
+        full_b = torch.zeros(kpad)
+        with torch.no_grad():
+            full_w[: dense.num_classes] = dense.fc.weight[: dense.num_classes]
+            full_b[: dense.num_classes] = dense.fc.bias[: dense.num_classes]
+        lo, hi = shard_range(kpad, ws, r)
+        self.fc_weight = nn.Parameter(full_w[lo:hi].clone())
+        self.fc_bias = nn.Parameter(full_b[lo:hi].clone())
+        self.fc_weight.tp_sharded = True
+        self.fc_bias.tp_sharded = True
+        dense.fc = nn.Identity()           # the dense classifier is replaced by the sharded one
+
+    def forward_loss(self, x, labels, loss_scale: float = 1.0):
+        f = self.backbone.features(x)
+        return _TPHeadLoss.apply(f, self.fc_weight, self.fc_bias, labels, self.comm,
+                                 self.num_classes, float(loss_scale))
+
+    def split_params(self):
+        rep, shd = [], []
+        for n, p in self.named_parameters():
+            (shd if getattr(p, "tp_sharded", False) else rep).append((n, p))
+        return rep, shd

@@ -1,0 +1,181 @@
+"""Layer / pipeline-parallel trainer (reference: layer_model_parallel_train.py:134-334).
+
+Each rank owns a contiguous chunk of the five atomic blocks (``partition_blocks`` — the reference's
+``SplitResNet`` rule), its own flat parameter store and its own fused Adam.  Per optimizer step the
+batch is split into ``--microbatches`` micro-batches run 1F1B (``parallel.pp.PipelineRunner``):
+activations down, gradients up, over NCCL p2p.  Reference CSV conventions are kept: only the last
+stage reports loss/accuracy/grad_divergence (others write 0, layer_…:304-317), ``avg_bandwidth`` is
+bytes sent per step, ``comm_time`` is time spent in p2p (blocking share).
+"""
+from __future__ import annotations
+
+import time
+from typing import List
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import checkpoint, ops
+from ..config import TrainConfig
+from ..data import BatchLoader, build_dataset
+from ..metrics import EpochRecorder, write_summary
+from ..models.flat import FlatAdam, FlatParams
+from ..models.partition import boundary_shape, partition_blocks
+from ..models.resnet import resnet18
+from ..parallel.pp import PipelineRunner
+from .common import (DeviceStats, FaultInjector, Heartbeat, Runtime, allreduce_max_scalar, gpu_mem_mb,
+                     setup_runtime)
+
+
+class PPEngine:
+    def __init__(self, cfg: TrainConfig, rt: Runtime):
+        self.cfg, self.rt = cfg, rt
+        S, s = rt.world, rt.rank
+        self.first_blk, self.last_blk = partition_blocks(S)[s]
+        self.is_first, self.is_last = s == 0, s == S - 1
+        full = resnet18(cfg.num_classes, seed=cfg.seed)     # identical init on every stage (seeded)
+        self.model = full.to(rt.device)
+        self.model.train()
+        names = set()
+        groups = self.model.block_param_names()
+        for b in range(self.first_blk, self.last_blk + 1):
+            names.update(groups[b])
+        mine = [(n, p) for n, p in self.model.named_parameters() if n in names]
+        # parameters of other stages are dropped (freed) — this stage never touches them
+        for n, p in self.model.named_parameters():
+            if n not in names:
+                p.requires_grad_(False)
+                p.data = torch.empty(0, device=rt.device)
+        self.flat = FlatParams(mine, rt.device, rt.dtype, cfg.bucket_mb)
+        self.opt = FlatAdam(self.flat, lr=cfg.lr)
+        self.stats = DeviceStats(rt.device)
+        self.prev_grad = torch.zeros_like(self.flat.grad) if (cfg.grad_divergence and self.is_last) else None
+        self.labels_mb: List[torch.Tensor] = []
+        self.mb_frac: List[float] = []
+        hw = 32
+        self.runner = PipelineRunner(
+            s, S, self._fwd,
+            in_shape=lambda n: boundary_shape(self.first_blk - 1, n, hw),
+            out_shape=lambda n: boundary_shape(self.last_blk, n, hw),
+            dtype=rt.dtype, device=rt.device)
+        self.global_step = 0
+
+    def _fwd(self, x, i):
+        if self.is_first and x.dtype == torch.uint8:
+            x = ops.stem_prepare(x.permute(0, 3, 1, 2), dtype=self.rt.dtype)
+        f = self.model.features(x, self.first_blk, self.last_blk)
+        if self.is_last:
+            return ops.head_loss(f, self.model.fc.weight, self.model.fc.bias, self.labels_mb[i],
+                                 loss_scale=self.mb_frac[i], n_valid=self.cfg.num_classes)
+        return f
+
+    def step(self, images, labels):
+        B = labels.shape[0]
+        M = max(1, min(self.cfg.microbatches, B))
+        sizes = [len(c) for c in np.array_split(np.arange(B), M)]
+        self.labels_mb = list(torch.split(labels, sizes))
+        self.mb_frac = [n / B for n in sizes]
+        imgs = list(torch.split(images, sizes)) if self.is_first else None
+        self.flat.begin_step()
+        loss, correct = self.runner.run(sizes, imgs)
+        self.opt.step()
+        sent = self.runner.p2p.end_step()
+        if self.is_last:
+            self.stats.add_step(loss, correct, B)
+            if self.prev_grad is not None:
+                self.stats.add_grad_div(ops.grad_diff_sq(self.flat.grad, self.prev_grad))
+        else:
+            self.stats.buf[5] += 1
+        self.global_step += 1
+        return sent
+
+
+def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
+    rt = setup_runtime(rank, world, cfg, device)
+    logs_dir = cfg.resolved_logs_dir()
+    images, labels = build_dataset(cfg.sample_size, cfg.synthetic, cfg.data_dir, cfg.seed)
+    if rank == 0 and not cfg.quiet:
+        print("Worker 0 generated the synthetic dataset." if cfg.synthetic else
+              "Worker 0 downloaded the dataset.", flush=True)
+    # every stage iterates the same (seeded, unshuffled) subset — layer_…:103-131
+    loader = BatchLoader(images, labels, cfg.batch_size, rt.device, sampler=None)
+    eng = PPEngine(cfg, rt)
+    rec = EpochRecorder("layer", rank, logs_dir, cfg.sample_size)
+    hb = Heartbeat(cfg.heartbeat_dir, rank)
+    fault = FaultInjector(cfg.inject_fault, rank)
+    tag = f"pp_stage{rank}of{world}"
+    start_epoch = 0
+    if cfg.resume:
+        payload = checkpoint.load(cfg.resume, tag, eng.model, eng.opt)
+        if payload is not None:
+            start_epoch, eng.global_step = payload["epoch"], payload["global_step"]
+    if not cfg.quiet:
+        print(f"Worker {rank} is starting training...", flush=True)
+    cuda = rt.device.type == "cuda"
+    for epoch in range(start_epoch, cfg.epochs):
+        t_epoch = time.time()
+        t0 = time.time()
+        if world > 1:
+            dist.barrier()
+        rec.total_idle += time.time() - t0
+        step_times: List[float] = []
+        sent_total, nsteps = 0, 0
+        if cuda:
+            torch.cuda.reset_peak_memory_stats(rt.device)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        for bi, (x, y) in enumerate(loader):
+            if cfg.max_steps and bi >= cfg.max_steps:
+                break
+            ts = time.time()
+            rec.host.sample()
+            fault.maybe_fail(eng.global_step)
+            sent_total += eng.step(x, y)
+            step_times.append(time.time() - ts)
+            nsteps += 1
+            if bi % 50 == 0:
+                hb.beat(epoch, eng.global_step)
+        if cuda:
+            ev1.record()
+            torch.cuda.synchronize()
+            dev_s = ev0.elapsed_time(ev1) / 1e3
+        else:
+            dev_s = time.time() - t_epoch
+        s = eng.stats.read_and_reset()
+        epoch_time = time.time() - t_epoch
+        steps = max(nsteps, 1)
+        if eng.is_last:
+            loss = s["loss_sum"] / steps
+            acc = 100.0 * s["correct"] / max(s["seen"], 1)
+            if s["grad_div_n"] > 0:
+                rec.grad_divs = [s["grad_div_sum"] / s["grad_div_n"]]
+        else:
+            loss, acc = 0, 0
+        rec.total_compute += dev_s * 0.5
+        rec.total_comm += dev_s * 0.5
+        dev_s_max = allreduce_max_scalar(dev_s, rt.device)
+        n_img = nsteps * cfg.batch_size if nsteps else 0
+        n_img = min(n_img, len(labels)) if not cfg.max_steps else n_img
+        ext = {"images_per_sec": n_img / dev_s_max if dev_s_max > 0 else 0, "steps": nsteps,
+               "gpu_mem_MB": gpu_mem_mb(rt.device),
+               "nvlink_GBps": sent_total / dev_s_max / 1e9 if dev_s_max > 0 else 0}
+        if cuda:
+            step_times = [dev_s / steps] * nsteps
+        rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times,
+                      avg_bandwidth=sent_total / steps, ext=ext)
+        if eng.is_last and not cfg.quiet:
+            print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "
+                  f"Time: {epoch_time:.2f}s", flush=True)
+        if cfg.save_dir and ((cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
+            checkpoint.save(cfg.save_dir, tag, eng.model, eng.opt, epoch + 1, eng.global_step)
+        if world > 1:
+            dist.barrier()
+    if eng.is_last:
+        write_summary(logs_dir, f"summary_{cfg.sample_size}.json", {
+            "strategy": "layer", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
+            "microbatches": cfg.microbatches, "partition": partition_blocks(world),
+            "final": rec.rows[-1] if rec.rows else None})
+    from ..launch import shutdown_distributed
+    shutdown_distributed()
+    return rec.frame()

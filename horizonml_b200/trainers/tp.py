@@ -1,0 +1,167 @@
+"""Tensor-parallel trainer (reference: tensor_parallel_train.py:155-296).
+
+Every rank sees the same (seeded) batches.  Sharded parameters (column-parallel classifier,
+channel-parallel layer3/4 convs) live in their own flat store and are never averaged; replicated
+parameters are averaged with the bucketed fused all-reduce (the reference does 62 blocking
+per-parameter all-reduces, tensor_…:215-218).  ``avg_bandwidth`` keeps the reference meaning (bytes
+moved per step).
+"""
+from __future__ import annotations
+
+import time
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+from .. import checkpoint, ops
+from ..config import TrainConfig
+from ..data import BatchLoader, build_dataset
+from ..metrics import EpochRecorder, write_summary
+from ..models.flat import FlatAdam, FlatParams
+from ..models.resnet import resnet18
+from ..parallel.comm import make_grad_allreduce
+from ..parallel.dp import GradReducer
+from ..parallel.tp import TensorParallelResNet, TPComm
+from .common import (DeviceStats, FaultInjector, GraphedStep, Heartbeat, Runtime, allreduce_max_scalar,
+                     gpu_mem_mb, setup_runtime)
+
+
+class TPEngine:
+    def __init__(self, cfg: TrainConfig, rt: Runtime):
+        self.cfg, self.rt = cfg, rt
+        self.comm = TPComm()
+        dense = resnet18(cfg.num_classes, seed=cfg.seed)
+        self.model = TensorParallelResNet(dense, self.comm, cfg.tp_conv_split).to(rt.device)
+        self.model.train()
+        rep, shd = self.model.split_params()
+        self.flat_rep = FlatParams(rep, rt.device, rt.dtype, cfg.bucket_mb)
+        self.flat_shd = FlatParams(shd, rt.device, rt.dtype, cfg.bucket_mb)
+        self.opt_rep = FlatAdam(self.flat_rep, lr=cfg.lr)
+        self.opt_shd = FlatAdam(self.flat_shd, lr=cfg.lr)
+        self.ar = make_grad_allreduce(cfg.allreduce, self.flat_rep.total, rt.device) if rt.world > 1 else None
+        self.reducer = GradReducer(self.flat_rep, self.ar, cfg.overlap) if self.ar is not None else None
+        self.stats = DeviceStats(rt.device)
+        self.prev_grad = torch.zeros_like(self.flat_rep.grad) if cfg.grad_divergence else None
+        # collectives inside the step (NCCL all-gather/all-reduce) are graph-capturable on CUDA
+        self._graphed = GraphedStep(self._step_impl, rt.device, cfg.cuda_graph and rt.backend == "native")
+        self.global_step = 0
+
+    def _step_impl(self, images, labels):
+        x = images
+        if x.dtype == torch.uint8:
+            x = ops.stem_prepare(x.permute(0, 3, 1, 2), dtype=self.rt.dtype)
+        self.flat_rep.begin_step(); self.flat_shd.begin_step()
+        if self.reducer is not None:
+            self.reducer.begin_step()
+        loss, correct = self.model.forward_loss(x, labels)
+        loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish()
+        self.opt_rep.step(); self.opt_shd.step()
+        self.stats.add_step(loss, correct, labels.shape[0])
+        if self.prev_grad is not None:
+            self.stats.add_grad_div(ops.grad_diff_sq(self.flat_rep.grad, self.prev_grad))
+
+    def step(self, images, labels):
+        self._graphed(images, labels)
+        self.global_step += 1
+
+    def bytes_per_step(self) -> int:
+        rep = sum(self.ar.wire_bytes(b.end - b.start) for b in self.flat_rep.buckets) if self.ar else 0
+        return rep
+
+
+def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
+    rt = setup_runtime(rank, world, cfg, device)
+    logs_dir = cfg.resolved_logs_dir()
+    images, labels = build_dataset(cfg.sample_size, cfg.synthetic, cfg.data_dir, cfg.seed)
+    if rank == 0 and not cfg.quiet:
+        print("Worker 0 generated the synthetic dataset." if cfg.synthetic else
+              "Worker 0 downloaded the dataset.", flush=True)
+    loader = BatchLoader(images, labels, cfg.batch_size, rt.device, sampler=None)   # all ranks: same data
+    eng = TPEngine(cfg, rt)
+    rec = EpochRecorder("tensor", rank, logs_dir, cfg.sample_size)
+    hb = Heartbeat(cfg.heartbeat_dir, rank)
+    fault = FaultInjector(cfg.inject_fault, rank)
+    tag = f"tp_rank{rank}of{world}"
+    start_epoch = 0
+    if cfg.resume:
+        payload = checkpoint.load(cfg.resume, tag, eng.model, None)
+        if payload is not None:
+            start_epoch, eng.global_step = payload["epoch"], payload["global_step"]
+            ex = payload.get("extra", {})
+            if "opt_rep" in ex:
+                eng.opt_rep.load_state_dict(ex["opt_rep"]); eng.opt_shd.load_state_dict(ex["opt_shd"])
+            eng.flat_rep.sync_shadow(); eng.flat_shd.sync_shadow()
+    if not cfg.quiet:
+        print(f"Worker {rank} is starting training...", flush=True)
+    cuda = rt.device.type == "cuda"
+    for epoch in range(start_epoch, cfg.epochs):
+        t_epoch = time.time()
+        t0 = time.time()
+        if world > 1:
+            dist.barrier()
+        rec.total_idle += time.time() - t0
+        step_times: List[float] = []
+        nsteps, tp_bytes = 0, 0
+        if cuda:
+            torch.cuda.reset_peak_memory_stats(rt.device)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        for bi, (x, y) in enumerate(loader):
+            if cfg.max_steps and bi >= cfg.max_steps:
+                break
+            ts = time.time()
+            rec.host.sample()
+            fault.maybe_fail(eng.global_step)
+            eng.step(x, y)
+            if cfg.step_barrier and world > 1:
+                ti = time.time()
+                if cuda:
+                    torch.cuda.synchronize()
+                dist.barrier()
+                rec.total_idle += time.time() - ti
+            step_times.append(time.time() - ts)
+            nsteps += 1
+            if bi % 50 == 0:
+                hb.beat(epoch, eng.global_step)
+        if cuda:
+            ev1.record()
+            torch.cuda.synchronize()
+            dev_s = ev0.elapsed_time(ev1) / 1e3
+        else:
+            dev_s = time.time() - t_epoch
+        tp_bytes = eng.comm.take_bytes()
+        s = eng.stats.read_and_reset()
+        epoch_time = time.time() - t_epoch
+        steps = max(int(s["steps"]), 1)
+        loss = s["loss_sum"] / steps
+        acc = 100.0 * s["correct"] / max(s["seen"], 1)
+        if s["grad_div_n"] > 0:
+            rec.grad_divs = [s["grad_div_sum"] / s["grad_div_n"]]
+        rec.total_compute += dev_s / 3.0
+        rec.total_comm += dev_s * 2.0 / 3.0
+        dev_s_max = allreduce_max_scalar(dev_s, rt.device)
+        bytes_per_step = eng.bytes_per_step() + (tp_bytes / steps if eng._graphed.graph is None else 0)
+        ext = {"images_per_sec": s["seen"] / dev_s_max if dev_s_max > 0 else 0, "steps": nsteps,
+               "gpu_mem_MB": gpu_mem_mb(rt.device),
+               "nvlink_GBps": bytes_per_step * nsteps / dev_s_max / 1e9 if dev_s_max > 0 else 0}
+        if cuda:
+            step_times = [dev_s / max(nsteps, 1)] * nsteps
+        rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times, avg_bandwidth=bytes_per_step, ext=ext)
+        if not cfg.quiet:   # the reference prints the epoch line on every rank (tensor_…:264)
+            print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "
+                  f"Time: {epoch_time:.2f}s", flush=True)
+        if cfg.save_dir and ((cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
+            checkpoint.save(cfg.save_dir, tag, eng.model, None, epoch + 1, eng.global_step,
+                            extra={"opt_rep": eng.opt_rep.state_dict(), "opt_shd": eng.opt_shd.state_dict()})
+        if world > 1:
+            dist.barrier()
+    if rank == 0:
+        write_summary(logs_dir, f"summary_{cfg.sample_size}.json", {
+            "strategy": "tensor", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
+            "conv_split": eng.model.conv_split, "final": rec.rows[-1] if rec.rows else None})
+    from ..launch import shutdown_distributed
+    shutdown_distributed()
+    return rec.frame()
