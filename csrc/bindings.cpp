@@ -1,0 +1,313 @@
+// Python bindings (torch tensors in, raw pointers + current CUDA stream out to the launchers).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include <string>
+#include <vector>
+
+#include "launchers.h"
+
+namespace py = pybind11;
+using at::Tensor;
+
+namespace {
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+inline const void* cptr(const Tensor& t) { return t.data_ptr(); }
+inline void* mptr(Tensor& t) { return t.data_ptr(); }
+inline float* fptr(const c10::optional<Tensor>& t) { return t.has_value() && t->defined() ? t->data_ptr<float>() : nullptr; }
+
+// physical NHWC dims of a logical NCHW channels_last tensor
+struct Dims { int N, C, H, W; };
+Dims dims_of(const Tensor& t) {
+  TORCH_CHECK(t.dim() == 4, "expected 4-D tensor");
+  return {(int)t.size(0), (int)t.size(1), (int)t.size(2), (int)t.size(3)};
+}
+void check_cl(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16, name, " must be bf16");
+  TORCH_CHECK(t.is_contiguous(at::MemoryFormat::ChannelsLast) || t.is_contiguous(), name,
+              " must be channels_last contiguous");
+  if (!(t.size(2) == 1 && t.size(3) == 1) && t.size(1) != 1)
+    TORCH_CHECK(t.is_contiguous(at::MemoryFormat::ChannelsLast), name, " must be channels_last");
+}
+Tensor empty_cl(const Tensor& like, int N, int C, int H, int W) {
+  return at::empty({N, C, H, W}, like.options().memory_format(at::MemoryFormat::ChannelsLast));
+}
+
+int channel_ok(int64_t C) { return hz_channel_ok((int)C); }
+
+Tensor channel_sums(const Tensor& y) {
+  check_cl(y, "y");
+  c10::cuda::CUDAGuard g(y.device());
+  auto d = dims_of(y);
+  Tensor sums = at::empty({2, d.C}, y.options().dtype(at::kFloat));
+  hz_channel_sums(cptr(y), sums.data_ptr<float>(), d.N * d.H * d.W, d.C, cur_stream());
+  return sums;
+}
+
+std::vector<Tensor> bn_act_fwd(const Tensor& y, const Tensor& sums, const Tensor& gamma, const Tensor& beta,
+                               const c10::optional<Tensor>& rmean, const c10::optional<Tensor>& rvar,
+                               double momentum, double eps, const c10::optional<Tensor>& residual, bool relu,
+                               bool training) {
+  check_cl(y, "y");
+  c10::cuda::CUDAGuard g(y.device());
+  auto d = dims_of(y);
+  Tensor out = at::empty_like(y);
+  Tensor mean = at::empty({d.C}, y.options().dtype(at::kFloat));
+  Tensor invstd = at::empty({d.C}, y.options().dtype(at::kFloat));
+  const void* res = nullptr;
+  if (residual.has_value() && residual->defined()) { check_cl(*residual, "residual"); res = residual->data_ptr(); }
+  hz_bn_act_fwd(cptr(y), sums.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(), res,
+                out.data_ptr(), mean.data_ptr<float>(), invstd.data_ptr<float>(), fptr(rmean), fptr(rvar),
+                d.N * d.H * d.W, d.C, (float)eps, (float)momentum, relu ? 1 : 0, training ? 1 : 0, cur_stream());
+  return {out, mean, invstd};
+}
+
+// writes dgamma/dbeta straight into their gradient slots
+std::vector<Tensor> bn_act_bwd(const Tensor& dout, const Tensor& out, const Tensor& yraw, const Tensor& mean,
+                               const Tensor& invstd, const Tensor& gamma, bool relu, bool has_res,
+                               Tensor dgamma, Tensor dbeta, bool acc_gamma, bool acc_beta) {
+  check_cl(dout, "dout"); check_cl(yraw, "yraw");
+  c10::cuda::CUDAGuard g(dout.device());
+  auto d = dims_of(yraw);
+  Tensor dy = at::empty_like(yraw);
+  Tensor dres;
+  if (has_res) dres = at::empty_like(yraw);
+  Tensor scratch = at::empty({2, d.C}, yraw.options().dtype(at::kFloat));
+  hz_bn_act_bwd(cptr(dout), cptr(out), cptr(yraw), mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                gamma.data_ptr<float>(), scratch.data_ptr<float>(), dy.data_ptr(),
+                has_res ? dres.data_ptr() : nullptr, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
+                acc_gamma ? 1 : 0, acc_beta ? 1 : 0, d.N * d.H * d.W, d.C, relu ? 1 : 0, cur_stream());
+  return {dy, dres};
+}
+
+Tensor maxpool_fwd(const Tensor& x) {
+  check_cl(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  auto d = dims_of(x);
+  const int Ho = (d.H + 2 - 3) / 2 + 1, Wo = (d.W + 2 - 3) / 2 + 1;
+  Tensor y = empty_cl(x, d.N, d.C, Ho, Wo);
+  hz_maxpool_fwd(cptr(x), y.data_ptr(), d.N, d.H, d.W, d.C, cur_stream());
+  return y;
+}
+
+Tensor maxpool_bwd(const Tensor& dy, const Tensor& x, const Tensor& y) {
+  check_cl(dy, "dy"); check_cl(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  auto d = dims_of(x);
+  Tensor dx = at::empty_like(x);
+  hz_maxpool_bwd(cptr(dy), cptr(x), cptr(y), dx.data_ptr(), d.N, d.H, d.W, d.C, cur_stream());
+  return dx;
+}
+
+// uint8 NHWC-physical (logical NCHW channels_last view) -> normalised bf16, same layout
+Tensor u8_normalize(const Tensor& img, double mean, double std) {
+  TORCH_CHECK(img.is_cuda() && img.scalar_type() == at::kByte);
+  c10::cuda::CUDAGuard g(img.device());
+  Tensor out = at::empty_strided(img.sizes(), img.strides(), img.options().dtype(at::kBFloat16));
+  hz_u8_normalize(img.data_ptr(), out.data_ptr(), (size_t)img.numel(), (float)mean, (float)std, cur_stream());
+  return out;
+}
+
+Tensor im2col_small(const Tensor& x, int64_t R, int64_t stride, int64_t pad, int64_t Kp) {
+  check_cl(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  auto d = dims_of(x);
+  const int Ho = (d.H + 2 * pad - R) / stride + 1, Wo = (d.W + 2 * pad - R) / stride + 1;
+  Tensor A = at::empty({(int64_t)d.N * Ho * Wo, Kp}, x.options());
+  hz_im2col_small(cptr(x), A.data_ptr(), d.N, d.H, d.W, d.C, (int)R, (int)R, (int)stride, (int)pad, Ho, Wo,
+                  (int)Kp, cur_stream());
+  return A;
+}
+
+Tensor pad_rows(const Tensor& w2d, int64_t Kp) {
+  TORCH_CHECK(w2d.is_cuda() && w2d.scalar_type() == at::kBFloat16 && w2d.dim() == 2 && w2d.is_contiguous());
+  c10::cuda::CUDAGuard g(w2d.device());
+  Tensor out = at::empty({w2d.size(0), Kp}, w2d.options());
+  hz_pad_rows(cptr(w2d), out.data_ptr(), (int)w2d.size(0), (int)w2d.size(1), (int)Kp, cur_stream());
+  return out;
+}
+
+std::vector<Tensor> head_fwd_bwd(const Tensor& feat, const Tensor& W, const c10::optional<Tensor>& bias,
+                                 const Tensor& labels, double loss_scale, int64_t n_valid, Tensor dW,
+                                 c10::optional<Tensor> db, bool accumulate, bool need_dfeat) {
+  check_cl(feat, "feat");
+  TORCH_CHECK(W.scalar_type() == at::kFloat && W.is_contiguous());
+  TORCH_CHECK(labels.scalar_type() == at::kLong);
+  c10::cuda::CUDAGuard g(feat.device());
+  auto d = dims_of(feat);
+  const int K = (int)W.size(0);
+  TORCH_CHECK(K <= 64, "head supports at most 64 (padded) classes");
+  auto fo = feat.options().dtype(at::kFloat);
+  Tensor pooled = at::empty({d.N, d.C}, fo), dlogits = at::empty({d.N, K}, fo), logits = at::empty({d.N, K}, fo);
+  Tensor loss = at::empty({}, fo), correct = at::empty({}, fo);
+  Tensor dfeat;
+  if (need_dfeat) dfeat = at::empty_like(feat);
+  hz_head_fwd_bwd(cptr(feat), W.data_ptr<float>(), fptr(bias), labels.data_ptr<int64_t>(),
+                  pooled.data_ptr<float>(), dlogits.data_ptr<float>(), logits.data_ptr<float>(),
+                  need_dfeat ? dfeat.data_ptr() : nullptr, loss.data_ptr<float>(), correct.data_ptr<float>(),
+                  dW.data_ptr<float>(), fptr(db), d.N, d.C, d.H * d.W, K, (int)n_valid, (float)loss_scale,
+                  accumulate ? 1 : 0, cur_stream());
+  return {loss, correct, dfeat, logits};
+}
+
+void adam_step(Tensor master, const Tensor& grad, Tensor m, Tensor v, c10::optional<Tensor> shadow, Tensor step,
+               double lr, double b1, double b2, double eps, double gscale) {
+  TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && master.numel() % 4 == 0);
+  c10::cuda::CUDAGuard g(master.device());
+  void* sh = nullptr;
+  if (shadow.has_value() && shadow->defined()) { TORCH_CHECK(shadow->scalar_type() == at::kBFloat16); sh = shadow->data_ptr(); }
+  hz_adam(master.data_ptr<float>(), grad.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), sh,
+          step.data_ptr<float>(), (size_t)master.numel(), (float)lr, (float)b1, (float)b2, (float)eps,
+          (float)gscale, cur_stream());
+}
+
+Tensor grad_diff_sq(const Tensor& grad, Tensor prev) {
+  TORCH_CHECK(grad.is_cuda() && grad.numel() % 4 == 0);
+  c10::cuda::CUDAGuard g(grad.device());
+  Tensor out = at::empty({}, grad.options());
+  hz_grad_diff(grad.data_ptr<float>(), prev.data_ptr<float>(), out.data_ptr<float>(), (size_t)grad.numel(),
+               cur_stream());
+  return out;
+}
+
+void stats_update(Tensor stats, Tensor has_prev, const Tensor& loss, const Tensor& correct, double batch,
+                  const c10::optional<Tensor>& diff_sq) {
+  c10::cuda::CUDAGuard g(stats.device());
+  hz_stats_update(stats.data_ptr<float>(), has_prev.data_ptr<float>(), loss.data_ptr<float>(),
+                  correct.data_ptr<float>(), (float)batch, fptr(diff_sq), cur_stream());
+}
+
+// ------------------------------------------------------------------ tcgen05 convs
+bool conv_supported(int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t stride,
+                    int64_t pad) {
+  return hz_conv_supported((int)N, (int)H, (int)W, (int)Cin, (int)Cout, (int)R, (int)stride, (int)pad) != 0;
+}
+
+std::vector<Tensor> conv_fwd(const Tensor& x, const Tensor& w, int64_t stride, int64_t pad, bool want_stats) {
+  check_cl(x, "x"); check_cl(w, "w");
+  c10::cuda::CUDAGuard g(x.device());
+  auto d = dims_of(x);
+  const int Cout = (int)w.size(0), R = (int)w.size(2);
+  const int Ho = (d.H + 2 * pad - R) / stride + 1, Wo = (d.W + 2 * pad - R) / stride + 1;
+  Tensor y = empty_cl(x, d.N, Cout, Ho, Wo);
+  Tensor stats;
+  if (want_stats) stats = at::empty({2, Cout}, x.options().dtype(at::kFloat));
+  int rc = hz_conv_fwd(cptr(x), cptr(w), y.data_ptr(), want_stats ? stats.data_ptr<float>() : nullptr, d.N, d.H,
+                       d.W, d.C, Cout, R, (int)stride, (int)pad, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_conv_fwd failed rc=", rc);
+  return {y, stats};
+}
+
+Tensor conv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride, int64_t pad) {
+  check_cl(dy, "dy"); check_cl(w, "w");
+  c10::cuda::CUDAGuard g(dy.device());
+  const int N = (int)x_shape[0], Cin = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
+  Tensor dx = empty_cl(dy, N, Cin, H, W);
+  int rc = hz_conv_dgrad(cptr(dy), cptr(w), dx.data_ptr(), N, H, W, Cin, (int)w.size(0), (int)w.size(2),
+                         (int)stride, (int)pad, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_conv_dgrad failed rc=", rc);
+  return dx;
+}
+
+// dw_out: fp32 tensor whose storage is [Cout, R, S, Cin]-physical (a view of the flat gradient bucket)
+void conv_wgrad(const Tensor& dy, const Tensor& x, Tensor dw_out, int64_t R, int64_t stride, int64_t pad,
+                bool accumulate, int64_t ld_out, int64_t n_valid) {
+  check_cl(dy, "dy"); check_cl(x, "x");
+  TORCH_CHECK(dw_out.scalar_type() == at::kFloat);
+  c10::cuda::CUDAGuard g(dy.device());
+  auto d = dims_of(x);
+  int rc = hz_conv_wgrad(cptr(dy), cptr(x), dw_out.data_ptr<float>(), d.N, d.H, d.W, d.C, (int)dy.size(1), (int)R,
+                         (int)stride, (int)pad, accumulate ? 1 : 0, (long long)ld_out, (int)n_valid, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_conv_wgrad failed rc=", rc);
+}
+
+// ------------------------------------------------------------------ peer all-reduce
+class PeerComm {
+ public:
+  PeerComm(int rank, int world, int device, int64_t max_wire_bytes, int max_blocks)
+      : rank_(rank), world_(world) {
+    c_ = hz_comm_create(rank, world, device, (size_t)max_wire_bytes, max_blocks);
+    TORCH_CHECK(c_ != nullptr, "hz_comm_create failed");
+  }
+  ~PeerComm() { hz_comm_destroy(c_); }
+  py::bytes export_handles() {
+    char h[64];
+    TORCH_CHECK(hz_comm_export(c_, h) == 0, "cudaIpcGetMemHandle failed");
+    return py::bytes(h, 64);
+  }
+  void import_handles(const std::vector<std::string>& hs) {
+    TORCH_CHECK((int)hs.size() == world_);
+    std::string all;
+    for (auto& s : hs) { TORCH_CHECK(s.size() == 64); all += s; }
+    TORCH_CHECK(hz_comm_import(c_, all.data()) == 0, "cudaIpcOpenMemHandle failed");
+  }
+  static void link_local(std::vector<PeerComm*> comms) {
+    std::vector<HzComm*> raw;
+    for (auto* c : comms) raw.push_back(c->c_);
+    hz_comm_link_local(raw.data(), (int)raw.size());
+  }
+  void set_multicast(int64_t mc_ptr, int64_t local_ptr, int64_t bytes) {
+    hz_comm_set_multicast(c_, (void*)mc_ptr, (void*)local_ptr, (size_t)bytes);
+  }
+  void allreduce(Tensor grad, const std::string& algo, bool wire_bf16, double scale) {
+    TORCH_CHECK(grad.is_cuda() && grad.scalar_type() == at::kFloat && grad.is_contiguous());
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : -1;
+    TORCH_CHECK(a >= 0, "unknown all-reduce algorithm ", algo);
+    c10::cuda::CUDAGuard g(grad.device());
+    int rc = hz_comm_allreduce(c_, grad.data_ptr<float>(), (size_t)grad.numel(), a, wire_bf16 ? 1 : 0,
+                               (float)scale, cur_stream());
+    TORCH_CHECK(rc == 0, "hz_comm_allreduce failed rc=", rc);
+  }
+  int64_t blocks_for(int64_t n, const std::string& algo, bool wire_bf16) {
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : 2;
+    return hz_comm_blocks_for(c_, (size_t)n, a, wire_bf16 ? 1 : 0);
+  }
+  void barrier(c10::optional<Tensor> stamps) {
+    long long* s = nullptr;
+    if (stamps.has_value() && stamps->defined()) s = (long long*)stamps->data_ptr<int64_t>();
+    TORCH_CHECK(hz_comm_barrier(c_, s, cur_stream()) == 0);
+  }
+  int error() { return hz_comm_error(c_); }
+
+ private:
+  HzComm* c_;
+  int rank_, world_;
+};
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "horizonml_b200 sm_100a kernels";
+  m.def("channel_ok", &channel_ok);
+  m.def("channel_sums", &channel_sums);
+  m.def("bn_act_fwd", &bn_act_fwd);
+  m.def("bn_act_bwd", &bn_act_bwd);
+  m.def("maxpool_fwd", &maxpool_fwd);
+  m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("u8_normalize", &u8_normalize);
+  m.def("im2col_small", &im2col_small);
+  m.def("pad_rows", &pad_rows);
+  m.def("head_fwd_bwd", &head_fwd_bwd);
+  m.def("adam_step", &adam_step);
+  m.def("grad_diff_sq", &grad_diff_sq);
+  m.def("stats_update", &stats_update);
+  m.def("conv_supported", &conv_supported);
+  m.def("conv_fwd", &conv_fwd);
+  m.def("conv_dgrad", &conv_dgrad);
+  m.def("conv_wgrad", &conv_wgrad);
+  py::class_<PeerComm>(m, "PeerComm")
+      .def(py::init<int, int, int, int64_t, int>())
+      .def("export_handles", &PeerComm::export_handles)
+      .def("import_handles", &PeerComm::import_handles)
+      .def_static("link_local", &PeerComm::link_local)
+      .def("set_multicast", &PeerComm::set_multicast)
+      .def("allreduce", &PeerComm::allreduce)
+      .def("blocks_for", &PeerComm::blocks_for)
+      .def("barrier", &PeerComm::barrier)
+      .def("error", &PeerComm::error);
+}

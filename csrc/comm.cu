@@ -1,0 +1,417 @@
+// Peer-memory gradient all-reduce for NVLink 5 / NVSwitch (§5.8).
+//
+// Replaces the reference's DDP bucket all-reduce on gloo (data_parallel_train.py:118,202; K2) and the
+// 62 blocking per-parameter all-reduces of the tensor-parallel script (tensor_parallel_train.py:215-218; K9),
+// and its per-step host barrier (K4/K10) with device-side flag barriers.
+//
+// One kernel per bucket does:   pack   : grad(fp32) * (1/W) -> wire dtype (bf16 | fp32) into the local,
+//                                         peer-visible staging buffer                       [fused cast+scale]
+//                               barrier: per-block flag exchange with the same block on every peer
+//                               reduce : one-shot  - read all W staged copies, sum in fp32, write grad
+//                                        two-shot  - reduce own 1/W slice, push it to every peer's `out`
+//                                                    buffer (NVLink stores), barrier, unpack out -> grad
+//                                        nvls      - like two-shot but the reduction is done by the switch:
+//                                                    multimem.ld_reduce on the multicast address, result
+//                                                    broadcast with multimem.st
+// Summation order is rank 0..W-1 on every rank, so replicas stay bit-identical.
+// Staging/out buffers alternate between calls (parity), which together with the in-call barrier makes
+// back-to-back calls race-free without a trailing barrier.  All counters live in device memory so the
+// kernels are CUDA-graph replayable.  Spins are bounded (error flag instead of a hang).
+#include "common.cuh"
+#include "launchers.h"
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace hz {
+
+constexpr int kMaxRanks = 8;
+constexpr int kCommThreads = 512;
+constexpr size_t kFlagBytes = 1 << 16;          // flags + counters region at the start of each rank's block
+constexpr long long kSpinTimeoutNs = 4000000000LL;   // 4 s
+
+struct CommDev {
+  char* base[kMaxRanks];      // every rank's region (flags first)
+  char* mc_base;              // multicast mapping of the NVLS data region (or null)
+  char* mc_local;             // this rank's local mapping of the same region
+  size_t buf_bytes;           // size of ONE staging/out buffer
+  int rank, world;
+};
+
+// region layout: [flags: maxBlocks*world u32][counters: maxBlocks u32 (+calls)][err u32] ... [data @kFlagBytes]
+// data: stage[0], stage[1], out[0], out[1]  (each buf_bytes)
+HZ_DEVINL uint32_t* flags_of(char* base) { return reinterpret_cast<uint32_t*>(base); }
+HZ_DEVINL uint32_t* counters_of(char* base) { return reinterpret_cast<uint32_t*>(base + 32768); }
+HZ_DEVINL uint32_t* calls_of(char* base) { return reinterpret_cast<uint32_t*>(base + 49152); }
+HZ_DEVINL uint32_t* err_of(char* base) { return reinterpret_cast<uint32_t*>(base + 61440); }
+
+HZ_DEVINL void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+HZ_DEVINL uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+HZ_DEVINL long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Barrier between block `blockIdx.x` of every rank.  All prior global writes of this block are made
+// visible system-wide before the flag is published; peers' writes are visible after it returns.
+HZ_DEVINL void peer_block_barrier(const CommDev& c, uint32_t* s_epoch) {
+  __syncthreads();
+  char* my = c.base[c.rank];
+  uint32_t* cnt = counters_of(my) + blockIdx.x;
+  if (threadIdx.x == 0) *s_epoch = *cnt + 1;
+  __syncthreads();
+  const uint32_t e = *s_epoch;
+  if (threadIdx.x < c.world) {
+    const int r = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(flags_of(c.base[r]) + blockIdx.x * c.world + c.rank, e);
+    const uint32_t* mine = flags_of(my) + blockIdx.x * c.world + r;
+    const long long t0 = globaltimer_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
+      if (globaltimer_ns() - t0 > kSpinTimeoutNs) {
+        atomicExch(err_of(my), 1u);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *cnt = e;
+}
+
+template <bool kBf16>
+struct Wire;
+template <>
+struct Wire<true> {          // 8 elements / 16 B
+  static constexpr int kVec = 8;
+  HZ_DEVINL static uint4 pack(const float* g, float s) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = g[i] * s;
+    bf16x8 p = pack8(f);
+    return *reinterpret_cast<uint4*>(&p);
+  }
+  HZ_DEVINL static void accum(float* a, const uint4& w) {
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(&w), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] += f[i];
+  }
+  HZ_DEVINL static uint4 from_acc(const float* a) {
+    bf16x8 p = pack8(a);
+    return *reinterpret_cast<uint4*>(&p);
+  }
+  HZ_DEVINL static uint4 mc_ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <>
+struct Wire<false> {         // 4 elements / 16 B
+  static constexpr int kVec = 4;
+  HZ_DEVINL static uint4 pack(const float* g, float s) {
+    float4 f = make_float4(g[0] * s, g[1] * s, g[2] * s, g[3] * s);
+    return *reinterpret_cast<uint4*>(&f);
+  }
+  HZ_DEVINL static void accum(float* a, const uint4& w) {
+    const float4 f = *reinterpret_cast<const float4*>(&w);
+    a[0] += f.x; a[1] += f.y; a[2] += f.z; a[3] += f.w;
+  }
+  HZ_DEVINL static uint4 from_acc(const float* a) {
+    float4 f = make_float4(a[0], a[1], a[2], a[3]);
+    return *reinterpret_cast<uint4*>(&f);
+  }
+  HZ_DEVINL static uint4 mc_ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+};
+
+HZ_DEVINL void mc_st(void* p, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int V>
+HZ_DEVINL void load_grad(const float* g, size_t vec, float* f) {
+#pragma unroll
+  for (int i = 0; i < V / 4; ++i) {
+    const float4 t = reinterpret_cast<const float4*>(g)[vec * (V / 4) + i];
+    f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
+  }
+}
+template <int V>
+HZ_DEVINL void store_grad(float* g, size_t vec, const float* f) {
+#pragma unroll
+  for (int i = 0; i < V / 4; ++i)
+    reinterpret_cast<float4*>(g)[vec * (V / 4) + i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+
+enum Algo { kOneShot = 0, kTwoShot = 1, kNvls = 2 };
+
+// sub-range b of slice r of nv vectors split over W ranks and B blocks
+HZ_DEVINL void sub_range(size_t nv, int W, int B, int r, int b, size_t& lo, size_t& hi) {
+  const size_t q = (nv + W - 1) / W;
+  const size_t slo = min((size_t)r * q, nv), shi = min(slo + q, nv);
+  const size_t qq = (shi - slo + B - 1) / B;
+  lo = min(slo + (size_t)b * qq, shi);
+  hi = min(lo + qq, shi);
+}
+
+template <bool kBf16, int kAlgo>
+__global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, float* __restrict__ grad,
+                                                                 size_t n, float scale) {
+  using Wt = Wire<kBf16>;
+  constexpr int V = Wt::kVec;
+  __shared__ uint32_t s_epoch;
+  const int W = c.world, B = gridDim.x, b = blockIdx.x;
+  const size_t nv = n / V;
+  char* my = c.base[c.rank];
+  const uint32_t parity = calls_of(my)[b] & 1u;
+  const size_t stage_off = kFlagBytes + (size_t)parity * c.buf_bytes;
+  const size_t out_off = kFlagBytes + (size_t)(2 + parity) * c.buf_bytes;
+  // NVLS uses the symmetric (multicast-mapped) region instead of the IPC region for data
+  char* my_data = (kAlgo == kNvls) ? c.mc_local - kFlagBytes : my;
+  uint4* my_stage = reinterpret_cast<uint4*>(my_data + stage_off);
+
+  // ---- pack: fused 1/W scale + cast into the peer-visible staging buffer -------------------------
+  if (kAlgo == kOneShot) {
+    const size_t per = (nv + B - 1) / B;
+    const size_t lo = min((size_t)b * per, nv), hi = min(lo + per, nv);
+    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+      float f[V];
+      load_grad<V>(grad, v, f);
+      my_stage[v] = Wt::pack(f, scale);
+    }
+  } else {
+    for (int r = 0; r < W; ++r) {
+      size_t lo, hi;
+      sub_range(nv, W, B, r, b, lo, hi);
+      for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+        float f[V];
+        load_grad<V>(grad, v, f);
+        my_stage[v] = Wt::pack(f, scale);
+      }
+    }
+  }
+  peer_block_barrier(c, &s_epoch);
+
+  if (kAlgo == kOneShot) {
+    const size_t per = (nv + B - 1) / B;
+    const size_t lo = min((size_t)b * per, nv), hi = min(lo + per, nv);
+    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+      uint4 w[kMaxRanks];
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < W) w[r] = reinterpret_cast<const uint4*>(c.base[r] + stage_off)[v];
+      float a[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < W) Wt::accum(a, w[r]);
+      store_grad<V>(grad, v, a);
+    }
+  } else {
+    size_t lo, hi;
+    sub_range(nv, W, B, c.rank, b, lo, hi);
+    if (kAlgo == kTwoShot) {
+      for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+        uint4 w[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < W) w[r] = reinterpret_cast<const uint4*>(c.base[r] + stage_off)[v];
+        float a[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = 0.f;
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < W) Wt::accum(a, w[r]);
+        const uint4 o = Wt::from_acc(a);
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < W) reinterpret_cast<uint4*>(c.base[r] + out_off)[v] = o;     // NVLink push
+      }
+    } else {
+      const char* mc_stage = c.mc_base - kFlagBytes + stage_off;
+      char* mc_out = c.mc_base - kFlagBytes + out_off;
+      for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+        const uint4 o = Wt::mc_ld_reduce(mc_stage + v * 16);   // reduced inside the NVSwitch
+        mc_st(mc_out + v * 16, o);                             // broadcast by the NVSwitch
+      }
+    }
+    peer_block_barrier(c, &s_epoch);
+    const uint4* my_out = reinterpret_cast<const uint4*>(my_data + out_off);
+    for (int r = 0; r < W; ++r) {
+      size_t l2, h2;
+      sub_range(nv, W, B, r, b, l2, h2);
+      for (size_t v = l2 + threadIdx.x; v < h2; v += blockDim.x) {
+        float a[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = 0.f;
+        Wt::accum(a, my_out[v]);
+        store_grad<V>(grad, v, a);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) calls_of(my)[b] += 1u;
+}
+
+__global__ void barrier_kernel(CommDev c, long long* stamp_ns) {
+  __shared__ uint32_t s_epoch;
+  const long long t0 = globaltimer_ns();
+  peer_block_barrier(c, &s_epoch);
+  if (threadIdx.x == 0 && stamp_ns != nullptr) {
+    stamp_ns[0] = t0;                       // arrival
+    stamp_ns[1] = globaltimer_ns();         // release: (release - arrival) = device-side idle time
+  }
+}
+
+}  // namespace hz
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct HzComm {
+  hz::CommDev dev;
+  int device;
+  int max_blocks;
+  size_t region_bytes;
+  char* local;                 // cudaMalloc'd region
+  bool imported[hz::kMaxRanks];
+  bool local_group;
+};
+
+#define HZ_CUDA(x)                                                                              \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) {                                                                    \
+      fprintf(stderr, "[hz comm] %s failed: %s (%s:%d)\n", #x, cudaGetErrorString(e_), __FILE__, \
+              __LINE__);                                                                        \
+      return -1;                                                                                \
+    }                                                                                           \
+  } while (0)
+
+extern "C" {
+
+HzComm* hz_comm_create(int rank, int world, int device, size_t max_wire_bytes, int max_blocks) {
+  if (world > hz::kMaxRanks || max_blocks * world * 4 > 32768 || max_blocks * 4 > 12288) return nullptr;
+  HzComm* c = new HzComm();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  c->max_blocks = max_blocks;
+  cudaSetDevice(device);
+  const size_t buf = (max_wire_bytes + 255) / 256 * 256;
+  c->dev.buf_bytes = buf;
+  c->dev.rank = rank;
+  c->dev.world = world;
+  c->region_bytes = hz::kFlagBytes + 4 * buf;
+  if (cudaMalloc(&c->local, c->region_bytes) != cudaSuccess) { delete c; return nullptr; }
+  cudaMemset(c->local, 0, hz::kFlagBytes);
+  c->dev.base[rank] = c->local;
+  cudaDeviceSynchronize();
+  return c;
+}
+
+int hz_comm_export(HzComm* c, void* handle64) {
+  cudaIpcMemHandle_t h;
+  HZ_CUDA(cudaIpcGetMemHandle(&h, c->local));
+  static_assert(sizeof(h) == 64, "ipc handle size");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int hz_comm_import(HzComm* c, const void* handles) {
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->dev.world; ++r) {
+    if (r == c->dev.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* p = nullptr;
+    HZ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->dev.base[r] = (char*)p;
+    c->imported[r] = true;
+  }
+  return 0;
+}
+
+// same-process "virtual ranks" on one device (single-GPU tests of the multi-rank protocol)
+int hz_comm_link_local(HzComm** comms, int world) {
+  for (int i = 0; i < world; ++i)
+    for (int r = 0; r < world; ++r) comms[i]->dev.base[r] = comms[r]->local;
+  for (int i = 0; i < world; ++i) comms[i]->local_group = true;
+  return 0;
+}
+
+void hz_comm_set_multicast(HzComm* c, void* mc_ptr, void* local_ptr, size_t bytes) {
+  if (bytes < 4 * c->dev.buf_bytes) return;
+  c->dev.mc_base = (char*)mc_ptr;
+  c->dev.mc_local = (char*)local_ptr;
+}
+
+int hz_comm_blocks_for(HzComm* c, size_t n, int algo, int wire_bf16) {
+  const int V = wire_bf16 ? 8 : 4;
+  const size_t nv = n / V;
+  // ~8 vectors per thread; one-shot (latency-bound) prefers fewer, fatter blocks
+  size_t want = (nv + (size_t)hz::kCommThreads * 8 - 1) / ((size_t)hz::kCommThreads * 8);
+  if (want < 1) want = 1;
+  if (want > (size_t)c->max_blocks) want = c->max_blocks;
+  (void)algo;
+  return (int)want;
+}
+
+int hz_comm_allreduce(HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
+                      cudaStream_t st) {
+  const int V = wire_bf16 ? 8 : 4;
+  if (n % V != 0) return -2;
+  if (n * (wire_bf16 ? 2 : 4) > c->dev.buf_bytes) return -3;
+  if (algo == hz::kNvls && c->dev.mc_base == nullptr) return -4;
+  const int blocks = hz_comm_blocks_for(c, n, algo, wire_bf16);
+#define HZ_LAUNCH(BF, AL) \
+  hz::allreduce_kernel<BF, AL><<<blocks, hz::kCommThreads, 0, st>>>(c->dev, grad, n, scale)
+  if (wire_bf16) {
+    if (algo == hz::kOneShot) HZ_LAUNCH(true, hz::kOneShot);
+    else if (algo == hz::kTwoShot) HZ_LAUNCH(true, hz::kTwoShot);
+    else HZ_LAUNCH(true, hz::kNvls);
+  } else {
+    if (algo == hz::kOneShot) HZ_LAUNCH(false, hz::kOneShot);
+    else if (algo == hz::kTwoShot) HZ_LAUNCH(false, hz::kTwoShot);
+    else HZ_LAUNCH(false, hz::kNvls);
+  }
+#undef HZ_LAUNCH
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int hz_comm_barrier(HzComm* c, long long* stamps, cudaStream_t st) {
+  hz::barrier_kernel<<<1, 32, 0, st>>>(c->dev, stamps);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int hz_comm_error(HzComm* c) {
+  uint32_t e = 0;
+  cudaMemcpy(&e, c->local + 61440, 4, cudaMemcpyDeviceToHost);
+  return (int)e;
+}
+
+void hz_comm_destroy(HzComm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->dev.world; ++r)
+    if (c->imported[r] && c->dev.base[r]) cudaIpcCloseMemHandle(c->dev.base[r]);
+  if (c->local) cudaFree(c->local);
+  delete c;
+}
+
+}  // extern "C"

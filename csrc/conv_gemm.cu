@@ -1,0 +1,624 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolutions for NHWC bf16.
+//
+// Replaces every torchvision conv of ResNet-18 (data_parallel_train.py:198 — ATen CPU convs in the
+// reference) in forward, dgrad and wgrad:
+//
+//   igemm_kernel  (fwd, dgrad, dense GEMM):   D[128 x BLOCK_N] = sum over (tap, 64-channel block) A * B
+//       A : activation tile, K-major.  One 4-D TMA box (64 ch, BW, BH, BN) per (tap, channel block) is
+//           exactly a 128-row x 128-byte SWIZZLE_128B operand tile; padding comes for free from TMA
+//           out-of-bounds zero fill (negative / overflowing coordinates).  Stride-2 convs read four
+//           "parity views" of the input (strided tensor maps), so no im2col buffer ever exists.
+//       B : weights [Cout, R*S*Cin]: K-major for fwd, MN-major for dgrad (no transposed weight copy).
+//       D : fp32 in TMEM; epilogue tcgen05.ld -> bf16 -> smem -> coalesced stores, plus the BatchNorm
+//           partial sums (sum y, sum y^2 per channel) so BN statistics cost no extra pass.
+//       Stride-2 dgrad is 4 output-parity classes (blockIdx.z), each a stride-1 gather over its taps.
+//       Taps whose receptive field is entirely padding are dropped on the host (layer4's 1x1 maps use
+//       only the centre tap: 9x less work).
+//
+//   wgrad_kernel:  dW[Cout, tap, Cin] = sum over pixels dY^T * X_tap.  Both operands MN-major straight
+//       from their NHWC tensors (64-pixel TMA boxes), split-K over pixel blocks (blockIdx.z), fp32 result
+//       written / accumulated directly into the flat gradient bucket (no flatten copy).
+//
+// Warp roles (128 threads, one output tile per CTA): warp0/lane0 TMA producer, warp1/lane0 MMA issuer,
+// all four warps epilogue (each owns its 32 TMEM lanes).  4-stage smem ring, mbarrier full/empty pairs,
+// tcgen05.commit releases stages and signals the epilogue.
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "launchers.h"
+#include "tc05.cuh"
+
+namespace hz {
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;
+constexpr int kKBlock = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kTileM * 128;             // 16 KB
+constexpr int kMaxTaps = 9;
+
+struct TapList {
+  int n;
+  int bk[kMaxTaps];          // element offset of this tap along the weight's (r,s,c) axis
+  int8_t dh[kMaxTaps], dw[kMaxTaps], map[kMaxTaps];
+};
+
+struct AMaps {
+  CUtensorMap m[4];
+};
+
+struct IgemmParams {
+  TapList cls[4];
+  long long cls_out_off[4];
+  long long out_n_stride, out_h_stride, out_w_stride;   // elements
+  int num_classes, cblocks;
+  int BN, BH, BW, tiles_per_img;
+  int n_images;
+  int ncols;                 // valid output columns (Cout / Cin total)
+  __nv_bfloat16* out;
+  float* stats;              // [2*ncols] or null
+};
+
+template <int BLOCK_N>
+struct IgemmSmem {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kStagingLd = BLOCK_N + 8;                 // bf16 elements, conflict-free 16B rows
+  static constexpr int kStagingBytes = kTileM * kStagingLd * 2;
+  static constexpr int kBarOff = (kPipeBytes > kStagingBytes ? kPipeBytes : kStagingBytes);
+  static constexpr int kTotal = kBarOff + 128 + 1024;            // + barriers + alignment slack
+};
+
+template <int BLOCK_N, bool B_MN>
+__global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMaps amaps,
+                                                    const __grid_constant__ CUtensorMap bmap,
+                                                    const __grid_constant__ IgemmParams p) {
+  using S = IgemmSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y, cls = blockIdx.z;
+  const TapList& taps = p.cls[cls];
+  const int n0 = (p.BN == 1) ? mt / p.tiles_per_img : mt * p.BN;
+  const int h0 = (p.BN == 1) ? (mt % p.tiles_per_img) * p.BH : 0;
+  const int k_iters = taps.n * p.cblocks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) tc::prefetch_tmap(&amaps.m[i]);
+    tc::prefetch_tmap(&bmap);
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, BLOCK_N);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int it = 0;
+    for (int t = 0; t < taps.n; ++t) {
+      const CUtensorMap* am = &amaps.m[taps.map[t]];
+      const int cw = taps.dw[t], ch = h0 + taps.dh[t];
+      for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+        tc::tma_load_4d(sa, am, &full[s], cb * kKBlock, cw, ch, n0);
+        if (!B_MN) {
+          tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[t] + cb * kKBlock, nt * BLOCK_N);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tc::tma_load_2d(sb + j * 8192, &bmap, &full[s], taps.bk[t] + nt * BLOCK_N + j * 64, cb * kKBlock);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = tc::make_idesc(kTileM, BLOCK_N, false, B_MN);
+    for (int it = 0; it < k_iters; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      tc::mbar_wait(&full[s], ph);
+      tc::fence_after_sync();
+      const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+      const uint32_t sb = sa + kABytes;
+#pragma unroll
+      for (int k = 0; k < kKBlock / 16; ++k) {
+        const uint64_t da = tc::make_sdesc(sa + k * 32, 16, 1024);
+        const uint64_t db = B_MN ? tc::make_sdesc(sb + k * 2048, 8192, 1024)
+                                 : tc::make_sdesc(sb + k * 32, 16, 1024);
+        tc::umma_f16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+      }
+      tc::umma_commit(&empty[s]);
+    }
+    tc::umma_commit(tmem_full);
+  }
+  __syncwarp();
+
+  // ===================== epilogue (all 4 warps) =====================
+  __nv_bfloat16* staging = reinterpret_cast<__nv_bfloat16*>(smem);
+  const int row = warp * 32 + lane;
+  if (k_iters > 0) {
+    tc::mbar_wait(tmem_full, 0);
+    tc::fence_after_sync();
+#pragma unroll
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+      tc::tmem_ld_wait();
+      __nv_bfloat16* dst = staging + row * S::kStagingLd + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[j + i]);
+        st8(dst + j, pack8(f));
+      }
+    }
+  } else {
+    // a class with no taps (1x1 stride-2 dgrad, odd parities): the gradient is exactly zero
+    float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 8) st8(staging + row * S::kStagingLd + c0, pack8(z));
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+
+  // coalesced stores: BLOCK_N/8 16-byte vectors per row
+  constexpr int kVecPerRow = BLOCK_N / 8;
+  constexpr int kRowsPerPass = 128 / kVecPerRow;
+  const int vec = threadIdx.x % kVecPerRow;
+  for (int r0 = threadIdx.x / kVecPerRow; r0 < kTileM; r0 += kRowsPerPass) {
+    const int wi = r0 % p.BW;
+    const int hi = (r0 / p.BW) % p.BH;
+    const int ni = r0 / (p.BW * p.BH);
+    const int n = n0 + ni;
+    if (n >= p.n_images) continue;
+    const long long off = (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride +
+                          (long long)wi * p.out_w_stride + p.cls_out_off[cls] + nt * BLOCK_N + vec * 8;
+    st8(p.out + off, ld8(staging + r0 * S::kStagingLd + vec * 8));
+  }
+  if (p.stats != nullptr) {
+    // per-channel sum / sum of squares over this tile's rows (zero-filled OOB rows contribute 0)
+    constexpr int kParts = 128 / BLOCK_N;          // 2 for BLOCK_N=64, 1 for 128
+    const int col = threadIdx.x % BLOCK_N;
+    const int part = threadIdx.x / BLOCK_N;
+    if (part < kParts) {
+      float s = 0.f, q = 0.f;
+      const int rows = kTileM / kParts;
+      for (int r0 = part * rows; r0 < (part + 1) * rows; ++r0) {
+        const float v = __bfloat162float(staging[r0 * S::kStagingLd + col]);
+        s += v;
+        q += v * v;
+      }
+      atomicAdd(&p.stats[nt * BLOCK_N + col], s);
+      atomicAdd(&p.stats[p.ncols + nt * BLOCK_N + col], q);
+    }
+  }
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_d, BLOCK_N);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  TapList taps;                  // bk[] = output tap index
+  int KBN, KBH, kb_per_img;      // 64-pixel k-block box over dY
+  int kblocks, splits;
+  int n_tiles;                   // Cin / BLOCK_N
+  int Cout;
+  long long ld_out, tap_stride;  // dW row stride / per-tap column offset (elements)
+  int n_valid;                   // valid columns per tap (Cin, or 147 for the padded stem)
+  int accumulate;
+  float* out;
+};
+
+template <int BLOCK_N>
+struct WgradSmem {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOff + 128 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ CUtensorMap dymap,
+                                                    const __grid_constant__ AMaps xmaps,
+                                                    const __grid_constant__ WgradParams p) {
+  using S = WgradSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x / p.n_tiles, nt = blockIdx.x % p.n_tiles;
+  const int t = blockIdx.y;
+  const int per = (p.kblocks + p.splits - 1) / p.splits;
+  const int kb_lo = blockIdx.z * per;
+  const int kb_hi = min(kb_lo + per, p.kblocks);
+  const int k_iters = max(kb_hi - kb_lo, 0);
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&dymap);
+    for (int i = 0; i < 4; ++i) tc::prefetch_tmap(&xmaps.m[i]);
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) {
+    tc::tmem_alloc(tmem_slot, BLOCK_N);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    const CUtensorMap* xm = &xmaps.m[p.taps.map[t]];
+    for (int it = 0; it < k_iters; ++it) {
+      const int kb = kb_lo + it;
+      const int n0 = (p.KBN == 1) ? kb / p.kb_per_img : kb * p.KBN;
+      const int h0 = (p.KBN == 1) ? (kb % p.kb_per_img) * p.KBH : 0;
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      tc::mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* sa = smem + s * S::kStageBytes;
+      uint8_t* sb = sa + kABytes;
+      tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+      // A: dY^T, two 64-channel atoms (the second is zero-filled by TMA when Cout == 64)
+      tc::tma_load_4d(sa, &dymap, &full[s], mt * 128, 0, h0, n0);
+      tc::tma_load_4d(sa + 8192, &dymap, &full[s], mt * 128 + 64, 0, h0, n0);
+#pragma unroll
+      for (int j = 0; j < BLOCK_N / 64; ++j)
+        tc::tma_load_4d(sb + j * 8192, xm, &full[s], nt * BLOCK_N + j * 64, p.taps.dw[t], h0 + p.taps.dh[t], n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = tc::make_idesc(kTileM, BLOCK_N, true, true);
+    for (int it = 0; it < k_iters; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      tc::mbar_wait(&full[s], ph);
+      tc::fence_after_sync();
+      const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+      const uint32_t sb = sa + kABytes;
+#pragma unroll
+      for (int k = 0; k < kKBlock / 16; ++k) {
+        const uint64_t da = tc::make_sdesc(sa + k * 2048, 8192, 1024);
+        const uint64_t db = tc::make_sdesc(sb + k * 2048, 8192, 1024);
+        tc::umma_f16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+      }
+      tc::umma_commit(&empty[s]);
+    }
+    tc::umma_commit(tmem_full);
+  }
+  __syncwarp();
+
+  const int co = mt * 128 + warp * 32 + lane;
+  if (k_iters > 0) {
+    tc::mbar_wait(tmem_full, 0);
+    tc::fence_after_sync();
+    float* orow = p.out + (long long)co * p.ld_out + (long long)p.taps.bk[t] * p.tap_stride + nt * BLOCK_N;
+    const bool atomic = p.splits > 1;
+#pragma unroll
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+      tc::tmem_ld_wait();
+      if (co < p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = nt * BLOCK_N + c0 + j;
+          if (c < p.n_valid) {
+            const float v = __uint_as_float(r[j]);
+            if (atomic) atomicAdd(orow + c0 + j, v);
+            else orow[c0 + j] = (p.accumulate ? orow[c0 + j] : 0.f) + v;
+          }
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_d, BLOCK_N);
+}
+
+}  // namespace hz
+
+// ================================================================================================
+// host: tensor maps + launch
+// ================================================================================================
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 4-D bf16 tensor map over an NHWC tensor view: dims (C, W, H, N) with element strides (1, sw, sh, sn)
+bool make_map4(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sw, long long sh,
+               long long sn, int boxC, int boxW, int boxH, int boxN) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, (cuuint32_t)boxN};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fprintf(stderr, "[hz conv] cuTensorMapEncodeTiled(4d) failed: %d\n", (int)r);
+  return r == CUDA_SUCCESS;
+}
+
+bool make_map2(CUtensorMap* m, const void* base, long long inner, long long rows, long long row_stride,
+               int box_inner, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_stride * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fprintf(stderr, "[hz conv] cuTensorMapEncodeTiled(2d) failed: %d\n", (int)r);
+  return r == CUDA_SUCCESS;
+}
+
+struct Tile {
+  int BN, BH, BW, per_img, tiles;
+};
+// rows-per-tile box over an [N, H, W] pixel lattice
+bool pick_tile(int rows, int N, int H, int W, Tile* t) {
+  if (H * W >= rows) {
+    if (W > rows || rows % W) return false;
+    t->BN = 1; t->BW = W; t->BH = rows / W;
+    if (H % t->BH) return false;
+    t->per_img = H / t->BH;
+    t->tiles = N * t->per_img;
+  } else {
+    if (rows % (H * W)) return false;
+    t->BN = rows / (H * W); t->BH = H; t->BW = W; t->per_img = 1;
+    t->tiles = (N + t->BN - 1) / t->BN;
+  }
+  return t->BW <= 256 && t->BH <= 256 && t->BN <= 256;
+}
+
+// does offset d hit any valid index: exists i in [0,n_out) with 0 <= i + d < n_in
+inline bool tap_hits(int d, int n_out, int n_in) { return d < n_in && d + n_out - 1 >= 0 && d > -n_out - n_in; }
+
+// x maps for a conv input: plain view (stride 1) or 4 parity views (stride 2)
+bool make_x_maps(hz::AMaps* am, const void* x, int N, int H, int W, int C, int stride, const Tile& t) {
+  if (stride == 1) {
+    if (!make_map4(&am->m[0], x, C, W, H, N, C, (long long)W * C, (long long)H * W * C, 64, t.BW, t.BH, t.BN))
+      return false;
+    for (int i = 1; i < 4; ++i) am->m[i] = am->m[0];
+    return true;
+  }
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      const char* base = (const char*)x + ((long long)ph * W + pw) * C * 2;
+      if (!make_map4(&am->m[ph * 2 + pw], base, C, W / 2, H / 2, N, 2LL * C, 2LL * W * C, (long long)H * W * C,
+                     64, t.BW, t.BH, t.BN))
+        return false;
+    }
+  return true;
+}
+
+// taps of a conv reading its input: coordinate offsets in (parity-)view space
+void input_taps(hz::TapList* tl, int R, int S, int stride, int pad, int Ho, int Wo, int H, int W, int Cin,
+                bool bk_is_tap_index) {
+  tl->n = 0;
+  const int Hv = stride == 1 ? H : H / 2, Wv = stride == 1 ? W : W / 2;
+  for (int r = 0; r < R; ++r)
+    for (int s = 0; s < S; ++s) {
+      int dh, dw, map = 0;
+      if (stride == 1) { dh = r - pad; dw = s - pad; }
+      else {
+        const int th = r - pad, tw = s - pad;
+        const int ph = th & 1, pw = tw & 1;
+        dh = (th - ph) / 2; dw = (tw - pw) / 2;
+        map = ph * 2 + pw;
+      }
+      if (!tap_hits(dh, Ho, Hv) || !tap_hits(dw, Wo, Wv)) continue;
+      const int i = tl->n++;
+      tl->dh[i] = (int8_t)dh; tl->dw[i] = (int8_t)dw; tl->map[i] = (int8_t)map;
+      tl->bk[i] = bk_is_tap_index ? (r * S + s) : (r * S + s) * Cin;
+    }
+}
+
+template <typename K>
+bool set_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad) {
+  if (Cin % 64 || Cout % 64) return 0;
+  if (!((R == 3 && pad == 1) || (R == 1 && pad == 0))) return 0;
+  if (stride != 1 && stride != 2) return 0;
+  if (stride == 2 && ((H | W) & 1)) return 0;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - R) / stride + 1;
+  Tile t;
+  if (!pick_tile(128, N, Ho, Wo, &t)) return 0;
+  if (!pick_tile(64, N, Ho, Wo, &t)) return 0;
+  if (!pick_tile(128, N, H, W, &t) && stride == 1) return 0;
+  return get_encode() != nullptr;
+}
+
+// y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w[Cout,R,S,Cin]); stats (2*Cout fp32, zeroed here) optional
+int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int N, int H, int W, int Cin, int Cout,
+                int R, int stride, int pad, cudaStream_t st) {
+  const int S_ = R;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
+  Tile t;
+  if (!pick_tile(128, N, Ho, Wo, &t)) return -10;
+  hz::AMaps am;
+  if (!make_x_maps(&am, x, N, H, W, Cin, stride, t)) return -11;
+  constexpr int BLOCK_N = 64;
+  CUtensorMap bm;
+  if (!make_map2(&bm, w, (long long)R * S_ * Cin, Cout, (long long)R * S_ * Cin, 64, BLOCK_N)) return -12;
+  hz::IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  input_taps(&p.cls[0], R, S_, stride, pad, Ho, Wo, H, W, Cin, false);
+  p.num_classes = 1;
+  p.cblocks = Cin / 64;
+  p.BN = t.BN; p.BH = t.BH; p.BW = t.BW; p.tiles_per_img = t.per_img;
+  p.n_images = N;
+  p.out_n_stride = (long long)Ho * Wo * Cout; p.out_h_stride = (long long)Wo * Cout; p.out_w_stride = Cout;
+  p.ncols = Cout;
+  p.out = (__nv_bfloat16*)y;
+  p.stats = stats;
+  if (stats) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, st);
+  using SM = hz::IgemmSmem<BLOCK_N>;
+  static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, false>, SM::kTotal);
+  (void)attr;
+  dim3 grid(t.tiles, Cout / BLOCK_N, 1);
+  hz::igemm_kernel<BLOCK_N, false><<<grid, 128, SM::kTotal, st>>>(am, bm, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w)
+int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R,
+                  int stride, int pad, cudaStream_t st) {
+  const int S_ = R;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
+  // output lattice per class: stride 1 -> (H,W); stride 2 -> (H/2,W/2) == (Ho,Wo)
+  const int Lh = stride == 1 ? H : H / 2, Lw = stride == 1 ? W : W / 2;
+  if (stride == 2 && (Lh != Ho || Lw != Wo)) return -13;
+  Tile t;
+  if (!pick_tile(128, N, Lh, Lw, &t)) return -10;
+  hz::AMaps am;
+  if (!make_map4(&am.m[0], dy, Cout, Wo, Ho, N, Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout, 64, t.BW,
+                 t.BH, t.BN))
+    return -11;
+  for (int i = 1; i < 4; ++i) am.m[i] = am.m[0];
+  constexpr int BLOCK_N = 64;
+  CUtensorMap bm;   // MN-major B: rows = Cout (K), inner = (r,s,ci)
+  if (!make_map2(&bm, w, (long long)R * S_ * Cin, Cout, (long long)R * S_ * Cin, 64, 64)) return -12;
+  hz::IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_classes = stride == 1 ? 1 : 4;
+  for (int c = 0; c < p.num_classes; ++c) {
+    const int ph = c >> 1, pw = c & 1;
+    hz::TapList& tl = p.cls[c];
+    tl.n = 0;
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S_; ++s) {
+        int dh, dw;
+        if (stride == 1) { dh = pad - r; dw = pad - s; }
+        else {
+          if (((ph + pad - r) & 1) || ((pw + pad - s) & 1)) continue;
+          dh = (ph + pad - r) / 2; dw = (pw + pad - s) / 2;
+        }
+        if (!tap_hits(dh, Lh, Ho) || !tap_hits(dw, Lw, Wo)) continue;
+        const int i = tl.n++;
+        tl.dh[i] = (int8_t)dh; tl.dw[i] = (int8_t)dw; tl.map[i] = 0;
+        tl.bk[i] = (r * S_ + s) * Cin;
+      }
+    p.cls_out_off[c] = stride == 1 ? 0 : ((long long)ph * W + pw) * Cin;
+  }
+  p.cblocks = Cout / 64;
+  p.BN = t.BN; p.BH = t.BH; p.BW = t.BW; p.tiles_per_img = t.per_img;
+  p.n_images = N;
+  p.out_n_stride = (long long)H * W * Cin;
+  p.out_h_stride = (long long)stride * W * Cin;
+  p.out_w_stride = (long long)stride * Cin;
+  p.ncols = Cin;
+  p.out = (__nv_bfloat16*)dx;
+  p.stats = nullptr;
+  using SM = hz::IgemmSmem<BLOCK_N>;
+  static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, true>, SM::kTotal);
+  (void)attr;
+  dim3 grid(t.tiles, Cin / BLOCK_N, p.num_classes);
+  hz::igemm_kernel<BLOCK_N, true><<<grid, 128, SM::kTotal, st>>>(am, bm, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// dw[Cout, R*S*Cin (ld_out)] (+)= dy^T * x_taps.   ld_out / n_valid allow the padded stem (Cin=192 -> 147)
+int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,
+                  int stride, int pad, int accumulate, long long ld_out, int n_valid, cudaStream_t st) {
+  const int S_ = R;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
+  Tile t;
+  if (!pick_tile(64, N, Ho, Wo, &t)) return -10;
+  CUtensorMap dym;
+  if (!make_map4(&dym, dy, Cout, Wo, Ho, N, Cout, (long long)Wo * Cout, (long long)Ho * Wo * Cout, 64, t.BW, t.BH,
+                 t.BN))
+    return -11;
+  hz::AMaps xm;
+  if (!make_x_maps(&xm, x, N, H, W, Cin, stride, t)) return -11;
+  hz::WgradParams p;
+  memset(&p, 0, sizeof(p));
+  input_taps(&p.taps, R, S_, stride, pad, Ho, Wo, H, W, Cin, true);
+  if (p.taps.n == 0) return 0;
+  constexpr int BLOCK_N = 64;
+  p.KBN = t.BN; p.KBH = t.BH; p.kb_per_img = t.per_img;
+  p.kblocks = t.tiles;
+  p.n_tiles = Cin / BLOCK_N;
+  const int m_tiles = (Cout + 127) / 128;
+  const int ctas = m_tiles * p.n_tiles * p.taps.n;
+  int splits = (120 + ctas - 1) / ctas;
+  if (splits > p.kblocks) splits = p.kblocks;
+  if (splits > 32) splits = 32;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  p.Cout = Cout;
+  p.ld_out = ld_out > 0 ? ld_out : (long long)R * S_ * Cin;
+  p.tap_stride = Cin;
+  p.n_valid = n_valid > 0 ? n_valid : Cin;
+  p.accumulate = accumulate;
+  p.out = dw;
+  if (splits > 1 && !accumulate) {
+    // split-K accumulates with atomics: clear exactly the region this conv owns (rows are ld_out apart)
+    if (p.ld_out == (long long)R * S_ * Cin || R == 1)
+      cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * p.ld_out, st);
+    else
+      return -14;
+  }
+  using SM = hz::WgradSmem<BLOCK_N>;
+  static bool attr = set_smem(hz::wgrad_kernel<BLOCK_N>, SM::kTotal);
+  (void)attr;
+  dim3 grid(m_tiles * p.n_tiles, p.taps.n, splits);
+  hz::wgrad_kernel<BLOCK_N><<<grid, 128, SM::kTotal, st>>>(dym, xm, p);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,623 @@
+// Memory-bound sm_100a kernels of the ResNet-18 training step:
+//   BatchNorm(train)+residual+ReLU forward / backward, channel statistics, 3x3/2 max-pool,
+//   stem input normalisation + im2col, fused avgpool+FC+softmax-CE head (fwd+bwd), flat fused Adam,
+//   gradient-divergence reduction, on-device step statistics.
+// Activations are NHWC bf16 ([M = N*H*W, C] row-major), 16-byte vectorised (8 channels / thread).
+// Reference sites: torchvision BatchNorm2d/ReLU/MaxPool2d inside resnet18 (data_parallel_train.py:198),
+// CrossEntropyLoss + argmax accuracy (:114-115,:128-130), optim.Adam.step (:122), grad divergence (:132-145).
+#include "common.cuh"
+#include "launchers.h"
+
+namespace hz {
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reductions over rows: block = (C/8 channel-vectors) x (256/(C/8) row lanes)
+// ------------------------------------------------------------------------------------------------
+template <bool kBwd>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(
+    const __nv_bfloat16* __restrict__ a,      // fwd: y_raw           bwd: dout
+    const __nv_bfloat16* __restrict__ outp,   // bwd: bn output (ReLU mask), may be null
+    const __nv_bfloat16* __restrict__ yraw,   // bwd: y_raw
+    const float* __restrict__ mean, const float* __restrict__ invstd,
+    float* __restrict__ sums,                 // [2C], pre-zeroed: fwd (Σy, Σy²)  bwd (Σg, Σg·x̂)
+    int M, int C, int relu) {
+  extern __shared__ float red[];              // [rlanes][nvec][16]
+  const int nvec = C >> 3;
+  const int rlanes = 256 / nvec;
+  const int vec = threadIdx.x % nvec, rl = threadIdx.x / nvec;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  float mu[8], is[8];
+  if (kBwd) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mu[i] = mean[vec * 8 + i]; is[i] = invstd[vec * 8 + i]; }
+  }
+  for (int r = blockIdx.x * rlanes + rl; r < M; r += gridDim.x * rlanes) {
+    const size_t off = (size_t)r * C + vec * 8;
+    float f[8];
+    unpack8(ld8(a + off), f);
+    if (!kBwd) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+    } else {
+      float y[8];
+      unpack8(ld8(yraw + off), y);
+      if (relu) {
+        float o[8];
+        unpack8(ld8(outp + off), o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = o[i] > 0.f ? f[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * (y[i] - mu[i]) * is[i]; }
+    }
+  }
+  float* mine = red + ((size_t)rl * nvec + vec) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
+  __syncthreads();
+  // nvec*16 outputs, each summed over rlanes
+  for (int o = threadIdx.x; o < nvec * 16; o += 256) {
+    const int v = o >> 4, j = o & 15;
+    float t = 0.f;
+    for (int k = 0; k < rlanes; ++k) t += red[((size_t)k * nvec + v) * 16 + j];
+    const int c = v * 8 + (j & 7);
+    atomicAdd(&sums[(j >> 3) * C + c], t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN apply (+ residual) (+ ReLU); every CTA derives scale/shift from the sums in smem,
+// CTA 0 publishes mean / invstd / running statistics.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(
+    const __nv_bfloat16* __restrict__ y, const float* __restrict__ sums,
+    const float* __restrict__ gamma, const float* __restrict__ beta,
+    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+    float* __restrict__ mean_out, float* __restrict__ invstd_out,
+    float* __restrict__ rmean, float* __restrict__ rvar,
+    int M, int C, float eps, float momentum, int relu, int training) {
+  extern __shared__ float sm[];   // scale[C], shift[C]
+  float* scale = sm;
+  float* shift = sm + C;
+  const float inv_cnt = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mu, var;
+    if (training) {
+      mu = sums[c] * inv_cnt;
+      var = fmaxf(sums[C + c] * inv_cnt - mu * mu, 0.f);
+    } else {
+      mu = rmean[c];
+      var = rvar[c];
+    }
+    const float is = rsqrtf(var + eps);
+    const float g = gamma[c];
+    scale[c] = g * is;
+    shift[c] = beta[c] - mu * g * is;
+    if (blockIdx.x == 0) {
+      mean_out[c] = mu;
+      invstd_out[c] = is;
+      if (training && rmean != nullptr) {
+        const float unb = var * ((float)M / (float)max(M - 1, 1));
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * mu;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * unb;
+      }
+    }
+  }
+  __syncthreads();
+  const int nvec = C >> 3;
+  const size_t total = (size_t)M * nvec;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % nvec) * 8;
+    float f[8];
+    unpack8(ld8(y + v * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = f[i] * scale[c0 + i] + shift[c0 + i];
+    if (residual != nullptr) {
+      float r[8];
+      unpack8(ld8(residual + v * 8), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += r[i];
+    }
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    st8(out + v * 8, pack8(f));
+  }
+}
+
+// dy_raw = γ·invstd·(g − Σg/M − x̂·Σ(g·x̂)/M), g = dout·[out>0];  dres = g;  CTA0: dγ, dβ
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ outp,
+    const __nv_bfloat16* __restrict__ yraw, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ sums, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int acc_gamma, int acc_beta,
+    int M, int C, int relu) {
+  extern __shared__ float sm[];   // k[C], a[C], b[C], mu[C], is[C]
+  float *k = sm, *a = sm + C, *b = sm + 2 * C, *mu = sm + 3 * C, *is = sm + 4 * C;
+  const float inv_cnt = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float i_s = invstd[c];
+    k[c] = gamma[c] * i_s;
+    a[c] = sums[c] * inv_cnt;
+    b[c] = sums[C + c] * inv_cnt;
+    mu[c] = mean[c];
+    is[c] = i_s;
+    if (blockIdx.x == 0) {
+      if (dgamma != nullptr) dgamma[c] = (acc_gamma ? dgamma[c] : 0.f) + sums[C + c];
+      if (dbeta != nullptr) dbeta[c] = (acc_beta ? dbeta[c] : 0.f) + sums[c];
+    }
+  }
+  __syncthreads();
+  const int nvec = C >> 3;
+  const size_t total = (size_t)M * nvec;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % nvec) * 8;
+    float g[8], y[8];
+    unpack8(ld8(dout + v * 8), g);
+    unpack8(ld8(yraw + v * 8), y);
+    if (relu) {
+      float o[8];
+      unpack8(ld8(outp + v * 8), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+    }
+    if (dres != nullptr) st8(dres + v * 8, pack8(g));
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      const float xh = (y[i] - mu[c]) * is[c];
+      d[i] = k[c] * (g[i] - a[c] - xh * b[c]);
+    }
+    st8(dy + v * 8, pack8(d));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 3x3 / stride 2 / pad 1, NHWC; backward recomputes the (first) arg-max: no index tensor
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                          __nv_bfloat16* __restrict__ y, int N, int H,
+                                                          int W, int C, int Ho, int Wo) {
+  const int nvec = C >> 3;
+  const size_t total = (size_t)N * Ho * Wo * nvec;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(v % nvec);
+    size_t p = v / nvec;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      const int h = ho * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int w = wo * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(ld8(x + (((size_t)n * H + h) * W + w) * C + cv * 8), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+      }
+    }
+    st8(y + v * 8, pack8(m));
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const __nv_bfloat16* __restrict__ x,
+                                                          const __nv_bfloat16* __restrict__ y,
+                                                          __nv_bfloat16* __restrict__ dx, int N, int H,
+                                                          int W, int C, int Ho, int Wo) {
+  const int nvec = C >> 3;
+  const size_t total = (size_t)N * H * W * nvec;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(v % nvec);
+    size_t p = v / nvec;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    float xv[8], acc[8];
+    unpack8(ld8(x + v * 8), xv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // windows (ho,wo) that contain (h,w): ho in {(h+1)/2 - 1 .. (h+1)/2} intersect valid
+    for (int ho = (h + 1) / 2 - ((h + 1) % 2 == 0 ? 1 : 0); ho <= (h + 1) / 2; ++ho) {
+      if (ho < 0 || ho >= Ho) continue;
+      for (int wo = (w + 1) / 2 - ((w + 1) % 2 == 0 ? 1 : 0); wo <= (w + 1) / 2; ++wo) {
+        if (wo < 0 || wo >= Wo) continue;
+        const size_t oo = (((size_t)n * Ho + ho) * Wo + wo) * C + cv * 8;
+        float yv[8], gv[8];
+        unpack8(ld8(y + oo), yv);
+        unpack8(ld8(dy + oo), gv);
+        // is (h,w) the FIRST position (row-major scan) in this window attaining the max?
+        bool hit[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hit[i] = (xv[i] == yv[i]);
+        for (int r = 0; r < 3; ++r) {
+          const int hh = ho * 2 - 1 + r;
+          if (hh < 0 || hh >= H) continue;
+          for (int s = 0; s < 3; ++s) {
+            const int ww = wo * 2 - 1 + s;
+            if (ww < 0 || ww >= W) continue;
+            if (hh > h || (hh == h && ww >= w)) continue;   // only earlier positions
+            float e[8];
+            unpack8(ld8(x + (((size_t)n * H + hh) * W + ww) * C + cv * 8), e);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hit[i] = hit[i] && !(e[i] == yv[i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += hit[i] ? gv[i] : 0.f;
+      }
+    }
+    st8(dx + v * 8, pack8(acc));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: uint8 NHWC -> normalised bf16 NHWC;  small-Cin im2col -> A[M, Kp] (K = (r,s,c), zero padded)
+// ------------------------------------------------------------------------------------------------
+__global__ void u8_normalize_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                    size_t n, float mean, float inv_std) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(((float)in[i] * (1.f / 255.f) - mean) * inv_std);
+}
+
+__global__ void __launch_bounds__(256) im2col_small_cin_kernel(
+    const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A, int N, int H, int W, int Cin,
+    int R, int S, int stride, int pad, int Ho, int Wo, int K, int Kp) {
+  const int kvec = Kp >> 3;
+  const size_t total = (size_t)N * Ho * Wo * kvec;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int kv = (int)(v % kvec);
+    size_t m = v / kvec;
+    const int wo = (int)(m % Wo);
+    size_t t = m / Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kv * 8 + i;
+      float val = 0.f;
+      if (k < K) {
+        const int c = k % Cin;
+        const int rs = k / Cin;
+        const int s = rs % S, r = rs / S;
+        const int h = ho * stride - pad + r, w = wo * stride - pad + s;
+        if (h >= 0 && h < H && w >= 0 && w < W)
+          val = __bfloat162float(x[(((size_t)n * H + h) * W + w) * Cin + c]);
+      }
+      f[i] = val;
+    }
+    st8(A + v * 8, pack8(f));
+  }
+}
+
+// rows of length K (bf16) -> rows of length Kp (zero padded): packs conv1's [64,147] weights for TMA
+__global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                int rows, int K, int Kp) {
+  const int total = rows * Kp;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / Kp, k = i % Kp;
+    out[i] = k < K ? in[(size_t)r * K + k] : __float2bfloat16_rn(0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: global-avg-pool -> FC -> softmax-CE (+accuracy) forward AND backward.
+//   kernel A: one CTA per sample (pooled, logits, loss, correct, dlogits, dfeat)
+//   kernel B: dW[k,c] = Σ_n dlogits[n,k]·pooled[n,c], db[k] = Σ_n dlogits[n,k]
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadMaxK = 64;
+
+__global__ void __launch_bounds__(128) head_sample_kernel(
+    const __nv_bfloat16* __restrict__ feat, const float* __restrict__ Wt, const float* __restrict__ bias,
+    const int64_t* __restrict__ labels, float* __restrict__ pooled, float* __restrict__ dlogits,
+    float* __restrict__ logits_out, __nv_bfloat16* __restrict__ dfeat,
+    float* __restrict__ loss_out, float* __restrict__ correct_out, int N, int C, int HW, int K,
+    int n_valid, float loss_scale) {
+  extern __shared__ float sm[];            // pooled[C], logit[kHeadMaxK], dl[kHeadMaxK]
+  float* pl = sm;
+  float* lg = sm + C;
+  float* dl = lg + kHeadMaxK;
+  const int n = blockIdx.x;
+  const float inv_hw = 1.f / (float)HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += __bfloat162float(feat[((size_t)n * HW + p) * C + c]);
+    s *= inv_hw;
+    pl[c] = s;
+    pooled[(size_t)n * C + c] = s;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int k = warp; k < K; k += nwarp) {
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += pl[c] * Wt[(size_t)k * C + c];
+    s = warp_sum(s);
+    if (lane == 0) lg[k] = (k < n_valid) ? s + (bias ? bias[k] : 0.f) : -INFINITY;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    int amax = 0;
+    for (int k = lane; k < K; k += 32) mx = fmaxf(mx, lg[k]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int k = lane; k < K; k += 32) se += __expf(lg[k] - mx);
+    se = warp_sum(se);
+    const float lse = mx + __logf(se);
+    const int lab = (int)labels[n];
+    // first arg-max (torch.argmax tie-break is irrelevant for real data; pick the lowest index)
+    int best = K;
+    for (int k = lane; k < K; k += 32) if (lg[k] == mx) best = min(best, k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    amax = best;
+    for (int k = lane; k < K; k += 32) {
+      const float p = __expf(lg[k] - lse);
+      const float d = (p - (k == lab ? 1.f : 0.f)) * (loss_scale / (float)N);
+      dl[k] = d;
+      dlogits[(size_t)n * K + k] = d;
+      if (logits_out) logits_out[(size_t)n * K + k] = lg[k];
+    }
+    if (lane == 0) {
+      atomicAdd(loss_out, (lse - lg[lab]) * (loss_scale / (float)N));
+      if (amax == lab) atomicAdd(correct_out, 1.f);
+    }
+  }
+  __syncthreads();
+  if (dfeat != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < n_valid; ++k) s += dl[k] * Wt[(size_t)k * C + c];
+      const __nv_bfloat16 g = __float2bfloat16_rn(s * inv_hw);
+      for (int p = 0; p < HW; ++p) dfeat[((size_t)n * HW + p) * C + c] = g;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict__ pooled,
+                                                         const float* __restrict__ dlogits,
+                                                         float* __restrict__ dW, float* __restrict__ db,
+                                                         int N, int C, int K, int accumulate) {
+  const int k = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dlogits[(size_t)n * K + k] * pooled[(size_t)n * C + c];
+    const size_t o = (size_t)k * C + c;
+    dW[o] = (accumulate ? dW[o] : 0.f) + s;
+  }
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dlogits[(size_t)n * K + k];
+    db[k] = (accumulate ? db[k] : 0.f) + s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat fused Adam (fp32 master + moments, bf16 shadow refresh)  — torch.optim.Adam semantics
+// ------------------------------------------------------------------------------------------------
+__global__ void bump_step_kernel(float* step) { step[0] += 1.f; }
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   __nv_bfloat16* __restrict__ shadow,
+                                                   const float* __restrict__ step, size_t n, float lr,
+                                                   float b1, float b2, float eps, float gscale) {
+  const float t = step[0];
+  const float bc1 = 1.f - __powf(b1, t), bc2 = 1.f - __powf(b2, t);
+  const float step_size = lr / bc1;
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const size_t nv = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; float* G = &gg.x; float* Mo = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = G[j] * gscale;
+      Mo[j] = b1 * Mo[j] + (1.f - b1) * gr;
+      V[j] = b2 * V[j] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(V[j]) * inv_sqrt_bc2 + eps;
+      P[j] -= step_size * Mo[j] / denom;
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow != nullptr) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(shadow)[i] = pk;
+    }
+  }
+}
+
+// Σ (g − prev)², prev ← g      (out pre-zeroed)
+__global__ void __launch_bounds__(256) grad_diff_kernel(const float* __restrict__ g,
+                                                        float* __restrict__ prev,
+                                                        float* __restrict__ out, size_t n) {
+  __shared__ float wsum[8];
+  float acc = 0.f;
+  const size_t nv = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(g)[i];
+    const float4 b = reinterpret_cast<float4*>(prev)[i];
+    const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+    acc += dx * dx + dy * dy + dz * dz + dw * dw;
+    reinterpret_cast<float4*>(prev)[i] = a;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = wsum[threadIdx.x];
+    t += __shfl_xor_sync(0xffu, t, 4);
+    t += __shfl_xor_sync(0xffu, t, 2);
+    t += __shfl_xor_sync(0xffu, t, 1);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+
+// stats[0..5] += (loss, correct, batch, sqrt(diff)*has_prev, has_prev, 1); has_prev = 1
+__global__ void stats_update_kernel(float* stats, float* has_prev, const float* loss,
+                                    const float* correct, float batch, const float* diff_sq) {
+  stats[0] += loss[0];
+  stats[1] += correct[0];
+  stats[2] += batch;
+  stats[5] += 1.f;
+  if (diff_sq != nullptr) {
+    const float hp = has_prev[0];
+    stats[3] += sqrtf(diff_sq[0]) * hp;
+    stats[4] += hp;
+    has_prev[0] = 1.f;
+  }
+}
+
+}  // namespace hz
+
+// ================================================================================================
+// launchers (plain C++ interface, no torch headers)
+// ================================================================================================
+namespace {
+inline int grid_for(size_t work_items, int block, int cap = 148 * 8) {
+  size_t g = (work_items + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > (size_t)cap) g = cap;
+  return (int)g;
+}
+inline int reduce_grid(int M, int C) {
+  const int rlanes = 256 / (C / 8);
+  int g = (M + rlanes - 1) / rlanes;
+  g = (g + 3) / 4;                       // >= 4 rows per lane
+  if (g < 1) g = 1;
+  if (g > 148 * 2) g = 148 * 2;
+  return g;
+}
+}  // namespace
+
+extern "C" {
+
+int hz_channel_ok(int C) {
+  if (C < 8 || C > 2048 || (C & 7)) return 0;
+  const int nvec = C >> 3;
+  return (nvec & (nvec - 1)) == 0 && nvec <= 256;
+}
+
+void hz_channel_sums(const void* y, float* sums, int M, int C, cudaStream_t st) {
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+  const size_t smem = sizeof(float) * 256 * 16;
+  hz::channel_reduce_kernel<false><<<reduce_grid(M, C), 256, smem, st>>>(
+      (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0);
+}
+
+void hz_bn_act_fwd(const void* y, const float* sums, const float* gamma, const float* beta,
+                   const void* residual, void* out, float* mean, float* invstd, float* rmean,
+                   float* rvar, int M, int C, float eps, float momentum, int relu, int training,
+                   cudaStream_t st) {
+  const size_t smem = sizeof(float) * 2 * C;
+  hz::bn_act_fwd_kernel<<<grid_for((size_t)M * (C / 8), 256, 148 * 4), 256, smem, st>>>(
+      (const __nv_bfloat16*)y, sums, gamma, beta, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out,
+      mean, invstd, rmean, rvar, M, C, eps, momentum, relu, training);
+}
+
+void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const float* mean,
+                   const float* invstd, const float* gamma, float* sums_scratch, void* dy, void* dres,
+                   float* dgamma, float* dbeta, int acc_gamma, int acc_beta, int M, int C, int relu,
+                   cudaStream_t st) {
+  cudaMemsetAsync(sums_scratch, 0, sizeof(float) * 2 * C, st);
+  const size_t smem_r = sizeof(float) * 256 * 16;
+  hz::channel_reduce_kernel<true><<<reduce_grid(M, C), 256, smem_r, st>>>(
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
+      sums_scratch, M, C, relu);
+  const size_t smem = sizeof(float) * 5 * C;
+  hz::bn_act_bwd_apply_kernel<<<grid_for((size_t)M * (C / 8), 256, 148 * 4), 256, smem, st>>>(
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
+      gamma, sums_scratch, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta, acc_gamma, acc_beta,
+      M, C, relu);
+}
+
+void hz_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  hz::maxpool_fwd_kernel<<<grid_for((size_t)N * Ho * Wo * (C / 8), 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, Ho, Wo);
+}
+
+void hz_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H, int W, int C,
+                    cudaStream_t st) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  hz::maxpool_bwd_kernel<<<grid_for((size_t)N * H * W * (C / 8), 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, N,
+      H, W, C, Ho, Wo);
+}
+
+void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std, cudaStream_t st) {
+  hz::u8_normalize_kernel<<<grid_for(n, 256), 256, 0, st>>>((const uint8_t*)in, (__nv_bfloat16*)out, n,
+                                                             mean, 1.f / std);
+}
+
+void hz_im2col_small(const void* x, void* A, int N, int H, int W, int Cin, int R, int S, int stride,
+                     int pad, int Ho, int Wo, int Kp, cudaStream_t st) {
+  hz::im2col_small_cin_kernel<<<grid_for((size_t)N * Ho * Wo * (Kp / 8), 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W, Cin, R, S, stride, pad, Ho, Wo, R * S * Cin,
+      Kp);
+}
+
+void hz_pad_rows(const void* in, void* out, int rows, int K, int Kp, cudaStream_t st) {
+  hz::pad_rows_kernel<<<grid_for((size_t)rows * Kp, 256), 256, 0, st>>>(
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, K, Kp);
+}
+
+void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const int64_t* labels,
+                     float* pooled, float* dlogits, float* logits, void* dfeat, float* loss,
+                     float* correct, float* dW, float* db, int N, int C, int HW, int K, int n_valid,
+                     float loss_scale, int accumulate, cudaStream_t st) {
+  cudaMemsetAsync(loss, 0, sizeof(float), st);
+  cudaMemsetAsync(correct, 0, sizeof(float), st);
+  const size_t smem = sizeof(float) * (C + 2 * hz::kHeadMaxK);
+  hz::head_sample_kernel<<<N, 128, smem, st>>>((const __nv_bfloat16*)feat, W, bias, labels, pooled,
+                                               dlogits, logits, (__nv_bfloat16*)dfeat, loss, correct, N,
+                                               C, HW, K, n_valid, loss_scale);
+  dim3 grid((C + 127) / 128, K);
+  hz::head_wgrad_kernel<<<grid, 128, 0, st>>>(pooled, dlogits, dW, db, N, C, K, accumulate);
+}
+
+void hz_adam(float* p, const float* g, float* m, float* v, void* shadow, float* step, size_t n,
+             float lr, float b1, float b2, float eps, float gscale, cudaStream_t st) {
+  hz::bump_step_kernel<<<1, 1, 0, st>>>(step);
+  hz::adam_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow,
+                                                                  step, n, lr, b1, b2, eps, gscale);
+}
+
+void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st) {
+  cudaMemsetAsync(out, 0, sizeof(float), st);
+  hz::grad_diff_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, st>>>(g, prev, out, n);
+}
+
+void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct,
+                     float batch, const float* diff_sq, cudaStream_t st) {
+  hz::stats_update_kernel<<<1, 1, 0, st>>>(stats, has_prev, loss, correct, batch, diff_sq);
+}
+
+}  // extern "C"

