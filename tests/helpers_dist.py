@@ -1,0 +1,156 @@
+"""Workers for the multi-process CPU (gloo) tests; importable by spawned children."""
+import os
+import sys
+import traceback
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _init(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+
+
+def _batch(n=8, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 3, 32, 32, generator=g).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (n,), generator=g)
+    return x, y
+
+
+def run(fn, world, port, out_dir):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_entry, args=(fn, r, world, port, out_dir)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    codes = [p.exitcode for p in procs]
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+    errs = [open(os.path.join(out_dir, f)).read() for f in sorted(os.listdir(out_dir)) if f.startswith("err")]
+    assert codes == [0] * world, f"exit codes {codes}\n" + "\n".join(errs)
+
+
+def _entry(fn, rank, world, port, out_dir):
+    try:
+        _init(rank, world, port)
+        globals()[fn](rank, world, out_dir)
+        dist.barrier()
+        dist.destroy_process_group()
+    except BaseException as e:  # noqa: BLE001
+        with open(os.path.join(out_dir, f"err{rank}.txt"), "w") as fh:
+            fh.write("".join(traceback.format_exception(type(e), e, e.__traceback__)))
+        os._exit(1)
+
+
+# ------------------------------------------------------------------------------------------------
+def dp_equivalence(rank, world, out_dir):
+    """DP(W) gradient == average over ranks of per-shard gradients (per-rank BN, like DDP)."""
+    from horizonml_b200 import ops
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.resnet import resnet18
+    from horizonml_b200.parallel.comm import TorchDistAllReduce
+    from horizonml_b200.parallel.dp import GradReducer
+    ops.set_backend("torch")
+    x, y = _batch(8 * world)
+    model = resnet18(10, seed=5).train()
+    flat = FlatParams(list(model.named_parameters()), "cpu", torch.float32, bucket_cap_mb=8.0)
+    red = GradReducer(flat, TorchDistAllReduce(), overlap=False)
+    assert len(flat.buckets) >= 3
+    xs, ys = x[rank * 8:(rank + 1) * 8], y[rank * 8:(rank + 1) * 8]
+    flat.begin_step(); red.begin_step()
+    model.forward_loss(xs.contiguous(memory_format=torch.channels_last), ys)[0].backward()
+    red.finish()
+    got = flat.grad.clone()
+    # oracle: every shard's gradient computed locally, then averaged
+    ref = torch.zeros_like(got)
+    m2 = resnet18(10, seed=5).train()
+    f2 = FlatParams(list(m2.named_parameters()), "cpu", torch.float32, bucket_cap_mb=8.0)
+    for r in range(world):
+        f2.begin_step()
+        m2.forward_loss(x[r * 8:(r + 1) * 8].contiguous(memory_format=torch.channels_last), y[r * 8:(r + 1) * 8])[0].backward()
+        ref += f2.grad / world
+    assert torch.allclose(got, ref, atol=1e-5), (got - ref).abs().max()
+    assert red.bytes_last_step == flat.total * 4
+
+
+def pp_equivalence(rank, world, out_dir):
+    """1F1B over `world` stages with M micro-batches == single-process micro-batched gradients."""
+    from horizonml_b200 import ops
+    from horizonml_b200.config import TrainConfig
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.pp import PPEngine
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.resnet import resnet18
+    from horizonml_b200.parallel.pp import one_f_one_b
+    ops.set_backend("torch")
+    M = 4
+    cfg = TrainConfig(strategy="layer", world_size=world, microbatches=M, seed=11, lr=0.0, grad_divergence=False)
+    rt = Runtime(rank, world, torch.device("cpu"), torch.float32, "torch", "gloo")
+    eng = PPEngine(cfg, rt)
+    x, y = _batch(16, seed=3)
+    eng.step(x, y)
+    assert eng.runner.trace == one_f_one_b(rank, world, M)
+    # oracle on every rank: same micro-batching, whole model
+    m = resnet18(10, seed=11).train()
+    flat = FlatParams(list(m.named_parameters()), "cpu", torch.float32)
+    flat.begin_step()
+    tot = 0.0
+    for xs, ys in zip(x.split(4), y.split(4)):
+        l, _ = m.forward_loss(xs.contiguous(memory_format=torch.channels_last), ys, loss_scale=0.25)
+        l.backward(); tot += l.item()
+    ref = {n: p.main_grad for n, p in m.named_parameters()}
+    for n, p in zip(eng.flat.names, eng.flat.params):
+        assert torch.allclose(p.main_grad, ref[n], atol=2e-5), (n, (p.main_grad - ref[n]).abs().max())
+    if eng.is_last:
+        s = eng.stats.read_and_reset()
+        assert abs(s["loss_sum"] - tot) < 1e-4
+
+
+def tp_equivalence(rank, world, out_dir):
+    """TP(W) (column-parallel classifier + channel-parallel layer3/4) == dense model."""
+    from horizonml_b200 import ops
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.resnet import resnet18
+    from horizonml_b200.parallel.tp import TensorParallelResNet, TPComm, shard_range, padded_classes
+    ops.set_backend("torch")
+    x, y = _batch(8, seed=4)
+    dense = resnet18(10, seed=21).train()
+    fd = FlatParams(list(dense.named_parameters()), "cpu", torch.float32)
+    ld, cd = dense.forward_loss(x, y)
+    ld.backward()
+    ref = {n: p.main_grad.clone() for n, p in dense.named_parameters()}
+    comm = TPComm()
+    tp = TensorParallelResNet(resnet18(10, seed=21), comm, conv_split=True).train()
+    rep, shd = tp.split_params()
+    fr = FlatParams(rep, "cpu", torch.float32); fs = FlatParams(shd, "cpu", torch.float32)
+    lt, ct = tp.forward_loss(x, y)
+    lt.backward()
+    assert abs(lt.item() - ld.item()) < 1e-4 and ct.item() == cd.item()
+    kpad = padded_classes(10, world)
+    lo, hi = shard_range(kpad, world, rank)
+    got = dict(tp.named_parameters())
+    wref = torch.zeros(kpad, 512); wref[:10] = ref["fc.weight"]
+    assert torch.allclose(got["fc_weight"].main_grad, wref[lo:hi], atol=2e-5)
+    for lname, cout in (("layer3", 256), ("layer4", 512)):
+        clo, chi = shard_range(cout, world, rank)
+        for b in (0, 1):
+            g1 = got[f"backbone.{lname}.{b}.conv1.weight"].main_grad
+            g2 = got[f"backbone.{lname}.{b}.conv2.weight"].main_grad
+            assert torch.allclose(g1, ref[f"{lname}.{b}.conv1.weight"][clo:chi], atol=5e-5), lname
+            assert torch.allclose(g2, ref[f"{lname}.{b}.conv2.weight"][:, clo:chi], atol=5e-5), lname
+            assert torch.allclose(got[f"backbone.{lname}.{b}.bn1.weight"].main_grad,
+                                  ref[f"{lname}.{b}.bn1.weight"][clo:chi], atol=5e-5)
+    for n in ("conv1.weight", "layer1.0.conv1.weight", "layer2.0.downsample.0.weight", "layer4.1.bn2.weight"):
+        assert torch.allclose(got["backbone." + n].main_grad, ref[n], atol=5e-5), n
+    assert comm.take_bytes() > 0
