@@ -70,18 +70,20 @@ std::vector<Tensor> bn_act_fwd(const Tensor& y, const Tensor& sums, const Tensor
 // writes dgamma/dbeta straight into their gradient slots
 std::vector<Tensor> bn_act_bwd(const Tensor& dout, const Tensor& out, const Tensor& yraw, const Tensor& mean,
                                const Tensor& invstd, const Tensor& gamma, bool relu, bool has_res,
-                               Tensor dgamma, Tensor dbeta, bool acc_gamma, bool acc_beta) {
+                               Tensor dgamma, Tensor dbeta, bool acc_gamma, bool acc_beta,
+                               c10::optional<Tensor> zeroed_scratch) {
   check_cl(dout, "dout"); check_cl(yraw, "yraw");
   c10::cuda::CUDAGuard g(dout.device());
   auto d = dims_of(yraw);
   Tensor dy = at::empty_like(yraw);
   Tensor dres;
   if (has_res) dres = at::empty_like(yraw);
-  Tensor scratch = at::empty({2, d.C}, yraw.options().dtype(at::kFloat));
+  const bool pre = zeroed_scratch.has_value() && zeroed_scratch->defined();
+  Tensor scratch = pre ? *zeroed_scratch : at::empty({2, d.C}, yraw.options().dtype(at::kFloat));
   hz_bn_act_bwd(cptr(dout), cptr(out), cptr(yraw), mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 gamma.data_ptr<float>(), scratch.data_ptr<float>(), dy.data_ptr(),
                 has_res ? dres.data_ptr() : nullptr, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
-                acc_gamma ? 1 : 0, acc_beta ? 1 : 0, d.N * d.H * d.W, d.C, relu ? 1 : 0, cur_stream());
+                acc_gamma ? 1 : 0, acc_beta ? 1 : 0, d.N * d.H * d.W, d.C, relu ? 1 : 0, pre ? 1 : 0, cur_stream());
   return {dy, dres};
 }
 
@@ -155,15 +157,16 @@ std::vector<Tensor> head_fwd_bwd(const Tensor& feat, const Tensor& W, const c10:
   return {loss, correct, dfeat, logits};
 }
 
-void adam_step(Tensor master, const Tensor& grad, Tensor m, Tensor v, c10::optional<Tensor> shadow, Tensor step,
-               double lr, double b1, double b2, double eps, double gscale) {
+void adam_step(Tensor master, Tensor grad, Tensor m, Tensor v, c10::optional<Tensor> shadow, Tensor step,
+               double lr, double b1, double b2, double eps, double gscale, c10::optional<Tensor> prev,
+               c10::optional<Tensor> diff_out, bool zero_grad) {
   TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && master.numel() % 4 == 0);
   c10::cuda::CUDAGuard g(master.device());
   void* sh = nullptr;
   if (shadow.has_value() && shadow->defined()) { TORCH_CHECK(shadow->scalar_type() == at::kBFloat16); sh = shadow->data_ptr(); }
   hz_adam(master.data_ptr<float>(), grad.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), sh,
-          step.data_ptr<float>(), (size_t)master.numel(), (float)lr, (float)b1, (float)b2, (float)eps,
-          (float)gscale, cur_stream());
+          step.data_ptr<float>(), fptr(prev), fptr(diff_out), zero_grad ? 1 : 0, (size_t)master.numel(), (float)lr,
+          (float)b1, (float)b2, (float)eps, (float)gscale, cur_stream());
 }
 
 Tensor grad_diff_sq(const Tensor& grad, Tensor prev) {
@@ -188,7 +191,8 @@ bool conv_supported(int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, 
   return hz_conv_supported((int)N, (int)H, (int)W, (int)Cin, (int)Cout, (int)R, (int)stride, (int)pad) != 0;
 }
 
-std::vector<Tensor> conv_fwd(const Tensor& x, const Tensor& w, int64_t stride, int64_t pad, bool want_stats) {
+std::vector<Tensor> conv_fwd(const Tensor& x, const Tensor& w, int64_t stride, int64_t pad, bool want_stats,
+                             c10::optional<Tensor> zeroed_stats) {
   check_cl(x, "x"); check_cl(w, "w");
   c10::cuda::CUDAGuard g(x.device());
   auto d = dims_of(x);
@@ -196,9 +200,11 @@ std::vector<Tensor> conv_fwd(const Tensor& x, const Tensor& w, int64_t stride, i
   const int Ho = (d.H + 2 * pad - R) / stride + 1, Wo = (d.W + 2 * pad - R) / stride + 1;
   Tensor y = empty_cl(x, d.N, Cout, Ho, Wo);
   Tensor stats;
-  if (want_stats) stats = at::empty({2, Cout}, x.options().dtype(at::kFloat));
-  int rc = hz_conv_fwd(cptr(x), cptr(w), y.data_ptr(), want_stats ? stats.data_ptr<float>() : nullptr, d.N, d.H,
-                       d.W, d.C, Cout, R, (int)stride, (int)pad, cur_stream());
+  const bool pre = want_stats && zeroed_stats.has_value() && zeroed_stats->defined();
+  if (pre) stats = *zeroed_stats;
+  else if (want_stats) stats = at::empty({2, Cout}, x.options().dtype(at::kFloat));
+  int rc = hz_conv_fwd(cptr(x), cptr(w), y.data_ptr(), want_stats ? stats.data_ptr<float>() : nullptr, pre ? 1 : 0,
+                       d.N, d.H, d.W, d.C, Cout, R, (int)stride, (int)pad, cur_stream());
   TORCH_CHECK(rc == 0, "hz_conv_fwd failed rc=", rc);
   return {y, stats};
 }

@@ -484,8 +484,8 @@ int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride,
 }
 
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w[Cout,R,S,Cin]); stats (2*Cout fp32, zeroed here) optional
-int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int N, int H, int W, int Cin, int Cout,
-                int R, int stride, int pad, cudaStream_t st) {
+int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_is_zero, int N, int H, int W,
+                int Cin, int Cout, int R, int stride, int pad, cudaStream_t st) {
   const int S_ = R;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
   Tile t;
@@ -506,7 +506,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int N, int 
   p.ncols = Cout;
   p.out = (__nv_bfloat16*)y;
   p.stats = stats;
-  if (stats) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, st);
+  if (stats && !stats_is_zero) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, st);
   using SM = hz::IgemmSmem<BLOCK_N>;
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, false>, SM::kTotal);
   (void)attr;

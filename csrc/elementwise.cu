@@ -391,40 +391,68 @@ __global__ void __launch_bounds__(128) head_sample_kernel(
   }
 }
 
+// thread = one input channel c, 16 classes in registers; dlogits tile staged in smem
 __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict__ pooled,
                                                          const float* __restrict__ dlogits,
                                                          float* __restrict__ dW, float* __restrict__ db,
                                                          int N, int C, int K, int accumulate) {
-  const int k = blockIdx.y;
+  extern __shared__ float dl[];                 // [N][16]
+  const int k0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
+    const int n = i >> 4, j = i & 15;
+    dl[i] = (k0 + j < K) ? dlogits[(size_t)n * K + k0 + j] : 0.f;
+  }
+  __syncthreads();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s += dlogits[(size_t)n * K + k] * pooled[(size_t)n * C + c];
-    const size_t o = (size_t)k * C + c;
-    dW[o] = (accumulate ? dW[o] : 0.f) + s;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float pv = pooled[(size_t)n * C + c];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] += dl[n * 16 + j] * pv;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (k0 + j < K) {
+        const size_t o = (size_t)(k0 + j) * C + c;
+        dW[o] = (accumulate ? dW[o] : 0.f) + acc[j];
+      }
+    }
   }
-  if (db != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
-    float s = 0.f;
-    for (int n = 0; n < N; ++n) s += dlogits[(size_t)n * K + k];
-    db[k] = (accumulate ? db[k] : 0.f) + s;
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x < 16 && k0 + threadIdx.x < K) {
+    float t = 0.f;
+    for (int n = 0; n < N; ++n) t += dl[n * 16 + threadIdx.x];
+    db[k0 + threadIdx.x] = (accumulate ? db[k0 + threadIdx.x] : 0.f) + t;
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // flat fused Adam (fp32 master + moments, bf16 shadow refresh)  — torch.optim.Adam semantics
 // ------------------------------------------------------------------------------------------------
-__global__ void bump_step_kernel(float* step) { step[0] += 1.f; }
+__global__ void bump_step_kernel(float* step, float* diff) {
+  step[0] += 1.f;
+  if (diff != nullptr) diff[0] = 0.f;
+}
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+// One pass over the flat buffers: Adam update, bf16 shadow refresh, optional gradient-divergence
+// accumulation Σ(g − prev)² with prev ← g (reference metric, data_parallel_train.py:132-145) and
+// optional g ← 0 (so the next step's wgrad kernels can accumulate without any memset).
+template <bool kDiff, bool kZero>
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    __nv_bfloat16* __restrict__ shadow,
-                                                   const float* __restrict__ step, size_t n, float lr,
+                                                   const float* __restrict__ step, float* __restrict__ prev,
+                                                   float* __restrict__ diff_out, size_t n, float lr,
                                                    float b1, float b2, float eps, float gscale) {
+  __shared__ float wsum[8];
   const float t = step[0];
   const float bc1 = 1.f - __powf(b1, t), bc2 = 1.f - __powf(b2, t);
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   const size_t nv = n >> 2;
+  float dacc = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
        i += (size_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -432,6 +460,12 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
     float* P = &pp.x; float* G = &gg.x; float* Mo = &mm.x; float* V = &vv.x;
+    if (kDiff) {
+      const float4 pr = reinterpret_cast<float4*>(prev)[i];
+      const float dx = gg.x - pr.x, dy = gg.y - pr.y, dz = gg.z - pr.z, dw = gg.w - pr.w;
+      dacc += dx * dx + dy * dy + dz * dz + dw * dw;
+      reinterpret_cast<float4*>(prev)[i] = gg;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float gr = G[j] * gscale;
@@ -443,12 +477,25 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (kZero) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (shadow != nullptr) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
       reinterpret_cast<uint2*>(shadow)[i] = pk;
+    }
+  }
+  if (kDiff) {
+    dacc = warp_sum(dacc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = dacc;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float tt = wsum[threadIdx.x];
+      tt += __shfl_xor_sync(0xffu, tt, 4);
+      tt += __shfl_xor_sync(0xffu, tt, 2);
+      tt += __shfl_xor_sync(0xffu, tt, 1);
+      if (threadIdx.x == 0) atomicAdd(diff_out, tt);
     }
   }
 }
@@ -545,8 +592,8 @@ void hz_bn_act_fwd(const void* y, const float* sums, const float* gamma, const f
 void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const float* mean,
                    const float* invstd, const float* gamma, float* sums_scratch, void* dy, void* dres,
                    float* dgamma, float* dbeta, int acc_gamma, int acc_beta, int M, int C, int relu,
-                   cudaStream_t st) {
-  cudaMemsetAsync(sums_scratch, 0, sizeof(float) * 2 * C, st);
+                   int scratch_is_zero, cudaStream_t st) {
+  if (!scratch_is_zero) cudaMemsetAsync(sums_scratch, 0, sizeof(float) * 2 * C, st);
   const size_t smem_r = sizeof(float) * 256 * 16;
   hz::channel_reduce_kernel<true><<<reduce_grid(M, C), 256, smem_r, st>>>(
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
@@ -599,15 +646,23 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
   hz::head_sample_kernel<<<N, 128, smem, st>>>((const __nv_bfloat16*)feat, W, bias, labels, pooled,
                                                dlogits, logits, (__nv_bfloat16*)dfeat, loss, correct, N,
                                                C, HW, K, n_valid, loss_scale);
-  dim3 grid((C + 127) / 128, K);
-  hz::head_wgrad_kernel<<<grid, 128, 0, st>>>(pooled, dlogits, dW, db, N, C, K, accumulate);
+  dim3 grid((C + 127) / 128, (K + 15) / 16);
+  hz::head_wgrad_kernel<<<grid, 128, sizeof(float) * N * 16, st>>>(pooled, dlogits, dW, db, N, C, K, accumulate);
 }
 
-void hz_adam(float* p, const float* g, float* m, float* v, void* shadow, float* step, size_t n,
-             float lr, float b1, float b2, float eps, float gscale, cudaStream_t st) {
-  hz::bump_step_kernel<<<1, 1, 0, st>>>(step);
-  hz::adam_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow,
-                                                                  step, n, lr, b1, b2, eps, gscale);
+void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
+             int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, cudaStream_t st) {
+  const bool diff = prev != nullptr && diff_out != nullptr;
+  hz::bump_step_kernel<<<1, 1, 0, st>>>(step, diff ? diff_out : nullptr);
+  const int grid = grid_for(n / 4, 256, 148 * 8);
+#define HZ_ADAM(D, Z)                                                                                   \
+  hz::adam_kernel<D, Z><<<grid, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow, step, prev, diff_out, n, lr, \
+                                              b1, b2, eps, gscale)
+  if (diff && zero_grad) HZ_ADAM(true, true);
+  else if (diff) HZ_ADAM(true, false);
+  else if (zero_grad) HZ_ADAM(false, true);
+  else HZ_ADAM(false, false);
+#undef HZ_ADAM
 }
 
 void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st) {

@@ -17,7 +17,7 @@ void hz_bn_act_fwd(const void* y, const float* sums, const float* gamma, const f
 void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const float* mean,
                    const float* invstd, const float* gamma, float* sums_scratch, void* dy, void* dres,
                    float* dgamma, float* dbeta, int acc_gamma, int acc_beta, int M, int C, int relu,
-                   cudaStream_t st);
+                   int scratch_is_zero, cudaStream_t st);
 void hz_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st);
 void hz_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H, int W, int C,
                     cudaStream_t st);
@@ -29,16 +29,16 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
                      float* dlogits, float* logits, void* dfeat, float* loss, float* correct, float* dW,
                      float* db, int N, int C, int HW, int K, int n_valid, float loss_scale, int accumulate,
                      cudaStream_t st);
-void hz_adam(float* p, const float* g, float* m, float* v, void* shadow, float* step, size_t n, float lr,
-             float b1, float b2, float eps, float gscale, cudaStream_t st);
+void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
+             int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, cudaStream_t st);
 void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st);
 void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct, float batch,
                      const float* diff_sq, cudaStream_t st);
 
 // ---- conv_gemm.cu (tcgen05 implicit GEMM)
 int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
-int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int N, int H, int W, int Cin, int Cout,
-                int R, int stride, int pad, cudaStream_t st);
+int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_is_zero, int N, int H, int W,
+                int Cin, int Cout, int R, int stride, int pad, cudaStream_t st);
 int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R,
                   int stride, int pad, cudaStream_t st);
 int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,

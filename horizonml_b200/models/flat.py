@@ -122,9 +122,11 @@ class FlatParams:
         return self._bucket_of[id(p)]
 
     def begin_step(self) -> None:
-        """Next gradient write overwrites (no zero-fill pass needed)."""
+        """Start of an optimizer step.  When the optimizer zeroes the gradient buffer in its own pass
+        (``zeroed_by_optimizer``) every producer accumulates; otherwise the first write overwrites."""
+        acc = bool(getattr(self, "zeroed_by_optimizer", False))
         for p in self.params:
-            p._acc = False
+            p._acc = acc
 
     def zero_grad(self) -> None:
         self.grad.zero_()
@@ -152,13 +154,18 @@ class FlatAdam:
         self.m = torch.zeros_like(flat.master)
         self.v = torch.zeros_like(flat.master)
         self.step_t = torch.zeros(1, dtype=torch.float32, device=flat.device)
+        # the Adam pass also clears the gradient buffer → producers only ever accumulate, no memsets
+        flat.zeroed_by_optimizer = True
+        flat.grad.zero_()
 
     @torch.no_grad()
-    def step(self, grad_scale: float = 1.0) -> None:
+    def step(self, grad_scale: float = 1.0, prev_grad=None):
+        """One fused pass: Adam + bf16 shadow refresh + (optional) gradient-divergence Σ(g−prev)² +
+        gradient clear.  Returns the divergence term (0-d tensor) or None."""
         from .. import ops
         f = self.flat
-        ops.adam_step(f.master, f.grad, self.m, self.v, f.shadow, self.step_t, self.lr,
-                      self.betas[0], self.betas[1], self.eps, grad_scale)
+        return ops.adam_step(f.master, f.grad, self.m, self.v, f.shadow, self.step_t, self.lr,
+                             self.betas[0], self.betas[1], self.eps, grad_scale, prev_grad, True)
 
     def state_dict(self) -> dict:
         return {"m": self.m.cpu(), "v": self.v.cpu(), "step": self.step_t.cpu(), "lr": self.lr,

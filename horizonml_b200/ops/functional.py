@@ -24,6 +24,33 @@ import torch
 from . import torch_backend as _tb
 
 _state = {"backend": "torch", "native": None}
+# wgrad kernels depend only on (dy, x): they run on a side stream, off the dgrad critical path
+_side = {"enabled": False, "stream": None, "keep": [], "dirty": False}
+
+
+def enable_side_stream(flag: bool) -> None:
+    _side["enabled"] = bool(flag)
+
+
+def join_side() -> None:
+    """Make the current stream wait for everything launched on the side stream (call before the
+    optimizer / at the end of backward; also required before a CUDA-graph capture ends)."""
+    if _side["dirty"]:
+        ev = torch.cuda.Event()
+        ev.record(_side["stream"])
+        torch.cuda.current_stream().wait_event(ev)
+        _side["keep"].clear()
+        _side["dirty"] = False
+
+
+def step_begin(device=None) -> None:
+    if _state["backend"] == "native" and (device is None or torch.device(device).type == "cuda"):
+        _state["native"].step_begin(device)
+
+
+def step_end() -> None:
+    if _state["backend"] == "native" and _state["native"] is not None:
+        _state["native"].step_end()
 
 
 def set_backend(name: str) -> None:
@@ -125,8 +152,20 @@ class _ConvBNAct(torch.autograd.Function):
         grad_written(beta)
         w = compute_weight(weight, x.dtype)
         tgt, acc = grad_target(weight)
-        be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc)
-        grad_written(weight)
+        if _side["enabled"] and x.is_cuda and ctx.x_needs_grad:
+            if _side["stream"] is None:
+                _side["stream"] = torch.cuda.Stream(device=x.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            _side["stream"].wait_event(ev)
+            with torch.cuda.stream(_side["stream"]):
+                be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc)
+                grad_written(weight)          # reducer hooks record their events on the side stream
+            _side["keep"].append((dy, x))     # keep operands alive until join_side()
+            _side["dirty"] = True
+        else:
+            be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc)
+            grad_written(weight)
         dx = be.conv_dgrad(dy, w, x.shape, stride, pad) if ctx.x_needs_grad else None
         if dx is not None and ctx.post_dgrad is not None:   # column-parallel conv: Σ over shards
             dx = ctx.post_dgrad(dx)
@@ -224,12 +263,18 @@ def head_logits(feat, fc_w, fc_b):
 # small utilities shared by trainers
 # ----------------------------------------------------------------------------------------------
 
-def adam_step(master, grad, m, v, shadow, step_t, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0):
-    _be(master).adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale)
+def adam_step(master, grad, m, v, shadow, step_t, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0,
+              prev=None, zero_grad=False):
+    """Returns Σ(g−prev)² (0-d tensor) when ``prev`` is given, else None."""
+    return _be(master).adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad)
 
 
 def grad_diff_sq(grad, prev):
     return _be(grad).grad_diff_sq(grad, prev)
+
+
+def stats_update(stats, has_prev, loss, correct, batch, diff_sq=None):
+    _be(stats).stats_update(stats, has_prev, loss, correct, batch, diff_sq)
 
 
 def stem_prepare(images, mean=0.5, std=0.5, dtype=torch.float32):

@@ -23,6 +23,45 @@ _STRICT = os.environ.get("HZ_STRICT_NATIVE", "0") == "1"
 STEM_KP = 192                       # 7*7*3 = 147 padded to 3 k-blocks of 64
 
 
+class _Arena:
+    """Pre-zeroed fp32 scratch for per-channel statistics (conv-epilogue BN sums, BN-backward sums):
+    one fill per step instead of one cudaMemset node per layer."""
+
+    def __init__(self, n=1 << 18):
+        self.n, self.buf, self.off, self.used_prev, self.active = n, None, 0, 0, False
+
+    def begin(self, device):
+        if self.buf is None or self.buf.device != device:
+            self.buf = torch.zeros(self.n, dtype=torch.float32, device=device)
+        elif max(self.off, self.used_prev) > 0:
+            self.buf[:max(self.off, self.used_prev)].zero_()
+        self.used_prev, self.off, self.active = self.off, 0, True
+
+    def take(self, rows, c, device):
+        if not self.active or self.buf is None or self.buf.device != device:
+            return None
+        n = rows * c
+        if self.off + n > self.n:
+            return None
+        t = self.buf[self.off:self.off + n].view(rows, c)
+        self.off += (n + 31) // 32 * 32
+        return t
+
+
+ARENA = _Arena()
+_STEM_CACHE = {"key": None, "A": None}
+
+
+def step_begin(device=None):
+    ARENA.begin(torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    _STEM_CACHE["key"] = None
+    _STEM_CACHE["A"] = None
+
+
+def step_end():
+    ARENA.active = False
+
+
 def _fallback(name: str, why: str):
     FALLBACKS[name] += 1
     if _STRICT:
@@ -48,17 +87,20 @@ def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
     if _bf16_cl(x) and w.dtype == torch.bfloat16:
         if _conv_ok(x.shape, w.shape, stride, pad):
             LAUNCHES["conv_fwd"] += 1
-            y, stats = C.conv_fwd(x, w, stride, pad, want_stats)
+            pre = ARENA.take(2, w.shape[0], x.device) if want_stats else None
+            y, stats = C.conv_fwd(x, w, stride, pad, want_stats, pre)
             return y, (stats if want_stats else None)
         if _is_stem(x.shape, w.shape):
             n, cin, h, wd = x.shape
             cout, _, r, _ = w.shape
             ho, wo = (h + 2 * pad - r) // stride + 1, (wd + 2 * pad - r) // stride + 1
             A = C.im2col_small(x, r, stride, pad, STEM_KP)                      # [N*Ho*Wo, 192]
+            _STEM_CACHE["key"], _STEM_CACHE["A"] = (x.data_ptr(), x._version, tuple(x.shape)), A
             wp = C.pad_rows(w.permute(0, 2, 3, 1).reshape(cout, -1), STEM_KP)   # [Cout, 192]
             LAUNCHES["stem_im2col"] += 2
             LAUNCHES["conv_fwd"] += 1
-            y2, stats = C.conv_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0, want_stats)
+            pre = ARENA.take(2, cout, x.device) if want_stats else None
+            y2, stats = C.conv_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0, want_stats, pre)
             y = y2.reshape(n, ho, wo, cout).permute(0, 3, 1, 2)
             return y, (stats if want_stats else None)
     _fallback("conv_fwd", f"x={tuple(x.shape)} w={tuple(w.shape)} s={stride}")
@@ -90,7 +132,8 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma
         else:
             dg, ag, db, ab = dgamma_slot.t, dgamma_slot.acc, dbeta_slot.t, dbeta_slot.acc
         LAUNCHES["bn_act_bwd"] += 2
-        dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dg, db, ag, ab)
+        dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dg, db, ag, ab,
+                                ARENA.take(2, c, y_raw.device))
         return dy, dg, db, (dres if has_residual else None)
     _fallback("bn_act_bwd", f"{tuple(y_raw.shape)}")
     return _tb.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot, dbeta_slot)
@@ -119,10 +162,13 @@ def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, ac
             C.conv_wgrad(dy, x, out_grad, r, stride, pad, accumulate, 0, 0)
             return
         if _is_stem(x.shape, w_shape):
-            A = C.im2col_small(x, r, stride, pad, STEM_KP)
+            if _STEM_CACHE["key"] == (x.data_ptr(), x._version, tuple(x.shape)):
+                A = _STEM_CACHE["A"]            # the forward's im2col matrix is still alive
+            else:
+                A = C.im2col_small(x, r, stride, pad, STEM_KP)
+                LAUNCHES["stem_im2col"] += 1
             n, _, ho, wo = dy.shape
             dy2 = dy.permute(0, 2, 3, 1).reshape(-1, cout, 1, 1)     # [M, Cout,1,1] (NHWC rows)
-            LAUNCHES["stem_im2col"] += 1
             LAUNCHES["conv_wgrad"] += 1
             C.conv_wgrad(dy2, A.view(-1, STEM_KP, 1, 1), out_grad, 1, 1, 0, accumulate, cin * r * s, cin * r * s)
             return
@@ -161,13 +207,14 @@ def linear_fwd(x2d, w, b):
     return _tb.linear_fwd(x2d, w, b)
 
 
-def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.0):
+def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.0, prev=None, zero_grad=False):
     if master.is_cuda and master.numel() % 4 == 0 and (shadow is None or shadow.dtype == torch.bfloat16):
         LAUNCHES["adam"] += 2
-        C.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale)
-        return
+        diff = torch.empty((), dtype=torch.float32, device=master.device) if prev is not None else None
+        C.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, diff, zero_grad)
+        return diff
     _fallback("adam_step", "")
-    _tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale)
+    return _tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad)
 
 
 def grad_diff_sq(grad, prev):
@@ -182,3 +229,11 @@ def stem_prepare(images, mean, std, dtype):
         LAUNCHES["u8_normalize"] += 1
         return C.u8_normalize(images, mean, std)
     return _tb.stem_prepare(images, mean, std, dtype)
+
+
+def stats_update(stats, has_prev, loss, correct, batch, diff_sq):
+    if stats.is_cuda and loss.dtype == torch.float32 and correct.dtype == torch.float32:
+        LAUNCHES["stats"] += 1
+        C.stats_update(stats, has_prev, loss.detach(), correct.detach(), float(batch), diff_sq)
+        return
+    _tb.stats_update(stats, has_prev, loss, correct, batch, diff_sq)

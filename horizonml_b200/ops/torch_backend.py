@@ -171,11 +171,17 @@ def linear_fwd(x2d, w, b):
 
 
 def adam_step(master, grad, m, v, shadow, step_t, lr: float, b1: float, b2: float, eps: float,
-              grad_scale: float = 1.0):
+              grad_scale: float = 1.0, prev=None, zero_grad: bool = False):
     """Flat fused Adam (torch.optim.Adam semantics, no weight decay / amsgrad).
-    ``step_t`` is a 1-element fp32/int tensor holding the step count (incremented here)."""
+    ``step_t`` holds the step count (incremented here).  ``prev``: gradient-divergence bookkeeping —
+    returns Σ(g−prev)² and sets prev ← g.  ``zero_grad``: g ← 0 afterwards (accumulate-only wgrads)."""
     step_t += 1
     t = float(step_t.item()) if step_t.device.type == "cpu" else step_t.float()
+    diff = None
+    if prev is not None:
+        d = grad - prev
+        diff = (d * d).sum()
+        prev.copy_(grad)
     g = grad if grad_scale == 1.0 else grad * grad_scale
     m.mul_(b1).add_(g, alpha=1 - b1)
     v.mul_(b2).addcmul_(g, g, value=1 - b2)
@@ -185,6 +191,9 @@ def adam_step(master, grad, m, v, shadow, step_t, lr: float, b1: float, b2: floa
     master.sub_((m / bc1) / denom * lr)
     if shadow is not None:
         shadow.copy_(master)
+    if zero_grad:
+        grad.zero_()
+    return diff
 
 
 def grad_diff_sq(grad, prev):
@@ -202,3 +211,23 @@ def stem_prepare(images, mean: float, std: float, dtype):
         x = x / 255.0
     x = (x - mean) / std
     return _cl(x.to(dtype))
+
+
+def step_begin():
+    """Start-of-step hook (the native backend recycles its statistics arena here)."""
+
+
+def step_end():
+    pass
+
+
+def stats_update(stats, has_prev, loss, correct, batch: float, diff_sq):
+    stats[0] += loss.detach().float()
+    stats[1] += correct.detach().float()
+    stats[2] += batch
+    stats[5] += 1
+    if diff_sq is not None:
+        hp = has_prev.reshape(())
+        stats[3] += diff_sq.reshape(()).sqrt() * hp
+        stats[4] += hp
+        has_prev.fill_(1.0)

@@ -87,11 +87,9 @@ class PeerAllReduce(GradAllReduce):
                                       self.max_numel * wire_bytes, max_blocks)
         self.has_nvls = False
         if self.world > 1:
-            mine = torch.tensor(list(self.handle.export_handles()), dtype=torch.uint8)
-            gathered = [torch.empty_like(mine) for _ in range(self.world)]
-            # handles are opaque host bytes: exchange through a CPU-side object gather
+            # 64-byte cudaIpcMemHandle of this rank's region -> everyone (opaque host bytes)
             objs: List[Optional[bytes]] = [None] * self.world
-            dist.all_gather_object(objs, bytes(mine.tolist()), group=group)
+            dist.all_gather_object(objs, bytes(self.handle.export_handles()), group=group)
             self.handle.import_handles([bytes(o) for o in objs])
             if algo in ("nvls", "auto"):
                 self.has_nvls = self._try_setup_nvls(group)
@@ -106,7 +104,7 @@ class PeerAllReduce(GradAllReduce):
         try:
             import torch.distributed._symmetric_memory as symm
             wire_bytes = 2 if self.wire == "bf16" else 4
-            nbytes = 2 * self.max_numel * wire_bytes
+            nbytes = 4 * ((self.max_numel * wire_bytes + 255) // 256 * 256)   # stage[2] + out[2]
             buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
             hdl = symm.rendezvous(buf, group=group if group is not None else dist.group.WORLD)
             mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
@@ -139,7 +137,7 @@ class PeerAllReduce(GradAllReduce):
         self.handle.allreduce(t, a, self.wire == "bf16", 1.0 / self.world)
 
     def barrier(self) -> None:
-        self.handle.barrier()
+        self.handle.barrier(None)
 
 
 def make_grad_allreduce(kind: str, max_numel: int, device, group=None, wire: str = "bf16") -> GradAllReduce:

@@ -28,6 +28,7 @@ class GradReducer:
         self.enabled = True
         self.comm_stream = torch.cuda.Stream(device=flat.device) if self.overlap else None
         self._pending: List[int] = []
+        self._main_stream = None
         self._counts = [len(b.names) for b in flat.buckets]
         self._launched: List[bool] = []
         self._events: List[Optional[torch.cuda.Event]] = []
@@ -37,6 +38,7 @@ class GradReducer:
         self.begin_step()
 
     def begin_step(self) -> None:
+        self._main_stream = torch.cuda.current_stream(self.flat.device) if self.cuda else None
         self._pending = list(self._counts)
         self._launched = [False] * len(self._counts)
         self._events = [None] * len(self._counts)
@@ -48,7 +50,8 @@ class GradReducer:
             return
         b = self.flat.bucket_index(p)
         self._pending[b] -= 1
-        if self._pending[b] == 0 and not self._launched[b]:
+        # without overlap every bucket is launched from finish() (after the side stream has been joined)
+        if self.overlap and self._pending[b] == 0 and not self._launched[b]:
             self._launch(b)
 
     def _launch(self, b: int) -> None:
@@ -57,10 +60,17 @@ class GradReducer:
         self._launched[b] = True
         self.bytes_last_step += self.ar.wire_bytes(bk.end - bk.start)
         if self.overlap:
-            cur = torch.cuda.current_stream(self.flat.device)
-            ready = torch.cuda.Event()
-            ready.record(cur)
-            self.comm_stream.wait_event(ready)
+            # gradients of one bucket are produced on two streams: BN/dgrad chain (main) and the wgrad
+            # side stream — the collective must wait for both
+            from ..ops import functional as F
+            streams = {torch.cuda.current_stream(self.flat.device)}
+            if F._side["stream"] is not None:
+                streams.add(F._side["stream"])
+                streams.add(self._main_stream or torch.cuda.current_stream(self.flat.device))
+            for st in streams:
+                ready = torch.cuda.Event()
+                ready.record(st)
+                self.comm_stream.wait_event(ready)
             with torch.cuda.stream(self.comm_stream):
                 self.ar.allreduce_avg_(view)
                 done = torch.cuda.Event()

@@ -50,18 +50,11 @@ class DeviceStats:
 
     def __init__(self, device):
         self.buf = torch.zeros(self.N, dtype=torch.float32, device=device)
-        self.has_prev = torch.zeros((), dtype=torch.float32, device=device)
+        self.has_prev = torch.zeros(1, dtype=torch.float32, device=device)
 
-    def add_step(self, loss, correct, batch: int) -> None:
-        self.buf[0] += loss.detach().float()
-        self.buf[1] += correct.detach().float()
-        self.buf[2] += batch
-        self.buf[5] += 1
-
-    def add_grad_div(self, diff_sq) -> None:
-        self.buf[3] += diff_sq.sqrt() * self.has_prev
-        self.buf[4] += self.has_prev
-        self.has_prev.fill_(1.0)
+    def add_step(self, loss, correct, batch: int, diff_sq=None) -> None:
+        """One tiny kernel: loss/accuracy/sample counters (+ grad-divergence term when given)."""
+        ops.stats_update(self.buf, self.has_prev, loss, correct, float(batch), diff_sq)
 
     def read_and_reset(self, keep_div: bool = True) -> Dict[str, float]:
         v = self.buf.tolist()

@@ -60,6 +60,7 @@ class DPEngine:
         self.ar = make_grad_allreduce(kind, self.flat.total, dev) if rt.world > 1 else None
         self.reducer = GradReducer(self.flat, self.ar, cfg.overlap) if self.ar is not None else None
         self.stats = DeviceStats(dev)
+        ops.enable_side_stream(dev.type == "cuda" and rt.backend == "native")
         self.prev_grad = torch.zeros_like(self.flat.grad) if cfg.grad_divergence else None
         self._graphed = GraphedStep(self._step_impl, dev, cfg.cuda_graph)
         self.global_step = 0
@@ -70,17 +71,18 @@ class DPEngine:
         x = images
         if x.dtype == torch.uint8:
             x = ops.stem_prepare(x.permute(0, 3, 1, 2), dtype=self.rt.dtype)
+        ops.step_begin(self.rt.device)
         self.flat.begin_step()
         if self.reducer is not None:
             self.reducer.begin_step()
         loss, correct = self.model.forward_loss(x, labels)
         loss.backward()
+        ops.join_side()
         if self.reducer is not None:
             self.reducer.finish()
-        self.opt.step()
-        self.stats.add_step(loss, correct, labels.shape[0])
-        if self.prev_grad is not None:
-            self.stats.add_grad_div(ops.grad_diff_sq(self.flat.grad, self.prev_grad))
+        diff = self.opt.step(prev_grad=self.prev_grad)
+        self.stats.add_step(loss, correct, labels.shape[0], diff)
+        ops.step_end()
 
     def step(self, images, labels) -> None:
         self._graphed(images, labels)

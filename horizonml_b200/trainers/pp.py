@@ -77,14 +77,15 @@ class PPEngine:
         self.labels_mb = list(torch.split(labels, sizes))
         self.mb_frac = [n / B for n in sizes]
         imgs = list(torch.split(images, sizes)) if self.is_first else None
+        ops.step_begin(self.rt.device)
         self.flat.begin_step()
         loss, correct = self.runner.run(sizes, imgs)
-        self.opt.step()
+        ops.join_side()
+        diff = self.opt.step(prev_grad=self.prev_grad)
         sent = self.runner.p2p.end_step()
+        ops.step_end()
         if self.is_last:
-            self.stats.add_step(loss, correct, B)
-            if self.prev_grad is not None:
-                self.stats.add_grad_div(ops.grad_diff_sq(self.flat.grad, self.prev_grad))
+            self.stats.add_step(loss, correct, B, diff)
         else:
             self.stats.buf[5] += 1
         self.global_step += 1

@@ -51,17 +51,19 @@ class TPEngine:
         x = images
         if x.dtype == torch.uint8:
             x = ops.stem_prepare(x.permute(0, 3, 1, 2), dtype=self.rt.dtype)
+        ops.step_begin(self.rt.device)
         self.flat_rep.begin_step(); self.flat_shd.begin_step()
         if self.reducer is not None:
             self.reducer.begin_step()
         loss, correct = self.model.forward_loss(x, labels)
         loss.backward()
+        ops.join_side()
         if self.reducer is not None:
             self.reducer.finish()
-        self.opt_rep.step(); self.opt_shd.step()
-        self.stats.add_step(loss, correct, labels.shape[0])
-        if self.prev_grad is not None:
-            self.stats.add_grad_div(ops.grad_diff_sq(self.flat_rep.grad, self.prev_grad))
+        diff = self.opt_rep.step(prev_grad=self.prev_grad)
+        self.opt_shd.step()
+        self.stats.add_step(loss, correct, labels.shape[0], diff)
+        ops.step_end()
 
     def step(self, images, labels):
         self._graphed(images, labels)

@@ -99,6 +99,7 @@ def pp_equivalence(rank, world, out_dir):
     rt = Runtime(rank, world, torch.device("cpu"), torch.float32, "torch", "gloo")
     eng = PPEngine(cfg, rt)
     x, y = _batch(16, seed=3)
+    eng.opt.step = lambda **kw: None          # keep the accumulated gradients for inspection
     eng.step(x, y)
     assert eng.runner.trace == one_f_one_b(rank, world, M)
     # oracle on every rank: same micro-batching, whole model
