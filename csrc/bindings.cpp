@@ -83,26 +83,29 @@ std::vector<Tensor> bn_act_bwd(const Tensor& dout, const Tensor& out, const Tens
   hz_bn_act_bwd(cptr(dout), cptr(out), cptr(yraw), mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 gamma.data_ptr<float>(), scratch.data_ptr<float>(), dy.data_ptr(),
                 has_res ? dres.data_ptr() : nullptr, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
-                acc_gamma ? 1 : 0, acc_beta ? 1 : 0, d.N * d.H * d.W, d.C, relu ? 1 : 0, pre ? 1 : 0, cur_stream());
+                acc_gamma ? 1 : 0, acc_beta ? 1 : 0, d.N * d.H * d.W, d.C, relu ? 1 : 0,
+                pre ? (scratch.numel() >= 2 * d.C + 32 ? 2 : 1) : 0, cur_stream());
   return {dy, dres};
 }
 
-Tensor maxpool_fwd(const Tensor& x) {
+std::vector<Tensor> maxpool_fwd(const Tensor& x, bool want_idx) {
   check_cl(x, "x");
   c10::cuda::CUDAGuard g(x.device());
   auto d = dims_of(x);
   const int Ho = (d.H + 2 - 3) / 2 + 1, Wo = (d.W + 2 - 3) / 2 + 1;
   Tensor y = empty_cl(x, d.N, d.C, Ho, Wo);
-  hz_maxpool_fwd(cptr(x), y.data_ptr(), d.N, d.H, d.W, d.C, cur_stream());
-  return y;
+  Tensor idx;
+  if (want_idx) idx = at::empty({d.N, Ho, Wo, d.C}, x.options().dtype(at::kByte));
+  hz_maxpool_fwd(cptr(x), y.data_ptr(), want_idx ? idx.data_ptr() : nullptr, d.N, d.H, d.W, d.C, cur_stream());
+  return {y, idx};
 }
 
-Tensor maxpool_bwd(const Tensor& dy, const Tensor& x, const Tensor& y) {
-  check_cl(dy, "dy"); check_cl(x, "x");
-  c10::cuda::CUDAGuard g(x.device());
-  auto d = dims_of(x);
-  Tensor dx = at::empty_like(x);
-  hz_maxpool_bwd(cptr(dy), cptr(x), cptr(y), dx.data_ptr(), d.N, d.H, d.W, d.C, cur_stream());
+Tensor maxpool_bwd(const Tensor& dy, const Tensor& idx, std::vector<int64_t> x_shape) {
+  check_cl(dy, "dy");
+  c10::cuda::CUDAGuard g(dy.device());
+  const int N = (int)x_shape[0], Cc = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
+  Tensor dx = empty_cl(dy, N, Cc, H, W);
+  hz_maxpool_bwd(cptr(dy), idx.data_ptr(), dx.data_ptr(), N, H, W, Cc, cur_stream());
   return dx;
 }
 
@@ -136,7 +139,8 @@ Tensor pad_rows(const Tensor& w2d, int64_t Kp) {
 
 std::vector<Tensor> head_fwd_bwd(const Tensor& feat, const Tensor& W, const c10::optional<Tensor>& bias,
                                  const Tensor& labels, double loss_scale, int64_t n_valid, Tensor dW,
-                                 c10::optional<Tensor> db, bool accumulate, bool need_dfeat) {
+                                 c10::optional<Tensor> db, bool accumulate, bool need_dfeat,
+                                 c10::optional<Tensor> zeroed2) {
   check_cl(feat, "feat");
   TORCH_CHECK(W.scalar_type() == at::kFloat && W.is_contiguous());
   TORCH_CHECK(labels.scalar_type() == at::kLong);
@@ -146,14 +150,16 @@ std::vector<Tensor> head_fwd_bwd(const Tensor& feat, const Tensor& W, const c10:
   TORCH_CHECK(K <= 64, "head supports at most 64 (padded) classes");
   auto fo = feat.options().dtype(at::kFloat);
   Tensor pooled = at::empty({d.N, d.C}, fo), dlogits = at::empty({d.N, K}, fo), logits = at::empty({d.N, K}, fo);
-  Tensor loss = at::empty({}, fo), correct = at::empty({}, fo);
+  const bool pre = zeroed2.has_value() && zeroed2->defined() && zeroed2->numel() >= 2;
+  Tensor loss = pre ? zeroed2->view({-1})[0] : at::empty({}, fo);
+  Tensor correct = pre ? zeroed2->view({-1})[1] : at::empty({}, fo);
   Tensor dfeat;
   if (need_dfeat) dfeat = at::empty_like(feat);
   hz_head_fwd_bwd(cptr(feat), W.data_ptr<float>(), fptr(bias), labels.data_ptr<int64_t>(),
                   pooled.data_ptr<float>(), dlogits.data_ptr<float>(), logits.data_ptr<float>(),
                   need_dfeat ? dfeat.data_ptr() : nullptr, loss.data_ptr<float>(), correct.data_ptr<float>(),
                   dW.data_ptr<float>(), fptr(db), d.N, d.C, d.H * d.W, K, (int)n_valid, (float)loss_scale,
-                  accumulate ? 1 : 0, cur_stream());
+                  accumulate ? 1 : 0, pre ? 1 : 0, cur_stream());
   return {loss, correct, dfeat, logits};
 }
 

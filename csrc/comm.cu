@@ -169,6 +169,55 @@ HZ_DEVINL void sub_range(size_t nv, int W, int B, int r, int b, size_t& lo, size
   hi = min(lo + qq, shi);
 }
 
+constexpr int kUnroll = 4;     // independent 16-byte requests in flight per thread and phase
+
+// pack [lo,hi): grad(fp32)*scale -> wire vectors in the local staging buffer
+template <bool kBf16>
+HZ_DEVINL void pack_range(const float* __restrict__ grad, uint4* __restrict__ stage, size_t lo, size_t hi,
+                          float scale) {
+  using Wt = Wire<kBf16>;
+  constexpr int V = Wt::kVec;
+  for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * kUnroll) {
+    float f[kUnroll][V];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t v = v0 + (size_t)u * blockDim.x;
+      if (v < hi) load_grad<V>(grad, v, f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t v = v0 + (size_t)u * blockDim.x;
+      if (v < hi) stage[v] = Wt::pack(f[u], scale);
+    }
+  }
+}
+
+// unpack [lo,hi): wire vectors -> grad(fp32)
+template <bool kBf16>
+HZ_DEVINL void unpack_range(float* __restrict__ grad, const uint4* __restrict__ src, size_t lo, size_t hi) {
+  using Wt = Wire<kBf16>;
+  constexpr int V = Wt::kVec;
+  for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * kUnroll) {
+    uint4 w[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t v = v0 + (size_t)u * blockDim.x;
+      if (v < hi) w[u] = src[v];
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t v = v0 + (size_t)u * blockDim.x;
+      if (v < hi) {
+        float a[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = 0.f;
+        Wt::accum(a, w[u]);
+        store_grad<V>(grad, v, a);
+      }
+    }
+  }
+}
+
 template <bool kBf16, int kAlgo>
 __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, float* __restrict__ grad,
                                                                  size_t n, float scale) {
@@ -189,20 +238,12 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
   if (kAlgo == kOneShot) {
     const size_t per = (nv + B - 1) / B;
     const size_t lo = min((size_t)b * per, nv), hi = min(lo + per, nv);
-    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-      float f[V];
-      load_grad<V>(grad, v, f);
-      my_stage[v] = Wt::pack(f, scale);
-    }
+    pack_range<kBf16>(grad, my_stage, lo, hi, scale);
   } else {
     for (int r = 0; r < W; ++r) {
       size_t lo, hi;
       sub_range(nv, W, B, r, b, lo, hi);
-      for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-        float f[V];
-        load_grad<V>(grad, v, f);
-        my_stage[v] = Wt::pack(f, scale);
-      }
+      pack_range<kBf16>(grad, my_stage, lo, hi, scale);
     }
   }
   peer_block_barrier(c, &s_epoch);
@@ -246,9 +287,18 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
     } else {
       const char* mc_stage = c.mc_base - kFlagBytes + stage_off;
       char* mc_out = c.mc_base - kFlagBytes + out_off;
-      for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-        const uint4 o = Wt::mc_ld_reduce(mc_stage + v * 16);   // reduced inside the NVSwitch
-        mc_st(mc_out + v * 16, o);                             // broadcast by the NVSwitch
+      for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * kUnroll) {
+        uint4 o[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const size_t v = v0 + (size_t)u * blockDim.x;
+          if (v < hi) o[u] = Wt::mc_ld_reduce(mc_stage + v * 16);   // reduced inside the NVSwitch
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const size_t v = v0 + (size_t)u * blockDim.x;
+          if (v < hi) mc_st(mc_out + v * 16, o[u]);                 // broadcast by the NVSwitch
+        }
       }
     }
     peer_block_barrier(c, &s_epoch);
@@ -256,13 +306,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
     for (int r = 0; r < W; ++r) {
       size_t l2, h2;
       sub_range(nv, W, B, r, b, l2, h2);
-      for (size_t v = l2 + threadIdx.x; v < h2; v += blockDim.x) {
-        float a[V];
-#pragma unroll
-        for (int i = 0; i < V; ++i) a[i] = 0.f;
-        Wt::accum(a, my_out[v]);
-        store_grad<V>(grad, v, a);
-      }
+      unpack_range<kBf16>(grad, my_out, l2, h2);
     }
   }
   __syncthreads();
@@ -364,8 +408,9 @@ void hz_comm_set_multicast(HzComm* c, void* mc_ptr, void* local_ptr, size_t byte
 int hz_comm_blocks_for(HzComm* c, size_t n, int algo, int wire_bf16) {
   const int V = wire_bf16 ? 8 : 4;
   const size_t nv = n / V;
-  // ~8 vectors per thread; one-shot (latency-bound) prefers fewer, fatter blocks
-  size_t want = (nv + (size_t)hz::kCommThreads * 8 - 1) / ((size_t)hz::kCommThreads * 8);
+  // ~4 vectors (64 B) per thread and phase: enough CTAs to pull HBM + NVLink bandwidth on big buckets,
+  // a single CTA for latency-bound small ones
+  size_t want = (nv + (size_t)hz::kCommThreads * 4 - 1) / ((size_t)hz::kCommThreads * 4);
   if (want < 1) want = 1;
   if (want > (size_t)c->max_blocks) want = c->max_blocks;
   (void)algo;

@@ -20,7 +20,7 @@
 //       written / accumulated directly into the flat gradient bucket (no flatten copy).
 //
 // Warp roles (128 threads, one output tile per CTA): warp0/lane0 TMA producer, warp1/lane0 MMA issuer,
-// all four warps epilogue (each owns its 32 TMEM lanes).  4-stage smem ring, mbarrier full/empty pairs,
+// all four warps epilogue (each owns its 32 TMEM lanes).  6-stage smem ring, mbarrier full/empty pairs,
 // tcgen05.commit releases stages and signals the epilogue.
 #include <cuda.h>
 #include <cstdio>
@@ -32,7 +32,7 @@
 
 namespace hz {
 
-constexpr int kStages = 4;
+constexpr int kStages = 6;
 constexpr int kTileM = 128;
 constexpr int kKBlock = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kTileM * 128;             // 16 KB
@@ -595,7 +595,7 @@ int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W,
   p.n_tiles = Cin / BLOCK_N;
   const int m_tiles = (Cout + 127) / 128;
   const int ctas = m_tiles * p.n_tiles * p.taps.n;
-  int splits = (120 + ctas - 1) / ctas;
+  int splits = (72 + ctas - 1) / ctas;      // leave SMs for the concurrently running dgrad chain
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits > 32) splits = 32;
   if (splits < 1) splits = 1;

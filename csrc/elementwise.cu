@@ -179,12 +179,118 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
   }
 }
 
+// Single-kernel BN backward: per-channel reduction -> device-wide barrier -> apply.
+// grid <= #SMs so all CTAs are co-resident (the barrier spins); sums[2C] and the barrier counter come
+// pre-zeroed from the statistics arena.
+HZ_DEVINL unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) bn_act_bwd_fused_kernel(
+    const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ outp,
+    const __nv_bfloat16* __restrict__ yraw, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, float* __restrict__ sums,
+    unsigned* __restrict__ counter, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int acc_gamma, int acc_beta, int M, int C,
+    int relu) {
+  extern __shared__ float sm[];      // phase 1: red[256*16]   phase 2: k,a,b,mu,is [5C]
+  {
+    float* red = sm;
+    const int nvec = C >> 3;
+    const int rlanes = 256 / nvec;
+    const int vec = threadIdx.x % nvec, rl = threadIdx.x / nvec;
+    float s[8], q[8], mu8[8], is8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = q[i] = 0.f; mu8[i] = mean[vec * 8 + i]; is8[i] = invstd[vec * 8 + i]; }
+    for (int r = blockIdx.x * rlanes + rl; r < M; r += gridDim.x * rlanes) {
+      const size_t off = (size_t)r * C + vec * 8;
+      float f[8], y[8];
+      unpack8(ld8(dout + off), f);
+      unpack8(ld8(yraw + off), y);
+      if (relu) {
+        float o[8];
+        unpack8(ld8(outp + off), o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = o[i] > 0.f ? f[i] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * (y[i] - mu8[i]) * is8[i]; }
+    }
+    float* mine = red + ((size_t)rl * nvec + vec) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
+    __syncthreads();
+    for (int o = threadIdx.x; o < nvec * 16; o += 256) {
+      const int v = o >> 4, j = o & 15;
+      float t = 0.f;
+      for (int k = 0; k < rlanes; ++k) t += red[((size_t)k * nvec + v) * 16 + j];
+      atomicAdd(&sums[(j >> 3) * C + v * 8 + (j & 7)], t);
+    }
+  }
+  // ---- device-wide barrier
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu_u32(counter) < gridDim.x) {
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+  // ---- apply
+  float *k = sm, *a = sm + C, *b = sm + 2 * C, *mu = sm + 3 * C, *is = sm + 4 * C;
+  const float inv_cnt = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float i_s = invstd[c];
+    const float sg = __ldcg(&sums[c]), sq = __ldcg(&sums[C + c]);
+    k[c] = gamma[c] * i_s;
+    a[c] = sg * inv_cnt;
+    b[c] = sq * inv_cnt;
+    mu[c] = mean[c];
+    is[c] = i_s;
+    if (blockIdx.x == 0) {
+      if (dgamma != nullptr) dgamma[c] = (acc_gamma ? dgamma[c] : 0.f) + sq;
+      if (dbeta != nullptr) dbeta[c] = (acc_beta ? dbeta[c] : 0.f) + sg;
+    }
+  }
+  __syncthreads();
+  const int nvec = C >> 3;
+  const size_t total = (size_t)M * nvec;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+       v += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % nvec) * 8;
+    float g[8], y[8];
+    unpack8(ld8(dout + v * 8), g);
+    unpack8(ld8(yraw + v * 8), y);
+    if (relu) {
+      float o[8];
+      unpack8(ld8(outp + v * 8), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+    }
+    if (dres != nullptr) st8(dres + v * 8, pack8(g));
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      const float xh = (y[i] - mu[c]) * is[c];
+      d[i] = k[c] * (g[i] - a[c] - xh * b[c]);
+    }
+    st8(dy + v * 8, pack8(d));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // max-pool 3x3 / stride 2 / pad 1, NHWC; backward recomputes the (first) arg-max: no index tensor
 // ------------------------------------------------------------------------------------------------
+// forward also records the window position (0..8, row-major) of the first maximum: backward is a gather
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
-                                                          __nv_bfloat16* __restrict__ y, int N, int H,
-                                                          int W, int C, int Ho, int Wo) {
+                                                          __nv_bfloat16* __restrict__ y,
+                                                          uint8_t* __restrict__ idx, int N, int H, int W, int C,
+                                                          int Ho, int Wo) {
   const int nvec = C >> 3;
   const size_t total = (size_t)N * Ho * Wo * nvec;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
@@ -195,29 +301,38 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* _
     const int ho = (int)(p % Ho);
     const int n = (int)(p / Ho);
     float m[8];
+    int am[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    for (int i = 0; i < 8; ++i) { m[i] = -INFINITY; am[i] = 0; }
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int h = ho * 2 - 1 + r;
       if (h < 0 || h >= H) continue;
+#pragma unroll
       for (int s = 0; s < 3; ++s) {
         const int w = wo * 2 - 1 + s;
         if (w < 0 || w >= W) continue;
         float f[8];
         unpack8(ld8(x + (((size_t)n * H + h) * W + w) * C + cv * 8), f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+        for (int i = 0; i < 8; ++i)
+          if (f[i] > m[i]) { m[i] = f[i]; am[i] = r * 3 + s; }
       }
     }
     st8(y + v * 8, pack8(m));
+    if (idx != nullptr) {
+      uint2 pk;
+      pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+      pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+      *reinterpret_cast<uint2*>(idx + v * 8) = pk;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                          const __nv_bfloat16* __restrict__ x,
-                                                          const __nv_bfloat16* __restrict__ y,
-                                                          __nv_bfloat16* __restrict__ dx, int N, int H,
-                                                          int W, int C, int Ho, int Wo) {
+                                                          const uint8_t* __restrict__ idx,
+                                                          __nv_bfloat16* __restrict__ dx, int N, int H, int W,
+                                                          int C, int Ho, int Wo) {
   const int nvec = C >> 3;
   const size_t total = (size_t)N * H * W * nvec;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
@@ -227,38 +342,24 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
     const int w = (int)(p % W); p /= W;
     const int h = (int)(p % H);
     const int n = (int)(p / H);
-    float xv[8], acc[8];
-    unpack8(ld8(x + v * 8), xv);
+    float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // windows (ho,wo) that contain (h,w): ho in {(h+1)/2 - 1 .. (h+1)/2} intersect valid
-    for (int ho = (h + 1) / 2 - ((h + 1) % 2 == 0 ? 1 : 0); ho <= (h + 1) / 2; ++ho) {
-      if (ho < 0 || ho >= Ho) continue;
-      for (int wo = (w + 1) / 2 - ((w + 1) % 2 == 0 ? 1 : 0); wo <= (w + 1) / 2; ++wo) {
-        if (wo < 0 || wo >= Wo) continue;
+    for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho >= Ho) continue;
+      const int r = h - (ho * 2 - 1);
+      for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo >= Wo) continue;
+        const int me = r * 3 + (w - (wo * 2 - 1));
         const size_t oo = (((size_t)n * Ho + ho) * Wo + wo) * C + cv * 8;
-        float yv[8], gv[8];
-        unpack8(ld8(y + oo), yv);
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + oo);
+        float gv[8];
         unpack8(ld8(dy + oo), gv);
-        // is (h,w) the FIRST position (row-major scan) in this window attaining the max?
-        bool hit[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) hit[i] = (xv[i] == yv[i]);
-        for (int r = 0; r < 3; ++r) {
-          const int hh = ho * 2 - 1 + r;
-          if (hh < 0 || hh >= H) continue;
-          for (int s = 0; s < 3; ++s) {
-            const int ww = wo * 2 - 1 + s;
-            if (ww < 0 || ww >= W) continue;
-            if (hh > h || (hh == h && ww >= w)) continue;   // only earlier positions
-            float e[8];
-            unpack8(ld8(x + (((size_t)n * H + hh) * W + ww) * C + cv * 8), e);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hit[i] = hit[i] && !(e[i] == yv[i]);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int a = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xFF;
+          acc[i] += (a == me) ? gv[i] : 0.f;
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += hit[i] ? gv[i] : 0.f;
       }
     }
     st8(dx + v * 8, pack8(acc));
@@ -275,9 +376,13 @@ __global__ void u8_normalize_kernel(const uint8_t* __restrict__ in, __nv_bfloat1
     out[i] = __float2bfloat16_rn(((float)in[i] * (1.f / 255.f) - mean) * inv_std);
 }
 
+template <int CIN, int RR, int SS>
 __global__ void __launch_bounds__(256) im2col_small_cin_kernel(
-    const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A, int N, int H, int W, int Cin,
-    int R, int S, int stride, int pad, int Ho, int Wo, int K, int Kp) {
+    const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A, int N, int H, int W, int Cin_,
+    int R_, int S_, int stride, int pad, int Ho, int Wo, int K, int Kp) {
+  const int Cin = CIN > 0 ? CIN : Cin_;
+  const int S = SS > 0 ? SS : S_;
+  (void)R_;
   const int kvec = Kp >> 3;
   const size_t total = (size_t)N * Ho * Wo * kvec;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
@@ -391,34 +496,45 @@ __global__ void __launch_bounds__(128) head_sample_kernel(
   }
 }
 
-// thread = one input channel c, 16 classes in registers; dlogits tile staged in smem
+// CTA = 32 input channels x 4 sample groups; 16 classes in registers; dlogits tile staged in smem
 __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict__ pooled,
                                                          const float* __restrict__ dlogits,
                                                          float* __restrict__ dW, float* __restrict__ db,
                                                          int N, int C, int K, int accumulate) {
-  extern __shared__ float dl[];                 // [N][16]
+  extern __shared__ float hsm[];                // dl[N][16] | part[4][32][16]
+  float* dl = hsm;
+  float* part = hsm + N * 16;
   const int k0 = blockIdx.y * 16;
   for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
     const int n = i >> 4, j = i & 15;
     dl[i] = (k0 + j < K) ? dlogits[(size_t)n * K + k0 + j] : 0.f;
   }
   __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    float acc[16];
+  const int cl = threadIdx.x & 31, ng = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float acc[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    for (int n = 0; n < N; ++n) {
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  if (c < C) {
+#pragma unroll 4
+    for (int n = ng; n < N; n += 4) {
       const float pv = pooled[(size_t)n * C + c];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] += dl[n * 16 + j] * pv;
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (k0 + j < K) {
-        const size_t o = (size_t)(k0 + j) * C + c;
-        dW[o] = (accumulate ? dW[o] : 0.f) + acc[j];
-      }
+  for (int j = 0; j < 16; ++j) part[(ng * 32 + cl) * 16 + j] = acc[j];
+  __syncthreads();
+  // 32 channels x 16 classes = 512 outputs, 128 threads x 4
+  for (int o = threadIdx.x; o < 512; o += 128) {
+    const int cc = o >> 4, j = o & 15;
+    const float t = part[(0 * 32 + cc) * 16 + j] + part[(1 * 32 + cc) * 16 + j] + part[(2 * 32 + cc) * 16 + j] +
+                    part[(3 * 32 + cc) * 16 + j];
+    const int ch = blockIdx.x * 32 + cc;
+    if (ch < C && k0 + j < K) {
+      const size_t oo = (size_t)(k0 + j) * C + ch;
+      dW[oo] = (accumulate ? dW[oo] : 0.f) + t;
     }
   }
   if (db != nullptr && blockIdx.x == 0 && threadIdx.x < 16 && k0 + threadIdx.x < K) {
@@ -593,6 +709,17 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
                    const float* invstd, const float* gamma, float* sums_scratch, void* dy, void* dres,
                    float* dgamma, float* dbeta, int acc_gamma, int acc_beta, int M, int C, int relu,
                    int scratch_is_zero, cudaStream_t st) {
+  if (scratch_is_zero == 2) {
+    // arena slice [2C sums | 32-float pad holding the barrier counter], all zero: one fused kernel
+    int grid = grid_for((size_t)M * (C / 8), 256, 148);
+    size_t smem = sizeof(float) * 256 * 16;
+    if (smem < sizeof(float) * 5 * C) smem = sizeof(float) * 5 * C;
+    hz::bn_act_bwd_fused_kernel<<<grid, 256, smem, st>>>(
+        (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd, gamma,
+        sums_scratch, (unsigned*)(sums_scratch + 2 * C), (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta,
+        acc_gamma, acc_beta, M, C, relu);
+    return;
+  }
   if (!scratch_is_zero) cudaMemsetAsync(sums_scratch, 0, sizeof(float) * 2 * C, st);
   const size_t smem_r = sizeof(float) * 256 * 16;
   hz::channel_reduce_kernel<true><<<reduce_grid(M, C), 256, smem_r, st>>>(
@@ -605,18 +732,16 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
       M, C, relu);
 }
 
-void hz_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st) {
+void hz_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, cudaStream_t st) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   hz::maxpool_fwd_kernel<<<grid_for((size_t)N * Ho * Wo * (C / 8), 256), 256, 0, st>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, Ho, Wo);
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)idx, N, H, W, C, Ho, Wo);
 }
 
-void hz_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H, int W, int C,
-                    cudaStream_t st) {
+void hz_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, cudaStream_t st) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   hz::maxpool_bwd_kernel<<<grid_for((size_t)N * H * W * (C / 8), 256), 256, 0, st>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, N,
-      H, W, C, Ho, Wo);
+      (const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
 }
 
 void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std, cudaStream_t st) {
@@ -626,9 +751,13 @@ void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std,
 
 void hz_im2col_small(const void* x, void* A, int N, int H, int W, int Cin, int R, int S, int stride,
                      int pad, int Ho, int Wo, int Kp, cudaStream_t st) {
-  hz::im2col_small_cin_kernel<<<grid_for((size_t)N * Ho * Wo * (Kp / 8), 256), 256, 0, st>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W, Cin, R, S, stride, pad, Ho, Wo, R * S * Cin,
-      Kp);
+  const int grid = grid_for((size_t)N * Ho * Wo * (Kp / 8), 256, 148 * 16);
+  if (Cin == 3 && R == 7 && S == 7)
+    hz::im2col_small_cin_kernel<3, 7, 7><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W,
+                                                                Cin, R, S, stride, pad, Ho, Wo, R * S * Cin, Kp);
+  else
+    hz::im2col_small_cin_kernel<0, 0, 0><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W,
+                                                                Cin, R, S, stride, pad, Ho, Wo, R * S * Cin, Kp);
 }
 
 void hz_pad_rows(const void* in, void* out, int rows, int K, int Kp, cudaStream_t st) {
@@ -639,15 +768,18 @@ void hz_pad_rows(const void* in, void* out, int rows, int K, int Kp, cudaStream_
 void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const int64_t* labels,
                      float* pooled, float* dlogits, float* logits, void* dfeat, float* loss,
                      float* correct, float* dW, float* db, int N, int C, int HW, int K, int n_valid,
-                     float loss_scale, int accumulate, cudaStream_t st) {
-  cudaMemsetAsync(loss, 0, sizeof(float), st);
-  cudaMemsetAsync(correct, 0, sizeof(float), st);
+                     float loss_scale, int accumulate, int out_is_zero, cudaStream_t st) {
+  if (!out_is_zero) {
+    cudaMemsetAsync(loss, 0, sizeof(float), st);
+    cudaMemsetAsync(correct, 0, sizeof(float), st);
+  }
   const size_t smem = sizeof(float) * (C + 2 * hz::kHeadMaxK);
   hz::head_sample_kernel<<<N, 128, smem, st>>>((const __nv_bfloat16*)feat, W, bias, labels, pooled,
                                                dlogits, logits, (__nv_bfloat16*)dfeat, loss, correct, N,
                                                C, HW, K, n_valid, loss_scale);
-  dim3 grid((C + 127) / 128, (K + 15) / 16);
-  hz::head_wgrad_kernel<<<grid, 128, sizeof(float) * N * 16, st>>>(pooled, dlogits, dW, db, N, C, K, accumulate);
+  dim3 grid((C + 31) / 32, (K + 15) / 16);
+  hz::head_wgrad_kernel<<<grid, 128, sizeof(float) * (N * 16 + 4 * 32 * 16), st>>>(pooled, dlogits, dW, db, N, C, K,
+                                                                                  accumulate);
 }
 
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,

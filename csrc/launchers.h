@@ -18,9 +18,8 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
                    const float* invstd, const float* gamma, float* sums_scratch, void* dy, void* dres,
                    float* dgamma, float* dbeta, int acc_gamma, int acc_beta, int M, int C, int relu,
                    int scratch_is_zero, cudaStream_t st);
-void hz_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st);
-void hz_maxpool_bwd(const void* dy, const void* x, const void* y, void* dx, int N, int H, int W, int C,
-                    cudaStream_t st);
+void hz_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, cudaStream_t st);
+void hz_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, cudaStream_t st);
 void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std, cudaStream_t st);
 void hz_im2col_small(const void* x, void* A, int N, int H, int W, int Cin, int R, int S, int stride, int pad,
                      int Ho, int Wo, int Kp, cudaStream_t st);
@@ -28,7 +27,7 @@ void hz_pad_rows(const void* in, void* out, int rows, int K, int Kp, cudaStream_
 void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const int64_t* labels, float* pooled,
                      float* dlogits, float* logits, void* dfeat, float* loss, float* correct, float* dW,
                      float* db, int N, int C, int HW, int K, int n_valid, float loss_scale, int accumulate,
-                     cudaStream_t st);
+                     int out_is_zero, cudaStream_t st);
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
              int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, cudaStream_t st);
 void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st);

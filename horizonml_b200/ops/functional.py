@@ -196,19 +196,18 @@ def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True,
 class _MaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        y = _be(x).maxpool_fwd(x)
-        ctx.save_for_backward(x, y)
+        ctx.be = _be(x)
+        y, ctx.aux = ctx.be.maxpool_fwd(x, True)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y = ctx.saved_tensors
-        return _be(x).maxpool_bwd(dy.contiguous(memory_format=torch.channels_last), x, y)
+        return ctx.be.maxpool_bwd(dy.contiguous(memory_format=torch.channels_last), ctx.aux)
 
 
 def maxpool3x3s2(x):
     if not x.requires_grad or not torch.is_grad_enabled():
-        return _be(x).maxpool_fwd(x)
+        return _be(x).maxpool_fwd(x, False)[0]
     return _MaxPool.apply(x)
 
 

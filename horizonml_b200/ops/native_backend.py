@@ -132,8 +132,10 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma
         else:
             dg, ag, db, ab = dgamma_slot.t, dgamma_slot.acc, dbeta_slot.t, dbeta_slot.acc
         LAUNCHES["bn_act_bwd"] += 2
+        scratch = ARENA.take(1, 2 * c + 32, y_raw.device)      # [Σg | Σg·x̂ | barrier counter], pre-zeroed
+        LAUNCHES["bn_act_bwd"] -= 1 if scratch is not None else 0
         dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dg, db, ag, ab,
-                                ARENA.take(2, c, y_raw.device))
+                                scratch)
         return dy, dg, db, (dres if has_residual else None)
     _fallback("bn_act_bwd", f"{tuple(y_raw.shape)}")
     return _tb.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot, dbeta_slot)
@@ -176,20 +178,20 @@ def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, ac
     _tb.conv_wgrad(dy, x, w_shape, stride, pad, out_grad, accumulate)
 
 
-def maxpool_fwd(x):
+def maxpool_fwd(x, want_aux: bool = False):
     if _bf16_cl(x) and x.shape[1] % 8 == 0:
         LAUNCHES["maxpool"] += 1
-        return C.maxpool_fwd(x)
+        y, idx = C.maxpool_fwd(x, want_aux)
+        return y, (("native", idx, tuple(x.shape)) if want_aux else None)
     _fallback("maxpool_fwd", str(tuple(x.shape)))
-    return _tb.maxpool_fwd(x)
+    return _tb.maxpool_fwd(x, want_aux)
 
 
-def maxpool_bwd(dy, x, y):
-    if _bf16_cl(x) and x.shape[1] % 8 == 0:
+def maxpool_bwd(dy, aux):
+    if isinstance(aux, tuple) and aux and isinstance(aux[0], str) and aux[0] == "native":
         LAUNCHES["maxpool"] += 1
-        return C.maxpool_bwd(dy, x, y)
-    _fallback("maxpool_bwd", str(tuple(x.shape)))
-    return _tb.maxpool_bwd(dy, x, y)
+        return C.maxpool_bwd(dy, aux[1], list(aux[2]))
+    return _tb.maxpool_bwd(dy, aux)
 
 
 def head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out, db_out, accumulate, need_dfeat=True):
@@ -197,7 +199,7 @@ def head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out, db_out, 
             and dw_out.is_contiguous()):
         LAUNCHES["head"] += 2
         loss, correct, dfeat, logits = C.head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out,
-                                                      db_out, accumulate, need_dfeat)
+                                                      db_out, accumulate, need_dfeat, ARENA.take(1, 2, feat.device))
         return loss, correct, (dfeat if need_dfeat else None), logits
     _fallback("head_fwd_bwd", str(tuple(feat.shape)))
     return _tb.head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out, db_out, accumulate, need_dfeat)

@@ -112,17 +112,19 @@ def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, ac
         out_grad.copy_(gw)
 
 
-def maxpool_fwd(x):
-    return _cl(F.max_pool2d(x, 3, 2, 1))
+def maxpool_fwd(x, want_aux: bool = False):
+    """3x3 / stride 2 / pad 1.  Returns (y, aux) - aux is whatever backward needs besides dy."""
+    if not want_aux:
+        return _cl(F.max_pool2d(x, 3, 2, 1)), None
+    y, idx = F.max_pool2d(x, 3, 2, 1, return_indices=True)
+    return _cl(y), (idx, tuple(x.shape))
 
 
-def maxpool_bwd(dy, x, y):
-    # recompute-style backward (no saved indices): route gradient to the arg-max positions
-    xf = x.detach().float().requires_grad_(True)
-    with torch.enable_grad():
-        yy = F.max_pool2d(xf, 3, 2, 1)
-    (dx,) = torch.autograd.grad(yy, xf, dy.float())
-    return _cl(dx.to(x.dtype))
+def maxpool_bwd(dy, aux):
+    idx, x_shape = aux
+    dx = torch.ops.aten.max_pool2d_with_indices_backward(
+        dy.contiguous(), dy.new_empty(x_shape), [3, 3], [2, 2], [1, 1], [1, 1], False, idx.contiguous())
+    return _cl(dx)
 
 
 def head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale: float, n_valid: int,

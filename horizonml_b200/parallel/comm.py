@@ -74,7 +74,7 @@ class PeerAllReduce(GradAllReduce):
     name = "peer"
 
     def __init__(self, max_numel: int, device, group=None, algo: str = "auto", wire: str = "bf16",
-                 max_blocks: int = 32):
+                 max_blocks: int = 96):
         super().__init__(group)
         from ..ops import _ext
         self.C = _ext.load(required=True)
