@@ -228,13 +228,14 @@ Tensor conv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shap
 
 // dw_out: fp32 tensor whose storage is [Cout, R, S, Cin]-physical (a view of the flat gradient bucket)
 void conv_wgrad(const Tensor& dy, const Tensor& x, Tensor dw_out, int64_t R, int64_t stride, int64_t pad,
-                bool accumulate, int64_t ld_out, int64_t n_valid) {
+                bool accumulate, bool prezeroed, int64_t ld_out, int64_t n_valid) {
   check_cl(dy, "dy"); check_cl(x, "x");
   TORCH_CHECK(dw_out.scalar_type() == at::kFloat);
   c10::cuda::CUDAGuard g(dy.device());
   auto d = dims_of(x);
   int rc = hz_conv_wgrad(cptr(dy), cptr(x), dw_out.data_ptr<float>(), d.N, d.H, d.W, d.C, (int)dy.size(1), (int)R,
-                         (int)stride, (int)pad, accumulate ? 1 : 0, (long long)ld_out, (int)n_valid, cur_stream());
+                         (int)stride, (int)pad, accumulate ? 1 : 0, prezeroed ? 1 : 0, (long long)ld_out, (int)n_valid,
+                         cur_stream());
   TORCH_CHECK(rc == 0, "hz_conv_wgrad failed rc=", rc);
 }
 

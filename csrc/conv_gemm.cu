@@ -24,6 +24,7 @@
 // tcgen05.commit releases stages and signals the epilogue.
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -56,6 +57,9 @@ struct IgemmParams {
   int BN, BH, BW, tiles_per_img;
   int n_images;
   int ncols;                 // valid output columns (Cout / Cin total)
+  int splits;                // split-K factor (blockIdx.z = class * splits + split)
+  float* ws;                 // fp32 split-K workspace [tiles][128][BLOCK_N], all-zero between launches
+  unsigned* sem;             // per-tile arrival counters, all-zero between launches
   __nv_bfloat16* out;
   float* stats;              // [2*ncols] or null
 };
@@ -84,11 +88,16 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y, cls = blockIdx.z;
+  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int cls = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const TapList& taps = p.cls[cls];
   const int n0 = (p.BN == 1) ? mt / p.tiles_per_img : mt * p.BN;
   const int h0 = (p.BN == 1) ? (mt % p.tiles_per_img) * p.BH : 0;
-  const int k_iters = taps.n * p.cblocks;
+  // split-K: one SM pulls only ~80 GB/s out of L2, so the K loop of a tile is spread over `splits` CTAs
+  const int k_total = taps.n * p.cblocks;
+  const int k_per = (k_total + p.splits - 1) / p.splits;
+  const int k_lo = min(split * k_per, k_total);
+  const int k_iters = min(k_lo + k_per, k_total) - k_lo;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) tc::prefetch_tmap(&amaps.m[i]);
@@ -108,25 +117,23 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    int it = 0;
-    for (int t = 0; t < taps.n; ++t) {
+    for (int it = 0; it < k_iters; ++it) {
+      const int t = (k_lo + it) / p.cblocks, cb = (k_lo + it) % p.cblocks;
       const CUtensorMap* am = &amaps.m[taps.map[t]];
       const int cw = taps.dw[t], ch = h0 + taps.dh[t];
-      for (int cb = 0; cb < p.cblocks; ++cb, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        tc::mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sa = smem + s * S::kStageBytes;
-        uint8_t* sb = sa + kABytes;
-        tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
-        tc::tma_load_4d(sa, am, &full[s], cb * kKBlock, cw, ch, n0);
-        if (!B_MN) {
-          tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[t] + cb * kKBlock, nt * BLOCK_N);
-        } else {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      tc::mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* sa = smem + s * S::kStageBytes;
+      uint8_t* sb = sa + kABytes;
+      tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+      tc::tma_load_4d(sa, am, &full[s], cb * kKBlock, cw, ch, n0);
+      if (!B_MN) {
+        tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[t] + cb * kKBlock, nt * BLOCK_N);
+      } else {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            tc::tma_load_2d(sb + j * 8192, &bmap, &full[s], taps.bk[t] + nt * BLOCK_N + j * 64, cb * kKBlock);
-        }
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tc::tma_load_2d(sb + j * 8192, &bmap, &full[s], taps.bk[t] + nt * BLOCK_N + j * 64, cb * kKBlock);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       }
       tc::umma_commit(&empty[s]);
     }
-    tc::umma_commit(tmem_full);
+    if (k_iters > 0) tc::umma_commit(tmem_full);
   }
   __syncwarp();
 
@@ -158,24 +165,72 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   if (k_iters > 0) {
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
+  }
+  if (p.splits == 1) {
+    if (k_iters > 0) {
 #pragma unroll
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t r[32];
-      tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
-      tc::tmem_ld_wait();
-      __nv_bfloat16* dst = staging + row * S::kStagingLd + c0;
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tc::tmem_ld_wait();
+        __nv_bfloat16* dst = staging + row * S::kStagingLd + c0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float f[8];
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[j + i]);
-        st8(dst + j, pack8(f));
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[j + i]);
+          st8(dst + j, pack8(f));
+        }
       }
+    } else {
+      // a class with no taps (1x1 stride-2 dgrad, odd parities): the gradient is exactly zero
+      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 8) st8(staging + row * S::kStagingLd + c0, pack8(z));
     }
   } else {
-    // a class with no taps (1x1 stride-2 dgrad, odd parities): the gradient is exactly zero
-    float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 8) st8(staging + row * S::kStagingLd + c0, pack8(z));
+    // ---- split-K: accumulate the partial tile into the fp32 workspace (vector red), the last-arriving
+    //      CTA of the tile turns the sum into the output tile and leaves workspace + counter zeroed
+    const int tile = (cls * gridDim.y + nt) * gridDim.x + mt;
+    float* wrow = p.ws + ((size_t)tile * kTileM + row) * BLOCK_N;
+    if (k_iters > 0) {
+#pragma unroll
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + c0 + j),
+                       "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
+                       "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                       : "memory");
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+      const unsigned old = atomicAdd(&p.sem[tile], 1u);
+      const int last = (old == (unsigned)(p.splits - 1));
+      if (last) { p.sem[tile] = 0u; __threadfence(); }
+      s_last = last;
+    }
+    __syncthreads();
+    if (!s_last) {                       // uniform per CTA
+      tc::fence_before_sync();
+      __syncthreads();
+      if (warp == 2) tc::tmem_dealloc(tmem_d, BLOCK_N);
+      return;
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 8) {
+      const float4 a = __ldcg(reinterpret_cast<const float4*>(wrow + c0));
+      const float4 b = __ldcg(reinterpret_cast<const float4*>(wrow + c0 + 4));
+      __stcg(reinterpret_cast<float4*>(wrow + c0), make_float4(0.f, 0.f, 0.f, 0.f));
+      __stcg(reinterpret_cast<float4*>(wrow + c0 + 4), make_float4(0.f, 0.f, 0.f, 0.f));
+      const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      st8(staging + row * S::kStagingLd + c0, pack8(f));
+    }
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -226,7 +281,7 @@ struct WgradParams {
   int Cout;
   long long ld_out, tap_stride;  // dW row stride / per-tap column offset (elements)
   int n_valid;                   // valid columns per tap (Cin, or 147 for the padded stem)
-  int accumulate;
+  int mode;                      // 0 = store, 1 = read-add-store, 2 = atomic add (split-K)
   float* out;
 };
 
@@ -314,25 +369,55 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ CUte
   }
   __syncwarp();
 
-  const int co = mt * 128 + warp * 32 + lane;
+  // epilogue: TMEM -> fp32 tile in smem (pipeline buffers are idle now) -> coalesced row-wise float4 writes
+  constexpr int kLd = BLOCK_N + 4;                       // fp32 words per staged row (conflict-free 16B rows)
+  float* tile = reinterpret_cast<float*>(smem);
   if (k_iters > 0) {
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
-    float* orow = p.out + (long long)co * p.ld_out + (long long)p.taps.bk[t] * p.tap_stride + nt * BLOCK_N;
-    const bool atomic = p.splits > 1;
+    const int row = warp * 32 + lane;
 #pragma unroll
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
       tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
       tc::tmem_ld_wait();
-      if (co < p.Cout) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = nt * BLOCK_N + c0 + j;
-          if (c < p.n_valid) {
-            const float v = __uint_as_float(r[j]);
-            if (atomic) atomicAdd(orow + c0 + j, v);
-            else orow[c0 + j] = (p.accumulate ? orow[c0 + j] : 0.f) + v;
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(tile + row * kLd + c0 + j) =
+            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                        __uint_as_float(r[j + 3]));
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (k_iters > 0) {
+    constexpr int kChunks = BLOCK_N / 4;                 // float4 chunks per row
+    const bool vec_ok = ((p.ld_out | p.tap_stride) & 3) == 0 && (p.n_valid & 3) == 0;
+    for (int idx = threadIdx.x; idx < kTileM * kChunks; idx += 128) {
+      const int r = idx / kChunks, ch = idx % kChunks;
+      const int co = mt * 128 + r;
+      if (co >= p.Cout) continue;
+      const int c = nt * BLOCK_N + ch * 4;
+      float* dst = p.out + (long long)co * p.ld_out + (long long)p.taps.bk[t] * p.tap_stride + c;
+      const float4 v = *reinterpret_cast<const float4*>(tile + r * kLd + ch * 4);
+      if (vec_ok && c + 3 < p.n_valid) {
+        if (p.mode == 2) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z),
+                       "f"(v.w) : "memory");
+        } else if (p.mode == 1) {
+          float4 o = *reinterpret_cast<float4*>(dst);
+          o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+          *reinterpret_cast<float4*>(dst) = v;
+        }
+      } else {
+        const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (c + j < p.n_valid) {
+            if (p.mode == 2) atomicAdd(dst + j, f[j]);
+            else dst[j] = (p.mode == 1 ? dst[j] : 0.f) + f[j];
           }
         }
       }
@@ -461,6 +546,37 @@ void input_taps(hz::TapList* tl, int R, int S, int stride, int pad, int Ho, int 
     }
 }
 
+// persistent split-K workspace (per device): self-cleaning, so it is zeroed exactly once
+constexpr size_t kWsTiles = 512;
+struct SplitWs { float* ws = nullptr; unsigned* sem = nullptr; };
+SplitWs get_split_ws() {
+  static SplitWs per_dev[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SplitWs& w = per_dev[dev & 15];
+  if (w.ws == nullptr) {
+    const size_t bytes = kWsTiles * 128 * 64 * sizeof(float);
+    if (cudaMalloc(&w.ws, bytes + kWsTiles * sizeof(unsigned)) != cudaSuccess) { w.ws = nullptr; return w; }
+    cudaMemset(w.ws, 0, bytes + kWsTiles * sizeof(unsigned));
+    w.sem = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(w.ws) + bytes);
+  }
+  return w;
+}
+int pick_splits(int tiles, int k_total) {
+  // Measured on B200: accumulating 32 KB fp32 tiles with red.global.add.v4.f32 costs more than the
+  // K-loop time it saves (layer1 conv 7.7 -> 26 us), so workspace split-K stays opt-in (HZ_SPLITK=1).
+  static const bool enabled = [] { const char* e = getenv("HZ_SPLITK"); return e && e[0] == '1'; }();
+  if (!enabled) return 1;
+  if (tiles <= 0 || k_total <= 1 || (size_t)tiles > kWsTiles) return 1;
+  int s = 132 / tiles;
+  if (s > k_total) s = k_total;
+  if (s < 1) s = 1;
+  // never leave a split with nothing to do
+  const int per = (k_total + s - 1) / s;
+  s = (k_total + per - 1) / per;
+  return s;
+}
+
 template <typename K>
 bool set_smem(K kernel, int bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
@@ -507,10 +623,16 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   p.out = (__nv_bfloat16*)y;
   p.stats = stats;
   if (stats && !stats_is_zero) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, st);
+  {
+    const SplitWs w = get_split_ws();
+    const int tiles = t.tiles * (Cout / BLOCK_N);
+    p.splits = w.ws ? pick_splits(tiles, p.cls[0].n * p.cblocks) : 1;
+    p.ws = w.ws; p.sem = w.sem;
+  }
   using SM = hz::IgemmSmem<BLOCK_N>;
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, false>, SM::kTotal);
   (void)attr;
-  dim3 grid(t.tiles, Cout / BLOCK_N, 1);
+  dim3 grid(t.tiles, Cout / BLOCK_N, p.splits);
   hz::igemm_kernel<BLOCK_N, false><<<grid, 128, SM::kTotal, st>>>(am, bm, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -564,17 +686,26 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, 
   p.ncols = Cin;
   p.out = (__nv_bfloat16*)dx;
   p.stats = nullptr;
+  {
+    const SplitWs w = get_split_ws();
+    const int tiles = t.tiles * (Cin / BLOCK_N) * p.num_classes;
+    int kmax = 0;
+    for (int c = 0; c < p.num_classes; ++c) kmax = kmax > p.cls[c].n ? kmax : p.cls[c].n;
+    p.splits = w.ws ? pick_splits(tiles, kmax * p.cblocks) : 1;
+    p.ws = w.ws; p.sem = w.sem;
+  }
   using SM = hz::IgemmSmem<BLOCK_N>;
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, true>, SM::kTotal);
   (void)attr;
-  dim3 grid(t.tiles, Cin / BLOCK_N, p.num_classes);
+  dim3 grid(t.tiles, Cin / BLOCK_N, p.num_classes * p.splits);
   hz::igemm_kernel<BLOCK_N, true><<<grid, 128, SM::kTotal, st>>>(am, bm, p);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // dw[Cout, R*S*Cin (ld_out)] (+)= dy^T * x_taps.   ld_out / n_valid allow the padded stem (Cin=192 -> 147)
 int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,
-                  int stride, int pad, int accumulate, long long ld_out, int n_valid, cudaStream_t st) {
+                  int stride, int pad, int accumulate, int prezeroed, long long ld_out, int n_valid,
+                  cudaStream_t st) {
   const int S_ = R;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
   Tile t;
@@ -604,9 +735,9 @@ int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W,
   p.ld_out = ld_out > 0 ? ld_out : (long long)R * S_ * Cin;
   p.tap_stride = Cin;
   p.n_valid = n_valid > 0 ? n_valid : Cin;
-  p.accumulate = accumulate;
+  p.mode = splits > 1 ? 2 : (accumulate ? 1 : 0);
   p.out = dw;
-  if (splits > 1 && !accumulate) {
+  if (splits > 1 && !accumulate && !prezeroed) {
     // split-K accumulates with atomics: clear exactly the region this conv owns (rows are ld_out apart)
     if (p.ld_out == (long long)R * S_ * Cin || R == 1)
       cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * p.ld_out, st);

@@ -41,7 +41,8 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
 int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R,
                   int stride, int pad, cudaStream_t st);
 int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,
-                  int stride, int pad, int accumulate, long long ld_out, int n_valid, cudaStream_t st);
+                  int stride, int pad, int accumulate, int prezeroed, long long ld_out, int n_valid,
+                  cudaStream_t st);
 
 // ---- comm.cu (peer-memory all-reduce)
 struct HzComm;

@@ -122,11 +122,13 @@ class FlatParams:
         return self._bucket_of[id(p)]
 
     def begin_step(self) -> None:
-        """Start of an optimizer step.  When the optimizer zeroes the gradient buffer in its own pass
-        (``zeroed_by_optimizer``) every producer accumulates; otherwise the first write overwrites."""
-        acc = bool(getattr(self, "zeroed_by_optimizer", False))
+        """Start of an optimizer step: the first gradient write of each parameter overwrites, later ones
+        (micro-batches) accumulate.  When the optimizer clears the buffer in its own pass
+        (``zeroed_by_optimizer``) producers that add atomically need no memset either."""
+        zeroed = bool(getattr(self, "zeroed_by_optimizer", False))
         for p in self.params:
-            p._acc = acc
+            p._acc = False          # first write of the step may overwrite ...
+            p._zeroed = zeroed      # ... and split-K / atomic producers may rely on an all-zero buffer
 
     def zero_grad(self) -> None:
         self.grad.zero_()

@@ -152,6 +152,7 @@ class _ConvBNAct(torch.autograd.Function):
         grad_written(beta)
         w = compute_weight(weight, x.dtype)
         tgt, acc = grad_target(weight)
+        zeroed = bool(getattr(weight, "_zeroed", False))      # buffer known to be all-zero before this step
         if _side["enabled"] and x.is_cuda and ctx.x_needs_grad:
             if _side["stream"] is None:
                 _side["stream"] = torch.cuda.Stream(device=x.device)
@@ -159,12 +160,12 @@ class _ConvBNAct(torch.autograd.Function):
             ev.record(torch.cuda.current_stream())
             _side["stream"].wait_event(ev)
             with torch.cuda.stream(_side["stream"]):
-                be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc)
+                be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc, zeroed)
                 grad_written(weight)          # reducer hooks record their events on the side stream
             _side["keep"].append((dy, x))     # keep operands alive until join_side()
             _side["dirty"] = True
         else:
-            be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc)
+            be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc, zeroed)
             grad_written(weight)
         dx = be.conv_dgrad(dy, w, x.shape, stride, pad) if ctx.x_needs_grad else None
         if dx is not None and ctx.post_dgrad is not None:   # column-parallel conv: Σ over shards

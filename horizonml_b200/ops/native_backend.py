@@ -156,12 +156,13 @@ def _flat_dw_ok(out_grad: torch.Tensor, w_shape) -> bool:
             out_grad.permute(0, 2, 3, 1).is_contiguous())
 
 
-def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, accumulate: bool):
+def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, accumulate: bool,
+               prezeroed: bool = False):
     cout, cin, r, s = w_shape
     if _bf16_cl(dy) and _bf16_cl(x) and _flat_dw_ok(out_grad, w_shape):
         if _conv_ok(x.shape, w_shape, stride, pad):
             LAUNCHES["conv_wgrad"] += 1
-            C.conv_wgrad(dy, x, out_grad, r, stride, pad, accumulate, 0, 0)
+            C.conv_wgrad(dy, x, out_grad, r, stride, pad, accumulate, prezeroed, 0, 0)
             return
         if _is_stem(x.shape, w_shape):
             if _STEM_CACHE["key"] == (x.data_ptr(), x._version, tuple(x.shape)):
@@ -172,7 +173,7 @@ def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, ac
             n, _, ho, wo = dy.shape
             dy2 = dy.permute(0, 2, 3, 1).reshape(-1, cout, 1, 1)     # [M, Cout,1,1] (NHWC rows)
             LAUNCHES["conv_wgrad"] += 1
-            C.conv_wgrad(dy2, A.view(-1, STEM_KP, 1, 1), out_grad, 1, 1, 0, accumulate, cin * r * s, cin * r * s)
+            C.conv_wgrad(dy2, A.view(-1, STEM_KP, 1, 1), out_grad, 1, 1, 0, accumulate, prezeroed, cin * r * s, cin * r * s)
             return
     _fallback("conv_wgrad", f"x={tuple(x.shape)} w={tuple(w_shape)}")
     _tb.conv_wgrad(dy, x, w_shape, stride, pad, out_grad, accumulate)

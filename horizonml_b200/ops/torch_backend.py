@@ -99,7 +99,8 @@ def conv_dgrad(dy, w, x_shape, stride: int, pad: int):
     return _cl(dx)
 
 
-def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, accumulate: bool):
+def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, accumulate: bool,
+               prezeroed: bool = False):
     """dW written (or accumulated) as fp32 into ``out_grad`` — a view of the flat gradient bucket
     with the weight's logical shape / channels_last strides."""
     _, gw, _ = torch.ops.aten.convolution_backward(
