@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 
 #define HZ_DEVINL __device__ __forceinline__
 
@@ -46,6 +47,38 @@ HZ_DEVINL bf16x8 pack8(const float* f) {
 HZ_DEVINL bf16x8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
 HZ_DEVINL void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
 
+// Programmatic dependent launch (PDL): `pdl_launch()` lets the next kernel in the stream become resident and
+// run its prologue while this one drains; `pdl_wait()` blocks until every prerequisite grid has completed and
+// flushed its memory.  Both are no-ops when the kernel was not launched with the PDL attribute.
+HZ_DEVINL void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+HZ_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 HZ_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 }  // namespace hz
+
+// ---- host: launch with the PDL attribute (HZ_PDL=0 disables) ------------------------------------
+#ifdef __CUDACC__
+#include <cstdlib>
+namespace hz {
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("HZ_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+}  // namespace hz
+#endif

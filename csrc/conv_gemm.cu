@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   uint64_t* tmem_full = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
+  pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
   const int cls = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_wait();          // everything above overlapped the tail of the previous kernel
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ CUte
   uint64_t* tmem_full = empty + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
+  pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x / p.n_tiles, nt = blockIdx.x % p.n_tiles;
   const int t = blockIdx.y;
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const __grid_constant__ CUte
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     const CUtensorMap* xm = &xmaps.m[p.taps.map[t]];
@@ -633,8 +637,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, false>, SM::kTotal);
   (void)attr;
   dim3 grid(t.tiles, Cout / BLOCK_N, p.splits);
-  hz::igemm_kernel<BLOCK_N, false><<<grid, 128, SM::kTotal, st>>>(am, bm, p);
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  return hz::launch(hz::igemm_kernel<BLOCK_N, false>, grid, dim3(128), SM::kTotal, st, am, bm, p) == cudaSuccess ? 0 : -1;
 }
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w)
@@ -698,8 +701,7 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, 
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, true>, SM::kTotal);
   (void)attr;
   dim3 grid(t.tiles, Cin / BLOCK_N, p.num_classes * p.splits);
-  hz::igemm_kernel<BLOCK_N, true><<<grid, 128, SM::kTotal, st>>>(am, bm, p);
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  return hz::launch(hz::igemm_kernel<BLOCK_N, true>, grid, dim3(128), SM::kTotal, st, am, bm, p) == cudaSuccess ? 0 : -1;
 }
 
 // dw[Cout, R*S*Cin (ld_out)] (+)= dy^T * x_taps.   ld_out / n_valid allow the padded stem (Cin=192 -> 147)
@@ -748,8 +750,7 @@ int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W,
   static bool attr = set_smem(hz::wgrad_kernel<BLOCK_N>, SM::kTotal);
   (void)attr;
   dim3 grid(m_tiles * p.n_tiles, p.taps.n, splits);
-  hz::wgrad_kernel<BLOCK_N><<<grid, 128, SM::kTotal, st>>>(dym, xm, p);
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  return hz::launch(hz::wgrad_kernel<BLOCK_N>, grid, dim3(128), SM::kTotal, st, dym, xm, p) == cudaSuccess ? 0 : -1;
 }
 
 }  // extern "C"

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
     const float* __restrict__ mean, const float* __restrict__ invstd,
     float* __restrict__ sums,                 // [2C], pre-zeroed: fwd (Σy, Σy²)  bwd (Σg, Σg·x̂)
     int M, int C, int relu) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float red[];              // [rlanes][nvec][16]
   const int nvec = C >> 3;
   const int rlanes = 256 / nvec;
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(
     float* __restrict__ mean_out, float* __restrict__ invstd_out,
     float* __restrict__ rmean, float* __restrict__ rvar,
     int M, int C, float eps, float momentum, int relu, int training) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sm[];   // scale[C], shift[C]
   float* scale = sm;
   float* shift = sm + C;
@@ -137,6 +141,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const float* __restrict__ sums, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres,
     float* __restrict__ dgamma, float* __restrict__ dbeta, int acc_gamma, int acc_beta,
     int M, int C, int relu) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sm[];   // k[C], a[C], b[C], mu[C], is[C]
   float *k = sm, *a = sm + C, *b = sm + 2 * C, *mu = sm + 3 * C, *is = sm + 4 * C;
   const float inv_cnt = 1.f / (float)M;
@@ -195,6 +201,8 @@ __global__ void __launch_bounds__(256) bn_act_bwd_fused_kernel(
     unsigned* __restrict__ counter, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres,
     float* __restrict__ dgamma, float* __restrict__ dbeta, int acc_gamma, int acc_beta, int M, int C,
     int relu) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sm[];      // phase 1: red[256*16]   phase 2: k,a,b,mu,is [5C]
   {
     float* red = sm;
@@ -291,6 +299,8 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* _
                                                           __nv_bfloat16* __restrict__ y,
                                                           uint8_t* __restrict__ idx, int N, int H, int W, int C,
                                                           int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();
   const int nvec = C >> 3;
   const size_t total = (size_t)N * Ho * Wo * nvec;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
@@ -333,6 +343,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
                                                           const uint8_t* __restrict__ idx,
                                                           __nv_bfloat16* __restrict__ dx, int N, int H, int W,
                                                           int C, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();
   const int nvec = C >> 3;
   const size_t total = (size_t)N * H * W * nvec;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < total;
@@ -371,6 +383,8 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
 // ------------------------------------------------------------------------------------------------
 __global__ void u8_normalize_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                     size_t n, float mean, float inv_std) {
+  pdl_launch();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(((float)in[i] * (1.f / 255.f) - mean) * inv_std);
@@ -380,6 +394,8 @@ template <int CIN, int RR, int SS>
 __global__ void __launch_bounds__(256) im2col_small_cin_kernel(
     const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A, int N, int H, int W, int Cin_,
     int R_, int S_, int stride, int pad, int Ho, int Wo, int K, int Kp) {
+  pdl_launch();
+  pdl_wait();
   const int Cin = CIN > 0 ? CIN : Cin_;
   const int S = SS > 0 ? SS : S_;
   (void)R_;
@@ -415,6 +431,8 @@ __global__ void __launch_bounds__(256) im2col_small_cin_kernel(
 // rows of length K (bf16) -> rows of length Kp (zero padded): packs conv1's [64,147] weights for TMA
 __global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                 int rows, int K, int Kp) {
+  pdl_launch();
+  pdl_wait();
   const int total = rows * Kp;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / Kp, k = i % Kp;
@@ -435,6 +453,8 @@ __global__ void __launch_bounds__(128) head_sample_kernel(
     float* __restrict__ logits_out, __nv_bfloat16* __restrict__ dfeat,
     float* __restrict__ loss_out, float* __restrict__ correct_out, int N, int C, int HW, int K,
     int n_valid, float loss_scale) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sm[];            // pooled[C], logit[kHeadMaxK], dl[kHeadMaxK]
   float* pl = sm;
   float* lg = sm + C;
@@ -501,6 +521,8 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
                                                          const float* __restrict__ dlogits,
                                                          float* __restrict__ dW, float* __restrict__ db,
                                                          int N, int C, int K, int accumulate) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float hsm[];                // dl[N][16] | part[4][32][16]
   float* dl = hsm;
   float* part = hsm + N * 16;
@@ -548,6 +570,8 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float* __restrict
 // flat fused Adam (fp32 master + moments, bf16 shadow refresh)  — torch.optim.Adam semantics
 // ------------------------------------------------------------------------------------------------
 __global__ void bump_step_kernel(float* step, float* diff) {
+  pdl_launch();
+  pdl_wait();
   step[0] += 1.f;
   if (diff != nullptr) diff[0] = 0.f;
 }
@@ -562,6 +586,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
                                                    const float* __restrict__ step, float* __restrict__ prev,
                                                    float* __restrict__ diff_out, size_t n, float lr,
                                                    float b1, float b2, float eps, float gscale) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float wsum[8];
   const float t = step[0];
   const float bc1 = 1.f - __powf(b1, t), bc2 = 1.f - __powf(b2, t);
@@ -620,6 +646,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
 __global__ void __launch_bounds__(256) grad_diff_kernel(const float* __restrict__ g,
                                                         float* __restrict__ prev,
                                                         float* __restrict__ out, size_t n) {
+  pdl_launch();
+  pdl_wait();
   __shared__ float wsum[8];
   float acc = 0.f;
   const size_t nv = n >> 2;
@@ -646,6 +674,8 @@ __global__ void __launch_bounds__(256) grad_diff_kernel(const float* __restrict_
 // stats[0..5] += (loss, correct, batch, sqrt(diff)*has_prev, has_prev, 1); has_prev = 1
 __global__ void stats_update_kernel(float* stats, float* has_prev, const float* loss,
                                     const float* correct, float batch, const float* diff_sq) {
+  pdl_launch();
+  pdl_wait();
   stats[0] += loss[0];
   stats[1] += correct[0];
   stats[2] += batch;
@@ -691,7 +721,7 @@ int hz_channel_ok(int C) {
 void hz_channel_sums(const void* y, float* sums, int M, int C, cudaStream_t st) {
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
   const size_t smem = sizeof(float) * 256 * 16;
-  hz::channel_reduce_kernel<false><<<reduce_grid(M, C), 256, smem, st>>>(
+  hz::launch(hz::channel_reduce_kernel<false>, dim3(reduce_grid(M, C)), dim3(256), smem, st, 
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0);
 }
 
@@ -700,7 +730,7 @@ void hz_bn_act_fwd(const void* y, const float* sums, const float* gamma, const f
                    float* rvar, int M, int C, float eps, float momentum, int relu, int training,
                    cudaStream_t st) {
   const size_t smem = sizeof(float) * 2 * C;
-  hz::bn_act_fwd_kernel<<<grid_for((size_t)M * (C / 8), 256, 148 * 4), 256, smem, st>>>(
+  hz::launch(hz::bn_act_fwd_kernel, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st, 
       (const __nv_bfloat16*)y, sums, gamma, beta, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out,
       mean, invstd, rmean, rvar, M, C, eps, momentum, relu, training);
 }
@@ -714,7 +744,7 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
     int grid = grid_for((size_t)M * (C / 8), 256, 148);
     size_t smem = sizeof(float) * 256 * 16;
     if (smem < sizeof(float) * 5 * C) smem = sizeof(float) * 5 * C;
-    hz::bn_act_bwd_fused_kernel<<<grid, 256, smem, st>>>(
+    hz::launch(hz::bn_act_bwd_fused_kernel, dim3(grid), dim3(256), smem, st, 
         (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd, gamma,
         sums_scratch, (unsigned*)(sums_scratch + 2 * C), (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta,
         acc_gamma, acc_beta, M, C, relu);
@@ -722,11 +752,11 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
   }
   if (!scratch_is_zero) cudaMemsetAsync(sums_scratch, 0, sizeof(float) * 2 * C, st);
   const size_t smem_r = sizeof(float) * 256 * 16;
-  hz::channel_reduce_kernel<true><<<reduce_grid(M, C), 256, smem_r, st>>>(
+  hz::launch(hz::channel_reduce_kernel<true>, dim3(reduce_grid(M, C)), dim3(256), smem_r, st, 
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
       sums_scratch, M, C, relu);
   const size_t smem = sizeof(float) * 5 * C;
-  hz::bn_act_bwd_apply_kernel<<<grid_for((size_t)M * (C / 8), 256, 148 * 4), 256, smem, st>>>(
+  hz::launch(hz::bn_act_bwd_apply_kernel, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st, 
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
       gamma, sums_scratch, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta, acc_gamma, acc_beta,
       M, C, relu);
@@ -734,18 +764,18 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
 
 void hz_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, cudaStream_t st) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  hz::maxpool_fwd_kernel<<<grid_for((size_t)N * Ho * Wo * (C / 8), 256), 256, 0, st>>>(
+  hz::launch(hz::maxpool_fwd_kernel, dim3(grid_for((size_t)N * Ho * Wo * (C / 8), 256)), dim3(256), 0, st, 
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)idx, N, H, W, C, Ho, Wo);
 }
 
 void hz_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, cudaStream_t st) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  hz::maxpool_bwd_kernel<<<grid_for((size_t)N * H * W * (C / 8), 256), 256, 0, st>>>(
+  hz::launch(hz::maxpool_bwd_kernel, dim3(grid_for((size_t)N * H * W * (C / 8), 256)), dim3(256), 0, st, 
       (const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
 }
 
 void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std, cudaStream_t st) {
-  hz::u8_normalize_kernel<<<grid_for(n, 256), 256, 0, st>>>((const uint8_t*)in, (__nv_bfloat16*)out, n,
+  hz::launch(hz::u8_normalize_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const uint8_t*)in, (__nv_bfloat16*)out, n,
                                                              mean, 1.f / std);
 }
 
@@ -753,15 +783,15 @@ void hz_im2col_small(const void* x, void* A, int N, int H, int W, int Cin, int R
                      int pad, int Ho, int Wo, int Kp, cudaStream_t st) {
   const int grid = grid_for((size_t)N * Ho * Wo * (Kp / 8), 256, 148 * 16);
   if (Cin == 3 && R == 7 && S == 7)
-    hz::im2col_small_cin_kernel<3, 7, 7><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W,
+    hz::launch(hz::im2col_small_cin_kernel<3, 7, 7>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W,
                                                                 Cin, R, S, stride, pad, Ho, Wo, R * S * Cin, Kp);
   else
-    hz::im2col_small_cin_kernel<0, 0, 0><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W,
+    hz::launch(hz::im2col_small_cin_kernel<0, 0, 0>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W,
                                                                 Cin, R, S, stride, pad, Ho, Wo, R * S * Cin, Kp);
 }
 
 void hz_pad_rows(const void* in, void* out, int rows, int K, int Kp, cudaStream_t st) {
-  hz::pad_rows_kernel<<<grid_for((size_t)rows * Kp, 256), 256, 0, st>>>(
+  hz::launch(hz::pad_rows_kernel, dim3(grid_for((size_t)rows * Kp, 256)), dim3(256), 0, st, 
       (const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, K, Kp);
 }
 
@@ -774,21 +804,21 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
     cudaMemsetAsync(correct, 0, sizeof(float), st);
   }
   const size_t smem = sizeof(float) * (C + 2 * hz::kHeadMaxK);
-  hz::head_sample_kernel<<<N, 128, smem, st>>>((const __nv_bfloat16*)feat, W, bias, labels, pooled,
+  hz::launch(hz::head_sample_kernel, dim3(N), dim3(128), smem, st, (const __nv_bfloat16*)feat, W, bias, labels, pooled,
                                                dlogits, logits, (__nv_bfloat16*)dfeat, loss, correct, N,
                                                C, HW, K, n_valid, loss_scale);
   dim3 grid((C + 31) / 32, (K + 15) / 16);
-  hz::head_wgrad_kernel<<<grid, 128, sizeof(float) * (N * 16 + 4 * 32 * 16), st>>>(pooled, dlogits, dW, db, N, C, K,
+  hz::launch(hz::head_wgrad_kernel, dim3(grid), dim3(128), sizeof(float) * (N * 16 + 4 * 32 * 16), st, pooled, dlogits, dW, db, N, C, K,
                                                                                   accumulate);
 }
 
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
              int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, cudaStream_t st) {
   const bool diff = prev != nullptr && diff_out != nullptr;
-  hz::bump_step_kernel<<<1, 1, 0, st>>>(step, diff ? diff_out : nullptr);
+  hz::launch(hz::bump_step_kernel, dim3(1), dim3(1), 0, st, step, diff ? diff_out : nullptr);
   const int grid = grid_for(n / 4, 256, 148 * 8);
 #define HZ_ADAM(D, Z)                                                                                   \
-  hz::adam_kernel<D, Z><<<grid, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)shadow, step, prev, diff_out, n, lr, \
+  hz::launch(hz::adam_kernel<D, Z>, dim3(grid), dim3(256), 0, st, p, g, m, v, (__nv_bfloat16*)shadow, step, prev, diff_out, n, lr, \
                                               b1, b2, eps, gscale)
   if (diff && zero_grad) HZ_ADAM(true, true);
   else if (diff) HZ_ADAM(true, false);
@@ -799,12 +829,12 @@ void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, 
 
 void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st) {
   cudaMemsetAsync(out, 0, sizeof(float), st);
-  hz::grad_diff_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, st>>>(g, prev, out, n);
+  hz::launch(hz::grad_diff_kernel, dim3(grid_for(n / 4, 256, 148 * 4)), dim3(256), 0, st, g, prev, out, n);
 }
 
 void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct,
                      float batch, const float* diff_sq, cudaStream_t st) {
-  hz::stats_update_kernel<<<1, 1, 0, st>>>(stats, has_prev, loss, correct, batch, diff_sq);
+  hz::launch(hz::stats_update_kernel, dim3(1), dim3(1), 0, st, stats, has_prev, loss, correct, batch, diff_sq);
 }
 
 }  // extern "C"
