@@ -8,11 +8,10 @@ iterate the whole subset on every rank).  There is no network here, so the defau
 class-dependent signal so loss/accuracy curves are meaningful.  Real CIFAR-10 python batches are
 read from ``data_dir`` when ``synthetic=False``.
 
-Loader design (B200-first): the whole (sub)set is tiny (50 000×3 KiB = 150 MB), so it is staged
-once in *pinned* host memory as uint8 NHWC; each step's batch is one async H2D copy of 64×3 KiB
-on a copy stream, double-buffered, normalisation + bf16 cast fused into the stem's im2col kernel.
-A native C++ prefetch thread (csrc/loader.cpp) assembles shuffled batches into the pinned
-staging ring; the pure-Python path below is the fallback and the CPU path.
+Loader design (B200-first): the whole (sub)set is tiny (50 000×3 KiB = 150 MB) and stays in host
+memory as uint8 NHWC; each step's batch is gathered into a slot of a small *pinned* staging ring
+and sent with one async H2D copy of 64×3 KiB on a copy stream several batches ahead of compute;
+normalisation + the bf16 cast run on the device (stem input kernel), so the wire format is uint8.
 """
 from __future__ import annotations
 
@@ -113,12 +112,13 @@ class BatchLoader:
     """Iterates (images, labels) batches on ``device``.
 
     images are delivered as uint8 NHWC ``[B,32,32,3]`` on CUDA (normalisation is fused into the
-    stem kernel) or as normalised fp32 NCHW-channels_last on CPU.  H2D copies are issued from
-    pinned memory on a dedicated copy stream one batch ahead of compute."""
+    stem kernel) or as normalised fp32 NCHW-channels_last on CPU.  The dataset lives in pinned host
+    memory; every batch is gathered into one slot of a small pinned staging ring (no per-step
+    allocation) and copied H2D on a dedicated copy stream ``depth`` batches ahead of compute."""
 
     def __init__(self, images: np.ndarray, labels: np.ndarray, batch_size: int, device,
                  sampler: Optional[ShardedSampler] = None, drop_last: bool = False,
-                 prefetch: bool = True):
+                 prefetch: bool = True, depth: int = 3):
         self.device = torch.device(device)
         self.bs = batch_size
         self.sampler = sampler
@@ -126,10 +126,17 @@ class BatchLoader:
         self.images = torch.from_numpy(images)
         self.labels = torch.from_numpy(labels)
         self.cuda = self.device.type == "cuda"
+        self.depth = max(depth, 1)
         if self.cuda:
-            self.images = self.images.pin_memory()
-            self.labels = self.labels.pin_memory()
             self.copy_stream = torch.cuda.Stream(device=self.device)
+            ring = self.depth + 1
+            self._hx = [torch.empty((batch_size,) + tuple(self.images.shape[1:]), dtype=torch.uint8).pin_memory()
+                        for _ in range(ring)]
+            self._hy = [torch.empty(batch_size, dtype=torch.int64).pin_memory() for _ in range(ring)]
+            self._dx = [torch.empty_like(t, device=self.device) for t in self._hx]
+            self._dy = [torch.empty_like(t, device=self.device) for t in self._hy]
+            self._copied = [None] * ring          # H2D done (slot's host buffer reusable, device valid)
+            self._consumed = [None] * ring        # compute finished reading the device buffers of the slot
         self.prefetch = prefetch and self.cuda
         self.h2d_bytes_per_batch = batch_size * (images[0].nbytes + 8)
 
@@ -147,39 +154,64 @@ class BatchLoader:
         for b in range(nb):
             yield idx[b * self.bs:(b + 1) * self.bs]
 
-    def _stage(self, bidx):
+    def _stage_cpu(self, bidx):
         t = torch.from_numpy(np.ascontiguousarray(bidx))
         x = self.images.index_select(0, t)
         y = self.labels.index_select(0, t)
-        if not self.cuda:
-            xf = x.permute(0, 3, 1, 2).float().div_(255.0).sub_(CIFAR_MEAN).div_(CIFAR_STD)
-            return xf.contiguous(memory_format=torch.channels_last), y
-        x, y = x.pin_memory(), y.pin_memory()
+        xf = x.permute(0, 3, 1, 2).float().div_(255.0).sub_(CIFAR_MEAN).div_(CIFAR_STD)
+        return xf.contiguous(memory_format=torch.channels_last), y
+
+    def _stage(self, bidx, slot: int):
+        n = len(bidx)
+        if self._copied[slot] is not None:
+            self._copied[slot].synchronize()                  # host buffer free again
+        t = torch.from_numpy(np.ascontiguousarray(bidx))
+        torch.index_select(self.images, 0, t, out=self._hx[slot][:n])
+        torch.index_select(self.labels, 0, t, out=self._hy[slot][:n])
         with torch.cuda.stream(self.copy_stream):
-            xd = x.to(self.device, non_blocking=True)
-            yd = y.to(self.device, non_blocking=True)
+            if self._consumed[slot] is not None:
+                self.copy_stream.wait_event(self._consumed[slot])   # device buffer no longer read
+            self._dx[slot][:n].copy_(self._hx[slot][:n], non_blocking=True)
+            self._dy[slot][:n].copy_(self._hy[slot][:n], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        return xd, yd, ev, (x, y)
+        self._copied[slot] = ev
+        return slot, n
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
         it = self._index_batches()
         if not self.cuda:
             for bidx in it:
-                yield self._stage(bidx)
+                yield self._stage_cpu(bidx)
             return
-        nxt = None
+        ring = len(self._hx)
+        pending = []
+        k = 0
+        prev_slot = None
         for bidx in it:
-            cur = nxt
-            nxt = self._stage(bidx)
-            if cur is not None:
-                yield self._deliver(cur)
-        if nxt is not None:
-            yield self._deliver(nxt)
+            pending.append(self._stage(bidx, k % ring))
+            k += 1
+            if len(pending) > self.depth:
+                prev_slot = self._release(prev_slot)
+                slot, n = pending.pop(0)
+                yield self._deliver(slot, n)
+                prev_slot = slot
+        while pending:
+            prev_slot = self._release(prev_slot)
+            slot, n = pending.pop(0)
+            yield self._deliver(slot, n)
+            prev_slot = slot
+        self._release(prev_slot)
 
-    def _deliver(self, staged):
-        xd, yd, ev, _keep = staged
-        torch.cuda.current_stream(self.device).wait_event(ev)
-        xd.record_stream(torch.cuda.current_stream(self.device))
-        yd.record_stream(torch.cuda.current_stream(self.device))
-        return xd, yd
+    def _release(self, slot):
+        """The consumer has moved past ``slot``: mark its device buffers reusable once the work
+        enqueued so far on the compute stream is done."""
+        if slot is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._consumed[slot] = ev
+        return None
+
+    def _deliver(self, slot, n):
+        torch.cuda.current_stream(self.device).wait_event(self._copied[slot])
+        return self._dx[slot][:n], self._dy[slot][:n]

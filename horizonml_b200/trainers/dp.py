@@ -189,6 +189,9 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
             "comm": rt.comm_backend, "allreduce": getattr(eng.ar, "name", None),
             "graph": eng._graphed.graph is not None, "graph_error": eng._graphed.capture_error,
             "final": rec.rows[-1] if rec.rows else None})
+    eng._graphed.graph = None
+    if cuda:
+        torch.cuda.synchronize()
     from ..launch import shutdown_distributed
     shutdown_distributed()
     return df

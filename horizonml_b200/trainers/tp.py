@@ -164,6 +164,10 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         write_summary(logs_dir, f"summary_{cfg.sample_size}.json", {
             "strategy": "tensor", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
             "conv_split": eng.model.conv_split, "final": rec.rows[-1] if rec.rows else None})
+    # a captured graph that contains NCCL kernels must be gone before the communicator is torn down
+    eng._graphed.graph = None
+    if cuda:
+        torch.cuda.synchronize()
     from ..launch import shutdown_distributed
     shutdown_distributed()
     return rec.frame()
