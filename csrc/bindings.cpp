@@ -242,10 +242,45 @@ void conv_wgrad(const Tensor& dy, const Tensor& x, Tensor dw_out, int64_t R, int
 // ------------------------------------------------------------------ peer all-reduce
 class PeerComm {
  public:
-  PeerComm(int rank, int world, int device, int64_t max_wire_bytes, int max_blocks)
-      : rank_(rank), world_(world) {
-    c_ = hz_comm_create(rank, world, device, (size_t)max_wire_bytes, max_blocks);
+  PeerComm(int rank, int world, int device, int64_t max_wire_bytes, int max_blocks, int64_t heap_bytes)
+      : rank_(rank), world_(world), device_(device) {
+    c_ = hz_comm_create2(rank, world, device, (size_t)max_wire_bytes, max_blocks, (size_t)heap_bytes);
     TORCH_CHECK(c_ != nullptr, "hz_comm_create failed");
+  }
+  int64_t heap_bytes() { return (int64_t)hz_comm_heap_bytes(c_); }
+  // torch view of [offset, offset+numel*itemsize) of the LOCAL symmetric heap (storage owned by the comm)
+  Tensor heap_tensor(int64_t offset, std::vector<int64_t> sizes, std::vector<int64_t> strides, const std::string& dtype) {
+    auto dt = dtype == "bf16" ? at::kBFloat16 : dtype == "f32" ? at::kFloat : dtype == "i32" ? at::kInt : at::kByte;
+    char* base = hz_comm_heap_base(c_, rank_);
+    TORCH_CHECK(base != nullptr && offset >= 0, "no symmetric heap");
+    auto opts = at::TensorOptions().dtype(dt).device(at::kCUDA, device_);
+    return at::from_blob(base + offset, sizes, strides, opts);
+  }
+  // fused tcgen05 GEMM + collective (csrc/tp_fused.cu).  All offsets are byte offsets into the symmetric heap.
+  void tp_conv(int64_t kind, int64_t x_off, c10::optional<Tensor> x_local, const Tensor& w, int64_t out_off,
+               int64_t ws_off, int64_t flags_off, int64_t tiles, std::vector<int64_t> x_shape, int64_t Cout,
+               int64_t R, int64_t pad, bool reduce, bool bcast, bool ag) {
+    c10::cuda::CUDAGuard g(w.device());
+    const int N = (int)x_shape[0], Ca = (int)x_shape[1], H = (int)x_shape[2], Wd = (int)x_shape[3];
+    const void* xp[8];
+    char* heaps[8];
+    for (int r = 0; r < world_; ++r) {
+      heaps[r] = hz_comm_heap_base(c_, r);
+      TORCH_CHECK(heaps[r] != nullptr, "peer heap not mapped");
+      xp[r] = ag ? (const void*)(heaps[r] + x_off) : nullptr;
+    }
+    if (!ag) { TORCH_CHECK(x_local.has_value()); xp[rank_] = x_local->data_ptr(); }
+    // flags block: [arrive tiles*W][result tiles][ready W][epoch][done]
+    const long long arrive_off = flags_off;
+    const long long result_off = arrive_off + 4LL * tiles * world_;
+    const long long ready_off = result_off + 4LL * tiles;
+    const long long epoch_off = ready_off + 4LL * world_;
+    unsigned* epoch = reinterpret_cast<unsigned*>(heaps[rank_] + epoch_off);
+    const int Cin = kind == 0 ? Ca : (int)Cout, Co = kind == 0 ? (int)Cout : Ca;
+    int rc = hz_tp_conv((int)kind, xp, w.data_ptr(), heaps, out_off, ws_off, arrive_off, result_off, ready_off, epoch,
+                        epoch + 1, world_, rank_, reduce ? 1 : 0, bcast ? 1 : 0, ag ? 1 : 0, N, H, Wd, Cin, Co, (int)R,
+                        (int)pad, cur_stream());
+    TORCH_CHECK(rc == 0, "hz_tp_conv failed rc=", rc);
   }
   ~PeerComm() { hz_comm_destroy(c_); }
   py::bytes export_handles() {
@@ -289,7 +324,7 @@ class PeerComm {
 
  private:
   HzComm* c_;
-  int rank_, world_;
+  int rank_, world_, device_;
 };
 
 }  // namespace
@@ -314,7 +349,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_wgrad", &conv_wgrad);
   py::class_<PeerComm>(m, "PeerComm")
-      .def(py::init<int, int, int, int64_t, int>())
+      .def(py::init<int, int, int, int64_t, int, int64_t>(), py::arg("rank"), py::arg("world"), py::arg("device"),
+           py::arg("max_wire_bytes"), py::arg("max_blocks"), py::arg("heap_bytes") = 0)
+      .def("heap_bytes", &PeerComm::heap_bytes)
+      .def("heap_tensor", &PeerComm::heap_tensor)
+      .def("tp_conv", &PeerComm::tp_conv)
       .def("export_handles", &PeerComm::export_handles)
       .def("import_handles", &PeerComm::import_handles)
       .def_static("link_local", &PeerComm::link_local)

@@ -334,6 +334,7 @@ struct HzComm {
   int max_blocks;
   size_t region_bytes;
   char* local;                 // cudaMalloc'd region
+  size_t heap_off, heap_bytes; // symmetric heap (optional)
   bool imported[hz::kMaxRanks];
   bool local_group;
 };
@@ -350,7 +351,14 @@ struct HzComm {
 
 extern "C" {
 
+HzComm* hz_comm_create2(int rank, int world, int device, size_t max_wire_bytes, int max_blocks, size_t heap_bytes);
 HzComm* hz_comm_create(int rank, int world, int device, size_t max_wire_bytes, int max_blocks) {
+  return hz_comm_create2(rank, world, device, max_wire_bytes, max_blocks, 0);
+}
+
+// heap_bytes > 0 appends a zero-initialised symmetric heap (same offsets on every rank) used by the fused
+// tensor-parallel kernels for peer-writable activations, partial-tile slots and flags.
+HzComm* hz_comm_create2(int rank, int world, int device, size_t max_wire_bytes, int max_blocks, size_t heap_bytes) {
   if (world > hz::kMaxRanks || max_blocks * world * 4 > 32768 || max_blocks * 4 > 12288) return nullptr;
   HzComm* c = new HzComm();
   memset(c, 0, sizeof(*c));
@@ -361,9 +369,12 @@ HzComm* hz_comm_create(int rank, int world, int device, size_t max_wire_bytes, i
   c->dev.buf_bytes = buf;
   c->dev.rank = rank;
   c->dev.world = world;
-  c->region_bytes = hz::kFlagBytes + 4 * buf;
+  c->heap_off = hz::kFlagBytes + 4 * buf;
+  c->heap_bytes = (heap_bytes + 1023) / 1024 * 1024;
+  c->region_bytes = c->heap_off + c->heap_bytes;
   if (cudaMalloc(&c->local, c->region_bytes) != cudaSuccess) { delete c; return nullptr; }
   cudaMemset(c->local, 0, hz::kFlagBytes);
+  if (c->heap_bytes) cudaMemset(c->local + c->heap_off, 0, c->heap_bytes);
   c->dev.base[rank] = c->local;
   cudaDeviceSynchronize();
   return c;
@@ -443,6 +454,9 @@ int hz_comm_barrier(HzComm* c, long long* stamps, cudaStream_t st) {
   hz::barrier_kernel<<<1, 32, 0, st>>>(c->dev, stamps);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+
+char* hz_comm_heap_base(HzComm* c, int r) { return c->dev.base[r] ? c->dev.base[r] + c->heap_off : nullptr; }
+size_t hz_comm_heap_bytes(HzComm* c) { return c->heap_bytes; }
 
 int hz_comm_error(HzComm* c) {
   uint32_t e = 0;

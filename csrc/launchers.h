@@ -47,6 +47,10 @@ int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W,
 // ---- comm.cu (peer-memory all-reduce)
 struct HzComm;
 struct HzComm* hz_comm_create(int rank, int world, int device, size_t max_wire_bytes, int max_blocks);
+struct HzComm* hz_comm_create2(int rank, int world, int device, size_t max_wire_bytes, int max_blocks,
+                               size_t heap_bytes);
+char* hz_comm_heap_base(struct HzComm* c, int r);
+size_t hz_comm_heap_bytes(struct HzComm* c);
 int hz_comm_export(struct HzComm* c, void* handle64);
 int hz_comm_import(struct HzComm* c, const void* handles);
 int hz_comm_link_local(struct HzComm** comms, int world);
@@ -57,6 +61,13 @@ int hz_comm_allreduce(struct HzComm* c, float* grad, size_t n, int algo, int wir
 int hz_comm_barrier(struct HzComm* c, long long* stamps, cudaStream_t st);
 int hz_comm_error(struct HzComm* c);
 void hz_comm_destroy(struct HzComm* c);
+
+// ---- tp_fused.cu (GEMM fused with its collective over peer memory)
+size_t hz_tp_ws_bytes(int world, int tiles);
+int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, char* const* heaps, long long out_off,
+               long long ws_off, long long arrive_off, long long result_off, long long ready_off,
+               unsigned* epoch, unsigned* done, int world, int rank, int reduce, int bcast, int ag, int N, int H,
+               int W_, int Cin, int Cout, int R, int pad, cudaStream_t st);
 
 #ifdef __cplusplus
 }

@@ -120,13 +120,17 @@ def _write_vec_grad(p, g):
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
-                momentum, eps, training, post_conv, post_dgrad):
+                momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn):
         be = _be(x)
         w = compute_weight(weight, x.dtype)
-        y_raw, sums = be.conv_fwd(x, w, stride, pad, training and post_conv is None)
-        if post_conv is not None:      # row-parallel conv: partial sums → all-reduce before BN
-            y_raw, sums = post_conv(y_raw), None
+        if conv_fn is not None:        # fused GEMM + collective kernel (tensor parallel): already reduced
+            y_raw, sums = conv_fn(x, w), None
+        else:
+            y_raw, sums = be.conv_fwd(x, w, stride, pad, training and post_conv is None)
+            if post_conv is not None:  # row-parallel conv: partial sums → all-reduce before BN
+                y_raw, sums = post_conv(y_raw), None
         ctx.post_dgrad = post_dgrad
+        ctx.dgrad_fn = dgrad_fn
         out, mean, invstd = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar,
                                           momentum, eps, residual, relu, training)
         ctx.save_for_backward(x, y_raw, out, mean, invstd)
@@ -167,27 +171,37 @@ class _ConvBNAct(torch.autograd.Function):
         else:
             be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc, zeroed)
             grad_written(weight)
-        dx = be.conv_dgrad(dy, w, x.shape, stride, pad) if ctx.x_needs_grad else None
-        if dx is not None and ctx.post_dgrad is not None:   # column-parallel conv: Σ over shards
-            dx = ctx.post_dgrad(dx)
-        return (dx, None, None, None, dres) + (None,) * 10
+        dx = None
+        if ctx.x_needs_grad:
+            if ctx.dgrad_fn is not None:                      # fused dgrad GEMM + all-reduce
+                dx = ctx.dgrad_fn(dy, w)
+            else:
+                dx = be.conv_dgrad(dy, w, x.shape, stride, pad)
+                if ctx.post_dgrad is not None:                # column-parallel conv: Σ over shards
+                    dx = ctx.post_dgrad(dx)
+        return (dx, None, None, None, dres) + (None,) * 12
 
 
 def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True, residual=None,
-                momentum=0.1, eps=1e-5, training=True, post_conv=None, post_dgrad=None):
+                momentum=0.1, eps=1e-5, training=True, post_conv=None, post_dgrad=None,
+                conv_fn=None, dgrad_fn=None):
     """``post_conv`` / ``post_dgrad`` are the tensor-parallel reduction points (row-parallel conv
-    output, column-parallel conv input-gradient); they take and return a tensor."""
+    output, column-parallel conv input-gradient); they take and return a tensor.  ``conv_fn(x, w)`` /
+    ``dgrad_fn(dy, w)`` replace conv + reduction by ONE fused GEMM+collective kernel."""
     if not training or not torch.is_grad_enabled():
         be = _be(x)
-        y_raw, sums = be.conv_fwd(x, compute_weight(weight, x.dtype), stride, pad,
-                                  training and post_conv is None)
-        if post_conv is not None:
+        if conv_fn is not None:
+            y_raw, sums = conv_fn(x, compute_weight(weight, x.dtype)), None
+        else:
+            y_raw, sums = be.conv_fwd(x, compute_weight(weight, x.dtype), stride, pad,
+                                      training and post_conv is None)
+        if conv_fn is None and post_conv is not None:
             y_raw, sums = post_conv(y_raw), None
         out, _, _ = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar,
                                   momentum, eps, residual, relu, training)
         return out
     return _ConvBNAct.apply(x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
-                            momentum, eps, training, post_conv, post_dgrad)
+                            momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -36,11 +36,12 @@ from ..ops.functional import grad_target, grad_written
 class TPComm:
     """Reduction / gather points of the tensor-parallel group."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, fused: "Optional[FusedTP]" = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bytes = 0
+        self.fused = fused          # fused GEMM+collective kernels (CUDA, native backend) or None
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
@@ -65,7 +66,101 @@ class TPComm:
 
     def take_bytes(self) -> int:
         b, self.bytes = self.bytes, 0
+        if self.fused is not None:
+            b += self.fused.bytes_moved
+            self.fused.bytes_moved = 0
         return b
+
+
+class FusedTP:
+    """Fused tcgen05 GEMM + collective ops over a CUDA-IPC symmetric heap (csrc/tp_fused.cu).
+
+    ``allreduce_conv(kind, x_shape, n_out, R, pad)`` returns a callable ``op(a, w) -> y`` that runs ONE kernel:
+    implicit-GEMM conv of the local shard + push-reduce of the partial tiles to their owner rank +
+    broadcast of the finished tiles to every rank (kind 0 = forward of a row-parallel conv, 1 = dgrad
+    of a column-parallel conv).  ``ag_conv`` is the all-gather→GEMM variant (A pulled from the peers
+    by TMA).  Every rank must create the ops in the same order (symmetric offsets)."""
+
+    def __init__(self, device, group=None, heap_mb: int = 96):
+        from ..ops import _ext
+        self.C = _ext.load(required=True)
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.comm = self.C.PeerComm(self.rank, self.world, self.device.index or 0, 1024, 8, heap_mb << 20)
+        if self.world > 1:
+            objs = [None] * self.world
+            dist.all_gather_object(objs, bytes(self.comm.export_handles()), group=group)
+            self.comm.import_handles([bytes(o) for o in objs])
+            dist.barrier(group=group)
+        self.off = 0
+        self.ws_off = None
+        self.ws_bytes = 0
+        self.bytes_moved = 0
+
+    def alloc(self, nbytes: int, align: int = 1024) -> int:
+        off = (self.off + align - 1) // align * align
+        if off + nbytes > self.comm.heap_bytes():
+            raise MemoryError("symmetric heap exhausted")
+        self.off = off + nbytes
+        return off
+
+    @staticmethod
+    def tiles_for(n, h, w, n_out):
+        if h * w >= 128:
+            if 128 % w or h % (128 // w):
+                return None
+            tm = n * (h // (128 // w))
+        else:
+            if 128 % (h * w):
+                return None
+            tm = -(-n // (128 // (h * w)))
+        return tm * (n_out // 64)
+
+    def supported(self, a_shape, n_out) -> bool:
+        n, ca, h, w = a_shape
+        t = self.tiles_for(n, h, w, n_out) if (ca % 64 == 0 and n_out % 64 == 0) else None
+        return t is not None and t <= 148
+
+    def _ensure_ws(self, tiles):
+        need = self.world * tiles * 128 * 64 * 4
+        if self.ws_off is None or need > self.ws_bytes:
+            self.ws_off, self.ws_bytes = self.alloc(max(need, 4 << 20)), max(need, 4 << 20)
+
+    def _make(self, kind, a_shape, n_out, R, pad, reduce, bcast, ag, x_off=0):
+        n, ca, h, w = a_shape
+        tiles = self.tiles_for(n, h, w, n_out)
+        self._ensure_ws(tiles)
+        out_off = self.alloc(n * h * w * n_out * 2)
+        flags_off = self.alloc(4 * (tiles * self.world + tiles + self.world + 2))
+        out = self.comm.heap_tensor(out_off, [n, n_out, h, w], [h * w * n_out, 1, w * n_out, n_out], "bf16")
+        comm, ws_off = self.comm, self.ws_off
+        wire = (self.world - 1) * tiles * 128 * 64 * (4 + 2) // max(self.world, 1)
+
+        def op(a, wgt):
+            comm.tp_conv(kind, x_off, None if ag else a, wgt, out_off, ws_off, flags_off, tiles, list(a_shape),
+                         n_out, R, pad, reduce, bcast, ag)
+            self.bytes_moved += wire
+            return out
+        op.out = out
+        return op
+
+    def allreduce_conv(self, kind, a_shape, n_out, R=3, pad=1):
+        return self._make(kind, tuple(a_shape), n_out, R, pad, True, True, False)
+
+    def reduce_scatter_conv(self, kind, a_shape, n_out, R=3, pad=1):
+        return self._make(kind, tuple(a_shape), n_out, R, pad, True, False, False)
+
+    def ag_buffer(self, shard_shape):
+        """A peer-readable activation shard [n_local, C, H, W] (channels_last) in the symmetric heap."""
+        n, c, h, w = shard_shape
+        off = self.alloc(n * c * h * w * 2)
+        return off, self.comm.heap_tensor(off, [n, c, h, w], [h * w * c, 1, w * c, c], "bf16")
+
+    def ag_conv(self, x_off, full_shape, n_out, R=3, pad=1):
+        """conv(all_gather(x shards over the image axis), w_local): the gather is done by the kernel's TMA."""
+        return self._make(0, tuple(full_shape), n_out, R, pad, False, False, True, x_off=x_off)
 
 
 def padded_classes(num_classes: int, ws: int) -> int:
@@ -144,6 +239,26 @@ class TPBasicBlock(nn.Module):
         self.downsample = dense.downsample
         for p in (self.conv1.weight, self.bn1.weight, self.bn1.bias, self.conv2.weight):
             p.tp_sharded = True
+        self._fused = {}            # batch size -> (fwd op of conv2, dgrad op of conv1) or (None, None)
+
+    def _fused_ops(self, x):
+        """Fused GEMM+all-reduce kernels for this block at this batch size (built once, same order on
+        every rank), or (None, None) → separate conv + collective."""
+        key = tuple(x.shape)
+        if key not in self._fused:
+            f = self.comm.fused
+            fwd = dg = None
+            if f is not None and x.is_cuda and x.dtype == torch.bfloat16 and ops.get_backend() == "native":
+                n, cin, h, w = x.shape
+                s1 = self.conv1.stride
+                ho, wo = (h + 2 - 3) // s1 + 1, (w + 2 - 3) // s1 + 1
+                cs, cout = self.conv1.cout, self.conv2.cout
+                if f.supported((n, cs, ho, wo), cout):
+                    fwd = f.allreduce_conv(0, (n, cs, ho, wo), cout)            # conv2 forward (row-parallel)
+                if s1 == 1 and f.supported((n, cs, ho, wo), cin):
+                    dg = f.allreduce_conv(1, (n, cs, ho, wo), cin)              # conv1 dgrad (column-parallel)
+            self._fused[key] = (fwd, dg)
+        return self._fused[key]
 
     def forward(self, x):
         t = self.training
@@ -151,12 +266,13 @@ class TPBasicBlock(nn.Module):
         if self.downsample is not None:
             idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t)
         c1, b1, c2, b2 = self.conv1, self.bn1, self.conv2, self.bn2
+        fwd2, dg1 = self._fused_ops(x)
         y = ops.conv_bn_act(x, c1.weight, b1.weight, b1.bias, b1.running_mean, b1.running_var,
                             stride=c1.stride, pad=1, relu=True, training=t,
-                            post_dgrad=self.comm.all_reduce_sum)
+                            post_dgrad=self.comm.all_reduce_sum, dgrad_fn=dg1)
         return ops.conv_bn_act(y, c2.weight, b2.weight, b2.bias, b2.running_mean, b2.running_var,
                                stride=1, pad=1, relu=True, residual=idt, training=t,
-                               post_conv=self.comm.all_reduce_sum)
+                               post_conv=self.comm.all_reduce_sum, conv_fn=fwd2)
 
 
 class TensorParallelResNet(nn.Module):

@@ -30,7 +30,11 @@ from .common import (DeviceStats, FaultInjector, GraphedStep, Heartbeat, Runtime
 class TPEngine:
     def __init__(self, cfg: TrainConfig, rt: Runtime):
         self.cfg, self.rt = cfg, rt
-        self.comm = TPComm()
+        fused = None
+        if rt.device.type == "cuda" and rt.backend == "native" and rt.world > 1 and cfg.tp_conv_split:
+            from ..parallel.tp import FusedTP
+            fused = FusedTP(rt.device)
+        self.comm = TPComm(fused=fused)
         dense = resnet18(cfg.num_classes, seed=cfg.seed)
         self.model = TensorParallelResNet(dense, self.comm, cfg.tp_conv_split).to(rt.device)
         self.model.train()

@@ -1,0 +1,171 @@
+"""Fused tensor-parallel kernels vs (native conv + NCCL collective), run under torchrun:
+GEMM→all-reduce (row-parallel forward, column-parallel dgrad), all-gather→GEMM; correctness,
+re-launch / CUDA-graph replay, device-timed latency (max over ranks) and roofline fraction."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def main():
+    out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/tp_fused.json"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    dist.init_process_group("nccl", device_id=dev)
+    from horizonml_b200 import ops
+    from horizonml_b200.ops import native_backend as nb
+    from horizonml_b200.ops import torch_backend as tb
+    from horizonml_b200.parallel.tp import FusedTP
+    ops.set_backend("native")
+    f = FusedTP(dev, heap_mb=128)
+    res = {"world": world, "cases": [], "timing": []}
+
+    def rmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def time_fn(fn, iters=30):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return rmax(e0.elapsed_time(e1) / iters * 1e3)
+
+    def report(name, got, ref, extra=None):
+        err = ((got.float() - ref.float()).abs().max() / (ref.float().abs().max() + 1e-6)).item()
+        gathered = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(gathered, got.contiguous())
+        same = all(torch.equal(gathered[0], t) for t in gathered)
+        c = {"name": name, "rel_err": err, "identical_across_ranks": same, "ok": bool(err < 3e-2)}
+        c.update(extra or {})
+        res["cases"].append(c)
+        if rank == 0:
+            print(("PASS " if c["ok"] else "FAIL ") + json.dumps(c), flush=True)
+
+    # (N, C_shard, H, W, N_out): row-parallel conv2 forward and column-parallel conv1 dgrad shapes
+    shapes = [(64, 128, 2, 2, 256), (64, 256, 1, 1, 512), (64, 64, 8, 8, 128), (64, 64, 4, 4, 128)]
+    for (n, cs, h, w, nout) in shapes:
+        g = torch.Generator().manual_seed(10 + rank)
+        x = cl((torch.randn(n, cs, h, w, generator=g) * 0.5).to(dev).bfloat16())
+        # ---- forward, row-parallel: y = sum_r conv(x_r, w_r), w_r [nout, cs, 3, 3]
+        wf = cl((torch.randn(nout, cs, 3, 3, generator=g) / (cs * 9 * world) ** 0.5).to(dev).bfloat16())
+        op = f.allreduce_conv(0, (n, cs, h, w), nout)
+        ref, _ = tb.conv_fwd(x.float(), wf.float(), 1, 1, False)
+        dist.all_reduce(ref)
+        for _ in range(3):
+            y = op(x, wf)
+        torch.cuda.synchronize()
+        report(f"allreduce_conv_fwd_{(n, cs, h, w, nout)}", y, ref)
+        # ---- dgrad, column-parallel: dx = sum_r dgrad(dy_r, w_r), w_r [cs, nout, 3, 3] (its Cout shard)
+        wd = cl((torch.randn(cs, nout, 3, 3, generator=g) / (cs * 9 * world) ** 0.5).to(dev).bfloat16())
+        opd = f.allreduce_conv(1, (n, cs, h, w), nout)
+        refd = tb.conv_dgrad(x.float(), wd.float(), (n, nout, h, w), 1, 1)
+        dist.all_reduce(refd)
+        for _ in range(3):
+            dx = opd(x, wd)
+        torch.cuda.synchronize()
+        report(f"allreduce_conv_dgrad_{(n, cs, h, w, nout)}", dx, refd)
+
+        # ---- timing vs the unfused path (tcgen05 conv kernel, then NCCL all-reduce of the bf16 output)
+        def unfused():
+            yy, _ = nb.conv_fwd(x, wf, 1, 1, False)
+            phys = yy.permute(0, 2, 3, 1)
+            dist.all_reduce(phys)
+        t_f = time_fn(lambda: op(x, wf))
+        t_u = time_fn(unfused)
+        t_c = time_fn(lambda: nb.conv_fwd(x, wf, 1, 1, False))
+        flops = 2.0 * n * h * w * nout * cs * 9
+        out_bytes = n * h * w * nout
+        # bytes that must cross NVLink per rank: (W-1)/W of the tiles as fp32 partials out, bf16 results in
+        nv = (world - 1) / world * out_bytes * (4 + 2)
+        roof = max(flops / 1433.5e12, nv / 770e9) * 1e6
+        row = {"shape": [n, cs, h, w, nout], "fused_us": t_f, "unfused_conv_plus_nccl_us": t_u, "conv_only_us": t_c,
+               "roofline_us": roof, "frac_of_roofline": roof / t_f}
+        res["timing"].append(row)
+        if rank == 0:
+            print("TIME " + json.dumps(row), flush=True)
+
+    # ---- all-gather -> GEMM: x image-sharded across ranks (in the symmetric heap), w local
+    for (n, c, h, w, nout) in [(64, 64, 8, 8, 64), (64, 128, 4, 4, 128)]:
+        g = torch.Generator().manual_seed(77 + rank)
+        nl = n // world
+        x_off, xbuf = f.ag_buffer((nl, c, h, w))
+        xs = cl((torch.randn(nl, c, h, w, generator=g) * 0.5).to(dev).bfloat16())
+        xbuf.copy_(xs)
+        wl = cl((torch.randn(nout, c, 3, 3, generator=g) / (c * 9) ** 0.5).to(dev).bfloat16())
+        op = f.ag_conv(x_off, (n, c, h, w), nout)
+        parts = [torch.empty_like(xs) for _ in range(world)]
+        dist.all_gather(parts, xs)
+        xfull = cl(torch.cat(parts, dim=0))
+        ref, _ = tb.conv_fwd(xfull.float(), wl.float(), 1, 1, False)
+        torch.cuda.synchronize(); dist.barrier()
+        for _ in range(3):
+            y = op(None, wl)
+        torch.cuda.synchronize()
+        err = ((y.float() - ref).abs().max() / ref.abs().max()).item()
+        c_ = {"name": f"ag_conv_{(n, c, h, w, nout)}", "rel_err": err, "ok": bool(err < 3e-2)}
+        res["cases"].append(c_)
+        if rank == 0:
+            print(("PASS " if c_["ok"] else "FAIL ") + json.dumps(c_), flush=True)
+
+        def unfused_ag():
+            dist.all_gather(parts, xs)
+            nb.conv_fwd(cl(torch.cat(parts, dim=0)), wl, 1, 1, False)
+        t_f = time_fn(lambda: op(None, wl))
+        t_u = time_fn(unfused_ag)
+        nv = (world - 1) / world * n * h * w * c * 2
+        roof = max(2.0 * n * h * w * nout * c * 9 / 1433.5e12, nv / 770e9) * 1e6
+        row = {"ag_shape": [n, c, h, w, nout], "fused_us": t_f, "nccl_allgather_plus_conv_us": t_u,
+               "roofline_us": roof, "frac_of_roofline": roof / t_f}
+        res["timing"].append(row)
+        if rank == 0:
+            print("TIME " + json.dumps(row), flush=True)
+
+    # ---- CUDA-graph replay of a fused kernel
+    try:
+        n, cs, h, w, nout = 64, 128, 2, 2, 256
+        g = torch.Generator().manual_seed(5 + rank)
+        x = cl((torch.randn(n, cs, h, w, generator=g) * 0.5).to(dev).bfloat16())
+        wf = cl((torch.randn(nout, cs, 3, 3, generator=g) / (cs * 9 * world) ** 0.5).to(dev).bfloat16())
+        op = f.allreduce_conv(0, (n, cs, h, w), nout)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            op(x, wf)
+        torch.cuda.synchronize(); dist.barrier()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            yg = op(x, wf)
+        for _ in range(4):
+            gr.replay()
+        torch.cuda.synchronize()
+        ref, _ = tb.conv_fwd(x.float(), wf.float(), 1, 1, False)
+        dist.all_reduce(ref)
+        res["graph_replay_ok"] = bool(((yg.float() - ref).abs().max() / ref.abs().max()).item() < 3e-2)
+    except Exception as e:  # noqa: BLE001
+        res["graph_replay_ok"] = False
+        res["graph_exc"] = repr(e)
+    res["n_fail"] = sum(1 for c in res["cases"] if not c["ok"])
+    dist.barrier()
+    if rank == 0:
+        os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+        json.dump(res, open(out_path, "w"), indent=1)
+        print(f"tp_fused: {len(res['cases'])} cases, {res['n_fail']} failed, graph={res.get('graph_replay_ok')}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
