@@ -258,8 +258,9 @@ class PeerComm {
   }
   // fused tcgen05 GEMM + collective (csrc/tp_fused.cu).  All offsets are byte offsets into the symmetric heap.
   void tp_conv(int64_t kind, int64_t x_off, c10::optional<Tensor> x_local, const Tensor& w, int64_t out_off,
-               int64_t ws_off, int64_t flags_off, int64_t tiles, std::vector<int64_t> x_shape, int64_t Cout,
-               int64_t R, int64_t pad, bool reduce, bool bcast, bool ag) {
+               int64_t ws_off, int64_t ws_stride, int64_t flags_off, int64_t tiles, std::vector<int64_t> x_shape,
+               int64_t Cout,
+               int64_t R, int64_t pad, int64_t reduce, bool bcast, bool ag) {
     c10::cuda::CUDAGuard g(w.device());
     const int N = (int)x_shape[0], Ca = (int)x_shape[1], H = (int)x_shape[2], Wd = (int)x_shape[3];
     const void* xp[8];
@@ -277,8 +278,8 @@ class PeerComm {
     const long long epoch_off = ready_off + 4LL * world_;
     unsigned* epoch = reinterpret_cast<unsigned*>(heaps[rank_] + epoch_off);
     const int Cin = kind == 0 ? Ca : (int)Cout, Co = kind == 0 ? (int)Cout : Ca;
-    int rc = hz_tp_conv((int)kind, xp, w.data_ptr(), heaps, out_off, ws_off, arrive_off, result_off, ready_off, epoch,
-                        epoch + 1, world_, rank_, reduce ? 1 : 0, bcast ? 1 : 0, ag ? 1 : 0, N, H, Wd, Cin, Co, (int)R,
+    int rc = hz_tp_conv((int)kind, xp, w.data_ptr(), heaps, out_off, ws_off, ws_stride, arrive_off, result_off, ready_off, epoch,
+                        epoch + 1, world_, rank_, (int)reduce, bcast ? 1 : 0, ag ? 1 : 0, N, H, Wd, Cin, Co, (int)R,
                         (int)pad, cur_stream());
     TORCH_CHECK(rc == 0, "hz_tp_conv failed rc=", rc);
   }

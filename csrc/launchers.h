@@ -65,9 +65,9 @@ void hz_comm_destroy(struct HzComm* c);
 // ---- tp_fused.cu (GEMM fused with its collective over peer memory)
 size_t hz_tp_ws_bytes(int world, int tiles);
 int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, char* const* heaps, long long out_off,
-               long long ws_off, long long arrive_off, long long result_off, long long ready_off,
-               unsigned* epoch, unsigned* done, int world, int rank, int reduce, int bcast, int ag, int N, int H,
-               int W_, int Cin, int Cout, int R, int pad, cudaStream_t st);
+               long long ws_off, long long ws_stride, long long arrive_off, long long result_off,
+               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int reduce, int bcast,
+               int ag, int N, int H, int W_, int Cin, int Cout, int R, int pad, cudaStream_t st);
 
 #ifdef __cplusplus
 }

@@ -41,13 +41,14 @@ struct TpParams {
   int ncols;
   // ---- peer part
   int world, rank;
-  int reduce;                    // 1: partial tiles are reduced over ranks (owner = tile % world)
+  int reduce;                    // 1: push-to-owner reduce (owner = tile % world); 2: one-shot (push to all, reduce everywhere)
   int bcast;                     // 1: all-reduce (owner broadcasts), 0: reduce-scatter (owner keeps)
   int ag;                        // 1: A is image-sharded, ag_imgs images per rank
   int ag_imgs;
   char* heap[kTpMaxRanks];       // symmetric heap base of every rank
   long long out_off;             // bf16 output [n_images, ...] (bytes from heap base)
   long long ws_off;              // fp32 partial slots [world][tiles][128][BLOCK_N]
+  long long ws_stride;           // one-shot: second copy of the slots, selected by call parity (no back-pressure needed)
   long long arrive_off;          // u32 [tiles][world]
   long long result_off;          // u32 [tiles]
   long long ready_off;           // u32 [world]      (AG: "my A shard is ready")
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   const int W = p.world, me = p.rank;
   const unsigned e = *p.epoch + 1u;             // epoch of this call (same on every rank)
   char* my_heap = p.heap[me];
+  const long long ws_off = p.ws_off + (long long)(e & 1u) * p.ws_stride;
 
   // which rank holds this tile's A rows (all-gather mode) and the image index inside that shard
   const int src = p.ag ? min(n0 / p.ag_imgs, W - 1) : me;
@@ -168,11 +170,33 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   tc::mbar_wait(tmem_full, 0);
   tc::fence_after_sync();
 
-  const int owner = p.reduce ? tile % W : me;
+  const int owner = p.reduce == 1 ? tile % W : me;
   bool have_result = true;            // staging holds the final bf16 tile
-  if (p.reduce && owner != me) {
+  if (p.reduce == 2 && W > 1) {
+    // ---- one-shot: push the fp32 partial into slot [me][tile] of EVERY peer (one NVLink hop), then each
+    //      rank reduces all W partials itself in rank order -> bit-identical results, no second hop
+#pragma unroll
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+      tc::tmem_ld_wait();
+      for (int d = 1; d < W; ++d) {
+        const int rr = (me + d) % W;
+        float* dst = reinterpret_cast<float*>(p.heap[rr] + ws_off) + ((size_t)(me * tiles + tile) * kTileM + row) * BLOCK_N + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < W && threadIdx.x != me)
+      st_release_sys_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.arrive_off) + tile * W + me, e);
+  }
+  if (p.reduce == 1 && owner != me) {
     // ---- push the fp32 partial into the owner's slot [me][tile] over NVLink
-    float* dst = reinterpret_cast<float*>(p.heap[owner] + p.ws_off) + ((size_t)(me * tiles + tile) * kTileM + row) * BLOCK_N;
+    float* dst = reinterpret_cast<float*>(p.heap[owner] + ws_off) + ((size_t)(me * tiles + tile) * kTileM + row) * BLOCK_N;
 #pragma unroll
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
@@ -194,7 +218,7 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
         spin_until_ge(reinterpret_cast<unsigned*>(my_heap + p.arrive_off) + tile * W + threadIdx.x, e);
       __syncthreads();
     }
-    const float* slots = reinterpret_cast<const float*>(my_heap + p.ws_off);
+    const float* slots = reinterpret_cast<const float*>(my_heap + ws_off);
 #pragma unroll
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
@@ -204,7 +228,7 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = 0.f;
       if (p.reduce) {
-        for (int rr = 0; rr < W; ++rr) {          // fixed rank order: deterministic sum
+        for (int rr = 0; rr < W; ++rr) {          // fixed rank order: deterministic (and rank-identical) sum
           if (rr == me) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
@@ -234,9 +258,9 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   const int vec = threadIdx.x % kVecPerRow;
   if (have_result) {
     // store the finished tile into the local output and (all-reduce) into every peer's output
-    const int n_dst = (p.reduce && p.bcast) ? W : 1;
+    const int n_dst = (p.reduce == 1 && p.bcast) ? W : 1;
     for (int d = 0; d < n_dst; ++d) {
-      const int rr = (p.reduce && p.bcast) ? (me + d) % W : me;   // start with self, stagger peers
+      const int rr = (p.reduce == 1 && p.bcast) ? (me + d) % W : me;   // start with self, stagger peers
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.heap[rr] + p.out_off);
       for (int r0 = threadIdx.x / kVecPerRow; r0 < kTileM; r0 += kRowsPerPass) {
         const int wi = r0 % p.BW;
@@ -249,7 +273,7 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
         st8(out + off, ld8(staging + r0 * S::kStagingLd + vec * 8));
       }
     }
-    if (p.reduce && p.bcast && W > 1) {
+    if (p.reduce == 1 && p.bcast && W > 1) {
       __threadfence_system();
       __syncthreads();
       if (threadIdx.x < W && threadIdx.x != me)
@@ -292,9 +316,9 @@ size_t hz_tp_ws_bytes(int world, int tiles) {
 // heaps[r]: heap base of rank r.  x_ptrs[r]: rank r's A buffer (only [rank] is used unless ag).
 // Stride-1 convs and dense GEMMs only (H=W=1, R=1).
 int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, char* const* heaps, long long out_off,
-               long long ws_off, long long arrive_off, long long result_off, long long ready_off,
-               unsigned* epoch, unsigned* done, int world, int rank, int reduce, int bcast, int ag, int N, int H,
-               int W_, int Cin, int Cout, int R, int pad, cudaStream_t st) {
+               long long ws_off, long long ws_stride, long long arrive_off, long long result_off,
+               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int reduce, int bcast,
+               int ag, int N, int H, int W_, int Cin, int Cout, int R, int pad, cudaStream_t st) {
   // logical conv: x [N,H,W,Cin] -> y [N,H,W,Cout] (fwd)   |   dy [N,H,W,Cout] -> dx [N,H,W,Cin] (dgrad)
   const int S_ = R;
   const int Ka = kind == 0 ? Cin : Cout;       // channels of the A operand
@@ -342,7 +366,7 @@ int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, char* const* 
   p.ncols = Nn;
   p.world = world; p.rank = rank; p.reduce = reduce; p.bcast = bcast; p.ag = ag; p.ag_imgs = imgs_per_rank;
   for (int r = 0; r < world; ++r) p.heap[r] = heaps[r];
-  p.out_off = out_off; p.ws_off = ws_off; p.arrive_off = arrive_off; p.result_off = result_off;
+  p.out_off = out_off; p.ws_off = ws_off; p.ws_stride = ws_stride; p.arrive_off = arrive_off; p.result_off = result_off;
   p.ready_off = ready_off;
   p.epoch = epoch; p.done = done;
   using SM = hz::IgemmSmem<BLOCK_N>;

@@ -189,10 +189,12 @@ class BatchLoader:
         k = 0
         prev_slot = None
         for bidx in it:
+            # we are resumed after the consumer enqueued its work on the previous delivery: only now may
+            # that slot's device buffers be handed to the copy stream again (ring = depth + 1 slots)
+            prev_slot = self._release(prev_slot)
             pending.append(self._stage(bidx, k % ring))
             k += 1
             if len(pending) > self.depth:
-                prev_slot = self._release(prev_slot)
                 slot, n = pending.pop(0)
                 yield self._deliver(slot, n)
                 prev_slot = slot

@@ -81,7 +81,7 @@ class FusedTP:
     of a column-parallel conv).  ``ag_conv`` is the all-gather→GEMM variant (A pulled from the peers
     by TMA).  Every rank must create the ops in the same order (symmetric offsets)."""
 
-    def __init__(self, device, group=None, heap_mb: int = 96):
+    def __init__(self, device, group=None, heap_mb: int = 256):
         from ..ops import _ext
         self.C = _ext.load(required=True)
         self.device = torch.device(device)
@@ -131,26 +131,35 @@ class FusedTP:
     def _make(self, kind, a_shape, n_out, R, pad, reduce, bcast, ag, x_off=0):
         n, ca, h, w = a_shape
         tiles = self.tiles_for(n, h, w, n_out)
-        self._ensure_ws(tiles)
+        if reduce == 2:
+            # one-shot has no result-flag back-pressure: private slots, double-buffered by call parity
+            ws_stride = self.world * tiles * 128 * 64 * 4
+            ws_off = self.alloc(2 * ws_stride)
+        else:
+            self._ensure_ws(tiles)
+            ws_off, ws_stride = self.ws_off, 0
         out_off = self.alloc(n * h * w * n_out * 2)
         flags_off = self.alloc(4 * (tiles * self.world + tiles + self.world + 2))
         out = self.comm.heap_tensor(out_off, [n, n_out, h, w], [h * w * n_out, 1, w * n_out, n_out], "bf16")
-        comm, ws_off = self.comm, self.ws_off
+        comm = self.comm
         wire = (self.world - 1) * tiles * 128 * 64 * (4 + 2) // max(self.world, 1)
 
         def op(a, wgt):
-            comm.tp_conv(kind, x_off, None if ag else a, wgt, out_off, ws_off, flags_off, tiles, list(a_shape),
+            comm.tp_conv(kind, x_off, None if ag else a, wgt, out_off, ws_off, ws_stride, flags_off, tiles, list(a_shape),
                          n_out, R, pad, reduce, bcast, ag)
             self.bytes_moved += wire
             return out
         op.out = out
         return op
 
-    def allreduce_conv(self, kind, a_shape, n_out, R=3, pad=1):
-        return self._make(kind, tuple(a_shape), n_out, R, pad, True, True, False)
+    def allreduce_conv(self, kind, a_shape, n_out, R=3, pad=1, algo="oneshot"):
+        """algo 'oneshot': every rank pushes its partial tile to all peers and reduces locally (one NVLink
+        hop, latency-optimal for ResNet-sized tiles); 'owner': push-to-owner reduce + broadcast (2 hops,
+        (W-1)/W of the traffic: bandwidth-optimal)."""
+        return self._make(kind, tuple(a_shape), n_out, R, pad, 2 if algo == "oneshot" else 1, True, False)
 
     def reduce_scatter_conv(self, kind, a_shape, n_out, R=3, pad=1):
-        return self._make(kind, tuple(a_shape), n_out, R, pad, True, False, False)
+        return self._make(kind, tuple(a_shape), n_out, R, pad, 1, False, False)
 
     def ag_buffer(self, shard_shape):
         """A peer-readable activation shard [n_local, C, H, W] (channels_last) in the symmetric heap."""
@@ -160,7 +169,7 @@ class FusedTP:
 
     def ag_conv(self, x_off, full_shape, n_out, R=3, pad=1):
         """conv(all_gather(x shards over the image axis), w_local): the gather is done by the kernel's TMA."""
-        return self._make(0, tuple(full_shape), n_out, R, pad, False, False, True, x_off=x_off)
+        return self._make(0, tuple(full_shape), n_out, R, pad, 0, False, True, x_off=x_off)
 
 
 def padded_classes(num_classes: int, ws: int) -> int:

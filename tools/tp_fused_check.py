@@ -86,6 +86,11 @@ def main():
             phys = yy.permute(0, 2, 3, 1)
             dist.all_reduce(phys)
         t_f = time_fn(lambda: op(x, wf))
+        op_owner = f.allreduce_conv(0, (n, cs, h, w), nout, algo="owner")
+        yo = op_owner(x, wf)
+        torch.cuda.synchronize()
+        report(f"allreduce_conv_fwd_owner_{(n, cs, h, w, nout)}", yo, ref)
+        t_o = time_fn(lambda: op_owner(x, wf))
         t_u = time_fn(unfused)
         t_c = time_fn(lambda: nb.conv_fwd(x, wf, 1, 1, False))
         flops = 2.0 * n * h * w * nout * cs * 9
@@ -93,7 +98,7 @@ def main():
         # bytes that must cross NVLink per rank: (W-1)/W of the tiles as fp32 partials out, bf16 results in
         nv = (world - 1) / world * out_bytes * (4 + 2)
         roof = max(flops / 1433.5e12, nv / 770e9) * 1e6
-        row = {"shape": [n, cs, h, w, nout], "fused_us": t_f, "unfused_conv_plus_nccl_us": t_u, "conv_only_us": t_c,
+        row = {"shape": [n, cs, h, w, nout], "fused_us": t_f, "fused_owner_algo_us": t_o, "unfused_conv_plus_nccl_us": t_u, "conv_only_us": t_c,
                "roofline_us": roof, "frac_of_roofline": roof / t_f}
         res["timing"].append(row)
         if rank == 0:
