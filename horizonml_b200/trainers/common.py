@@ -38,6 +38,8 @@ def setup_runtime(rank: int, world: int, cfg: TrainConfig, device: str) -> Runti
     ops.set_backend(backend)
     if dev.type == "cpu":
         torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
+    else:
+        torch.set_num_threads(1)     # the host only launches kernels: no spinning OpenMP teams next to it
     torch.manual_seed(cfg.seed)
     return Runtime(rank, world, dev, dtype, backend, comm_backend)
 
