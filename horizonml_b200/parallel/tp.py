@@ -152,10 +152,15 @@ class FusedTP:
         op.out = out
         return op
 
-    def allreduce_conv(self, kind, a_shape, n_out, R=3, pad=1, algo="oneshot"):
+    def allreduce_conv(self, kind, a_shape, n_out, R=3, pad=1, algo="auto"):
         """algo 'oneshot': every rank pushes its partial tile to all peers and reduces locally (one NVLink
         hop, latency-optimal for ResNet-sized tiles); 'owner': push-to-owner reduce + broadcast (2 hops,
         (W-1)/W of the traffic: bandwidth-optimal)."""
+        if algo == "auto":
+            # measured (profiles/tp_fused{2,8}_r1.json): one hop wins while the (W-1)x fp32 traffic stays small
+            n, _, h, w = a_shape
+            tiles = self.tiles_for(n, h, w, n_out) or 0
+            algo = "oneshot" if (self.world <= 2 or tiles * (self.world - 1) <= 64) else "owner"
         return self._make(kind, tuple(a_shape), n_out, R, pad, 2 if algo == "oneshot" else 1, True, False)
 
     def reduce_scatter_conv(self, kind, a_shape, n_out, R=3, pad=1):
