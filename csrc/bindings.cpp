@@ -165,14 +165,16 @@ std::vector<Tensor> head_fwd_bwd(const Tensor& feat, const Tensor& W, const c10:
 
 void adam_step(Tensor master, Tensor grad, Tensor m, Tensor v, c10::optional<Tensor> shadow, Tensor step,
                double lr, double b1, double b2, double eps, double gscale, c10::optional<Tensor> prev,
-               c10::optional<Tensor> diff_out, bool zero_grad) {
+               c10::optional<Tensor> diff_out, bool zero_grad, c10::optional<Tensor> live_blocks) {
   TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && master.numel() % 4 == 0);
   c10::cuda::CUDAGuard g(master.device());
   void* sh = nullptr;
   if (shadow.has_value() && shadow->defined()) { TORCH_CHECK(shadow->scalar_type() == at::kBFloat16); sh = shadow->data_ptr(); }
   hz_adam(master.data_ptr<float>(), grad.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), sh,
           step.data_ptr<float>(), fptr(prev), fptr(diff_out), zero_grad ? 1 : 0, (size_t)master.numel(), (float)lr,
-          (float)b1, (float)b2, (float)eps, (float)gscale, cur_stream());
+          (float)b1, (float)b2, (float)eps, (float)gscale,
+          live_blocks.has_value() && live_blocks->defined() ? live_blocks->data_ptr<int>() : nullptr,
+          live_blocks.has_value() && live_blocks->defined() ? (size_t)live_blocks->numel() : 0, cur_stream());
 }
 
 Tensor grad_diff_sq(const Tensor& grad, Tensor prev) {
@@ -303,13 +305,17 @@ class PeerComm {
   void set_multicast(int64_t mc_ptr, int64_t local_ptr, int64_t bytes) {
     hz_comm_set_multicast(c_, (void*)mc_ptr, (void*)local_ptr, (size_t)bytes);
   }
-  void allreduce(Tensor grad, const std::string& algo, bool wire_bf16, double scale) {
+  void allreduce(Tensor grad, const std::string& algo, bool wire_bf16, double scale,
+                 c10::optional<Tensor> live_blocks) {
     TORCH_CHECK(grad.is_cuda() && grad.scalar_type() == at::kFloat && grad.is_contiguous());
+    const bool has_live = live_blocks.has_value() && live_blocks->defined();
+    if (has_live) TORCH_CHECK(live_blocks->scalar_type() == at::kInt && live_blocks->is_cuda());
     int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : -1;
     TORCH_CHECK(a >= 0, "unknown all-reduce algorithm ", algo);
     c10::cuda::CUDAGuard g(grad.device());
-    int rc = hz_comm_allreduce(c_, grad.data_ptr<float>(), (size_t)grad.numel(), a, wire_bf16 ? 1 : 0,
-                               (float)scale, cur_stream());
+    const size_t n = has_live ? (size_t)live_blocks->numel() * 64 : (size_t)grad.numel();
+    int rc = hz_comm_allreduce(c_, grad.data_ptr<float>(), n, a, wire_bf16 ? 1 : 0, (float)scale,
+                               has_live ? live_blocks->data_ptr<int>() : nullptr, cur_stream());
     TORCH_CHECK(rc == 0, "hz_comm_allreduce failed rc=", rc);
   }
   int64_t blocks_for(int64_t n, const std::string& algo, bool wire_bf16) {
@@ -359,7 +365,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("import_handles", &PeerComm::import_handles)
       .def_static("link_local", &PeerComm::link_local)
       .def("set_multicast", &PeerComm::set_multicast)
-      .def("allreduce", &PeerComm::allreduce)
+      .def("allreduce", &PeerComm::allreduce, py::arg("grad"), py::arg("algo"), py::arg("wire_bf16"),
+           py::arg("scale"), py::arg("live_blocks") = py::none())
       .def("blocks_for", &PeerComm::blocks_for)
       .def("barrier", &PeerComm::barrier)
       .def("error", &PeerComm::error);

@@ -143,19 +143,27 @@ HZ_DEVINL void mc_st(void* p, const uint4& v) {
                "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// wire vector index -> element offset in the gradient buffer.  With `live` (indices of the 64-element blocks
+// that can ever be non-zero) the wire buffer is the *compacted* gradient: provably-dead parameters (conv taps
+// that only ever see padding) are neither packed, sent, reduced nor unpacked.
 template <int V>
-HZ_DEVINL void load_grad(const float* g, size_t vec, float* f) {
+HZ_DEVINL size_t goff(const int* __restrict__ live, size_t vec) {
+  constexpr int kPer = 64 / V;
+  return live ? (size_t)live[vec / kPer] * 64 + (vec % kPer) * V : vec * V;
+}
+template <int V>
+HZ_DEVINL void load_grad(const float* g, size_t off, float* f) {
 #pragma unroll
   for (int i = 0; i < V / 4; ++i) {
-    const float4 t = reinterpret_cast<const float4*>(g)[vec * (V / 4) + i];
+    const float4 t = reinterpret_cast<const float4*>(g + off)[i];
     f[4 * i] = t.x; f[4 * i + 1] = t.y; f[4 * i + 2] = t.z; f[4 * i + 3] = t.w;
   }
 }
 template <int V>
-HZ_DEVINL void store_grad(float* g, size_t vec, const float* f) {
+HZ_DEVINL void store_grad(float* g, size_t off, const float* f) {
 #pragma unroll
   for (int i = 0; i < V / 4; ++i)
-    reinterpret_cast<float4*>(g)[vec * (V / 4) + i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    reinterpret_cast<float4*>(g + off)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
 }
 
 enum Algo { kOneShot = 0, kTwoShot = 1, kNvls = 2 };
@@ -174,7 +182,7 @@ constexpr int kUnroll = 4;     // independent 16-byte requests in flight per thr
 // pack [lo,hi): grad(fp32)*scale -> wire vectors in the local staging buffer
 template <bool kBf16>
 HZ_DEVINL void pack_range(const float* __restrict__ grad, uint4* __restrict__ stage, size_t lo, size_t hi,
-                          float scale) {
+                          float scale, const int* __restrict__ live) {
   using Wt = Wire<kBf16>;
   constexpr int V = Wt::kVec;
   for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * kUnroll) {
@@ -182,7 +190,7 @@ HZ_DEVINL void pack_range(const float* __restrict__ grad, uint4* __restrict__ st
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const size_t v = v0 + (size_t)u * blockDim.x;
-      if (v < hi) load_grad<V>(grad, v, f[u]);
+      if (v < hi) load_grad<V>(grad, goff<V>(live, v), f[u]);
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -194,7 +202,8 @@ HZ_DEVINL void pack_range(const float* __restrict__ grad, uint4* __restrict__ st
 
 // unpack [lo,hi): wire vectors -> grad(fp32)
 template <bool kBf16>
-HZ_DEVINL void unpack_range(float* __restrict__ grad, const uint4* __restrict__ src, size_t lo, size_t hi) {
+HZ_DEVINL void unpack_range(float* __restrict__ grad, const uint4* __restrict__ src, size_t lo, size_t hi,
+                            const int* __restrict__ live) {
   using Wt = Wire<kBf16>;
   constexpr int V = Wt::kVec;
   for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * kUnroll) {
@@ -212,7 +221,7 @@ HZ_DEVINL void unpack_range(float* __restrict__ grad, const uint4* __restrict__ 
 #pragma unroll
         for (int i = 0; i < V; ++i) a[i] = 0.f;
         Wt::accum(a, w[u]);
-        store_grad<V>(grad, v, a);
+        store_grad<V>(grad, goff<V>(live, v), a);
       }
     }
   }
@@ -220,7 +229,8 @@ HZ_DEVINL void unpack_range(float* __restrict__ grad, const uint4* __restrict__ 
 
 template <bool kBf16, int kAlgo>
 __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, float* __restrict__ grad,
-                                                                 size_t n, float scale) {
+                                                                 size_t n, float scale,
+                                                                 const int* __restrict__ live) {
   using Wt = Wire<kBf16>;
   constexpr int V = Wt::kVec;
   __shared__ uint32_t s_epoch;
@@ -238,12 +248,12 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
   if (kAlgo == kOneShot) {
     const size_t per = (nv + B - 1) / B;
     const size_t lo = min((size_t)b * per, nv), hi = min(lo + per, nv);
-    pack_range<kBf16>(grad, my_stage, lo, hi, scale);
+    pack_range<kBf16>(grad, my_stage, lo, hi, scale, live);
   } else {
     for (int r = 0; r < W; ++r) {
       size_t lo, hi;
       sub_range(nv, W, B, r, b, lo, hi);
-      pack_range<kBf16>(grad, my_stage, lo, hi, scale);
+      pack_range<kBf16>(grad, my_stage, lo, hi, scale, live);
     }
   }
   peer_block_barrier(c, &s_epoch);
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
 #pragma unroll
       for (int r = 0; r < kMaxRanks; ++r)
         if (r < W) Wt::accum(a, w[r]);
-      store_grad<V>(grad, v, a);
+      store_grad<V>(grad, goff<V>(live, v), a);
     }
   } else {
     size_t lo, hi;
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
     for (int r = 0; r < W; ++r) {
       size_t l2, h2;
       sub_range(nv, W, B, r, b, l2, h2);
-      unpack_range<kBf16>(grad, my_out, l2, h2);
+      unpack_range<kBf16>(grad, my_out, l2, h2, live);
     }
   }
   __syncthreads();
@@ -428,7 +438,8 @@ int hz_comm_blocks_for(HzComm* c, size_t n, int algo, int wire_bf16) {
   return (int)want;
 }
 
-int hz_comm_allreduce(HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
+// n = number of gradient elements on the wire (= all of them, or 64 * #live blocks when `live` is given)
+int hz_comm_allreduce(HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale, const int* live,
                       cudaStream_t st) {
   const int V = wire_bf16 ? 8 : 4;
   if (n % V != 0) return -2;
@@ -436,7 +447,7 @@ int hz_comm_allreduce(HzComm* c, float* grad, size_t n, int algo, int wire_bf16,
   if (algo == hz::kNvls && c->dev.mc_base == nullptr) return -4;
   const int blocks = hz_comm_blocks_for(c, n, algo, wire_bf16);
 #define HZ_LAUNCH(BF, AL) \
-  hz::allreduce_kernel<BF, AL><<<blocks, hz::kCommThreads, 0, st>>>(c->dev, grad, n, scale)
+  hz::allreduce_kernel<BF, AL><<<blocks, hz::kCommThreads, 0, st>>>(c->dev, grad, n, scale, live)
   if (wire_bf16) {
     if (algo == hz::kOneShot) HZ_LAUNCH(true, hz::kOneShot);
     else if (algo == hz::kTwoShot) HZ_LAUNCH(true, hz::kTwoShot);

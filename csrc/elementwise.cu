@@ -585,7 +585,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
                                                    __nv_bfloat16* __restrict__ shadow,
                                                    const float* __restrict__ step, float* __restrict__ prev,
                                                    float* __restrict__ diff_out, size_t n, float lr,
-                                                   float b1, float b2, float eps, float gscale) {
+                                                   float b1, float b2, float eps, float gscale,
+                                                   const int* __restrict__ live) {
   pdl_launch();
   pdl_wait();
   __shared__ float wsum[8];
@@ -593,10 +594,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   const float bc1 = 1.f - __powf(b1, t), bc2 = 1.f - __powf(b2, t);
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
+  // n counts the elements actually visited: all of them, or 64 per live block (dead conv taps never get a
+  // gradient, so their m = v = 0 and their weights never move: skipping them is exact, not an approximation)
   const size_t nv = n >> 2;
   float dacc = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
-       i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t iv = (size_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nv;
+       iv += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = live ? (size_t)live[iv >> 4] * 16 + (iv & 15) : iv;
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 gg = reinterpret_cast<const float4*>(g)[i];
     float4 mm = reinterpret_cast<float4*>(m)[i];
@@ -813,13 +817,15 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
 }
 
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
-             int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, cudaStream_t st) {
+             int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, const int* live,
+             size_t n_live_blocks, cudaStream_t st) {
+  if (live != nullptr) n = n_live_blocks * 64;
   const bool diff = prev != nullptr && diff_out != nullptr;
   hz::launch(hz::bump_step_kernel, dim3(1), dim3(1), 0, st, step, diff ? diff_out : nullptr);
   const int grid = grid_for(n / 4, 256, 148 * 8);
 #define HZ_ADAM(D, Z)                                                                                   \
   hz::launch(hz::adam_kernel<D, Z>, dim3(grid), dim3(256), 0, st, p, g, m, v, (__nv_bfloat16*)shadow, step, prev, diff_out, n, lr, \
-                                              b1, b2, eps, gscale)
+                                              b1, b2, eps, gscale, live)
   if (diff && zero_grad) HZ_ADAM(true, true);
   else if (diff) HZ_ADAM(true, false);
   else if (zero_grad) HZ_ADAM(false, true);

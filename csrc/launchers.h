@@ -29,7 +29,8 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
                      float* db, int N, int C, int HW, int K, int n_valid, float loss_scale, int accumulate,
                      int out_is_zero, cudaStream_t st);
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
-             int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, cudaStream_t st);
+             int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, const int* live,
+             size_t n_live_blocks, cudaStream_t st);
 void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st);
 void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct, float batch,
                      const float* diff_sq, cudaStream_t st);
@@ -57,7 +58,7 @@ int hz_comm_link_local(struct HzComm** comms, int world);
 void hz_comm_set_multicast(struct HzComm* c, void* mc_ptr, void* local_ptr, size_t bytes);
 int hz_comm_blocks_for(struct HzComm* c, size_t n, int algo, int wire_bf16);
 int hz_comm_allreduce(struct HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
-                      cudaStream_t st);
+                      const int* live, cudaStream_t st);
 int hz_comm_barrier(struct HzComm* c, long long* stamps, cudaStream_t st);
 int hz_comm_error(struct HzComm* c);
 void hz_comm_destroy(struct HzComm* c);

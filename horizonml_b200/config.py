@@ -45,6 +45,7 @@ class TrainConfig:
     grad_divergence: bool = True      # reference metric (data_parallel_train.py:132-145)
     step_barrier: bool = False        # reference does a host barrier per step (:150-152)
     cuda_graph: bool = True
+    skip_dead_taps: bool = True       # optimizer / all-reduce skip conv taps that only ever see padding (exact)
     watchdog_s: float = 0.0           # 0 → reference rule max(120, 120*N/1000)
     save_dir: Optional[str] = None
     resume: Optional[str] = None
@@ -106,6 +107,7 @@ def add_train_flags(p: argparse.ArgumentParser, strategy: str) -> argparse.Argum
     g.add_argument('--no_grad_divergence', dest='grad_divergence', action='store_false')
     g.add_argument('--step_barrier', action='store_true')
     g.add_argument('--no_cuda_graph', dest='cuda_graph', action='store_false')
+    g.add_argument('--no_skip_dead_taps', dest='skip_dead_taps', action='store_false')
     g.add_argument('--watchdog_s', type=float, default=d.watchdog_s)
     g.add_argument('--save_dir', default=None)
     g.add_argument('--resume', default=None)

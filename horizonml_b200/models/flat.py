@@ -35,7 +35,8 @@ def _round_up(x: int, a: int) -> int:
 
 class FlatParams:
     def __init__(self, named_params: Sequence[Tuple[str, nn.Parameter]], device, compute_dtype,
-                 bucket_cap_mb: float = 25.0, reverse: bool = True, first_bucket_mb: float = 1.0):
+                 bucket_cap_mb: float = 25.0, reverse: bool = True, first_bucket_mb: float = 1.0,
+                 live_masks: Optional[Dict[str, torch.Tensor]] = None):
         named = list(named_params)
         order = list(reversed(named)) if reverse else named
         self.names = [n for n, _ in order]
@@ -76,6 +77,10 @@ class FlatParams:
         self.sync_shadow()
         self._attach_autograd_bridge()
         self.buckets = self._make_buckets(bucket_cap_mb, first_bucket_mb)
+        self.live_blocks = None               # int32 indices of the 64-element blocks that can be non-zero
+        self.bucket_live: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+        if live_masks:
+            self._build_live(live_masks)
         self._bucket_of: Dict[int, int] = {}
         for b in self.buckets:
             for nme in b.names:
@@ -96,6 +101,28 @@ class FlatParams:
                 start, names = end, []
                 cap = int(cap_mb * (1 << 20) / 4)
         return buckets
+
+    def _build_live(self, live_masks) -> None:
+        """Dead-parameter elision: block list for the optimizer (whole buffer) and per bucket (all-reduce)."""
+        nblk = self.total // ALIGN
+        live = torch.ones(self.total, dtype=torch.bool)
+        for nme, p, o in zip(self.names, self.params, self.offsets):
+            m = live_masks.get(nme)
+            if m is None:
+                continue
+            phys = m.permute(0, 2, 3, 1).reshape(-1) if m.dim() == 4 else m.reshape(-1)
+            live[o:o + p.numel()] = phys
+        blk = live.view(nblk, ALIGN).any(dim=1)
+        if bool(blk.all()):
+            return
+        idx = torch.nonzero(blk).flatten().to(torch.int32)
+        self.live_blocks = idx.to(self.device)
+        self.live_fraction = float(idx.numel()) / nblk
+        for b in self.buckets:
+            lo, hi = b.start // ALIGN, b.end // ALIGN
+            sel = idx[(idx >= lo) & (idx < hi)] - lo
+            if sel.numel() < hi - lo:
+                self.bucket_live[b.index] = sel.to(torch.int32).to(self.device)
 
     def _attach_autograd_bridge(self) -> None:
         """Parameters used by plain autograd ops (library models, e.g. MobileNetV2) receive ``.grad``;
@@ -167,7 +194,8 @@ class FlatAdam:
         from .. import ops
         f = self.flat
         return ops.adam_step(f.master, f.grad, self.m, self.v, f.shadow, self.step_t, self.lr,
-                             self.betas[0], self.betas[1], self.eps, grad_scale, prev_grad, True)
+                             self.betas[0], self.betas[1], self.eps, grad_scale, prev_grad, True,
+                             live_blocks=f.live_blocks)
 
     def state_dict(self) -> dict:
         return {"m": self.m.cpu(), "v": self.v.cpu(), "step": self.step_t.cpu(), "lr": self.lr,

@@ -115,6 +115,34 @@ class ResNet18(nn.Module):
         names = [n for n, _ in self.named_parameters()]
         return [[n for n in names if any(n.startswith(g) for g in gs)] for gs in groups]
 
+    def live_tap_masks(self, image_hw: int = 32) -> dict:
+        """{param name: bool mask (True = can ever receive a gradient)} for conv weights that have *dead taps*
+        at this input resolution: a 3×3 tap whose receptive field only ever covers zero padding (e.g. every
+        off-centre tap of layer4 on 1×1 maps) multiplies zeros in forward and gets an exactly-zero
+        gradient, so optimizer and all-reduce may skip it.  62 % of ResNet-18's parameters at 32×32."""
+        def live(r, k, stride, pad, h_in):
+            h_out = (h_in + 2 * pad - k) // stride + 1
+            return any(0 <= ho * stride + r - pad < h_in for ho in range(h_out))
+
+        masks = {}
+        hw = (image_hw + 2 * 3 - 7) // 2 + 1            # conv1
+        hw = (hw + 2 - 3) // 2 + 1                       # maxpool
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(self, f"layer{li}")):
+                for cname in ("conv1", "conv2"):
+                    conv = getattr(blk, cname)
+                    k, st, pd = conv.k, conv.stride, conv.pad
+                    lv = [live(r, k, st, pd, hw) for r in range(k)]
+                    if not all(lv):
+                        m = torch.zeros(conv.weight.shape, dtype=torch.bool)
+                        for r in range(k):
+                            for c in range(k):
+                                if lv[r] and lv[c]:
+                                    m[:, :, r, c] = True
+                        masks[f"layer{li}.{bi}.{cname}.weight"] = m
+                    hw = (hw + 2 * pd - k) // st + 1
+        return masks
+
     def features(self, x, first: int = 0, last: int = 4):
         blocks = self.atomic_blocks()
         for i in range(first, last + 1):

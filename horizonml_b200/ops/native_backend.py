@@ -210,14 +210,15 @@ def linear_fwd(x2d, w, b):
     return _tb.linear_fwd(x2d, w, b)
 
 
-def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.0, prev=None, zero_grad=False):
+def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.0, prev=None, zero_grad=False,
+              live_blocks=None):
     if master.is_cuda and master.numel() % 4 == 0 and (shadow is None or shadow.dtype == torch.bfloat16):
         LAUNCHES["adam"] += 2
         diff = torch.empty((), dtype=torch.float32, device=master.device) if prev is not None else None
-        C.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, diff, zero_grad)
+        C.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, diff, zero_grad, live_blocks)
         return diff
     _fallback("adam_step", "")
-    return _tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad)
+    return _tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad, live_blocks)
 
 
 def grad_diff_sq(grad, prev):

@@ -58,7 +58,7 @@ class TorchDistAllReduce(GradAllReduce):
 
     name = "nccl"
 
-    def allreduce_avg_(self, t: torch.Tensor) -> None:
+    def allreduce_avg_(self, t: torch.Tensor, algo=None, live=None) -> None:
         if self.world == 1:
             return
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -131,10 +131,13 @@ class PeerAllReduce(GradAllReduce):
     def wire_bytes(self, numel: int) -> int:
         return numel * (2 if self.wire == "bf16" else 4)
 
-    def allreduce_avg_(self, t: torch.Tensor, algo: Optional[str] = None) -> None:
+    def allreduce_avg_(self, t: torch.Tensor, algo: Optional[str] = None, live: Optional[torch.Tensor] = None) -> None:
+        """``live``: int32 indices (relative to ``t``) of the 64-element blocks to reduce — the rest of ``t`` is
+        known to be identically zero on every rank (dead conv taps) and never touches the wire."""
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_numel
-        a = algo or self.pick(t.numel())
-        self.handle.allreduce(t, a, self.wire == "bf16", 1.0 / self.world)
+        n_wire = t.numel() if live is None else live.numel() * 64
+        a = algo or self.pick(n_wire)
+        self.handle.allreduce(t, a, self.wire == "bf16", 1.0 / self.world, live)
 
     def barrier(self) -> None:
         self.handle.barrier(None)

@@ -24,7 +24,9 @@ class GradReducer:
     def __init__(self, flat: FlatParams, allreduce: GradAllReduce, overlap: bool = True):
         self.flat, self.ar = flat, allreduce
         self.cuda = flat.device.type == "cuda"
-        self.overlap = overlap and self.cuda and allreduce.world > 1
+        # NCCL collectives are captured on the main stream (the well-trodden CUDA-graph path); our peer kernels
+        # overlap with backward on a dedicated comm stream
+        self.overlap = overlap and self.cuda and allreduce.world > 1 and allreduce.name != "nccl"
         self.enabled = True
         self.comm_stream = torch.cuda.Stream(device=flat.device) if self.overlap else None
         self._pending: List[int] = []
@@ -58,7 +60,8 @@ class GradReducer:
         bk = self.flat.buckets[b]
         view = self.flat.grad[bk.start:bk.end]
         self._launched[b] = True
-        self.bytes_last_step += self.ar.wire_bytes(bk.end - bk.start)
+        live = self.flat.bucket_live[b] if hasattr(self.flat, "bucket_live") else None
+        self.bytes_last_step += self.ar.wire_bytes(bk.end - bk.start if live is None else live.numel() * 64)
         if self.overlap:
             # gradients of one bucket are produced on two streams: BN/dgrad chain (main) and the wgrad
             # side stream — the collective must wait for both
@@ -72,12 +75,12 @@ class GradReducer:
                 ready.record(st)
                 self.comm_stream.wait_event(ready)
             with torch.cuda.stream(self.comm_stream):
-                self.ar.allreduce_avg_(view)
+                self.ar.allreduce_avg_(view, live=live)
                 done = torch.cuda.Event()
                 done.record(self.comm_stream)
             self._events[b] = done
         else:
-            self.ar.allreduce_avg_(view)
+            self.ar.allreduce_avg_(view, live=live)
 
     def finish(self) -> None:
         """Flush buckets that never filled (e.g. unused params) and join the comm stream."""

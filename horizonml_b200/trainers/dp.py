@@ -48,7 +48,8 @@ class DPEngine:
         dev = rt.device
         self.model = build_model(cfg, dev)
         self.model.train()
-        self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype, cfg.bucket_mb)
+        live = self.model.live_tap_masks(32) if (cfg.skip_dead_taps and hasattr(self.model, "live_tap_masks")) else None
+        self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype, cfg.bucket_mb, live_masks=live)
         if rt.world > 1:   # K1: make replicas identical (same seed already does; belt and braces)
             dist.broadcast(self.flat.master, src=0)
             for b in self.model.buffers():
@@ -91,7 +92,8 @@ class DPEngine:
     def allreduce_bytes_per_step(self) -> int:
         if self.reducer is None:
             return 0
-        return sum(self.ar.wire_bytes(b.end - b.start) for b in self.flat.buckets)
+        return sum(self.ar.wire_bytes(b.end - b.start if self.flat.bucket_live[b.index] is None
+                                      else self.flat.bucket_live[b.index].numel() * 64) for b in self.flat.buckets)
 
 
 def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):

@@ -167,6 +167,42 @@ def test_adam_and_graddiff(nb):
     assert abs(d.item() - (gr * gr).sum().item()) < 1e-3 * (gr * gr).sum().item()
 
 
+def test_adam_and_allreduce_skip_dead_blocks(nb):
+    """Dead-parameter elision: only the listed 64-element blocks are visited / put on the wire."""
+    g = torch.Generator().manual_seed(8)
+    n = 64 * 1000
+    live = torch.arange(0, 1000, 3, dtype=torch.int32, device=DEV)          # every third block
+    mask = torch.zeros(1000, dtype=torch.bool, device=DEV); mask[live.long()] = True
+    emask = mask.repeat_interleave(64)
+    p = torch.randn(n, generator=g).to(DEV); p0 = p.clone()
+    gr = (torch.randn(n, generator=g) * 0.01).to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    sh = p.bfloat16(); sh0 = sh.clone()
+    st = torch.zeros(1, device=DEV)
+    prev = torch.zeros_like(p)
+    d = nb.adam_step(p, gr, m, v, sh, st, 1e-3, 0.9, 0.999, 1e-8, 1.0, prev, True, live)
+    assert torch.equal(p[~emask], p0[~emask]) and torch.equal(sh[~emask], sh0[~emask])     # untouched
+    assert (p[emask] != p0[emask]).all() and (gr[emask] == 0).all() and (gr[~emask] != 0).any()
+    assert abs(d.item() - (prev[emask] ** 2).sum().item()) < 1e-3 * d.item()
+    # all-reduce over the same live set with 2 virtual ranks
+    C = nb.C
+    comms = [C.PeerComm(r, 2, 0, n * 4, 16) for r in range(2)]
+    C.PeerComm.link_local(comms)
+    grads = [torch.randn(n, generator=g).to(DEV) for _ in range(2)]
+    for algo in ("oneshot", "twoshot"):
+        work = [x.clone() for x in grads]
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                comms[r].allreduce(work[r], algo, False, 0.5, live)
+        torch.cuda.synchronize()
+        ref = 0.5 * (grads[0] + grads[1])
+        for r in range(2):
+            assert torch.allclose(work[r][emask], ref[emask], atol=1e-6)
+            assert torch.equal(work[r][~emask], grads[r][~emask])             # dead blocks never touched
+
+
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
 @pytest.mark.parametrize("wire_bf16", [True, False])
