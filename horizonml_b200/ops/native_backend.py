@@ -33,8 +33,10 @@ class _Arena:
     def begin(self, device):
         if self.buf is None or self.buf.device != device:
             self.buf = torch.zeros(self.n, dtype=torch.float32, device=device)
-        elif max(self.off, self.used_prev) > 0:
-            self.buf[:max(self.off, self.used_prev)].zero_()
+            self.high = 0
+        self.high = max(getattr(self, "high", 0), self.off)
+        if self.high > 0:
+            self.buf[:self.high].zero_()          # everything ever handed out (slices baked into graphs too)
         self.used_prev, self.off, self.active = self.off, 0, True
 
     def take(self, rows, c, device):

@@ -97,7 +97,8 @@ class PipelineRunner:
     stage boundaries are tensors of ``in_shape(mb_size)`` / ``out_shape(mb_size)``."""
 
     def __init__(self, stage: int, num_stages: int, fwd_fn: Callable, in_shape: Callable,
-                 out_shape: Callable, dtype, device, group=None):
+                 out_shape: Callable, dtype, device, group=None, bwd_fn: Optional[Callable] = None):
+        self.bwd_fn = bwd_fn      # optional (i, dout) -> dx override (CUDA-graphed micro-batches)
         self.stage, self.S = stage, num_stages
         self.first, self.last = stage == 0, stage == num_stages - 1
         self.fwd_fn, self.in_shape, self.out_shape = fwd_fn, in_shape, out_shape
@@ -132,12 +133,18 @@ class PipelineRunner:
             self.trace.append(("F", i))
             if self.last:
                 loss, correct = out
-                loss_sum = loss.detach() if loss_sum is None else loss_sum + loss.detach()
-                correct_sum = correct if correct_sum is None else correct_sum + correct
+                # clone: with graphed micro-batches `loss` / `correct` are static buffers that the next replay overwrites
+                loss_sum = loss.detach().clone() if loss_sum is None else loss_sum + loss.detach()
+                correct_sum = correct.detach().clone() if correct_sum is None else correct_sum + correct.detach()
             return out
 
         def do_bwd(dout, i):
             x, out = inputs[i], outputs[i]
+            if self.bwd_fn is not None:
+                dx = self.bwd_fn(i, dout)
+                self.trace.append(("B", i))
+                inputs[i] = outputs[i] = None
+                return dx
             if self.last:
                 out[0].backward()
             else:
@@ -175,3 +182,55 @@ class PipelineRunner:
             self.p2p.exchange(send_bwd=dx)
             b_idx += 1
         return loss_sum, correct_sum
+
+
+class GraphedMicroBatch:
+    """One in-flight micro-batch slot of a pipeline stage captured as two CUDA graphs (forward, backward)
+    over static buffers — the 1F1B loop then replays graphs instead of launching ~130 kernels per
+    micro-batch from Python.  Stage ``s`` of ``S`` needs ``min(S - s, M)`` slots (1F1B in-flight bound)."""
+
+    def __init__(self, fwd, in_shape, in_dtype, device, first: bool, last: bool, label_shape=None,
+                 image_like=None, pool=None):
+        self.first, self.last = first, last
+        dev = device
+        if first:
+            self.x = torch.zeros_like(image_like)
+        else:
+            n, c, h, w = in_shape
+            self.x = torch.zeros((n, h, w, c), dtype=in_dtype, device=dev).permute(0, 3, 1, 2).requires_grad_(True)
+        self.labels = torch.zeros(label_shape, dtype=torch.long, device=dev) if last else None
+        self.fwd = fwd
+        self.gf, self.gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.pool = pool
+
+    def capture(self):
+        from .. import ops
+        with torch.cuda.graph(self.gf, pool=self.pool):
+            self.out = self.fwd(self.x, self.labels)
+        self.pool = self.gf.pool()
+        if self.last:
+            loss, correct = self.out
+            self.dy = None
+            with torch.cuda.graph(self.gb, pool=self.pool):
+                loss.backward()
+                ops.join_side()
+        else:
+            self.dy = torch.zeros_like(self.out)
+            with torch.cuda.graph(self.gb, pool=self.pool):
+                torch.autograd.backward(self.out, self.dy)
+                ops.join_side()
+        self.dx = None if self.first else self.x.grad
+        return self.pool
+
+    def run_fwd(self, x, labels=None):
+        self.x.detach().copy_(x, non_blocking=True)
+        if self.last:
+            self.labels.copy_(labels, non_blocking=True)
+        self.gf.replay()
+        return self.out
+
+    def run_bwd(self, dout):
+        if not self.last:
+            self.dy.copy_(dout, non_blocking=True)
+        self.gb.replay()
+        return self.dx

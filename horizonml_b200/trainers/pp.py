@@ -23,7 +23,7 @@ from ..metrics import EpochRecorder, write_summary
 from ..models.flat import FlatAdam, FlatParams
 from ..models.partition import boundary_shape, partition_blocks
 from ..models.resnet import resnet18
-from ..parallel.pp import PipelineRunner
+from ..parallel.pp import GraphedMicroBatch, PipelineRunner
 from .common import (DeviceStats, FaultInjector, Heartbeat, Runtime, allreduce_max_scalar, gpu_mem_mb,
                      setup_runtime)
 
@@ -60,6 +60,11 @@ class PPEngine:
             out_shape=lambda n: boundary_shape(self.last_blk, n, hw),
             dtype=rt.dtype, device=rt.device)
         self.global_step = 0
+        # CUDA-graphed micro-batches (GPU + native kernels): built lazily after one eager step
+        self.use_graphs = cfg.cuda_graph and rt.device.type == "cuda" and rt.backend == "native"
+        self.slots = None
+        self.slot_sizes = None
+        ops.enable_side_stream(rt.device.type == "cuda" and rt.backend == "native")
 
     def _fwd(self, x, i):
         if self.is_first and x.dtype == torch.uint8:
@@ -70,6 +75,44 @@ class PPEngine:
                                  loss_scale=self.mb_frac[i], n_valid=self.cfg.num_classes)
         return f
 
+    # ---- graphed micro-batches ------------------------------------------------------------------
+    def _stage_fwd_static(self, x, labels):
+        """Forward of this stage on static buffers (captured): returns y, or (loss, correct) on the last stage."""
+        if self.is_first and x.dtype == torch.uint8:
+            x = ops.stem_prepare(x.permute(0, 3, 1, 2), dtype=self.rt.dtype)
+        f = self.model.features(x, self.first_blk, self.last_blk)
+        if self.is_last:
+            return ops.head_loss(f, self.model.fc.weight, self.model.fc.bias, labels,
+                                 loss_scale=self._graph_frac, n_valid=self.cfg.num_classes)
+        return f
+
+    def _build_slots(self, sizes, images):
+        from ..ops import native_backend as nb
+        S, s = self.rt.world, self.rt.rank
+        n = sizes[0]
+        self._graph_frac = 1.0 / len(sizes)
+        nslots = max(1, min(S - s, len(sizes)))
+        nb.ARENA.active = False                      # captured micro-batches are replayed several times per step:
+        for p in self.flat.params:                   # they must not share pre-zeroed scratch, and every gradient
+            p._acc = True                            # write accumulates (the optimizer pass clears the buffer)
+        slots, pool = [], None
+        torch.cuda.synchronize()
+        for _ in range(nslots):
+            g = GraphedMicroBatch(self._stage_fwd_static, boundary_shape(self.first_blk - 1, n, 32) if not self.is_first else None,
+                                  self.rt.dtype, self.rt.device, self.is_first, self.is_last,
+                                  label_shape=(n,), image_like=images[0] if self.is_first else None, pool=pool)
+            pool = g.capture()
+            slots.append(g)
+        torch.cuda.synchronize()
+        self.slots, self.slot_sizes = slots, list(sizes)
+
+    def _fwd_graphed(self, x, i):
+        slot = self.slots[i % len(self.slots)]
+        return slot.run_fwd(x, self.labels_mb[i] if self.is_last else None)
+
+    def _bwd_graphed(self, i, dout):
+        return self.slots[i % len(self.slots)].run_bwd(dout)
+
     def step(self, images, labels):
         B = labels.shape[0]
         M = max(1, min(self.cfg.microbatches, B))
@@ -79,6 +122,21 @@ class PPEngine:
         imgs = list(torch.split(images, sizes)) if self.is_first else None
         ops.step_begin(self.rt.device)
         self.flat.begin_step()
+        uniform = len(set(sizes)) == 1
+        if self.use_graphs and uniform and self.global_step >= 2:
+            if self.slots is None or self.slot_sizes != list(sizes):
+                try:
+                    self._build_slots(sizes, imgs)
+                except Exception as e:  # noqa: BLE001
+                    print(f"[pp] graph capture failed on stage {self.rt.rank}, staying eager: {e!r}", flush=True)
+                    self.use_graphs, self.slots = False, None
+                    torch.cuda.synchronize()
+        if self.slots is not None and uniform and self.slot_sizes == list(sizes):
+            for p in self.flat.params:
+                p._acc = True
+            self.runner.fwd_fn, self.runner.bwd_fn = self._fwd_graphed, self._bwd_graphed
+        else:
+            self.runner.fwd_fn, self.runner.bwd_fn = self._fwd, None
         loss, correct = self.runner.run(sizes, imgs)
         ops.join_side()
         diff = self.opt.step(prev_grad=self.prev_grad)
