@@ -80,5 +80,19 @@ inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
+// Zero-fill as a *kernel* (not cudaMemsetAsync): a memset node sitting between two PDL-launched kernels is not
+// a grid, so `griddepcontrol.wait` in the consumer does not order against it (observed: BN sums cleared after
+// the conv epilogue had already accumulated into them inside captured graphs).
+static __global__ void zero_f32_kernel(float* __restrict__ p, size_t n) {
+  pdl_launch();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+inline void zero_f32(float* p, size_t n, cudaStream_t st) {
+  size_t g = (n + 255) / 256;
+  if (g > 592) g = 592;
+  if (g < 1) g = 1;
+  launch(zero_f32_kernel, dim3((unsigned)g), dim3(256), 0, st, p, n);
+}
 }  // namespace hz
 #endif

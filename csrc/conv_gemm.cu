@@ -486,7 +486,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   p.ncols = Cout;
   p.out = (__nv_bfloat16*)y;
   p.stats = stats;
-  if (stats && !stats_is_zero) cudaMemsetAsync(stats, 0, sizeof(float) * 2 * Cout, st);
+  if (stats && !stats_is_zero) hz::zero_f32(stats, (size_t)2 * Cout, st);
   {
     const SplitWs w = get_split_ws();
     const int tiles = t.tiles * (Cout / BLOCK_N);
@@ -602,7 +602,7 @@ int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W,
   if (splits > 1 && !accumulate && !prezeroed) {
     // split-K accumulates with atomics: clear exactly the region this conv owns (rows are ld_out apart)
     if (p.ld_out == (long long)R * S_ * Cin || R == 1)
-      cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * p.ld_out, st);
+      hz::zero_f32(dw, (size_t)Cout * p.ld_out, st);
     else
       return -14;
   }

@@ -723,7 +723,7 @@ int hz_channel_ok(int C) {
 }
 
 void hz_channel_sums(const void* y, float* sums, int M, int C, cudaStream_t st) {
-  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+  hz::zero_f32(sums, (size_t)2 * C, st);
   const size_t smem = sizeof(float) * 256 * 16;
   hz::launch(hz::channel_reduce_kernel<false>, dim3(reduce_grid(M, C)), dim3(256), smem, st, 
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0);
@@ -754,7 +754,7 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
         acc_gamma, acc_beta, M, C, relu);
     return;
   }
-  if (!scratch_is_zero) cudaMemsetAsync(sums_scratch, 0, sizeof(float) * 2 * C, st);
+  if (!scratch_is_zero) hz::zero_f32(sums_scratch, (size_t)2 * C, st);
   const size_t smem_r = sizeof(float) * 256 * 16;
   hz::launch(hz::channel_reduce_kernel<true>, dim3(reduce_grid(M, C)), dim3(256), smem_r, st, 
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
@@ -804,8 +804,8 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
                      float* correct, float* dW, float* db, int N, int C, int HW, int K, int n_valid,
                      float loss_scale, int accumulate, int out_is_zero, cudaStream_t st) {
   if (!out_is_zero) {
-    cudaMemsetAsync(loss, 0, sizeof(float), st);
-    cudaMemsetAsync(correct, 0, sizeof(float), st);
+    hz::zero_f32(loss, 1, st);
+    hz::zero_f32(correct, 1, st);
   }
   const size_t smem = sizeof(float) * (C + 2 * hz::kHeadMaxK);
   hz::launch(hz::head_sample_kernel, dim3(N), dim3(128), smem, st, (const __nv_bfloat16*)feat, W, bias, labels, pooled,
@@ -834,7 +834,7 @@ void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, 
 }
 
 void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st) {
-  cudaMemsetAsync(out, 0, sizeof(float), st);
+  hz::zero_f32(out, 1, st);
   hz::launch(hz::grad_diff_kernel, dim3(grid_for(n / 4, 256, 148 * 4)), dim3(256), 0, st, g, prev, out, n);
 }
 
