@@ -226,6 +226,9 @@ def run_ours(args):
         out["native_fallbacks"] = dict(nb.FALLBACKS)
     if rank == 0:
         print(json.dumps(out), flush=True)
+    # a captured graph holding NCCL kernels must be released before the communicator is destroyed
+    eng._graphed.graph = None
+    torch.cuda.synchronize()
     if dist.is_initialized():
         dist.destroy_process_group()
 

@@ -95,13 +95,15 @@ class PPEngine:
         nb.ARENA.active = False                      # captured micro-batches are replayed several times per step:
         for p in self.flat.params:                   # they must not share pre-zeroed scratch, and every gradient
             p._acc = True                            # write accumulates (the optimizer pass clears the buffer)
-        slots, pool = [], None
+        slots = []
         torch.cuda.synchronize()
         for _ in range(nslots):
+            # one private memory pool per slot: activations saved by slot A's forward graph are returned to the
+            # pool when its backward is captured, and must not be handed to slot B (both are in flight at once)
             g = GraphedMicroBatch(self._stage_fwd_static, boundary_shape(self.first_blk - 1, n, 32) if not self.is_first else None,
                                   self.rt.dtype, self.rt.device, self.is_first, self.is_last,
-                                  label_shape=(n,), image_like=images[0] if self.is_first else None, pool=pool)
-            pool = g.capture()
+                                  label_shape=(n,), image_like=images[0] if self.is_first else None, pool=None)
+            g.capture()
             slots.append(g)
         torch.cuda.synchronize()
         self.slots, self.slot_sizes = slots, list(sizes)
