@@ -44,6 +44,7 @@ struct IgemmParams {
   int n_images;
   int ncols;                 // valid output columns (Cout / Cin total)
   int splits;                // split-K factor (blockIdx.z = class * splits + split)
+  int cluster;               // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
   float* ws;                 // fp32 split-K workspace [tiles][128][BLOCK_N], all-zero between launches
   unsigned* sem;             // per-tile arrival counters, all-zero between launches
   __nv_bfloat16* out;
@@ -143,7 +144,52 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
   }
-  if (p.splits == 1) {
+  int row_lo = 0, row_hi = kTileM;          // rows of the tile this CTA writes out
+  if (p.splits > 1 && p.cluster) {
+    // ---- cluster split-K: every CTA of the cluster parks its fp32 partial tile in its own shared memory,
+    //      then CTA r reduces rows [r*128/S, (r+1)*128/S) of all S partials through distributed shared memory
+    constexpr int kRedLd = BLOCK_N + 4;                                  // fp32 words per row (conflict-free)
+    float* red = reinterpret_cast<float*>(smem);                          // [128][kRedLd]  (pipeline buffers are idle)
+    staging = reinterpret_cast<__nv_bfloat16*>(smem + 40960);            // keep the bf16 staging clear of `red`
+#pragma unroll
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t r[32];
+      if (k_iters > 0) {
+        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tc::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(red + row * kRedLd + c0 + j) =
+            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                        __uint_as_float(r[j + 3]));
+    }
+    cluster_sync();
+    const int Sx = p.splits;
+    const int rows_per = kTileM / Sx;
+    row_lo = split * rows_per;
+    row_hi = row_lo + rows_per;
+    constexpr int kChunks = BLOCK_N / 4;
+    const uint32_t red_base = smem_u32(red);
+    for (int idx = threadIdx.x; idx < rows_per * kChunks; idx += 128) {
+      const int rr = row_lo + idx / kChunks, ch = idx % kChunks;
+      const uint32_t off = (uint32_t)((rr * kRedLd + ch * 4) * 4);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s2 = 0; s2 < Sx; ++s2) {                                   // fixed order: deterministic
+        const float4 v = ld_dsmem_f4(map_to_cta(red_base + off, (uint32_t)s2));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      __nv_bfloat162 lo2 = __floats2bfloat162_rn(acc.x, acc.y), hi2 = __floats2bfloat162_rn(acc.z, acc.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+      *reinterpret_cast<uint2*>(staging + rr * S::kStagingLd + ch * 4) = pk;
+    }
+    cluster_sync();                                                       // peers are done reading my `red`
+  } else if (p.splits == 1) {
     if (k_iters > 0) {
 #pragma unroll
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -216,7 +262,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   constexpr int kVecPerRow = BLOCK_N / 8;
   constexpr int kRowsPerPass = 128 / kVecPerRow;
   const int vec = threadIdx.x % kVecPerRow;
-  for (int r0 = threadIdx.x / kVecPerRow; r0 < kTileM; r0 += kRowsPerPass) {
+  for (int r0 = row_lo + threadIdx.x / kVecPerRow; r0 < row_hi; r0 += kRowsPerPass) {
     const int wi = r0 % p.BW;
     const int hi = (r0 / p.BW) % p.BH;
     const int ni = r0 / (p.BW * p.BH);
@@ -227,14 +273,14 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     st8(p.out + off, ld8(staging + r0 * S::kStagingLd + vec * 8));
   }
   if (p.stats != nullptr) {
-    // per-channel sum / sum of squares over this tile's rows (zero-filled OOB rows contribute 0)
+    // per-channel sum / sum of squares over this CTA's rows (zero-filled OOB rows contribute 0)
     constexpr int kParts = 128 / BLOCK_N;          // 2 for BLOCK_N=64, 1 for 128
     const int col = threadIdx.x % BLOCK_N;
     const int part = threadIdx.x / BLOCK_N;
     if (part < kParts) {
       float s = 0.f, q = 0.f;
-      const int rows = kTileM / kParts;
-      for (int r0 = part * rows; r0 < (part + 1) * rows; ++r0) {
+      const int rows = (row_hi - row_lo) / kParts;
+      for (int r0 = row_lo + part * rows; r0 < row_lo + (part + 1) * rows; ++r0) {
         const float v = __bfloat162float(staging[r0 * S::kStagingLd + col]);
         s += v;
         q += v * v;
@@ -431,6 +477,16 @@ SplitWs get_split_ws() {
   }
   return w;
 }
+// cluster (DSMEM) split-K factor: power of two <= 8; only when the K loop is long enough to pay for the
+// two cluster barriers (~1.5 us) and the grid still fits in one wave
+int pick_cluster_splits(int tiles, int k_total) {
+  static const bool off = [] { const char* e = getenv("HZ_CLUSTER_SPLITK"); return e && e[0] == '0'; }();
+  if (off || tiles <= 0 || k_total < 16) return 1;
+  int s = 8;
+  while (s > 1 && (tiles * s > 148 || k_total / s < 2)) s >>= 1;
+  return s;
+}
+
 int pick_splits(int tiles, int k_total) {
   // Measured on B200: accumulating 32 KB fp32 tiles with red.global.add.v4.f32 costs more than the
   // K-loop time it saves (layer1 conv 7.7 -> 26 us), so workspace split-K stays opt-in (HZ_SPLITK=1).
@@ -492,12 +548,17 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
     const int tiles = t.tiles * (Cout / BLOCK_N);
     p.splits = w.ws ? pick_splits(tiles, p.cls[0].n * p.cblocks) : 1;
     p.ws = w.ws; p.sem = w.sem;
+    if (p.splits == 1) {
+      p.splits = pick_cluster_splits(tiles, p.cls[0].n * p.cblocks);
+      p.cluster = p.splits > 1;
+    }
   }
   using SM = hz::IgemmSmem<BLOCK_N>;
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, false>, SM::kTotal);
   (void)attr;
   dim3 grid(t.tiles, Cout / BLOCK_N, p.splits);
-  return hz::launch(hz::igemm_kernel<BLOCK_N, false>, grid, dim3(128), SM::kTotal, st, am, bm, p) == cudaSuccess ? 0 : -1;
+  return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, false>, grid, dim3(128), SM::kTotal, st,
+                            p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;
 }
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w)
@@ -556,12 +617,17 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, 
     for (int c = 0; c < p.num_classes; ++c) kmax = kmax > p.cls[c].n ? kmax : p.cls[c].n;
     p.splits = w.ws ? pick_splits(tiles, kmax * p.cblocks) : 1;
     p.ws = w.ws; p.sem = w.sem;
+    if (p.splits == 1) {
+      p.splits = pick_cluster_splits(tiles, kmax * p.cblocks);
+      p.cluster = p.splits > 1;
+    }
   }
   using SM = hz::IgemmSmem<BLOCK_N>;
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, true>, SM::kTotal);
   (void)attr;
   dim3 grid(t.tiles, Cin / BLOCK_N, p.num_classes * p.splits);
-  return hz::launch(hz::igemm_kernel<BLOCK_N, true>, grid, dim3(128), SM::kTotal, st, am, bm, p) == cudaSuccess ? 0 : -1;
+  return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, true>, grid, dim3(128), SM::kTotal, st,
+                            p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;
 }
 
 // dw[Cout, R*S*Cin (ld_out)] (+)= dy^T * x_taps.   ld_out / n_valid allow the padded stem (Cin=192 -> 147)
