@@ -448,19 +448,28 @@ __global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloa
 constexpr int kHeadMaxK = 64;
 
 __global__ void __launch_bounds__(128) head_sample_kernel(
-    const __nv_bfloat16* __restrict__ feat, const float* __restrict__ Wt, const float* __restrict__ bias,
+    const __nv_bfloat16* __restrict__ feat, const float* Wt, const float* __restrict__ bias,
     const int64_t* __restrict__ labels, float* __restrict__ pooled, float* __restrict__ dlogits,
     float* __restrict__ logits_out, __nv_bfloat16* __restrict__ dfeat,
     float* __restrict__ loss_out, float* __restrict__ correct_out, int N, int C, int HW, int K,
-    int n_valid, float loss_scale) {
+    int n_valid, float loss_scale, int w_in_smem) {
   pdl_launch();
   pdl_wait();
-  extern __shared__ float sm[];            // pooled[C], logit[kHeadMaxK], dl[kHeadMaxK]
+  extern __shared__ float sm[];            // pooled[C], logit[kHeadMaxK], dl[kHeadMaxK], (W[n_valid][C])
   float* pl = sm;
   float* lg = sm + C;
   float* dl = lg + kHeadMaxK;
   const int n = blockIdx.x;
   const float inv_hw = 1.f / (float)HW;
+  // stage the classifier weights once (coalesced float4): logits and dfeat then read shared memory only,
+  // so the kernel has one global-load latency instead of three dependent ones
+  if (w_in_smem) {
+    float* wsm = dl + kHeadMaxK;
+    const int nv4 = (n_valid * C) >> 2;
+    for (int i = threadIdx.x; i < nv4; i += blockDim.x)
+      reinterpret_cast<float4*>(wsm)[i] = reinterpret_cast<const float4*>(Wt)[i];
+    Wt = wsm;
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (int p = 0; p < HW; ++p) s += __bfloat162float(feat[((size_t)n * HW + p) * C + c]);
@@ -807,10 +816,12 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
     hz::zero_f32(loss, 1, st);
     hz::zero_f32(correct, 1, st);
   }
-  const size_t smem = sizeof(float) * (C + 2 * hz::kHeadMaxK);
+  size_t smem = sizeof(float) * (C + 2 * hz::kHeadMaxK);
+  const int w_in_smem = ((size_t)n_valid * C * sizeof(float) <= 40 * 1024 && (C & 3) == 0) ? 1 : 0;
+  if (w_in_smem) smem += sizeof(float) * (size_t)n_valid * C;
   hz::launch(hz::head_sample_kernel, dim3(N), dim3(128), smem, st, (const __nv_bfloat16*)feat, W, bias, labels, pooled,
                                                dlogits, logits, (__nv_bfloat16*)dfeat, loss, correct, N,
-                                               C, HW, K, n_valid, loss_scale);
+                                               C, HW, K, n_valid, loss_scale, w_in_smem);
   dim3 grid((C + 31) / 32, (K + 15) / 16);
   hz::launch(hz::head_wgrad_kernel, dim3(grid), dim3(128), sizeof(float) * (N * 16 + 4 * 32 * 16), st, pooled, dlogits, dW, db, N, C, K,
                                                                                   accumulate);

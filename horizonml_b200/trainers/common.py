@@ -159,3 +159,25 @@ def allreduce_max_scalar(x: float, device) -> float:
     t = torch.tensor([x], dtype=torch.float64, device=device if torch.device(device).type == "cuda" else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def profile_steps(step_fn, x, y, path: str, steps: int = 5) -> None:
+    """``--profile``: CUPTI kernel timeline of a few steps (chrome trace + per-kernel summary JSON)."""
+    import json
+    from torch.profiler import ProfilerActivity, profile
+    acts = [ProfilerActivity.CPU] + ([ProfilerActivity.CUDA] if torch.cuda.is_available() else [])
+    with profile(activities=acts) as prof:
+        for _ in range(steps):
+            step_fn(x, y)
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    prof.export_chrome_trace(path)
+    rows = {}
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            r = rows.setdefault(e.name[:80], [0, 0.0])
+            r[0] += 1
+            r[1] += e.time_range.end - e.time_range.start
+    with open(path.replace(".json", "_kernels.json"), "w") as fh:
+        json.dump({k: {"launches": v[0], "us": v[1]} for k, v in sorted(rows.items(), key=lambda kv: -kv[1][1])}, fh, indent=1)

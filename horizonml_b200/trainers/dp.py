@@ -28,7 +28,7 @@ from ..models.resnet import resnet18
 from ..parallel.comm import make_grad_allreduce
 from ..parallel.dp import GradReducer
 from .common import (DeviceStats, FaultInjector, GraphedStep, Heartbeat, Runtime, allreduce_max_scalar,
-                     gpu_mem_mb, setup_runtime)
+                     gpu_mem_mb, profile_steps, setup_runtime)
 
 
 def build_model(cfg: TrainConfig, device, class_pad_to: int = 1):
@@ -179,6 +179,8 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         if rank == 0 and not cfg.quiet:
             print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "
                   f"Time: {epoch_time:.2f}s", flush=True)
+        if cfg.profile and epoch == start_epoch and nsteps > 0:
+            profile_steps(eng.step, x, y, f"{logs_dir}/profile_rank{rank}.json")
         if cfg.save_dir and rank == 0 and (
                 (cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
             checkpoint.save(cfg.save_dir, "dp", eng.model, eng.opt, epoch + 1, eng.global_step)

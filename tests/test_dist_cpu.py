@@ -57,3 +57,47 @@ def test_fault_injection_tears_job_down(tmp_path):
     assert time.time() - t0 < 120, "a dead rank must not leave the job hanging"
     assert os.path.exists(tmp_path / "error_rank1.txt")
     assert "injected fault" in open(tmp_path / "error_rank1.txt").read()
+
+
+def test_checkpoint_resume_through_trainer(tmp_path):
+    """--save_dir / --resume: epoch counter, weights and Adam state survive (absent in the reference)."""
+    import torch
+    cfg = FAST.replace(save_dir=str(tmp_path / "ck"))
+    df1 = run_data_parallel(1, 1, 64, logs_dir=str(tmp_path / "a"), cfg=cfg)
+    assert df1 is not None and os.path.exists(tmp_path / "ck" / "ckpt_dp.pt")
+    ck = torch.load(tmp_path / "ck" / "ckpt_dp.pt", map_location="cpu", weights_only=False)
+    assert ck["epoch"] == 1 and ck["global_step"] == 4 and float(ck["optim"]["step"][0]) == 4
+    df2 = run_data_parallel(1, 2, 64, logs_dir=str(tmp_path / "b"), cfg=cfg.replace(resume=str(tmp_path / "ck")))
+    assert df2 is not None and df2["epoch"].tolist() == [2]          # resumed: only epoch 2 is run
+    assert df2["loss"].iloc[0] < df1["loss"].iloc[0]
+
+
+def test_legacy_train_entrypoint(tmp_path):
+    """train.py: env-var rendezvous, MODEL_TYPE, legacy CSV columns (reference train.py:15-126)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(find_free_port()),
+               MODEL_TYPE="resnet", EPOCHS="1", SAMPLE_SIZE="64", BATCH_SIZE="16", DEVICE="cpu", LOGS_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(root, "train.py")], cwd=tmp_path, env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    df = pd.read_csv(tmp_path / "training_logs_worker_0.csv")
+    assert list(df.columns) == ["Worker", "Epoch", "Loss", "Accuracy", "Time"] and len(df) == 1
+
+
+def test_main_benchmark_sweep_cpu(tmp_path):
+    """main.py programme: the three strategies in turn + the eight comparison artefacts (reference main.py:17-61,64-390)."""
+    from horizonml_b200.bench_suite import generate_comparison_graphs, run_benchmarks
+    cfg = FAST.replace(logs_dir=None)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        res = run_benchmarks([64], 2, 1, cfg)
+        written = generate_comparison_graphs(res, str(tmp_path / "out"))
+    finally:
+        os.chdir(cwd)
+    assert all(res[s][64] is not None for s in ("data_parallel", "model_parallel", "tensor_parallel"))
+    summ = __import__("json").load(open(tmp_path / "out" / "benchmark_summary.json"))
+    assert {b["strategy"] for b in summ["bars"]} == {"data_parallel", "model_parallel", "tensor_parallel"}
+    assert os.path.exists(tmp_path / "out" / "overall_performance_comparison.csv")
