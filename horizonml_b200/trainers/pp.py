@@ -42,12 +42,13 @@ class PPEngine:
         for b in range(self.first_blk, self.last_blk + 1):
             names.update(groups[b])
         mine = [(n, p) for n, p in self.model.named_parameters() if n in names]
+        live = self.model.live_tap_masks(32) if cfg.skip_dead_taps else None
         # parameters of other stages are dropped (freed) — this stage never touches them
         for n, p in self.model.named_parameters():
             if n not in names:
                 p.requires_grad_(False)
                 p.data = torch.empty(0, device=rt.device)
-        self.flat = FlatParams(mine, rt.device, rt.dtype, cfg.bucket_mb)
+        self.flat = FlatParams(mine, rt.device, rt.dtype, cfg.bucket_mb, live_masks=live)
         self.opt = FlatAdam(self.flat, lr=cfg.lr)
         self.stats = DeviceStats(rt.device)
         self.prev_grad = torch.zeros_like(self.flat.grad) if (cfg.grad_divergence and self.is_last) else None
