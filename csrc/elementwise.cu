@@ -481,8 +481,10 @@ __global__ void __launch_bounds__(128) head_sample_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int k = warp; k < K; k += nwarp) {
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += pl[c] * Wt[(size_t)k * C + c];
-    s = warp_sum(s);
+    if (k < n_valid) {                       // padded classes are masked: never touch their (unstaged) rows
+      for (int c = lane; c < C; c += 32) s += pl[c] * Wt[(size_t)k * C + c];
+      s = warp_sum(s);
+    }
     if (lane == 0) lg[k] = (k < n_valid) ? s + (bias ? bias[k] : 0.f) : -INFINITY;
   }
   __syncthreads();
