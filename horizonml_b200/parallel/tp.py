@@ -326,3 +326,125 @@ class TensorParallelResNet(nn.Module):
         for n, p in self.named_parameters():
             (shd if getattr(p, "tp_sharded", False) else rep).append((n, p))
         return rep, shd
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Stand-alone tensor-parallel Linear layers (the reference's ``TensorParallelLinear``, tensor_parallel_train.py:27-64,
+# done right — plus the row-split counterpart BASELINE.json asks for).
+# ----------------------------------------------------------------------------------------------------------
+class _ColumnLinearFn(torch.autograd.Function):
+    """y = all_gather_cols(x · W_rᵀ + b_r);  dX = Σ_r dY_r · W_r (all-reduce);  dW_r = dY_rᵀ · x."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, comm: TPComm, gather: bool):
+        ctx.comm, ctx.gather = comm, gather
+        ctx.save_for_backward(x, w)
+        ctx.has_b = b is not None
+        y = x.float() @ w.float().t()
+        if b is not None:
+            y = y + b.float()
+        y = y.to(x.dtype)
+        return comm.all_gather_cols(y) if gather else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        comm = ctx.comm
+        k = w.shape[0]
+        dl = dy[:, comm.rank * k:(comm.rank + 1) * k] if ctx.gather else dy
+        dl = dl.float()
+        dx = comm.all_reduce_sum((dl @ w.float()).contiguous()).to(x.dtype)
+        dw = (dl.t() @ x.float()).to(w.dtype)
+        db = dl.sum(0).to(w.dtype) if ctx.has_b else None
+        return dx, dw, db, None, None
+
+
+class _RowLinearFn(torch.autograd.Function):
+    """y = all_reduce(x_r · W_rᵀ) + b;  dX_r = dY · W_r;  dW_r = dYᵀ · x_r   (x is split along features)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, comm: TPComm, fused_op):
+        ctx.save_for_backward(x, w)
+        ctx.has_b = b is not None
+        if fused_op is not None:
+            # ONE kernel: tcgen05 GEMM of the local shard + peer-memory all-reduce of the output tiles
+            y = fused_op(x.view(x.shape[0], x.shape[1], 1, 1), w.view(w.shape[0], w.shape[1], 1, 1))
+            y = y.view(x.shape[0], -1).clone()
+        else:
+            y = comm.all_reduce_sum((x.float() @ w.float().t()).contiguous()).to(x.dtype)
+        if b is not None:
+            y = (y.float() + b.float()).to(x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dyf = dy.float()
+        dx = (dyf @ w.float()).to(x.dtype)
+        dw = (dyf.t() @ x.float()).to(w.dtype)
+        db = dyf.sum(0).to(w.dtype) if ctx.has_b else None
+        return dx, dw, db, None, None
+
+
+class ColumnParallelLinear(nn.Module):
+    """``out_features`` split over the group (padded to a multiple of the group size; the reference truncates,
+    SURVEY Q5).  ``gather_output=True`` returns the full (unpadded) output on every rank."""
+
+    def __init__(self, in_features: int, out_features: int, comm: TPComm, bias: bool = True,
+                 gather_output: bool = True, full_weight: Optional[torch.Tensor] = None,
+                 full_bias: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.comm, self.out_features, self.gather_output = comm, out_features, gather_output
+        kpad = padded_classes(out_features, comm.world)
+        lo, hi = shard_range(kpad, comm.world, comm.rank)
+        w = torch.zeros(kpad, in_features)
+        if full_weight is None:
+            full_weight = torch.empty(out_features, in_features)
+            nn.init.kaiming_uniform_(full_weight, a=5 ** 0.5)
+        w[:out_features] = full_weight
+        self.weight = nn.Parameter(w[lo:hi].clone())
+        self.weight.tp_sharded = True
+        self.bias = None
+        if bias:
+            bb = torch.zeros(kpad)
+            if full_bias is not None:
+                bb[:out_features] = full_bias
+            self.bias = nn.Parameter(bb[lo:hi].clone())
+            self.bias.tp_sharded = True
+
+    def forward(self, x):
+        y = _ColumnLinearFn.apply(x, self.weight, self.bias, self.comm, self.gather_output)
+        return y[:, : self.out_features] if self.gather_output else y
+
+
+class RowParallelLinear(nn.Module):
+    """``in_features`` split over the group: the input is the local feature shard, the partial products are
+    all-reduced — on GPUs by the fused GEMM+all-reduce kernel when a ``FusedTP`` heap is attached and shapes
+    are multiples of 64 (bf16)."""
+
+    def __init__(self, in_features: int, out_features: int, comm: TPComm, bias: bool = True,
+                 full_weight: Optional[torch.Tensor] = None, full_bias: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.comm = comm
+        lo, hi = shard_range(in_features, comm.world, comm.rank)
+        if full_weight is None:
+            full_weight = torch.empty(out_features, in_features)
+            nn.init.kaiming_uniform_(full_weight, a=5 ** 0.5)
+        self.weight = nn.Parameter(full_weight[:, lo:hi].clone())
+        self.weight.tp_sharded = True
+        self.bias = nn.Parameter(full_bias.clone() if full_bias is not None else torch.zeros(out_features)) if bias else None
+        self._fused = {}
+
+    def _fused_op(self, x):
+        f = self.comm.fused
+        if f is None or not x.is_cuda or x.dtype != torch.bfloat16 or self.weight.dtype != torch.bfloat16:
+            return None
+        key = tuple(x.shape)
+        if key not in self._fused:
+            n, ks = x.shape
+            ok = f.supported((n, ks, 1, 1), self.weight.shape[0])
+            self._fused[key] = f.allreduce_conv(0, (n, ks, 1, 1), self.weight.shape[0], R=1, pad=0) if ok else None
+        return self._fused[key]
+
+    def forward(self, x_shard):
+        return _RowLinearFn.apply(x_shard, self.weight, self.bias, self.comm, self._fused_op(x_shard))

@@ -120,6 +120,10 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         print(f"Worker {rank} is starting training...", flush=True)
     cuda = rt.device.type == "cuda"
     df = None
+    dev_idle = dev_stamps = None
+    if cfg.step_barrier and world > 1 and hasattr(getattr(eng, "ar", None), "handle"):
+        dev_stamps = torch.zeros(2, dtype=torch.int64, device=rt.device)
+        dev_idle = torch.zeros((), dtype=torch.int64, device=rt.device)
     for epoch in range(start_epoch, cfg.epochs):
         sampler.set_epoch(epoch)
         t_epoch = time.time()
@@ -142,11 +146,16 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
             fault.maybe_fail(eng.global_step)
             eng.step(x, y)
             if cfg.step_barrier and world > 1:
-                ti = time.time()
-                if cuda:
-                    torch.cuda.synchronize()
-                dist.barrier()
-                rec.total_idle += time.time() - ti
+                if dev_idle is not None:
+                    # device-side flag barrier over NVLink: no host sync; idle = release − arrival
+                    eng.ar.handle.barrier(dev_stamps)
+                    dev_idle += (dev_stamps[1] - dev_stamps[0])
+                else:
+                    ti = time.time()
+                    if cuda:
+                        torch.cuda.synchronize()
+                    dist.barrier()
+                    rec.total_idle += time.time() - ti
             step_times.append(time.time() - ts)
             nsteps += 1
             if bi % 50 == 0:
@@ -158,6 +167,9 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         else:
             dev_s = time.time() - t_epoch
         s = eng.stats.read_and_reset()
+        if dev_idle is not None:
+            rec.total_idle += float(dev_idle.item()) * 1e-9
+            dev_idle.zero_()
         epoch_time = time.time() - t_epoch
         steps = max(int(s["steps"]), 1)
         loss = s["loss_sum"] / steps

@@ -155,3 +155,29 @@ def tp_equivalence(rank, world, out_dir):
     for n in ("conv1.weight", "layer1.0.conv1.weight", "layer2.0.downsample.0.weight", "layer4.1.bn2.weight"):
         assert torch.allclose(got["backbone." + n].main_grad, ref[n], atol=5e-5), n
     assert comm.take_bytes() > 0
+
+
+def tp_linear_equivalence(rank, world, out_dir):
+    """ColumnParallelLinear → RowParallelLinear (the Megatron MLP pattern) == dense Linear → Linear, incl. grads;
+    out_features=10 is not divisible by the group size (padding path)."""
+    from horizonml_b200.parallel.tp import ColumnParallelLinear, RowParallelLinear, TPComm, shard_range, padded_classes
+    comm = TPComm()
+    g = torch.Generator().manual_seed(0)
+    w1, b1 = torch.randn(64, 32, generator=g) * 0.1, torch.randn(64, generator=g) * 0.1
+    w2, b2 = torch.randn(10, 64, generator=g) * 0.1, torch.randn(10, generator=g) * 0.1
+    x = torch.randn(8, 32, generator=g, requires_grad=True)
+    y = torch.relu(x @ w1.t() + b1) @ w2.t() + b2
+    y.square().sum().backward()
+    gx_ref = x.grad.clone()
+    col = ColumnParallelLinear(32, 64, comm, full_weight=w1, full_bias=b1, gather_output=False)
+    row = RowParallelLinear(64, 10, comm, full_weight=w2, full_bias=b2)
+    x2 = x.detach().clone().requires_grad_(True)
+    y2 = row(torch.relu(col(x2)))
+    assert torch.allclose(y2, y.detach(), atol=1e-5)
+    y2.square().sum().backward()
+    assert torch.allclose(x2.grad, gx_ref, atol=1e-5)
+    # gathered column-parallel head with padding: 10 classes over `world` ranks
+    head = ColumnParallelLinear(64, 10, comm, full_weight=w2, full_bias=b2, gather_output=True)
+    h = torch.randn(8, 64, generator=g)
+    assert torch.allclose(head(h), h @ w2.t() + b2, atol=1e-5)
+    assert head.weight.shape[0] == padded_classes(10, world) // world

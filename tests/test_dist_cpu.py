@@ -30,6 +30,10 @@ def test_tp_equivalence_gloo(tmp_path):
     run("tp_equivalence", 2, find_free_port(), str(tmp_path))
 
 
+def test_tp_linear_layers_gloo(tmp_path):
+    run("tp_linear_equivalence", 4, find_free_port(), str(tmp_path))
+
+
 @pytest.mark.parametrize("runner,strategy,ws", [(run_data_parallel, "data", 2), (run_model_parallel, "layer", 2),
                                                 (run_tensor_parallel, "tensor", 2)])
 def test_entrypoints_world2_cpu(tmp_path, runner, strategy, ws):
