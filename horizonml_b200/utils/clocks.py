@@ -29,6 +29,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Samples taken before this call (warm-up, start-up of nvidia-smi itself) are discarded by ``stop``."""
+        self._mark = len(self.lines)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -38,7 +42,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "_mark", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
