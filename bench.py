@@ -39,6 +39,7 @@ def parse():
     p.add_argument("--no_graph", action="store_true")
     p.add_argument("--no_flush", action="store_true")
     p.add_argument("--no_grad_divergence", action="store_true")
+    p.add_argument("--bucket_mb", type=float, default=25.0)
     return p.parse_args()
 
 
@@ -64,7 +65,7 @@ def run_ours(args):
         backend = "torch"
     cfg = TrainConfig(strategy="data", world_size=world, batch_size=args.batch, device="cuda", dtype="bf16",
                       backend=backend, allreduce=args.allreduce, cuda_graph=not args.no_graph,
-                      grad_divergence=not args.no_grad_divergence, quiet=True)
+                      grad_divergence=not args.no_grad_divergence, quiet=True, bucket_mb=args.bucket_mb)
     rt = setup_runtime(rank, world, cfg, "cuda")
     dev = rt.device
     eng = DPEngine(cfg, rt)
@@ -93,7 +94,7 @@ def run_ours(args):
         if rt.backend == "native" and i == 1:
             launches = sum(nb.LAUNCHES.values()) - before
     torch.cuda.synchronize()
-    if eng.reducer is not None and launches is not None:
+    if eng.ar is not None and launches is not None:      # one fused all-reduce kernel per bucket
         launches += len(eng.flat.buckets)
     graphed = eng._graphed.graph is not None
 
@@ -171,6 +172,7 @@ def run_ours(args):
                    "image": "32x32x3", "optimizer": "Adam(lr=1e-3)", "parallelism": f"dp{world}",
                    "backend": rt.backend, "allreduce": getattr(eng.ar, "name", None) if eng.ar else None,
                    "cuda_graph": graphed, "grad_divergence_metric": cfg.grad_divergence,
+                   "bucket_mb": cfg.bucket_mb, "buckets": len(eng.flat.buckets), "bucketwise_adam": eng.bucket_adam,
                    "l2": "256 MiB flush-write between timed steps (untimed); per-step working set "
                          "(fp32 master+m+v+grad, bf16 shadow ~ 200 MB) also exceeds the 126 MB L2",
                    "baseline_ref": "BASELINE.md: reference DP ~51 img/s (5 CPU procs, gloo, N=1000)"},

@@ -165,7 +165,7 @@ std::vector<Tensor> head_fwd_bwd(const Tensor& feat, const Tensor& W, const c10:
 
 void adam_step(Tensor master, Tensor grad, Tensor m, Tensor v, c10::optional<Tensor> shadow, Tensor step,
                double lr, double b1, double b2, double eps, double gscale, c10::optional<Tensor> prev,
-               c10::optional<Tensor> diff_out, bool zero_grad, c10::optional<Tensor> live_blocks) {
+               c10::optional<Tensor> diff_out, bool zero_grad, c10::optional<Tensor> live_blocks, bool bump) {
   TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && master.numel() % 4 == 0);
   c10::cuda::CUDAGuard g(master.device());
   void* sh = nullptr;
@@ -174,7 +174,7 @@ void adam_step(Tensor master, Tensor grad, Tensor m, Tensor v, c10::optional<Ten
           step.data_ptr<float>(), fptr(prev), fptr(diff_out), zero_grad ? 1 : 0, (size_t)master.numel(), (float)lr,
           (float)b1, (float)b2, (float)eps, (float)gscale,
           live_blocks.has_value() && live_blocks->defined() ? live_blocks->data_ptr<int>() : nullptr,
-          live_blocks.has_value() && live_blocks->defined() ? (size_t)live_blocks->numel() : 0, cur_stream());
+          live_blocks.has_value() && live_blocks->defined() ? (size_t)live_blocks->numel() : 0, bump ? 1 : 0, cur_stream());
 }
 
 Tensor grad_diff_sq(const Tensor& grad, Tensor prev) {
@@ -217,12 +217,20 @@ std::vector<Tensor> conv_fwd(const Tensor& x, const Tensor& w, int64_t stride, i
   return {y, stats};
 }
 
-Tensor conv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride, int64_t pad) {
+// addend (optional, same shape/layout as dx): dx = dgrad(dy, w) + addend, fused into the epilogue
+Tensor conv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride, int64_t pad,
+                  c10::optional<Tensor> addend) {
   check_cl(dy, "dy"); check_cl(w, "w");
   c10::cuda::CUDAGuard g(dy.device());
   const int N = (int)x_shape[0], Cin = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
   Tensor dx = empty_cl(dy, N, Cin, H, W);
-  int rc = hz_conv_dgrad(cptr(dy), cptr(w), dx.data_ptr(), N, H, W, Cin, (int)w.size(0), (int)w.size(2),
+  const void* add = nullptr;
+  if (addend.has_value() && addend->defined()) {
+    check_cl(*addend, "addend");
+    TORCH_CHECK(addend->sizes() == dx.sizes() && addend->scalar_type() == dx.scalar_type(), "dgrad addend mismatch");
+    add = addend->data_ptr();
+  }
+  int rc = hz_conv_dgrad(cptr(dy), cptr(w), dx.data_ptr(), add, N, H, W, Cin, (int)w.size(0), (int)w.size(2),
                          (int)stride, (int)pad, cur_stream());
   TORCH_CHECK(rc == 0, "hz_conv_dgrad failed rc=", rc);
   return dx;

@@ -48,6 +48,7 @@ struct IgemmParams {
   float* ws;                 // fp32 split-K workspace [tiles][128][BLOCK_N], all-zero between launches
   unsigned* sem;             // per-tile arrival counters, all-zero between launches
   __nv_bfloat16* out;
+  const __nv_bfloat16* addend;   // optional, same layout as out: out = tile + addend (residual-gradient fusion)
   float* stats;              // [2*ncols] or null
 };
 
@@ -270,7 +271,13 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     if (n >= p.n_images) continue;
     const long long off = (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride +
                           (long long)wi * p.out_w_stride + p.cls_out_off[cls] + nt * BLOCK_N + vec * 8;
-    st8(p.out + off, ld8(staging + r0 * S::kStagingLd + vec * 8));
+    bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
+    if (p.addend != nullptr) {
+      const bf16x8 a = ld8(p.addend + off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v.v[i] = __hadd2(v.v[i], a.v[i]);      // bf16 + bf16 -> bf16, as the separate add did
+    }
+    st8(p.out + off, v);
   }
   if (p.stats != nullptr) {
     // per-channel sum / sum of squares over this CTA's rows (zero-filled OOB rows contribute 0)
@@ -482,9 +489,11 @@ SplitWs get_split_ws() {
 int pick_cluster_splits(int tiles, int k_total) {
   // validated on B200 (all conv numerics tests; 0.670 -> 0.612 ms/step); HZ_CLUSTER_SPLITK=0 disables
   static const bool off = [] { const char* e = getenv("HZ_CLUSTER_SPLITK"); return e && e[0] == '0'; }();
-  if (off || tiles <= 0 || k_total < 16) return 1;
+  static const int min_k = [] { const char* e = getenv("HZ_CLUSTER_MIN_K"); return e ? atoi(e) : 16; }();
+  static const int min_per = [] { const char* e = getenv("HZ_CLUSTER_MIN_PER"); return e ? atoi(e) : 2; }();
+  if (off || tiles <= 0 || k_total < min_k) return 1;
   int s = 8;
-  while (s > 1 && (tiles * s > 148 || k_total / s < 2)) s >>= 1;
+  while (s > 1 && (tiles * s > 148 || k_total / s < min_per)) s >>= 1;
   return s;
 }
 
@@ -542,6 +551,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   p.out_n_stride = (long long)Ho * Wo * Cout; p.out_h_stride = (long long)Wo * Cout; p.out_w_stride = Cout;
   p.ncols = Cout;
   p.out = (__nv_bfloat16*)y;
+  p.addend = nullptr;
   p.stats = stats;
   if (stats && !stats_is_zero) hz::zero_f32(stats, (size_t)2 * Cout, st);
   {
@@ -563,7 +573,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
 }
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w)
-int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int R,
+int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout, int R,
                   int stride, int pad, cudaStream_t st) {
   const int S_ = R;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
@@ -610,6 +620,7 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, 
   p.out_w_stride = (long long)stride * Cin;
   p.ncols = Cin;
   p.out = (__nv_bfloat16*)dx;
+  p.addend = (const __nv_bfloat16*)addend;
   p.stats = nullptr;
   {
     const SplitWs w = get_split_ws();

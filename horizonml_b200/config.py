@@ -37,6 +37,7 @@ class TrainConfig:
     allreduce: str = "auto"           # auto | oneshot | twoshot | nvls | nccl
     bucket_mb: float = 25.0           # DDP-like bucket cap (MiB); reference uses DDP default 25
     overlap: bool = True              # overlap bucket all-reduce with backward
+    overlap_adam: bool = True         # bucket-wise Adam right behind each bucket's all-reduce (hidden under backward)
     microbatches: int = 4             # pipeline micro-batches (1F1B)
     tp_conv_split: bool = True        # channel-split layer3/4 convs in tensor-parallel mode
     synthetic: bool = True            # no network in this environment: synthetic CIFAR-shaped data
@@ -97,6 +98,7 @@ def add_train_flags(p: argparse.ArgumentParser, strategy: str) -> argparse.Argum
                    choices=["auto", "oneshot", "twoshot", "nvls", "nccl"])
     g.add_argument('--bucket_mb', type=float, default=d.bucket_mb)
     g.add_argument('--no_overlap', dest='overlap', action='store_false')
+    g.add_argument('--no_overlap_adam', dest='overlap_adam', action='store_false')
     g.add_argument('--microbatches', type=int, default=d.microbatches)
     g.add_argument('--no_tp_conv_split', dest='tp_conv_split', action='store_false')
     g.add_argument('--real_data', dest='synthetic', action='store_false',

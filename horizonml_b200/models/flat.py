@@ -197,6 +197,21 @@ class FlatAdam:
                              self.betas[0], self.betas[1], self.eps, grad_scale, prev_grad, True,
                              live_blocks=f.live_blocks)
 
+    @torch.no_grad()
+    def step_bucket(self, b: int, first: bool, diff_out=None, prev_grad=None, grad_scale: float = 1.0) -> None:
+        """The same fused pass restricted to bucket ``b`` — launched by the gradient reducer the moment that
+        bucket's gradients are final, so the optimizer overlaps the rest of backward.  ``first`` marks the first
+        bucket processed in this step (advances the step counter, clears the divergence accumulator)."""
+        from .. import ops
+        f = self.flat
+        bk = f.buckets[b]
+        sl = slice(bk.start, bk.end)
+        ops.adam_step(f.master[sl], f.grad[sl], self.m[sl], self.v[sl],
+                      f.shadow[sl] if f.shadow is not None else None, self.step_t, self.lr,
+                      self.betas[0], self.betas[1], self.eps, grad_scale,
+                      prev_grad[sl] if prev_grad is not None else None, True,
+                      live_blocks=f.bucket_live[b], diff_out=diff_out if prev_grad is not None else None, bump=first)
+
     def state_dict(self) -> dict:
         return {"m": self.m.cpu(), "v": self.v.cpu(), "step": self.step_t.cpu(), "lr": self.lr,
                 "betas": self.betas, "eps": self.eps}

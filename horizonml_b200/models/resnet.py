@@ -13,6 +13,7 @@ strategy (the layer-parallel script keeps torchvision's 1000-way fc, Q2).
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -46,10 +47,15 @@ class BNP(nn.Module):
         self.momentum, self.eps = 0.1, 1e-5
 
 
-def _cba(x, conv: ConvW, bn: BNP, relu: bool, residual=None, training=True):
+def _cba(x, conv: ConvW, bn: BNP, relu: bool, residual=None, training=True, in_link=None, res_link=None):
     return ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                            stride=conv.stride, pad=conv.pad, relu=relu, residual=residual,
-                           momentum=bn.momentum, eps=bn.eps, training=training)
+                           momentum=bn.momentum, eps=bn.eps, training=training, in_link=in_link, res_link=res_link)
+
+
+# the block input feeds two branches; their gradients are summed inside the later dgrad kernel's epilogue
+# (ops.GradLink) instead of by a separate accumulation kernel.  HZ_FUSE_RESADD=0 restores plain autograd.
+_FUSE_RESADD = os.environ.get("HZ_FUSE_RESADD", "1") != "0"
 
 
 class BasicBlock(nn.Module):
@@ -67,11 +73,13 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         t = self.training
-        idt = x
+        link = ops.GradLink(2) if (_FUSE_RESADD and t and torch.is_grad_enabled() and x.requires_grad) else None
         if self.downsample is not None:
-            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t)
-        y = _cba(x, self.conv1, self.bn1, relu=True, training=t)
-        return _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t)
+            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t, in_link=link)
+            y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link)
+            return _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t)
+        y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link)
+        return _cba(y, self.conv2, self.bn2, relu=True, residual=x, training=t, res_link=link)
 
 
 class Stem(nn.Module):

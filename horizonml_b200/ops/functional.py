@@ -117,10 +117,34 @@ def _write_vec_grad(p, g):
 # conv + BN + (residual) + (ReLU)
 # ----------------------------------------------------------------------------------------------
 
+class GradLink:
+    """Gradient hand-off between the ``n`` autograd nodes that consume ONE tensor (in a BasicBlock: conv1 and the
+    identity / downsample branch).  Instead of every node returning its share and autograd launching an add
+    kernel, a node that is not the last to run parks its share here and returns None; the next node folds the
+    parked tensor into its dgrad epilogue (``addend``); the last one returns the total.  Order independent."""
+    __slots__ = ("n", "k", "pending")
+
+    def __init__(self, n: int = 2):
+        self.n, self.k, self.pending = n, 0, None
+
+    def take(self):
+        a, self.pending = self.pending, None
+        return a
+
+    def put(self, g):
+        """``g`` already contains whatever ``take()`` returned."""
+        self.k += 1
+        if self.k >= self.n:
+            self.k = 0
+            return g
+        self.pending = g
+        return None
+
+
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
-                momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn):
+                momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link=None, res_link=None):
         be = _be(x)
         w = compute_weight(weight, x.dtype)
         if conv_fn is not None:        # fused GEMM + collective kernel (tensor parallel): already reduced
@@ -131,6 +155,7 @@ class _ConvBNAct(torch.autograd.Function):
                 y_raw, sums = post_conv(y_raw), None
         ctx.post_dgrad = post_dgrad
         ctx.dgrad_fn = dgrad_fn
+        ctx.in_link, ctx.res_link = in_link, res_link
         out, mean, invstd = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar,
                                           momentum, eps, residual, relu, training)
         ctx.save_for_backward(x, y_raw, out, mean, invstd)
@@ -157,11 +182,35 @@ class _ConvBNAct(torch.autograd.Function):
         w = compute_weight(weight, x.dtype)
         tgt, acc = grad_target(weight)
         zeroed = bool(getattr(weight, "_zeroed", False))      # buffer known to be all-zero before this step
-        if _side["enabled"] and x.is_cuda and ctx.x_needs_grad:
+        if has_res and ctx.res_link is not None:              # identity branch: park dres for conv1's dgrad epilogue
+            parked = ctx.res_link.take()
+            dres = ctx.res_link.put(dres if parked is None else dres + parked)
+        use_side = _side["enabled"] and x.is_cuda and ctx.x_needs_grad
+        if use_side:
             if _side["stream"] is None:
                 _side["stream"] = torch.cuda.Stream(device=x.device)
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
+            ev.record(torch.cuda.current_stream())            # wgrad needs dy only — not the dgrad enqueued next
+        # dgrad first: it is the critical path, and every read of this layer's weight is then enqueued before
+        # ``grad_written(weight)`` lets a bucket-wise optimizer update that weight
+        dx = None
+        if ctx.x_needs_grad:
+            link = ctx.in_link
+            addend = link.take() if link is not None else None
+            if ctx.dgrad_fn is not None:                      # fused dgrad GEMM + all-reduce
+                dx = ctx.dgrad_fn(dy, w)
+                if addend is not None:
+                    dx = dx + addend
+            else:
+                if ctx.post_dgrad is None:
+                    dx = be.conv_dgrad(dy, w, x.shape, stride, pad, addend)
+                else:                                         # column-parallel conv: Σ over shards
+                    dx = ctx.post_dgrad(be.conv_dgrad(dy, w, x.shape, stride, pad))
+                    if addend is not None:
+                        dx = dx + addend
+            if link is not None:
+                dx = link.put(dx)
+        if use_side:
             _side["stream"].wait_event(ev)
             with torch.cuda.stream(_side["stream"]):
                 be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc, zeroed)
@@ -171,20 +220,12 @@ class _ConvBNAct(torch.autograd.Function):
         else:
             be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc, zeroed)
             grad_written(weight)
-        dx = None
-        if ctx.x_needs_grad:
-            if ctx.dgrad_fn is not None:                      # fused dgrad GEMM + all-reduce
-                dx = ctx.dgrad_fn(dy, w)
-            else:
-                dx = be.conv_dgrad(dy, w, x.shape, stride, pad)
-                if ctx.post_dgrad is not None:                # column-parallel conv: Σ over shards
-                    dx = ctx.post_dgrad(dx)
-        return (dx, None, None, None, dres) + (None,) * 12
+        return (dx, None, None, None, dres) + (None,) * 14
 
 
 def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True, residual=None,
                 momentum=0.1, eps=1e-5, training=True, post_conv=None, post_dgrad=None,
-                conv_fn=None, dgrad_fn=None):
+                conv_fn=None, dgrad_fn=None, in_link=None, res_link=None):
     """``post_conv`` / ``post_dgrad`` are the tensor-parallel reduction points (row-parallel conv
     output, column-parallel conv input-gradient); they take and return a tensor.  ``conv_fn(x, w)`` /
     ``dgrad_fn(dy, w)`` replace conv + reduction by ONE fused GEMM+collective kernel."""
@@ -201,7 +242,7 @@ def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True,
                                   momentum, eps, residual, relu, training)
         return out
     return _ConvBNAct.apply(x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
-                            momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn)
+                            momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link, res_link)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -278,11 +319,13 @@ def head_logits(feat, fc_w, fc_b):
 # ----------------------------------------------------------------------------------------------
 
 def adam_step(master, grad, m, v, shadow, step_t, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0,
-              prev=None, zero_grad=False, live_blocks=None):
+              prev=None, zero_grad=False, live_blocks=None, diff_out=None, bump=True):
     """Returns Σ(g−prev)² (0-d tensor) when ``prev`` is given, else None.  ``live_blocks``: visit only these
-    64-element blocks (all other parameters provably never receive a gradient)."""
+    64-element blocks (all other parameters provably never receive a gradient).  Bucket-wise use: pass slices,
+    a shared ``diff_out`` accumulator, and ``bump=True`` only for the first bucket of the step (it advances the
+    step counter and clears the accumulator)."""
     return _be(master).adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad,
-                                 live_blocks)
+                                 live_blocks, diff_out, bump)
 
 
 def grad_diff_sq(grad, prev):

@@ -143,12 +143,16 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma
     return _tb.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot, dbeta_slot)
 
 
-def conv_dgrad(dy, w, x_shape, stride: int, pad: int):
+def conv_dgrad(dy, w, x_shape, stride: int, pad: int, addend=None):
+    """``addend``: bf16 channels_last tensor of x's shape added in the kernel epilogue (the residual-branch
+    gradient), replacing autograd's separate accumulation kernel."""
     if _bf16_cl(dy) and w.dtype == torch.bfloat16 and _conv_ok(tuple(x_shape), w.shape, stride, pad):
         LAUNCHES["conv_dgrad"] += 1
-        return C.conv_dgrad(dy, w, list(x_shape), stride, pad)
+        if addend is not None and not (_bf16_cl(addend) and tuple(addend.shape) == tuple(x_shape)):
+            return C.conv_dgrad(dy, w, list(x_shape), stride, pad, None).add_(addend)
+        return C.conv_dgrad(dy, w, list(x_shape), stride, pad, addend)
     _fallback("conv_dgrad", f"x={tuple(x_shape)} w={tuple(w.shape)}")
-    return _tb.conv_dgrad(dy, w, x_shape, stride, pad)
+    return _tb.conv_dgrad(dy, w, x_shape, stride, pad, addend)
 
 
 def _flat_dw_ok(out_grad: torch.Tensor, w_shape) -> bool:
@@ -213,14 +217,18 @@ def linear_fwd(x2d, w, b):
 
 
 def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.0, prev=None, zero_grad=False,
-              live_blocks=None):
+              live_blocks=None, diff_out=None, bump=True):
     if master.is_cuda and master.numel() % 4 == 0 and (shadow is None or shadow.dtype == torch.bfloat16):
-        LAUNCHES["adam"] += 2
-        diff = torch.empty((), dtype=torch.float32, device=master.device) if prev is not None else None
-        C.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, diff, zero_grad, live_blocks)
+        LAUNCHES["adam"] += 2 if bump else 1
+        diff = diff_out
+        if diff is None and prev is not None:
+            diff = torch.empty((), dtype=torch.float32, device=master.device)
+        C.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, diff, zero_grad, live_blocks,
+                    bump)
         return diff
     _fallback("adam_step", "")
-    return _tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad, live_blocks)
+    return _tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad, live_blocks,
+                         diff_out, bump)
 
 
 def grad_diff_sq(grad, prev):

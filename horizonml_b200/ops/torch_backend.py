@@ -92,10 +92,12 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: 
     return _cl(dy.to(y_raw.dtype)), dgamma, dbeta, dres
 
 
-def conv_dgrad(dy, w, x_shape, stride: int, pad: int):
+def conv_dgrad(dy, w, x_shape, stride: int, pad: int, addend=None):
     dx, _, _ = torch.ops.aten.convolution_backward(
         dy, dy.new_empty(x_shape), w.to(dy.dtype), None, [stride, stride], [pad, pad], [1, 1], False,
         [0, 0], 1, [True, False, False])
+    if addend is not None:
+        dx = dx + addend.to(dx.dtype)
     return _cl(dx)
 
 
@@ -174,16 +176,23 @@ def linear_fwd(x2d, w, b):
 
 
 def adam_step(master, grad, m, v, shadow, step_t, lr: float, b1: float, b2: float, eps: float,
-              grad_scale: float = 1.0, prev=None, zero_grad: bool = False, live_blocks=None):
+              grad_scale: float = 1.0, prev=None, zero_grad: bool = False, live_blocks=None, diff_out=None,
+              bump: bool = True):
     """Flat fused Adam (torch.optim.Adam semantics, no weight decay / amsgrad).
     ``step_t`` holds the step count (incremented here).  ``prev``: gradient-divergence bookkeeping —
     returns Σ(g−prev)² and sets prev ← g.  ``zero_grad``: g ← 0 afterwards (accumulate-only wgrads)."""
-    step_t += 1
+    if bump:                       # first (or only) bucket of this optimizer step
+        step_t += 1
+        if diff_out is not None:
+            diff_out.zero_()
     t = float(step_t.item()) if step_t.device.type == "cpu" else step_t.float()
-    diff = None
+    diff = diff_out
     if prev is not None:
         d = grad - prev
-        diff = (d * d).sum()
+        if diff_out is not None:
+            diff_out += (d * d).sum()
+        else:
+            diff = (d * d).sum()
         prev.copy_(grad)
     g = grad if grad_scale == 1.0 else grad * grad_scale
     m.mul_(b1).add_(g, alpha=1 - b1)

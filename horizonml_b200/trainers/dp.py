@@ -13,6 +13,7 @@ epoch.  No host barrier per step (flag ``--step_barrier`` restores the reference
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import Dict, List, Optional
 
@@ -59,12 +60,22 @@ class DPEngine:
         self.opt = FlatAdam(self.flat, lr=cfg.lr)
         kind = cfg.allreduce
         self.ar = make_grad_allreduce(kind, self.flat.total, dev) if rt.world > 1 else None
-        self.reducer = GradReducer(self.flat, self.ar, cfg.overlap) if self.ar is not None else None
         self.stats = DeviceStats(dev)
         ops.enable_side_stream(dev.type == "cuda" and rt.backend == "native")
         self.prev_grad = torch.zeros_like(self.flat.grad) if cfg.grad_divergence else None
+        # bucket-wise optimizer: Adam for a bucket runs right behind that bucket's all-reduce (or, on one GPU, as
+        # soon as its gradients are final) and overlaps the rest of backward
+        self.bucket_adam = bool(cfg.overlap_adam) and os.environ.get("HZ_OVERLAP_ADAM", "1") != "0"
+        self._diff_acc = torch.zeros((), dtype=torch.float32, device=dev) if self.prev_grad is not None else None
+        self.reducer = None
+        if self.ar is not None or self.bucket_adam:
+            self.reducer = GradReducer(self.flat, self.ar, cfg.overlap,
+                                       post_bucket=self._adam_bucket if self.bucket_adam else None)
         self._graphed = GraphedStep(self._step_impl, dev, cfg.cuda_graph)
         self.global_step = 0
+
+    def _adam_bucket(self, b: int, first: bool) -> None:
+        self.opt.step_bucket(b, first, diff_out=self._diff_acc, prev_grad=self.prev_grad)
 
     # one full training step; everything inside is stream-ordered and graph-capturable
     def _step_impl(self, images, labels) -> None:
@@ -81,7 +92,10 @@ class DPEngine:
         ops.join_side()
         if self.reducer is not None:
             self.reducer.finish()
-        diff = self.opt.step(prev_grad=self.prev_grad)
+        if self.bucket_adam:
+            diff = self._diff_acc          # every bucket's Adam has been joined by reducer.finish()
+        else:
+            diff = self.opt.step(prev_grad=self.prev_grad)
         self.stats.add_step(loss, correct, labels.shape[0], diff)
         ops.step_end()
 
@@ -90,7 +104,7 @@ class DPEngine:
         self.global_step += 1
 
     def allreduce_bytes_per_step(self) -> int:
-        if self.reducer is None:
+        if self.ar is None:
             return 0
         return sum(self.ar.wire_bytes(b.end - b.start if self.flat.bucket_live[b.index] is None
                                       else self.flat.bucket_live[b.index].numel() * 64) for b in self.flat.buckets)

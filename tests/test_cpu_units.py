@@ -298,3 +298,56 @@ def test_dead_tap_masks_are_exact():
     # per-bucket lists are relative to the bucket and cover exactly the live blocks
     tot = sum((b.end - b.start) // 64 if lv is None else lv.numel() for b, lv in zip(flat.buckets, flat.bucket_live))
     assert tot == flat.live_blocks.numel()
+
+
+def test_gradlink_fusion_equals_plain_autograd(monkeypatch):
+    """Residual-gradient hand-off (ops.GradLink): folding the identity/downsample-branch gradient into the
+    other branch's dgrad must give the same parameter and input gradients as autograd's own accumulation."""
+    from horizonml_b200.models import resnet as R
+    gen = torch.Generator().manual_seed(11)
+    x0 = torch.randn(8, 3, 32, 32, generator=gen).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (8,), generator=gen)
+    grads = {}
+    for fuse in (True, False):
+        monkeypatch.setattr(R, "_FUSE_RESADD", fuse)
+        m = resnet18(10, seed=4).train()
+        flat = FlatParams(list(m.named_parameters()), "cpu", torch.float32)
+        flat.begin_step()
+        x = x0.clone().requires_grad_(True)
+        m.forward_loss(x, y)[0].backward()
+        grads[fuse] = (flat.grad.clone(), x.grad.clone())
+    for a, b in zip(grads[True], grads[False]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (a - b).abs().max()
+
+
+def test_bucketwise_adam_equals_whole_buffer_adam():
+    """FlatAdam.step_bucket over all buckets (any order of buckets, first one bumps the step) == FlatAdam.step."""
+    outs = []
+    for bucketwise in (False, True):
+        m = resnet18(10, seed=6).train()
+        flat = FlatParams(list(m.named_parameters()), "cpu", torch.float32, bucket_cap_mb=4.0,
+                          live_masks=m.live_tap_masks(32))
+        assert len(flat.buckets) > 4
+        opt = FlatAdam(flat, lr=1e-3)
+        prev = torch.zeros_like(flat.grad)
+        acc = torch.zeros(())
+        gen = torch.Generator().manual_seed(3)
+        diffs = []
+        for it in range(3):
+            flat.grad.copy_(torch.randn(flat.total, generator=gen) * 0.01)
+            if bucketwise:
+                order = list(range(len(flat.buckets)))
+                if it == 1:
+                    order = order[::-1]
+                for k, b in enumerate(order):
+                    opt.step_bucket(b, k == 0, diff_out=acc, prev_grad=prev)
+                diffs.append(float(acc))
+            else:
+                diffs.append(float(opt.step(prev_grad=prev)))
+            assert float(flat.grad.abs().max()) == 0.0          # cleared by the optimizer pass
+        outs.append((flat.master.clone(), opt.m.clone(), opt.v.clone(), float(opt.step_t), diffs))
+    a, b = outs
+    assert a[3] == b[3] == 3.0
+    for i in range(3):
+        assert torch.allclose(a[i], b[i], rtol=1e-6, atol=1e-8)
+    assert all(abs(x - y) <= 1e-4 * abs(x) for x, y in zip(a[4], b[4]))

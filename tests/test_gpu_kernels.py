@@ -69,6 +69,20 @@ def test_conv_dgrad_tcgen05(nb, tb, cfg):
 
 
 @pytest.mark.parametrize("cfg", CONVS)
+def test_conv_dgrad_fused_addend(nb, tb, cfg):
+    """dx = dgrad(dy, w) + addend in the kernel epilogue (residual-gradient fusion), every tile / split-K path."""
+    x, w, dy = _conv_data(cfg)
+    add = cl((torch.randn(x.shape, generator=torch.Generator().manual_seed(3)) * 0.5).to(DEV).bfloat16())
+    before = nb.FALLBACKS["conv_dgrad"]
+    dx = nb.conv_dgrad(dy, w, x.shape, cfg[6], cfg[7], add)
+    assert nb.FALLBACKS["conv_dgrad"] == before
+    plain = nb.conv_dgrad(dy, w, x.shape, cfg[6], cfg[7])
+    assert torch.equal(dx, plain + add)            # bf16 + bf16 -> bf16, exactly what the separate add produced
+    dxr = tb.conv_dgrad(dy.float(), w.float(), x.shape, cfg[6], cfg[7]) + add.float()
+    assert rel_err(dx, dxr) < 2e-2
+
+
+@pytest.mark.parametrize("cfg", CONVS)
 def test_conv_wgrad_tcgen05(nb, tb, cfg):
     N, Cin, H, W, Cout, R, s, p = cfg
     x, w, dy = _conv_data(cfg)
@@ -165,6 +179,39 @@ def test_adam_and_graddiff(nb):
     assert torch.equal(sh, p.bfloat16()) and st.item() == 3
     d = nb.grad_diff_sq(gr, torch.zeros_like(gr))
     assert abs(d.item() - (gr * gr).sum().item()) < 1e-3 * (gr * gr).sum().item()
+
+
+def test_adam_bucketwise_matches_whole(nb):
+    """Bucket slices + shared divergence accumulator + single step bump == one whole-buffer pass (bitwise)."""
+    g = torch.Generator().manual_seed(16)
+    n = 64 * 900
+    cuts = [0, 64 * 100, 64 * 101, 64 * 500, n]
+    live = torch.arange(0, 900, 2, dtype=torch.int32, device=DEV)
+    state = []
+    for bucketwise in (False, True):
+        g.manual_seed(16)
+        p = torch.randn(n, generator=g).to(DEV)
+        m, v, prev = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+        sh = p.bfloat16()
+        st = torch.zeros(1, device=DEV)
+        acc = torch.zeros((), device=DEV)
+        for it in range(3):
+            gr = (torch.randn(n, generator=g) * 0.01).to(DEV)
+            if not bucketwise:
+                d = nb.adam_step(p, gr, m, v, sh, st, 1e-3, 0.9, 0.999, 1e-8, 1.0, prev, True, live)
+            else:
+                for k, (lo, hi) in enumerate(zip(cuts, cuts[1:])):
+                    sel = live[(live >= lo // 64) & (live < hi // 64)] - lo // 64
+                    nb.adam_step(p[lo:hi], gr[lo:hi], m[lo:hi], v[lo:hi], sh[lo:hi], st, 1e-3, 0.9, 0.999, 1e-8, 1.0,
+                                 prev[lo:hi], True, sel.contiguous(), diff_out=acc, bump=(k == 0))
+                d = acc
+            torch.cuda.synchronize()
+        state.append((p.clone(), m.clone(), v.clone(), sh.clone(), st.item(), d.item()))
+    a, b = state
+    assert a[4] == b[4] == 3
+    for i in range(4):
+        assert torch.equal(a[i], b[i])
+    assert abs(a[5] - b[5]) <= 1e-4 * abs(a[5])
 
 
 def test_adam_and_allreduce_skip_dead_blocks(nb):
