@@ -165,7 +165,8 @@ std::vector<Tensor> head_fwd_bwd(const Tensor& feat, const Tensor& W, const c10:
 
 void adam_step(Tensor master, Tensor grad, Tensor m, Tensor v, c10::optional<Tensor> shadow, Tensor step,
                double lr, double b1, double b2, double eps, double gscale, c10::optional<Tensor> prev,
-               c10::optional<Tensor> diff_out, bool zero_grad, c10::optional<Tensor> live_blocks, bool bump) {
+               c10::optional<Tensor> diff_out, bool zero_grad, c10::optional<Tensor> live_blocks, bool bump,
+               int64_t max_ctas) {
   TORCH_CHECK(master.is_cuda() && master.scalar_type() == at::kFloat && master.numel() % 4 == 0);
   c10::cuda::CUDAGuard g(master.device());
   void* sh = nullptr;
@@ -174,7 +175,7 @@ void adam_step(Tensor master, Tensor grad, Tensor m, Tensor v, c10::optional<Ten
           step.data_ptr<float>(), fptr(prev), fptr(diff_out), zero_grad ? 1 : 0, (size_t)master.numel(), (float)lr,
           (float)b1, (float)b2, (float)eps, (float)gscale,
           live_blocks.has_value() && live_blocks->defined() ? live_blocks->data_ptr<int>() : nullptr,
-          live_blocks.has_value() && live_blocks->defined() ? (size_t)live_blocks->numel() : 0, bump ? 1 : 0, cur_stream());
+          live_blocks.has_value() && live_blocks->defined() ? (size_t)live_blocks->numel() : 0, bump ? 1 : 0, (int)max_ctas, cur_stream());
 }
 
 Tensor grad_diff_sq(const Tensor& grad, Tensor prev) {
@@ -200,7 +201,7 @@ bool conv_supported(int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, 
 }
 
 std::vector<Tensor> conv_fwd(const Tensor& x, const Tensor& w, int64_t stride, int64_t pad, bool want_stats,
-                             c10::optional<Tensor> zeroed_stats) {
+                             c10::optional<Tensor> zeroed_stats, bool weights_stable) {
   check_cl(x, "x"); check_cl(w, "w");
   c10::cuda::CUDAGuard g(x.device());
   auto d = dims_of(x);
@@ -212,14 +213,14 @@ std::vector<Tensor> conv_fwd(const Tensor& x, const Tensor& w, int64_t stride, i
   if (pre) stats = *zeroed_stats;
   else if (want_stats) stats = at::empty({2, Cout}, x.options().dtype(at::kFloat));
   int rc = hz_conv_fwd(cptr(x), cptr(w), y.data_ptr(), want_stats ? stats.data_ptr<float>() : nullptr, pre ? 1 : 0,
-                       d.N, d.H, d.W, d.C, Cout, R, (int)stride, (int)pad, cur_stream());
+                       d.N, d.H, d.W, d.C, Cout, R, (int)stride, (int)pad, weights_stable ? 1 : 0, cur_stream());
   TORCH_CHECK(rc == 0, "hz_conv_fwd failed rc=", rc);
   return {y, stats};
 }
 
 // addend (optional, same shape/layout as dx): dx = dgrad(dy, w) + addend, fused into the epilogue
 Tensor conv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride, int64_t pad,
-                  c10::optional<Tensor> addend) {
+                  c10::optional<Tensor> addend, bool weights_stable) {
   check_cl(dy, "dy"); check_cl(w, "w");
   c10::cuda::CUDAGuard g(dy.device());
   const int N = (int)x_shape[0], Cin = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
@@ -231,7 +232,7 @@ Tensor conv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shap
     add = addend->data_ptr();
   }
   int rc = hz_conv_dgrad(cptr(dy), cptr(w), dx.data_ptr(), add, N, H, W, Cin, (int)w.size(0), (int)w.size(2),
-                         (int)stride, (int)pad, cur_stream());
+                         (int)stride, (int)pad, weights_stable ? 1 : 0, cur_stream());
   TORCH_CHECK(rc == 0, "hz_conv_dgrad failed rc=", rc);
   return dx;
 }

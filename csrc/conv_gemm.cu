@@ -45,6 +45,7 @@ struct IgemmParams {
   int ncols;                 // valid output columns (Cout / Cin total)
   int splits;                // split-K factor (blockIdx.z = class * splits + split)
   int cluster;               // 1: the `splits` CTAs of a tile form a thread-block cluster and reduce through DSMEM
+  int prefetch_b;            // 1: weight tiles of the first stages are requested BEFORE griddepcontrol.wait
   float* ws;                 // fp32 split-K workspace [tiles][128][BLOCK_N], all-zero between launches
   unsigned* sem;             // per-tile arrival counters, all-zero between launches
   __nv_bfloat16* out;
@@ -92,6 +93,30 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
+
+  auto load_b = [&](int it) {
+    const int t = (k_lo + it) / p.cblocks, cb = (k_lo + it) % p.cblocks;
+    const int s = it % kStages;
+    uint8_t* sb = smem + s * S::kStageBytes + kABytes;
+    if (!B_MN) {
+      tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[t] + cb * kKBlock, nt * BLOCK_N);
+    } else {
+#pragma unroll
+      for (int j = 0; j < BLOCK_N / 64; ++j)
+        tc::tma_load_2d(sb + j * 8192, &bmap, &full[s], taps.bk[t] + nt * BLOCK_N + j * 64, cb * kKBlock);
+    }
+  };
+  // The B operand is the weight tensor: it was last written by the optimizer at least two kernels upstream, so
+  // (unlike A, the previous kernel's output) it may be requested before griddepcontrol.wait — the first ring of
+  // weight tiles (cold in L2: DRAM latency) streams in under the previous kernel's tail.
+  int n_pre = 0;
+  if (warp == 0 && lane == 0 && p.prefetch_b) {
+    n_pre = min(k_iters, kStages);
+    for (int it = 0; it < n_pre; ++it) {
+      tc::mbar_arrive_expect_tx(&full[it], S::kStageBytes);
+      load_b(it);
+    }
+  }
   pdl_wait();          // everything above overlapped the tail of the previous kernel
 
   if (warp == 0 && lane == 0) {
@@ -102,18 +127,13 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       const int cw = taps.dw[t], ch = h0 + taps.dh[t];
       const int s = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
-      tc::mbar_wait(&empty[s], ph ^ 1);
       uint8_t* sa = smem + s * S::kStageBytes;
-      uint8_t* sb = sa + kABytes;
-      tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
-      tc::tma_load_4d(sa, am, &full[s], cb * kKBlock, cw, ch, n0);
-      if (!B_MN) {
-        tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[t] + cb * kKBlock, nt * BLOCK_N);
-      } else {
-#pragma unroll
-        for (int j = 0; j < BLOCK_N / 64; ++j)
-          tc::tma_load_2d(sb + j * 8192, &bmap, &full[s], taps.bk[t] + nt * BLOCK_N + j * 64, cb * kKBlock);
+      if (it >= n_pre) {
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
       }
+      tc::tma_load_4d(sa, am, &full[s], cb * kKBlock, cw, ch, n0);
+      if (it >= n_pre) load_b(it);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
@@ -141,11 +161,38 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   // ===================== epilogue (all 4 warps) =====================
   __nv_bfloat16* staging = reinterpret_cast<__nv_bfloat16*>(smem);
   const int row = warp * 32 + lane;
+  int row_lo = 0, row_hi = kTileM;          // rows of the tile this CTA writes out
+  if (p.splits > 1 && p.cluster) {
+    row_lo = split * (kTileM / p.splits);
+    row_hi = row_lo + kTileM / p.splits;
+  }
+  constexpr int kVecPerRow = BLOCK_N / 8;
+  constexpr int kRowsPerPass = 128 / kVecPerRow;
+  constexpr int kPasses = kTileM / kRowsPerPass;
+  // global element offset of (tile row r0, this thread's 8-channel vector); -1 for rows past the last image
+  auto out_offset = [&](int r0) -> long long {
+    const int wi = r0 % p.BW;
+    const int hi = (r0 / p.BW) % p.BH;
+    const int n = n0 + r0 / (p.BW * p.BH);
+    if (n >= p.n_images) return -1;
+    return (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride + (long long)wi * p.out_w_stride +
+           p.cls_out_off[cls] + nt * BLOCK_N + (threadIdx.x % kVecPerRow) * 8;
+  };
+  // residual-gradient fusion: the addend rows this thread will write are requested now, so their L2 latency
+  // hides under the MMA tail instead of serialising with the stores
+  bf16x8 addv[kPasses];
+  if (p.addend != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
+      const long long off = r0 < row_hi ? out_offset(r0) : -1;
+      if (off >= 0) addv[i] = ld8(p.addend + off);
+    }
+  }
   if (k_iters > 0) {
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
   }
-  int row_lo = 0, row_hi = kTileM;          // rows of the tile this CTA writes out
   if (p.splits > 1 && p.cluster) {
     // ---- cluster split-K: every CTA of the cluster parks its fp32 partial tile in its own shared memory,
     //      then CTA r reduces rows [r*128/S, (r+1)*128/S) of all S partials through distributed shared memory
@@ -171,8 +218,6 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     cluster_sync();
     const int Sx = p.splits;
     const int rows_per = kTileM / Sx;
-    row_lo = split * rows_per;
-    row_hi = row_lo + rows_per;
     constexpr int kChunks = BLOCK_N / 4;
     const uint32_t red_base = smem_u32(red);
     for (int idx = threadIdx.x; idx < rows_per * kChunks; idx += 128) {
@@ -260,24 +305,21 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   __syncthreads();
 
   // coalesced stores: BLOCK_N/8 16-byte vectors per row
-  constexpr int kVecPerRow = BLOCK_N / 8;
-  constexpr int kRowsPerPass = 128 / kVecPerRow;
-  const int vec = threadIdx.x % kVecPerRow;
-  for (int r0 = row_lo + threadIdx.x / kVecPerRow; r0 < row_hi; r0 += kRowsPerPass) {
-    const int wi = r0 % p.BW;
-    const int hi = (r0 / p.BW) % p.BH;
-    const int ni = r0 / (p.BW * p.BH);
-    const int n = n0 + ni;
-    if (n >= p.n_images) continue;
-    const long long off = (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride +
-                          (long long)wi * p.out_w_stride + p.cls_out_off[cls] + nt * BLOCK_N + vec * 8;
-    bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
-    if (p.addend != nullptr) {
-      const bf16x8 a = ld8(p.addend + off);
+  {
+    const int vec = threadIdx.x % kVecPerRow;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v.v[i] = __hadd2(v.v[i], a.v[i]);      // bf16 + bf16 -> bf16, as the separate add did
+    for (int i = 0; i < kPasses; ++i) {
+      const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
+      if (r0 >= row_hi) break;
+      const long long off = out_offset(r0);
+      if (off < 0) continue;
+      bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
+      if (p.addend != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.v[j] = __hadd2(v.v[j], addv[i].v[j]);  // bf16 + bf16 -> bf16, as the separate add did
+      }
+      st8(p.out + off, v);
     }
-    st8(p.out + off, v);
   }
   if (p.stats != nullptr) {
     // per-channel sum / sum of squares over this CTA's rows (zero-filled OOB rows contribute 0)
@@ -489,12 +531,17 @@ SplitWs get_split_ws() {
 int pick_cluster_splits(int tiles, int k_total) {
   // validated on B200 (all conv numerics tests; 0.670 -> 0.612 ms/step); HZ_CLUSTER_SPLITK=0 disables
   static const bool off = [] { const char* e = getenv("HZ_CLUSTER_SPLITK"); return e && e[0] == '0'; }();
-  static const int min_k = [] { const char* e = getenv("HZ_CLUSTER_MIN_K"); return e ? atoi(e) : 16; }();
+  static const int min_k = [] { const char* e = getenv("HZ_CLUSTER_MIN_K"); return e ? atoi(e) : 8; }();
   static const int min_per = [] { const char* e = getenv("HZ_CLUSTER_MIN_PER"); return e ? atoi(e) : 2; }();
   if (off || tiles <= 0 || k_total < min_k) return 1;
   int s = 8;
   while (s > 1 && (tiles * s > 148 || k_total / s < min_per)) s >>= 1;
   return s;
+}
+
+int prefetch_weights_enabled() {
+  static const int on = [] { const char* e = getenv("HZ_PREFETCH_B"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on;
 }
 
 int pick_splits(int tiles, int k_total) {
@@ -531,7 +578,7 @@ int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride,
 
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w[Cout,R,S,Cin]); stats (2*Cout fp32, zeroed here) optional
 int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_is_zero, int N, int H, int W,
-                int Cin, int Cout, int R, int stride, int pad, cudaStream_t st) {
+                int Cin, int Cout, int R, int stride, int pad, int weights_stable, cudaStream_t st) {
   const int S_ = R;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
   Tile t;
@@ -564,6 +611,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
       p.cluster = p.splits > 1;
     }
   }
+  p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;
   using SM = hz::IgemmSmem<BLOCK_N>;
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, false>, SM::kTotal);
   (void)attr;
@@ -574,7 +622,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w)
 int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout, int R,
-                  int stride, int pad, cudaStream_t st) {
+                  int stride, int pad, int weights_stable, cudaStream_t st) {
   const int S_ = R;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
   // output lattice per class: stride 1 -> (H,W); stride 2 -> (H/2,W/2) == (Ho,Wo)
@@ -634,6 +682,7 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
       p.cluster = p.splits > 1;
     }
   }
+  p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;
   using SM = hz::IgemmSmem<BLOCK_N>;
   static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, true>, SM::kTotal);
   (void)attr;

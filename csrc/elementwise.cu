@@ -831,13 +831,14 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
 
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
              int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, const int* live,
-             size_t n_live_blocks, int bump, cudaStream_t st) {
+             size_t n_live_blocks, int bump, int max_ctas, cudaStream_t st) {
   if (live != nullptr) n = n_live_blocks * 64;
   const bool diff = prev != nullptr && diff_out != nullptr;
   // bump = 0: a later bucket of the same optimizer step (step counter / divergence accumulator already set up)
   if (bump) hz::launch(hz::bump_step_kernel, dim3(1), dim3(1), 0, st, step, diff ? diff_out : nullptr);
   if (n == 0) return;
-  const int grid = grid_for(n / 4, 256, 148 * 8);
+  // max_ctas > 0: a bucket pass that runs beside backward kernels on another stream — leave thread slots free
+  const int grid = grid_for(n / 4, 256, max_ctas > 0 ? max_ctas : 148 * 8);
 #define HZ_ADAM(D, Z)                                                                                   \
   hz::launch(hz::adam_kernel<D, Z>, dim3(grid), dim3(256), 0, st, p, g, m, v, (__nv_bfloat16*)shadow, step, prev, diff_out, n, lr, \
                                               b1, b2, eps, gscale, live)

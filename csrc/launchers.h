@@ -30,7 +30,7 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
                      int out_is_zero, cudaStream_t st);
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
              int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, const int* live,
-             size_t n_live_blocks, int bump, cudaStream_t st);
+             size_t n_live_blocks, int bump, int max_ctas, cudaStream_t st);
 void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st);
 void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct, float batch,
                      const float* diff_sq, cudaStream_t st);
@@ -38,9 +38,9 @@ void hz_stats_update(float* stats, float* has_prev, const float* loss, const flo
 // ---- conv_gemm.cu (tcgen05 implicit GEMM)
 int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
 int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_is_zero, int N, int H, int W,
-                int Cin, int Cout, int R, int stride, int pad, cudaStream_t st);
+                int Cin, int Cout, int R, int stride, int pad, int weights_stable, cudaStream_t st);
 int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout, int R,
-                  int stride, int pad, cudaStream_t st);
+                  int stride, int pad, int weights_stable, cudaStream_t st);
 int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,
                   int stride, int pad, int accumulate, int prezeroed, long long ld_out, int n_valid,
                   cudaStream_t st);

@@ -12,6 +12,7 @@ address requirement is 16 B; 128 B keeps vector loads and swizzle atoms aligned)
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -19,6 +20,8 @@ import torch
 import torch.nn as nn
 
 ALIGN = 64
+# bucket-wise Adam runs beside backward kernels: 2 CTAs x 256 threads per SM leave room for their CTAs
+_BUCKET_CTAS = int(os.environ.get("HZ_ADAM_BUCKET_CTAS", "296"))
 
 
 @dataclass
@@ -74,6 +77,7 @@ class FlatParams:
             p._flat_range = (o, o + n)
             if self.shadow is not None:
                 p.shadow = view(self.shadow)
+                p.shadow._hz_stable = True      # only the optimizer pass writes it (see native_backend._stable)
         self.sync_shadow()
         self._attach_autograd_bridge()
         self.buckets = self._make_buckets(bucket_cap_mb, first_bucket_mb)
@@ -210,7 +214,8 @@ class FlatAdam:
                       f.shadow[sl] if f.shadow is not None else None, self.step_t, self.lr,
                       self.betas[0], self.betas[1], self.eps, grad_scale,
                       prev_grad[sl] if prev_grad is not None else None, True,
-                      live_blocks=f.bucket_live[b], diff_out=diff_out if prev_grad is not None else None, bump=first)
+                      live_blocks=f.bucket_live[b], diff_out=diff_out if prev_grad is not None else None, bump=first,
+                      max_ctas=_BUCKET_CTAS)
 
     def state_dict(self) -> dict:
         return {"m": self.m.cpu(), "v": self.v.cpu(), "step": self.step_t.cpu(), "lr": self.lr,

@@ -319,13 +319,13 @@ def head_logits(feat, fc_w, fc_b):
 # ----------------------------------------------------------------------------------------------
 
 def adam_step(master, grad, m, v, shadow, step_t, lr, b1=0.9, b2=0.999, eps=1e-8, grad_scale=1.0,
-              prev=None, zero_grad=False, live_blocks=None, diff_out=None, bump=True):
+              prev=None, zero_grad=False, live_blocks=None, diff_out=None, bump=True, max_ctas=0):
     """Returns Σ(g−prev)² (0-d tensor) when ``prev`` is given, else None.  ``live_blocks``: visit only these
     64-element blocks (all other parameters provably never receive a gradient).  Bucket-wise use: pass slices,
     a shared ``diff_out`` accumulator, and ``bump=True`` only for the first bucket of the step (it advances the
     step counter and clears the accumulator)."""
     return _be(master).adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad,
-                                 live_blocks, diff_out, bump)
+                                 live_blocks, diff_out, bump, max_ctas)
 
 
 def grad_diff_sq(grad, prev):

@@ -85,12 +85,20 @@ def _is_stem(x_shape, w_shape) -> bool:
 
 
 # ------------------------------------------------------------------------------------------------
+def _stable(w) -> bool:
+    """True for the persistent bf16 shadow of a FlatParams parameter: last written by the optimizer, i.e. at least
+    two kernels before any conv that reads it — the kernel may then request weight tiles before
+    ``griddepcontrol.wait`` (programmatic dependent launch).  Anything else (casts, slices, padded copies) may have
+    been produced by the immediately preceding kernel and is only read after the wait."""
+    return bool(getattr(w, "_hz_stable", False))
+
+
 def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
     if _bf16_cl(x) and w.dtype == torch.bfloat16:
         if _conv_ok(x.shape, w.shape, stride, pad):
             LAUNCHES["conv_fwd"] += 1
             pre = ARENA.take(2, w.shape[0], x.device) if want_stats else None
-            y, stats = C.conv_fwd(x, w, stride, pad, want_stats, pre)
+            y, stats = C.conv_fwd(x, w, stride, pad, want_stats, pre, _stable(w))
             return y, (stats if want_stats else None)
         if _is_stem(x.shape, w.shape):
             n, cin, h, wd = x.shape
@@ -102,7 +110,8 @@ def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
             LAUNCHES["stem_im2col"] += 2
             LAUNCHES["conv_fwd"] += 1
             pre = ARENA.take(2, cout, x.device) if want_stats else None
-            y2, stats = C.conv_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0, want_stats, pre)
+            y2, stats = C.conv_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0, want_stats, pre,
+                                  False)          # wp was produced by the kernel right before: no early weight prefetch
             y = y2.reshape(n, ho, wo, cout).permute(0, 3, 1, 2)
             return y, (stats if want_stats else None)
     _fallback("conv_fwd", f"x={tuple(x.shape)} w={tuple(w.shape)} s={stride}")
@@ -149,8 +158,8 @@ def conv_dgrad(dy, w, x_shape, stride: int, pad: int, addend=None):
     if _bf16_cl(dy) and w.dtype == torch.bfloat16 and _conv_ok(tuple(x_shape), w.shape, stride, pad):
         LAUNCHES["conv_dgrad"] += 1
         if addend is not None and not (_bf16_cl(addend) and tuple(addend.shape) == tuple(x_shape)):
-            return C.conv_dgrad(dy, w, list(x_shape), stride, pad, None).add_(addend)
-        return C.conv_dgrad(dy, w, list(x_shape), stride, pad, addend)
+            return C.conv_dgrad(dy, w, list(x_shape), stride, pad, None, _stable(w)).add_(addend)
+        return C.conv_dgrad(dy, w, list(x_shape), stride, pad, addend, _stable(w))
     _fallback("conv_dgrad", f"x={tuple(x_shape)} w={tuple(w.shape)}")
     return _tb.conv_dgrad(dy, w, x_shape, stride, pad, addend)
 
@@ -217,18 +226,18 @@ def linear_fwd(x2d, w, b):
 
 
 def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.0, prev=None, zero_grad=False,
-              live_blocks=None, diff_out=None, bump=True):
+              live_blocks=None, diff_out=None, bump=True, max_ctas=0):
     if master.is_cuda and master.numel() % 4 == 0 and (shadow is None or shadow.dtype == torch.bfloat16):
         LAUNCHES["adam"] += 2 if bump else 1
         diff = diff_out
         if diff is None and prev is not None:
             diff = torch.empty((), dtype=torch.float32, device=master.device)
         C.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, diff, zero_grad, live_blocks,
-                    bump)
+                    bump, max_ctas)
         return diff
     _fallback("adam_step", "")
     return _tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad, live_blocks,
-                         diff_out, bump)
+                         diff_out, bump, max_ctas)
 
 
 def grad_diff_sq(grad, prev):

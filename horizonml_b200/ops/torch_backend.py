@@ -177,7 +177,7 @@ def linear_fwd(x2d, w, b):
 
 def adam_step(master, grad, m, v, shadow, step_t, lr: float, b1: float, b2: float, eps: float,
               grad_scale: float = 1.0, prev=None, zero_grad: bool = False, live_blocks=None, diff_out=None,
-              bump: bool = True):
+              bump: bool = True, max_ctas: int = 0):
     """Flat fused Adam (torch.optim.Adam semantics, no weight decay / amsgrad).
     ``step_t`` holds the step count (incremented here).  ``prev``: gradient-divergence bookkeeping —
     returns Σ(g−prev)² and sets prev ← g.  ``zero_grad``: g ← 0 afterwards (accumulate-only wgrads)."""

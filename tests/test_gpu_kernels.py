@@ -56,6 +56,9 @@ def test_conv_fwd_tcgen05(nb, tb, cfg):
     yr, sr = tb.conv_fwd(x.float(), w.float(), cfg[6], cfg[7], True)
     assert rel_err(y, yr) < 2e-2
     assert rel_err(stats, sr) < 2e-2
+    w._hz_stable = True          # optimizer-owned weights: tiles requested before griddepcontrol.wait
+    y2, _ = nb.conv_fwd(x, w, cfg[6], cfg[7], True)
+    assert torch.equal(y, y2)
 
 
 @pytest.mark.parametrize("cfg", CONVS)
@@ -66,6 +69,8 @@ def test_conv_dgrad_tcgen05(nb, tb, cfg):
     assert nb.FALLBACKS["conv_dgrad"] == before
     dxr = tb.conv_dgrad(dy.float(), w.float(), x.shape, cfg[6], cfg[7])
     assert rel_err(dx, dxr) < 2e-2
+    w._hz_stable = True
+    assert torch.equal(dx, nb.conv_dgrad(dy, w, x.shape, cfg[6], cfg[7]))
 
 
 @pytest.mark.parametrize("cfg", CONVS)

@@ -16,9 +16,11 @@ try:
 except Exception as e:
     print("FAILED", e)')" | tee -a $OUT
 }
-run base            HZ_OVERLAP_ADAM=0 HZ_FUSE_RESADD=0 --
-run adam            HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=0 --
-run adam+resadd     HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 --
-run all_b4          HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 -- --bucket_mb 4
-run all_k8p2        HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 HZ_CLUSTER_MIN_K=8 HZ_CLUSTER_MIN_PER=2 --
-run all_k4p1        HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 HZ_CLUSTER_MIN_K=4 HZ_CLUSTER_MIN_PER=1 --
+run base            HZ_OVERLAP_ADAM=0 HZ_FUSE_RESADD=0 HZ_PREFETCH_B=0 --
+run prefetch        HZ_OVERLAP_ADAM=0 HZ_FUSE_RESADD=0 HZ_PREFETCH_B=1 --
+run pf+resadd       HZ_OVERLAP_ADAM=0 HZ_FUSE_RESADD=1 HZ_PREFETCH_B=1 --
+run pf+ra+adam296   HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 HZ_PREFETCH_B=1 --
+run all_b4_296      HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 HZ_PREFETCH_B=1 -- --bucket_mb 4
+run all_b4_148      HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 HZ_PREFETCH_B=1 HZ_ADAM_BUCKET_CTAS=148 -- --bucket_mb 4
+run all_b2_148      HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 HZ_PREFETCH_B=1 HZ_ADAM_BUCKET_CTAS=148 -- --bucket_mb 2
+run all_b4_74       HZ_OVERLAP_ADAM=1 HZ_FUSE_RESADD=1 HZ_PREFETCH_B=1 HZ_ADAM_BUCKET_CTAS=74 -- --bucket_mb 4
