@@ -40,6 +40,7 @@ def parse():
     p.add_argument("--no_flush", action="store_true")
     p.add_argument("--no_grad_divergence", action="store_true")
     p.add_argument("--bucket_mb", type=float, default=25.0)
+    p.add_argument("--live_bucket_mb", type=float, default=2.0)
     return p.parse_args()
 
 
@@ -65,7 +66,8 @@ def run_ours(args):
         backend = "torch"
     cfg = TrainConfig(strategy="data", world_size=world, batch_size=args.batch, device="cuda", dtype="bf16",
                       backend=backend, allreduce=args.allreduce, cuda_graph=not args.no_graph,
-                      grad_divergence=not args.no_grad_divergence, quiet=True, bucket_mb=args.bucket_mb)
+                      grad_divergence=not args.no_grad_divergence, quiet=True, bucket_mb=args.bucket_mb,
+                      live_bucket_mb=args.live_bucket_mb)
     rt = setup_runtime(rank, world, cfg, "cuda")
     dev = rt.device
     eng = DPEngine(cfg, rt)
@@ -172,7 +174,7 @@ def run_ours(args):
                    "image": "32x32x3", "optimizer": "Adam(lr=1e-3)", "parallelism": f"dp{world}",
                    "backend": rt.backend, "allreduce": getattr(eng.ar, "name", None) if eng.ar else None,
                    "cuda_graph": graphed, "grad_divergence_metric": cfg.grad_divergence,
-                   "bucket_mb": cfg.bucket_mb, "buckets": len(eng.flat.buckets), "bucketwise_adam": eng.bucket_adam,
+                   "bucket_mb": cfg.bucket_mb, "live_bucket_mb": cfg.live_bucket_mb, "buckets": len(eng.flat.buckets), "bucketwise_adam": eng.bucket_adam,
                    "l2": "256 MiB flush-write between timed steps (untimed); per-step working set "
                          "(fp32 master+m+v+grad, bf16 shadow ~ 200 MB) also exceeds the 126 MB L2",
                    "baseline_ref": "BASELINE.md: reference DP ~51 img/s (5 CPU procs, gloo, N=1000)"},

@@ -39,7 +39,7 @@ def _round_up(x: int, a: int) -> int:
 class FlatParams:
     def __init__(self, named_params: Sequence[Tuple[str, nn.Parameter]], device, compute_dtype,
                  bucket_cap_mb: float = 25.0, reverse: bool = True, first_bucket_mb: float = 1.0,
-                 live_masks: Optional[Dict[str, torch.Tensor]] = None):
+                 live_masks: Optional[Dict[str, torch.Tensor]] = None, bucket_by_live: bool = False):
         named = list(named_params)
         order = list(reversed(named)) if reverse else named
         self.names = [n for n, _ in order]
@@ -80,34 +80,42 @@ class FlatParams:
                 p.shadow._hz_stable = True      # only the optimizer pass writes it (see native_backend._stable)
         self.sync_shadow()
         self._attach_autograd_bridge()
-        self.buckets = self._make_buckets(bucket_cap_mb, first_bucket_mb)
         self.live_blocks = None               # int32 indices of the 64-element blocks that can be non-zero
+        blk = self._live_block_mask(live_masks) if live_masks else None
+        # bucket_by_live: the caps count elements that actually travel (dead taps excluded), so a "25 MiB" bucket
+        # of mostly-dead layer4 weights does not delay the collective of the live ones behind it
+        self.buckets = self._make_buckets(bucket_cap_mb, first_bucket_mb, blk if bucket_by_live else None)
         self.bucket_live: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
-        if live_masks:
-            self._build_live(live_masks)
+        if blk is not None:
+            self._build_live(blk)
         self._bucket_of: Dict[int, int] = {}
         for b in self.buckets:
             for nme in b.names:
                 self._bucket_of[id(self.params[self.names.index(nme)])] = b.index
 
     # ------------------------------------------------------------------------------------
-    def _make_buckets(self, cap_mb: float, first_mb: float) -> List[Bucket]:
+    def _make_buckets(self, cap_mb: float, first_mb: float, live_blk: Optional[torch.Tensor] = None) -> List[Bucket]:
         """Greedy contiguous bucketing in gradient-ready order (DDP-style: small first bucket so
-        the first all-reduce starts early, then ``cap_mb`` buckets)."""
+        the first all-reduce starts early, then ``cap_mb`` buckets).  With ``live_blk`` (bool per 64-element
+        block) sizes are measured in live elements."""
         buckets: List[Bucket] = []
         cap = int(first_mb * (1 << 20) / 4)
         start, names = 0, []
+        csum = None
+        if live_blk is not None:
+            csum = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(live_blk.long(), 0)]) * ALIGN
         for i, (nme, p, o) in enumerate(zip(self.names, self.params, self.offsets)):
             names.append(nme)
             end = self.offsets[i + 1] if i + 1 < len(self.offsets) else self.total
-            if end - start >= cap or i + 1 == len(self.params):
+            size = end - start if csum is None else int(csum[end // ALIGN] - csum[start // ALIGN])
+            if size >= cap or i + 1 == len(self.params):
                 buckets.append(Bucket(len(buckets), start, end, names))
                 start, names = end, []
                 cap = int(cap_mb * (1 << 20) / 4)
         return buckets
 
-    def _build_live(self, live_masks) -> None:
-        """Dead-parameter elision: block list for the optimizer (whole buffer) and per bucket (all-reduce)."""
+    def _live_block_mask(self, live_masks) -> Optional[torch.Tensor]:
+        """bool per 64-element block: can any element of it ever receive a gradient?  None when all can."""
         nblk = self.total // ALIGN
         live = torch.ones(self.total, dtype=torch.bool)
         for nme, p, o in zip(self.names, self.params, self.offsets):
@@ -117,8 +125,11 @@ class FlatParams:
             phys = m.permute(0, 2, 3, 1).reshape(-1) if m.dim() == 4 else m.reshape(-1)
             live[o:o + p.numel()] = phys
         blk = live.view(nblk, ALIGN).any(dim=1)
-        if bool(blk.all()):
-            return
+        return None if bool(blk.all()) else blk
+
+    def _build_live(self, blk: torch.Tensor) -> None:
+        """Dead-parameter elision: block list for the optimizer (whole buffer) and per bucket (all-reduce)."""
+        nblk = self.total // ALIGN
         idx = torch.nonzero(blk).flatten().to(torch.int32)
         self.live_blocks = idx.to(self.device)
         self.live_fraction = float(idx.numel()) / nblk

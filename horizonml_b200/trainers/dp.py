@@ -50,7 +50,9 @@ class DPEngine:
         self.model = build_model(cfg, dev)
         self.model.train()
         live = self.model.live_tap_masks(32) if (cfg.skip_dead_taps and hasattr(self.model, "live_tap_masks")) else None
-        self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype, cfg.bucket_mb, live_masks=live)
+        by_live = live is not None and bool(cfg.bucket_by_live) and os.environ.get("HZ_BUCKET_LIVE", "1") != "0"
+        self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype,
+                               cfg.live_bucket_mb if by_live else cfg.bucket_mb, live_masks=live, bucket_by_live=by_live)
         if rt.world > 1:   # K1: make replicas identical (same seed already does; belt and braces)
             dist.broadcast(self.flat.master, src=0)
             for b in self.model.buffers():
@@ -65,7 +67,7 @@ class DPEngine:
         self.prev_grad = torch.zeros_like(self.flat.grad) if cfg.grad_divergence else None
         # bucket-wise optimizer: Adam for a bucket runs right behind that bucket's all-reduce (or, on one GPU, as
         # soon as its gradients are final) and overlaps the rest of backward
-        self.bucket_adam = bool(cfg.overlap_adam) and os.environ.get("HZ_OVERLAP_ADAM", "1") != "0"
+        self.bucket_adam = bool(cfg.overlap_adam) or os.environ.get("HZ_OVERLAP_ADAM", "0") == "1"
         self._diff_acc = torch.zeros((), dtype=torch.float32, device=dev) if self.prev_grad is not None else None
         self.reducer = None
         if self.ar is not None or self.bucket_adam:
