@@ -38,7 +38,7 @@ class TrainConfig:
     bucket_mb: float = 25.0           # DDP-like bucket cap (MiB); reference uses DDP default 25
     overlap: bool = True              # overlap bucket all-reduce with backward
     overlap_adam: bool = False        # bucket-wise Adam right behind each bucket's all-reduce (measured: no gain on B200)
-    bucket_by_live: bool = True       # with dead-tap elision, size buckets by LIVE elements using live_bucket_mb
+    bucket_by_live: bool = False      # with dead-tap elision, size buckets by LIVE elements using live_bucket_mb
     live_bucket_mb: float = 2.0       # (fp32 MiB of live gradient per bucket; the last bucket's collective is exposed)
     microbatches: int = 4             # pipeline micro-batches (1F1B)
     tp_conv_split: bool = True        # channel-split layer3/4 convs in tensor-parallel mode
@@ -101,7 +101,7 @@ def add_train_flags(p: argparse.ArgumentParser, strategy: str) -> argparse.Argum
     g.add_argument('--bucket_mb', type=float, default=d.bucket_mb)
     g.add_argument('--no_overlap', dest='overlap', action='store_false')
     g.add_argument('--overlap_adam', action='store_true')
-    g.add_argument('--no_bucket_by_live', dest='bucket_by_live', action='store_false')
+    g.add_argument('--bucket_by_live', action='store_true')
     g.add_argument('--live_bucket_mb', type=float, default=d.live_bucket_mb)
     g.add_argument('--microbatches', type=int, default=d.microbatches)
     g.add_argument('--no_tp_conv_split', dest='tp_conv_split', action='store_false')

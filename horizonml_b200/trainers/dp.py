@@ -50,7 +50,7 @@ class DPEngine:
         self.model = build_model(cfg, dev)
         self.model.train()
         live = self.model.live_tap_masks(32) if (cfg.skip_dead_taps and hasattr(self.model, "live_tap_masks")) else None
-        by_live = live is not None and bool(cfg.bucket_by_live) and os.environ.get("HZ_BUCKET_LIVE", "1") != "0"
+        by_live = live is not None and (bool(cfg.bucket_by_live) or os.environ.get("HZ_BUCKET_LIVE", "0") == "1")
         self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype,
                                cfg.live_bucket_mb if by_live else cfg.bucket_mb, live_masks=live, bucket_by_live=by_live)
         if rt.world > 1:   # K1: make replicas identical (same seed already does; belt and braces)
@@ -104,6 +104,10 @@ class DPEngine:
     def step(self, images, labels) -> None:
         self._graphed(images, labels)
         self.global_step += 1
+
+    def input_buffers(self):
+        """Static (images, labels) buffers of the captured step, or None (eager mode / before capture)."""
+        return self._graphed.input_buffers()
 
     def allreduce_bytes_per_step(self) -> int:
         if self.ar is None:
