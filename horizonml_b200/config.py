@@ -53,6 +53,7 @@ class TrainConfig:
     resume: Optional[str] = None
     save_every: int = 0               # epochs; 0 = only at the end when save_dir is set
     profile: bool = False
+    region_probe: bool = True         # fill fwd_ms/bwd_ms/allreduce_ms/optimizer_ms/exposed_comm_ms once per run
     inject_fault: Optional[str] = None   # "rank:step" → that rank aborts at that global step
     heartbeat_dir: Optional[str] = None
     quiet: bool = False
@@ -117,6 +118,7 @@ def add_train_flags(p: argparse.ArgumentParser, strategy: str) -> argparse.Argum
     g.add_argument('--resume', default=None)
     g.add_argument('--save_every', type=int, default=0)
     g.add_argument('--profile', action='store_true')
+    g.add_argument('--no_region_probe', dest='region_probe', action='store_false')
     g.add_argument('--inject_fault', default=None, help='"rank:step" fault-injection test hook')
     g.add_argument('--heartbeat_dir', default=None)
     g.add_argument('--quiet', action='store_true')

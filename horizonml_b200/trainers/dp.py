@@ -105,6 +105,119 @@ class DPEngine:
         self._graphed(images, labels)
         self.global_step += 1
 
+    # ------------------------------------------------------------------------------------------
+    # device-timed breakdown of the step (SURVEY §5.1 / §5.5 extended columns)
+    # ------------------------------------------------------------------------------------------
+    def _state_tensors(self) -> List[torch.Tensor]:
+        ts = [self.flat.master, self.flat.grad, self.opt.m, self.opt.v, self.opt.step_t, self.stats.buf,
+              self.stats.has_prev]
+        if self.flat.shadow is not None:
+            ts.append(self.flat.shadow)
+        if self.prev_grad is not None:
+            ts += [self.prev_grad, self._diff_acc]
+        ts += [b for b in self.model.buffers()]
+        return ts
+
+    def probe_regions(self, images, labels, iters: int = 10) -> Dict[str, float]:
+        """{fwd_ms, bwd_ms, allreduce_ms, optimizer_ms, exposed_comm_ms, step_ms}: where one training step spends its
+        time.  The reference brackets regions with ``time.time()`` (data_parallel_train.py:103-124, with the Q8
+        caveat that its "comm_time" is backward+optimizer); here forward and backward (incl. the side-stream wgrads)
+        are replayed as two separate CUDA graphs and the bucket all-reduces / fused Adam are launched back to back,
+        every region bracketed by CUDA events and averaged over ``iters``; ``exposed_comm_ms`` is what the real
+        (single-graph, overlapped) step costs beyond forward+backward+optimizer.  Training state is snapshotted
+        before and restored after, so the probe does not perturb the run.  All ranks must call it together."""
+        dev = self.rt.device
+        cuda = dev.type == "cuda"
+        state = self._state_tensors()
+        snap = [t.clone() for t in state]
+        red = self.reducer
+        if red is not None:
+            red.enabled = False
+
+        def fwd(x, y):
+            ops.step_begin(dev)
+            self.flat.begin_step()
+            if x.dtype == torch.uint8:
+                x = ops.stem_prepare(x.permute(0, 3, 1, 2), dtype=self.rt.dtype)
+            return self.model.forward_loss(x, y)
+
+        def comm():
+            if self.ar is None:
+                return
+            for bk in self.flat.buckets:
+                self.ar.allreduce_avg_(self.flat.grad[bk.start:bk.end], live=self.flat.bucket_live[bk.index])
+
+        def clock():
+            if cuda:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                return e
+            return time.perf_counter()
+
+        def span(a, b) -> float:
+            return a.elapsed_time(b) if cuda else (b - a) * 1e3
+
+        out = {k: 0.0 for k in ("fwd_ms", "bwd_ms", "allreduce_ms", "optimizer_ms", "exposed_comm_ms", "step_ms")}
+        mb = None
+        graphed = cuda and self._graphed.graph is not None and tuple(images.shape) == self._graphed.shape
+        try:
+            if graphed:
+                from ..parallel.pp import GraphedMicroBatch
+                mb = GraphedMicroBatch(fwd, None, None, dev, True, True, label_shape=tuple(labels.shape),
+                                       image_like=images)
+                torch.cuda.synchronize()
+                mb.capture()
+                ops.step_end()
+                run_f = lambda: mb.run_fwd(images, labels)      # noqa: E731
+                run_b = lambda: mb.run_bwd(None)                # noqa: E731
+            else:
+                holder = {}
+
+                def run_f():
+                    holder["loss"] = fwd(images, labels)[0]
+
+                def run_b():
+                    holder.pop("loss").backward()
+                    ops.join_side()
+                    ops.step_end()
+            marks = []
+            for it in range(iters + 2):
+                row = [clock()]
+                run_f(); row.append(clock())
+                run_b(); row.append(clock())
+                comm(); row.append(clock())
+                self.opt.step(prev_grad=self.prev_grad); row.append(clock())
+                if it >= 2:
+                    marks.append(row)
+            step_marks = None
+            if graphed:
+                step_marks = [clock()]
+                for _ in range(iters):
+                    self._graphed.graph.replay()
+                step_marks.append(clock())
+            if cuda:
+                torch.cuda.synchronize()
+            n = float(len(marks))
+            for i, k in enumerate(("fwd_ms", "bwd_ms", "allreduce_ms", "optimizer_ms")):
+                out[k] = sum(span(r[i], r[i + 1]) for r in marks) / n
+            if step_marks is not None:
+                out["step_ms"] = span(step_marks[0], step_marks[1]) / iters
+                out["exposed_comm_ms"] = max(0.0, out["step_ms"] - out["fwd_ms"] - out["bwd_ms"] - out["optimizer_ms"])
+            else:
+                out["step_ms"] = sum(span(r[0], r[4]) for r in marks) / n
+                out["exposed_comm_ms"] = out["allreduce_ms"]        # nothing overlaps on the eager / CPU path
+        finally:
+            if cuda:
+                torch.cuda.synchronize()
+            mb = None
+            for t, s in zip(state, snap):
+                t.copy_(s)
+            self.flat.begin_step()
+            if red is not None:
+                red.enabled = True
+                red.begin_step()
+        return out
+
     def input_buffers(self):
         """Static (images, labels) buffers of the captured step, or None (eager mode / before capture)."""
         return self._graphed.input_buffers()
@@ -140,6 +253,8 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         print(f"Worker {rank} is starting training...", flush=True)
     cuda = rt.device.type == "cuda"
     df = None
+    probe_xy = None          # one full-size batch for the region probe
+    regions: Dict[str, float] = {}
     dev_idle = dev_stamps = None
     if cfg.step_barrier and world > 1 and hasattr(getattr(eng, "ar", None), "handle"):
         dev_stamps = torch.zeros(2, dtype=torch.int64, device=rt.device)
@@ -161,6 +276,8 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         for bi, (x, y) in enumerate(loader):
             if cfg.max_steps and bi >= cfg.max_steps:
                 break
+            if probe_xy is None or (x.shape[0] == cfg.batch_size and probe_xy[0].shape[0] != cfg.batch_size):
+                probe_xy = (x.clone(), y.clone())
             ts = time.time()
             rec.host.sample()
             fault.maybe_fail(eng.global_step)
@@ -207,6 +324,17 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
                "nvlink_GBps": (ar_bytes * nsteps / dev_s_max / 1e9) if dev_s_max > 0 else 0}
         if cuda:
             step_times = [dev_s / max(nsteps, 1)] * nsteps
+        if epoch == start_epoch and cfg.region_probe:
+            # every rank takes the same decision (the probe contains collectives)
+            have = allreduce_max_scalar(0.0 if probe_xy is not None else 1.0, rt.device) == 0.0
+            if have:
+                try:
+                    regions = eng.probe_regions(*probe_xy)
+                except Exception as e:  # noqa: BLE001 — a diagnostics feature must never take the run down
+                    if rank == 0:
+                        print(f"[probe] region breakdown unavailable: {e!r}", flush=True)
+                    regions = {}
+        ext.update({k: v for k, v in regions.items() if k != "step_ms"})
         rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times, ext=ext)
         if rank == 0 and not cfg.quiet:
             print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "

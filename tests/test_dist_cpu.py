@@ -48,6 +48,9 @@ def test_entrypoints_world2_cpu(tmp_path, runner, strategy, ws):
     assert os.path.exists(tmp_path / "combined_results_64.csv")
     last = df[df["worker"] == ws - 1]
     assert last["loss"].iloc[-1] < last["loss"].iloc[0]                # it trains
+    if strategy == "data":                                              # region probe fills the extended columns
+        assert (df["fwd_ms"] > 0).all() and (df["bwd_ms"] > 0).all() and (df["optimizer_ms"] > 0).all()
+        assert (df["allreduce_ms"] > 0).all()
     if strategy == "layer":                                             # non-last stages write 0 (reference)
         assert (df[df["worker"] == 0]["loss"] == 0).all()
         assert (df["avg_bandwidth"] > 0).any()
