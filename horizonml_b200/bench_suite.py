@@ -190,6 +190,44 @@ def _draw_all(plt, curves, bars, radar, out, written):  # pragma: no cover - nee
         save("overall_performance")
 
 
+def load_results(sample_sizes: Optional[List[int]] = None, logs_root: str = ".",
+                 logs_dirs: Optional[Dict[str, str]] = None) -> Dict[str, Dict[int, Optional[pd.DataFrame]]]:
+    """Re-read ``combined_results_{N}.csv`` files written by earlier runs (the offline analysis step the
+    reference README promises as ``analyze_results.py``, README.md:21, but never ships)."""
+    import glob
+    import re
+    dirs = {"data_parallel": "data_parallel_logs", "model_parallel": "model_parallel_logs",
+            "tensor_parallel": "tensor_parallel_logs"}
+    dirs.update(logs_dirs or {})
+    results: Dict[str, Dict[int, Optional[pd.DataFrame]]] = {s: {} for s in STRATEGIES}
+    for s in STRATEGIES:
+        d = os.path.join(logs_root, dirs[s])
+        found = {}
+        for f in glob.glob(os.path.join(d, "combined_results_*.csv")):
+            m = re.search(r"combined_results_(\d+)\.csv$", f)
+            if m:
+                found[int(m.group(1))] = f
+        for n in (sample_sizes or sorted(found)):
+            results[s][n] = pd.read_csv(found[n]) if n in found else None
+    return results
+
+
+def analyze_main(argv=None) -> int:
+    import argparse
+    p = argparse.ArgumentParser(description="Rebuild the comparison reports from existing training logs")
+    p.add_argument('--sample_sizes', type=int, nargs='*', default=None, help='default: every size found')
+    p.add_argument('--logs_root', default='.', help='directory holding data_/model_/tensor_parallel_logs')
+    p.add_argument('--output_dir', default='benchmark_results')
+    args = p.parse_args(argv)
+    results = load_results(args.sample_sizes, args.logs_root)
+    if not any(df is not None for per in results.values() for df in per.values()):
+        print(f"no combined_results_*.csv under {args.logs_root}")
+        return 1
+    written = generate_comparison_graphs(results, args.output_dir)
+    print(f"Analysis completed: {len(written)} artefacts in {args.output_dir}")
+    return 0
+
+
 def main(argv=None) -> int:
     import argparse
     from .config import add_train_flags, config_from_args

@@ -108,3 +108,10 @@ def test_main_benchmark_sweep_cpu(tmp_path):
     summ = __import__("json").load(open(tmp_path / "out" / "benchmark_summary.json"))
     assert {b["strategy"] for b in summ["bars"]} == {"data_parallel", "model_parallel", "tensor_parallel"}
     assert os.path.exists(tmp_path / "out" / "overall_performance_comparison.csv")
+    # analyze_results.py: the same reports rebuilt offline from the logs the sweep left behind
+    from horizonml_b200.bench_suite import analyze_main, load_results
+    again = load_results(None, str(tmp_path))
+    assert all(again[s][64] is not None and len(again[s][64]) == len(res[s][64]) for s in again)
+    assert analyze_main(["--logs_root", str(tmp_path), "--output_dir", str(tmp_path / "out2")]) == 0
+    s2 = __import__("json").load(open(tmp_path / "out2" / "benchmark_summary.json"))
+    assert {b["strategy"] for b in s2["bars"]} == {"data_parallel", "model_parallel", "tensor_parallel"}
