@@ -36,10 +36,14 @@ def one_f_one_b(stage: int, num_stages: int, num_micro: int) -> List[Tuple[str, 
 class P2P:
     """Static-shape activation/gradient exchange with the neighbouring stages."""
 
-    def __init__(self, stage: int, num_stages: int, group=None):
+    def __init__(self, stage: int, num_stages: int, group=None, peers=None):
+        """``peers`` = (global rank of the previous stage, of the next stage) when the pipeline is one row of a
+        process mesh (parallel/mesh.py); default: stage index == global rank."""
         self.stage, self.S, self.group = stage, num_stages, group
         self.prev = stage - 1 if stage > 0 else None
         self.next = stage + 1 if stage < num_stages - 1 else None
+        if peers is not None:
+            self.prev, self.next = peers
         self.bytes_sent = 0
         self._keep: List = []
 
@@ -97,13 +101,13 @@ class PipelineRunner:
     stage boundaries are tensors of ``in_shape(mb_size)`` / ``out_shape(mb_size)``."""
 
     def __init__(self, stage: int, num_stages: int, fwd_fn: Callable, in_shape: Callable,
-                 out_shape: Callable, dtype, device, group=None, bwd_fn: Optional[Callable] = None):
+                 out_shape: Callable, dtype, device, group=None, bwd_fn: Optional[Callable] = None, peers=None):
         self.bwd_fn = bwd_fn      # optional (i, dout) -> dx override (CUDA-graphed micro-batches)
         self.stage, self.S = stage, num_stages
         self.first, self.last = stage == 0, stage == num_stages - 1
         self.fwd_fn, self.in_shape, self.out_shape = fwd_fn, in_shape, out_shape
         self.dtype, self.device = dtype, device
-        self.p2p = P2P(stage, num_stages, group)
+        self.p2p = P2P(stage, num_stages, group, peers)
         self.trace: List[Tuple[str, int]] = []
 
     def _like_in(self, n):

@@ -29,9 +29,14 @@ from .common import (DeviceStats, FaultInjector, Heartbeat, Runtime, allreduce_m
 
 
 class PPEngine:
-    def __init__(self, cfg: TrainConfig, rt: Runtime):
-        self.cfg, self.rt = cfg, rt
-        S, s = rt.world, rt.rank
+    """One pipeline stage.  With a ``mesh`` (parallel/mesh.py) the pipeline is one row of a DP × PP process mesh:
+    stage index / neighbours come from the mesh and the stage's gradients are averaged over its data-parallel
+    group (fused peer all-reduce on GPUs) between the 1F1B schedule and the optimizer pass."""
+
+    def __init__(self, cfg: TrainConfig, rt: Runtime, mesh=None):
+        self.cfg, self.rt, self.mesh = cfg, rt, mesh
+        S, s = (mesh.pp, mesh.coord.pp) if mesh is not None else (rt.world, rt.rank)
+        self.S, self.s = S, s
         self.first_blk, self.last_blk = partition_blocks(S)[s]
         self.is_first, self.is_last = s == 0, s == S - 1
         full = resnet18(cfg.num_classes, seed=cfg.seed)     # identical init on every stage (seeded)
@@ -59,7 +64,12 @@ class PPEngine:
             s, S, self._fwd,
             in_shape=lambda n: boundary_shape(self.first_blk - 1, n, hw),
             out_shape=lambda n: boundary_shape(self.last_blk, n, hw),
-            dtype=rt.dtype, device=rt.device)
+            dtype=rt.dtype, device=rt.device, peers=mesh.pp_neighbours() if mesh is not None else None)
+        self.dp_ar = None
+        if mesh is not None and mesh.dp > 1:
+            from ..parallel.comm import make_grad_allreduce
+            kind = cfg.allreduce if cfg.allreduce not in ("auto", "nvls") else "twoshot"
+            self.dp_ar = make_grad_allreduce(kind, self.flat.total, rt.device, group=mesh.dp_group)
         self.global_step = 0
         # CUDA-graphed micro-batches (GPU + native kernels): built lazily after one eager step
         self.use_graphs = cfg.cuda_graph and rt.device.type == "cuda" and rt.backend == "native"
@@ -89,7 +99,7 @@ class PPEngine:
 
     def _build_slots(self, sizes, images):
         from ..ops import native_backend as nb
-        S, s = self.rt.world, self.rt.rank
+        S, s = self.S, self.s
         n = sizes[0]
         self._graph_frac = 1.0 / len(sizes)
         nslots = max(1, min(S - s, len(sizes)))
@@ -142,6 +152,9 @@ class PPEngine:
             self.runner.fwd_fn, self.runner.bwd_fn = self._fwd, None
         loss, correct = self.runner.run(sizes, imgs)
         ops.join_side()
+        if self.dp_ar is not None:                   # hybrid DP × PP: average this stage's gradients over its replicas
+            for bk in self.flat.buckets:
+                self.dp_ar.allreduce_avg_(self.flat.grad[bk.start:bk.end], live=self.flat.bucket_live[bk.index])
         diff = self.opt.step(prev_grad=self.prev_grad)
         sent = self.runner.p2p.end_step()
         ops.step_end()
@@ -160,13 +173,26 @@ def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
     if rank == 0 and not cfg.quiet:
         print("Worker 0 generated the synthetic dataset." if cfg.synthetic else
               "Worker 0 downloaded the dataset.", flush=True)
-    # every stage iterates the same (seeded, unshuffled) subset — layer_…:103-131
-    loader = BatchLoader(images, labels, cfg.batch_size, rt.device, sampler=None)
-    eng = PPEngine(cfg, rt)
+    mesh = None
+    if cfg.dp_replicas > 1:
+        from ..parallel.mesh import DeviceMesh
+        if world % cfg.dp_replicas:
+            raise ValueError(f"--dp_replicas {cfg.dp_replicas} does not divide world_size {world}")
+        mesh = DeviceMesh(world, rank, dp=cfg.dp_replicas, pp=world // cfg.dp_replicas)
+    # every stage iterates the same (seeded, unshuffled) subset — layer_…:103-131; replicas of a DP × PP mesh
+    # take disjoint shards of it
+    sampler = None
+    if mesh is not None:
+        from ..data import ShardedSampler
+        sampler = ShardedSampler(len(labels), mesh.dp, mesh.coord.dp, shuffle=False, seed=cfg.seed)
+    loader = BatchLoader(images, labels, cfg.batch_size, rt.device, sampler=sampler)
+    eng = PPEngine(cfg, rt, mesh)
+    stages = mesh.pp if mesh is not None else world
     rec = EpochRecorder("layer", rank, logs_dir, cfg.sample_size)
     hb = Heartbeat(cfg.heartbeat_dir, rank)
     fault = FaultInjector(cfg.inject_fault, rank)
-    tag = f"pp_stage{rank}of{world}"
+    tag = f"pp_stage{eng.s}of{stages}"
+    saver = mesh is None or mesh.coord.dp == 0          # replicas hold identical state: one copy per stage
     start_epoch = 0
     if cfg.resume:
         payload = checkpoint.load(cfg.resume, tag, eng.model, eng.opt)
@@ -219,6 +245,8 @@ def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         dev_s_max = allreduce_max_scalar(dev_s, rt.device)
         n_img = nsteps * cfg.batch_size if nsteps else 0
         n_img = min(n_img, len(labels)) if not cfg.max_steps else n_img
+        if mesh is not None:
+            n_img = min(nsteps * cfg.batch_size * mesh.dp, len(labels)) if not cfg.max_steps else n_img * mesh.dp
         ext = {"images_per_sec": n_img / dev_s_max if dev_s_max > 0 else 0, "steps": nsteps,
                "gpu_mem_MB": gpu_mem_mb(rt.device),
                "nvlink_GBps": sent_total / dev_s_max / 1e9 if dev_s_max > 0 else 0}
@@ -226,17 +254,18 @@ def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
             step_times = [dev_s / steps] * nsteps
         rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times,
                       avg_bandwidth=sent_total / steps, ext=ext)
-        if eng.is_last and not cfg.quiet:
+        if eng.is_last and saver and not cfg.quiet:
             print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "
                   f"Time: {epoch_time:.2f}s", flush=True)
-        if cfg.save_dir and ((cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
+        if cfg.save_dir and saver and ((cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
             checkpoint.save(cfg.save_dir, tag, eng.model, eng.opt, epoch + 1, eng.global_step)
         if world > 1:
             dist.barrier()
-    if eng.is_last:
+    if eng.is_last and saver:
         write_summary(logs_dir, f"summary_{cfg.sample_size}.json", {
             "strategy": "layer", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
-            "microbatches": cfg.microbatches, "partition": partition_blocks(world),
+            "microbatches": cfg.microbatches, "partition": partition_blocks(stages),
+            "mesh": mesh.describe() if mesh is not None else None,
             "final": rec.rows[-1] if rec.rows else None})
     from ..launch import shutdown_distributed
     shutdown_distributed()

@@ -28,13 +28,19 @@ from .common import (DeviceStats, FaultInjector, GraphedStep, Heartbeat, Runtime
 
 
 class TPEngine:
-    def __init__(self, cfg: TrainConfig, rt: Runtime):
-        self.cfg, self.rt = cfg, rt
+    """Tensor-parallel engine.  With a ``mesh`` (parallel/mesh.py) the tensor-parallel group is one row of a
+    DP × TP process mesh: TP collectives run on ``mesh.tp_group``, replicated-parameter gradients are averaged over
+    the whole world (identical inside a TP group, different across replicas) and sharded-parameter gradients over
+    the rank's data-parallel group."""
+
+    def __init__(self, cfg: TrainConfig, rt: Runtime, mesh=None):
+        self.cfg, self.rt, self.mesh = cfg, rt, mesh
         fused = None
-        if rt.device.type == "cuda" and rt.backend == "native" and rt.world > 1 and cfg.tp_conv_split:
+        if (mesh is None and rt.device.type == "cuda" and rt.backend == "native" and rt.world > 1
+                and cfg.tp_conv_split):
             from ..parallel.tp import FusedTP
-            fused = FusedTP(rt.device)
-        self.comm = TPComm(fused=fused)
+            fused = FusedTP(rt.device)        # symmetric heap spans the WORLD group: single-row meshes only
+        self.comm = TPComm(group=mesh.tp_group if mesh is not None else None, fused=fused)
         dense = resnet18(cfg.num_classes, seed=cfg.seed)
         self.model = TensorParallelResNet(dense, self.comm, cfg.tp_conv_split).to(rt.device)
         self.model.train()
@@ -45,6 +51,10 @@ class TPEngine:
         self.opt_shd = FlatAdam(self.flat_shd, lr=cfg.lr)
         self.ar = make_grad_allreduce(cfg.allreduce, self.flat_rep.total, rt.device) if rt.world > 1 else None
         self.reducer = GradReducer(self.flat_rep, self.ar, cfg.overlap) if self.ar is not None else None
+        self.ar_shd = None
+        if mesh is not None and mesh.dp > 1:
+            kind = cfg.allreduce if cfg.allreduce not in ("auto", "nvls") else "twoshot"
+            self.ar_shd = make_grad_allreduce(kind, self.flat_shd.total, rt.device, group=mesh.dp_group)
         self.stats = DeviceStats(rt.device)
         self.prev_grad = torch.zeros_like(self.flat_rep.grad) if cfg.grad_divergence else None
         # collectives inside the step (NCCL all-gather/all-reduce) are graph-capturable on CUDA
@@ -64,6 +74,9 @@ class TPEngine:
         ops.join_side()
         if self.reducer is not None:
             self.reducer.finish()
+        if self.ar_shd is not None:
+            for bk in self.flat_shd.buckets:
+                self.ar_shd.allreduce_avg_(self.flat_shd.grad[bk.start:bk.end])
         diff = self.opt_rep.step(prev_grad=self.prev_grad)
         self.opt_shd.step()
         self.stats.add_step(loss, correct, labels.shape[0], diff)
@@ -85,12 +98,23 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
     if rank == 0 and not cfg.quiet:
         print("Worker 0 generated the synthetic dataset." if cfg.synthetic else
               "Worker 0 downloaded the dataset.", flush=True)
-    loader = BatchLoader(images, labels, cfg.batch_size, rt.device, sampler=None)   # all ranks: same data
-    eng = TPEngine(cfg, rt)
+    mesh = None
+    if cfg.dp_replicas > 1:
+        from ..parallel.mesh import DeviceMesh
+        if world % cfg.dp_replicas:
+            raise ValueError(f"--dp_replicas {cfg.dp_replicas} does not divide world_size {world}")
+        mesh = DeviceMesh(world, rank, dp=cfg.dp_replicas, tp=world // cfg.dp_replicas)
+    sampler = None                       # all ranks of a TP group: same data (tensor_…:143); replicas: disjoint shards
+    if mesh is not None:
+        from ..data import ShardedSampler
+        sampler = ShardedSampler(len(labels), mesh.dp, mesh.coord.dp, shuffle=False, seed=cfg.seed)
+    loader = BatchLoader(images, labels, cfg.batch_size, rt.device, sampler=sampler)
+    eng = TPEngine(cfg, rt, mesh)
     rec = EpochRecorder("tensor", rank, logs_dir, cfg.sample_size)
     hb = Heartbeat(cfg.heartbeat_dir, rank)
     fault = FaultInjector(cfg.inject_fault, rank)
-    tag = f"tp_rank{rank}of{world}"
+    tag = f"tp_rank{rank}of{world}" if mesh is None else f"tp_rank{mesh.coord.tp}of{mesh.tp}"
+    saver = mesh is None or mesh.coord.dp == 0
     start_epoch = 0
     if cfg.resume:
         payload = checkpoint.load(cfg.resume, tag, eng.model, None)
@@ -150,7 +174,8 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         rec.total_comm += dev_s * 2.0 / 3.0
         dev_s_max = allreduce_max_scalar(dev_s, rt.device)
         bytes_per_step = eng.bytes_per_step() + (tp_bytes / steps if eng._graphed.graph is None else 0)
-        ext = {"images_per_sec": s["seen"] / dev_s_max if dev_s_max > 0 else 0, "steps": nsteps,
+        seen = s["seen"] * (mesh.dp if mesh is not None else 1)
+        ext = {"images_per_sec": seen / dev_s_max if dev_s_max > 0 else 0, "steps": nsteps,
                "gpu_mem_MB": gpu_mem_mb(rt.device),
                "nvlink_GBps": bytes_per_step * nsteps / dev_s_max / 1e9 if dev_s_max > 0 else 0}
         if cuda:
@@ -159,7 +184,7 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         if not cfg.quiet:   # the reference prints the epoch line on every rank (tensor_…:264)
             print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "
                   f"Time: {epoch_time:.2f}s", flush=True)
-        if cfg.save_dir and ((cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
+        if cfg.save_dir and saver and ((cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
             checkpoint.save(cfg.save_dir, tag, eng.model, None, epoch + 1, eng.global_step,
                             extra={"opt_rep": eng.opt_rep.state_dict(), "opt_shd": eng.opt_shd.state_dict()})
         if world > 1:
@@ -167,7 +192,7 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
     if rank == 0:
         write_summary(logs_dir, f"summary_{cfg.sample_size}.json", {
             "strategy": "tensor", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
-            "conv_split": eng.model.conv_split, "final": rec.rows[-1] if rec.rows else None})
+            "conv_split": eng.model.conv_split, "mesh": mesh.describe() if mesh is not None else None, "final": rec.rows[-1] if rec.rows else None})
     # a captured graph that contains NCCL kernels must be gone before the communicator is torn down
     eng._graphed.graph = None
     if cuda:

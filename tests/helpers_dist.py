@@ -118,6 +118,95 @@ def pp_equivalence(rank, world, out_dir):
         assert abs(s["loss_sum"] - tot) < 1e-4
 
 
+def hybrid_dp_pp_equivalence(rank, world, out_dir):
+    """DP(2) x PP(world/2) process mesh: every stage's gradients == mean over replicas of the single-process
+    micro-batched gradient on that replica's batch."""
+    from horizonml_b200 import ops
+    from horizonml_b200.config import TrainConfig
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.pp import PPEngine
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.resnet import resnet18
+    from horizonml_b200.parallel.mesh import DeviceMesh
+    from horizonml_b200.parallel.pp import one_f_one_b
+    ops.set_backend("torch")
+    M, dp = 4, 2
+    mesh = DeviceMesh(world, rank, dp=dp, pp=world // dp)
+    assert mesh.rank_of(mesh.coord.dp, mesh.coord.pp, 0) == rank
+    assert sorted(mesh.dp_ranks() + mesh.pp_ranks()).count(rank) == 2
+    cfg = TrainConfig(strategy="layer", world_size=world, microbatches=M, seed=11, lr=0.0, grad_divergence=False,
+                      dp_replicas=dp)
+    rt = Runtime(rank, world, torch.device("cpu"), torch.float32, "torch", "gloo")
+    eng = PPEngine(cfg, rt, mesh)
+    batches = [_batch(16, seed=3 + d) for d in range(dp)]
+    x, y = batches[mesh.coord.dp]
+    eng.opt.step = lambda **kw: None
+    eng.step(x, y)
+    assert eng.runner.trace == one_f_one_b(mesh.coord.pp, mesh.pp, M)
+    ref = None
+    for xb, yb in batches:
+        m = resnet18(10, seed=11).train()
+        flat = FlatParams(list(m.named_parameters()), "cpu", torch.float32)
+        flat.begin_step()
+        for xs, ys in zip(xb.split(4), yb.split(4)):
+            m.forward_loss(xs.contiguous(memory_format=torch.channels_last), ys, loss_scale=0.25)[0].backward()
+        g = {n: p.main_grad.clone() / dp for n, p in m.named_parameters()}
+        ref = g if ref is None else {n: ref[n] + g[n] for n in g}
+    for n, p in zip(eng.flat.names, eng.flat.params):
+        assert torch.allclose(p.main_grad, ref[n], atol=2e-5), (n, (p.main_grad - ref[n]).abs().max())
+
+
+def hybrid_dp_tp_equivalence(rank, world, out_dir):
+    """DP(2) x TP(world/2) mesh through TPEngine: replicated + sharded gradients == mean over replicas of the
+    dense model's gradient on that replica's batch."""
+    from horizonml_b200 import ops
+    from horizonml_b200.config import TrainConfig
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.tp import TPEngine
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.resnet import resnet18
+    from horizonml_b200.parallel.mesh import DeviceMesh
+    from horizonml_b200.parallel.tp import shard_range, padded_classes
+    ops.set_backend("torch")
+    dp = 2
+    mesh = DeviceMesh(world, rank, dp=dp, tp=world // dp)
+    cfg = TrainConfig(strategy="tensor", world_size=world, seed=21, lr=0.0, grad_divergence=False, dp_replicas=dp,
+                      cuda_graph=False)
+    rt = Runtime(rank, world, torch.device("cpu"), torch.float32, "torch", "gloo")
+    eng = TPEngine(cfg, rt, mesh)
+    assert eng.comm.world == mesh.tp and eng.comm.rank == mesh.coord.tp
+    batches = [_batch(8, seed=4 + d) for d in range(dp)]
+    eng.opt_rep.step = lambda **kw: None
+    eng.opt_shd.step = lambda **kw: None
+    x, y = batches[mesh.coord.dp]
+    eng.step(x, y)
+    ref = None
+    for xb, yb in batches:
+        dense = resnet18(10, seed=21).train()
+        FlatParams(list(dense.named_parameters()), "cpu", torch.float32)
+        dense.forward_loss(xb, yb)[0].backward()
+        g = {n: p.main_grad.clone() / dp for n, p in dense.named_parameters()}
+        ref = g if ref is None else {n: ref[n] + g[n] for n in g}
+    got = dict(eng.model.named_parameters())
+    tpw, tpr = mesh.tp, mesh.coord.tp
+    kpad = padded_classes(10, tpw)
+    lo, hi = shard_range(kpad, tpw, tpr)
+    wref = torch.zeros(kpad, 512); wref[:10] = ref["fc.weight"]
+    assert torch.allclose(got["fc_weight"].main_grad, wref[lo:hi], atol=2e-5)
+    n_rep = 0
+    for n, p in got.items():
+        dn = n[len("backbone."):] if n.startswith("backbone.") else n
+        if not getattr(p, "tp_sharded", False) and dn in ref:
+            assert torch.allclose(p.main_grad, ref[dn], atol=2e-5), (n, (p.main_grad - ref[dn]).abs().max())
+            n_rep += 1
+    assert n_rep > 20
+    # a sharded conv (layer4 conv1 is column-parallel: this rank's Cout slice of the dense gradient)
+    clo, chi = shard_range(512, tpw, tpr)
+    w = got["backbone.layer4.1.conv1.weight"]
+    if getattr(w, "tp_sharded", False):
+        assert torch.allclose(w.main_grad, ref["layer4.1.conv1.weight"][clo:chi], atol=2e-5)
+
+
 def tp_equivalence(rank, world, out_dir):
     """TP(W) (column-parallel classifier + channel-parallel layer3/4) == dense model."""
     from horizonml_b200 import ops

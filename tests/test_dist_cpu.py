@@ -26,6 +26,14 @@ def test_pp_1f1b_equivalence_gloo(tmp_path):
     run("pp_equivalence", 3, find_free_port(), str(tmp_path))
 
 
+def test_hybrid_dp_pp_mesh_equivalence_gloo(tmp_path):
+    run("hybrid_dp_pp_equivalence", 4, find_free_port(), str(tmp_path))
+
+
+def test_hybrid_dp_tp_mesh_equivalence_gloo(tmp_path):
+    run("hybrid_dp_tp_equivalence", 4, find_free_port(), str(tmp_path))
+
+
 def test_tp_equivalence_gloo(tmp_path):
     run("tp_equivalence", 2, find_free_port(), str(tmp_path))
 
@@ -54,6 +62,25 @@ def test_entrypoints_world2_cpu(tmp_path, runner, strategy, ws):
     if strategy == "layer":                                             # non-last stages write 0 (reference)
         assert (df[df["worker"] == 0]["loss"] == 0).all()
         assert (df["avg_bandwidth"] > 0).any()
+
+
+@pytest.mark.parametrize("inner", ["layer", "tensor"])
+def test_hybrid_entrypoint_world4_cpu(tmp_path, inner):
+    """hybrid_parallel_train.py: 2 replicas x (2-stage pipeline | TP-2 group) on a 4-process gloo mesh."""
+    import hybrid_parallel_train as hp
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        rc = hp.main(["--world_size", "4", "--dp_replicas", "2", "--inner", inner, "--epochs", "2",
+                      "--sample_size", "64", "--device", "cpu", "--batch_size", "16", "--quiet",
+                      "--logs_dir", str(tmp_path / "logs")])
+    finally:
+        os.chdir(cwd)
+    assert rc == 0
+    df = pd.read_csv(tmp_path / "logs" / "combined_results_64.csv")
+    assert sorted(df["worker"].unique()) == [0, 1, 2, 3] and df["epoch"].max() == 2
+    last = df[df["worker"] == 3]
+    assert last["loss"].iloc[-1] < last["loss"].iloc[0]
 
 
 def test_fault_injection_tears_job_down(tmp_path):
