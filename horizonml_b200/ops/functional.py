@@ -288,6 +288,7 @@ class _HeadLoss(torch.autograd.Function):
             stats_out["correct"] = correct
             stats_out["logits"] = logits
         ctx.mark_non_differentiable(correct)
+        ctx.set_materialize_grads(False)          # no zero-fill kernel for the (unused) gradient of ``correct``
         return loss, correct
 
     @staticmethod
@@ -306,6 +307,23 @@ def head_loss(feat, fc_w, fc_b, labels, loss_scale: float = 1.0, n_valid: Option
     """Returns (loss, correct_count).  ``loss.backward()`` must be seeded with 1 (the default)."""
     n_valid = fc_w.shape[0] if n_valid is None else n_valid
     return _HeadLoss.apply(feat, fc_w, fc_b, labels, float(loss_scale), int(n_valid), stats_out)
+
+
+_ROOT_GRAD = {}
+
+
+def backward(loss: torch.Tensor) -> None:
+    """``loss.backward()`` seeded with a cached constant 1 — autograd's default root gradient is a fresh
+    ``ones_like`` (a fill kernel on the critical path of every step, and not a PDL-aware one)."""
+    key = (loss.device, loss.dtype, tuple(loss.shape))
+    one = _ROOT_GRAD.get(key)
+    if one is None:
+        if loss.is_cuda and torch.cuda.is_current_stream_capturing():
+            loss.backward()               # never allocate the cache inside a capture (private pool memory)
+            return
+        one = torch.ones(loss.shape, dtype=loss.dtype, device=loss.device)
+        _ROOT_GRAD[key] = one
+    torch.autograd.backward(loss, grad_tensors=one)
 
 
 def head_logits(feat, fc_w, fc_b):

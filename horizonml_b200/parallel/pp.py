@@ -150,7 +150,8 @@ class PipelineRunner:
                 inputs[i] = outputs[i] = None
                 return dx
             if self.last:
-                out[0].backward()
+                from ..ops import backward as _bw
+                _bw(out[0])
             else:
                 torch.autograd.backward(out, dout)
             self.trace.append(("B", i))
@@ -216,7 +217,7 @@ class GraphedMicroBatch:
             loss, correct = self.out
             self.dy = None
             with torch.cuda.graph(self.gb, pool=self.pool):
-                loss.backward()
+                ops.backward(loss)
                 ops.join_side()
         else:
             self.dy = torch.zeros_like(self.out)

@@ -222,6 +222,7 @@ class _TPHeadLoss(torch.autograd.Function):
         ctx.save_for_backward(dfeat if dfeat is not None else torch.empty(0))
         ctx.has = dfeat is not None
         ctx.mark_non_differentiable(correct)
+        ctx.set_materialize_grads(False)
         return loss, correct
 
     @staticmethod

@@ -90,7 +90,7 @@ class DPEngine:
         if self.reducer is not None:
             self.reducer.begin_step()
         loss, correct = self.model.forward_loss(x, labels)
-        loss.backward()
+        ops.backward(loss)
         ops.join_side()
         if self.reducer is not None:
             self.reducer.finish()

@@ -70,7 +70,7 @@ class TPEngine:
         if self.reducer is not None:
             self.reducer.begin_step()
         loss, correct = self.model.forward_loss(x, labels)
-        loss.backward()
+        ops.backward(loss)
         ops.join_side()
         if self.reducer is not None:
             self.reducer.finish()
