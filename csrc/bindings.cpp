@@ -129,6 +129,26 @@ Tensor im2col_small(const Tensor& x, int64_t R, int64_t stride, int64_t pad, int
   return A;
 }
 
+// stem: (im2col matrix [N*Ho*Wo, Kp], zero-padded weights [Cout, Kp]) from one launch
+std::vector<Tensor> stem_pack(const Tensor& x, const Tensor& w2d, int64_t R, int64_t stride, int64_t pad, int64_t Kp) {
+  check_cl(x, "x");
+  TORCH_CHECK(w2d.is_cuda() && w2d.scalar_type() == at::kBFloat16 && w2d.dim() == 2 && w2d.is_contiguous());
+  c10::cuda::CUDAGuard g(x.device());
+  auto d = dims_of(x);
+  const int Ho = (d.H + 2 * pad - R) / stride + 1, Wo = (d.W + 2 * pad - R) / stride + 1;
+  Tensor A = at::empty({(int64_t)d.N * Ho * Wo, Kp}, x.options());
+  Tensor wp = at::empty({w2d.size(0), Kp}, w2d.options());
+  TORCH_CHECK(w2d.size(1) == d.C * R * R, "stem_pack: weight rows must be R*R*Cin long");
+  int rc = hz_stem_pack(cptr(x), A.data_ptr(), cptr(w2d), wp.data_ptr(), d.N, d.H, d.W, d.C, (int)R, (int)stride,
+                        (int)pad, Ho, Wo, (int)Kp, (int)w2d.size(0), cur_stream());
+  if (rc != 0) {   // shapes the fused kernel does not cover: the two generic kernels
+    hz_im2col_small(cptr(x), A.data_ptr(), d.N, d.H, d.W, d.C, (int)R, (int)R, (int)stride, (int)pad, Ho, Wo, (int)Kp,
+                    cur_stream());
+    hz_pad_rows(cptr(w2d), wp.data_ptr(), (int)w2d.size(0), (int)w2d.size(1), (int)Kp, cur_stream());
+  }
+  return {A, wp};
+}
+
 Tensor pad_rows(const Tensor& w2d, int64_t Kp) {
   TORCH_CHECK(w2d.is_cuda() && w2d.scalar_type() == at::kBFloat16 && w2d.dim() == 2 && w2d.is_contiguous());
   c10::cuda::CUDAGuard g(w2d.device());
@@ -213,9 +233,54 @@ std::vector<Tensor> conv_fwd(const Tensor& x, const Tensor& w, int64_t stride, i
   if (pre) stats = *zeroed_stats;
   else if (want_stats) stats = at::empty({2, Cout}, x.options().dtype(at::kFloat));
   int rc = hz_conv_fwd(cptr(x), cptr(w), y.data_ptr(), want_stats ? stats.data_ptr<float>() : nullptr, pre ? 1 : 0,
-                       d.N, d.H, d.W, d.C, Cout, R, (int)stride, (int)pad, weights_stable ? 1 : 0, cur_stream());
+                       d.N, d.H, d.W, d.C, Cout, R, (int)stride, (int)pad, weights_stable ? 1 : 0, nullptr, cur_stream());
   TORCH_CHECK(rc == 0, "hz_conv_fwd failed rc=", rc);
   return {y, stats};
+}
+
+// conv -> BatchNorm(batch statistics) -> (+residual) -> (ReLU) in ONE kernel (device-wide barrier inside the conv
+// epilogue).  `scratch`: pre-zeroed fp32 slice of >= 2*Cout + 32 elements ([Σy | Σy² | barrier counter]).
+// Returns {y_raw, out, mean, invstd}; when the grid would exceed the SM count (no co-residency) the unfused pair of
+// kernels runs instead — same results either way.
+std::vector<Tensor> conv_bn_act_fwd(const Tensor& x, const Tensor& w, int64_t stride, int64_t pad, Tensor scratch,
+                                    const Tensor& gamma, const Tensor& beta, const c10::optional<Tensor>& rmean,
+                                    const c10::optional<Tensor>& rvar, double momentum, double eps,
+                                    const c10::optional<Tensor>& residual, bool relu, bool weights_stable) {
+  check_cl(x, "x"); check_cl(w, "w");
+  c10::cuda::CUDAGuard g(x.device());
+  auto d = dims_of(x);
+  const int Cout = (int)w.size(0), R = (int)w.size(2);
+  const int Ho = (d.H + 2 * pad - R) / stride + 1, Wo = (d.W + 2 * pad - R) / stride + 1;
+  TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.numel() >= 2 * Cout + 32 && scratch.is_contiguous());
+  Tensor y = empty_cl(x, d.N, Cout, Ho, Wo);
+  Tensor out = at::empty_like(y);
+  Tensor mean = at::empty({Cout}, x.options().dtype(at::kFloat));
+  Tensor invstd = at::empty({Cout}, x.options().dtype(at::kFloat));
+  const void* res = nullptr;
+  if (residual.has_value() && residual->defined()) {
+    check_cl(*residual, "residual");
+    TORCH_CHECK(residual->sizes() == y.sizes(), "residual shape mismatch");
+    res = residual->data_ptr();
+  }
+  HzBnFuse bn;
+  bn.gamma = gamma.data_ptr<float>(); bn.beta = beta.data_ptr<float>();
+  bn.mean = mean.data_ptr<float>(); bn.invstd = invstd.data_ptr<float>();
+  bn.rmean = fptr(rmean); bn.rvar = fptr(rvar);
+  bn.residual = res; bn.out = out.data_ptr();
+  bn.counter = reinterpret_cast<unsigned*>(scratch.data_ptr<float>() + 2 * Cout);
+  bn.eps = (float)eps; bn.momentum = (float)momentum; bn.relu = relu ? 1 : 0;
+  int rc = hz_conv_fwd(cptr(x), cptr(w), y.data_ptr(), scratch.data_ptr<float>(), 1, d.N, d.H, d.W, d.C, Cout, R,
+                       (int)stride, (int)pad, weights_stable ? 1 : 0, &bn, cur_stream());
+  if (rc == -20) {
+    rc = hz_conv_fwd(cptr(x), cptr(w), y.data_ptr(), scratch.data_ptr<float>(), 1, d.N, d.H, d.W, d.C, Cout, R,
+                     (int)stride, (int)pad, weights_stable ? 1 : 0, nullptr, cur_stream());
+    TORCH_CHECK(rc == 0, "hz_conv_fwd failed rc=", rc);
+    hz_bn_act_fwd(y.data_ptr(), scratch.data_ptr<float>(), bn.gamma, bn.beta, res, out.data_ptr(), bn.mean, bn.invstd,
+                  bn.rmean, bn.rvar, d.N * Ho * Wo, Cout, (float)eps, (float)momentum, relu ? 1 : 0, 1, cur_stream());
+    return {y, out, mean, invstd};
+  }
+  TORCH_CHECK(rc == 0, "hz_conv_fwd (fused BN) failed rc=", rc);
+  return {y, out, mean, invstd};
 }
 
 // addend (optional, same shape/layout as dx): dx = dgrad(dy, w) + addend, fused into the epilogue
@@ -356,6 +421,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("u8_normalize", &u8_normalize);
   m.def("im2col_small", &im2col_small);
   m.def("pad_rows", &pad_rows);
+  m.def("conv_bn_act_fwd", &conv_bn_act_fwd);
+  m.def("stem_pack", &stem_pack);
   m.def("head_fwd_bwd", &head_fwd_bwd);
   m.def("adam_step", &adam_step);
   m.def("grad_diff_sq", &grad_diff_sq);

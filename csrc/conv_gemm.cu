@@ -51,7 +51,23 @@ struct IgemmParams {
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;   // optional, same layout as out: out = tile + addend (residual-gradient fusion)
   float* stats;              // [2*ncols] or null
+  // ---- fused BatchNorm(batch stats) + residual + ReLU (forward): after the tile's Σy, Σy² are in `stats`, a
+  //      device-wide barrier makes the totals final and the CTA normalises the tile it still holds in shared memory
+  __nv_bfloat16* bn_out;         // null = no fusion
+  const __nv_bfloat16* bn_residual;
+  const float* bn_gamma; const float* bn_beta;
+  float* bn_mean; float* bn_invstd;      // saved for backward
+  float* bn_rmean; float* bn_rvar;       // running statistics (may be null)
+  unsigned* bn_counter;          // zero before the launch
+  float bn_inv_count, bn_unbias, bn_eps, bn_momentum;
+  int bn_relu;
 };
+
+HZ_DEVINL unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 template <int BLOCK_N, bool B_MN>
 __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMaps amaps,
@@ -181,12 +197,13 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   // residual-gradient fusion: the addend rows this thread will write are requested now, so their L2 latency
   // hides under the MMA tail instead of serialising with the stores
   bf16x8 addv[kPasses];
-  if (p.addend != nullptr) {
+  const __nv_bfloat16* pre = p.addend != nullptr ? p.addend : p.bn_residual;      // (never both: dgrad vs forward)
+  if (pre != nullptr) {
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
       const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
       const long long off = r0 < row_hi ? out_offset(r0) : -1;
-      if (off >= 0) addv[i] = ld8(p.addend + off);
+      if (off >= 0) addv[i] = ld8(pre + off);
     }
   }
   if (k_iters > 0) {
@@ -336,6 +353,63 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       }
       atomicAdd(&p.stats[nt * BLOCK_N + col], s);
       atomicAdd(&p.stats[p.ncols + nt * BLOCK_N + col], q);
+    }
+  }
+  if (p.bn_out != nullptr) {
+    // ---- fused BN + residual + ReLU.  grid <= #SMs (host-checked) and 1 CTA/SM: all CTAs are co-resident, the
+    //      barrier cannot deadlock; PDL dependents are only scheduled once every CTA of this grid has started.
+    __shared__ float bn_scale[BLOCK_N], bn_shift[BLOCK_N];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(p.bn_counter, 1u);
+      const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+      const long long t0 = clock64();
+      while (ld_acquire_gpu_u32(p.bn_counter) < total) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < BLOCK_N) {
+      const int c = nt * BLOCK_N + threadIdx.x;
+      const float mu = __ldcg(&p.stats[c]) * p.bn_inv_count;
+      const float var = fmaxf(__ldcg(&p.stats[p.ncols + c]) * p.bn_inv_count - mu * mu, 0.f);
+      const float is = rsqrtf(var + p.bn_eps);
+      const float g = p.bn_gamma[c];
+      bn_scale[threadIdx.x] = g * is;
+      bn_shift[threadIdx.x] = p.bn_beta[c] - mu * g * is;
+      if (mt == 0 && blockIdx.z == 0) {            // one CTA per channel block publishes the statistics
+        p.bn_mean[c] = mu;
+        p.bn_invstd[c] = is;
+        if (p.bn_rmean != nullptr) {
+          p.bn_rmean[c] = (1.f - p.bn_momentum) * p.bn_rmean[c] + p.bn_momentum * mu;
+          p.bn_rvar[c] = (1.f - p.bn_momentum) * p.bn_rvar[c] + p.bn_momentum * var * p.bn_unbias;
+        }
+      }
+    }
+    __syncthreads();
+    const int vec = threadIdx.x % kVecPerRow;
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
+      if (r0 >= row_hi) break;
+      const long long off = out_offset(r0);
+      if (off < 0) continue;
+      float f[8];
+      unpack8(ld8(staging + r0 * S::kStagingLd + vec * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = f[j] * bn_scale[vec * 8 + j] + bn_shift[vec * 8 + j];
+      if (p.bn_residual != nullptr) {
+        float r[8];
+        unpack8(addv[i], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      if (p.bn_relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      st8(p.bn_out + off, pack8(f));
     }
   }
   __syncthreads();
@@ -539,6 +613,15 @@ int pick_cluster_splits(int tiles, int k_total) {
   return s;
 }
 
+int hz_num_sms() {
+  static const int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
 int prefetch_weights_enabled() {
   static const int on = [] { const char* e = getenv("HZ_PREFETCH_B"); return (e && e[0] == '0') ? 0 : 1; }();
   return on;
@@ -578,7 +661,8 @@ int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride,
 
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w[Cout,R,S,Cin]); stats (2*Cout fp32, zeroed here) optional
 int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_is_zero, int N, int H, int W,
-                int Cin, int Cout, int R, int stride, int pad, int weights_stable, cudaStream_t st) {
+                int Cin, int Cout, int R, int stride, int pad, int weights_stable, const HzBnFuse* bn,
+                cudaStream_t st) {
   const int S_ = R;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
   Tile t;
@@ -606,9 +690,25 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
     const int tiles = t.tiles * (Cout / BLOCK_N);
     p.splits = w.ws ? pick_splits(tiles, p.cls[0].n * p.cblocks) : 1;
     p.ws = w.ws; p.sem = w.sem;
+    if (bn != nullptr) p.splits = 1;      // workspace split-K retires CTAs early: incompatible with a grid barrier
     if (p.splits == 1) {
       p.splits = pick_cluster_splits(tiles, p.cls[0].n * p.cblocks);
       p.cluster = p.splits > 1;
+    }
+    if (bn != nullptr) {
+      if (stats == nullptr || !stats_is_zero) return -21;
+      // every CTA must be resident for the barrier; keep a few SMs spare for kernels of other streams (NCCL p2p)
+      if (tiles * p.splits > hz_num_sms() - 16) return -20;
+      p.bn_out = (__nv_bfloat16*)bn->out;
+      p.bn_residual = (const __nv_bfloat16*)bn->residual;
+      p.bn_gamma = bn->gamma; p.bn_beta = bn->beta;
+      p.bn_mean = bn->mean; p.bn_invstd = bn->invstd;
+      p.bn_rmean = bn->rmean; p.bn_rvar = bn->rvar;
+      p.bn_counter = bn->counter;
+      const long long M = (long long)N * Ho * Wo;
+      p.bn_inv_count = 1.f / (float)M;
+      p.bn_unbias = (float)M / (float)(M > 1 ? M - 1 : 1);
+      p.bn_eps = bn->eps; p.bn_momentum = bn->momentum; p.bn_relu = bn->relu;
     }
   }
   p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;

@@ -428,6 +428,60 @@ __global__ void __launch_bounds__(256) im2col_small_cin_kernel(
   }
 }
 
+// The 7x7/2 stem in one launch: CTAs [0, a_blocks) build the im2col matrix A[N*Ho*Wo][KP] of the 3-channel
+// input (k = (r*7+s)*3+c, zero padded to KP), the remaining CTAs pad the [Cout,147] weight rows to KP —
+// 32-bit index math with compile-time divisors (the generic kernel above spends its time in 64-bit divides).
+template <int KP>
+__global__ void __launch_bounds__(256) stem_pack_kernel(const __nv_bfloat16* __restrict__ x,
+                                                        __nv_bfloat16* __restrict__ A,
+                                                        const __nv_bfloat16* __restrict__ w_in,
+                                                        __nv_bfloat16* __restrict__ w_out, int N, int H, int W,
+                                                        int stride, int pad, int Ho, int Wo, int rows_w,
+                                                        int a_blocks) {
+  constexpr int CIN = 3, SS = 7, K = 147, KVEC = KP / 8, RUN = SS * CIN;
+  pdl_launch();
+  pdl_wait();
+  if ((int)blockIdx.x >= a_blocks) {
+    const int total = rows_w * KP;
+    for (int i = ((int)blockIdx.x - a_blocks) * 256 + threadIdx.x; i < total; i += ((int)gridDim.x - a_blocks) * 256) {
+      const int r = i / KP, k = i % KP;
+      w_out[i] = k < K ? w_in[r * K + k] : __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
+  const int total = N * Ho * Wo * KVEC;
+  const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+  for (int v = (int)blockIdx.x * 256 + threadIdx.x; v < total; v += a_blocks * 256) {
+    const int kv = v % KVEC;
+    const int m = v / KVEC;
+    const int wo = m % Wo;
+    const int t = m / Wo;
+    const int ho = t % Ho;
+    const int n = t / Ho;
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    const int img = n * H;
+    unsigned short e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kv * 8 + i;
+      unsigned short val = 0;
+      if (k < K) {
+        const int r = k / RUN, j = k % RUN;           // j = s*3 + c: 21 contiguous input elements per patch row
+        const int h = h0 + r, w = w0 + j / CIN;
+        if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W)
+          val = __ldg(xs + ((img + h) * W + w0) * CIN + j);
+      }
+      e[i] = val;
+    }
+    uint4 pk;
+    pk.x = e[0] | ((uint32_t)e[1] << 16);
+    pk.y = e[2] | ((uint32_t)e[3] << 16);
+    pk.z = e[4] | ((uint32_t)e[5] << 16);
+    pk.w = e[6] | ((uint32_t)e[7] << 16);
+    *reinterpret_cast<uint4*>(A + (size_t)v * 8) = pk;
+  }
+}
+
 // rows of length K (bf16) -> rows of length Kp (zero padded): packs conv1's [64,147] weights for TMA
 __global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                 int rows, int K, int Kp) {
@@ -803,6 +857,20 @@ void hz_im2col_small(const void* x, void* A, int N, int H, int W, int Cin, int R
   else
     hz::launch(hz::im2col_small_cin_kernel<0, 0, 0>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)x, (__nv_bfloat16*)A, N, H, W,
                                                                 Cin, R, S, stride, pad, Ho, Wo, R * S * Cin, Kp);
+}
+
+// stem (Cin=3, 7x7): im2col of x and zero-padding of the weight rows in one launch; returns 0 if handled
+int hz_stem_pack(const void* x, void* A, const void* w, void* wp, int N, int H, int W, int Cin, int R, int stride,
+                 int pad, int Ho, int Wo, int Kp, int rows_w, cudaStream_t st) {
+  if (Cin != 3 || R != 7 || Kp != 192) return -1;
+  const long long vecs = (long long)N * Ho * Wo * (Kp / 8);
+  if (vecs > (1ll << 30)) return -1;
+  const int a_blocks = (int)((vecs + 255) / 256) < 148 * 16 ? (int)((vecs + 255) / 256) : 148 * 16;
+  const int w_blocks = (rows_w * Kp + 255) / 256;
+  hz::launch(hz::stem_pack_kernel<192>, dim3(a_blocks + w_blocks), dim3(256), 0, st, (const __nv_bfloat16*)x,
+             (__nv_bfloat16*)A, (const __nv_bfloat16*)w, (__nv_bfloat16*)wp, N, H, W, stride, pad, Ho, Wo, rows_w,
+             a_blocks);
+  return 0;
 }
 
 void hz_pad_rows(const void* in, void* out, int rows, int K, int Kp, cudaStream_t st) {

@@ -24,6 +24,8 @@ void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std,
 void hz_im2col_small(const void* x, void* A, int N, int H, int W, int Cin, int R, int S, int stride, int pad,
                      int Ho, int Wo, int Kp, cudaStream_t st);
 void hz_pad_rows(const void* in, void* out, int rows, int K, int Kp, cudaStream_t st);
+int hz_stem_pack(const void* x, void* A, const void* w, void* wp, int N, int H, int W, int Cin, int R, int stride,
+                 int pad, int Ho, int Wo, int Kp, int rows_w, cudaStream_t st);
 void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const int64_t* labels, float* pooled,
                      float* dlogits, float* logits, void* dfeat, float* loss, float* correct, float* dW,
                      float* db, int N, int C, int HW, int K, int n_valid, float loss_scale, int accumulate,
@@ -37,8 +39,21 @@ void hz_stats_update(float* stats, float* has_prev, const float* loss, const flo
 
 // ---- conv_gemm.cu (tcgen05 implicit GEMM)
 int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
+// optional fused BatchNorm(batch statistics) + residual + ReLU epilogue of the forward convolution
+struct HzBnFuse {
+  const float* gamma; const float* beta;
+  float* mean; float* invstd;          // [C] saved for backward
+  float* rmean; float* rvar;           // running statistics, updated in place (may be null)
+  const void* residual;                // bf16, layout of the output, or null
+  void* out;                           // bf16 activation
+  unsigned* counter;                   // device-wide barrier counter, zero before the launch
+  float eps, momentum;
+  int relu;
+};
+// rc -20: grid larger than the SM count (barrier needs co-residency) — caller runs the unfused pair instead
 int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_is_zero, int N, int H, int W,
-                int Cin, int Cout, int R, int stride, int pad, int weights_stable, cudaStream_t st);
+                int Cin, int Cout, int R, int stride, int pad, int weights_stable, const HzBnFuse* bn,
+                cudaStream_t st);
 int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout, int R,
                   int stride, int pad, int weights_stable, cudaStream_t st);
 int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,

@@ -147,17 +147,25 @@ class _ConvBNAct(torch.autograd.Function):
                 momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link=None, res_link=None):
         be = _be(x)
         w = compute_weight(weight, x.dtype)
-        if conv_fn is not None:        # fused GEMM + collective kernel (tensor parallel): already reduced
-            y_raw, sums = conv_fn(x, w), None
-        else:
-            y_raw, sums = be.conv_fwd(x, w, stride, pad, training and post_conv is None)
-            if post_conv is not None:  # row-parallel conv: partial sums → all-reduce before BN
-                y_raw, sums = post_conv(y_raw), None
         ctx.post_dgrad = post_dgrad
         ctx.dgrad_fn = dgrad_fn
         ctx.in_link, ctx.res_link = in_link, res_link
-        out, mean, invstd = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar,
-                                          momentum, eps, residual, relu, training)
+        fused = None
+        if conv_fn is None and post_conv is None and training and hasattr(be, "conv_bn_act_fwd"):
+            # one kernel: conv + BN statistics + device-wide barrier + normalise / residual / ReLU
+            fused = be.conv_bn_act_fwd(x, w, stride, pad, gamma.detach(), beta.detach(), rmean, rvar, momentum, eps,
+                                       residual, relu)
+        if fused is not None:
+            y_raw, out, mean, invstd = fused
+        else:
+            if conv_fn is not None:        # fused GEMM + collective kernel (tensor parallel): already reduced
+                y_raw, sums = conv_fn(x, w), None
+            else:
+                y_raw, sums = be.conv_fwd(x, w, stride, pad, training and post_conv is None)
+                if post_conv is not None:  # row-parallel conv: partial sums → all-reduce before BN
+                    y_raw, sums = post_conv(y_raw), None
+            out, mean, invstd = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar,
+                                              momentum, eps, residual, relu, training)
         ctx.save_for_backward(x, y_raw, out, mean, invstd)
         ctx.params = (weight, gamma, beta)
         ctx.cfg = (stride, pad, relu, residual is not None, training)

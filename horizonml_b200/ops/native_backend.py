@@ -104,10 +104,12 @@ def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
             n, cin, h, wd = x.shape
             cout, _, r, _ = w.shape
             ho, wo = (h + 2 * pad - r) // stride + 1, (wd + 2 * pad - r) // stride + 1
-            A = C.im2col_small(x, r, stride, pad, STEM_KP)                      # [N*Ho*Wo, 192]
+            w2d = w.permute(0, 2, 3, 1).reshape(cout, -1)
+            if not w2d.is_contiguous():
+                w2d = w2d.contiguous()
+            A, wp = C.stem_pack(x, w2d, r, stride, pad, STEM_KP)                # [N*Ho*Wo, 192], [Cout, 192]: one launch
             _STEM_CACHE["key"], _STEM_CACHE["A"] = (x.data_ptr(), x._version, tuple(x.shape)), A
-            wp = C.pad_rows(w.permute(0, 2, 3, 1).reshape(cout, -1), STEM_KP)   # [Cout, 192]
-            LAUNCHES["stem_im2col"] += 2
+            LAUNCHES["stem_im2col"] += 1
             LAUNCHES["conv_fwd"] += 1
             pre = ARENA.take(2, cout, x.device) if want_stats else None
             y2, stats = C.conv_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0, want_stats, pre,
@@ -116,6 +118,47 @@ def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
             return y, (stats if want_stats else None)
     _fallback("conv_fwd", f"x={tuple(x.shape)} w={tuple(w.shape)} s={stride}")
     return _tb.conv_fwd(x, w, stride, pad, want_stats)
+
+
+_FUSE_BN = os.environ.get("HZ_FUSE_BN", "1") != "0"
+
+
+def conv_bn_act_fwd(x, w, stride: int, pad: int, gamma, beta, rmean, rvar, momentum, eps, residual, relu: bool):
+    """Training-mode conv → BN(batch stats) → (+residual) → (ReLU) as ONE kernel: the conv epilogue leaves Σy, Σy²
+    in the statistics arena, a device-wide barrier makes them final, and every CTA normalises the tile it still
+    holds in shared memory.  Returns (y_raw, out, mean, invstd), or None when not applicable (caller runs the
+    conv and BN kernels separately)."""
+    if not (_FUSE_BN and _bf16_cl(x) and w.dtype == torch.bfloat16 and C.channel_ok(w.shape[0])):
+        return None
+    if residual is not None and not _bf16_cl(residual):
+        return None
+    cout = w.shape[0]
+    direct = _conv_ok(x.shape, w.shape, stride, pad)
+    if not direct and not _is_stem(x.shape, w.shape):
+        return None
+    scratch = ARENA.take(1, 2 * cout + 32, x.device)          # [Σy | Σy² | barrier counter], pre-zeroed
+    if scratch is None:
+        return None
+    LAUNCHES["conv_bn_fused"] += 1
+    if direct:
+        y, out, mean, invstd = C.conv_bn_act_fwd(x, w, stride, pad, scratch.view(-1), gamma, beta, rmean, rvar,
+                                                 momentum, eps, residual, relu, _stable(w))
+        return y, out, mean, invstd
+    n, cin, h, wd = x.shape
+    r = w.shape[2]
+    ho, wo = (h + 2 * pad - r) // stride + 1, (wd + 2 * pad - r) // stride + 1
+    w2d = w.permute(0, 2, 3, 1).reshape(cout, -1)
+    if not w2d.is_contiguous():
+        w2d = w2d.contiguous()
+    A, wp = C.stem_pack(x, w2d, r, stride, pad, STEM_KP)
+    _STEM_CACHE["key"], _STEM_CACHE["A"] = (x.data_ptr(), x._version, tuple(x.shape)), A
+    LAUNCHES["stem_im2col"] += 1
+    res2 = residual.permute(0, 2, 3, 1).reshape(-1, cout, 1, 1) if residual is not None else None
+    y2, o2, mean, invstd = C.conv_bn_act_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0,
+                                             scratch.view(-1), gamma, beta, rmean, rvar, momentum, eps, res2, relu,
+                                             False)
+    return (y2.reshape(n, ho, wo, cout).permute(0, 3, 1, 2), o2.reshape(n, ho, wo, cout).permute(0, 3, 1, 2),
+            mean, invstd)
 
 
 def bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual, relu, training):

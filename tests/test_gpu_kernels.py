@@ -62,6 +62,58 @@ def test_conv_fwd_tcgen05(nb, tb, cfg):
 
 
 @pytest.mark.parametrize("cfg", CONVS)
+@pytest.mark.parametrize("res,relu", [(False, True), (True, True), (False, False)])
+def test_conv_bn_act_fused(nb, tb, cfg, res, relu):
+    """conv + BN(batch stats) + residual + ReLU in one kernel (grid barrier in the conv epilogue) == the conv kernel
+    followed by the BN kernel == fp32 oracle."""
+    x, w, _ = _conv_data(cfg)
+    cout = w.shape[0]
+    g = torch.Generator().manual_seed(5)
+    gamma = (torch.rand(cout, generator=g) + 0.5).to(DEV)
+    beta = (torch.randn(cout, generator=g) * 0.1).to(DEV)
+    nb.step_begin(DEV)
+    try:
+        y0, sums = nb.conv_fwd(x, w, cfg[6], cfg[7], True)
+        r = cl((torch.randn(y0.shape, generator=g) * 0.5).to(DEV).bfloat16()) if res else None
+        rm0, rv0 = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+        o0, m0, i0 = nb.bn_act_fwd(y0, sums, gamma, beta, rm0, rv0, 0.1, 1e-5, r, relu, True)
+        rm1, rv1 = torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV)
+        fused = nb.conv_bn_act_fwd(x, w, cfg[6], cfg[7], gamma, beta, rm1, rv1, 0.1, 1e-5, r, relu)
+        assert fused is not None, "fused path not taken"
+        y1, o1, m1, i1 = fused
+        torch.cuda.synchronize()
+    finally:
+        nb.step_end()
+    assert torch.equal(y0, y1)
+    assert torch.allclose(m0, m1, rtol=1e-4, atol=1e-5) and torch.allclose(i0, i1, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rm0, rm1, rtol=1e-4, atol=1e-6) and torch.allclose(rv0, rv1, rtol=1e-4, atol=1e-6)
+    assert rel_err(o1, o0) < 1e-2                       # same maths; Σ order may move a bf16 ulp
+    yr, sr = tb.conv_fwd(x.float(), w.float(), cfg[6], cfg[7], True)
+    orf, _, _ = tb.bn_act_fwd(yr, sr, gamma, beta, torch.zeros(cout, device=DEV), torch.ones(cout, device=DEV), 0.1, 1e-5,
+                              r.float() if res else None, relu, True)
+    assert rel_err(o1, orf) < 3e-2
+
+
+def test_stem_conv_bn_fused(nb, tb):
+    g = torch.Generator().manual_seed(9)
+    x = cl((torch.randn(64, 3, 32, 32, generator=g)).to(DEV).bfloat16())
+    w = cl((torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5).to(DEV).bfloat16())
+    gamma, beta = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
+    nb.step_begin(DEV)
+    try:
+        y0, sums = nb.conv_fwd(x, w, 2, 3, True)
+        o0, m0, i0 = nb.bn_act_fwd(y0, sums, gamma, beta, None, None, 0.1, 1e-5, None, True, True)
+        fused = nb.conv_bn_act_fwd(x, w, 2, 3, gamma, beta, None, None, 0.1, 1e-5, None, True)
+        assert fused is not None
+        y1, o1, m1, i1 = fused
+        torch.cuda.synchronize()
+    finally:
+        nb.step_end()
+    assert torch.equal(y0, y1) and y1.shape == (64, 64, 16, 16)
+    assert torch.allclose(m0, m1, rtol=1e-4, atol=1e-5) and rel_err(o1, o0) < 1e-2
+
+
+@pytest.mark.parametrize("cfg", CONVS)
 def test_conv_dgrad_tcgen05(nb, tb, cfg):
     x, w, dy = _conv_data(cfg)
     before = nb.FALLBACKS["conv_dgrad"]
