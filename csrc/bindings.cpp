@@ -421,6 +421,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("u8_normalize", &u8_normalize);
   m.def("im2col_small", &im2col_small);
   m.def("pad_rows", &pad_rows);
+  m.def("cluster_capacity", [] { int v[4]; hz_cluster_capacity(v); return std::vector<int64_t>{v[0], v[1], v[2], v[3]}; });
   m.def("conv_bn_act_fwd", &conv_bn_act_fwd);
   m.def("stem_pack", &stem_pack);
   m.def("head_fwd_bwd", &head_fwd_bwd);

@@ -602,17 +602,6 @@ SplitWs get_split_ws() {
 }
 // cluster (DSMEM) split-K factor: power of two <= 8; only when the K loop is long enough to pay for the
 // two cluster barriers (~1.5 us) and the grid still fits in one wave
-int pick_cluster_splits(int tiles, int k_total) {
-  // validated on B200 (all conv numerics tests; 0.670 -> 0.612 ms/step); HZ_CLUSTER_SPLITK=0 disables
-  static const bool off = [] { const char* e = getenv("HZ_CLUSTER_SPLITK"); return e && e[0] == '0'; }();
-  static const int min_k = [] { const char* e = getenv("HZ_CLUSTER_MIN_K"); return e ? atoi(e) : 8; }();
-  static const int min_per = [] { const char* e = getenv("HZ_CLUSTER_MIN_PER"); return e ? atoi(e) : 2; }();
-  if (off || tiles <= 0 || k_total < min_k) return 1;
-  int s = 8;
-  while (s > 1 && (tiles * s > 148 || k_total / s < min_per)) s >>= 1;
-  return s;
-}
-
 int hz_num_sms() {
   static const int n = [] {
     int dev = 0, v = 148;
@@ -620,6 +609,46 @@ int hz_num_sms() {
     return v > 0 ? v : 148;
   }();
   return n;
+}
+
+// How many clusters of `cluster` CTAs of this kernel can be resident at once (1 CTA/SM, clusters live inside a GPC:
+// on B200 a cluster of 8 does not tile the 148 SMs evenly).  A grid with more clusters than that runs in two
+// waves — and a kernel with a device-wide barrier would deadlock — so the split factor is chosen to fit.
+template <typename K>
+int max_active_clusters(K kernel, size_t smem, int cluster) {
+  static int cache[17] = {0};
+  if (cluster < 1 || cluster > 16) return 0;
+  if (cache[cluster] == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1, 1, (unsigned)cluster);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = (unsigned)cluster;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cluster == 1) {
+      n = hz_num_sms();
+    } else if (cudaOccupancyMaxActiveClusters(&n, (const void*)kernel, &cfg) != cudaSuccess || n <= 0) {
+      (void)cudaGetLastError();
+      n = hz_num_sms() / cluster - 2;          // conservative guess
+    }
+    cache[cluster] = n > 0 ? n : 1;
+  }
+  return cache[cluster];
+}
+
+int pick_cluster_splits(int tiles, int k_total, int (*max_clusters)(int)) {
+  // validated on B200 (all conv numerics tests; 0.670 -> 0.612 ms/step); HZ_CLUSTER_SPLITK=0 disables
+  static const bool off = [] { const char* e = getenv("HZ_CLUSTER_SPLITK"); return e && e[0] == '0'; }();
+  static const int min_k = [] { const char* e = getenv("HZ_CLUSTER_MIN_K"); return e ? atoi(e) : 8; }();
+  static const int min_per = [] { const char* e = getenv("HZ_CLUSTER_MIN_PER"); return e ? atoi(e) : 2; }();
+  if (off || tiles <= 0 || k_total < min_k) return 1;
+  static const bool one_wave = [] { const char* e = getenv("HZ_CLUSTER_ONE_WAVE"); return !(e && e[0] == '0'); }();
+  int s = 8;
+  while (s > 1 && (tiles * s > 148 || k_total / s < min_per || (one_wave && tiles > max_clusters(s)))) s >>= 1;
+  return s;
 }
 
 int prefetch_weights_enabled() {
@@ -659,12 +688,22 @@ int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride,
   return get_encode() != nullptr;
 }
 
+// resident clusters of the forward conv kernel for cluster sizes 1,2,4,8 (diagnostics)
+void hz_cluster_capacity(int out[4]) {
+  static bool attr = set_smem(hz::igemm_kernel<64, false>, hz::IgemmSmem<64>::kTotal);
+  (void)attr;
+  const int cs[4] = {1, 2, 4, 8};
+  for (int i = 0; i < 4; ++i) out[i] = max_active_clusters(hz::igemm_kernel<64, false>, hz::IgemmSmem<64>::kTotal, cs[i]);
+}
+
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w[Cout,R,S,Cin]); stats (2*Cout fp32, zeroed here) optional
 int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_is_zero, int N, int H, int W,
                 int Cin, int Cout, int R, int stride, int pad, int weights_stable, const HzBnFuse* bn,
                 cudaStream_t st) {
   const int S_ = R;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
+  static bool attr = set_smem(hz::igemm_kernel<64, false>, hz::IgemmSmem<64>::kTotal);   // before any occupancy query
+  (void)attr;
   Tile t;
   if (!pick_tile(128, N, Ho, Wo, &t)) return -10;
   hz::AMaps am;
@@ -692,13 +731,18 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
     p.ws = w.ws; p.sem = w.sem;
     if (bn != nullptr) p.splits = 1;      // workspace split-K retires CTAs early: incompatible with a grid barrier
     if (p.splits == 1) {
-      p.splits = pick_cluster_splits(tiles, p.cls[0].n * p.cblocks);
+      p.splits = pick_cluster_splits(tiles, p.cls[0].n * p.cblocks, [](int c) {
+        return max_active_clusters(hz::igemm_kernel<64, false>, hz::IgemmSmem<64>::kTotal, c);
+      });
       p.cluster = p.splits > 1;
     }
     if (bn != nullptr) {
       if (stats == nullptr || !stats_is_zero) return -21;
-      // every CTA must be resident for the barrier; keep a few SMs spare for kernels of other streams (NCCL p2p)
-      if (tiles * p.splits > hz_num_sms() - 16) return -20;
+      // every CTA must be resident for the barrier: clusters are already limited to one wave by
+      // pick_cluster_splits; plain grids keep a few SMs spare for kernels of other streams (NCCL p2p)
+      if (p.cluster ? tiles > max_active_clusters(hz::igemm_kernel<64, false>, hz::IgemmSmem<64>::kTotal, p.splits)
+                    : tiles > hz_num_sms() - 16)
+        return -20;
       p.bn_out = (__nv_bfloat16*)bn->out;
       p.bn_residual = (const __nv_bfloat16*)bn->residual;
       p.bn_gamma = bn->gamma; p.bn_beta = bn->beta;
@@ -713,8 +757,6 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   }
   p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;
   using SM = hz::IgemmSmem<BLOCK_N>;
-  static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, false>, SM::kTotal);
-  (void)attr;
   dim3 grid(t.tiles, Cout / BLOCK_N, p.splits);
   return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, false>, grid, dim3(128), SM::kTotal, st,
                             p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;
@@ -728,6 +770,8 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
   // output lattice per class: stride 1 -> (H,W); stride 2 -> (H/2,W/2) == (Ho,Wo)
   const int Lh = stride == 1 ? H : H / 2, Lw = stride == 1 ? W : W / 2;
   if (stride == 2 && (Lh != Ho || Lw != Wo)) return -13;
+  static bool attr = set_smem(hz::igemm_kernel<64, true>, hz::IgemmSmem<64>::kTotal);    // before any occupancy query
+  (void)attr;
   Tile t;
   if (!pick_tile(128, N, Lh, Lw, &t)) return -10;
   hz::AMaps am;
@@ -778,14 +822,14 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
     p.splits = w.ws ? pick_splits(tiles, kmax * p.cblocks) : 1;
     p.ws = w.ws; p.sem = w.sem;
     if (p.splits == 1) {
-      p.splits = pick_cluster_splits(tiles, kmax * p.cblocks);
+      p.splits = pick_cluster_splits(tiles, kmax * p.cblocks, [](int c) {
+        return max_active_clusters(hz::igemm_kernel<64, true>, hz::IgemmSmem<64>::kTotal, c);
+      });
       p.cluster = p.splits > 1;
     }
   }
   p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;
   using SM = hz::IgemmSmem<BLOCK_N>;
-  static bool attr = set_smem(hz::igemm_kernel<BLOCK_N, true>, SM::kTotal);
-  (void)attr;
   dim3 grid(t.tiles, Cin / BLOCK_N, p.num_classes * p.splits);
   return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, true>, grid, dim3(128), SM::kTotal, st,
                             p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;

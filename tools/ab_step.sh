@@ -18,3 +18,4 @@ except Exception as e:
 }
 run nofuse   HZ_FUSE_BN=0 --
 run fusebn   HZ_FUSE_BN=1 --
+run nofuse_2wave HZ_FUSE_BN=0 HZ_CLUSTER_ONE_WAVE=0 --
