@@ -120,7 +120,10 @@ def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
     return _tb.conv_fwd(x, w, stride, pad, want_stats)
 
 
-_FUSE_BN = os.environ.get("HZ_FUSE_BN", "1") != "0"
+# Measured on B200 (profiles/README.md): the device-wide barrier costs more than the separate BN kernel saves once
+# programmatic dependent launch overlaps that kernel's launch and prologue (0.586 vs 0.571 ms/step) — opt-in.
+_FUSE_BN = os.environ.get("HZ_FUSE_BN", "0") == "1"
+_BN_BWD_FUSED = os.environ.get("HZ_BN_BWD_FUSED", "1") != "0"
 
 
 def conv_bn_act_fwd(x, w, stride: int, pad: int, gamma, beta, rmean, rvar, momentum, eps, residual, relu: bool):
@@ -186,8 +189,10 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma
         else:
             dg, ag, db, ab = dgamma_slot.t, dgamma_slot.acc, dbeta_slot.t, dbeta_slot.acc
         LAUNCHES["bn_act_bwd"] += 2
-        scratch = ARENA.take(1, 2 * c + 32, y_raw.device)      # [Σg | Σg·x̂ | barrier counter], pre-zeroed
-        LAUNCHES["bn_act_bwd"] -= 1 if scratch is not None else 0
+        # [Σg | Σg·x̂ | barrier counter], pre-zeroed: one kernel (reduce → device-wide barrier → apply); without
+        # room for the counter the binding runs the reduce and apply kernels separately
+        scratch = ARENA.take(1, 2 * c + (32 if _BN_BWD_FUSED else 0), y_raw.device)
+        LAUNCHES["bn_act_bwd"] -= 1 if (scratch is not None and _BN_BWD_FUSED) else 0
         dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dg, db, ag, ab,
                                 scratch)
         return dy, dg, db, (dres if has_residual else None)

@@ -16,6 +16,5 @@ try:
 except Exception as e:
     print("FAILED", e)')" | tee -a $OUT
 }
-run nofuse   HZ_FUSE_BN=0 --
-run fusebn   HZ_FUSE_BN=1 --
-run nofuse_2wave HZ_FUSE_BN=0 HZ_CLUSTER_ONE_WAVE=0 --
+run default      --
+run bnbwd_2k     HZ_BN_BWD_FUSED=0 --
