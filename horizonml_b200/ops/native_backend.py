@@ -123,7 +123,9 @@ def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
 # Measured on B200 (profiles/README.md): the device-wide barrier costs more than the separate BN kernel saves once
 # programmatic dependent launch overlaps that kernel's launch and prologue (0.586 vs 0.571 ms/step) — opt-in.
 _FUSE_BN = os.environ.get("HZ_FUSE_BN", "0") == "1"
-_BN_BWD_FUSED = os.environ.get("HZ_BN_BWD_FUSED", "1") != "0"
+# Same finding for BN backward: reduce → device-wide barrier → apply in one kernel (0.572 ms/step) loses to two
+# PDL-chained kernels (0.562 ms/step); HZ_BN_BWD_FUSED=1 selects the single-kernel variant.
+_BN_BWD_FUSED = os.environ.get("HZ_BN_BWD_FUSED", "0") == "1"
 
 
 def conv_bn_act_fwd(x, w, stride: int, pad: int, gamma, beta, rmean, rvar, momentum, eps, residual, relu: bool):
