@@ -421,6 +421,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("u8_normalize", &u8_normalize);
   m.def("im2col_small", &im2col_small);
   m.def("pad_rows", &pad_rows);
+  m.def("conv_set_debug", [](c10::optional<Tensor> buf) {
+    if (buf.has_value() && buf->defined()) {
+      TORCH_CHECK(buf->is_cuda() && buf->scalar_type() == at::kLong && buf->is_contiguous());
+      hz_conv_set_debug(reinterpret_cast<long long*>(buf->data_ptr<int64_t>()));
+    } else {
+      hz_conv_set_debug(nullptr);
+    }
+  });
   m.def("cluster_capacity", [] { int v[4]; hz_cluster_capacity(v); return std::vector<int64_t>{v[0], v[1], v[2], v[3]}; });
   m.def("conv_bn_act_fwd", &conv_bn_act_fwd);
   m.def("stem_pack", &stem_pack);

@@ -61,6 +61,7 @@ struct IgemmParams {
   unsigned* bn_counter;          // zero before the launch
   float bn_inv_count, bn_unbias, bn_eps, bn_momentum;
   int bn_relu;
+  long long* dbg;                // optional: per-CTA clock64 stamps of the kernel's phases (tools/conv_timeline.py)
 };
 
 HZ_DEVINL unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -84,6 +85,9 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
+  long long* dbg = p.dbg ? p.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+#define HZ_STAMP(i) do { if (dbg != nullptr) dbg[i] = clock64(); } while (0)
+  if (threadIdx.x == 0) HZ_STAMP(0);                     // kernel entry
   const int cls = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const TapList& taps = p.cls[cls];
   const int n0 = (p.BN == 1) ? mt / p.tiles_per_img : mt * p.BN;
@@ -133,7 +137,9 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       load_b(it);
     }
   }
+  if (threadIdx.x == 0) HZ_STAMP(1);                     // prologue done (barriers, TMEM, first weight requests)
   pdl_wait();          // everything above overlapped the tail of the previous kernel
+  if (threadIdx.x == 0) HZ_STAMP(2);                     // upstream kernel complete
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       const int s = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
       tc::mbar_wait(&full[s], ph);
+      if (it == 0) HZ_STAMP(3);                          // first operand stage landed
       tc::fence_after_sync();
       const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
       const uint32_t sb = sa + kABytes;
@@ -171,6 +178,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       tc::umma_commit(&empty[s]);
     }
     if (k_iters > 0) tc::umma_commit(tmem_full);
+    HZ_STAMP(4);                                         // last MMA issued
   }
   __syncwarp();
 
@@ -210,6 +218,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
   }
+  if (threadIdx.x == 64) HZ_STAMP(5);                    // accumulator complete
   if (p.splits > 1 && p.cluster) {
     // ---- cluster split-K: every CTA of the cluster parks its fp32 partial tile in its own shared memory,
     //      then CTA r reduces rows [r*128/S, (r+1)*128/S) of all S partials through distributed shared memory
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   }
   tc::fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 64) HZ_STAMP(6);                    // tile (reduced over the cluster) staged in shared memory
 
   // coalesced stores: BLOCK_N/8 16-byte vectors per row
   {
@@ -355,6 +365,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       atomicAdd(&p.stats[p.ncols + nt * BLOCK_N + col], q);
     }
   }
+  if (threadIdx.x == 64) HZ_STAMP(7);                    // output rows + BN sums written
   if (p.bn_out != nullptr) {
     // ---- fused BN + residual + ReLU.  grid <= #SMs (host-checked) and 1 CTA/SM: all CTAs are co-resident, the
     //      barrier cannot deadlock; PDL dependents are only scheduled once every CTA of this grid has started.
@@ -414,6 +425,8 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   }
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tmem_d, BLOCK_N);
+  if (threadIdx.x == 64) HZ_STAMP(8);                    // done
+#undef HZ_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -602,6 +615,8 @@ SplitWs get_split_ws() {
 }
 // cluster (DSMEM) split-K factor: power of two <= 8; only when the K loop is long enough to pay for the
 // two cluster barriers (~1.5 us) and the grid still fits in one wave
+long long* g_conv_dbg = nullptr;
+
 int hz_num_sms() {
   static const int n = [] {
     int dev = 0, v = 148;
@@ -688,6 +703,9 @@ int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride,
   return get_encode() != nullptr;
 }
 
+// per-CTA phase stamps (16 x int64 per CTA) for the next forward / dgrad launches; nullptr switches them off
+void hz_conv_set_debug(long long* buf) { g_conv_dbg = buf; }
+
 // resident clusters of the forward conv kernel for cluster sizes 1,2,4,8 (diagnostics)
 void hz_cluster_capacity(int out[4]) {
   static bool attr = set_smem(hz::igemm_kernel<64, false>, hz::IgemmSmem<64>::kTotal);
@@ -756,6 +774,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
     }
   }
   p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;
+  p.dbg = g_conv_dbg;
   using SM = hz::IgemmSmem<BLOCK_N>;
   dim3 grid(t.tiles, Cout / BLOCK_N, p.splits);
   return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, false>, grid, dim3(128), SM::kTotal, st,
@@ -829,6 +848,7 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
     }
   }
   p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;
+  p.dbg = g_conv_dbg;
   using SM = hz::IgemmSmem<BLOCK_N>;
   dim3 grid(t.tiles, Cin / BLOCK_N, p.num_classes * p.splits);
   return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, true>, grid, dim3(128), SM::kTotal, st,

@@ -40,6 +40,7 @@ void hz_stats_update(float* stats, float* has_prev, const float* loss, const flo
 // ---- conv_gemm.cu (tcgen05 implicit GEMM)
 int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
 void hz_cluster_capacity(int out[4]);
+void hz_conv_set_debug(long long* buf);
 // optional fused BatchNorm(batch statistics) + residual + ReLU epilogue of the forward convolution
 struct HzBnFuse {
   const float* gamma; const float* beta;
