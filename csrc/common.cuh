@@ -75,6 +75,15 @@ HZ_DEVINL float4 ld_dsmem_f4(uint32_t addr) {
   return v;
 }
 
+// same load without the compiler memory barrier: lets a batch of independent remote loads be issued back to back
+// (ordering against the surrounding barrier.cluster is kept by `volatile`)
+HZ_DEVINL float4 ld_dsmem_f4_nb(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 HZ_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 }  // namespace hz

@@ -70,6 +70,41 @@ HZ_DEVINL unsigned ld_acquire_gpu_u32(const unsigned* p) {
   return v;
 }
 
+// Cluster split-K reduction of this CTA's row slice: the fp32 partial tiles of all SX CTAs are read through
+// distributed shared memory.  Measured with the in-kernel phase stamps (tools/conv_timeline.py): issuing the SX
+// remote loads of an item one after the other, each feeding an add, serialises ~16 DSMEM round trips (2.3 us of a
+// 6 us kernel) — here all of a thread's remote loads are in flight before the first add.
+template <int SX, int BLOCK_N, int RED_LD, int STAGING_LD>
+HZ_DEVINL void cluster_reduce_rows(uint32_t red_base, int row_lo, __nv_bfloat16* staging) {
+  constexpr int kChunks = BLOCK_N / 4;
+  constexpr int kItems = (kTileM / SX) * kChunks / 128;
+  static_assert(kItems >= 1 && kItems * SX <= 32, "remote loads in flight per thread");
+  float4 v[kItems][SX];
+#pragma unroll
+  for (int it = 0; it < kItems; ++it) {
+    const int idx = threadIdx.x + it * 128;
+    const int rr = row_lo + idx / kChunks, ch = idx % kChunks;
+    const uint32_t off = (uint32_t)((rr * RED_LD + ch * 4) * 4);
+#pragma unroll
+    for (int s2 = 0; s2 < SX; ++s2) v[it][s2] = ld_dsmem_f4_nb(map_to_cta(red_base + off, (uint32_t)s2));
+  }
+#pragma unroll
+  for (int it = 0; it < kItems; ++it) {
+    const int idx = threadIdx.x + it * 128;
+    const int rr = row_lo + idx / kChunks, ch = idx % kChunks;
+    float4 acc = v[it][0];
+#pragma unroll
+    for (int s2 = 1; s2 < SX; ++s2) {                                     // fixed order: deterministic
+      acc.x += v[it][s2].x; acc.y += v[it][s2].y; acc.z += v[it][s2].z; acc.w += v[it][s2].w;
+    }
+    __nv_bfloat162 lo2 = __floats2bfloat162_rn(acc.x, acc.y), hi2 = __floats2bfloat162_rn(acc.z, acc.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+    *reinterpret_cast<uint2*>(staging + rr * STAGING_LD + ch * 4) = pk;
+  }
+}
+
 template <int BLOCK_N, bool B_MN>
 __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMaps amaps,
                                                     const __grid_constant__ CUtensorMap bmap,
@@ -204,15 +239,20 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   };
   // residual-gradient fusion: the addend rows this thread will write are requested now, so their L2 latency
   // hides under the MMA tail instead of serialising with the stores
+  // all of this thread's output addresses, computed while the MMAs are still running (the runtime divisions in
+  // out_offset() used to sit between the accumulator and the stores)
+  long long offs[kPasses];
+#pragma unroll
+  for (int i = 0; i < kPasses; ++i) {
+    const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
+    offs[i] = r0 < row_hi ? out_offset(r0) : -1;
+  }
   bf16x8 addv[kPasses];
   const __nv_bfloat16* pre = p.addend != nullptr ? p.addend : p.bn_residual;      // (never both: dgrad vs forward)
   if (pre != nullptr) {
 #pragma unroll
-    for (int i = 0; i < kPasses; ++i) {
-      const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
-      const long long off = r0 < row_hi ? out_offset(r0) : -1;
-      if (off >= 0) addv[i] = ld8(pre + off);
-    }
+    for (int i = 0; i < kPasses; ++i)
+      if (offs[i] >= 0) addv[i] = ld8(pre + offs[i]);
   }
   if (k_iters > 0) {
     tc::mbar_wait(tmem_full, 0);
@@ -246,6 +286,13 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     const int rows_per = kTileM / Sx;
     constexpr int kChunks = BLOCK_N / 4;
     const uint32_t red_base = smem_u32(red);
+    if (Sx == 4) {
+      cluster_reduce_rows<4, BLOCK_N, kRedLd, S::kStagingLd>(red_base, row_lo, staging);
+    } else if (Sx == 8) {
+      cluster_reduce_rows<8, BLOCK_N, kRedLd, S::kStagingLd>(red_base, row_lo, staging);
+    } else if (Sx == 2) {
+      cluster_reduce_rows<2, BLOCK_N, kRedLd, S::kStagingLd>(red_base, row_lo, staging);
+    } else
     for (int idx = threadIdx.x; idx < rows_per * kChunks; idx += 128) {
       const int rr = row_lo + idx / kChunks, ch = idx % kChunks;
       const uint32_t off = (uint32_t)((rr * kRedLd + ch * 4) * 4);
@@ -337,8 +384,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
       const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
-      if (r0 >= row_hi) break;
-      const long long off = out_offset(r0);
+      const long long off = offs[i];
       if (off < 0) continue;
       bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
       if (p.addend != nullptr) {
@@ -403,8 +449,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
       const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
-      if (r0 >= row_hi) break;
-      const long long off = out_offset(r0);
+      const long long off = offs[i];
       if (off < 0) continue;
       float f[8];
       unpack8(ld8(staging + r0 * S::kStagingLd + vec * 8), f);
