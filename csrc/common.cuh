@@ -62,6 +62,9 @@ HZ_DEVINL uint32_t cluster_ctarank() {
 HZ_DEVINL void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split form: arrive as soon as this CTA is done with its peers' memory, wait only where the hazard really is
+HZ_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+HZ_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // shared::cluster address of `local_smem_addr` inside CTA `rank` of this cluster
 HZ_DEVINL uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
   uint32_t r;

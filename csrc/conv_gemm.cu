@@ -307,7 +307,9 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       pk.y = *reinterpret_cast<uint32_t*>(&hi2);
       *reinterpret_cast<uint2*>(staging + rr * S::kStagingLd + ch * 4) = pk;
     }
-    cluster_sync();                                                       // peers are done reading my `red`
+    // Peers may still be reading my `red` (it is not written again), so the only hazard left is this CTA
+    // exiting early: arrive now, wait right before the kernel ends — the stores below overlap the barrier.
+    cluster_arrive();
   } else if (p.splits == 1) {
     if (k_iters > 0) {
 #pragma unroll
@@ -378,15 +380,27 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   __syncthreads();
   if (threadIdx.x == 64) HZ_STAMP(6);                    // tile (reduced over the cluster) staged in shared memory
 
-  // coalesced stores: BLOCK_N/8 16-byte vectors per row
+  // coalesced stores: BLOCK_N/8 16-byte vectors per row.  The BatchNorm sums (forward) come from the same
+  // registers: a separate per-column pass over the staged tile was a chain of dependent shared-memory loads
+  // (~1.1 us for a 128-row tile, measured with the phase stamps).
+  static_assert(BLOCK_N == 64, "stats reduction below assumes 8 vectors per row");
+  float ssum[8], ssq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
   {
     const int vec = threadIdx.x % kVecPerRow;
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
       const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
       const long long off = offs[i];
-      if (off < 0) continue;
+      if (off < 0) continue;              // rows past the last image are zero-filled: they add nothing to the sums
       bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
+      if (p.stats != nullptr) {
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ssum[j] += f[j]; ssq[j] += f[j] * f[j]; }
+      }
       if (p.addend != nullptr) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) v.v[j] = __hadd2(v.v[j], addv[i].v[j]);  // bf16 + bf16 -> bf16, as the separate add did
@@ -395,21 +409,26 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     }
   }
   if (p.stats != nullptr) {
-    // per-channel sum / sum of squares over this CTA's rows (zero-filled OOB rows contribute 0)
-    constexpr int kParts = 128 / BLOCK_N;          // 2 for BLOCK_N=64, 1 for 128
-    const int col = threadIdx.x % BLOCK_N;
-    const int part = threadIdx.x / BLOCK_N;
-    if (part < kParts) {
-      float s = 0.f, q = 0.f;
-      const int rows = (row_hi - row_lo) / kParts;
-      for (int r0 = row_lo + part * rows; r0 < row_lo + (part + 1) * rows; ++r0) {
-        const float v = __bfloat162float(staging[r0 * S::kStagingLd + col]);
-        s += v;
-        q += v * v;
-      }
-      atomicAdd(&p.stats[nt * BLOCK_N + col], s);
-      atomicAdd(&p.stats[p.ncols + nt * BLOCK_N + col], q);
+    // lanes l, l^8, l^16, l^24 hold the same 8 columns (different rows): fold them, then the 4 warps through smem
+    __shared__ float stat_sm[4][2][BLOCK_N];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 8);
+      ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 8);
+      ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
+      ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 16);
     }
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        stat_sm[warp][0][lane * 8 + j] = ssum[j];
+        stat_sm[warp][1][lane * 8 + j] = ssq[j];
+      }
+    }
+    __syncthreads();
+    const int col = threadIdx.x % BLOCK_N, which = threadIdx.x / BLOCK_N;       // 128 threads = 64 columns x {Σ, Σ²}
+    const float tot = stat_sm[0][which][col] + stat_sm[1][which][col] + stat_sm[2][which][col] + stat_sm[3][which][col];
+    atomicAdd(&p.stats[which * p.ncols + nt * BLOCK_N + col], tot);
   }
   if (threadIdx.x == 64) HZ_STAMP(7);                    // output rows + BN sums written
   if (p.bn_out != nullptr) {
@@ -468,6 +487,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       st8(p.bn_out + off, pack8(f));
     }
   }
+  if (p.splits > 1 && p.cluster) cluster_wait();         // no peer reads this CTA's shared memory any more
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tmem_d, BLOCK_N);
   if (threadIdx.x == 64) HZ_STAMP(8);                    // done
