@@ -351,3 +351,61 @@ def test_bucketwise_adam_equals_whole_buffer_adam():
     for i in range(3):
         assert torch.allclose(a[i], b[i], rtol=1e-6, atol=1e-8)
     assert all(abs(x - y) <= 1e-4 * abs(x) for x, y in zip(a[4], b[4]))
+
+
+def test_device_mesh_layout():
+    """rank = (dp*PP + pp)*TP + tp: TP ranks adjacent, DP outermost; neighbours and group membership are consistent."""
+    from horizonml_b200.parallel.mesh import DeviceMesh
+    world, dp, pp, tp = 8, 2, 2, 2
+    seen = set()
+    for r in range(world):
+        m = DeviceMesh(world, r, dp=dp, pp=pp, tp=tp, create_groups=False)
+        c = m.coord
+        assert m.rank_of(c.dp, c.pp, c.tp) == r
+        seen.add((c.dp, c.pp, c.tp))
+        assert r in m.dp_ranks() and r in m.pp_ranks() and r in m.tp_ranks()
+        assert len(m.dp_ranks()) == dp and len(m.pp_ranks()) == pp and len(m.tp_ranks()) == tp
+        assert m.tp_ranks() == list(range(r - c.tp, r - c.tp + tp))                   # adjacent GPUs
+        prev, nxt = m.pp_neighbours()
+        assert (prev is None) == (c.pp == 0) and (nxt is None) == (c.pp == pp - 1)
+        if nxt is not None:
+            assert DeviceMesh(world, nxt, dp, pp, tp, create_groups=False).pp_neighbours()[0] == r
+    assert len(seen) == world
+    with pytest.raises(ValueError):
+        DeviceMesh(8, 0, dp=3, pp=2, tp=1, create_groups=False)
+
+
+def test_hybrid_cli_flags():
+    import argparse
+    from horizonml_b200.config import add_train_flags, config_from_args
+    p = argparse.ArgumentParser()
+    add_train_flags(p, "layer")
+    cfg = config_from_args(p.parse_args(["--world_size", "8", "--dp_replicas", "2", "--overlap_adam",
+                                         "--no_region_probe", "--bucket_by_live", "--live_bucket_mb", "4"]), "layer")
+    assert cfg.dp_replicas == 2 and cfg.overlap_adam and not cfg.region_probe and cfg.bucket_by_live
+    assert cfg.live_bucket_mb == 4.0 and TrainConfig().dp_replicas == 1 and TrainConfig().region_probe
+
+
+def test_dp_engine_bucketwise_adam_equals_whole_adam():
+    """DPEngine with --overlap_adam (Adam per bucket from the reducer's post_bucket hook) == the single fused pass."""
+    from horizonml_b200 import ops
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.dp import DPEngine
+    ops.set_backend("torch")
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(8, 3, 32, 32, generator=gen).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (8,), generator=gen)
+    out = []
+    for bw in (False, True):
+        cfg = TrainConfig(strategy="data", world_size=1, device="cpu", dtype="fp32", backend="torch", quiet=True,
+                          overlap_adam=bw, bucket_mb=4.0, seed=5)
+        eng = DPEngine(cfg, Runtime(0, 1, torch.device("cpu"), torch.float32, "torch", "none"))
+        assert eng.bucket_adam == bw and (eng.reducer is not None) == bw
+        for _ in range(3):
+            eng.step(x, y)
+        s = eng.stats.read_and_reset()
+        out.append((eng.flat.master.clone(), eng.opt.m.clone(), float(eng.opt.step_t), s["loss_sum"], s["grad_div_sum"]))
+    a, b = out
+    assert a[2] == b[2] == 3.0
+    assert torch.allclose(a[0], b[0], rtol=1e-6, atol=1e-8) and torch.allclose(a[1], b[1], rtol=1e-6, atol=1e-9)
+    assert abs(a[3] - b[3]) < 1e-5 and abs(a[4] - b[4]) <= 1e-4 * max(abs(a[4]), 1e-12)
