@@ -16,12 +16,14 @@ def _path(save_dir: str, tag: str) -> str:
     return os.path.join(save_dir, f"ckpt_{tag}.pt")
 
 
-def save(save_dir: str, tag: str, model, optimizer, epoch: int, global_step: int, extra: Optional[dict] = None):
+def save(save_dir: str, tag: str, model, optimizer, epoch: int, global_step: int, extra: Optional[dict] = None,
+         optim_state: Optional[dict] = None):
+    """``optim_state``: an already-collected optimizer state (sharded optimizers gather it collectively first)."""
     os.makedirs(save_dir, exist_ok=True)
     sd = {k: v.detach().cpu().contiguous() for k, v in model.state_dict().items()}
     payload = {
         "model": sd,
-        "optim": optimizer.state_dict() if optimizer is not None else None,
+        "optim": optim_state if optim_state is not None else (optimizer.state_dict() if optimizer is not None else None),
         "flat_names": list(optimizer.flat.names) if optimizer is not None else None,
         "epoch": epoch, "global_step": global_step,
         "rng": torch.random.get_rng_state(),

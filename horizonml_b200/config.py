@@ -37,6 +37,7 @@ class TrainConfig:
     allreduce: str = "auto"           # auto | oneshot | twoshot | nvls | nccl
     bucket_mb: float = 25.0           # DDP-like bucket cap (MiB); reference uses DDP default 25
     overlap: bool = True              # overlap bucket all-reduce with backward
+    zero1: bool = False               # ZeRO-1: shard Adam's moments over the data-parallel group (parallel/zero.py)
     overlap_adam: bool = False        # bucket-wise Adam right behind each bucket's all-reduce (measured: no gain on B200)
     bucket_by_live: bool = False      # with dead-tap elision, size buckets by LIVE elements using live_bucket_mb
     live_bucket_mb: float = 2.0       # (fp32 MiB of live gradient per bucket; the last bucket's collective is exposed)
@@ -103,6 +104,7 @@ def add_train_flags(p: argparse.ArgumentParser, strategy: str) -> argparse.Argum
     g.add_argument('--bucket_mb', type=float, default=d.bucket_mb)
     g.add_argument('--no_overlap', dest='overlap', action='store_false')
     g.add_argument('--overlap_adam', action='store_true')
+    g.add_argument('--zero1', action='store_true', help='shard the optimizer state over the data-parallel ranks')
     g.add_argument('--bucket_by_live', action='store_true')
     g.add_argument('--live_bucket_mb', type=float, default=d.live_bucket_mb)
     g.add_argument('--microbatches', type=int, default=d.microbatches)

@@ -39,7 +39,8 @@ def _round_up(x: int, a: int) -> int:
 class FlatParams:
     def __init__(self, named_params: Sequence[Tuple[str, nn.Parameter]], device, compute_dtype,
                  bucket_cap_mb: float = 25.0, reverse: bool = True, first_bucket_mb: float = 1.0,
-                 live_masks: Optional[Dict[str, torch.Tensor]] = None, bucket_by_live: bool = False):
+                 live_masks: Optional[Dict[str, torch.Tensor]] = None, bucket_by_live: bool = False,
+                 pad_multiple: int = ALIGN):
         named = list(named_params)
         order = list(reversed(named)) if reverse else named
         self.names = [n for n, _ in order]
@@ -49,7 +50,8 @@ class FlatParams:
             offs.append(cur)
             cur = _round_up(cur + p.numel(), ALIGN)
         self.offsets = offs
-        self.total = max(cur, ALIGN)
+        # pad_multiple = 64 * world lets an optimizer shard the flat buffers evenly (parallel/zero.py)
+        self.total = max(_round_up(cur, max(pad_multiple, ALIGN)), ALIGN)
         self.device = torch.device(device)
         self.compute_dtype = compute_dtype
         self.master = torch.zeros(self.total, dtype=torch.float32, device=self.device)

@@ -51,23 +51,31 @@ class DPEngine:
         self.model.train()
         live = self.model.live_tap_masks(32) if (cfg.skip_dead_taps and hasattr(self.model, "live_tap_masks")) else None
         by_live = live is not None and (bool(cfg.bucket_by_live) or os.environ.get("HZ_BUCKET_LIVE", "0") == "1")
+        self.zero1 = bool(cfg.zero1) and rt.world > 1
         self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype,
-                               cfg.live_bucket_mb if by_live else cfg.bucket_mb, live_masks=live, bucket_by_live=by_live)
+                               cfg.live_bucket_mb if by_live else cfg.bucket_mb, live_masks=live, bucket_by_live=by_live,
+                               pad_multiple=64 * rt.world if self.zero1 else 64)
         if rt.world > 1:   # K1: make replicas identical (same seed already does; belt and braces)
             dist.broadcast(self.flat.master, src=0)
             for b in self.model.buffers():
                 if b.dtype.is_floating_point:
                     dist.broadcast(b, src=0)
             self.flat.sync_shadow()
-        self.opt = FlatAdam(self.flat, lr=cfg.lr)
+        if self.zero1:
+            from ..parallel.zero import ShardedFlatAdam
+            self.opt = ShardedFlatAdam(self.flat, lr=cfg.lr)      # reduce-scatter + sharded Adam + all-gather
+        else:
+            self.opt = FlatAdam(self.flat, lr=cfg.lr)
         kind = cfg.allreduce
-        self.ar = make_grad_allreduce(kind, self.flat.total, dev) if rt.world > 1 else None
+        self.ar = make_grad_allreduce(kind, self.flat.total, dev) if (rt.world > 1 and not self.zero1) else None
         self.stats = DeviceStats(dev)
         ops.enable_side_stream(dev.type == "cuda" and rt.backend == "native")
-        self.prev_grad = torch.zeros_like(self.flat.grad) if cfg.grad_divergence else None
+        self.prev_grad = None
+        if cfg.grad_divergence:
+            self.prev_grad = torch.zeros_like(self.opt.gshard if self.zero1 else self.flat.grad)
         # bucket-wise optimizer: Adam for a bucket runs right behind that bucket's all-reduce (or, on one GPU, as
         # soon as its gradients are final) and overlaps the rest of backward
-        self.bucket_adam = bool(cfg.overlap_adam) or os.environ.get("HZ_OVERLAP_ADAM", "0") == "1"
+        self.bucket_adam = (bool(cfg.overlap_adam) or os.environ.get("HZ_OVERLAP_ADAM", "0") == "1") and not self.zero1
         self._diff_acc = torch.zeros((), dtype=torch.float32, device=dev) if self.prev_grad is not None else None
         self.reducer = None
         if self.ar is not None or self.bucket_adam:
@@ -111,6 +119,8 @@ class DPEngine:
     def _state_tensors(self) -> List[torch.Tensor]:
         ts = [self.flat.master, self.flat.grad, self.opt.m, self.opt.v, self.opt.step_t, self.stats.buf,
               self.stats.has_prev]
+        if self.zero1:
+            ts.append(self.opt.gshard)
         if self.flat.shadow is not None:
             ts.append(self.flat.shadow)
         if self.prev_grad is not None:
@@ -341,9 +351,12 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
                   f"Time: {epoch_time:.2f}s", flush=True)
         if cfg.profile and epoch == start_epoch and nsteps > 0:
             profile_steps(eng.step, x, y, f"{logs_dir}/profile_rank{rank}.json")
-        if cfg.save_dir and rank == 0 and (
-                (cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
-            checkpoint.save(cfg.save_dir, "dp", eng.model, eng.opt, epoch + 1, eng.global_step)
+        if cfg.save_dir and ((cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
+            # ZeRO-1: the moments are sharded — every rank takes part in gathering them, rank 0 writes the file
+            optim_state = eng.opt.gather_state() if eng.zero1 else None
+            if rank == 0:
+                checkpoint.save(cfg.save_dir, "dp", eng.model, eng.opt, epoch + 1, eng.global_step,
+                                optim_state=optim_state)
         if world > 1:
             dist.barrier()
     df = rec.frame()

@@ -84,6 +84,41 @@ def dp_equivalence(rank, world, out_dir):
     assert red.bytes_last_step == flat.total * 4
 
 
+def zero1_equivalence(rank, world, out_dir):
+    """ZeRO-1 (reduce-scatter → sharded Adam → all-gather) == replicated Adam after all-reduce, step for step."""
+    from horizonml_b200 import ops
+    from horizonml_b200.config import TrainConfig
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.dp import DPEngine
+    ops.set_backend("torch")
+    rt = Runtime(rank, world, torch.device("cpu"), torch.float32, "torch", "gloo")
+    x, y = _batch(8, seed=20 + rank)                      # a different shard per rank
+    res = []
+    for zero in (False, True):
+        cfg = TrainConfig(strategy="data", world_size=world, device="cpu", dtype="fp32", backend="torch", quiet=True,
+                          zero1=zero, seed=9, allreduce="nccl")
+        eng = DPEngine(cfg, rt)
+        assert eng.zero1 == zero
+        if zero:
+            assert eng.opt.m.numel() * world == eng.flat.total and eng.ar is None     # moments are 1/W of the model
+        for _ in range(3):
+            eng.step(x, y)
+        s = eng.stats.read_and_reset()
+        n = eng.flat.numel()
+        full = eng.opt.gather_state() if zero else eng.opt.state_dict()
+        res.append((eng.flat.master.clone(), full["m"], s["loss_sum"], s["grad_div_sum"], float(full["step"])))
+    a, b = res
+    lim = min(a[0].numel(), b[0].numel())                 # the sharded store is padded to a multiple of 64*W
+    assert a[4] == b[4] == 3.0
+    assert torch.allclose(a[0][:lim], b[0][:lim], rtol=1e-5, atol=1e-7), (a[0][:lim] - b[0][:lim]).abs().max()
+    assert torch.allclose(a[1][:lim], b[1][:lim], rtol=1e-5, atol=1e-8)
+    assert abs(a[2] - b[2]) < 1e-4 and abs(a[3] - b[3]) <= 1e-3 * max(abs(a[3]), 1e-12)
+    # every rank holds the same parameters after the all-gather
+    ref = eng.flat.master.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(ref, eng.flat.master)
+
+
 def pp_equivalence(rank, world, out_dir):
     """1F1B over `world` stages with M micro-batches == single-process micro-batched gradients."""
     from horizonml_b200 import ops
