@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of step-level optimisations on ONE GPU (each variant in its own process: the switches are read once).
+# A/B of step-level switches on ONE GPU (each variant in its own process: the switches are read once).
 # Usage: tools/ab_step.sh  -> gpurun_out/ab_step.txt
 mkdir -p gpurun_out
 OUT=gpurun_out/ab_step.txt
@@ -12,9 +12,11 @@ run() {  # name, env..., -- bench args
   line=$(env "${envs[@]}" timeout 200 python bench.py --steps 200 --warmup 20 "$@" 2>gpurun_out/ab_err_$name.log | tail -1)
   echo "$name $(echo "$line" | python -c 'import sys,json
 try:
-    d=json.loads(sys.stdin.read()); print("ms_per_step=%.4f img_s=%.0f e2e=%.0f b2b=%.4f launches=%s buckets=%s sm=%s loss=%s" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["back_to_back_ms_per_step"], d["launches_per_step"], d["config"].get("buckets"), d["clocks"]["sm_mhz"], d.get("last_step_loss")))
+    d=json.loads(sys.stdin.read()); print("ms_per_step=%.4f img_s=%.0f e2e=%.0f b2b=%.4f launches=%s sm=%s loss=%s" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["back_to_back_ms_per_step"], d["launches_per_step"], d["clocks"]["sm_mhz"], d.get("last_step_loss")))
 except Exception as e:
     print("FAILED", e)')" | tee -a $OUT
 }
 run default      --
-run bnbwd_2k     HZ_BN_BWD_FUSED=0 --
+run mink10       HZ_CLUSTER_MIN_K=10 --
+run mink16       HZ_CLUSTER_MIN_K=16 --
+run mink4        HZ_CLUSTER_MIN_K=4 --
