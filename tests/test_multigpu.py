@@ -47,3 +47,16 @@ def test_trainers_converge_on_gpus(tmp_path, script, ws):
     df = pd.read_csv(tmp_path / "combined_results_4096.csv")
     last = df[(df["worker"] == ws - 1) & (df["epoch"] == 2)]
     assert float(last["loss"].iloc[0]) < 0.5 and float(last["accuracy"].iloc[0]) > 85.0
+
+
+def test_hybrid_mesh_on_gpus(tmp_path):
+    """DP x PP process mesh on GPUs: 2 replicas x (GPUs/2)-stage pipeline, fused peer all-reduce over the DP sub-group."""
+    import pandas as pd
+    ws = 4 if _ngpu() >= 4 else 2
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "hybrid_parallel_train.py"), "--world_size", str(ws),
+                        "--dp_replicas", "2", "--inner", "layer", "--epochs", "2", "--sample_size", "8192",
+                        "--logs_dir", str(tmp_path)], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    df = pd.read_csv(tmp_path / "combined_results_8192.csv")
+    last = df[(df["worker"] == ws - 1) & (df["epoch"] == 2)]
+    assert float(last["loss"].iloc[0]) < 0.5 and float(last["accuracy"].iloc[0]) > 85.0
