@@ -138,15 +138,59 @@ def generate_comparison_graphs(results, output_dir: str = "benchmark_results") -
         written[name + "_csv"] = p
     with open(os.path.join(output_dir, "benchmark_summary.json"), "w") as fh:
         json.dump({"bars": summ["bars"], "radar": radar}, fh, indent=1)
+    _draw_svg(summ, radar, output_dir, written)
     try:
         import matplotlib
         matplotlib.use("Agg")
         import matplotlib.pyplot as plt
     except Exception:
-        print("matplotlib not available: wrote CSV/JSON summaries only")
+        print("matplotlib not available: wrote CSV/JSON summaries and SVG figures")
         return written
     _draw_all(plt, curves, bars, radar, output_dir, written)
     return written
+
+
+def _draw_svg(summ: Dict, radar: Dict, out: str, written: Dict[str, str]) -> None:
+    """The reference's eight figures (main.py:64-390) as SVG, with no plotting dependency."""
+    from . import svgplot
+
+    def save(name, svg):
+        p = os.path.join(out, f"{name}_comparison.svg")
+        with open(p, "w") as fh:
+            fh.write(svg)
+        written[name + "_svg"] = p
+
+    curves, bars = summ["curves"], summ["bars"]
+    for metric, ylabel in (("accuracy", "Accuracy (%)"), ("loss", "Loss")):
+        series: Dict[str, list] = {}
+        for c in curves:
+            series.setdefault(f"{LABEL[c['strategy']]} ({c['sample_size']} samples)", []).append((c["epoch"], c[metric]))
+        save(metric, svgplot.line_chart(series, f"{ylabel} Comparison", "Epoch", ylabel))
+    sizes = sorted({b["sample_size"] for b in bars})
+    strategies = [s for s in STRATEGIES if any(b["strategy"] == s for b in bars)]
+
+    def val(s, n, col):
+        for b in bars:
+            if b["strategy"] == s and b["sample_size"] == n:
+                return float(b[col])
+        return 0.0
+
+    for name, col, ylabel in (("training_time", "epoch_time", "Average Epoch Time (s)"),
+                              ("cpu_utilization", "avg_cpu", "CPU Utilization (%)"),
+                              ("memory_usage", "avg_memory", "Memory Usage (MB)"),
+                              ("idle_time", "idle_time", "Idle Time (s)")):
+        series = {LABEL[s]: [val(s, n, col) for n in sizes] for s in strategies}
+        save(name, svgplot.grouped_bars([str(n) for n in sizes], series, ylabel, "Sample size", ylabel))
+    short = {"data_parallel": "DP", "model_parallel": "MP", "tensor_parallel": "TP"}
+    groups = [f"{short[s]} {n}" for n in sizes for s in strategies]
+    series = {"Compute": [val(s, n, "compute_time") for n in sizes for s in strategies],
+              "Communication": [val(s, n, "comm_time") for n in sizes for s in strategies]}
+    save("compute_vs_comm", svgplot.grouped_bars(groups, series, "Compute vs Communication Time",
+                                                 "Strategy (DP data / MP model / TP tensor parallel) and sample size",
+                                                 "Time (s, cumulative)", stacked=True))
+    if radar:
+        save("overall_performance", svgplot.radar({LABEL[s]: sc for s, sc in radar.items()},
+                                                  f"Overall Performance ({sizes[-1]} samples)" if sizes else "Overall"))
 
 
 def _draw_all(plt, curves, bars, radar, out, written):  # pragma: no cover - needs matplotlib

@@ -139,6 +139,11 @@ def test_main_benchmark_sweep_cpu(tmp_path):
     summ = __import__("json").load(open(tmp_path / "out" / "benchmark_summary.json"))
     assert {b["strategy"] for b in summ["bars"]} == {"data_parallel", "model_parallel", "tensor_parallel"}
     assert os.path.exists(tmp_path / "out" / "overall_performance_comparison.csv")
+    for fig in ("accuracy", "loss", "training_time", "compute_vs_comm", "cpu_utilization", "memory_usage", "idle_time",
+                "overall_performance"):        # the reference's eight figures, drawn without matplotlib
+        svg = open(tmp_path / "out" / f"{fig}_comparison.svg").read()
+        assert svg.startswith("<svg") and svg.rstrip().endswith("</svg>")
+        assert ("Data Parallel" in svg) or fig == "compute_vs_comm"
     # analyze_results.py: the same reports rebuilt offline from the logs the sweep left behind
     from horizonml_b200.bench_suite import analyze_main, load_results
     again = load_results(None, str(tmp_path))
