@@ -5,9 +5,9 @@ Same programme: for every sample size run data-parallel, layer-parallel, tensor-
 then emit the eight comparison artefacts (accuracy, loss, training time, compute-vs-comm, CPU,
 memory, idle, overall radar).  Differences: the real ``world_size`` is used to pick the
 last pipeline rank (the reference hard-codes 5), a failed strategy degrades gracefully instead of
-crashing, and because matplotlib/seaborn are optional the numbers behind every figure are always
-written as ``*_comparison.csv`` + ``benchmark_summary.json``; PNGs are drawn only when matplotlib
-imports.
+crashing, and because matplotlib/seaborn are optional the figures are always drawn as
+``*_comparison.svg`` by the built-in renderer (``svgplot.py``) next to the numbers behind them
+(``*_comparison.csv`` + ``benchmark_summary.json``); PNGs are drawn as well when matplotlib imports.
 """
 from __future__ import annotations
 
