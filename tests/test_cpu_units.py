@@ -409,3 +409,43 @@ def test_dp_engine_bucketwise_adam_equals_whole_adam():
     assert a[2] == b[2] == 3.0
     assert torch.allclose(a[0], b[0], rtol=1e-6, atol=1e-8) and torch.allclose(a[1], b[1], rtol=1e-6, atol=1e-9)
     assert abs(a[3] - b[3]) < 1e-5 and abs(a[4] - b[4]) <= 1e-4 * max(abs(a[4]), 1e-12)
+
+
+def test_svgplot_figures_are_wellformed_xml():
+    import xml.etree.ElementTree as ET
+    from horizonml_b200 import svgplot
+    figs = [
+        svgplot.line_chart({"Data Parallel (1000 samples)": [(1, 2.0), (2, 1.0), (3, 0.5)], "b & <c>": [(1, 3.0)]},
+                           "Loss Comparison", "Epoch", "Loss"),
+        svgplot.line_chart({}, "empty", "x", "y"),
+        svgplot.grouped_bars(["1000", "10000"], {"Data Parallel": [1.0, 9.5], "Tensor Parallel": [2.0, 20.0]},
+                             "Average Epoch Time (s)", "Sample size", "s"),
+        svgplot.grouped_bars(["DP 1000", "TP 1000"], {"Compute": [1.0, 2.0], "Communication": [0.5, 4.0]},
+                             "Compute vs Communication", "x", "s", stacked=True),
+        svgplot.radar({"Data Parallel": {"Accuracy": 1.0, "Training Speed": 0.3, "Idle Time": 0.0},
+                       "Model Parallel": {"Accuracy": 0.5, "Training Speed": 1.2, "Idle Time": -0.1}}, "Overall"),
+    ]
+    for svg in figs:
+        root = ET.fromstring(svg)                       # raises on malformed XML (escaping of & < > included)
+        assert root.tag.endswith("svg") and "nan" not in svg
+
+
+def test_sharded_adam_single_process_matches_flat_adam():
+    """ZeRO-1 optimizer with a world of one == FlatAdam (no collectives involved)."""
+    from horizonml_b200.parallel.zero import ShardedFlatAdam
+    outs = []
+    for sharded in (False, True):
+        m = resnet18(10, seed=3).train()
+        flat = FlatParams(list(m.named_parameters()), "cpu", torch.float32)
+        opt = ShardedFlatAdam(flat, lr=1e-3) if sharded else FlatAdam(flat, lr=1e-3)
+        gen = torch.Generator().manual_seed(1)
+        prev = torch.zeros_like(flat.grad)
+        d = None
+        for _ in range(2):
+            flat.grad.copy_(torch.randn(flat.total, generator=gen) * 0.01)
+            d = opt.step(prev_grad=prev)
+        outs.append((flat.master.clone(), float(d)))
+        assert float(flat.grad.abs().max()) == 0.0
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-8) and abs(outs[0][1] - outs[1][1]) < 1e-6 * outs[0][1]
+    sd = opt.state_dict()
+    assert sd["m"].numel() == flat.total and float(sd["step"]) == 2.0
