@@ -194,6 +194,17 @@ def adam_step(master, grad, m, v, shadow, step_t, lr: float, b1: float, b2: floa
         else:
             diff = (d * d).sum()
         prev.copy_(grad)
+    if (master.device.type == "cpu" and grad_scale == 1.0 and master.dtype == torch.float32
+            and hasattr(torch, "_fused_adam_")):
+        # CPU path (BASELINE config #1, tests): ATen's vectorised multi-threaded fused Adam — one pass over the flat
+        # buffers instead of eight elementwise passes (11 M parameters: 2.7 ms vs 42 ms)
+        torch._fused_adam_([master], [grad], [m], [v], [], [step_t.view(())], lr=lr, beta1=b1, beta2=b2,
+                           weight_decay=0.0, eps=eps, amsgrad=False, maximize=False)
+        if shadow is not None:
+            shadow.copy_(master)
+        if zero_grad:
+            grad.zero_()
+        return diff
     g = grad if grad_scale == 1.0 else grad * grad_scale
     m.mul_(b1).add_(g, alpha=1 - b1)
     v.mul_(b2).addcmul_(g, g, value=1 - b2)

@@ -61,21 +61,18 @@ class ShardedFlatAdam:
             else:
                 dist.all_reduce(f.grad, op=dist.ReduceOp.SUM, group=self.group)
                 self.gshard.copy_(f.grad[self.lo:self.hi])
-            g = self.gshard
+            g = self.gshard.mul_(1.0 / W)            # average (the replicated path folds 1/W into its all-reduce)
         else:
             g = f.grad
         sl = slice(self.lo, self.hi)
         diff = ops.adam_step(f.master[sl], g, self.m, self.v, f.shadow[sl] if f.shadow is not None else None,
-                             self.step_t, self.lr, self.betas[0], self.betas[1], self.eps, grad_scale / W, prev_grad,
+                             self.step_t, self.lr, self.betas[0], self.betas[1], self.eps, grad_scale, prev_grad,
                              False, live_blocks=self.live)
         if W > 1:
             self._gather_src.copy_(f.master[sl])
             dist.all_gather_into_tensor(f.master, self._gather_src, group=self.group)
             f.sync_shadow()
-            if diff is not None:
-                # the kernel takes Σ(g−prev)² on the raw reduce-scattered SUM (prev holds sums too): 1/W² turns it into
-                # the metric of the averaged gradient; then add the shards
-                diff.mul_(1.0 / (W * W))
+            if diff is not None:                     # Σ(g−prev)² of this shard → of the whole gradient
                 dist.all_reduce(diff, op=dist.ReduceOp.SUM, group=self.group)
         f.grad.zero_()
         return diff
