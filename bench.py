@@ -177,7 +177,7 @@ def run_ours(args):
         "vs_baseline": round(value / BASELINE_IMG_S, 1), "dtype": "bf16", "data": "synthetic",
         "impl": "ours" if args.impl == "ours" else "torch-backend",
         "config": {"model": "resnet18(num_classes=10)", "global_batch": B * world, "per_gpu_batch": B,
-                   "image": "32x32x3", "optimizer": "Adam(lr=1e-3)", "parallelism": f"dp{world}",
+                   "seq_len": None, "image": "32x32x3", "optimizer": "Adam(lr=1e-3)", "parallelism": f"dp{world}",
                    "backend": rt.backend, "allreduce": getattr(eng.ar, "name", None) if eng.ar else None,
                    "cuda_graph": graphed, "grad_divergence_metric": cfg.grad_divergence,
                    "bucket_mb": cfg.bucket_mb, "live_bucket_mb": cfg.live_bucket_mb, "buckets": len(eng.flat.buckets), "bucketwise_adam": eng.bucket_adam,
