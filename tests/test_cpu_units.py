@@ -449,3 +449,29 @@ def test_sharded_adam_single_process_matches_flat_adam():
     assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-8) and abs(outs[0][1] - outs[1][1]) < 1e-6 * outs[0][1]
     sd = opt.state_dict()
     assert sd["m"].numel() == flat.total and float(sd["step"]) == 2.0
+
+
+def test_real_cifar_batches_reader(tmp_path):
+    """--real_data path: CIFAR-10 'python version' pickles (the files torchvision.datasets.CIFAR10 downloads in the
+    reference, data_parallel_train.py:49-57) → uint8 NHWC images + int64 labels, seeded subset."""
+    import pickle
+    from horizonml_b200.data import CIFAR10Files, build_dataset
+    base = tmp_path / "cifar-10-batches-py"
+    base.mkdir()
+    rng = np.random.default_rng(0)
+    allx, ally = [], []
+    for i in range(1, 6):
+        x = rng.integers(0, 256, size=(20, 3072), dtype=np.uint8)
+        y = rng.integers(0, 10, size=20).tolist()
+        with open(base / f"data_batch_{i}", "wb") as fh:
+            pickle.dump({"data": x, "labels": y}, fh)
+        allx.append(x); ally += y
+    ds = CIFAR10Files(str(tmp_path))
+    assert len(ds) == 100 and ds.images.shape == (100, 32, 32, 3) and ds.images.dtype == np.uint8
+    x0 = np.concatenate(allx)[7].reshape(3, 32, 32)                       # stored planar CHW → delivered HWC
+    assert np.array_equal(ds.images[7], x0.transpose(1, 2, 0)) and ds.labels[7] == ally[7]
+    a = build_dataset(30, False, str(tmp_path), seed=5)
+    b = build_dataset(30, False, str(tmp_path), seed=5)
+    assert a[0].shape == (30, 32, 32, 3) and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    with pytest.raises(FileNotFoundError):
+        CIFAR10Files(str(tmp_path / "nowhere"))
