@@ -46,13 +46,39 @@ class P2P:
             self.prev, self.next = peers
         self.bytes_sent = 0
         self._keep: List = []
+        self.timing = False          # trainers switch this on: per-exchange spans, resolved once per epoch
+        self._spans: List = []
 
     def _run(self, ops_: List[dist.P2POp]):
         if not ops_:
             return
+        t0 = self._clock() if self.timing else None
         reqs = dist.batch_isend_irecv(ops_)
         for r in reqs:
             r.wait()
+        if t0 is not None:
+            self._spans.append((t0, self._clock()))
+
+    @staticmethod
+    def _clock():
+        """A CUDA event on the compute stream (which ``req.wait()`` blocks behind the transfer) or the host clock:
+        the span is the time this stage's compute stream is held up by the exchange — exposed p2p time."""
+        if torch.cuda.is_available() and dist.get_backend() == "nccl":
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        import time
+        return time.perf_counter()
+
+    def take_time_ms(self) -> float:
+        """Σ of the exchange spans since the last call (synchronises the device once: call at epoch end)."""
+        spans, self._spans = self._spans, []
+        if not spans:
+            return 0.0
+        if not isinstance(spans[0][0], float):
+            torch.cuda.synchronize()
+            return float(sum(a.elapsed_time(b) for a, b in spans))
+        return float(sum(b - a for a, b in spans) * 1e3)
 
     def _send(self, t, peer):
         self.bytes_sent += t.numel() * t.element_size()

@@ -187,6 +187,7 @@ def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         sampler = ShardedSampler(len(labels), mesh.dp, mesh.coord.dp, shuffle=False, seed=cfg.seed)
     loader = BatchLoader(images, labels, cfg.batch_size, rt.device, sampler=sampler)
     eng = PPEngine(cfg, rt, mesh)
+    eng.runner.p2p.timing = bool(cfg.region_probe)
     stages = mesh.pp if mesh is not None else world
     rec = EpochRecorder("layer", rank, logs_dir, cfg.sample_size)
     hb = Heartbeat(cfg.heartbeat_dir, rank)
@@ -252,6 +253,11 @@ def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
                "nvlink_GBps": sent_total / dev_s_max / 1e9 if dev_s_max > 0 else 0}
         if cuda:
             step_times = [dev_s / steps] * nsteps
+        if cfg.region_probe:
+            # time per step this stage's compute stream is blocked behind activation / gradient exchanges (includes
+            # the pipeline bubble, like the reference's blocking send/recv "comm_time", layer_…:188-195,209)
+            ext["p2p_ms"] = eng.runner.p2p.take_time_ms() / steps
+            ext["exposed_comm_ms"] = ext["p2p_ms"]
         rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times,
                       avg_bandwidth=sent_total / steps, ext=ext)
         if eng.is_last and saver and not cfg.quiet:

@@ -66,6 +66,7 @@ def test_entrypoints_world2_cpu(tmp_path, runner, strategy, ws):
     if strategy == "layer":                                             # non-last stages write 0 (reference)
         assert (df[df["worker"] == 0]["loss"] == 0).all()
         assert (df["avg_bandwidth"] > 0).any()
+        assert (df["p2p_ms"] > 0).all()                                 # exposed exchange time per step, every stage
 
 
 @pytest.mark.parametrize("inner", ["layer", "tensor"])
