@@ -44,6 +44,45 @@ def setup_runtime(rank: int, world: int, cfg: TrainConfig, device: str) -> Runti
     return Runtime(rank, world, dev, dtype, backend, comm_backend)
 
 
+class _NullRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL_RANGE = _NullRange()
+_NVTX = os.environ.get("HZ_NVTX", "0") == "1"
+
+
+class _NvtxRange:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *a):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
+def nvtx_range(name: str):
+    """``with nvtx_range("forward"):`` — an NVTX range around a region of the step when ``HZ_NVTX=1`` (or ``--profile``
+    sets it) on a CUDA box, for nsys / ncu ``--nvtx`` filtering; otherwise a shared no-op object, so the
+    hot path pays one attribute lookup."""
+    if _NVTX and torch.cuda.is_available():
+        return _NvtxRange(name)
+    return _NULL_RANGE
+
+
+def enable_nvtx(flag: bool = True) -> None:
+    global _NVTX
+    _NVTX = bool(flag)
+
+
 class DeviceStats:
     """On-device accumulators: no ``.item()`` in the step loop (the reference syncs three times per
     step: data_parallel_train.py:126,130,140)."""

@@ -29,7 +29,7 @@ from ..models.resnet import resnet18
 from ..parallel.comm import make_grad_allreduce
 from ..parallel.dp import GradReducer
 from .common import (DeviceStats, FaultInjector, GraphedStep, Heartbeat, Runtime, allreduce_max_scalar,
-                     gpu_mem_mb, profile_steps, setup_runtime)
+                     enable_nvtx, gpu_mem_mb, nvtx_range, profile_steps, setup_runtime)
 
 
 def build_model(cfg: TrainConfig, device, class_pad_to: int = 1):
@@ -97,15 +97,19 @@ class DPEngine:
         self.flat.begin_step()
         if self.reducer is not None:
             self.reducer.begin_step()
-        loss, correct = self.model.forward_loss(x, labels)
-        ops.backward(loss)
-        ops.join_side()
-        if self.reducer is not None:
-            self.reducer.finish()
-        if self.bucket_adam:
-            diff = self._diff_acc          # every bucket's Adam has been joined by reducer.finish()
-        else:
-            diff = self.opt.step(prev_grad=self.prev_grad)
+        with nvtx_range("forward"):
+            loss, correct = self.model.forward_loss(x, labels)
+        with nvtx_range("backward"):
+            ops.backward(loss)
+            ops.join_side()
+        with nvtx_range("allreduce_join"):
+            if self.reducer is not None:
+                self.reducer.finish()
+        with nvtx_range("optimizer"):
+            if self.bucket_adam:
+                diff = self._diff_acc          # every bucket's Adam has been joined by reducer.finish()
+            else:
+                diff = self.opt.step(prev_grad=self.prev_grad)
         self.stats.add_step(loss, correct, labels.shape[0], diff)
         ops.step_end()
 
@@ -242,6 +246,8 @@ class DPEngine:
 def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
     """Per-rank worker (the reference's ``worker`` + ``train``)."""
     rt = setup_runtime(rank, world, cfg, device)
+    if cfg.profile:
+        enable_nvtx(True)                      # --profile: NVTX ranges around forward / backward / collectives / optimizer
     logs_dir = cfg.resolved_logs_dir()
     images, labels = build_dataset(cfg.sample_size, cfg.synthetic, cfg.data_dir, cfg.seed)
     if rank == 0 and not cfg.quiet:
