@@ -475,3 +475,21 @@ def test_real_cifar_batches_reader(tmp_path):
     assert a[0].shape == (30, 32, 32, 3) and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     with pytest.raises(FileNotFoundError):
         CIFAR10Files(str(tmp_path / "nowhere"))
+
+
+def test_host_tiling_logic(tmp_path):
+    """csrc/tests/host_logic_test.cu: tap elimination, stride-2 parity-view addressing and 128-row tiling of the
+    implicit-GEMM convolution, checked against the convolution definition on the host (no GPU, no kernel launch)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_logic_test")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-I",
+                        os.path.join(root, "csrc"), "-o", exe, os.path.join(root, "csrc", "tests", "host_logic_test.cu")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "host tiling logic ok" in r.stdout, r.stdout + r.stderr
