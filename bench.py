@@ -207,9 +207,16 @@ def run_ours(args):
 # ================================================================================================
 def run_reference(args):
     """Unmodified reference (baseline/_ref/data_parallel_train.py) through its own public API
-    ``run_data_parallel(world_size, epochs, sample_size)``: CPU + gloo, its own mp launcher.
-    CIFAR-10 cannot be downloaded here, so torchvision.datasets.CIFAR10 is shimmed with a synthetic
-    dataset of identical shape (tools/ref_shim/sitecustomize.py) — the reference code itself is untouched."""
+    ``run_data_parallel(world_size, epochs, sample_size)``: CPU + gloo, its own mp launcher — the reference has no
+    GPU path (README.md:14), so this arm runs on the box's CPUs whatever ``--gpus`` says; N is its ``world_size``.
+    CIFAR-10 cannot be downloaded here, so torchvision.datasets.CIFAR10 is shimmed with a synthetic dataset of
+    identical shape (tools/ref_shim/sitecustomize.py) — the reference code itself is untouched.
+
+    Bookkeeping mirrors the repo arm: ``sample_size = K·64·N`` makes one reference epoch exactly K steps of
+    batch 64 per worker; epoch 1 is the warm-up (K ≥ W steps), epoch 2 is timed by the reference's own
+    ``epoch_time`` stopwatch (max over workers).  That stopwatch brackets data loading, forward, backward, DDP
+    all-reduce, optimizer step, ``loss.item()`` and the per-step barrier — i.e. it *is* the end-to-end number, so
+    ``e2e`` repeats it (no device, hence zero H2D/D2H bytes)."""
     rank = int(os.environ.get("RANK", 0))
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     script = os.path.join(ref_dir, "data_parallel_train.py")
@@ -221,8 +228,9 @@ def run_reference(args):
         return      # the reference spawns its own world_size workers from one launcher process
     import tempfile
     W, K, Wm, B = args.gpus, args.steps, max(args.warmup, 3), 64
-    # reference step count per epoch = ceil(sample_size / world / 64): epoch 1 = warm-up, epoch 2 = timed
-    steps = max(min(K, 20), Wm)
+    # the reference's launcher kills its workers after max(120, 0.12·sample_size) s and its exit handshake hangs for
+    # 300 s, so very long runs only add waiting: cap the timed steps, never below the warm-up request
+    steps = max(min(K, 50), Wm)
     sample = steps * B * W
     work = tempfile.mkdtemp(prefix="hz_ref_")
     code = (
@@ -230,43 +238,69 @@ def run_reference(args):
         f"sys.path.insert(0, {ref_dir!r})\n"
         "import data_parallel_train as ref\n"
         f"df = ref.run_data_parallel({W}, 2, {sample})\n"
-        "ok = df is not None and len(df) > 0\n"
-        "res = {'ok': bool(ok)}\n"
+        "ok = df is not None and len(df) > 0 and int(df['epoch'].max()) >= 2\n"
+        "res = {'ok': bool(ok), 'rows': 0 if df is None else int(len(df))}\n"
         "if ok:\n"
         "    e2 = df[df['epoch'] == df['epoch'].max()]\n"
         "    res.update(epoch_time=float(e2['epoch_time'].max()), epochs=int(df['epoch'].max()),\n"
-        "               avg_step_time=float(e2['avg_step_time'].max()))\n"
+        "               avg_step_time=float(e2['avg_step_time'].max()), workers=int(e2['worker'].nunique()))\n"
         "print('HZREF ' + json.dumps(res))\n")
     env = dict(os.environ)
     env["PYTHONPATH"] = os.path.join(ROOT, "tools", "ref_shim") + os.pathsep + env.get("PYTHONPATH", "")
-    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE",
-              "TORCHELASTIC_RUN_ID", "ROLE_RANK", "ROLE_WORLD_SIZE"):
-        env.pop(k, None)
+    # not a torchrun child: the reference does its own rendezvous (localhost:<free port>) and spawns its own workers
+    for k in list(env):
+        if k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE",
+                 "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "GROUP_WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS",
+                 "NCCL_ASYNC_ERROR_HANDLING", "TORCH_NCCL_ASYNC_ERROR_HANDLING") or k.startswith("TORCHELASTIC_"):
+            env.pop(k, None)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, ncpu // max(W, 1))          # torchrun exports OMP_NUM_THREADS=1; give every worker its share
+    env["OMP_NUM_THREADS"] = env["MKL_NUM_THREADS"] = str(threads)
+    # gloo picks its interface from the host name, which does not resolve inside the GPU box's container: every pair
+    # connection then times out after 300 s (round 1: "no results" at N >= 2).  Loopback is all a one-node run needs.
+    env.setdefault("GLOO_SOCKET_IFNAME", "lo")
     env["CUDA_VISIBLE_DEVICES"] = ""     # the reference is CPU-only (README.md:14)
     t0 = time.time()
     try:
-        r = subprocess.run([sys.executable, "-c", code], cwd=work, env=env, capture_output=True, text=True, timeout=1500)
-    except subprocess.TimeoutExpired:
-        print(json.dumps({"impl": "reference", "unavailable": "reference run exceeded 1500 s"}))
+        r = subprocess.run([sys.executable, "-c", code], cwd=work, env=env, capture_output=True, text=True, timeout=840)
+    except subprocess.TimeoutExpired as ex:
+        tail = ((ex.stdout or b"")[-600:] if isinstance(ex.stdout, bytes) else (ex.stdout or "")[-600:])
+        print(json.dumps({"impl": "reference", "unavailable": "reference run exceeded 840 s: " + str(tail).replace("\n", " | ")}))
         return
     res = None
     for ln in r.stdout.splitlines():
         if ln.startswith("HZREF "):
             res = json.loads(ln[6:])
     if not res or not res.get("ok"):
-        print(json.dumps({"impl": "reference", "unavailable": "reference run produced no results: " +
-                          (r.stderr[-300:] if r.stderr else "no stderr").replace("\n", " ")}))
+        # keep the workers' own words: what they printed last and the tail of stderr
+        keep = [ln for ln in r.stdout.splitlines() if ("xception" in ln or "rror" in ln or "Could not" in ln)][-6:]
+        diag = " | ".join(keep + [r.stderr[-500:].replace("\n", " | ") if r.stderr else "no stderr"])
+        sys.stderr.write("---- reference stdout tail ----\n" + r.stdout[-3000:] + "\n---- reference stderr tail ----\n" +
+                         (r.stderr[-3000:] if r.stderr else "") + "\n")
+        print(json.dumps({"impl": "reference", "unavailable": f"reference run produced no epoch-2 results (rc={r.returncode}, "
+                          f"{time.time() - t0:.0f} s): {diag}"[:1500]}))
         return
     value = sample / res["epoch_time"]
+    ms = res["epoch_time"] * 1e3 / steps
     print(json.dumps({
         "metric": "ResNet-18 CIFAR-shape images/sec (whole box, max over ranks)", "impl": "reference",
-        "value": round(value, 1), "unit": "images/s", "n_gpus": W, "steps": steps, "warmup": steps,
-        "ms_per_step": round(res["epoch_time"] * 1e3 / steps, 3), "higher_is_better": True, "scaling": "weak",
+        "value": round(value, 1), "unit": "images/s", "n_gpus": W, "steps": steps, "warmup": Wm,
+        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": round(value / BASELINE_IMG_S, 2), "dtype": "fp32", "data": "synthetic",
-        "config": {"model": "torchvision resnet18 (fc->10)", "global_batch": B * W, "seq_len": None,
-                   "parallelism": f"dp{W} (DDP/gloo, CPU processes; the reference has no GPU path)",
-                   "note": "epoch 2 of run_data_parallel(world_size, 2, sample_size); host-timed by the reference itself",
-                   "total_wall_s": round(time.time() - t0, 1)}}))
+        "config": {"model": "resnet18(num_classes=10)", "global_batch": B * W, "per_gpu_batch": B, "seq_len": None,
+                   "image": "32x32x3", "optimizer": "Adam(lr=1e-3)", "parallelism": f"dp{W}",
+                   "backend": "reference: torchvision resnet18 + DDP/gloo on CPU processes (it has no GPU path, "
+                              "README.md:14); dtype fp32 is the only one it supports",
+                   "warmup_steps_run": steps, "requested_steps": K, "workers": res.get("workers"),
+                   "omp_threads_per_worker": threads,
+                   "note": "epoch 2 of run_data_parallel(world_size, 2, steps*64*world_size), timed by the reference's "
+                           "own per-epoch stopwatch (max over workers); epoch 1 is the warm-up",
+                   "total_wall_s": round(time.time() - t0, 1)},
+        "e2e": {"value": round(value, 1), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "ms_per_step": round(ms, 3),
+                "note": "the reference's epoch stopwatch already brackets data loading, forward, backward, all-reduce, "
+                        "optimizer, loss.item() and the step barrier on the CPU: there is no device copy to add"},
+        "gpu_launches": 0}))
 
 
 def main():

@@ -4,6 +4,10 @@
 #include <pybind11/stl.h>
 #include <torch/extension.h>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <string>
 #include <vector>
 
@@ -332,33 +336,8 @@ class PeerComm {
     auto opts = at::TensorOptions().dtype(dt).device(at::kCUDA, device_);
     return at::from_blob(base + offset, sizes, strides, opts);
   }
-  // fused tcgen05 GEMM + collective (csrc/tp_fused.cu).  All offsets are byte offsets into the symmetric heap.
-  void tp_conv(int64_t kind, int64_t x_off, c10::optional<Tensor> x_local, const Tensor& w, int64_t out_off,
-               int64_t ws_off, int64_t ws_stride, int64_t flags_off, int64_t tiles, std::vector<int64_t> x_shape,
-               int64_t Cout,
-               int64_t R, int64_t pad, int64_t reduce, bool bcast, bool ag) {
-    c10::cuda::CUDAGuard g(w.device());
-    const int N = (int)x_shape[0], Ca = (int)x_shape[1], H = (int)x_shape[2], Wd = (int)x_shape[3];
-    const void* xp[8];
-    char* heaps[8];
-    for (int r = 0; r < world_; ++r) {
-      heaps[r] = hz_comm_heap_base(c_, r);
-      TORCH_CHECK(heaps[r] != nullptr, "peer heap not mapped");
-      xp[r] = ag ? (const void*)(heaps[r] + x_off) : nullptr;
-    }
-    if (!ag) { TORCH_CHECK(x_local.has_value()); xp[rank_] = x_local->data_ptr(); }
-    // flags block: [arrive tiles*W][result tiles][ready W][epoch][done]
-    const long long arrive_off = flags_off;
-    const long long result_off = arrive_off + 4LL * tiles * world_;
-    const long long ready_off = result_off + 4LL * tiles;
-    const long long epoch_off = ready_off + 4LL * world_;
-    unsigned* epoch = reinterpret_cast<unsigned*>(heaps[rank_] + epoch_off);
-    const int Cin = kind == 0 ? Ca : (int)Cout, Co = kind == 0 ? (int)Cout : Ca;
-    int rc = hz_tp_conv((int)kind, xp, w.data_ptr(), heaps, out_off, ws_off, ws_stride, arrive_off, result_off, ready_off, epoch,
-                        epoch + 1, world_, rank_, (int)reduce, bcast ? 1 : 0, ag ? 1 : 0, N, H, Wd, Cin, Co, (int)R,
-                        (int)pad, cur_stream());
-    TORCH_CHECK(rc == 0, "hz_tp_conv failed rc=", rc);
-  }
+  // base address of rank r's symmetric heap as mapped in this process (0 when not mapped)
+  int64_t heap_ptr(int64_t r) { return (int64_t)(uintptr_t)hz_comm_heap_base(c_, (int)r); }
   ~PeerComm() { hz_comm_destroy(c_); }
   py::bytes export_handles() {
     char h[64];
@@ -408,10 +387,133 @@ class PeerComm {
   int rank_, world_, device_;
 };
 
+
+// ------------------------------------------------------------------ fused tensor-parallel ops (csrc/tp_fused.cu)
+// `heaps`: base address of every rank's symmetric heap as mapped in this process; `mc`: multicast mapping or 0.
+// All *_off arguments are byte offsets into the heap.  ctrl_off: u32 [epoch, done] of this op.
+struct HeapPtrs { char* h[8]; };
+HeapPtrs heap_ptrs(const std::vector<int64_t>& heaps) {
+  TORCH_CHECK(heaps.size() >= 1 && heaps.size() <= 8, "1..8 tensor-parallel ranks");
+  HeapPtrs o{};
+  for (size_t i = 0; i < heaps.size(); ++i) { TORCH_CHECK(heaps[i] != 0, "peer heap not mapped"); o.h[i] = (char*)(uintptr_t)heaps[i]; }
+  return o;
+}
+
+int64_t tp_tiles(int64_t kind, std::vector<int64_t> x_shape, int64_t Cout, int64_t stride) {
+  return hz_tp_tiles((int)kind, (int)x_shape[0], (int)x_shape[2], (int)x_shape[3], (int)x_shape[1], (int)Cout, (int)stride);
+}
+
+// kind 0: out[N,Cout,H,W] = reduce_r conv(a_r[N,Cin,H,W], w_r[Cout,Cin,R,R]) (stride 1)
+// kind 1: out[N,Cin,H,W]  = reduce_r dgrad(a_r = dy_r[N,Cout,Ho,Wo], w_r[Cout,Cin,R,R])  (x_shape = [N,Cin,H,W])
+// mode 0 none | 1 all-reduce | 2 reduce-scatter (rank tile%W keeps).  ag: a is None, A shards live at a_off in each heap.
+Tensor tp_conv(int64_t kind, c10::optional<Tensor> a, int64_t a_off, const Tensor& w, std::vector<int64_t> x_shape,
+               int64_t stride, int64_t pad, c10::optional<Tensor> addend, c10::optional<Tensor> stats,
+               std::vector<int64_t> heaps, int64_t mc, int64_t part_off, int64_t part_stride, int64_t cnt_off,
+               int64_t ready_off, int64_t ctrl_off, int64_t rank, int64_t mode, bool nvls, bool ag) {
+  check_cl(w, "w");
+  c10::cuda::CUDAGuard g(w.device());
+  const int world = (int)heaps.size();
+  HeapPtrs hp = heap_ptrs(heaps);
+  const int N = (int)x_shape[0], Cin = (int)x_shape[1], H = (int)x_shape[2], Wd = (int)x_shape[3];
+  const int Cout = (int)w.size(0), R = (int)w.size(2);
+  TORCH_CHECK((int)w.size(1) == Cin, "tp_conv: weight Cin mismatch");
+  const void* xp[8] = {nullptr};
+  if (ag) {
+    for (int r = 0; r < world; ++r) xp[r] = hp.h[r] + a_off;
+  } else {
+    TORCH_CHECK(a.has_value() && a->defined(), "tp_conv: operand missing");
+    check_cl(*a, "a");
+    xp[rank] = a->data_ptr();
+  }
+  const int Ho = (H + 2 * (int)pad - R) / (int)stride + 1, Wo = (Wd + 2 * (int)pad - R) / (int)stride + 1;
+  Tensor out = kind == 0 ? at::empty({N, Cout, Ho, Wo}, w.options().memory_format(at::MemoryFormat::ChannelsLast))
+                         : at::empty({N, Cin, H, Wd}, w.options().memory_format(at::MemoryFormat::ChannelsLast));
+  const void* add = nullptr;
+  if (addend.has_value() && addend->defined()) {
+    check_cl(*addend, "addend");
+    TORCH_CHECK(addend->sizes() == out.sizes(), "tp_conv: addend shape mismatch");
+    add = addend->data_ptr();
+  }
+  float* st = nullptr;
+  if (stats.has_value() && stats->defined()) {
+    TORCH_CHECK(stats->scalar_type() == at::kFloat && stats->numel() >= 2 * out.size(1) && stats->is_contiguous());
+    st = stats->data_ptr<float>();
+  }
+  unsigned* ctrl = reinterpret_cast<unsigned*>(hp.h[rank] + ctrl_off);
+  int rc = hz_tp_conv((int)kind, xp, w.data_ptr(), out.data_ptr(), add, st, hp.h, (char*)(uintptr_t)mc, part_off,
+                      part_stride, cnt_off, ready_off, ctrl, ctrl + 1, world, (int)rank, (int)mode, nvls ? 1 : 0,
+                      ag ? 1 : 0, N, H, Wd, Cin, Cout, R, (int)stride, (int)pad, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_tp_conv failed rc=", rc);
+  return out;
+}
+
+// Tensor-parallel head: returns {loss, correct, dfeat, logits[N,K]}; dW_r/db_r are written into dW/db.
+std::vector<Tensor> tp_head(const Tensor& feat, const Tensor& Wl, const c10::optional<Tensor>& bl, const Tensor& labels,
+                            double loss_scale, int64_t n_valid, Tensor dW, c10::optional<Tensor> db, bool accumulate,
+                            bool need_dfeat, c10::optional<Tensor> zeroed2, std::vector<int64_t> heaps, int64_t mc,
+                            int64_t logits_off, int64_t dfeat_off, int64_t cnt_off, int64_t ctrl_off, int64_t rank,
+                            bool nvls) {
+  check_cl(feat, "feat");
+  TORCH_CHECK(Wl.scalar_type() == at::kFloat && Wl.is_contiguous() && labels.scalar_type() == at::kLong);
+  c10::cuda::CUDAGuard g(feat.device());
+  auto d = dims_of(feat);
+  const int world = (int)heaps.size();
+  HeapPtrs hp = heap_ptrs(heaps);
+  const int kl = (int)Wl.size(0), K = kl * world;
+  TORCH_CHECK(K <= 64 && kl <= 16, "tp_head: at most 64 padded classes");
+  auto fo = feat.options().dtype(at::kFloat);
+  Tensor pooled = at::empty({d.N, d.C}, fo), dl = at::empty({d.N, kl}, fo), logits = at::empty({d.N, K}, fo);
+  const bool pre = zeroed2.has_value() && zeroed2->defined() && zeroed2->numel() >= 2;
+  Tensor acc2 = pre ? zeroed2->view({-1}) : at::zeros({2}, fo);
+  Tensor loss = acc2[0], correct = acc2[1];
+  Tensor dfeat;
+  if (need_dfeat) dfeat = at::empty_like(feat);
+  unsigned* ctrl = reinterpret_cast<unsigned*>(hp.h[rank] + ctrl_off);
+  int rc = hz_tp_head(cptr(feat), Wl.data_ptr<float>(), fptr(bl), labels.data_ptr<int64_t>(), pooled.data_ptr<float>(),
+                      dl.data_ptr<float>(), logits.data_ptr<float>(), need_dfeat ? dfeat.data_ptr() : nullptr,
+                      loss.data_ptr<float>(), correct.data_ptr<float>(), hp.h, (char*)(uintptr_t)mc, logits_off, dfeat_off,
+                      cnt_off, ctrl, ctrl + 1, world, (int)rank, nvls ? 1 : 0, d.N, d.C, d.H * d.W, kl, (int)n_valid,
+                      (float)loss_scale, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_tp_head failed rc=", rc);
+  hz_head_wgrad(pooled.data_ptr<float>(), dl.data_ptr<float>(), dW.data_ptr<float>(), fptr(db), d.N, d.C, kl,
+                accumulate ? 1 : 0, cur_stream());
+  return {loss, correct, dfeat, logits};
+}
+
+int64_t tp_head_bytes(int64_t N, int64_t C, int64_t K) { return (int64_t)hz_tp_head_bytes((int)N, (int)C, (int)K); }
+
+// sum over the tensor-parallel ranks of a small bf16 tensor (dense layout preserved)
+Tensor tp_allreduce_bf16(const Tensor& in, std::vector<int64_t> heaps, int64_t mc, int64_t buf_off, int64_t cnt_off,
+                         int64_t ctrl_off, int64_t rank, bool nvls, int64_t blocks) {
+  TORCH_CHECK(in.is_cuda() && in.scalar_type() == at::kBFloat16 && in.is_non_overlapping_and_dense() && in.numel() % 8 == 0);
+  c10::cuda::CUDAGuard g(in.device());
+  HeapPtrs hp = heap_ptrs(heaps);
+  Tensor out = at::empty_like(in);
+  unsigned* ctrl = reinterpret_cast<unsigned*>(hp.h[rank] + ctrl_off);
+  int rc = hz_tp_allreduce_bf16(in.data_ptr(), out.data_ptr(), (size_t)in.numel(), hp.h, (char*)(uintptr_t)mc, buf_off,
+                                cnt_off, ctrl, ctrl + 1, (int)heaps.size(), (int)rank, nvls ? 1 : 0, (int)blocks,
+                                cur_stream());
+  TORCH_CHECK(rc == 0, "hz_tp_allreduce_bf16 failed rc=", rc);
+  return out;
+}
+
 }  // namespace
+
+// Failure diagnostics: a native crash inside a rank otherwise dies silently under the launcher; with this
+// handler the rank prints its C/C++ frames (resolve with `addr2line -e horizonml_b200/_C.so`) before re-raising.
+static void hz_segv_handler(int sig) {
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "\n[hz] fatal signal in native code, backtrace:\n";
+  (void)!write(2, msg, sizeof(msg) - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "horizonml_b200 sm_100a kernels";
+  m.def("install_crash_backtrace", [] { signal(SIGSEGV, hz_segv_handler); signal(SIGBUS, hz_segv_handler); signal(SIGABRT, hz_segv_handler); });
   m.def("channel_ok", &channel_ok);
   m.def("channel_sums", &channel_sums);
   m.def("bn_act_fwd", &bn_act_fwd);
@@ -440,12 +542,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_fwd", &conv_fwd);
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_wgrad", &conv_wgrad);
+  m.def("tp_tiles", &tp_tiles);
+  m.def("tp_conv", &tp_conv);
+  m.def("tp_head", &tp_head);
+  m.def("tp_head_bytes", &tp_head_bytes);
+  m.def("tp_allreduce_bf16", &tp_allreduce_bf16);
   py::class_<PeerComm>(m, "PeerComm")
       .def(py::init<int, int, int, int64_t, int, int64_t>(), py::arg("rank"), py::arg("world"), py::arg("device"),
            py::arg("max_wire_bytes"), py::arg("max_blocks"), py::arg("heap_bytes") = 0)
       .def("heap_bytes", &PeerComm::heap_bytes)
       .def("heap_tensor", &PeerComm::heap_tensor)
-      .def("tp_conv", &PeerComm::tp_conv)
+      .def("heap_ptr", &PeerComm::heap_ptr)
       .def("export_handles", &PeerComm::export_handles)
       .def("import_handles", &PeerComm::import_handles)
       .def_static("link_local", &PeerComm::link_local)

@@ -21,6 +21,7 @@
 #include "launchers.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -29,13 +30,14 @@ namespace hz {
 constexpr int kMaxRanks = 8;
 constexpr int kCommThreads = 512;
 constexpr size_t kFlagBytes = 1 << 16;          // flags + counters region at the start of each rank's block
-constexpr long long kSpinTimeoutNs = 4000000000LL;   // 4 s
+constexpr long long kDefaultSpinTimeoutNs = 30000000000LL;   // 30 s (HZ_COMM_TIMEOUT_S overrides)
 
 struct CommDev {
   char* base[kMaxRanks];      // every rank's region (flags first)
   char* mc_base;              // multicast mapping of the NVLS data region (or null)
   char* mc_local;             // this rank's local mapping of the same region
   size_t buf_bytes;           // size of ONE staging/out buffer
+  long long timeout_ns;       // bound on every peer spin: error flag + trap instead of a hang / silent garbage
   int rank, world;
 };
 
@@ -76,9 +78,12 @@ HZ_DEVINL void peer_block_barrier(const CommDev& c, uint32_t* s_epoch) {
     const uint32_t* mine = flags_of(my) + blockIdx.x * c.world + r;
     const long long t0 = globaltimer_ns();
     while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
-      if (globaltimer_ns() - t0 > kSpinTimeoutNs) {
+      if (globaltimer_ns() - t0 > c.timeout_ns) {
+        // a peer never arrived: reducing whatever sits in its staging buffer would silently corrupt the
+        // gradients, so record the error (host-visible through hz_comm_error) and kill the context
         atomicExch(err_of(my), 1u);
-        break;
+        __threadfence_system();
+        __trap();
       }
     }
   }
@@ -237,7 +242,11 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
   const int W = c.world, B = gridDim.x, b = blockIdx.x;
   const size_t nv = n / V;
   char* my = c.base[c.rank];
-  const uint32_t parity = calls_of(my)[b] & 1u;
+  // Staging/out buffers alternate by call.  The parity comes from ONE per-communicator call counter that every
+  // block reads at entry and the last-finishing block bumps (ticket): a per-block counter would let a block that
+  // did not exist in the previous (smaller-grid) call reuse that call's parity and overwrite a region a slow peer
+  // is still reading (kernels of one communicator are stream-ordered, so the counter is stable while they run).
+  const uint32_t parity = calls_of(my)[0] & 1u;
   const size_t stage_off = kFlagBytes + (size_t)parity * c.buf_bytes;
   const size_t out_off = kFlagBytes + (size_t)(2 + parity) * c.buf_bytes;
   // NVLS uses the symmetric (multicast-mapped) region instead of the IPC region for data
@@ -320,7 +329,15 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) calls_of(my)[b] += 1u;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    uint32_t* ticket = calls_of(my) + 1;
+    if (atomicAdd(ticket, 1u) == (uint32_t)(B - 1)) {      // last block of this call
+      *ticket = 0u;
+      calls_of(my)[0] += 1u;
+      __threadfence();
+    }
+  }
 }
 
 __global__ void barrier_kernel(CommDev c, long long* stamp_ns) {
@@ -379,6 +396,11 @@ HzComm* hz_comm_create2(int rank, int world, int device, size_t max_wire_bytes, 
   c->dev.buf_bytes = buf;
   c->dev.rank = rank;
   c->dev.world = world;
+  {
+    const char* e = getenv("HZ_COMM_TIMEOUT_S");
+    const double sec = e ? atof(e) : 0.0;
+    c->dev.timeout_ns = sec > 0.0 ? (long long)(sec * 1e9) : hz::kDefaultSpinTimeoutNs;
+  }
   c->heap_off = hz::kFlagBytes + 4 * buf;
   c->heap_bytes = (heap_bytes + 1023) / 1024 * 1024;
   c->region_bytes = c->heap_off + c->heap_bytes;

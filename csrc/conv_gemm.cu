@@ -233,7 +233,9 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     const int wi = r0 % p.BW;
     const int hi = (r0 / p.BW) % p.BH;
     const int n = n0 + r0 / (p.BW * p.BH);
-    if (n >= p.n_images) return -1;
+    // rows past the last image, and columns past the last channel (channel counts that are not a multiple of 64:
+    // the TMA boxes were zero-filled / over-read there, the results are simply not stored)
+    if (n >= p.n_images || nt * BLOCK_N + (int)(threadIdx.x % kVecPerRow) * 8 >= p.ncols) return -1;
     return (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride + (long long)wi * p.out_w_stride +
            p.cls_out_off[cls] + nt * BLOCK_N + (threadIdx.x % kVecPerRow) * 8;
   };
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
     __syncthreads();
     const int col = threadIdx.x % BLOCK_N, which = threadIdx.x / BLOCK_N;       // 128 threads = 64 columns x {Σ, Σ²}
     const float tot = stat_sm[0][which][col] + stat_sm[1][which][col] + stat_sm[2][which][col] + stat_sm[3][which][col];
-    atomicAdd(&p.stats[which * p.ncols + nt * BLOCK_N + col], tot);
+    if (nt * BLOCK_N + col < p.ncols) atomicAdd(&p.stats[which * p.ncols + nt * BLOCK_N + col], tot);
   }
   if (threadIdx.x == 64) HZ_STAMP(7);                    // output rows + BN sums written
   if (p.bn_out != nullptr) {
@@ -756,7 +758,9 @@ int pick_splits(int tiles, int k_total) {
 extern "C" {
 
 int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad) {
-  if (Cin % 64 || Cout % 64) return 0;
+  // channel counts only need 16-byte rows (TMA): a 64-wide box over a narrower tensor is zero-filled, surplus output
+  // columns are masked in the epilogue — tensor-parallel shards (256/8 = 32 channels) stay on these kernels
+  if ((Cin & 7) || (Cout & 7) || Cin < 8 || Cout < 8) return 0;
   if (!((R == 3 && pad == 1) || (R == 1 && pad == 0))) return 0;
   if (stride != 1 && stride != 2) return 0;
   if (stride == 2 && ((H | W) & 1)) return 0;
@@ -798,7 +802,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   memset(&p, 0, sizeof(p));
   input_taps(&p.cls[0], R, S_, stride, pad, Ho, Wo, H, W, Cin, false);
   p.num_classes = 1;
-  p.cblocks = Cin / 64;
+  p.cblocks = (Cin + 63) / 64;
   p.BN = t.BN; p.BH = t.BH; p.BW = t.BW; p.tiles_per_img = t.per_img;
   p.n_images = N;
   p.out_n_stride = (long long)Ho * Wo * Cout; p.out_h_stride = (long long)Wo * Cout; p.out_w_stride = Cout;
@@ -809,7 +813,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   if (stats && !stats_is_zero) hz::zero_f32(stats, (size_t)2 * Cout, st);
   {
     const SplitWs w = get_split_ws();
-    const int tiles = t.tiles * (Cout / BLOCK_N);
+    const int tiles = t.tiles * ((Cout + BLOCK_N - 1) / BLOCK_N);
     p.splits = w.ws ? pick_splits(tiles, p.cls[0].n * p.cblocks) : 1;
     p.ws = w.ws; p.sem = w.sem;
     if (bn != nullptr) p.splits = 1;      // workspace split-K retires CTAs early: incompatible with a grid barrier
@@ -821,6 +825,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
     }
     if (bn != nullptr) {
       if (stats == nullptr || !stats_is_zero) return -21;
+      if (Cout % BLOCK_N) return -20;            // the fused BN epilogue assumes full 64-column tiles
       // every CTA must be resident for the barrier: clusters are already limited to one wave by
       // pick_cluster_splits; plain grids keep a few SMs spare for kernels of other streams (NCCL p2p)
       if (p.cluster ? tiles > max_active_clusters(hz::igemm_kernel<64, false>, hz::IgemmSmem<64>::kTotal, p.splits)
@@ -841,7 +846,7 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;
   p.dbg = g_conv_dbg;
   using SM = hz::IgemmSmem<BLOCK_N>;
-  dim3 grid(t.tiles, Cout / BLOCK_N, p.splits);
+  dim3 grid(t.tiles, (Cout + BLOCK_N - 1) / BLOCK_N, p.splits);
   return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, false>, grid, dim3(128), SM::kTotal, st,
                             p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;
 }
@@ -888,7 +893,7 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
       }
     p.cls_out_off[c] = stride == 1 ? 0 : ((long long)ph * W + pw) * Cin;
   }
-  p.cblocks = Cout / 64;
+  p.cblocks = (Cout + 63) / 64;
   p.BN = t.BN; p.BH = t.BH; p.BW = t.BW; p.tiles_per_img = t.per_img;
   p.n_images = N;
   p.out_n_stride = (long long)H * W * Cin;
@@ -900,7 +905,7 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
   p.stats = nullptr;
   {
     const SplitWs w = get_split_ws();
-    const int tiles = t.tiles * (Cin / BLOCK_N) * p.num_classes;
+    const int tiles = t.tiles * ((Cin + BLOCK_N - 1) / BLOCK_N) * p.num_classes;
     int kmax = 0;
     for (int c = 0; c < p.num_classes; ++c) kmax = kmax > p.cls[c].n ? kmax : p.cls[c].n;
     p.splits = w.ws ? pick_splits(tiles, kmax * p.cblocks) : 1;
@@ -915,7 +920,7 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
   p.prefetch_b = weights_stable ? prefetch_weights_enabled() : 0;
   p.dbg = g_conv_dbg;
   using SM = hz::IgemmSmem<BLOCK_N>;
-  dim3 grid(t.tiles, Cin / BLOCK_N, p.num_classes * p.splits);
+  dim3 grid(t.tiles, (Cin + BLOCK_N - 1) / BLOCK_N, p.num_classes * p.splits);
   return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, true>, grid, dim3(128), SM::kTotal, st,
                             p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;
 }
@@ -941,7 +946,7 @@ int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W,
   constexpr int BLOCK_N = 64;
   p.KBN = t.BN; p.KBH = t.BH; p.kb_per_img = t.per_img;
   p.kblocks = t.tiles;
-  p.n_tiles = Cin / BLOCK_N;
+  p.n_tiles = (Cin + BLOCK_N - 1) / BLOCK_N;
   const int m_tiles = (Cout + 127) / 128;
   const int ctas = m_tiles * p.n_tiles * p.taps.n;
   int splits = (72 + ctas - 1) / ctas;      // leave SMs for the concurrently running dgrad chain

@@ -897,6 +897,14 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
                                                                                   accumulate);
 }
 
+// dW[k,c] (+)= sum_n dlogits[n,k] * pooled[n,c], db[k] (+)= sum_n dlogits[n,k]   (tensor-parallel head: local shard)
+void hz_head_wgrad(const float* pooled, const float* dlogits, float* dW, float* db, int N, int C, int K,
+                   int accumulate, cudaStream_t st) {
+  dim3 grid((C + 31) / 32, (K + 15) / 16);
+  hz::launch(hz::head_wgrad_kernel, dim3(grid), dim3(128), sizeof(float) * (N * 16 + 4 * 32 * 16), st, pooled, dlogits,
+             dW, db, N, C, K, accumulate);
+}
+
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,
              int zero_grad, size_t n, float lr, float b1, float b2, float eps, float gscale, const int* live,
              size_t n_live_blocks, int bump, int max_ctas, cudaStream_t st) {

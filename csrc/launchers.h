@@ -80,12 +80,23 @@ int hz_comm_barrier(struct HzComm* c, long long* stamps, cudaStream_t st);
 int hz_comm_error(struct HzComm* c);
 void hz_comm_destroy(struct HzComm* c);
 
-// ---- tp_fused.cu (GEMM fused with its collective over peer memory)
-size_t hz_tp_ws_bytes(int world, int tiles);
-int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, char* const* heaps, long long out_off,
-               long long ws_off, long long ws_stride, long long arrive_off, long long result_off,
-               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int reduce, int bcast,
-               int ag, int N, int H, int W_, int Cin, int Cout, int R, int pad, cudaStream_t st);
+// ---- tp_fused.cu (GEMM fused with its collective over peer memory; TP head; small bf16 all-reduce)
+int hz_tp_tiles(int kind, int N, int H, int W_, int Cin, int Cout, int stride);
+int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, const void* addend, float* stats,
+               char* const* heaps, char* mc_heap, long long part_off, long long part_stride, long long cnt_off,
+               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int mode, int nvls, int ag,
+               int N, int H, int W_, int Cin, int Cout, int R, int stride, int pad, cudaStream_t st);
+int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t* labels, float* pooled,
+               float* dl_local, float* logits, void* dfeat, float* loss, float* correct, char* const* heaps,
+               char* mc_heap, long long logits_off, long long dfeat_off, long long cnt_off, unsigned* epoch,
+               unsigned* done, int world, int rank, int nvls, int N, int C, int HW, int k_local, int n_valid,
+               float loss_scale, cudaStream_t st);
+size_t hz_tp_head_bytes(int N, int C, int K);
+int hz_tp_allreduce_bf16(const void* in, void* out, size_t n, char* const* heaps, char* mc_heap, long long buf_off,
+                         long long cnt_off, unsigned* epoch, unsigned* done, int world, int rank, int nvls, int blocks,
+                         cudaStream_t st);
+void hz_head_wgrad(const float* pooled, const float* dlogits, float* dW, float* db, int N, int C, int K,
+                   int accumulate, cudaStream_t st);
 
 #ifdef __cplusplus
 }

@@ -1,24 +1,33 @@
-// Tensor-parallel fused compute+collective kernels: one tcgen05 implicit-GEMM kernel
-// that ALSO moves its data over NVLink from inside the kernel, tile by tile.
+// Tensor-parallel fused compute+collective kernels: ONE tcgen05 implicit-GEMM kernel that
+// also performs its collective over NVLink / NVSwitch from inside the kernel, tile by tile.
 //
-//   GEMM -> all-reduce / reduce-scatter  (row-parallel conv/linear forward; column-parallel dgrad):
-//       every rank computes a partial 128xBLOCK_N tile in TMEM.  Tiles are owned round-robin
-//       (tile % W).  A non-owner *pushes* its fp32 partial straight into the owner's workspace slot
-//       with NVLink stores and raises a per-tile flag; the owner waits for the W-1 flags, adds the
-//       partials in rank order (deterministic), converts to bf16 and - for all-reduce - broadcasts the
-//       finished tile into every rank's output buffer with peer stores, then raises the tile's result
-//       flag on every rank.  No NCCL call, no separate reduction pass: the transfer of tile i overlaps
-//       the MMA of tile j running on another SM.   (reference site: the missing reduction of
-//       tensor_parallel_train.py:215-218 / SURVEY Q4; row-split is required by BASELINE.json.)
+//   GEMM -> all-reduce   (row-parallel conv/linear forward; column-parallel dgrad)      mode 1
+//   GEMM -> reduce-scatter (tile t is reduced and kept by rank t % W only)              mode 2
+//       every rank computes its partial 128x64 tile in TMEM, drops it as bf16 into ITS OWN slot of the symmetric
+//       heap (a local store, no NVLink traffic yet) and bumps the tile's arrival counter on the ranks that need
+//       the tile - with ONE `multimem.red` on the NVSwitch multicast address when the heap is multicast-mapped,
+//       else one `red.release.sys` per peer.  A rank that needs the tile waits for the W arrivals and then
+//       *pulls*: either `multimem.ld_reduce` (the switch adds the W copies in flight - one NVLink round trip,
+//       1/W of the ingress bytes) or W `cp.async.bulk` copies of the peers' slots straight into the (now idle)
+//       operand ring in shared memory, summed in rank order (bit-identical on every rank).  The reduced tile goes
+//       through the normal conv epilogue: BatchNorm partial sums, optional residual-gradient addend, bf16 store
+//       into a plain local tensor.  Round 1 pushed fp32 partials to every peer and used 7 flags per tile: 2x the
+//       bytes, W-1 posted-store streams per thread and a flag fan-out - it lost to conv + NCCL at 8 GPUs.
+//       (reference site: the missing reduction of tensor_parallel_train.py:215-218 / SURVEY Q4; the row split
+//       is required by BASELINE.json.)
 //
-//   all-gather -> GEMM  (A operand row/image-sharded across ranks):
-//       the TMA producer loads A tiles *directly from the owning peer's memory* (tensor maps built on
-//       the peer-mapped addresses) after a per-kernel ready-flag handshake - the all-gather never
-//       materialises.   (reference site: the ws-broadcast "all-gather" of tensor_parallel_train.py:49-62.)
+//   all-gather -> GEMM   (A operand image-sharded across ranks)                          ag = 1
+//       the TMA producer loads A tiles *directly from the owning peer's memory* (tensor maps built on the
+//       peer-mapped addresses) after a ready-flag handshake - the gathered tensor never materialises.
+//       (reference site: the ws-broadcast "all-gather" of tensor_parallel_train.py:49-62.)
 //
-// All buffers live in a symmetric heap (same offsets on every rank, CUDA-IPC mapped).  Flags are epoch
-// numbered (device-side counter) so the kernels are re-launchable / CUDA-graph replayable; spins are
-// bounded (trap instead of hang).  Grids are <= #SMs so all CTAs are co-resident while they spin.
+// Channel counts need not be multiples of 64: a 64-wide TMA box over a narrower tensor is zero-filled by the
+// TMA unit (and columns past `ncols` are masked in the epilogue), so the 32-channel shards of layer3 at W=8 run
+// here too.  Stride-2 dgrad runs as 4 output-parity classes (blockIdx.z) like the dense kernel.
+// All counters are epoch based and live in device memory: re-launchable and CUDA-graph replayable; partial
+// slots alternate by call parity (every call contains an all-to-all dependency, so a slot is never rewritten
+// while a peer can still read it).  Spins are bounded (trap instead of a hang); grids are <= #SMs so all CTAs
+// are co-resident while they spin.  Programmatic dependent launch like every other compute kernel.
 #include <cuda.h>
 
 #include "igemm_common.cuh"
@@ -27,33 +36,38 @@
 namespace hz {
 
 constexpr int kTpMaxRanks = 8;
+constexpr int kTpPartBytes = kTileM * 64 * 2;      // one bf16 partial tile
 
 struct PeerAMaps {
   CUtensorMap m[kTpMaxRanks];     // A tensor map on rank r's buffer (AG mode); m[rank] is the local one
 };
 
 struct TpParams {
-  TapList taps;
+  TapList cls[4];
+  long long cls_out_off[4];
   long long out_n_stride, out_h_stride, out_w_stride;   // elements
-  int cblocks;
+  int num_classes, cblocks;
   int BN, BH, BW, tiles_per_img;
   int n_images;                  // total images (all ranks)
-  int ncols;
+  int ncols;                     // valid output columns
   // ---- peer part
   int world, rank;
-  int reduce;                    // 1: push-to-owner reduce (owner = tile % world); 2: one-shot (push to all, reduce everywhere)
-  int bcast;                     // 1: all-reduce (owner broadcasts), 0: reduce-scatter (owner keeps)
+  int mode;                      // 0: no reduction, 1: all-reduce, 2: reduce-scatter (tile % world keeps)
+  int nvls;                      // 1: multimem.red arrival + multimem.ld_reduce pull (heap is multicast-mapped)
   int ag;                        // 1: A is image-sharded, ag_imgs images per rank
   int ag_imgs;
-  char* heap[kTpMaxRanks];       // symmetric heap base of every rank
-  long long out_off;             // bf16 output [n_images, ...] (bytes from heap base)
-  long long ws_off;              // fp32 partial slots [world][tiles][128][BLOCK_N]
-  long long ws_stride;           // one-shot: second copy of the slots, selected by call parity (no back-pressure needed)
-  long long arrive_off;          // u32 [tiles][world]
-  long long result_off;          // u32 [tiles]
+  char* heap[kTpMaxRanks];       // symmetric heap base of every rank, as mapped in this process
+  char* mc_heap;                 // multicast mapping of the same heap (nvls)
+  long long part_off;            // bf16 partial tiles [2 parities][tiles][128][64] (bytes from heap base)
+  long long part_stride;         // bytes between the two parity copies
+  long long cnt_off;             // u32 [tiles] arrival counters (monotonic: += W per call)
   long long ready_off;           // u32 [world]      (AG: "my A shard is ready")
   unsigned* epoch;               // local: number of completed calls
   unsigned* done;                // local: CTAs finished in this call
+  __nv_bfloat16* out;            // local output tensor
+  const __nv_bfloat16* addend;   // optional, layout of out: out = reduced tile + addend (residual gradient)
+  float* stats;                  // optional [2*ncols]: sum y, sum y^2 of the REDUCED output (pre-zeroed)
+  long long timeout_clk;
 };
 
 HZ_DEVINL void st_release_sys_u32(unsigned* p, unsigned v) {
@@ -64,36 +78,57 @@ HZ_DEVINL unsigned ld_acquire_sys_u32(const unsigned* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-HZ_DEVINL void spin_until_ge(const unsigned* p, unsigned e) {
+HZ_DEVINL void red_release_sys_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// one instruction, delivered by the NVSwitch to the same offset on every rank of the multicast group
+HZ_DEVINL void multimem_red_add_u32(unsigned* mc_p, unsigned v) {
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_p), "r"(v) : "memory");
+}
+HZ_DEVINL uint4 multimem_ld_reduce_bf16x8(const void* mc_p) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc_p) : "memory");
+  return v;
+}
+HZ_DEVINL void spin_until_ge(const unsigned* p, unsigned e, long long timeout_clk) {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys_u32(p) - e) < 0) {
-    if (clock64() - t0 > 8000000000LL) __trap();
+    if (clock64() - t0 > timeout_clk) __trap();
   }
 }
+// 1-D bulk copy global (possibly a peer's HBM over NVLink) -> shared, completion on an mbarrier
+HZ_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
-template <int BLOCK_N, bool B_MN>
+template <bool B_MN>
 __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ PeerAMaps amaps,
                                                        const __grid_constant__ CUtensorMap bmap,
                                                        const __grid_constant__ TpParams p) {
+  constexpr int BLOCK_N = 64;
   using S = IgemmSmem<BLOCK_N>;
+  static_assert(kTpMaxRanks * kTpPartBytes <= S::kPipeBytes, "peer partial tiles are pulled into the idle operand ring");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
   uint64_t* empty = full + kStages;
   uint64_t* tmem_full = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* pull_bar = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pull_bar + 1);
 
+  pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y;
-  const int tiles = gridDim.x * gridDim.y;
-  const int tile = nt * gridDim.x + mt;
+  const int mt = blockIdx.x, nt = blockIdx.y, cls = blockIdx.z;
+  const int tiles = gridDim.x * gridDim.y * gridDim.z;
+  const int tile = (cls * gridDim.y + nt) * gridDim.x + mt;
+  const TapList& taps = p.cls[cls];
   const int n0 = (p.BN == 1) ? mt / p.tiles_per_img : mt * p.BN;
   const int h0 = (p.BN == 1) ? (mt % p.tiles_per_img) * p.BH : 0;
-  const int k_iters = p.taps.n * p.cblocks;
+  const int k_iters = taps.n * p.cblocks;
   const int W = p.world, me = p.rank;
-  const unsigned e = *p.epoch + 1u;             // epoch of this call (same on every rank)
   char* my_heap = p.heap[me];
-  const long long ws_off = p.ws_off + (long long)(e & 1u) * p.ws_stride;
 
   // which rank holds this tile's A rows (all-gather mode) and the image index inside that shard
   const int src = p.ag ? min(n0 / p.ag_imgs, W - 1) : me;
@@ -104,24 +139,29 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
     tc::prefetch_tmap(&bmap);
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     tc::mbar_init(tmem_full, 1);
+    tc::mbar_init(pull_bar, 1);
     tc::fence_barrier_init();
   }
   if (warp == 2) {
     tc::tmem_alloc(tmem_slot, BLOCK_N);
     tc::tmem_relinquish();
   }
-  if (p.ag && warp == 3) {
-    // ready handshake: our shard was produced by earlier kernels of this stream, so any CTA may vouch
-    // for it; then wait until the shard we are about to read is published by its owner
-    if (blockIdx.x == 0 && blockIdx.y == 0 && lane < W)
-      st_release_sys_u32(reinterpret_cast<unsigned*>(p.heap[lane] + p.ready_off) + me, e);
-    if (lane == 0 && src != me) spin_until_ge(reinterpret_cast<unsigned*>(my_heap + p.ready_off) + src, e);
-    __syncwarp();
-  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
+  pdl_wait();                                   // the A operand / addend / epoch counter come from upstream kernels
+  const unsigned e = *p.epoch + 1u;             // epoch of this call (same on every rank)
+
+  if (p.ag && warp == 3) {
+    // ready handshake: our shard was produced by earlier kernels of this stream (complete: pdl_wait above), so
+    // any CTA may vouch for it; then wait until the shard we are about to read is published by its owner
+    if (tile == 0 && lane < W) st_release_sys_u32(reinterpret_cast<unsigned*>(p.heap[lane] + p.ready_off) + me, e);
+    if (lane == 0 && src != me)
+      spin_until_ge(reinterpret_cast<unsigned*>(my_heap + p.ready_off) + src, e, p.timeout_clk);
+    __syncwarp();
+  }
+  if (p.ag) __syncthreads();
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (A possibly straight out of a peer's HBM over NVLink) ==========
@@ -134,13 +174,11 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
       uint8_t* sa = smem + s * S::kStageBytes;
       uint8_t* sb = sa + kABytes;
       tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
-      tc::tma_load_4d(sa, am, &full[s], cb * kKBlock, p.taps.dw[t], h0 + p.taps.dh[t], n0_src);
+      tc::tma_load_4d(sa, am, &full[s], cb * kKBlock, taps.dw[t], h0 + taps.dh[t], n0_src);
       if (!B_MN) {
-        tc::tma_load_2d(sb, &bmap, &full[s], p.taps.bk[t] + cb * kKBlock, nt * BLOCK_N);
+        tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[t] + cb * kKBlock, nt * BLOCK_N);
       } else {
-#pragma unroll
-        for (int j = 0; j < BLOCK_N / 64; ++j)
-          tc::tma_load_2d(sb + j * 8192, &bmap, &full[s], p.taps.bk[t] + nt * BLOCK_N + j * 64, cb * kKBlock);
+        tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[t] + nt * BLOCK_N, cb * kKBlock);
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -160,129 +198,190 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
       }
       tc::umma_commit(&empty[s]);
     }
-    tc::umma_commit(tmem_full);
+    if (k_iters > 0) tc::umma_commit(tmem_full);
   }
   __syncwarp();
 
   // ===================== epilogue =====================
-  __nv_bfloat16* staging = reinterpret_cast<__nv_bfloat16*>(smem);
   const int row = warp * 32 + lane;
-  tc::mbar_wait(tmem_full, 0);
-  tc::fence_after_sync();
-
-  const int owner = p.reduce == 1 ? tile % W : me;
-  bool have_result = true;            // staging holds the final bf16 tile
-  if (p.reduce == 2 && W > 1) {
-    // ---- one-shot: push the fp32 partial into slot [me][tile] of EVERY peer (one NVLink hop), then each
-    //      rank reduces all W partials itself in rank order -> bit-identical results, no second hop
+  constexpr int kVecPerRow = BLOCK_N / 8;              // 16-byte vectors per tile row
+  constexpr int kRowsPerPass = 128 / kVecPerRow;
+  constexpr int kPasses = kTileM / kRowsPerPass;
+  const int vec = threadIdx.x % kVecPerRow;
+  const bool col_ok = nt * BLOCK_N + vec * 8 < p.ncols;
+  // global element offsets of the rows this thread stores, computed while the MMAs are still running
+  long long offs[kPasses];
 #pragma unroll
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t r[32];
-      tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
-      tc::tmem_ld_wait();
-      for (int d = 1; d < W; ++d) {
-        const int rr = (me + d) % W;
-        float* dst = reinterpret_cast<float*>(p.heap[rr] + ws_off) + ((size_t)(me * tiles + tile) * kTileM + row) * BLOCK_N + c0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-      }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < W && threadIdx.x != me)
-      st_release_sys_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.arrive_off) + tile * W + me, e);
+  for (int i = 0; i < kPasses; ++i) {
+    const int r0 = threadIdx.x / kVecPerRow + i * kRowsPerPass;
+    const int wi = r0 % p.BW;
+    const int hi = (r0 / p.BW) % p.BH;
+    const int n = n0 + r0 / (p.BW * p.BH);
+    offs[i] = (n < p.n_images && col_ok)
+                  ? (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride +
+                        (long long)wi * p.out_w_stride + p.cls_out_off[cls] + nt * BLOCK_N + vec * 8
+                  : -1;
   }
-  if (p.reduce == 1 && owner != me) {
-    // ---- push the fp32 partial into the owner's slot [me][tile] over NVLink
-    float* dst = reinterpret_cast<float*>(p.heap[owner] + ws_off) + ((size_t)(me * tiles + tile) * kTileM + row) * BLOCK_N;
+  const bool reducing = p.mode != 0 && W > 1;
+  const bool keeper = !reducing || p.mode == 1 || (tile % W) == me;     // this rank finishes / stores the tile
+  bf16x8 addv[kPasses];
+  if (p.addend != nullptr && keeper) {
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i)
+      if (offs[i] >= 0) addv[i] = ld8(p.addend + offs[i]);
+  }
+  if (k_iters > 0) {
+    tc::mbar_wait(tmem_full, 0);
+    tc::fence_after_sync();
+  }
+
+  __nv_bfloat16* staging = reinterpret_cast<__nv_bfloat16*>(smem);          // [128][kStagingLd]   (mode 0)
+  uint4 red[kPasses];                                                        // reduced bf16x8 vectors (modes 1, 2)
+  if (reducing) {
+    // ---- 1. my partial tile -> bf16 -> my own slot (row-major [128][64]: every thread writes one full 128 B line)
+    const long long slot = p.part_off + (long long)(e & 1u) * p.part_stride + (long long)tile * kTpPartBytes;
+    __nv_bfloat16* mine = reinterpret_cast<__nv_bfloat16*>(my_heap + slot) + row * BLOCK_N;
 #pragma unroll
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
-      tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0)
-      st_release_sys_u32(reinterpret_cast<unsigned*>(p.heap[owner] + p.arrive_off) + tile * W + me, e);
-    have_result = false;
-  } else {
-    if (p.reduce && W > 1) {
-      if (threadIdx.x < W && threadIdx.x != me)
-        spin_until_ge(reinterpret_cast<unsigned*>(my_heap + p.arrive_off) + tile * W + threadIdx.x, e);
-      __syncthreads();
-    }
-    const float* slots = reinterpret_cast<const float*>(my_heap + ws_off);
-#pragma unroll
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t r[32];
-      tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
-      tc::tmem_ld_wait();
-      float acc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-      if (p.reduce) {
-        for (int rr = 0; rr < W; ++rr) {          // fixed rank order: deterministic (and rank-identical) sum
-          if (rr == me) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-          } else {
-            const float* sp = slots + ((size_t)(rr * tiles + tile) * kTileM + row) * BLOCK_N + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(sp + j));
-              acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
-            }
-          }
-        }
+      if (k_iters > 0) {
+        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tc::tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) r[j] = 0u;            // a parity class without taps: exactly zero
       }
-      __nv_bfloat16* dstg = staging + row * S::kStagingLd + c0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) st8(dstg + j, pack8(acc + j));
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[j + i]);
+        st8(mine + c0 + j, pack8(f));
+      }
+    }
+    __threadfence_system();
+    tc::fence_before_sync();
+    __syncthreads();
+    // ---- 2. arrival: bump the tile's counter wherever the tile is needed
+    unsigned* cnt_local = reinterpret_cast<unsigned*>(my_heap + p.cnt_off) + tile;
+    if (p.mode == 1) {
+      if (p.nvls) {
+        if (threadIdx.x == 0) multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + tile, 1u);
+      } else if (threadIdx.x < W) {
+        red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.cnt_off) + tile, 1u);
+      }
+    } else if (threadIdx.x == 0) {
+      red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[tile % W] + p.cnt_off) + tile, 1u);
+    }
+    if (keeper) {
+      // ---- 3. wait for all W partials of this tile, 4. pull them
+      if (threadIdx.x == 0) spin_until_ge(cnt_local, (unsigned)W * e, p.timeout_clk);
+      __syncthreads();
+      if (p.nvls) {
+        const char* mc_tile = p.mc_heap + slot;
+#pragma unroll
+        for (int i = 0; i < kPasses; ++i) {
+          const int r0 = threadIdx.x / kVecPerRow + i * kRowsPerPass;
+          red[i] = multimem_ld_reduce_bf16x8(mc_tile + (r0 * BLOCK_N + vec * 8) * 2);   // summed inside the NVSwitch
+        }
+      } else {
+        if (threadIdx.x == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          tc::mbar_arrive_expect_tx(pull_bar, (uint32_t)(W * kTpPartBytes));
+          for (int d = 0; d < W; ++d) {
+            const int rr = (me + d) % W;                    // own (local) slot first, peers staggered
+            bulk_g2s(smem + rr * kTpPartBytes, p.heap[rr] + slot, kTpPartBytes, pull_bar);
+          }
+        }
+        tc::mbar_wait(pull_bar, 0);
+#pragma unroll
+        for (int i = 0; i < kPasses; ++i) {
+          const int r0 = threadIdx.x / kVecPerRow + i * kRowsPerPass;
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+          for (int rr = 0; rr < W; ++rr) {                  // fixed rank order: deterministic and rank-identical
+            float f[8];
+            unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(smem + rr * kTpPartBytes) + r0 * BLOCK_N + vec * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          }
+          const bf16x8 pk = pack8(acc);
+          red[i] = *reinterpret_cast<const uint4*>(&pk);
+        }
+      }
+    }
+  } else {
+    if (k_iters > 0) {
+#pragma unroll
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+        tc::tmem_ld_wait();
+        __nv_bfloat16* dst = staging + row * S::kStagingLd + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[j + i]);
+          st8(dst + j, pack8(f));
+        }
+      }
+    } else {
+      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 8) st8(staging + row * S::kStagingLd + c0, pack8(z));
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+  }
+
+  if (keeper) {
+    // ---- coalesced stores of the finished tile (+ BatchNorm sums, + residual-gradient addend)
+    float ssum[8], ssq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      const long long off = offs[i];
+      if (off < 0) continue;
+      const int r0 = threadIdx.x / kVecPerRow + i * kRowsPerPass;
+      bf16x8 v = reducing ? *reinterpret_cast<const bf16x8*>(&red[i]) : ld8(staging + r0 * S::kStagingLd + vec * 8);
+      if (p.stats != nullptr) {
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ssum[j] += f[j]; ssq[j] += f[j] * f[j]; }
+      }
+      if (p.addend != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.v[j] = __hadd2(v.v[j], addv[i].v[j]);
+      }
+      st8(p.out + off, v);
+    }
+    if (p.stats != nullptr) {
+      // lanes l, l^8, l^16, l^24 hold the same 8 columns (different rows): fold them, then the 4 warps through smem
+      __shared__ float stat_sm[4][2][BLOCK_N];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 8);
+        ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 8);
+        ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
+        ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 16);
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          stat_sm[warp][0][lane * 8 + j] = ssum[j];
+          stat_sm[warp][1][lane * 8 + j] = ssq[j];
+        }
+      }
+      __syncthreads();
+      const int col = threadIdx.x % BLOCK_N, which = threadIdx.x / BLOCK_N;
+      const float tot = stat_sm[0][which][col] + stat_sm[1][which][col] + stat_sm[2][which][col] + stat_sm[3][which][col];
+      if (nt * BLOCK_N + col < p.ncols) atomicAdd(&p.stats[which * p.ncols + nt * BLOCK_N + col], tot);
     }
   }
   tc::fence_before_sync();
-  __syncthreads();
-
-  constexpr int kVecPerRow = BLOCK_N / 8;
-  constexpr int kRowsPerPass = 128 / kVecPerRow;
-  const int vec = threadIdx.x % kVecPerRow;
-  if (have_result) {
-    // store the finished tile into the local output and (all-reduce) into every peer's output
-    const int n_dst = (p.reduce == 1 && p.bcast) ? W : 1;
-    for (int d = 0; d < n_dst; ++d) {
-      const int rr = (p.reduce == 1 && p.bcast) ? (me + d) % W : me;   // start with self, stagger peers
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.heap[rr] + p.out_off);
-      for (int r0 = threadIdx.x / kVecPerRow; r0 < kTileM; r0 += kRowsPerPass) {
-        const int wi = r0 % p.BW;
-        const int hi = (r0 / p.BW) % p.BH;
-        const int ni = r0 / (p.BW * p.BH);
-        const int n = n0 + ni;
-        if (n >= p.n_images) continue;
-        const long long off = (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride +
-                              (long long)wi * p.out_w_stride + nt * BLOCK_N + vec * 8;
-        st8(out + off, ld8(staging + r0 * S::kStagingLd + vec * 8));
-      }
-    }
-    if (p.reduce == 1 && p.bcast && W > 1) {
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < W && threadIdx.x != me)
-        st_release_sys_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.result_off) + tile, e);
-    }
-  } else if (p.bcast) {
-    // non-owner of an all-reduce: the owner delivers the finished tile into our output buffer
-    if (threadIdx.x == 0) spin_until_ge(reinterpret_cast<unsigned*>(my_heap + p.result_off) + tile, e);
-  }
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tmem_d, BLOCK_N);
   // ---- the last CTA of the grid publishes the new epoch (every CTA has already read the old one)
@@ -297,6 +396,237 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-parallel classifier head in ONE kernel (reference: TensorParallelLinear + CrossEntropy,
+// tensor_parallel_train.py:27-64,203-204): global-avg-pool -> column-parallel FC (this rank's k classes)
+// -> all-gather of the logit columns by peer stores -> softmax-CE + accuracy (replicated) -> dlogits ->
+// dW_r / db_r inputs (pooled, dlogits) -> dX = sum_r dY_r . W_r by a peer pull-reduce (multimem.ld_reduce when
+// the heap is multicast-mapped) -> bf16 dfeat.  One CTA per sample; two cross-rank rendezvous per sample.
+// ------------------------------------------------------------------------------------------------
+struct TpHeadParams {
+  int world, rank, nvls;
+  int N, C, HW, K, k_local, n_valid;       // K = k_local * world padded classes
+  float loss_scale;
+  char* heap[kTpMaxRanks];
+  char* mc_heap;
+  long long logits_off;          // f32 [2 parities][N][K]
+  long long dfeat_off;           // f32 [2 parities][N][C]   partial dX of this rank
+  long long cnt_off;             // u32 [2][N] arrival counters (logits, dfeat), monotonic
+  long long par_stride_logits, par_stride_dfeat;
+  unsigned* epoch; unsigned* done;
+  long long timeout_clk;
+};
+
+__global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __restrict__ feat,
+                                                      const float* __restrict__ Wl, const float* __restrict__ bl,
+                                                      const int64_t* __restrict__ labels, float* __restrict__ pooled,
+                                                      float* __restrict__ dl_local, float* __restrict__ logits_out,
+                                                      __nv_bfloat16* __restrict__ dfeat, float* __restrict__ loss_out,
+                                                      float* __restrict__ correct_out, const TpHeadParams p) {
+  pdl_launch();
+  pdl_wait();
+  extern __shared__ float hsm[];            // pooled[C] | logit[K] | dl[K]
+  float* pl = hsm;
+  float* lg = hsm + p.C;
+  float* dl = lg + p.K;
+  const int n = blockIdx.x, W = p.world, me = p.rank, C = p.C, K = p.K, kl = p.k_local;
+  const unsigned e = *p.epoch + 1u;
+  const unsigned par = e & 1u;
+  char* my_heap = p.heap[me];
+  const float inv_hw = 1.f / (float)p.HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < p.HW; ++q) s += __bfloat162float(feat[((size_t)n * p.HW + q) * C + c]);
+    s *= inv_hw;
+    pl[c] = s;
+    pooled[(size_t)n * C + c] = s;
+  }
+  __syncthreads();
+  // ---- my logit columns, pushed into the logits row of EVERY rank (the reference's K8 all-gather: k floats per peer)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const long long lrow = p.logits_off + (long long)par * p.par_stride_logits + ((long long)n * K + me * kl) * 4;
+  for (int k = warp; k < kl; k += nwarp) {
+    const int kg = me * kl + k;
+    float s = 0.f;
+    if (kg < p.n_valid) {
+      for (int c = lane; c < C; c += 32) s += pl[c] * Wl[(size_t)k * C + c];
+      s = warp_sum(s);
+      s += bl ? bl[k] : 0.f;
+    } else {
+      s = -INFINITY;                          // class padding (10 classes over 8 ranks -> 16): masked
+    }
+    if (lane < W) *reinterpret_cast<float*>(p.heap[lane] + lrow + k * 4) = s;
+  }
+  __threadfence_system();
+  __syncthreads();
+  unsigned* cnt_lg = reinterpret_cast<unsigned*>(my_heap + p.cnt_off) + n;
+  unsigned* cnt_df = cnt_lg + p.N;
+  if (W > 1) {
+    if (p.nvls) {
+      if (threadIdx.x == 0) multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + n, 1u);
+    } else if (threadIdx.x < W) {
+      red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.cnt_off) + n, 1u);
+    }
+    if (threadIdx.x == 0) spin_until_ge(cnt_lg, (unsigned)W * e, p.timeout_clk);
+    __syncthreads();
+  }
+  const float* lrow_all = reinterpret_cast<const float*>(my_heap + p.logits_off + (long long)par * p.par_stride_logits) + (size_t)n * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) lg[k] = __ldcg(lrow_all + k);
+  __syncthreads();
+  // ---- softmax cross-entropy over the gathered row (identical on every rank)
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int k = lane; k < K; k += 32) mx = fmaxf(mx, lg[k]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int k = lane; k < K; k += 32) se += __expf(lg[k] - mx);
+    se = warp_sum(se);
+    const float lse = mx + __logf(se);
+    const int lab = (int)labels[n];
+    int best = K;
+    for (int k = lane; k < K; k += 32) if (lg[k] == mx) best = min(best, k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    for (int k = lane; k < K; k += 32) {
+      const float pr = __expf(lg[k] - lse);
+      const float d = (pr - (k == lab ? 1.f : 0.f)) * (p.loss_scale / (float)p.N);
+      dl[k] = d;
+      if (logits_out) logits_out[(size_t)n * K + k] = lg[k];
+      if (k >= me * kl && k < (me + 1) * kl) dl_local[(size_t)n * kl + (k - me * kl)] = d;
+    }
+    if (lane == 0) {
+      atomicAdd(loss_out, (lse - lg[lab]) * (p.loss_scale / (float)p.N));
+      if (best == lab) atomicAdd(correct_out, 1.f);
+    }
+  }
+  __syncthreads();
+  if (dfeat != nullptr) {
+    // ---- dX = sum_r dY_r . W_r : my partial (fp32) -> my slot, arrival, pull-reduce over the ranks
+    const long long drow = p.dfeat_off + (long long)par * p.par_stride_dfeat + (long long)n * C * 4;
+    float* mine = reinterpret_cast<float*>(my_heap + drow);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < kl; ++k)
+        if (me * kl + k < p.n_valid) s += dl[me * kl + k] * Wl[(size_t)k * C + c];
+      mine[c] = s;
+    }
+    if (W > 1) {
+      __threadfence_system();
+      __syncthreads();
+      if (p.nvls) {
+        if (threadIdx.x == 0) multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + p.N + n, 1u);
+      } else if (threadIdx.x < W) {
+        red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.cnt_off) + p.N + n, 1u);
+      }
+      if (threadIdx.x == 0) spin_until_ge(cnt_df, (unsigned)W * e, p.timeout_clk);
+      __syncthreads();
+    }
+    for (int c4 = threadIdx.x * 4; c4 < C; c4 += blockDim.x * 4) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (W > 1 && p.nvls) {
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p.mc_heap + drow + c4 * 4) : "memory");
+      } else {
+        float4 v[kTpMaxRanks];
+#pragma unroll
+        for (int rr = 0; rr < kTpMaxRanks; ++rr)
+          if (rr < W) v[rr] = __ldcg(reinterpret_cast<const float4*>(p.heap[rr] + drow + c4 * 4));
+#pragma unroll
+        for (int rr = 0; rr < kTpMaxRanks; ++rr)
+          if (rr < W) { a.x += v[rr].x; a.y += v[rr].y; a.z += v[rr].z; a.w += v[rr].w; }
+      }
+      const float g[4] = {a.x * inv_hw, a.y * inv_hw, a.z * inv_hw, a.w * inv_hw};
+      for (int q = 0; q < p.HW; ++q) {
+        __nv_bfloat16* d = dfeat + ((size_t)n * p.HW + q) * C + c4;
+        *reinterpret_cast<__nv_bfloat162*>(d) = __floats2bfloat162_rn(g[0], g[1]);
+        *reinterpret_cast<__nv_bfloat162*>(d + 2) = __floats2bfloat162_rn(g[2], g[3]);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned fin = atomicAdd(p.done, 1u);
+    if (fin == (unsigned)(gridDim.x - 1)) {
+      *p.done = 0u;
+      *p.epoch = e;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone bf16 all-reduce (sum) of a small activation tensor over the symmetric heap - the reduction point
+// of a tensor-parallel layer whose GEMM cannot take the fused kernel (grid larger than the SM count).  Same
+// protocol as the fused epilogue: copy in -> arrival counter -> multimem.ld_reduce / rank-ordered peer pull.
+// ------------------------------------------------------------------------------------------------
+struct TpArParams {
+  int world, rank, nvls;
+  char* heap[kTpMaxRanks];
+  char* mc_heap;
+  long long buf_off, buf_stride;     // bf16 [2 parities][n]
+  long long cnt_off;                 // u32 [gridDim.x]
+  unsigned* epoch; unsigned* done;
+  long long timeout_clk;
+};
+
+__global__ void __launch_bounds__(256) tp_allreduce_bf16_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                __nv_bfloat16* __restrict__ out, size_t nvec,
+                                                                const TpArParams p) {
+  pdl_launch();
+  pdl_wait();
+  const int W = p.world, me = p.rank;
+  const unsigned e = *p.epoch + 1u;
+  const long long boff = p.buf_off + (long long)(e & 1u) * p.buf_stride;
+  const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  const size_t lo = min((size_t)blockIdx.x * per, nvec), hi = min(lo + per, nvec);
+  uint4* mine = reinterpret_cast<uint4*>(p.heap[me] + boff);
+  for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) mine[v] = reinterpret_cast<const uint4*>(in)[v];
+  __threadfence_system();
+  __syncthreads();
+  if (p.nvls) {
+    if (threadIdx.x == 0) multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + blockIdx.x, 1u);
+  } else if (threadIdx.x < W) {
+    red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.cnt_off) + blockIdx.x, 1u);
+  }
+  if (threadIdx.x == 0)
+    spin_until_ge(reinterpret_cast<unsigned*>(p.heap[me] + p.cnt_off) + blockIdx.x, (unsigned)W * e, p.timeout_clk);
+  __syncthreads();
+  for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+    uint4 o;
+    if (p.nvls) {
+      o = multimem_ld_reduce_bf16x8(p.mc_heap + boff + v * 16);
+    } else {
+      uint4 w[kTpMaxRanks];
+#pragma unroll
+      for (int r = 0; r < kTpMaxRanks; ++r)
+        if (r < W) w[r] = __ldcg(reinterpret_cast<const uint4*>(p.heap[r] + boff) + v);
+      float a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < kTpMaxRanks; ++r)
+        if (r < W) {
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(&w[r]), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] += f[i];
+        }
+      const bf16x8 pk = pack8(a);
+      o = *reinterpret_cast<const uint4*>(&pk);
+    }
+    reinterpret_cast<uint4*>(out)[v] = o;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned fin = atomicAdd(p.done, 1u);
+    if (fin == gridDim.x - 1) {
+      *p.done = 0u;
+      *p.epoch = e;
+      __threadfence();
+    }
+  }
+}
+
 }  // namespace hz
 
 // ================================================================================================
@@ -304,83 +634,162 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
 // ================================================================================================
 using namespace hz::host;
 
+namespace {
+long long tp_timeout_clk() {
+  static const long long v = [] {
+    const char* e = getenv("HZ_COMM_TIMEOUT_S");
+    const double sec = e ? atof(e) : 0.0;
+    return (long long)((sec > 0.0 ? sec : 20.0) * 1.9e9);       // clock64 ticks at ~1.9 GHz
+  }();
+  return v;
+}
+}  // namespace
+
 extern "C" {
 
-// layout helper: bytes needed in the symmetric heap for the flag/workspace part of one fused op
-size_t hz_tp_ws_bytes(int world, int tiles) {
-  return (size_t)world * tiles * 128 * 64 * sizeof(float);
+// tiles of the fused op over output [N, H, W, n_out] (per parity class for stride-2 dgrad), or -1
+int hz_tp_tiles(int kind, int N, int H, int W_, int Cin, int Cout, int stride) {
+  const int Nn = kind == 0 ? Cout : Cin;
+  const int Lh = (kind == 1 && stride == 2) ? H / 2 : H, Lw = (kind == 1 && stride == 2) ? W_ / 2 : W_;
+  Tile t;
+  if (!pick_tile(128, N, Lh, Lw, &t)) return -1;
+  return t.tiles * ((Nn + 63) / 64) * ((kind == 1 && stride == 2) ? 4 : 1);
 }
 
-// y (in the symmetric heap at out_off on every rank) = [all-reduce|reduce-scatter] over ranks of conv(x_r, w_r)
-// or, with ag=1, conv(all-gather(x shards), w_local).  kind: 0 = forward (w K-major), 1 = dgrad (w MN-major).
-// heaps[r]: heap base of rank r.  x_ptrs[r]: rank r's A buffer (only [rank] is used unless ag).
-// Stride-1 convs and dense GEMMs only (H=W=1, R=1).
-int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, char* const* heaps, long long out_off,
-               long long ws_off, long long ws_stride, long long arrive_off, long long result_off,
-               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int reduce, int bcast,
-               int ag, int N, int H, int W_, int Cin, int Cout, int R, int pad, cudaStream_t st) {
-  // logical conv: x [N,H,W,Cin] -> y [N,H,W,Cout] (fwd)   |   dy [N,H,W,Cout] -> dx [N,H,W,Cin] (dgrad)
+// y = [all-reduce | reduce-scatter | nothing] over ranks of conv(x_r, w_r)   (kind 0: forward, stride 1)
+// or of dgrad(dy_r, w_r) (kind 1: w MN-major, stride 1 or 2; H, W_ are the INPUT (dx) extents).
+// With ag=1 (kind 0) the A operand is image-sharded: x_ptrs[r] is rank r's shard inside its heap.
+// heaps[r]: heap base of rank r as mapped here; mc_heap: multicast mapping (nvls) or null.
+int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, const void* addend, float* stats,
+               char* const* heaps, char* mc_heap, long long part_off, long long part_stride, long long cnt_off,
+               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int mode, int nvls, int ag,
+               int N, int H, int W_, int Cin, int Cout, int R, int stride, int pad, cudaStream_t st) {
   const int S_ = R;
+  if (kind == 0 && stride != 1) return -23;
+  if ((Cin | Cout) & 7) return -20;
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W_ + 2 * pad - S_) / stride + 1;
   const int Ka = kind == 0 ? Cin : Cout;       // channels of the A operand
   const int Nn = kind == 0 ? Cout : Cin;       // output channels
-  if (Ka % 64 || Nn % 64) return -20;
+  // output lattice (per class): fwd (Ho,Wo) == (H,W_); dgrad stride 1 (H,W_), stride 2 (H/2,W_/2)
+  const int Lh = (kind == 1 && stride == 2) ? H / 2 : H, Lw = (kind == 1 && stride == 2) ? W_ / 2 : W_;
+  if (kind == 1 && stride == 2 && (Lh != Ho || Lw != Wo)) return -13;
   Tile t;
-  if (!pick_tile(128, N, H, W_, &t)) return -10;
-  constexpr int BLOCK_N = 64;
-  const int tiles = t.tiles * (Nn / BLOCK_N);
+  if (!pick_tile(128, N, Lh, Lw, &t)) return -10;
+  const int classes = (kind == 1 && stride == 2) ? 4 : 1;
+  const int n_tiles = (Nn + 63) / 64;
+  const int tiles = t.tiles * n_tiles * classes;
   if (tiles > 148) return -21;                 // all CTAs must be co-resident (they spin on peers)
+  if (mode == 2 && tiles < world) return -24;  // reduce-scatter: every rank must own a tile (keeps ranks in step)
   const int imgs_per_rank = ag ? N / world : N;
-  if (ag && (N % world || (t.BN > 1 && imgs_per_rank % t.BN))) return -22;
+  if (ag && (kind != 0 || N % world || (t.BN > 1 && imgs_per_rank % t.BN))) return -22;
   hz::PeerAMaps am;
   memset(&am, 0, sizeof(am));
+  const int Ha = kind == 0 ? H : Ho, Wa = kind == 0 ? W_ : Wo;      // extents of the A tensor
   for (int r = 0; r < world; ++r) {
-    const void* base = ag ? x_ptrs[r] : x_ptrs[rank];
-    if (!ag && r != rank) { am.m[r] = am.m[rank]; continue; }
-    if (!make_map4(&am.m[r], base, Ka, W_, H, imgs_per_rank, Ka, (long long)W_ * Ka, (long long)H * W_ * Ka, 64, t.BW,
-                   t.BH, t.BN))
+    if (!ag && r != rank) continue;
+    if (!make_map4(&am.m[r], x_ptrs[r], Ka, Wa, Ha, imgs_per_rank, Ka, (long long)Wa * Ka, (long long)Ha * Wa * Ka, 64,
+                   t.BW, t.BH, t.BN))
       return -11;
-    if (!ag) break;
   }
   if (!ag) for (int r = 0; r < world; ++r) if (r != rank) am.m[r] = am.m[rank];
   CUtensorMap bm;
-  if (kind == 0) {
-    if (!make_map2(&bm, w, (long long)R * S_ * Cin, Cout, (long long)R * S_ * Cin, 64, BLOCK_N)) return -12;
-  } else {
-    if (!make_map2(&bm, w, (long long)R * S_ * Cin, Cout, (long long)R * S_ * Cin, 64, 64)) return -12;
-  }
+  if (!make_map2(&bm, w, (long long)R * S_ * Cin, Cout, (long long)R * S_ * Cin, 64, 64)) return -12;
   hz::TpParams p;
   memset(&p, 0, sizeof(p));
-  p.taps.n = 0;
-  for (int r = 0; r < R; ++r)
-    for (int s = 0; s < S_; ++s) {
-      const int dh = kind == 0 ? r - pad : pad - r, dw = kind == 0 ? s - pad : pad - s;
-      if (!tap_hits(dh, H, H) || !tap_hits(dw, W_, W_)) continue;
-      const int i = p.taps.n++;
-      p.taps.dh[i] = (int8_t)dh; p.taps.dw[i] = (int8_t)dw; p.taps.map[i] = 0;
-      p.taps.bk[i] = (r * S_ + s) * Cin;
-    }
-  p.cblocks = Ka / 64;
+  p.num_classes = classes;
+  for (int c = 0; c < classes; ++c) {
+    hz::TapList& tl = p.cls[c];
+    tl.n = 0;
+    const int ph = c >> 1, pw = c & 1;
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S_; ++s) {
+        int dh, dw;
+        if (kind == 0) { dh = r - pad; dw = s - pad; }
+        else if (stride == 1) { dh = pad - r; dw = pad - s; }
+        else {
+          if (((ph + pad - r) & 1) || ((pw + pad - s) & 1)) continue;
+          dh = (ph + pad - r) / 2; dw = (pw + pad - s) / 2;
+        }
+        if (!tap_hits(dh, Lh, Ha) || !tap_hits(dw, Lw, Wa)) continue;
+        const int i = tl.n++;
+        tl.dh[i] = (int8_t)dh; tl.dw[i] = (int8_t)dw; tl.map[i] = 0;
+        tl.bk[i] = (r * S_ + s) * Cin;
+      }
+    p.cls_out_off[c] = (kind == 1 && stride == 2) ? ((long long)ph * W_ + pw) * Nn : 0;
+  }
+  p.cblocks = (Ka + 63) / 64;
   p.BN = t.BN; p.BH = t.BH; p.BW = t.BW; p.tiles_per_img = t.per_img;
   p.n_images = N;
-  p.out_n_stride = (long long)H * W_ * Nn; p.out_h_stride = (long long)W_ * Nn; p.out_w_stride = Nn;
+  const int so = (kind == 1) ? stride : 1;
+  const int Hout = kind == 0 ? Ho : H, Wout = kind == 0 ? Wo : W_;
+  p.out_n_stride = (long long)Hout * Wout * Nn; p.out_h_stride = (long long)so * Wout * Nn; p.out_w_stride = (long long)so * Nn;
   p.ncols = Nn;
-  p.world = world; p.rank = rank; p.reduce = reduce; p.bcast = bcast; p.ag = ag; p.ag_imgs = imgs_per_rank;
+  p.world = world; p.rank = rank; p.mode = world > 1 ? mode : 0; p.nvls = (nvls && mc_heap != nullptr && world > 1) ? 1 : 0;
+  p.ag = ag; p.ag_imgs = imgs_per_rank;
   for (int r = 0; r < world; ++r) p.heap[r] = heaps[r];
-  p.out_off = out_off; p.ws_off = ws_off; p.ws_stride = ws_stride; p.arrive_off = arrive_off; p.result_off = result_off;
-  p.ready_off = ready_off;
+  p.mc_heap = mc_heap;
+  p.part_off = part_off; p.part_stride = part_stride; p.cnt_off = cnt_off; p.ready_off = ready_off;
   p.epoch = epoch; p.done = done;
-  using SM = hz::IgemmSmem<BLOCK_N>;
-  dim3 grid(t.tiles, Nn / BLOCK_N, 1);
+  p.out = (__nv_bfloat16*)out; p.addend = (const __nv_bfloat16*)addend; p.stats = stats;
+  p.timeout_clk = tp_timeout_clk();
+  using SM = hz::IgemmSmem<64>;
+  dim3 grid(t.tiles, n_tiles, classes);
   if (kind == 0) {
-    static bool attr = set_smem(hz::igemm_tp_kernel<BLOCK_N, false>, SM::kTotal);
+    static bool attr = set_smem(hz::igemm_tp_kernel<false>, SM::kTotal);
     (void)attr;
-    hz::igemm_tp_kernel<BLOCK_N, false><<<grid, 128, SM::kTotal, st>>>(am, bm, p);
-  } else {
-    static bool attr = set_smem(hz::igemm_tp_kernel<BLOCK_N, true>, SM::kTotal);
-    (void)attr;
-    hz::igemm_tp_kernel<BLOCK_N, true><<<grid, 128, SM::kTotal, st>>>(am, bm, p);
+    return hz::launch(hz::igemm_tp_kernel<false>, grid, dim3(128), SM::kTotal, st, am, bm, p) == cudaSuccess ? 0 : -1;
   }
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  static bool attr = set_smem(hz::igemm_tp_kernel<true>, SM::kTotal);
+  (void)attr;
+  return hz::launch(hz::igemm_tp_kernel<true>, grid, dim3(128), SM::kTotal, st, am, bm, p) == cudaSuccess ? 0 : -1;
+}
+
+// Tensor-parallel classifier head (see tp_head_kernel).  Wl [k_local, C] fp32 (this rank's class rows), bl [k_local].
+// Outputs: pooled [N,C] f32, dl_local [N,k_local] f32 (inputs of the local dW/db kernel), logits [N,K] (optional),
+// dfeat [N,HW,C] bf16 (optional), loss / correct accumulators (pre-zeroed).
+int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t* labels, float* pooled,
+               float* dl_local, float* logits, void* dfeat, float* loss, float* correct, char* const* heaps,
+               char* mc_heap, long long logits_off, long long dfeat_off, long long cnt_off, unsigned* epoch,
+               unsigned* done, int world, int rank, int nvls, int N, int C, int HW, int k_local, int n_valid,
+               float loss_scale, cudaStream_t st) {
+  if (C & 3) return -20;
+  hz::TpHeadParams p;
+  memset(&p, 0, sizeof(p));
+  p.world = world; p.rank = rank; p.nvls = (nvls && mc_heap != nullptr && world > 1) ? 1 : 0;
+  p.N = N; p.C = C; p.HW = HW; p.K = k_local * world; p.k_local = k_local; p.n_valid = n_valid;
+  p.loss_scale = loss_scale;
+  for (int r = 0; r < world; ++r) p.heap[r] = heaps[r];
+  p.mc_heap = mc_heap;
+  p.logits_off = logits_off; p.dfeat_off = dfeat_off; p.cnt_off = cnt_off;
+  p.par_stride_logits = (long long)N * p.K * 4;
+  p.par_stride_dfeat = (long long)N * C * 4;
+  p.epoch = epoch; p.done = done;
+  p.timeout_clk = tp_timeout_clk();
+  if (N > 148) return -21;
+  const size_t smem = sizeof(float) * (C + 2 * p.K);
+  return hz::launch(hz::tp_head_kernel, dim3(N), dim3(128), smem, st, (const __nv_bfloat16*)feat, Wl, bl, labels,
+                    pooled, dl_local, logits, (__nv_bfloat16*)dfeat, loss, correct, p) == cudaSuccess ? 0 : -1;
+}
+
+size_t hz_tp_head_bytes(int N, int C, int K) { return 2 * ((size_t)N * K * 4 + (size_t)N * C * 4) + 2 * (size_t)N * 4 + 64; }
+
+// out = sum over ranks of `in` (bf16, n elements, n % 8 == 0); buf: bf16 [2][n] in the heap, cnt: u32 [blocks]
+int hz_tp_allreduce_bf16(const void* in, void* out, size_t n, char* const* heaps, char* mc_heap, long long buf_off,
+                         long long cnt_off, unsigned* epoch, unsigned* done, int world, int rank, int nvls, int blocks,
+                         cudaStream_t st) {
+  if (n & 7) return -20;
+  hz::TpArParams p;
+  memset(&p, 0, sizeof(p));
+  p.world = world; p.rank = rank; p.nvls = (nvls && mc_heap != nullptr && world > 1) ? 1 : 0;
+  for (int r = 0; r < world; ++r) p.heap[r] = heaps[r];
+  p.mc_heap = mc_heap;
+  p.buf_off = buf_off; p.buf_stride = (long long)n * 2; p.cnt_off = cnt_off;
+  p.epoch = epoch; p.done = done;
+  p.timeout_clk = tp_timeout_clk();
+  if (blocks < 1) blocks = 1;
+  if (blocks > 64) blocks = 64;
+  return hz::launch(hz::tp_allreduce_bf16_kernel, dim3(blocks), dim3(256), 0, st, (const __nv_bfloat16*)in,
+                    (__nv_bfloat16*)out, n / 8, p) == cudaSuccess ? 0 : -1;
 }
 
 }  // extern "C"

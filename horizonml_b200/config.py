@@ -42,6 +42,7 @@ class TrainConfig:
     bucket_by_live: bool = False      # with dead-tap elision, size buckets by LIVE elements using live_bucket_mb
     live_bucket_mb: float = 2.0       # (fp32 MiB of live gradient per bucket; the last bucket's collective is exposed)
     microbatches: int = 4             # pipeline micro-batches (1F1B)
+    pp_overlap: bool = True           # GPUs: per-direction NCCL channels + streams, prefetched receives (no host wait between graphs)
     dp_replicas: int = 1              # hybrid DP x PP / DP x TP mesh: number of data-parallel replicas of the pipeline / TP group
     tp_conv_split: bool = True        # channel-split layer3/4 convs in tensor-parallel mode
     synthetic: bool = True            # no network in this environment: synthetic CIFAR-shaped data
@@ -108,6 +109,8 @@ def add_train_flags(p: argparse.ArgumentParser, strategy: str) -> argparse.Argum
     g.add_argument('--bucket_by_live', action='store_true')
     g.add_argument('--live_bucket_mb', type=float, default=d.live_bucket_mb)
     g.add_argument('--microbatches', type=int, default=d.microbatches)
+    g.add_argument('--no_pp_overlap', dest='pp_overlap', action='store_false',
+                   help='pipeline: blocking batch_isend_irecv exchanges on the compute stream (round-1 schedule)')
     g.add_argument('--dp_replicas', type=int, default=d.dp_replicas,
                    help='hybrid mesh: replicate the pipeline / tensor-parallel group this many times (world_size = dp_replicas x stages)')
     g.add_argument('--no_tp_conv_split', dest='tp_conv_split', action='store_false')

@@ -168,6 +168,13 @@ def init_distributed(rank: int, world_size: int, device: str, comm: str = "auto"
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29500")
     backend = comm if comm != "auto" else ("nccl" if device == "cuda" else "gloo")
+    # compute, wgrad side stream, comm stream, one stream per pipeline channel plus NCCL's own: with the default 8
+    # hardware queues two of them can share a queue, and a parked receive would then hold up unrelated kernels
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+    if os.environ["MASTER_ADDR"] in ("127.0.0.1", "localhost"):
+        # one node: gloo would otherwise derive its interface from the host name, which need not resolve in a container
+        # (every pair connection then times out); NCCL's bootstrap socket has the same habit
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
     kw = {}
     if device == "cuda":
         local = int(os.environ.get("LOCAL_RANK", rank)) % max(torch.cuda.device_count(), 1)

@@ -158,8 +158,8 @@ class _ConvBNAct(torch.autograd.Function):
         if fused is not None:
             y_raw, out, mean, invstd = fused
         else:
-            if conv_fn is not None:        # fused GEMM + collective kernel (tensor parallel): already reduced
-                y_raw, sums = conv_fn(x, w), None
+            if conv_fn is not None:        # fused GEMM + collective kernel (tensor parallel): already reduced,
+                y_raw, sums = conv_fn(x, w, training)      # BN partial sums of the REDUCED output from its epilogue
             else:
                 y_raw, sums = be.conv_fwd(x, w, stride, pad, training and post_conv is None)
                 if post_conv is not None:  # row-parallel conv: partial sums → all-reduce before BN
@@ -205,10 +205,8 @@ class _ConvBNAct(torch.autograd.Function):
         if ctx.x_needs_grad:
             link = ctx.in_link
             addend = link.take() if link is not None else None
-            if ctx.dgrad_fn is not None:                      # fused dgrad GEMM + all-reduce
-                dx = ctx.dgrad_fn(dy, w)
-                if addend is not None:
-                    dx = dx + addend
+            if ctx.dgrad_fn is not None:                      # fused dgrad GEMM + all-reduce (+ residual-gradient addend)
+                dx = ctx.dgrad_fn(dy, w, addend)
             else:
                 if ctx.post_dgrad is None:
                     dx = be.conv_dgrad(dy, w, x.shape, stride, pad, addend)
@@ -235,12 +233,13 @@ def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True,
                 momentum=0.1, eps=1e-5, training=True, post_conv=None, post_dgrad=None,
                 conv_fn=None, dgrad_fn=None, in_link=None, res_link=None):
     """``post_conv`` / ``post_dgrad`` are the tensor-parallel reduction points (row-parallel conv
-    output, column-parallel conv input-gradient); they take and return a tensor.  ``conv_fn(x, w)`` /
-    ``dgrad_fn(dy, w)`` replace conv + reduction by ONE fused GEMM+collective kernel."""
+    output, column-parallel conv input-gradient); they take and return a tensor.  ``conv_fn(x, w, want_stats) ->
+    (y, sums | None)`` / ``dgrad_fn(dy, w, addend) -> dx`` replace conv + reduction (+ BN statistics pass / residual
+    gradient add) by ONE fused GEMM+collective kernel."""
     if not training or not torch.is_grad_enabled():
         be = _be(x)
         if conv_fn is not None:
-            y_raw, sums = conv_fn(x, compute_weight(weight, x.dtype)), None
+            y_raw, sums = conv_fn(x, compute_weight(weight, x.dtype), training)
         else:
             y_raw, sums = be.conv_fwd(x, compute_weight(weight, x.dtype), stride, pad,
                                       training and post_conv is None)

@@ -265,3 +265,171 @@ class GraphedMicroBatch:
             self.dy.copy_(dout, non_blocking=True)
         self.gb.replay()
         return self.dx
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Overlapped 1F1B on GPUs: the pipeline as a pipeline
+# ----------------------------------------------------------------------------------------------------------
+class P2PChannels:
+    """One NCCL communicator **and** one CUDA stream per (neighbour, direction) of a pipeline stage.
+
+    A channel is used in one direction only (activations down *or* gradients up), in micro-batch order on both
+    ends, so a send can only ever wait for its own matching receive — which the receiver posts ahead of time —
+    never for traffic of the opposite direction queued on the same communicator (the reason the blocking runner
+    has to issue facing pairs as one ``batch_isend_irecv`` group).  A posted ``irecv`` parks on its own stream:
+    nothing else is serialised behind it.  Every rank creates every channel group in the same order
+    (``pipelines`` = the global ranks of every pipeline row, stage-major)."""
+
+    def __init__(self, rank: int, pipelines: Sequence[Sequence[int]], device):
+        self.device = torch.device(device)
+        self.recv_fwd = self.send_fwd = self.recv_bwd = self.send_bwd = None      # (group, peer global rank)
+        for row in pipelines:
+            for s in range(len(row) - 1):
+                a, b = row[s], row[s + 1]
+                g_down = dist.new_group([a, b])          # activations a -> b
+                g_up = dist.new_group([a, b])            # gradients  b -> a
+                if rank == a:
+                    self.send_fwd, self.recv_bwd = (g_down, b), (g_up, b)
+                if rank == b:
+                    self.recv_fwd, self.send_bwd = (g_down, a), (g_up, a)
+        mk = lambda ch: torch.cuda.Stream(device=self.device) if ch is not None else None   # noqa: E731
+        self.streams = {k: mk(getattr(self, k)) for k in ("recv_fwd", "send_fwd", "recv_bwd", "send_bwd")}
+        self.bytes_sent = 0
+
+    def post(self, kind: str, tensor: torch.Tensor, after: Sequence[torch.cuda.Event] = ()) -> torch.cuda.Event:
+        """Enqueue one transfer on the channel's own stream (after ``after``); returns the event that fires when the
+        payload has arrived (recv) / left the buffer (send).  Never blocks the host or the compute stream."""
+        group, peer = getattr(self, kind)
+        st = self.streams[kind]
+        for ev in after:
+            if ev is not None:
+                st.wait_event(ev)
+        with torch.cuda.stream(st):
+            if kind.startswith("send"):
+                self.bytes_sent += tensor.numel() * tensor.element_size()
+                w = dist.isend(tensor, peer, group=group)
+            else:
+                w = dist.irecv(tensor, peer, group=group)
+            w.wait()                      # orders the channel stream behind the NCCL kernel (no host block)
+            done = torch.cuda.Event()
+            done.record(st)
+        return done
+
+    def end_step(self) -> int:
+        b, self.bytes_sent = self.bytes_sent, 0
+        return b
+
+
+class OverlappedPipelineRunner:
+    """1F1B over CUDA-graphed micro-batch slots with every exchange on its own channel stream.
+
+    Per micro-batch ``i`` (slot ``i % nslots``) the host only *enqueues*:
+
+    * ``irecv`` of the activation **straight into the slot's static input** — posted as soon as the slot is free,
+      i.e. one or more micro-batches ahead of its forward (one spare slot beyond the 1F1B in-flight bound makes
+      that window exist), so the transfer overlaps the stage's own compute;
+    * forward graph replay behind the arrival event; ``isend`` of the slot's static output fired from an event
+      recorded right after the replay; ``irecv`` of the matching gradient into the slot's static ``dy``;
+    * backward graph replay behind the gradient's arrival event; ``isend`` of the slot's static ``dx``.
+
+    There is no host ``wait()`` and no copy between graph replays; the compute stream blocks only where the data
+    dependency is real.  ``stall_ms()`` reports how long it was blocked behind arrivals (exposed p2p + pipeline
+    bubble — the reference's blocking send/recv "comm_time", layer_model_parallel_train.py:188-209)."""
+
+    def __init__(self, stage: int, num_stages: int, slots: List["GraphedMicroBatch"], channels: P2PChannels, device,
+                 timing: bool = True):
+        self.stage, self.S = stage, num_stages
+        self.first, self.last = stage == 0, stage == num_stages - 1
+        self.slots, self.ch, self.device = slots, channels, torch.device(device)
+        self.timing = timing
+        self._stalls: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+        self.trace: List[Tuple[str, int]] = []
+        n = len(slots)
+        self._bwd_done: List[Optional[torch.cuda.Event]] = [None] * n     # slot's last backward finished (inputs reusable)
+        self._sent_fwd: List[Optional[torch.cuda.Event]] = [None] * n     # slot's output has left (forward may overwrite it)
+        self._sent_bwd: List[Optional[torch.cuda.Event]] = [None] * n     # slot's dx has left (backward may overwrite it)
+
+    @staticmethod
+    def _phys(t: torch.Tensor) -> torch.Tensor:
+        """The dense NHWC storage view of a channels_last activation (what travels)."""
+        return t.detach().permute(0, 2, 3, 1)
+
+    def _wait(self, cur, ev):
+        if ev is None:
+            return
+        if self.timing:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(cur)
+            cur.wait_event(ev)
+            b.record(cur)
+            self._stalls.append((a, b))
+        else:
+            cur.wait_event(ev)
+
+    def stall_ms(self) -> float:
+        """Σ time the compute stream was blocked behind arrivals since the last call (one device sync)."""
+        st, self._stalls = self._stalls, []
+        if not st:
+            return 0.0
+        torch.cuda.synchronize(self.device)
+        return float(sum(a.elapsed_time(b) for a, b in st))
+
+    def run(self, M: int, first_inputs: Optional[Sequence] = None, labels: Optional[Sequence] = None):
+        ns = len(self.slots)
+        cur = torch.cuda.current_stream(self.device)
+        acts = one_f_one_b(self.stage, self.S, M)
+        recv_f: List[Optional[torch.cuda.Event]] = [None] * M
+        recv_b: List[Optional[torch.cuda.Event]] = [None] * M
+        posted_f = b_enq = 0
+        loss_sum = correct_sum = None
+        self.trace = []
+
+        def prefetch_fwd():
+            """post the activation receive of every micro-batch whose slot is free: its previous owner's backward
+            has been enqueued (``_bwd_done`` then holds that backward's event)"""
+            nonlocal posted_f
+            while not self.first and posted_f < M and (posted_f < ns or posted_f - ns < b_enq):
+                i = posted_f
+                recv_f[i] = self.ch.post("recv_fwd", self._phys(self.slots[i % ns].x), after=[self._bwd_done[i % ns]])
+                posted_f += 1
+
+        prefetch_fwd()
+        for a, i in acts:
+            s = i % ns
+            slot = self.slots[s]
+            if a == "F":
+                if self.first:
+                    slot.x.copy_(first_inputs[i], non_blocking=True)
+                else:
+                    self._wait(cur, recv_f[i])
+                if self.last:
+                    slot.labels.copy_(labels[i], non_blocking=True)
+                if self._sent_fwd[s] is not None:
+                    cur.wait_event(self._sent_fwd[s])
+                slot.gf.replay()
+                self.trace.append(("F", i))
+                if self.last:
+                    loss, correct = slot.out
+                    loss_sum = loss.detach().clone() if loss_sum is None else loss_sum + loss.detach()
+                    correct_sum = correct.detach().clone() if correct_sum is None else correct_sum + correct.detach()
+                else:
+                    done = torch.cuda.Event()
+                    done.record(cur)
+                    self._sent_fwd[s] = self.ch.post("send_fwd", self._phys(slot.out), after=[done])
+                    # the gradient of this micro-batch comes back into the slot's static dy
+                    recv_b[i] = self.ch.post("recv_bwd", self._phys(slot.dy), after=[self._bwd_done[s]])
+            else:
+                if not self.last:
+                    self._wait(cur, recv_b[i])
+                if self._sent_bwd[s] is not None:
+                    cur.wait_event(self._sent_bwd[s])
+                slot.gb.replay()
+                self.trace.append(("B", i))
+                done = torch.cuda.Event()
+                done.record(cur)
+                self._bwd_done[s] = done
+                b_enq += 1
+                if not self.first:
+                    self._sent_bwd[s] = self.ch.post("send_bwd", self._phys(slot.dx), after=[done])
+            prefetch_fwd()
+        return loss_sum, correct_sum

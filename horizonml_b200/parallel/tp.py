@@ -34,7 +34,8 @@ from ..ops.functional import grad_target, grad_written
 
 
 class TPComm:
-    """Reduction / gather points of the tensor-parallel group."""
+    """Reduction / gather points of the tensor-parallel group.  On GPUs with the native backend every one of them
+    is a hand-written peer-memory kernel (``FusedTP``): no NCCL call is left inside the training step."""
 
     def __init__(self, group=None, fused: "Optional[FusedTP]" = None):
         self.group = group
@@ -42,11 +43,19 @@ class TPComm:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bytes = 0
         self.fused = fused          # fused GEMM+collective kernels (CUDA, native backend) or None
+        self.library_collectives = 0   # calls that went through torch.distributed (must stay 0 on the GPU hot path)
 
     def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
         if self.world == 1:
             return t
         self.bytes += t.numel() * t.element_size()
+        f = self.fused
+        if f is not None and t.is_cuda and t.dtype == torch.bfloat16 and t.numel() % 8 == 0:
+            # stand-alone peer-pull all-reduce kernel (csrc/tp_fused.cu): the reduction point of a layer whose
+            # GEMM could not take the fused kernel (e.g. more tiles than SMs at a large batch)
+            dense = t if t.is_non_overlapping_and_dense() else t.contiguous(memory_format=torch.channels_last)
+            return f.allreduce_bf16(dense)
+        self.library_collectives += 1
         if t.dim() == 4:     # c10d wants a dense tensor: reduce the physical NHWC buffer
             phys = t.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
             dist.all_reduce(phys, group=self.group)
@@ -60,6 +69,7 @@ class TPComm:
         if self.world == 1:
             return local
         self.bytes += local.numel() * local.element_size() * (self.world - 1)
+        self.library_collectives += 1
         parts = [torch.empty_like(local) for _ in range(self.world)]
         dist.all_gather(parts, local.contiguous(), group=self.group)
         return torch.cat(parts, dim=1)
@@ -73,108 +83,137 @@ class TPComm:
 
 
 class FusedTP:
-    """Fused tcgen05 GEMM + collective ops over a CUDA-IPC symmetric heap (csrc/tp_fused.cu).
+    """Fused tcgen05 GEMM + collective ops over a symmetric heap (csrc/tp_fused.cu, parallel/symm.py).
 
-    ``allreduce_conv(kind, x_shape, n_out, R, pad)`` returns a callable ``op(a, w) -> y`` that runs ONE kernel:
-    implicit-GEMM conv of the local shard + push-reduce of the partial tiles to their owner rank +
-    broadcast of the finished tiles to every rank (kind 0 = forward of a row-parallel conv, 1 = dgrad
-    of a column-parallel conv).  ``ag_conv`` is the all-gather→GEMM variant (A pulled from the peers
-    by TMA).  Every rank must create the ops in the same order (symmetric offsets)."""
+    ``conv(kind, x_shape, w_shape, stride, pad, mode)`` returns ``op(a, w, addend=None, stats=None) -> y`` that
+    runs ONE kernel: implicit-GEMM conv of the local shard (kind 0 = forward of a row-parallel conv, 1 = dgrad of
+    a column-parallel conv) whose epilogue drops the bf16 partial tile into this rank's heap slot, bumps the
+    tile's arrival counter on the peers (one ``multimem.red`` through the NVSwitch when the heap is
+    multicast-mapped) and pulls the reduced tile back (``multimem.ld_reduce`` or rank-ordered bulk copies of the
+    peers' slots) — then BN partial sums / residual-gradient addend / store, like the dense conv epilogue.
+    ``ag_conv`` is the all-gather→GEMM variant (A tiles pulled from the peers by TMA), ``head`` the classifier,
+    ``allreduce_bf16`` the stand-alone reduction.  Every rank must create its ops in the same order (symmetric
+    offsets).  ``x_shape`` is always the conv's *input* shape [N, Cin, H, W] (for kind 1: the shape of dx)."""
 
-    def __init__(self, device, group=None, heap_mb: int = 256):
+    PART = 128 * 64 * 2
+
+    def __init__(self, device, group=None, heap_mb: int = 64, heap=None):
         from ..ops import _ext
+        from .symm import SymmHeap
         self.C = _ext.load(required=True)
         self.device = torch.device(device)
+        self.heap = heap if heap is not None else SymmHeap(self.device, heap_mb << 20, group)
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.comm = self.C.PeerComm(self.rank, self.world, self.device.index or 0, 1024, 8, heap_mb << 20)
-        if self.world > 1:
-            objs = [None] * self.world
-            dist.all_gather_object(objs, bytes(self.comm.export_handles()), group=group)
-            self.comm.import_handles([bytes(o) for o in objs])
-            dist.barrier(group=group)
-        self.off = 0
-        self.ws_off = None
-        self.ws_bytes = 0
+        self.world, self.rank = self.heap.world, self.heap.rank
+        self.nvls = self.heap.nvls
         self.bytes_moved = 0
+        self.ops: List[dict] = []
+        self._ar_ops = {}
 
-    def alloc(self, nbytes: int, align: int = 1024) -> int:
-        off = (self.off + align - 1) // align * align
-        if off + nbytes > self.comm.heap_bytes():
-            raise MemoryError("symmetric heap exhausted")
-        self.off = off + nbytes
-        return off
+    # ---- capability ------------------------------------------------------------------------------
+    def tiles_for(self, kind, x_shape, cout, stride=1):
+        t = int(self.C.tp_tiles(kind, list(x_shape), int(cout), int(stride)))
+        return t if t > 0 else None
 
-    @staticmethod
-    def tiles_for(n, h, w, n_out):
-        if h * w >= 128:
-            if 128 % w or h % (128 // w):
-                return None
-            tm = n * (h // (128 // w))
-        else:
-            if 128 % (h * w):
-                return None
-            tm = -(-n // (128 // (h * w)))
-        return tm * (n_out // 64)
-
-    def supported(self, a_shape, n_out) -> bool:
-        n, ca, h, w = a_shape
-        t = self.tiles_for(n, h, w, n_out) if (ca % 64 == 0 and n_out % 64 == 0) else None
+    def supported(self, kind, x_shape, cout, stride=1) -> bool:
+        n, cin, h, w = x_shape
+        if cin % 8 or cout % 8 or (kind == 0 and stride != 1) or (stride == 2 and (h % 2 or w % 2)):
+            return False
+        t = self.tiles_for(kind, x_shape, cout, stride)
         return t is not None and t <= 148
 
-    def _ensure_ws(self, tiles):
-        need = self.world * tiles * 128 * 64 * 4
-        if self.ws_off is None or need > self.ws_bytes:
-            self.ws_off, self.ws_bytes = self.alloc(max(need, 4 << 20)), max(need, 4 << 20)
+    def _wire(self, tiles):     # bytes this rank receives per call
+        return tiles * self.PART * (1 if self.nvls else max(self.world - 1, 0))
 
-    def _make(self, kind, a_shape, n_out, R, pad, reduce, bcast, ag, x_off=0):
-        n, ca, h, w = a_shape
-        tiles = self.tiles_for(n, h, w, n_out)
-        if reduce == 2:
-            # one-shot has no result-flag back-pressure: private slots, double-buffered by call parity
-            ws_stride = self.world * tiles * 128 * 64 * 4
-            ws_off = self.alloc(2 * ws_stride)
-        else:
-            self._ensure_ws(tiles)
-            ws_off, ws_stride = self.ws_off, 0
-        out_off = self.alloc(n * h * w * n_out * 2)
-        flags_off = self.alloc(4 * (tiles * self.world + tiles + self.world + 2))
-        out = self.comm.heap_tensor(out_off, [n, n_out, h, w], [h * w * n_out, 1, w * n_out, n_out], "bf16")
-        comm = self.comm
-        wire = (self.world - 1) * tiles * 128 * 64 * (4 + 2) // max(self.world, 1)
+    # ---- ops ---------------------------------------------------------------------------------------
+    def conv(self, kind, x_shape, w_shape, stride=1, pad=1, mode="allreduce", ag_off=None):
+        h = self.heap
+        cout = w_shape[0]
+        tiles = self.tiles_for(kind, x_shape, cout, stride)
+        if tiles is None or tiles > 148:
+            raise ValueError(f"fused TP conv does not fit: {x_shape} -> {cout}, tiles={tiles}")
+        m = {"none": 0, "allreduce": 1, "reduce_scatter": 2}[mode]
+        if m == 2 and tiles < self.world:
+            raise ValueError("reduce-scatter needs at least one tile per rank")
+        part_off = h.alloc(2 * tiles * self.PART)
+        cnt_off = h.alloc(4 * tiles)
+        ready_off = h.alloc(4 * self.world)
+        ctrl_off = h.alloc(8)
+        ag = ag_off is not None
+        C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
+        part_stride, xs = tiles * self.PART, list(x_shape)
+        wire = self._wire(tiles) if m else 0
+        self.ops.append({"kind": kind, "x": tuple(x_shape), "w": tuple(w_shape), "stride": stride, "mode": mode,
+                         "ag": ag, "tiles": tiles, "nvls": nvls})
 
-        def op(a, wgt):
-            comm.tp_conv(kind, x_off, None if ag else a, wgt, out_off, ws_off, ws_stride, flags_off, tiles, list(a_shape),
-                         n_out, R, pad, reduce, bcast, ag)
+        def op(a, wgt, addend=None, stats=None):
+            y = C.tp_conv(kind, None if ag else a, ag_off or 0, wgt, xs, stride, pad, addend, stats, ptrs, mc,
+                          part_off, part_stride, cnt_off, ready_off, ctrl_off, rank, m, nvls, ag)
             self.bytes_moved += wire
-            return out
-        op.out = out
+            return y
+        op.tiles, op.mode = tiles, mode
         return op
 
-    def allreduce_conv(self, kind, a_shape, n_out, R=3, pad=1, algo="auto"):
-        """algo 'oneshot': every rank pushes its partial tile to all peers and reduces locally (one NVLink
-        hop, latency-optimal for ResNet-sized tiles); 'owner': push-to-owner reduce + broadcast (2 hops,
-        (W-1)/W of the traffic: bandwidth-optimal)."""
-        if algo == "auto":
-            # measured (profiles/tp_fused{2,8}_r1.json): one hop wins while the (W-1)x fp32 traffic stays small
-            n, _, h, w = a_shape
-            tiles = self.tiles_for(n, h, w, n_out) or 0
-            algo = "oneshot" if (self.world <= 2 or tiles * (self.world - 1) <= 64) else "owner"
-        return self._make(kind, tuple(a_shape), n_out, R, pad, 2 if algo == "oneshot" else 1, True, False)
+    def allreduce_conv(self, kind, x_shape, w_shape, stride=1, pad=1):
+        return self.conv(kind, x_shape, w_shape, stride, pad, "allreduce")
 
-    def reduce_scatter_conv(self, kind, a_shape, n_out, R=3, pad=1):
-        return self._make(kind, tuple(a_shape), n_out, R, pad, 1, False, False)
+    def reduce_scatter_conv(self, kind, x_shape, w_shape, stride=1, pad=1):
+        """Tile t of the output is reduced and kept by rank ``t % world`` only (the other ranks' output rows of
+        that tile are left untouched)."""
+        return self.conv(kind, x_shape, w_shape, stride, pad, "reduce_scatter")
 
     def ag_buffer(self, shard_shape):
         """A peer-readable activation shard [n_local, C, H, W] (channels_last) in the symmetric heap."""
         n, c, h, w = shard_shape
-        off = self.alloc(n * c * h * w * 2)
-        return off, self.comm.heap_tensor(off, [n, c, h, w], [h * w * c, 1, w * c, c], "bf16")
+        off = self.heap.alloc(n * c * h * w * 2)
+        return off, self.heap.tensor(off, [n, c, h, w], [h * w * c, 1, w * c, c], "bf16")
 
-    def ag_conv(self, x_off, full_shape, n_out, R=3, pad=1):
+    def ag_conv(self, x_off, full_shape, w_shape, pad=1):
         """conv(all_gather(x shards over the image axis), w_local): the gather is done by the kernel's TMA."""
-        return self._make(0, tuple(full_shape), n_out, R, pad, 0, False, True, x_off=x_off)
+        return self.conv(0, full_shape, w_shape, 1, pad, "none", ag_off=x_off)
+
+    def head(self, n, c, k_local):
+        """Tensor-parallel classifier head for batches of ``n`` samples (see ``tp_head_kernel``)."""
+        h = self.heap
+        K = k_local * self.world
+        logits_off = h.alloc(2 * n * K * 4)
+        dfeat_off = h.alloc(2 * n * c * 4)
+        cnt_off = h.alloc(2 * n * 4)
+        ctrl_off = h.alloc(8)
+        C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
+        wire = (self.world - 1) * n * (k_local * 4) + n * c * 4 * (1 if nvls else self.world - 1)
+        self.ops.append({"kind": "head", "n": n, "c": c, "k_local": k_local, "nvls": nvls})
+
+        def op(feat, wl, bl, labels, loss_scale, n_valid, dw, db, accumulate, need_dfeat, zeroed2):
+            out = C.tp_head(feat, wl, bl, labels, float(loss_scale), int(n_valid), dw, db, bool(accumulate),
+                            bool(need_dfeat), zeroed2, ptrs, mc, logits_off, dfeat_off, cnt_off, ctrl_off, rank, nvls)
+            self.bytes_moved += wire
+            return out
+        return op
+
+    def allreduce_bf16(self, t: torch.Tensor) -> torch.Tensor:
+        n = t.numel()
+        op = self._ar_ops.get(n)
+        if op is None:
+            h = self.heap
+            blocks = max(1, min(32, n * 2 // 16384))
+            buf_off = h.alloc(2 * n * 2)
+            cnt_off = h.alloc(4 * blocks)
+            ctrl_off = h.alloc(8)
+            C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
+            self.ops.append({"kind": "allreduce_bf16", "numel": n, "nvls": nvls})
+
+            def op(x):
+                return C.tp_allreduce_bf16(x, ptrs, mc, buf_off, cnt_off, ctrl_off, rank, nvls, blocks)
+            self._ar_ops[n] = op
+        self.bytes_moved += n * 2 * (1 if self.nvls else self.world - 1)
+        return op(t)
+
+    def describe(self) -> dict:
+        d = self.heap.describe()
+        d["ops"] = len(self.ops)
+        d["fused_convs"] = sum(1 for o in self.ops if o["kind"] in (0, 1))
+        return d
 
 
 def padded_classes(num_classes: int, ws: int) -> int:
@@ -233,6 +272,34 @@ class _TPHeadLoss(torch.autograd.Function):
         return (dfeat if ctx.has else None), None, None, None, None, None, None
 
 
+class _TPHeadLossFused(torch.autograd.Function):
+    """The same head as ONE sm_100a kernel (+ the local dW/db kernel): avg-pool, this rank's logit columns, the
+    logits all-gather by peer stores, softmax-CE + accuracy, and dX = Σ_r dY_r·W_r by a peer pull-reduce — no
+    ``dist.all_gather`` / ``dist.all_reduce`` (reference: tensor_parallel_train.py:39-64,203-204)."""
+
+    @staticmethod
+    def forward(ctx, feat, w_local, b_local, labels, head_op, n_valid: int, loss_scale: float):
+        from ..ops import native_backend as nb
+        tw, accw = grad_target(w_local)
+        tb, accb = grad_target(b_local)
+        nb.LAUNCHES["tp_head"] += 2
+        loss, correct, dfeat, logits = head_op(feat, w_local.detach(), b_local.detach(), labels, loss_scale, n_valid,
+                                               tw, tb, accw, feat.requires_grad, nb.ARENA.take(1, 2, feat.device))
+        ctx.params = (w_local, b_local)
+        ctx.has = feat.requires_grad
+        ctx.save_for_backward(dfeat if ctx.has else torch.empty(0))
+        ctx.mark_non_differentiable(correct)
+        ctx.set_materialize_grads(False)
+        return loss, correct
+
+    @staticmethod
+    def backward(ctx, dloss, _dc):
+        for p in ctx.params:
+            grad_written(p)
+        (dfeat,) = ctx.saved_tensors
+        return (dfeat if ctx.has else None), None, None, None, None, None, None
+
+
 class TPBasicBlock(nn.Module):
     """BasicBlock with conv1 column-parallel and conv2 row-parallel (see module docstring)."""
 
@@ -258,36 +325,57 @@ class TPBasicBlock(nn.Module):
 
     def _fused_ops(self, x):
         """Fused GEMM+all-reduce kernels for this block at this batch size (built once, same order on
-        every rank), or (None, None) → separate conv + collective."""
+        every rank), or None → separate conv + stand-alone reduction kernel."""
         key = tuple(x.shape)
         if key not in self._fused:
             f = self.comm.fused
             fwd = dg = None
             if f is not None and x.is_cuda and x.dtype == torch.bfloat16 and ops.get_backend() == "native":
+                from ..ops import native_backend as nb
                 n, cin, h, w = x.shape
                 s1 = self.conv1.stride
                 ho, wo = (h + 2 - 3) // s1 + 1, (w + 2 - 3) // s1 + 1
                 cs, cout = self.conv1.cout, self.conv2.cout
-                if f.supported((n, cs, ho, wo), cout):
-                    fwd = f.allreduce_conv(0, (n, cs, ho, wo), cout)            # conv2 forward (row-parallel)
-                if s1 == 1 and f.supported((n, cs, ho, wo), cin):
-                    dg = f.allreduce_conv(1, (n, cs, ho, wo), cin)              # conv1 dgrad (column-parallel)
+                if f.supported(0, (n, cs, ho, wo), cout, 1):
+                    op2 = f.allreduce_conv(0, (n, cs, ho, wo), (cout, cs, 3, 3), 1, 1)   # conv2 forward (row-parallel)
+
+                    def fwd(a, wgt, want_stats, _op=op2, _cout=cout):
+                        st = None
+                        if want_stats:
+                            st = nb.ARENA.take(2, _cout, a.device)
+                            if st is None:
+                                st = torch.zeros(2, _cout, dtype=torch.float32, device=a.device)
+                        nb.LAUNCHES["tp_conv_allreduce"] += 1
+                        return _op(a, wgt, None, st), st
+                if f.supported(1, (n, cin, h, w), cs, s1):
+                    op1 = f.allreduce_conv(1, (n, cin, h, w), (cs, cin, 3, 3), s1, 1)    # conv1 dgrad (column-parallel)
+
+                    def dg(dy, wgt, addend, _op=op1):
+                        nb.LAUNCHES["tp_dgrad_allreduce"] += 1
+                        if addend is not None and not (addend.dtype == torch.bfloat16 and addend.is_contiguous(
+                                memory_format=torch.channels_last)):
+                            return _op(dy, wgt, None, None) + addend
+                        return _op(dy, wgt, addend, None)
             self._fused[key] = (fwd, dg)
         return self._fused[key]
 
     def forward(self, x):
         t = self.training
-        idt = x
+        # the block input feeds two branches: the first to run backward parks its gradient, conv1's fused
+        # dgrad+all-reduce kernel adds it in its epilogue (ops.GradLink, as in the dense BasicBlock)
+        link = ops.GradLink(2) if (t and torch.is_grad_enabled() and x.requires_grad) else None
+        idt, res_link = x, link
         if self.downsample is not None:
-            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t)
+            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t, in_link=link)
+            res_link = None
         c1, b1, c2, b2 = self.conv1, self.bn1, self.conv2, self.bn2
         fwd2, dg1 = self._fused_ops(x)
         y = ops.conv_bn_act(x, c1.weight, b1.weight, b1.bias, b1.running_mean, b1.running_var,
                             stride=c1.stride, pad=1, relu=True, training=t,
-                            post_dgrad=self.comm.all_reduce_sum, dgrad_fn=dg1)
+                            post_dgrad=self.comm.all_reduce_sum, dgrad_fn=dg1, in_link=link)
         return ops.conv_bn_act(y, c2.weight, b2.weight, b2.bias, b2.running_mean, b2.running_var,
                                stride=1, pad=1, relu=True, residual=idt, training=t,
-                               post_conv=self.comm.all_reduce_sum, conv_fn=fwd2)
+                               post_conv=self.comm.all_reduce_sum, conv_fn=fwd2, res_link=res_link)
 
 
 class TensorParallelResNet(nn.Module):
@@ -316,9 +404,28 @@ class TensorParallelResNet(nn.Module):
         self.fc_weight.tp_sharded = True
         self.fc_bias.tp_sharded = True
         dense.fc = nn.Identity()           # the dense classifier is replaced by the sharded one
+        self._heads = {}
+
+    def _head_op(self, f):
+        """The one-kernel head for this batch size (native backend on GPUs), else None → PyTorch ops + c10d."""
+        fz = self.comm.fused
+        if fz is None or not f.is_cuda or f.dtype != torch.bfloat16 or ops.get_backend() != "native":
+            return None
+        n, c = f.shape[0], f.shape[1]
+        kl = self.fc_weight.shape[0]
+        if n > 148 or c % 4 or kl > 16 or kl * self.comm.world > 64 or self.fc_weight.dtype != torch.float32:
+            return None
+        key = (n, c)
+        if key not in self._heads:
+            self._heads[key] = fz.head(n, c, kl)
+        return self._heads[key]
 
     def forward_loss(self, x, labels, loss_scale: float = 1.0):
         f = self.backbone.features(x)
+        op = self._head_op(f)
+        if op is not None:
+            return _TPHeadLossFused.apply(f, self.fc_weight, self.fc_bias, labels, op, self.num_classes,
+                                          float(loss_scale))
         return _TPHeadLoss.apply(f, self.fc_weight, self.fc_bias, labels, self.comm,
                                  self.num_classes, float(loss_scale))
 
@@ -370,7 +477,7 @@ class _RowLinearFn(torch.autograd.Function):
         if fused_op is not None:
             # ONE kernel: tcgen05 GEMM of the local shard + peer-memory all-reduce of the output tiles
             y = fused_op(x.view(x.shape[0], x.shape[1], 1, 1), w.view(w.shape[0], w.shape[1], 1, 1))
-            y = y.view(x.shape[0], -1).clone()
+            y = y.view(x.shape[0], -1)
         else:
             y = comm.all_reduce_sum((x.float() @ w.float().t()).contiguous()).to(x.dtype)
         if b is not None:
@@ -443,8 +550,9 @@ class RowParallelLinear(nn.Module):
         key = tuple(x.shape)
         if key not in self._fused:
             n, ks = x.shape
-            ok = f.supported((n, ks, 1, 1), self.weight.shape[0])
-            self._fused[key] = f.allreduce_conv(0, (n, ks, 1, 1), self.weight.shape[0], R=1, pad=0) if ok else None
+            nout = self.weight.shape[0]
+            ok = f.supported(0, (n, ks, 1, 1), nout, 1)
+            self._fused[key] = f.allreduce_conv(0, (n, ks, 1, 1), (nout, ks, 1, 1), 1, 0) if ok else None
         return self._fused[key]
 
     def forward(self, x_shard):

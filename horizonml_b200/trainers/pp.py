@@ -23,7 +23,7 @@ from ..metrics import EpochRecorder, write_summary
 from ..models.flat import FlatAdam, FlatParams
 from ..models.partition import boundary_shape, partition_blocks
 from ..models.resnet import resnet18
-from ..parallel.pp import GraphedMicroBatch, PipelineRunner
+from ..parallel.pp import GraphedMicroBatch, OverlappedPipelineRunner, P2PChannels, PipelineRunner
 from .common import (DeviceStats, FaultInjector, Heartbeat, Runtime, allreduce_max_scalar, gpu_mem_mb,
                      setup_runtime)
 
@@ -75,6 +75,16 @@ class PPEngine:
         self.use_graphs = cfg.cuda_graph and rt.device.type == "cuda" and rt.backend == "native"
         self.slots = None
         self.slot_sizes = None
+        # overlapped 1F1B (GPU + graphs): one NCCL communicator and one CUDA stream per neighbour and direction, so
+        # receives are posted ahead of the compute that needs them and sends fire from events (parallel/pp.py)
+        self.channels = None
+        self.overlapped = None
+        if self.use_graphs and S > 1 and rt.comm_backend == "nccl" and bool(getattr(cfg, "pp_overlap", True)):
+            if mesh is not None:
+                rows = [[mesh.rank_of(d, st, t) for st in range(mesh.pp)] for d in range(mesh.dp) for t in range(mesh.tp)]
+            else:
+                rows = [list(range(S))]
+            self.channels = P2PChannels(rt.rank, rows, rt.device)
         ops.enable_side_stream(rt.device.type == "cuda" and rt.backend == "native")
 
     def _fwd(self, x, i):
@@ -102,7 +112,9 @@ class PPEngine:
         S, s = self.S, self.s
         n = sizes[0]
         self._graph_frac = 1.0 / len(sizes)
-        nslots = max(1, min(S - s, len(sizes)))
+        # 1F1B keeps min(S - s, M) micro-batches in flight; one spare slot lets the next activation be received
+        # (straight into the slot's static input) while the in-flight ones are still being computed
+        nslots = max(1, min(S - s + (1 if self.channels is not None else 0), len(sizes)))
         nb.ARENA.active = False                      # captured micro-batches are replayed several times per step:
         for p in self.flat.params:                   # they must not share pre-zeroed scratch, and every gradient
             p._acc = True                            # write accumulates (the optimizer pass clears the buffer)
@@ -118,6 +130,12 @@ class PPEngine:
             slots.append(g)
         torch.cuda.synchronize()
         self.slots, self.slot_sizes = slots, list(sizes)
+        if self.channels is not None:
+            for g in slots:      # payloads travel as the dense NHWC storage of the static buffers: no staging copies
+                for t in ([] if self.is_first else [g.x, g.dx]) + ([] if self.is_last else [g.out, g.dy]):
+                    assert t is not None and t.permute(0, 2, 3, 1).is_contiguous(), "stage boundary tensor is not NHWC-dense"
+            self.overlapped = OverlappedPipelineRunner(s, S, slots, self.channels, self.rt.device,
+                                                       timing=bool(self.cfg.region_probe))
 
     def _fwd_graphed(self, x, i):
         slot = self.slots[i % len(self.slots)]
@@ -144,19 +162,23 @@ class PPEngine:
                     print(f"[pp] graph capture failed on stage {self.rt.rank}, staying eager: {e!r}", flush=True)
                     self.use_graphs, self.slots = False, None
                     torch.cuda.synchronize()
-        if self.slots is not None and uniform and self.slot_sizes == list(sizes):
+        graphed = self.slots is not None and uniform and self.slot_sizes == list(sizes)
+        if graphed:
             for p in self.flat.params:
                 p._acc = True
             self.runner.fwd_fn, self.runner.bwd_fn = self._fwd_graphed, self._bwd_graphed
         else:
             self.runner.fwd_fn, self.runner.bwd_fn = self._fwd, None
-        loss, correct = self.runner.run(sizes, imgs)
+        if graphed and self.overlapped is not None:
+            loss, correct = self.overlapped.run(M, imgs, self.labels_mb)
+        else:
+            loss, correct = self.runner.run(sizes, imgs)
         ops.join_side()
         if self.dp_ar is not None:                   # hybrid DP × PP: average this stage's gradients over its replicas
             for bk in self.flat.buckets:
                 self.dp_ar.allreduce_avg_(self.flat.grad[bk.start:bk.end], live=self.flat.bucket_live[bk.index])
         diff = self.opt.step(prev_grad=self.prev_grad)
-        sent = self.runner.p2p.end_step()
+        sent = self.runner.p2p.end_step() + (self.channels.end_step() if self.channels is not None else 0)
         ops.step_end()
         if self.is_last:
             self.stats.add_step(loss, correct, B, diff)
@@ -256,7 +278,8 @@ def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         if cfg.region_probe:
             # time per step this stage's compute stream is blocked behind activation / gradient exchanges (includes
             # the pipeline bubble, like the reference's blocking send/recv "comm_time", layer_…:188-195,209)
-            ext["p2p_ms"] = eng.runner.p2p.take_time_ms() / steps
+            p2p_total = eng.runner.p2p.take_time_ms() + (eng.overlapped.stall_ms() if eng.overlapped is not None else 0.0)
+            ext["p2p_ms"] = p2p_total / steps
             ext["exposed_comm_ms"] = ext["p2p_ms"]
         rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times,
                       avg_bandwidth=sent_total / steps, ext=ext)

@@ -36,11 +36,15 @@ class TPEngine:
     def __init__(self, cfg: TrainConfig, rt: Runtime, mesh=None):
         self.cfg, self.rt, self.mesh = cfg, rt, mesh
         fused = None
-        if (mesh is None and rt.device.type == "cuda" and rt.backend == "native" and rt.world > 1
-                and cfg.tp_conv_split):
+        tp_group = mesh.tp_group if mesh is not None else None
+        tp_world = mesh.tp if mesh is not None else rt.world
+        if rt.device.type == "cuda" and rt.backend == "native" and tp_world > 1:
             from ..parallel.tp import FusedTP
-            fused = FusedTP(rt.device)        # symmetric heap spans the WORLD group: single-row meshes only
-        self.comm = TPComm(group=mesh.tp_group if mesh is not None else None, fused=fused)
+            # one symmetric heap (+ NVSwitch multicast mapping when available) per tensor-parallel group: under a
+            # DP × TP mesh every row gets its own
+            fused = FusedTP(rt.device, group=tp_group)
+        self.fused = fused
+        self.comm = TPComm(group=tp_group, fused=fused)
         dense = resnet18(cfg.num_classes, seed=cfg.seed)
         self.model = TensorParallelResNet(dense, self.comm, cfg.tp_conv_split).to(rt.device)
         self.model.train()

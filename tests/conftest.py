@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# Virtual-rank tests run several ranks' kernels of ONE process concurrently, the early ones spinning until the late ones
+# arrive.  With CUDA's default lazy module loading the first launch of a not-yet-loaded kernel has to wait for running
+# kernels — the spinning rank — and the late rank is never launched (deadlock, then the kernels' bounded spins trap).
+# Eager loading (set before the CUDA context exists) removes the hazard; one rank per process is never affected.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -1,0 +1,241 @@
+"""Tensor-parallel ResNet-18 training step over W *virtual ranks* on ONE GPU (native kernels only) vs the dense model:
+loss and per-parameter gradients after reassembling the shards.  Each virtual rank is a host thread with its own CUDA
+stream; the ranks' fused GEMM+all-reduce / head kernels rendezvous on the device exactly as W processes would
+(parallel/symm.py ``SymmHeap.virtual``).  Usage: HZ_PDL=0 python tools/tp_virtual_step.py WORLD out.json"""
+import json
+import os
+import sys
+import threading
+
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")   # virtual ranks of one process wait for each other on the device:
+                                                        # no lazy kernel load may block behind a spinning kernel
+import torch  # noqa: E402
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+DEV = "cuda:0"
+
+
+def _run_threads(fns):
+    errors = []
+
+    def wrap(fn):
+        def run():
+            try:
+                torch.cuda.set_device(0)
+                fn()
+            except Exception:  # noqa: BLE001
+                import traceback
+                errors.append(traceback.format_exc())
+        return run
+    threads = [threading.Thread(target=wrap(fn)) for fn in fns]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    torch.cuda.synchronize()
+    if errors:
+        print("\n".join(errors))
+        sys.exit(1)
+
+
+def block_check(world: int, out_path: str):
+    """ONE tensor-parallel BasicBlock (conv1 column-, conv2 row-parallel, fused reductions) vs the dense block on the
+    same input and upstream gradient: output, input gradient and every parameter gradient, tight tolerances (a single
+    block does not amplify rounding the way the whole network does)."""
+    from horizonml_b200 import ops
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.resnet import BasicBlock
+    from horizonml_b200.ops import native_backend as nb
+    from horizonml_b200.parallel.symm import SymmHeap
+    from horizonml_b200.parallel.tp import FusedTP, TPBasicBlock, TPComm
+    ops.set_backend("native")
+    ops.enable_side_stream(False)
+    res = {"world": world, "blocks": []}
+    fz = [FusedTP(DEV, heap=h) for h in SymmHeap.virtual(world, DEV, 64 << 20)]
+    for (cin, cout, stride, hw) in [(128, 256, 2, 4), (256, 256, 1, 2), (256, 512, 2, 2), (512, 512, 1, 1)]:
+        g = torch.Generator().manual_seed(cin + stride)
+        torch.manual_seed(cin * 7 + stride)
+        dense = BasicBlock(cin, cout, stride).to(DEV).train()
+        with torch.no_grad():
+            for m in (dense.bn1, dense.bn2):
+                m.weight.copy_(torch.rand(cout, generator=g) + 0.5); m.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+        x0 = (torch.randn(64, cin, hw, hw, generator=g) * 0.7).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+        ho = hw // stride
+        dout = (torch.randn(64, cout, ho, ho, generator=g) * 0.5).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+        comms, blocks, flats, xs, outs = [], [], [], [], [None] * world
+        for r in range(world):
+            comm = TPComm.__new__(TPComm)
+            comm.group, comm.world, comm.rank, comm.bytes, comm.fused, comm.library_collectives = None, world, r, 0, fz[r], 0
+            blk = TPBasicBlock(dense, comm).to(DEV).train()
+            # the replicated parameters (bn2, downsample) are shared module objects of `dense`: give every rank its own copy
+            import copy
+            blk.downsample = copy.deepcopy(dense.downsample)
+            blocks.append(blk); comms.append(comm)
+        dflat = FlatParams(list(dense.named_parameters()), DEV, torch.bfloat16)
+        for r in range(world):
+            flats.append(FlatParams(list(blocks[r].named_parameters()), DEV, torch.bfloat16))
+        xd = x0.clone().requires_grad_(True)
+        dflat.begin_step()
+        yd = dense(xd)
+        yd.backward(dout)
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream() for _ in range(world)]
+
+        def make(r):
+            def fn():
+                with torch.cuda.stream(streams[r]):
+                    flats[r].begin_step()
+                    xr = x0.clone().requires_grad_(True)
+                    xs.append((r, xr))
+                    y = blocks[r](xr)
+                    y.backward(dout)
+                    outs[r] = y
+                    streams[r].synchronize()
+            return fn
+        _run_threads([make(r) for r in range(world)])
+
+        def rel(a, b):
+            return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-6)).item()
+        xg = dict(xs)
+        row = {"block": [cin, cout, stride, hw], "out": max(rel(outs[r], yd) for r in range(world)),
+               "dx": max(rel(xg[r].grad, xd.grad) for r in range(world)), "params": {}}
+        dpar = dict(dense.named_parameters())
+        for name, pd in dpar.items():
+            parts = [dict(blocks[r].named_parameters())[name].main_grad for r in range(world)]
+            gd = pd.main_grad
+            if parts[0].shape == gd.shape:
+                got = parts[0]
+            elif parts[0].dim() == 4 and parts[0].shape[0] != gd.shape[0]:
+                got = torch.cat(parts, dim=0)
+            elif parts[0].dim() == 4:
+                got = torch.cat(parts, dim=1)
+            else:
+                got = torch.cat(parts, dim=0)
+            row["params"][name] = rel(got, gd)
+        row["worst"] = max([row["out"], row["dx"]] + list(row["params"].values()))
+        res["blocks"].append(row)
+    res["worst"] = max(b["worst"] for b in res["blocks"])
+    res["library_collectives"] = sum(c.library_collectives for c in comms)
+    res["native_fallbacks"] = dict(nb.FALLBACKS)
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    json.dump(res, open(out_path, "w"), indent=1)
+    print(json.dumps(res))
+
+
+def main():
+    if len(sys.argv) > 3 and sys.argv[3] == "block":
+        return block_check(int(sys.argv[1]), sys.argv[2])
+    world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    out_path = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/tp_virtual_step.json"
+    from horizonml_b200 import ops
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.resnet import resnet18
+    from horizonml_b200.ops import native_backend as nb
+    from horizonml_b200.parallel.symm import SymmHeap
+    from horizonml_b200.parallel.tp import FusedTP, TensorParallelResNet, TPComm
+    ops.set_backend("native")
+    ops.enable_side_stream(False)
+    g = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (64, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+    labels = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    x = ops.stem_prepare(images.permute(0, 3, 1, 2), dtype=torch.bfloat16)
+
+    dense = resnet18(10, seed=0).to(DEV).train()
+    dflat = FlatParams(list(dense.named_parameters()), DEV, torch.bfloat16)
+    dflat.begin_step()
+    dloss, _ = dense.forward_loss(x, labels)
+    ops.backward(dloss)
+    ops.join_side()
+    torch.cuda.synchronize()
+    dgrads = {n: p.main_grad.clone() for n, p in dense.named_parameters()}
+    # noise floor: the same dense step on the PyTorch-op (cuDNN, bf16) backend — an independent bf16 implementation
+    # of the same maths.  ResNet-18 at random init with batch statistics over 1x1 maps amplifies rounding
+    # differences, so "equal" can only mean "no further from the dense native gradients than the oracle is".
+    ops.set_backend("torch")
+    oracle = resnet18(10, seed=0).to(DEV).train()
+    oflat = FlatParams(list(oracle.named_parameters()), DEV, torch.bfloat16)
+    oflat.begin_step()
+    oloss, _ = oracle.forward_loss(x, labels)
+    ops.backward(oloss)
+    torch.cuda.synchronize()
+    ograds = {n: p.main_grad.clone() for n, p in oracle.named_parameters()}
+    ops.set_backend("native")
+    noise = {n: torch.nn.functional.cosine_similarity(ograds[n].float().flatten(), dgrads[n].float().flatten(), dim=0).item()
+             for n in dgrads}
+
+    fz = [FusedTP(DEV, heap=h) for h in SymmHeap.virtual(world, DEV, 64 << 20)]
+    models, flats = [], []
+    for r in range(world):
+        comm = TPComm.__new__(TPComm)
+        comm.group, comm.world, comm.rank, comm.bytes, comm.fused, comm.library_collectives = None, world, r, 0, fz[r], 0
+        m = TensorParallelResNet(resnet18(10, seed=0), comm, True).to(DEV).train()
+        rep, shd = m.split_params()
+        flats.append((FlatParams(rep, DEV, torch.bfloat16), FlatParams(shd, DEV, torch.bfloat16)))
+        models.append(m)
+    losses, errors = [None] * world, []
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    torch.cuda.synchronize()
+
+    def run(r):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(streams[r]):
+                for fl in flats[r]:
+                    fl.begin_step()
+                loss, _ = models[r].forward_loss(x, labels)
+                ops.backward(loss)
+                losses[r] = loss
+                streams[r].synchronize()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            errors.append(traceback.format_exc())
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    torch.cuda.synchronize()
+    if errors:
+        print("\n".join(errors))
+        sys.exit(1)
+    worst, cos = {}, {}
+    for name, gd in dgrads.items():
+        parts = []
+        for r in range(world):
+            pr = dict(models[r].named_parameters())
+            key = "backbone." + name
+            if name.startswith("fc."):
+                key = "fc_weight" if name == "fc.weight" else "fc_bias"
+            parts.append(pr[key].main_grad)
+        p0 = parts[0]
+        if p0.shape == gd.shape:
+            got = p0
+        elif name.startswith("fc."):
+            got = torch.cat(parts, dim=0)[: gd.shape[0]]
+        elif p0.dim() == 4 and p0.shape[0] != gd.shape[0]:
+            got = torch.cat(parts, dim=0)
+        elif p0.dim() == 4:
+            got = torch.cat(parts, dim=1)
+        else:
+            got = torch.cat(parts, dim=0)
+        scale = gd.abs().max().item() + 1e-6
+        worst[name] = (got.float() - gd.float()).abs().max().item() / scale
+        cos[name] = torch.nn.functional.cosine_similarity(got.float().flatten(), gd.float().flatten(), dim=0).item()
+    res = {"world": world, "loss_dense": dloss.item(), "loss_tp": [l.item() for l in losses],
+           "loss_rel_err": max(abs(l.item() - dloss.item()) for l in losses) / abs(dloss.item()),
+           "library_collectives": sum(m.comm.library_collectives for m in models),
+           "native_fallbacks": dict(nb.FALLBACKS), "launches": dict(nb.LAUNCHES),
+           "worst_param_rel_err": max(worst.values()), "worst_param": max(worst, key=worst.get),
+           "bad": {k: [round(cos[k], 4), round(noise[k], 4)] for k in cos
+                   if cos[k] < min(noise[k], 0.999) - 0.03 or (k.startswith("fc.") and worst[k] > 5e-2)},
+           "min_cos_tp_vs_dense": min(cos.values()), "min_cos_oracle_vs_dense": min(noise.values()),
+           "fused_ops": fz[0].describe(),
+           "per_param": {k: [round(worst[k], 4), round(cos[k], 5), round(noise[k], 5)] for k in worst}}
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    json.dump(res, open(out_path, "w"), indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k not in ("launches", "per_param")}))
+
+
+if __name__ == "__main__":
+    main()
