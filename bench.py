@@ -41,6 +41,8 @@ def parse():
     p.add_argument("--no_grad_divergence", action="store_true")
     p.add_argument("--bucket_mb", type=float, default=25.0)
     p.add_argument("--live_bucket_mb", type=float, default=2.0)
+    p.add_argument("--no_fused_adam", action="store_true")
+    p.add_argument("--bucket_layout", default="auto", choices=["auto", "layers", "size"])
     return p.parse_args()
 
 
@@ -67,7 +69,8 @@ def run_ours(args):
     cfg = TrainConfig(strategy="data", world_size=world, batch_size=args.batch, device="cuda", dtype="bf16",
                       backend=backend, allreduce=args.allreduce, cuda_graph=not args.no_graph,
                       grad_divergence=not args.no_grad_divergence, quiet=True, bucket_mb=args.bucket_mb,
-                      live_bucket_mb=args.live_bucket_mb)
+                      live_bucket_mb=args.live_bucket_mb, fused_adam=not args.no_fused_adam,
+                      bucket_layout=args.bucket_layout)
     rt = setup_runtime(rank, world, cfg, "cuda")
     dev = rt.device
     eng = DPEngine(cfg, rt)
@@ -181,6 +184,9 @@ def run_ours(args):
                    "backend": rt.backend, "allreduce": getattr(eng.ar, "name", None) if eng.ar else None,
                    "cuda_graph": graphed, "grad_divergence_metric": cfg.grad_divergence,
                    "bucket_mb": cfg.bucket_mb, "live_bucket_mb": cfg.live_bucket_mb, "buckets": len(eng.flat.buckets), "bucketwise_adam": eng.bucket_adam,
+                   "fused_allreduce_adam": eng.fused_adam,
+                   "bucket_allreduce_algos": eng.reducer.algos if (eng.reducer is not None and eng.fused_adam) else None,
+                   "allreduce_detail": eng.ar.describe() if (eng.ar is not None and hasattr(eng.ar, "describe")) else None,
                    "l2": "256 MiB flush-write between timed steps (untimed); per-step working set "
                          "(fp32 master+m+v+grad, bf16 shadow ~ 200 MB) also exceeds the 126 MB L2",
                    "baseline_ref": "BASELINE.md: reference DP ~51 img/s (5 CPU procs, gloo, N=1000)"},

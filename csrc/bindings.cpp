@@ -371,6 +371,28 @@ class PeerComm {
                                has_live ? live_blocks->data_ptr<int>() : nullptr, cur_stream());
     TORCH_CHECK(rc == 0, "hz_comm_allreduce failed rc=", rc);
   }
+  // all-reduce (average) + Adam on the bucket in one kernel; every tensor is the bucket's slice of its flat buffer
+  void allreduce_adam(Tensor grad, const std::string& algo, bool wire_bf16, double scale,
+                      c10::optional<Tensor> live_blocks, Tensor master, Tensor m, Tensor v, c10::optional<Tensor> shadow,
+                      c10::optional<Tensor> prev, c10::optional<Tensor> diff_out, Tensor step, double lr, double b1,
+                      double b2, double eps, bool bump) {
+    TORCH_CHECK(grad.is_cuda() && grad.scalar_type() == at::kFloat && grad.is_contiguous());
+    TORCH_CHECK(master.numel() == grad.numel() && m.numel() == grad.numel() && v.numel() == grad.numel());
+    const bool has_live = live_blocks.has_value() && live_blocks->defined();
+    if (has_live) TORCH_CHECK(live_blocks->scalar_type() == at::kInt && live_blocks->is_cuda());
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : -1;
+    TORCH_CHECK(a >= 0, "unknown all-reduce algorithm ", algo);
+    c10::cuda::CUDAGuard g(grad.device());
+    const size_t n = has_live ? (size_t)live_blocks->numel() * 64 : (size_t)grad.numel();
+    void* sh = nullptr;
+    if (shadow.has_value() && shadow->defined()) { TORCH_CHECK(shadow->scalar_type() == at::kBFloat16); sh = shadow->data_ptr(); }
+    int rc = hz_comm_allreduce_adam(c_, grad.data_ptr<float>(), n, a, wire_bf16 ? 1 : 0, (float)scale,
+                                    has_live ? live_blocks->data_ptr<int>() : nullptr, master.data_ptr<float>(),
+                                    m.data_ptr<float>(), v.data_ptr<float>(), sh, fptr(prev), fptr(diff_out),
+                                    step.data_ptr<float>(), (float)lr, (float)b1, (float)b2, (float)eps, bump ? 1 : 0,
+                                    cur_stream());
+    TORCH_CHECK(rc == 0, "hz_comm_allreduce_adam failed rc=", rc);
+  }
   int64_t blocks_for(int64_t n, const std::string& algo, bool wire_bf16) {
     int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : 2;
     return hz_comm_blocks_for(c_, (size_t)n, a, wire_bf16 ? 1 : 0);
@@ -409,7 +431,7 @@ int64_t tp_tiles(int64_t kind, std::vector<int64_t> x_shape, int64_t Cout, int64
 Tensor tp_conv(int64_t kind, c10::optional<Tensor> a, int64_t a_off, const Tensor& w, std::vector<int64_t> x_shape,
                int64_t stride, int64_t pad, c10::optional<Tensor> addend, c10::optional<Tensor> stats,
                std::vector<int64_t> heaps, int64_t mc, int64_t part_off, int64_t part_stride, int64_t cnt_off,
-               int64_t ready_off, int64_t ctrl_off, int64_t rank, int64_t mode, bool nvls, bool ag) {
+               int64_t ready_off, int64_t ctrl_off, int64_t rank, int64_t mode, bool nvls, bool ag, bool ll) {
   check_cl(w, "w");
   c10::cuda::CUDAGuard g(w.device());
   const int world = (int)heaps.size();
@@ -442,7 +464,7 @@ Tensor tp_conv(int64_t kind, c10::optional<Tensor> a, int64_t a_off, const Tenso
   unsigned* ctrl = reinterpret_cast<unsigned*>(hp.h[rank] + ctrl_off);
   int rc = hz_tp_conv((int)kind, xp, w.data_ptr(), out.data_ptr(), add, st, hp.h, (char*)(uintptr_t)mc, part_off,
                       part_stride, cnt_off, ready_off, ctrl, ctrl + 1, world, (int)rank, (int)mode, nvls ? 1 : 0,
-                      ag ? 1 : 0, N, H, Wd, Cin, Cout, R, (int)stride, (int)pad, cur_stream());
+                      ll ? 1 : 0, ag ? 1 : 0, N, H, Wd, Cin, Cout, R, (int)stride, (int)pad, cur_stream());
   TORCH_CHECK(rc == 0, "hz_tp_conv failed rc=", rc);
   return out;
 }
@@ -451,8 +473,7 @@ Tensor tp_conv(int64_t kind, c10::optional<Tensor> a, int64_t a_off, const Tenso
 std::vector<Tensor> tp_head(const Tensor& feat, const Tensor& Wl, const c10::optional<Tensor>& bl, const Tensor& labels,
                             double loss_scale, int64_t n_valid, Tensor dW, c10::optional<Tensor> db, bool accumulate,
                             bool need_dfeat, c10::optional<Tensor> zeroed2, std::vector<int64_t> heaps, int64_t mc,
-                            int64_t logits_off, int64_t dfeat_off, int64_t cnt_off, int64_t ctrl_off, int64_t rank,
-                            bool nvls) {
+                            int64_t logits_off, int64_t dfeat_off, int64_t ctrl_off, int64_t rank, bool nvls) {
   check_cl(feat, "feat");
   TORCH_CHECK(Wl.scalar_type() == at::kFloat && Wl.is_contiguous() && labels.scalar_type() == at::kLong);
   c10::cuda::CUDAGuard g(feat.device());
@@ -472,7 +493,7 @@ std::vector<Tensor> tp_head(const Tensor& feat, const Tensor& Wl, const c10::opt
   int rc = hz_tp_head(cptr(feat), Wl.data_ptr<float>(), fptr(bl), labels.data_ptr<int64_t>(), pooled.data_ptr<float>(),
                       dl.data_ptr<float>(), logits.data_ptr<float>(), need_dfeat ? dfeat.data_ptr() : nullptr,
                       loss.data_ptr<float>(), correct.data_ptr<float>(), hp.h, (char*)(uintptr_t)mc, logits_off, dfeat_off,
-                      cnt_off, ctrl, ctrl + 1, world, (int)rank, nvls ? 1 : 0, d.N, d.C, d.H * d.W, kl, (int)n_valid,
+                      ctrl, ctrl + 1, world, (int)rank, nvls ? 1 : 0, d.N, d.C, d.H * d.W, kl, (int)n_valid,
                       (float)loss_scale, cur_stream());
   TORCH_CHECK(rc == 0, "hz_tp_head failed rc=", rc);
   hz_head_wgrad(pooled.data_ptr<float>(), dl.data_ptr<float>(), dW.data_ptr<float>(), fptr(db), d.N, d.C, kl,
@@ -480,19 +501,21 @@ std::vector<Tensor> tp_head(const Tensor& feat, const Tensor& Wl, const c10::opt
   return {loss, correct, dfeat, logits};
 }
 
-int64_t tp_head_bytes(int64_t N, int64_t C, int64_t K) { return (int64_t)hz_tp_head_bytes((int)N, (int)C, (int)K); }
+int64_t tp_head_bytes(int64_t N, int64_t C, int64_t K, int64_t world) {
+  return (int64_t)hz_tp_head_bytes((int)N, (int)C, (int)K, (int)world);
+}
 
 // sum over the tensor-parallel ranks of a small bf16 tensor (dense layout preserved)
 Tensor tp_allreduce_bf16(const Tensor& in, std::vector<int64_t> heaps, int64_t mc, int64_t buf_off, int64_t cnt_off,
-                         int64_t ctrl_off, int64_t rank, bool nvls, int64_t blocks) {
+                         int64_t ctrl_off, int64_t rank, bool nvls, int64_t blocks, bool ll) {
   TORCH_CHECK(in.is_cuda() && in.scalar_type() == at::kBFloat16 && in.is_non_overlapping_and_dense() && in.numel() % 8 == 0);
   c10::cuda::CUDAGuard g(in.device());
   HeapPtrs hp = heap_ptrs(heaps);
   Tensor out = at::empty_like(in);
   unsigned* ctrl = reinterpret_cast<unsigned*>(hp.h[rank] + ctrl_off);
   int rc = hz_tp_allreduce_bf16(in.data_ptr(), out.data_ptr(), (size_t)in.numel(), hp.h, (char*)(uintptr_t)mc, buf_off,
-                                cnt_off, ctrl, ctrl + 1, (int)heaps.size(), (int)rank, nvls ? 1 : 0, (int)blocks,
-                                cur_stream());
+                                cnt_off, ctrl, ctrl + 1, (int)heaps.size(), (int)rank, nvls ? 1 : 0, ll ? 1 : 0,
+                                (int)blocks, cur_stream());
   TORCH_CHECK(rc == 0, "hz_tp_allreduce_bf16 failed rc=", rc);
   return out;
 }
@@ -542,6 +565,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_fwd", &conv_fwd);
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_wgrad", &conv_wgrad);
+  m.def("tp_set_debug", [](c10::optional<Tensor> buf) {
+    if (buf.has_value() && buf->defined()) {
+      TORCH_CHECK(buf->is_cuda() && buf->scalar_type() == at::kLong && buf->is_contiguous());
+      hz_tp_set_debug(reinterpret_cast<long long*>(buf->data_ptr<int64_t>()));
+    } else {
+      hz_tp_set_debug(nullptr);
+    }
+  });
   m.def("tp_tiles", &tp_tiles);
   m.def("tp_conv", &tp_conv);
   m.def("tp_head", &tp_head);
@@ -559,6 +590,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_multicast", &PeerComm::set_multicast)
       .def("allreduce", &PeerComm::allreduce, py::arg("grad"), py::arg("algo"), py::arg("wire_bf16"),
            py::arg("scale"), py::arg("live_blocks") = py::none())
+      .def("allreduce_adam", &PeerComm::allreduce_adam)
       .def("blocks_for", &PeerComm::blocks_for)
       .def("barrier", &PeerComm::barrier)
       .def("error", &PeerComm::error);

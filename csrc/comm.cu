@@ -16,7 +16,9 @@
 // Summation order is rank 0..W-1 on every rank, so replicas stay bit-identical.
 // Staging/out buffers alternate between calls (parity), which together with the in-call barrier makes
 // back-to-back calls race-free without a trailing barrier.  All counters live in device memory so the
-// kernels are CUDA-graph replayable.  Spins are bounded (error flag instead of a hang).
+// kernels are CUDA-graph replayable.  Spins are bounded (error flag + trap instead of a hang or silent garbage).
+// With the optimizer epilogue (AdamFuse) the reduced values go straight into the Adam update of the bucket's
+// parameters: no gradient round trip through HBM, no separate optimizer kernel waiting for "all buckets".
 #include "common.cuh"
 #include "launchers.h"
 
@@ -232,10 +234,91 @@ HZ_DEVINL void unpack_range(float* __restrict__ grad, const uint4* __restrict__ 
   }
 }
 
-template <bool kBf16, int kAlgo>
+// Optimizer epilogue of the all-reduce (kAdam): the reduced gradient never goes back to HBM as a gradient — the
+// thread that holds it applies torch.optim.Adam to the parameter slice of the bucket right away (fp32 master +
+// moments, bf16 shadow refresh, the reference's gradient-divergence term sum (g - g_prev)^2 with g_prev <- g, and the
+// gradient clear the producers rely on).  All pointers address the bucket's slice (same element offsets as `grad`).
+struct AdamFuse {
+  float* p; float* m; float* v;
+  __nv_bfloat16* shadow;         // may be null (fp32 compute)
+  float* prev; float* diff_out;  // may be null (metric off)
+  float* step;                   // [1] optimizer step counter: this call uses step+1; `bump` makes the call's last
+  float lr, b1, b2, eps;         //     block store step+1 (the final bucket of the optimizer step)
+  int bump;
+};
+
+struct AdamCoef { float step_size, inv_sqrt_bc2, b1, b2, eps; };
+
+template <int V>
+HZ_DEVINL void adam_apply(const AdamFuse& a, const AdamCoef& k, float* __restrict__ grad, size_t off, const float* g,
+                          float& dacc) {
+#pragma unroll
+  for (int q = 0; q < V / 4; ++q) {
+    const size_t o = off + 4 * q;
+    float4 pp = *reinterpret_cast<float4*>(a.p + o);
+    float4 mm = *reinterpret_cast<float4*>(a.m + o);
+    float4 vv = *reinterpret_cast<float4*>(a.v + o);
+    float* P = &pp.x; float* Mo = &mm.x; float* Vv = &vv.x;
+    const float* G = g + 4 * q;
+    if (a.prev != nullptr) {
+      const float4 pr = *reinterpret_cast<const float4*>(a.prev + o);
+      const float dx = G[0] - pr.x, dy = G[1] - pr.y, dz = G[2] - pr.z, dw = G[3] - pr.w;
+      dacc += dx * dx + dy * dy + dz * dz + dw * dw;
+      *reinterpret_cast<float4*>(a.prev + o) = make_float4(G[0], G[1], G[2], G[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gr = G[j];
+      Mo[j] = k.b1 * Mo[j] + (1.f - k.b1) * gr;
+      Vv[j] = k.b2 * Vv[j] + (1.f - k.b2) * gr * gr;
+      const float denom = sqrtf(Vv[j]) * k.inv_sqrt_bc2 + k.eps;
+      P[j] -= k.step_size * Mo[j] / denom;
+    }
+    *reinterpret_cast<float4*>(a.p + o) = pp;
+    *reinterpret_cast<float4*>(a.m + o) = mm;
+    *reinterpret_cast<float4*>(a.v + o) = vv;
+    *reinterpret_cast<float4*>(grad + o) = make_float4(0.f, 0.f, 0.f, 0.f);     // producers only ever accumulate
+    if (a.shadow != nullptr) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(a.shadow + o) = pk;
+    }
+  }
+}
+
+// [lo,hi) of the wire buffer `src` -> Adam on the bucket (two-shot / NVLS final phase with kAdam)
+template <bool kBf16>
+HZ_DEVINL void unpack_adam_range(float* __restrict__ grad, const uint4* __restrict__ src, size_t lo, size_t hi,
+                                 const int* __restrict__ live, const AdamFuse& ad, const AdamCoef& k, float& dacc) {
+  using Wt = Wire<kBf16>;
+  constexpr int V = Wt::kVec;
+  for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * 2) {
+    uint4 w[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t v = v0 + (size_t)u * blockDim.x;
+      if (v < hi) w[u] = src[v];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const size_t v = v0 + (size_t)u * blockDim.x;
+      if (v < hi) {
+        float a[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) a[i] = 0.f;
+        Wt::accum(a, w[u]);
+        adam_apply<V>(ad, k, grad, goff<V>(live, v), a, dacc);
+      }
+    }
+  }
+}
+
+template <bool kBf16, int kAlgo, bool kAdam>
 __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, float* __restrict__ grad,
                                                                  size_t n, float scale,
-                                                                 const int* __restrict__ live) {
+                                                                 const int* __restrict__ live, const AdamFuse ad) {
   using Wt = Wire<kBf16>;
   constexpr int V = Wt::kVec;
   __shared__ uint32_t s_epoch;
@@ -252,6 +335,13 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
   // NVLS uses the symmetric (multicast-mapped) region instead of the IPC region for data
   char* my_data = (kAlgo == kNvls) ? c.mc_local - kFlagBytes : my;
   uint4* my_stage = reinterpret_cast<uint4*>(my_data + stage_off);
+  AdamCoef ak{};
+  float dacc = 0.f;
+  if (kAdam) {
+    const float t = ad.step[0] + 1.f;
+    const float bc1 = 1.f - __powf(ad.b1, t), bc2 = 1.f - __powf(ad.b2, t);
+    ak.step_size = ad.lr / bc1; ak.inv_sqrt_bc2 = rsqrtf(bc2); ak.b1 = ad.b1; ak.b2 = ad.b2; ak.eps = ad.eps;
+  }
 
   // ---- pack: fused 1/W scale + cast into the peer-visible staging buffer -------------------------
   if (kAlgo == kOneShot) {
@@ -281,7 +371,8 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
 #pragma unroll
       for (int r = 0; r < kMaxRanks; ++r)
         if (r < W) Wt::accum(a, w[r]);
-      store_grad<V>(grad, goff<V>(live, v), a);
+      if (kAdam) adam_apply<V>(ad, ak, grad, goff<V>(live, v), a, dacc);
+      else store_grad<V>(grad, goff<V>(live, v), a);
     }
   } else {
     size_t lo, hi;
@@ -325,7 +416,19 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
     for (int r = 0; r < W; ++r) {
       size_t l2, h2;
       sub_range(nv, W, B, r, b, l2, h2);
-      unpack_range<kBf16>(grad, my_out, l2, h2, live);
+      if (kAdam) unpack_adam_range<kBf16>(grad, my_out, l2, h2, live, ad, ak, dacc);
+      else unpack_range<kBf16>(grad, my_out, l2, h2, live);
+    }
+  }
+  if (kAdam && ad.prev != nullptr && ad.diff_out != nullptr) {
+    __shared__ float wsum[kCommThreads / 32];
+    dacc = warp_sum(dacc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = dacc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float tt = threadIdx.x < kCommThreads / 32 ? wsum[threadIdx.x] : 0.f;
+      tt = warp_sum(tt);
+      if (threadIdx.x == 0) atomicAdd(ad.diff_out, tt);
     }
   }
   __syncthreads();
@@ -335,6 +438,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
     if (atomicAdd(ticket, 1u) == (uint32_t)(B - 1)) {      // last block of this call
       *ticket = 0u;
       calls_of(my)[0] += 1u;
+      if (kAdam && ad.bump) ad.step[0] += 1.f;             // every block has read the counter long ago (barriers above)
       __threadfence();
     }
   }
@@ -461,15 +565,21 @@ int hz_comm_blocks_for(HzComm* c, size_t n, int algo, int wire_bf16) {
 }
 
 // n = number of gradient elements on the wire (= all of them, or 64 * #live blocks when `live` is given)
-int hz_comm_allreduce(HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale, const int* live,
-                      cudaStream_t st) {
+static int comm_allreduce_impl(HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale, const int* live,
+                               const hz::AdamFuse* adam, cudaStream_t st) {
   const int V = wire_bf16 ? 8 : 4;
   if (n % V != 0) return -2;
   if (n * (wire_bf16 ? 2 : 4) > c->dev.buf_bytes) return -3;
   if (algo == hz::kNvls && c->dev.mc_base == nullptr) return -4;
   const int blocks = hz_comm_blocks_for(c, n, algo, wire_bf16);
-#define HZ_LAUNCH(BF, AL) \
-  hz::allreduce_kernel<BF, AL><<<blocks, hz::kCommThreads, 0, st>>>(c->dev, grad, n, scale, live)
+  hz::AdamFuse ad;
+  memset(&ad, 0, sizeof(ad));
+  if (adam) ad = *adam;
+#define HZ_LAUNCH(BF, AL)                                                                                     \
+  do {                                                                                                        \
+    if (adam) hz::allreduce_kernel<BF, AL, true><<<blocks, hz::kCommThreads, 0, st>>>(c->dev, grad, n, scale, live, ad);  \
+    else hz::allreduce_kernel<BF, AL, false><<<blocks, hz::kCommThreads, 0, st>>>(c->dev, grad, n, scale, live, ad);      \
+  } while (0)
   if (wire_bf16) {
     if (algo == hz::kOneShot) HZ_LAUNCH(true, hz::kOneShot);
     else if (algo == hz::kTwoShot) HZ_LAUNCH(true, hz::kTwoShot);
@@ -481,6 +591,22 @@ int hz_comm_allreduce(HzComm* c, float* grad, size_t n, int algo, int wire_bf16,
   }
 #undef HZ_LAUNCH
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int hz_comm_allreduce(HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale, const int* live,
+                      cudaStream_t st) {
+  return comm_allreduce_impl(c, grad, n, algo, wire_bf16, scale, live, nullptr, st);
+}
+
+// All-reduce (average) of a gradient bucket with the Adam update of the bucket's parameters fused into the
+// reduction's final phase (see AdamFuse).  `bump`: this is the last bucket of the optimizer step.
+int hz_comm_allreduce_adam(HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale, const int* live,
+                           float* p, float* m, float* v, void* shadow, float* prev, float* diff_out, float* step,
+                           float lr, float b1, float b2, float eps, int bump, cudaStream_t st) {
+  hz::AdamFuse ad;
+  ad.p = p; ad.m = m; ad.v = v; ad.shadow = (__nv_bfloat16*)shadow; ad.prev = prev; ad.diff_out = diff_out;
+  ad.step = step; ad.lr = lr; ad.b1 = b1; ad.b2 = b2; ad.eps = eps; ad.bump = bump;
+  return comm_allreduce_impl(c, grad, n, algo, wire_bf16, scale, live, &ad, st);
 }
 
 int hz_comm_barrier(HzComm* c, long long* stamps, cudaStream_t st) {

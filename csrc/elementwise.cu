@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(256) grad_diff_kernel(const float* __restrict_
 
 // stats[0..5] += (loss, correct, batch, sqrt(diff)*has_prev, has_prev, 1); has_prev = 1
 __global__ void stats_update_kernel(float* stats, float* has_prev, const float* loss,
-                                    const float* correct, float batch, const float* diff_sq) {
+                                    const float* correct, float batch, float* diff_sq) {
   pdl_launch();
   pdl_wait();
   stats[0] += loss[0];
@@ -754,6 +754,7 @@ __global__ void stats_update_kernel(float* stats, float* has_prev, const float* 
     stats[3] += sqrtf(diff_sq[0]) * hp;
     stats[4] += hp;
     has_prev[0] = 1.f;
+    diff_sq[0] = 0.f;      // consumed: the bucket-wise optimizer passes of the next step accumulate into it from zero
   }
 }
 
@@ -931,7 +932,7 @@ void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_
 }
 
 void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct,
-                     float batch, const float* diff_sq, cudaStream_t st) {
+                     float batch, float* diff_sq, cudaStream_t st) {
   hz::launch(hz::stats_update_kernel, dim3(1), dim3(1), 0, st, stats, has_prev, loss, correct, batch, diff_sq);
 }
 

@@ -35,7 +35,7 @@ void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, 
              size_t n_live_blocks, int bump, int max_ctas, cudaStream_t st);
 void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_t st);
 void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct, float batch,
-                     const float* diff_sq, cudaStream_t st);
+                     float* diff_sq, cudaStream_t st);
 
 // ---- conv_gemm.cu (tcgen05 implicit GEMM)
 int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
@@ -76,25 +76,29 @@ void hz_comm_set_multicast(struct HzComm* c, void* mc_ptr, void* local_ptr, size
 int hz_comm_blocks_for(struct HzComm* c, size_t n, int algo, int wire_bf16);
 int hz_comm_allreduce(struct HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
                       const int* live, cudaStream_t st);
+int hz_comm_allreduce_adam(struct HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
+                           const int* live, float* p, float* m, float* v, void* shadow, float* prev, float* diff_out,
+                           float* step, float lr, float b1, float b2, float eps, int bump, cudaStream_t st);
 int hz_comm_barrier(struct HzComm* c, long long* stamps, cudaStream_t st);
 int hz_comm_error(struct HzComm* c);
 void hz_comm_destroy(struct HzComm* c);
 
 // ---- tp_fused.cu (GEMM fused with its collective over peer memory; TP head; small bf16 all-reduce)
+void hz_tp_set_debug(long long* buf);
 int hz_tp_tiles(int kind, int N, int H, int W_, int Cin, int Cout, int stride);
 int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, const void* addend, float* stats,
                char* const* heaps, char* mc_heap, long long part_off, long long part_stride, long long cnt_off,
-               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int mode, int nvls, int ag,
-               int N, int H, int W_, int Cin, int Cout, int R, int stride, int pad, cudaStream_t st);
+               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int mode, int nvls, int ll,
+               int ag, int N, int H, int W_, int Cin, int Cout, int R, int stride, int pad, cudaStream_t st);
 int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t* labels, float* pooled,
                float* dl_local, float* logits, void* dfeat, float* loss, float* correct, char* const* heaps,
-               char* mc_heap, long long logits_off, long long dfeat_off, long long cnt_off, unsigned* epoch,
+               char* mc_heap, long long logits_off, long long dfeat_off, unsigned* epoch,
                unsigned* done, int world, int rank, int nvls, int N, int C, int HW, int k_local, int n_valid,
                float loss_scale, cudaStream_t st);
-size_t hz_tp_head_bytes(int N, int C, int K);
+size_t hz_tp_head_bytes(int N, int C, int K, int world);
 int hz_tp_allreduce_bf16(const void* in, void* out, size_t n, char* const* heaps, char* mc_heap, long long buf_off,
-                         long long cnt_off, unsigned* epoch, unsigned* done, int world, int rank, int nvls, int blocks,
-                         cudaStream_t st);
+                         long long cnt_off, unsigned* epoch, unsigned* done, int world, int rank, int nvls, int ll,
+                         int blocks, cudaStream_t st);
 void hz_head_wgrad(const float* pooled, const float* dlogits, float* dW, float* db, int N, int C, int K,
                    int accumulate, cudaStream_t st);
 

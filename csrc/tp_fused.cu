@@ -53,13 +53,14 @@ struct TpParams {
   // ---- peer part
   int world, rank;
   int mode;                      // 0: no reduction, 1: all-reduce, 2: reduce-scatter (tile % world keeps)
-  int nvls;                      // 1: multimem.red arrival + multimem.ld_reduce pull (heap is multicast-mapped)
+  int nvls;                      // 1: the heap is multicast-mapped: multimem.st / multimem.red / multimem.ld_reduce
+  int ll;                        // 1: latency protocol (flag-in-data push), 0: bandwidth protocol (counter + pull)
   int ag;                        // 1: A is image-sharded, ag_imgs images per rank
   int ag_imgs;
   char* heap[kTpMaxRanks];       // symmetric heap base of every rank, as mapped in this process
   char* mc_heap;                 // multicast mapping of the same heap (nvls)
-  long long part_off;            // bf16 partial tiles [2 parities][tiles][128][64] (bytes from heap base)
-  long long part_stride;         // bytes between the two parity copies
+  long long part_off;            // partial tiles (bytes from heap base): bandwidth protocol bf16 [2 parities][tiles][128][64];
+  long long part_stride;         //   latency protocol LL words [2][world][tiles][128][64] (2x the bytes); stride of a parity
   long long cnt_off;             // u32 [tiles] arrival counters (monotonic: += W per call)
   long long ready_off;           // u32 [world]      (AG: "my A shard is ready")
   unsigned* epoch;               // local: number of completed calls
@@ -68,6 +69,7 @@ struct TpParams {
   const __nv_bfloat16* addend;   // optional, layout of out: out = reduced tile + addend (residual gradient)
   float* stats;                  // optional [2*ncols]: sum y, sum y^2 of the REDUCED output (pre-zeroed)
   long long timeout_clk;
+  long long* dbg;                // optional: per-CTA clock64 stamps of the kernel's phases (tools/tp_timeline.py)
 };
 
 HZ_DEVINL void st_release_sys_u32(unsigned* p, unsigned v) {
@@ -97,6 +99,20 @@ HZ_DEVINL void spin_until_ge(const unsigned* p, unsigned e, long long timeout_cl
     if (clock64() - t0 > timeout_clk) __trap();
   }
 }
+// "LL" words: 16 bytes = {data, flag, data, flag}.  8-byte halves are single-copy atomic, so a receiver that sees the
+// flag sees the data next to it - no fence between payload and flag (the protocol NCCL uses for small messages).
+HZ_DEVINL void ll_store(void* dst, const uint4& v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+HZ_DEVINL void ll_mc_store(void* mc_dst, const uint4& v) {      // replicated to every rank by the NVSwitch
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_dst), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w) : "memory");
+}
+HZ_DEVINL uint4 ll_load(const void* src) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+  return v;
+}
 // 1-D bulk copy global (possibly a peer's HBM over NVLink) -> shared, completion on an mbarrier
 HZ_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -123,6 +139,9 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   const int mt = blockIdx.x, nt = blockIdx.y, cls = blockIdx.z;
   const int tiles = gridDim.x * gridDim.y * gridDim.z;
   const int tile = (cls * gridDim.y + nt) * gridDim.x + mt;
+  long long* dbg = p.dbg ? p.dbg + (size_t)tile * 16 : nullptr;
+#define HZ_STAMP(i) do { if (dbg != nullptr && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
+  HZ_STAMP(0);                                   // kernel entry
   const TapList& taps = p.cls[cls];
   const int n0 = (p.BN == 1) ? mt / p.tiles_per_img : mt * p.BN;
   const int h0 = (p.BN == 1) ? (mt % p.tiles_per_img) * p.BH : 0;
@@ -150,7 +169,9 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_d = *tmem_slot;
+  HZ_STAMP(1);                                  // prologue done
   pdl_wait();                                   // the A operand / addend / epoch counter come from upstream kernels
+  HZ_STAMP(2);                                  // upstream kernel complete
   const unsigned e = *p.epoch + 1u;             // epoch of this call (same on every rank)
 
   if (p.ag && warp == 3) {
@@ -234,13 +255,11 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
     tc::mbar_wait(tmem_full, 0);
     tc::fence_after_sync();
   }
+  HZ_STAMP(3);                                  // accumulator complete
 
-  __nv_bfloat16* staging = reinterpret_cast<__nv_bfloat16*>(smem);          // [128][kStagingLd]   (mode 0)
-  uint4 red[kPasses];                                                        // reduced bf16x8 vectors (modes 1, 2)
-  if (reducing) {
-    // ---- 1. my partial tile -> bf16 -> my own slot (row-major [128][64]: every thread writes one full 128 B line)
-    const long long slot = p.part_off + (long long)(e & 1u) * p.part_stride + (long long)tile * kTpPartBytes;
-    __nv_bfloat16* mine = reinterpret_cast<__nv_bfloat16*>(my_heap + slot) + row * BLOCK_N;
+  // ---- accumulator -> bf16 tile in shared memory (the operand ring is idle now)
+  __nv_bfloat16* staging = reinterpret_cast<__nv_bfloat16*>(smem + S::kPipeBytes - S::kStagingBytes);   // [128][kStagingLd]
+  {
 #pragma unroll
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
@@ -251,32 +270,128 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;            // a parity class without taps: exactly zero
       }
+      __nv_bfloat16* dst = staging + row * S::kStagingLd + c0;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[j + i]);
-        st8(mine + c0 + j, pack8(f));
+        st8(dst + j, pack8(f));
       }
     }
-    __threadfence_system();
     tc::fence_before_sync();
     __syncthreads();
+  }
+  uint4 red[kPasses];                                                        // reduced bf16x8 vectors (modes 1, 2)
+  if (reducing && p.ll) {
+    // ================= latency protocol ("LL"): data and flag travel in the same 8 bytes =================
+    // Every 16-byte store carries {2 bf16, epoch, 2 bf16, epoch}: the receiver polls the payload itself, so there is
+    // no fence, no separate flag and no counter on the critical path (phase stamps of the fence + counter protocol on
+    // 2 GPUs: 7.3 us for the system fences, 3.4 us for the releasing arrival, 2 us waiting, 3.9 us pulling).
+    // Push: my partial tile goes into slot [parity][me][tile] of every rank that keeps the tile - ONE multimem.st
+    // per 16 bytes when the heap is multicast-mapped (the NVSwitch replicates it), else one store per peer.
+    const long long slot0 = p.part_off + (long long)(e & 1u) * p.part_stride;
+    const long long tile_bytes = 2LL * kTpPartBytes;                        // 32 KB on the wire per tile
+    const long long my_slot = slot0 + ((long long)me * tiles + tile) * tile_bytes;
+    const bool use_mc = p.nvls && p.mode == 1;
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      const int r0 = threadIdx.x / kVecPerRow + i * kRowsPerPass;
+      const bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+      const long long off = my_slot + (long long)(r0 * BLOCK_N + vec * 8) * 4;           // 4 wire bytes per element
+      const uint4 lo = make_uint4(w[0], e, w[1], e), hi = make_uint4(w[2], e, w[3], e);
+      if (use_mc) {
+        ll_mc_store(p.mc_heap + off, lo);
+        ll_mc_store(p.mc_heap + off + 16, hi);
+      } else if (p.mode == 1) {
+        for (int d = 0; d < W; ++d) {
+          char* dst = p.heap[(me + d) % W] + off;
+          ll_store(dst, lo);
+          ll_store(dst + 16, hi);
+        }
+      } else {
+        char* dst = p.heap[tile % W] + off;
+        ll_store(dst, lo);
+        ll_store(dst + 16, hi);
+      }
+    }
+    HZ_STAMP(4);                                // partial tile pushed
+    HZ_STAMP(5);
+    if (keeper) {
+      // Receive: every rank's copy of the tile sits in MY memory; poll the words until they carry this epoch and sum
+      // in rank order (deterministic, bit-identical on every rank).
+      float acc[kPasses][8];
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+      const long long t0 = clock64();
+      for (int rr = 0; rr < W; ++rr) {
+        const char* src = my_heap + slot0 + ((long long)rr * tiles + tile) * tile_bytes;
+        uint4 lo[kPasses], hi[kPasses];
+#pragma unroll
+        for (int i = 0; i < kPasses; ++i) {
+          const int r0 = threadIdx.x / kVecPerRow + i * kRowsPerPass;
+          const char* q = src + (long long)(r0 * BLOCK_N + vec * 8) * 4;
+          lo[i] = ll_load(q);
+          hi[i] = ll_load(q + 16);
+        }
+#pragma unroll
+        for (int i = 0; i < kPasses; ++i) {
+          const int r0 = threadIdx.x / kVecPerRow + i * kRowsPerPass;
+          const char* q = src + (long long)(r0 * BLOCK_N + vec * 8) * 4;
+          while (lo[i].y != e || lo[i].w != e || hi[i].y != e || hi[i].w != e) {
+            if (clock64() - t0 > p.timeout_clk) __trap();
+            lo[i] = ll_load(q);
+            hi[i] = ll_load(q + 16);
+          }
+          const uint32_t w[4] = {lo[i].x, lo[i].z, hi[i].x, hi[i].z};
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(w), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] += f[j];
+        }
+        if (rr == 0) HZ_STAMP(6);               // first rank's tile has arrived
+      }
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const bf16x8 pk = pack8(acc[i]);
+        red[i] = *reinterpret_cast<const uint4*>(&pk);
+      }
+    }
+  } else if (reducing) {
+    // ================= bandwidth protocol: partial in my own slot, arrival counter, pull =================
+    // ---- 1. my partial tile -> my own slot (row-major [128][64] bf16, coalesced 16-byte stores)
+    const long long slot = p.part_off + (long long)(e & 1u) * p.part_stride + (long long)tile * kTpPartBytes;
+#pragma unroll
+    for (int i = 0; i < kPasses; ++i) {
+      const int r0 = threadIdx.x / kVecPerRow + i * kRowsPerPass;
+      st8(reinterpret_cast<__nv_bfloat16*>(my_heap + slot) + r0 * BLOCK_N + vec * 8, ld8(staging + r0 * S::kStagingLd + vec * 8));
+    }
+    // one releasing arrival per CTA orders the whole tile: the CTA barrier makes every thread's stores happen-before
+    // thread 0's release (cumulativity) - no per-thread system fence (measured 7 us for 128 of them)
+    __syncthreads();
+    HZ_STAMP(4);                                // partial tile written
     // ---- 2. arrival: bump the tile's counter wherever the tile is needed
     unsigned* cnt_local = reinterpret_cast<unsigned*>(my_heap + p.cnt_off) + tile;
-    if (p.mode == 1) {
-      if (p.nvls) {
-        if (threadIdx.x == 0) multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + tile, 1u);
-      } else if (threadIdx.x < W) {
-        red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.cnt_off) + tile, 1u);
+    if (threadIdx.x == 0) {
+      if (p.mode == 1) {
+        if (p.nvls) {
+          multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + tile, 1u);
+        } else {
+          for (int d = 0; d < W; ++d) red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[(me + d) % W] + p.cnt_off) + tile, 1u);
+        }
+      } else {
+        red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[tile % W] + p.cnt_off) + tile, 1u);
       }
-    } else if (threadIdx.x == 0) {
-      red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[tile % W] + p.cnt_off) + tile, 1u);
     }
+    HZ_STAMP(5);                                // arrival posted
     if (keeper) {
       // ---- 3. wait for all W partials of this tile, 4. pull them
       if (threadIdx.x == 0) spin_until_ge(cnt_local, (unsigned)W * e, p.timeout_clk);
       __syncthreads();
+      HZ_STAMP(6);                              // all W partials have arrived
       if (p.nvls) {
         const char* mc_tile = p.mc_heap + slot;
 #pragma unroll
@@ -311,30 +426,8 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
         }
       }
     }
-  } else {
-    if (k_iters > 0) {
-#pragma unroll
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
-        tc::tmem_ld_wait();
-        __nv_bfloat16* dst = staging + row * S::kStagingLd + c0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[j + i]);
-          st8(dst + j, pack8(f));
-        }
-      }
-    } else {
-      float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 8) st8(staging + row * S::kStagingLd + c0, pack8(z));
-    }
-    tc::fence_before_sync();
-    __syncthreads();
   }
-
+  HZ_STAMP(7);                                  // reduced tile in registers (pull complete)
   if (keeper) {
     // ---- coalesced stores of the finished tile (+ BatchNorm sums, + residual-gradient addend)
     float ssum[8], ssq[8];
@@ -383,6 +476,7 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   }
   tc::fence_before_sync();
   __syncthreads();
+  HZ_STAMP(8);                                  // output rows (+ BN sums) written
   if (warp == 2) tc::tmem_dealloc(tmem_d, BLOCK_N);
   // ---- the last CTA of the grid publishes the new epoch (every CTA has already read the old one)
   if (threadIdx.x == 0) {
@@ -394,6 +488,8 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
       __threadfence();
     }
   }
+  HZ_STAMP(9);
+#undef HZ_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -409,13 +505,21 @@ struct TpHeadParams {
   float loss_scale;
   char* heap[kTpMaxRanks];
   char* mc_heap;
-  long long logits_off;          // f32 [2 parities][N][K]
-  long long dfeat_off;           // f32 [2 parities][N][C]   partial dX of this rank
-  long long cnt_off;             // u32 [2][N] arrival counters (logits, dfeat), monotonic
+  long long logits_off;          // LL words {f32, epoch}: [2 parities][N][K]
+  long long dfeat_off;           // LL words {f32, epoch}: [2 parities][world][N][C]   partial dX of every rank
   long long par_stride_logits, par_stride_dfeat;
   unsigned* epoch; unsigned* done;
   long long timeout_clk;
 };
+
+HZ_DEVINL void ll_store2(void* dst, uint32_t data, uint32_t flag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(dst), "r"(data), "r"(flag) : "memory");
+}
+HZ_DEVINL uint2 ll_load2(const void* src) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(src) : "memory");
+  return v;
+}
 
 __global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __restrict__ feat,
                                                       const float* __restrict__ Wl, const float* __restrict__ bl,
@@ -434,6 +538,7 @@ __global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __res
   const unsigned par = e & 1u;
   char* my_heap = p.heap[me];
   const float inv_hw = 1.f / (float)p.HW;
+  const long long t0 = clock64();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (int q = 0; q < p.HW; ++q) s += __bfloat162float(feat[((size_t)n * p.HW + q) * C + c]);
@@ -443,8 +548,9 @@ __global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __res
   }
   __syncthreads();
   // ---- my logit columns, pushed into the logits row of EVERY rank (the reference's K8 all-gather: k floats per peer)
+  //      as {value, epoch} words: the receiver polls the word itself, no fence and no separate flag
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const long long lrow = p.logits_off + (long long)par * p.par_stride_logits + ((long long)n * K + me * kl) * 4;
+  const long long lrow = p.logits_off + (long long)par * p.par_stride_logits + ((long long)n * K) * 8;
   for (int k = warp; k < kl; k += nwarp) {
     const int kg = me * kl + k;
     float s = 0.f;
@@ -455,23 +561,17 @@ __global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __res
     } else {
       s = -INFINITY;                          // class padding (10 classes over 8 ranks -> 16): masked
     }
-    if (lane < W) *reinterpret_cast<float*>(p.heap[lane] + lrow + k * 4) = s;
+    if (lane < W) ll_store2(p.heap[lane] + lrow + (long long)kg * 8, __float_as_uint(s), e);
   }
-  __threadfence_system();
-  __syncthreads();
-  unsigned* cnt_lg = reinterpret_cast<unsigned*>(my_heap + p.cnt_off) + n;
-  unsigned* cnt_df = cnt_lg + p.N;
-  if (W > 1) {
-    if (p.nvls) {
-      if (threadIdx.x == 0) multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + n, 1u);
-    } else if (threadIdx.x < W) {
-      red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.cnt_off) + n, 1u);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const char* q = my_heap + lrow + (long long)k * 8;
+    uint2 v = ll_load2(q);
+    while (v.y != e) {
+      if (clock64() - t0 > p.timeout_clk) __trap();
+      v = ll_load2(q);
     }
-    if (threadIdx.x == 0) spin_until_ge(cnt_lg, (unsigned)W * e, p.timeout_clk);
-    __syncthreads();
+    lg[k] = __uint_as_float(v.x);
   }
-  const float* lrow_all = reinterpret_cast<const float*>(my_heap + p.logits_off + (long long)par * p.par_stride_logits) + (size_t)n * K;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) lg[k] = __ldcg(lrow_all + k);
   __syncthreads();
   // ---- softmax cross-entropy over the gathered row (identical on every rank)
   if (warp == 0) {
@@ -501,41 +601,44 @@ __global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __res
   }
   __syncthreads();
   if (dfeat != nullptr) {
-    // ---- dX = sum_r dY_r . W_r : my partial (fp32) -> my slot, arrival, pull-reduce over the ranks
-    const long long drow = p.dfeat_off + (long long)par * p.par_stride_dfeat + (long long)n * C * 4;
-    float* mine = reinterpret_cast<float*>(my_heap + drow);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s = 0.f;
+    // ---- dX = sum_r dY_r . W_r : my partial (fp32) pushed as {value, epoch} words into slot [me] of every rank, then
+    //      the W slots of MY memory are polled and summed in rank order (bit-identical everywhere)
+    const long long dbase = p.dfeat_off + (long long)par * p.par_stride_dfeat;
+    for (int c4 = threadIdx.x * 4; c4 < C; c4 += blockDim.x * 4) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
       for (int k = 0; k < kl; ++k)
-        if (me * kl + k < p.n_valid) s += dl[me * kl + k] * Wl[(size_t)k * C + c];
-      mine[c] = s;
-    }
-    if (W > 1) {
-      __threadfence_system();
-      __syncthreads();
-      if (p.nvls) {
-        if (threadIdx.x == 0) multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + p.N + n, 1u);
-      } else if (threadIdx.x < W) {
-        red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.cnt_off) + p.N + n, 1u);
+        if (me * kl + k < p.n_valid) {
+          const float d = dl[me * kl + k];
+          const float4 w = *reinterpret_cast<const float4*>(Wl + (size_t)k * C + c4);
+          s[0] += d * w.x; s[1] += d * w.y; s[2] += d * w.z; s[3] += d * w.w;
+        }
+      const long long off = dbase + (((long long)me * p.N + n) * C + c4) * 8;
+      const uint4 lo = make_uint4(__float_as_uint(s[0]), e, __float_as_uint(s[1]), e);
+      const uint4 hi = make_uint4(__float_as_uint(s[2]), e, __float_as_uint(s[3]), e);
+      if (W > 1 && p.nvls) {
+        ll_mc_store(p.mc_heap + off, lo);
+        ll_mc_store(p.mc_heap + off + 16, hi);
+      } else {
+        for (int d = 0; d < W; ++d) {
+          char* dst = p.heap[(me + d) % W] + off;
+          ll_store(dst, lo);
+          ll_store(dst + 16, hi);
+        }
       }
-      if (threadIdx.x == 0) spin_until_ge(cnt_df, (unsigned)W * e, p.timeout_clk);
-      __syncthreads();
     }
     for (int c4 = threadIdx.x * 4; c4 < C; c4 += blockDim.x * 4) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (W > 1 && p.nvls) {
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p.mc_heap + drow + c4 * 4) : "memory");
-      } else {
-        float4 v[kTpMaxRanks];
-#pragma unroll
-        for (int rr = 0; rr < kTpMaxRanks; ++rr)
-          if (rr < W) v[rr] = __ldcg(reinterpret_cast<const float4*>(p.heap[rr] + drow + c4 * 4));
-#pragma unroll
-        for (int rr = 0; rr < kTpMaxRanks; ++rr)
-          if (rr < W) { a.x += v[rr].x; a.y += v[rr].y; a.z += v[rr].z; a.w += v[rr].w; }
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int rr = 0; rr < W; ++rr) {
+        const char* q = my_heap + dbase + (((long long)rr * p.N + n) * C + c4) * 8;
+        uint4 lo = ll_load(q), hi = ll_load(q + 16);
+        while (lo.y != e || lo.w != e || hi.y != e || hi.w != e) {
+          if (clock64() - t0 > p.timeout_clk) __trap();
+          lo = ll_load(q); hi = ll_load(q + 16);
+        }
+        a[0] += __uint_as_float(lo.x); a[1] += __uint_as_float(lo.z);
+        a[2] += __uint_as_float(hi.x); a[3] += __uint_as_float(hi.z);
       }
-      const float g[4] = {a.x * inv_hw, a.y * inv_hw, a.z * inv_hw, a.w * inv_hw};
+      const float g[4] = {a[0] * inv_hw, a[1] * inv_hw, a[2] * inv_hw, a[3] * inv_hw};
       for (int q = 0; q < p.HW; ++q) {
         __nv_bfloat16* d = dfeat + ((size_t)n * p.HW + q) * C + c4;
         *reinterpret_cast<__nv_bfloat162*>(d) = __floats2bfloat162_rn(g[0], g[1]);
@@ -560,10 +663,10 @@ __global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __res
 // protocol as the fused epilogue: copy in -> arrival counter -> multimem.ld_reduce / rank-ordered peer pull.
 // ------------------------------------------------------------------------------------------------
 struct TpArParams {
-  int world, rank, nvls;
+  int world, rank, nvls, ll;
   char* heap[kTpMaxRanks];
   char* mc_heap;
-  long long buf_off, buf_stride;     // bf16 [2 parities][n]
+  long long buf_off, buf_stride;     // bw: bf16 [2 parities][n];  ll: LL words [2 parities][world][n/8] x 32 B
   long long cnt_off;                 // u32 [gridDim.x]
   unsigned* epoch; unsigned* done;
   long long timeout_clk;
@@ -579,17 +682,68 @@ __global__ void __launch_bounds__(256) tp_allreduce_bf16_kernel(const __nv_bfloa
   const long long boff = p.buf_off + (long long)(e & 1u) * p.buf_stride;
   const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
   const size_t lo = min((size_t)blockIdx.x * per, nvec), hi = min(lo + per, nvec);
+  if (p.ll) {
+    // latency protocol: {2 bf16, epoch} words pushed into slot [me] of every rank, W local slots polled and summed
+    const long long lbase = p.buf_off + (long long)(e & 1u) * p.buf_stride;          // [world][nvec] x 32 B
+    const long long t0 = clock64();
+    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+      const uint4 d = reinterpret_cast<const uint4*>(in)[v];
+      const uint4 w0 = make_uint4(d.x, e, d.y, e), w1 = make_uint4(d.z, e, d.w, e);
+      const long long off = lbase + ((long long)me * nvec + v) * 32;
+      if (p.nvls) {
+        ll_mc_store(p.mc_heap + off, w0);
+        ll_mc_store(p.mc_heap + off + 16, w1);
+      } else {
+        for (int dd = 0; dd < W; ++dd) {
+          char* dst = p.heap[(me + dd) % W] + off;
+          ll_store(dst, w0);
+          ll_store(dst + 16, w1);
+        }
+      }
+    }
+    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+      float a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = 0.f;
+      for (int r = 0; r < W; ++r) {
+        const char* q = p.heap[me] + lbase + ((long long)r * nvec + v) * 32;
+        uint4 w0 = ll_load(q), w1 = ll_load(q + 16);
+        while (w0.y != e || w0.w != e || w1.y != e || w1.w != e) {
+          if (clock64() - t0 > p.timeout_clk) __trap();
+          w0 = ll_load(q); w1 = ll_load(q + 16);
+        }
+        const uint32_t w[4] = {w0.x, w0.z, w1.x, w1.z};
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(w), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] += f[i];
+      }
+      const bf16x8 pk = pack8(a);
+      reinterpret_cast<uint4*>(out)[v] = *reinterpret_cast<const uint4*>(&pk);
+    }
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned fin = atomicAdd(p.done, 1u);
+      if (fin == gridDim.x - 1) {
+        *p.done = 0u;
+        *p.epoch = e;
+        __threadfence();
+      }
+    }
+    return;
+  }
   uint4* mine = reinterpret_cast<uint4*>(p.heap[me] + boff);
   for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) mine[v] = reinterpret_cast<const uint4*>(in)[v];
-  __threadfence_system();
-  __syncthreads();
-  if (p.nvls) {
-    if (threadIdx.x == 0) multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + blockIdx.x, 1u);
-  } else if (threadIdx.x < W) {
-    red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[threadIdx.x] + p.cnt_off) + blockIdx.x, 1u);
-  }
-  if (threadIdx.x == 0)
+  __syncthreads();              // one releasing arrival per CTA orders the block's stores (no per-thread system fence)
+  if (threadIdx.x == 0) {
+    if (p.nvls) {
+      multimem_red_add_u32(reinterpret_cast<unsigned*>(p.mc_heap + p.cnt_off) + blockIdx.x, 1u);
+    } else {
+      for (int dd = 0; dd < W; ++dd)
+        red_release_sys_add_u32(reinterpret_cast<unsigned*>(p.heap[(me + dd) % W] + p.cnt_off) + blockIdx.x, 1u);
+    }
     spin_until_ge(reinterpret_cast<unsigned*>(p.heap[me] + p.cnt_off) + blockIdx.x, (unsigned)W * e, p.timeout_clk);
+  }
   __syncthreads();
   for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
     uint4 o;
@@ -635,6 +789,7 @@ __global__ void __launch_bounds__(256) tp_allreduce_bf16_kernel(const __nv_bfloa
 using namespace hz::host;
 
 namespace {
+long long* g_tp_dbg = nullptr;
 long long tp_timeout_clk() {
   static const long long v = [] {
     const char* e = getenv("HZ_COMM_TIMEOUT_S");
@@ -646,6 +801,9 @@ long long tp_timeout_clk() {
 }  // namespace
 
 extern "C" {
+
+// per-CTA phase stamps (16 x int64 per tile) for the next fused launches; nullptr switches them off
+void hz_tp_set_debug(long long* buf) { g_tp_dbg = buf; }
 
 // tiles of the fused op over output [N, H, W, n_out] (per parity class for stride-2 dgrad), or -1
 int hz_tp_tiles(int kind, int N, int H, int W_, int Cin, int Cout, int stride) {
@@ -662,8 +820,8 @@ int hz_tp_tiles(int kind, int N, int H, int W_, int Cin, int Cout, int stride) {
 // heaps[r]: heap base of rank r as mapped here; mc_heap: multicast mapping (nvls) or null.
 int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, const void* addend, float* stats,
                char* const* heaps, char* mc_heap, long long part_off, long long part_stride, long long cnt_off,
-               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int mode, int nvls, int ag,
-               int N, int H, int W_, int Cin, int Cout, int R, int stride, int pad, cudaStream_t st) {
+               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int mode, int nvls, int ll,
+               int ag, int N, int H, int W_, int Cin, int Cout, int R, int stride, int pad, cudaStream_t st) {
   const int S_ = R;
   if (kind == 0 && stride != 1) return -23;
   if ((Cin | Cout) & 7) return -20;
@@ -725,6 +883,7 @@ int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, co
   p.out_n_stride = (long long)Hout * Wout * Nn; p.out_h_stride = (long long)so * Wout * Nn; p.out_w_stride = (long long)so * Nn;
   p.ncols = Nn;
   p.world = world; p.rank = rank; p.mode = world > 1 ? mode : 0; p.nvls = (nvls && mc_heap != nullptr && world > 1) ? 1 : 0;
+  p.ll = ll ? 1 : 0;
   p.ag = ag; p.ag_imgs = imgs_per_rank;
   for (int r = 0; r < world; ++r) p.heap[r] = heaps[r];
   p.mc_heap = mc_heap;
@@ -732,6 +891,7 @@ int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, co
   p.epoch = epoch; p.done = done;
   p.out = (__nv_bfloat16*)out; p.addend = (const __nv_bfloat16*)addend; p.stats = stats;
   p.timeout_clk = tp_timeout_clk();
+  p.dbg = g_tp_dbg;
   using SM = hz::IgemmSmem<64>;
   dim3 grid(t.tiles, n_tiles, classes);
   if (kind == 0) {
@@ -749,7 +909,7 @@ int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, co
 // dfeat [N,HW,C] bf16 (optional), loss / correct accumulators (pre-zeroed).
 int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t* labels, float* pooled,
                float* dl_local, float* logits, void* dfeat, float* loss, float* correct, char* const* heaps,
-               char* mc_heap, long long logits_off, long long dfeat_off, long long cnt_off, unsigned* epoch,
+               char* mc_heap, long long logits_off, long long dfeat_off, unsigned* epoch,
                unsigned* done, int world, int rank, int nvls, int N, int C, int HW, int k_local, int n_valid,
                float loss_scale, cudaStream_t st) {
   if (C & 3) return -20;
@@ -760,9 +920,9 @@ int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t
   p.loss_scale = loss_scale;
   for (int r = 0; r < world; ++r) p.heap[r] = heaps[r];
   p.mc_heap = mc_heap;
-  p.logits_off = logits_off; p.dfeat_off = dfeat_off; p.cnt_off = cnt_off;
-  p.par_stride_logits = (long long)N * p.K * 4;
-  p.par_stride_dfeat = (long long)N * C * 4;
+  p.logits_off = logits_off; p.dfeat_off = dfeat_off;
+  p.par_stride_logits = (long long)N * p.K * 8;
+  p.par_stride_dfeat = (long long)world * N * C * 8;
   p.epoch = epoch; p.done = done;
   p.timeout_clk = tp_timeout_clk();
   if (N > 148) return -21;
@@ -771,19 +931,20 @@ int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t
                     pooled, dl_local, logits, (__nv_bfloat16*)dfeat, loss, correct, p) == cudaSuccess ? 0 : -1;
 }
 
-size_t hz_tp_head_bytes(int N, int C, int K) { return 2 * ((size_t)N * K * 4 + (size_t)N * C * 4) + 2 * (size_t)N * 4 + 64; }
+size_t hz_tp_head_bytes(int N, int C, int K, int world) { return 2 * ((size_t)N * K * 8 + (size_t)world * N * C * 8) + 64; }
 
 // out = sum over ranks of `in` (bf16, n elements, n % 8 == 0); buf: bf16 [2][n] in the heap, cnt: u32 [blocks]
 int hz_tp_allreduce_bf16(const void* in, void* out, size_t n, char* const* heaps, char* mc_heap, long long buf_off,
-                         long long cnt_off, unsigned* epoch, unsigned* done, int world, int rank, int nvls, int blocks,
-                         cudaStream_t st) {
+                         long long cnt_off, unsigned* epoch, unsigned* done, int world, int rank, int nvls, int ll,
+                         int blocks, cudaStream_t st) {
   if (n & 7) return -20;
   hz::TpArParams p;
   memset(&p, 0, sizeof(p));
   p.world = world; p.rank = rank; p.nvls = (nvls && mc_heap != nullptr && world > 1) ? 1 : 0;
   for (int r = 0; r < world; ++r) p.heap[r] = heaps[r];
   p.mc_heap = mc_heap;
-  p.buf_off = buf_off; p.buf_stride = (long long)n * 2; p.cnt_off = cnt_off;
+  p.ll = ll ? 1 : 0;
+  p.buf_off = buf_off; p.buf_stride = ll ? (long long)world * n * 4 : (long long)n * 2; p.cnt_off = cnt_off;
   p.epoch = epoch; p.done = done;
   p.timeout_clk = tp_timeout_clk();
   if (blocks < 1) blocks = 1;

@@ -28,7 +28,7 @@ REF_COLUMNS_DP = ["epoch", "loss", "accuracy", "epoch_time", "avg_step_time", "c
                   "comm_time", "idle_time", "avg_cpu", "avg_memory", "grad_divergence"]
 REF_COLUMNS_BW = REF_COLUMNS_DP[:-1] + ["avg_bandwidth", "grad_divergence"]
 EXT_COLUMNS = ["images_per_sec", "fwd_ms", "bwd_ms", "allreduce_ms", "exposed_comm_ms", "p2p_ms",
-               "optimizer_ms", "nvlink_GBps", "gpu_mem_MB", "steps"]
+               "optimizer_ms", "nvlink_GBps", "gpu_mem_MB", "steps", "split_source"]
 
 
 def ref_columns(strategy: str) -> List[str]:

@@ -40,7 +40,7 @@ class FlatParams:
     def __init__(self, named_params: Sequence[Tuple[str, nn.Parameter]], device, compute_dtype,
                  bucket_cap_mb: float = 25.0, reverse: bool = True, first_bucket_mb: float = 1.0,
                  live_masks: Optional[Dict[str, torch.Tensor]] = None, bucket_by_live: bool = False,
-                 pad_multiple: int = ALIGN):
+                 pad_multiple: int = ALIGN, bucket_starts: Optional[Sequence[str]] = None):
         named = list(named_params)
         order = list(reversed(named)) if reverse else named
         self.names = [n for n, _ in order]
@@ -86,7 +86,12 @@ class FlatParams:
         blk = self._live_block_mask(live_masks) if live_masks else None
         # bucket_by_live: the caps count elements that actually travel (dead taps excluded), so a "25 MiB" bucket
         # of mostly-dead layer4 weights does not delay the collective of the live ones behind it
-        self.buckets = self._make_buckets(bucket_cap_mb, first_bucket_mb, blk if bucket_by_live else None)
+        # bucket_starts: explicit boundaries — a parameter whose name starts with one of these prefixes opens a new
+        # bucket the first time the prefix is met (gradient-ready order), e.g. ("layer3.", "layer2.", "layer1.") gives
+        # [fc+layer4] [layer3] [layer2] [layer1+stem]: every bucket's collective starts the moment its layer group's
+        # backward is done and the bucket that can only be reduced after the very last gradient is the smallest one
+        self.buckets = (self._make_buckets_at(bucket_starts) if bucket_starts else
+                        self._make_buckets(bucket_cap_mb, first_bucket_mb, blk if bucket_by_live else None))
         self.bucket_live: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
         if blk is not None:
             self._build_live(blk)
@@ -114,6 +119,21 @@ class FlatParams:
                 buckets.append(Bucket(len(buckets), start, end, names))
                 start, names = end, []
                 cap = int(cap_mb * (1 << 20) / 4)
+        return buckets
+
+    def _make_buckets_at(self, starts: Sequence[str]) -> List[Bucket]:
+        buckets: List[Bucket] = []
+        seen = set()
+        start, names = 0, []
+        for i, nme in enumerate(self.names):
+            hit = next((s for s in starts if nme.startswith(s) and s not in seen), None)
+            if hit is not None:
+                seen.add(hit)
+                if names:
+                    buckets.append(Bucket(len(buckets), start, self.offsets[i], names))
+                    start, names = self.offsets[i], []
+            names.append(nme)
+        buckets.append(Bucket(len(buckets), start, self.total, names))
         return buckets
 
     def _live_block_mask(self, live_masks) -> Optional[torch.Tensor]:

@@ -254,3 +254,4 @@ def stats_update(stats, has_prev, loss, correct, batch: float, diff_sq):
         stats[3] += diff_sq.reshape(()).sqrt() * hp
         stats[4] += hp
         has_prev.fill_(1.0)
+        diff_sq.zero_()         # consumed (bucket-wise optimizer passes accumulate into it from zero)

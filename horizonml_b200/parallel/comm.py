@@ -86,6 +86,7 @@ class PeerAllReduce(GradAllReduce):
         self.handle = self.C.PeerComm(self.rank, self.world, self.device.index or 0,
                                       self.max_numel * wire_bytes, max_blocks)
         self.has_nvls = False
+        self.nvls_error: Optional[str] = None
         if self.world > 1:
             # 64-byte cudaIpcMemHandle of this rank's region -> everyone (opaque host bytes)
             objs: List[Optional[bytes]] = [None] * self.world
@@ -115,7 +116,8 @@ class PeerAllReduce(GradAllReduce):
             self._symm_buf, self._symm_hdl = buf, hdl
             self.handle.set_multicast(mc, buf.data_ptr(), nbytes)
             return True
-        except Exception as e:  # noqa: BLE001
+        except Exception as e:  # noqa: BLE001 — recorded (bench line / summaries show why NVLS is off), never silent
+            self.nvls_error = repr(e)
             if os.environ.get("HZ_DEBUG"):
                 print(f"[comm] NVLS setup failed: {e!r}")
             return False
@@ -131,6 +133,10 @@ class PeerAllReduce(GradAllReduce):
     def wire_bytes(self, numel: int) -> int:
         return numel * (2 if self.wire == "bf16" else 4)
 
+    def describe(self) -> dict:
+        return {"kind": "peer", "wire": self.wire, "algo": self.algo, "nvls": self.has_nvls, "nvls_error": self.nvls_error,
+                "max_blocks": self.max_blocks}
+
     def allreduce_avg_(self, t: torch.Tensor, algo: Optional[str] = None, live: Optional[torch.Tensor] = None) -> None:
         """``live``: int32 indices (relative to ``t``) of the 64-element blocks to reduce — the rest of ``t`` is
         known to be identically zero on every rank (dead conv taps) and never touches the wire."""
@@ -139,8 +145,26 @@ class PeerAllReduce(GradAllReduce):
         a = algo or self.pick(n_wire)
         self.handle.allreduce(t, a, self.wire == "bf16", 1.0 / self.world, live)
 
+    def allreduce_adam_(self, t: torch.Tensor, master, m, v, shadow, prev, diff_out, step_t, lr, b1, b2, eps,
+                        bump: bool, algo: Optional[str] = None, live: Optional[torch.Tensor] = None) -> str:
+        """Averaging all-reduce of gradient bucket ``t`` **and** the Adam update of the bucket's parameters in ONE
+        kernel (csrc/comm.cu ``AdamFuse``): the reduced values feed the update directly, the gradient slice is
+        cleared.  All tensors are the bucket's slices of their flat buffers.  Returns the algorithm used."""
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_numel
+        n_wire = t.numel() if live is None else live.numel() * 64
+        a = algo or self.pick(n_wire)
+        self.handle.allreduce_adam(t, a, self.wire == "bf16", 1.0 / self.world, live, master, m, v, shadow, prev,
+                                   diff_out, step_t, float(lr), float(b1), float(b2), float(eps), bool(bump))
+        return a
+
     def barrier(self) -> None:
         self.handle.barrier(None)
+
+    def check_error(self) -> None:
+        """Raise if a kernel of this communicator ever gave up waiting for a peer (it also traps, which surfaces as a
+        CUDA error at the next synchronisation; this is the explicit check trainers run once per epoch)."""
+        if self.handle.error():
+            raise RuntimeError("peer all-reduce: a rank never arrived at a flag barrier (HZ_COMM_TIMEOUT_S to extend)")
 
 
 def make_grad_allreduce(kind: str, max_numel: int, device, group=None, wire: str = "bf16") -> GradAllReduce:

@@ -25,10 +25,15 @@ from .comm import GradAllReduce
 
 class GradReducer:
     def __init__(self, flat: FlatParams, allreduce: Optional[GradAllReduce], overlap: bool = True,
-                 post_bucket: Optional[Callable[[int, bool], None]] = None):
+                 post_bucket: Optional[Callable[[int, bool], None]] = None,
+                 fused_bucket: Optional[Callable[[int, bool], None]] = None):
+        """``fused_bucket(b, last)`` replaces all-reduce + ``post_bucket`` by ONE kernel per bucket that reduces the
+        gradients over the peers and applies the optimizer to the bucket's parameters (csrc/comm.cu ``AdamFuse``)."""
         self.flat, self.ar = flat, allreduce
         self.world = allreduce.world if allreduce is not None else 1
         self.post_bucket = post_bucket
+        self.fused_bucket = fused_bucket
+        self.algos: List[Optional[str]] = [None] * len(flat.buckets)
         self.cuda = flat.device.type == "cuda"
         # NCCL collectives are captured on the main stream (the well-trodden CUDA-graph path); our peer kernels
         # (and, on one GPU, the bucket-wise optimizer alone) overlap with backward on a dedicated comm stream
@@ -58,12 +63,16 @@ class GradReducer:
         self._events = [None] * len(self._counts)
         self._n_launched = 0
         self.bytes_last_step = 0
+        self._seen = set()
 
     # called from inside backward, right after the kernel producing p's gradient was enqueued
     def _on_ready(self, p) -> None:
         if not self.active:
             return
         b = self.flat.bucket_index(p)
+        if id(p) in self._seen:          # one ready-hook per parameter per step: a repeat (module applied twice,
+            return                       # gradient accumulation) must not release the bucket early
+        self._seen.add(id(p))
         self._pending[b] -= 1
         # without overlap every bucket is launched from finish() (after the side stream has been joined)
         if self.overlap and self._pending[b] == 0 and not self._launched[b]:
@@ -71,6 +80,13 @@ class GradReducer:
 
     def _work(self, b: int) -> None:
         bk = self.flat.buckets[b]
+        if self.fused_bucket is not None and self.world > 1:
+            live = self.flat.bucket_live[b]
+            self.bytes_last_step += self.ar.wire_bytes(bk.end - bk.start if live is None else live.numel() * 64)
+            # buckets become ready in index order (reverse execution order), so the highest index is the last one
+            self.algos[b] = self.fused_bucket(b, self._n_launched == len(self.flat.buckets) - 1)
+            self._n_launched += 1
+            return
         if self.world > 1:
             live = self.flat.bucket_live[b] if hasattr(self.flat, "bucket_live") else None
             self.bytes_last_step += self.ar.wire_bytes(bk.end - bk.start if live is None else live.numel() * 64)

@@ -22,6 +22,7 @@ NCCL otherwise.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -96,8 +97,12 @@ class FusedTP:
     offsets).  ``x_shape`` is always the conv's *input* shape [N, Cin, H, W] (for kind 1: the shape of dx)."""
 
     PART = 128 * 64 * 2
+    # protocol choice: the latency ("LL", flag-in-data push) protocol moves world x tiles x 32 KB into every rank;
+    # beyond this many bytes the bandwidth protocol (bf16 partial in the owner's slot + arrival counter + NVSwitch
+    # ld_reduce / bulk pull) wins
+    LL_MAX_INGRESS = 6 << 20
 
-    def __init__(self, device, group=None, heap_mb: int = 64, heap=None):
+    def __init__(self, device, group=None, heap_mb: int = 256, heap=None, proto: str = "auto"):
         from ..ops import _ext
         from .symm import SymmHeap
         self.C = _ext.load(required=True)
@@ -106,6 +111,7 @@ class FusedTP:
         self.group = group
         self.world, self.rank = self.heap.world, self.heap.rank
         self.nvls = self.heap.nvls
+        self.proto = os.environ.get("HZ_TP_PROTO", proto)      # auto | ll | bw
         self.bytes_moved = 0
         self.ops: List[dict] = []
         self._ar_ops = {}
@@ -122,7 +128,14 @@ class FusedTP:
         t = self.tiles_for(kind, x_shape, cout, stride)
         return t is not None and t <= 148
 
-    def _wire(self, tiles):     # bytes this rank receives per call
+    def _use_ll(self, tiles) -> bool:
+        if self.proto in ("ll", "bw"):
+            return self.proto == "ll"
+        return self.world * tiles * 2 * self.PART <= self.LL_MAX_INGRESS
+
+    def _wire(self, tiles, ll):     # bytes this rank receives per call
+        if ll:
+            return (self.world - 1) * tiles * 2 * self.PART
         return tiles * self.PART * (1 if self.nvls else max(self.world - 1, 0))
 
     # ---- ops ---------------------------------------------------------------------------------------
@@ -135,23 +148,25 @@ class FusedTP:
         m = {"none": 0, "allreduce": 1, "reduce_scatter": 2}[mode]
         if m == 2 and tiles < self.world:
             raise ValueError("reduce-scatter needs at least one tile per rank")
-        part_off = h.alloc(2 * tiles * self.PART)
+        ll = bool(m) and self._use_ll(tiles)
+        part_stride = (self.world * tiles * 2 * self.PART) if ll else tiles * self.PART
+        part_off = h.alloc(2 * part_stride)
         cnt_off = h.alloc(4 * tiles)
         ready_off = h.alloc(4 * self.world)
         ctrl_off = h.alloc(8)
         ag = ag_off is not None
         C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
-        part_stride, xs = tiles * self.PART, list(x_shape)
-        wire = self._wire(tiles) if m else 0
+        xs = list(x_shape)
+        wire = self._wire(tiles, ll) if m else 0
         self.ops.append({"kind": kind, "x": tuple(x_shape), "w": tuple(w_shape), "stride": stride, "mode": mode,
-                         "ag": ag, "tiles": tiles, "nvls": nvls})
+                         "ag": ag, "tiles": tiles, "nvls": nvls, "protocol": ("ll" if ll else "bw") if m else None})
 
         def op(a, wgt, addend=None, stats=None):
             y = C.tp_conv(kind, None if ag else a, ag_off or 0, wgt, xs, stride, pad, addend, stats, ptrs, mc,
-                          part_off, part_stride, cnt_off, ready_off, ctrl_off, rank, m, nvls, ag)
+                          part_off, part_stride, cnt_off, ready_off, ctrl_off, rank, m, nvls, ag, ll)
             self.bytes_moved += wire
             return y
-        op.tiles, op.mode = tiles, mode
+        op.tiles, op.mode, op.ll = tiles, mode, ll
         return op
 
     def allreduce_conv(self, kind, x_shape, w_shape, stride=1, pad=1):
@@ -176,17 +191,16 @@ class FusedTP:
         """Tensor-parallel classifier head for batches of ``n`` samples (see ``tp_head_kernel``)."""
         h = self.heap
         K = k_local * self.world
-        logits_off = h.alloc(2 * n * K * 4)
-        dfeat_off = h.alloc(2 * n * c * 4)
-        cnt_off = h.alloc(2 * n * 4)
+        logits_off = h.alloc(2 * n * K * 8)                    # {value, epoch} words (flag-in-data protocol)
+        dfeat_off = h.alloc(2 * self.world * n * c * 8)
         ctrl_off = h.alloc(8)
         C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
-        wire = (self.world - 1) * n * (k_local * 4) + n * c * 4 * (1 if nvls else self.world - 1)
+        wire = (self.world - 1) * n * (k_local * 8 + c * 8)
         self.ops.append({"kind": "head", "n": n, "c": c, "k_local": k_local, "nvls": nvls})
 
         def op(feat, wl, bl, labels, loss_scale, n_valid, dw, db, accumulate, need_dfeat, zeroed2):
             out = C.tp_head(feat, wl, bl, labels, float(loss_scale), int(n_valid), dw, db, bool(accumulate),
-                            bool(need_dfeat), zeroed2, ptrs, mc, logits_off, dfeat_off, cnt_off, ctrl_off, rank, nvls)
+                            bool(need_dfeat), zeroed2, ptrs, mc, logits_off, dfeat_off, ctrl_off, rank, nvls)
             self.bytes_moved += wire
             return out
         return op
@@ -197,16 +211,18 @@ class FusedTP:
         if op is None:
             h = self.heap
             blocks = max(1, min(32, n * 2 // 16384))
-            buf_off = h.alloc(2 * n * 2)
+            ll = self.proto == "ll" or (self.proto == "auto" and self.world * n * 4 <= self.LL_MAX_INGRESS)
+            buf_off = h.alloc(2 * (self.world * n * 4 if ll else n * 2))
             cnt_off = h.alloc(4 * blocks)
             ctrl_off = h.alloc(8)
             C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
-            self.ops.append({"kind": "allreduce_bf16", "numel": n, "nvls": nvls})
+            self.ops.append({"kind": "allreduce_bf16", "numel": n, "nvls": nvls, "protocol": "ll" if ll else "bw"})
 
             def op(x):
-                return C.tp_allreduce_bf16(x, ptrs, mc, buf_off, cnt_off, ctrl_off, rank, nvls, blocks)
+                return C.tp_allreduce_bf16(x, ptrs, mc, buf_off, cnt_off, ctrl_off, rank, nvls, blocks, ll)
+            op.ll = ll
             self._ar_ops[n] = op
-        self.bytes_moved += n * 2 * (1 if self.nvls else self.world - 1)
+        self.bytes_moved += (self.world - 1) * n * 4 if op.ll else n * 2 * (1 if self.nvls else self.world - 1)
         return op(t)
 
     def describe(self) -> dict:

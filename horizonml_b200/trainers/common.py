@@ -209,6 +209,109 @@ def allreduce_max_scalar(x: float, device) -> float:
     return float(t.item())
 
 
+def split_compute_comm(dev_s: float, regions: Dict[str, float]):
+    """(compute_s, comm_s, source) of an epoch's device time in the reference's convention (its
+    "compute_time" stopwatch brackets the forward pass, its "comm_time" stopwatch backward + gradient exchange +
+    optimizer step; data_parallel_train.py:111-124).  The split is the measured forward share of the step
+    (``probe_step_regions``); without a measurement everything is reported as compute and the source says so."""
+    step = regions.get("step_ms", 0.0) or (regions.get("fwd_ms", 0.0) + regions.get("bwd_ms", 0.0) +
+                                            regions.get("optimizer_ms", 0.0) + regions.get("exposed_comm_ms", 0.0))
+    fwd = regions.get("fwd_ms", 0.0)
+    if step > 0 and fwd > 0:
+        f = min(max(fwd / step, 0.0), 1.0)
+        return dev_s * f, dev_s * (1.0 - f), "device-timed regions"
+    return dev_s, 0.0, "unmeasured (region probe off)"
+
+
+def probe_step_regions(dev, state: List[torch.Tensor], reducers, graphed: "GraphedStep", fwd: Callable, comm: Callable,
+                       opt: Callable, restore: Callable, images, labels, iters: int = 10) -> Dict[str, float]:
+    """{fwd_ms, bwd_ms, allreduce_ms, optimizer_ms, exposed_comm_ms, step_ms} of one training step.
+
+    The reference brackets regions with ``time.time()`` (data_parallel_train.py:103-124, with the Q8 caveat that its
+    "comm_time" is backward+optimizer); here forward and backward (incl. the side-stream wgrads and every collective
+    fused into them) are replayed as two separate CUDA graphs and the gradient all-reduces (``comm``) / the optimizer
+    pass (``opt``) are launched back to back, every region bracketed by CUDA events and averaged over ``iters``;
+    ``exposed_comm_ms`` is what the real (single-graph, overlapped) step costs beyond forward+backward+optimizer.
+    ``state`` is snapshotted before and restored after, so the probe does not perturb the run.  Every rank of the
+    job must call it together (the regions contain collectives)."""
+    dev = torch.device(dev)
+    cuda = dev.type == "cuda"
+    snap = [t.clone() for t in state]
+    reducers = [r for r in reducers if r is not None]
+    for r in reducers:
+        r.enabled = False
+
+    def clock():
+        if cuda:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        return time.perf_counter()
+
+    def span(a, b) -> float:
+        return a.elapsed_time(b) if cuda else (b - a) * 1e3
+
+    out = {k: 0.0 for k in ("fwd_ms", "bwd_ms", "allreduce_ms", "optimizer_ms", "exposed_comm_ms", "step_ms")}
+    mb = None
+    is_graphed = cuda and graphed is not None and graphed.graph is not None and tuple(images.shape) == graphed.shape
+    try:
+        if is_graphed:
+            from ..parallel.pp import GraphedMicroBatch
+            mb = GraphedMicroBatch(fwd, None, None, dev, True, True, label_shape=tuple(labels.shape), image_like=images)
+            torch.cuda.synchronize()
+            mb.capture()
+            ops.step_end()
+            run_f = lambda: mb.run_fwd(images, labels)      # noqa: E731
+            run_b = lambda: mb.run_bwd(None)                # noqa: E731
+        else:
+            holder = {}
+
+            def run_f():
+                holder["loss"] = fwd(images, labels)[0]
+
+            def run_b():
+                ops.backward(holder.pop("loss"))
+                ops.join_side()
+                ops.step_end()
+        marks = []
+        for it in range(iters + 2):
+            row = [clock()]
+            run_f(); row.append(clock())
+            run_b(); row.append(clock())
+            comm(); row.append(clock())
+            opt(); row.append(clock())
+            if it >= 2:
+                marks.append(row)
+        step_marks = None
+        if is_graphed:
+            step_marks = [clock()]
+            for _ in range(iters):
+                graphed.graph.replay()
+            step_marks.append(clock())
+        if cuda:
+            torch.cuda.synchronize()
+        n = float(len(marks))
+        for i, k in enumerate(("fwd_ms", "bwd_ms", "allreduce_ms", "optimizer_ms")):
+            out[k] = sum(span(r[i], r[i + 1]) for r in marks) / n
+        if step_marks is not None:
+            out["step_ms"] = span(step_marks[0], step_marks[1]) / iters
+            out["exposed_comm_ms"] = max(0.0, out["step_ms"] - out["fwd_ms"] - out["bwd_ms"] - out["optimizer_ms"])
+        else:
+            out["step_ms"] = sum(span(r[0], r[4]) for r in marks) / n
+            out["exposed_comm_ms"] = out["allreduce_ms"]        # nothing overlaps on the eager / CPU path
+    finally:
+        if cuda:
+            torch.cuda.synchronize()
+        mb = None
+        for t, s_ in zip(state, snap):
+            t.copy_(s_)
+        restore()
+        for r in reducers:
+            r.enabled = True
+            r.begin_step()
+    return out
+
+
 def profile_steps(step_fn, x, y, path: str, steps: int = 5) -> None:
     """``--profile``: CUPTI kernel timeline of a few steps (chrome trace + per-kernel summary JSON)."""
     import json

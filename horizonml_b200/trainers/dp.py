@@ -29,7 +29,8 @@ from ..models.resnet import resnet18
 from ..parallel.comm import make_grad_allreduce
 from ..parallel.dp import GradReducer
 from .common import (DeviceStats, FaultInjector, GraphedStep, Heartbeat, Runtime, allreduce_max_scalar,
-                     enable_nvtx, gpu_mem_mb, nvtx_range, profile_steps, setup_runtime)
+                     enable_nvtx, gpu_mem_mb, nvtx_range, probe_step_regions, profile_steps, setup_runtime,
+                     split_compute_comm)
 
 
 def build_model(cfg: TrainConfig, device, class_pad_to: int = 1):
@@ -52,9 +53,17 @@ class DPEngine:
         live = self.model.live_tap_masks(32) if (cfg.skip_dead_taps and hasattr(self.model, "live_tap_masks")) else None
         by_live = live is not None and (bool(cfg.bucket_by_live) or os.environ.get("HZ_BUCKET_LIVE", "0") == "1")
         self.zero1 = bool(cfg.zero1) and rt.world > 1
+        # Adam inside the all-reduce kernel (csrc/comm.cu AdamFuse): peer kernels only, replicated optimizer state
+        self.fused_adam = (bool(cfg.fused_adam) and rt.world > 1 and not self.zero1 and dev.type == "cuda"
+                           and cfg.allreduce != "nccl" and rt.backend == "native" and not cfg.overlap_adam
+                           and os.environ.get("HZ_OVERLAP_ADAM", "0") != "1")
+        layout = cfg.bucket_layout
+        if layout == "auto":
+            layout = "layers" if (self.fused_adam and cfg.model == "resnet18") else "size"
+        starts = ("layer3.", "layer2.", "layer1.") if layout == "layers" else None
         self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype,
                                cfg.live_bucket_mb if by_live else cfg.bucket_mb, live_masks=live, bucket_by_live=by_live,
-                               pad_multiple=64 * rt.world if self.zero1 else 64)
+                               pad_multiple=64 * rt.world if self.zero1 else 64, bucket_starts=starts)
         if rt.world > 1:   # K1: make replicas identical (same seed already does; belt and braces)
             dist.broadcast(self.flat.master, src=0)
             for b in self.model.buffers():
@@ -77,12 +86,27 @@ class DPEngine:
         # soon as its gradients are final) and overlaps the rest of backward
         self.bucket_adam = (bool(cfg.overlap_adam) or os.environ.get("HZ_OVERLAP_ADAM", "0") == "1") and not self.zero1
         self._diff_acc = torch.zeros((), dtype=torch.float32, device=dev) if self.prev_grad is not None else None
+        self.fused_adam = self.fused_adam and hasattr(self.ar, "allreduce_adam_")
+        if self.fused_adam and self._diff_acc is None and self.prev_grad is not None:
+            self._diff_acc = torch.zeros((), dtype=torch.float32, device=dev)
         self.reducer = None
         if self.ar is not None or self.bucket_adam:
             self.reducer = GradReducer(self.flat, self.ar, cfg.overlap,
-                                       post_bucket=self._adam_bucket if self.bucket_adam else None)
+                                       post_bucket=self._adam_bucket if self.bucket_adam else None,
+                                       fused_bucket=self._fused_bucket if self.fused_adam else None)
         self._graphed = GraphedStep(self._step_impl, dev, cfg.cuda_graph)
         self.global_step = 0
+
+    def _fused_bucket(self, b: int, last: bool):
+        """One kernel: average bucket ``b``'s gradients over the ranks and apply Adam to its parameters."""
+        f, o = self.flat, self.opt
+        bk = f.buckets[b]
+        sl = slice(bk.start, bk.end)
+        return self.ar.allreduce_adam_(f.grad[sl], f.master[sl], o.m[sl], o.v[sl],
+                                       f.shadow[sl] if f.shadow is not None else None,
+                                       self.prev_grad[sl] if self.prev_grad is not None else None,
+                                       self._diff_acc if self.prev_grad is not None else None, o.step_t, o.lr,
+                                       o.betas[0], o.betas[1], o.eps, bump=last, live=f.bucket_live[b])
 
     def _adam_bucket(self, b: int, first: bool) -> None:
         self.opt.step_bucket(b, first, diff_out=self._diff_acc, prev_grad=self.prev_grad)
@@ -106,7 +130,7 @@ class DPEngine:
             if self.reducer is not None:
                 self.reducer.finish()
         with nvtx_range("optimizer"):
-            if self.bucket_adam:
+            if self.bucket_adam or self.fused_adam:
                 diff = self._diff_acc          # every bucket's Adam has been joined by reducer.finish()
             else:
                 diff = self.opt.step(prev_grad=self.prev_grad)
@@ -134,19 +158,8 @@ class DPEngine:
 
     def probe_regions(self, images, labels, iters: int = 10) -> Dict[str, float]:
         """{fwd_ms, bwd_ms, allreduce_ms, optimizer_ms, exposed_comm_ms, step_ms}: where one training step spends its
-        time.  The reference brackets regions with ``time.time()`` (data_parallel_train.py:103-124, with the Q8
-        caveat that its "comm_time" is backward+optimizer); here forward and backward (incl. the side-stream wgrads)
-        are replayed as two separate CUDA graphs and the bucket all-reduces / fused Adam are launched back to back,
-        every region bracketed by CUDA events and averaged over ``iters``; ``exposed_comm_ms`` is what the real
-        (single-graph, overlapped) step costs beyond forward+backward+optimizer.  Training state is snapshotted
-        before and restored after, so the probe does not perturb the run.  All ranks must call it together."""
+        time (trainers/common.py ``probe_step_regions``).  All ranks must call it together."""
         dev = self.rt.device
-        cuda = dev.type == "cuda"
-        state = self._state_tensors()
-        snap = [t.clone() for t in state]
-        red = self.reducer
-        if red is not None:
-            red.enabled = False
 
         def fwd(x, y):
             ops.step_begin(dev)
@@ -161,76 +174,11 @@ class DPEngine:
             for bk in self.flat.buckets:
                 self.ar.allreduce_avg_(self.flat.grad[bk.start:bk.end], live=self.flat.bucket_live[bk.index])
 
-        def clock():
-            if cuda:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                return e
-            return time.perf_counter()
-
-        def span(a, b) -> float:
-            return a.elapsed_time(b) if cuda else (b - a) * 1e3
-
-        out = {k: 0.0 for k in ("fwd_ms", "bwd_ms", "allreduce_ms", "optimizer_ms", "exposed_comm_ms", "step_ms")}
-        mb = None
-        graphed = cuda and self._graphed.graph is not None and tuple(images.shape) == self._graphed.shape
-        try:
-            if graphed:
-                from ..parallel.pp import GraphedMicroBatch
-                mb = GraphedMicroBatch(fwd, None, None, dev, True, True, label_shape=tuple(labels.shape),
-                                       image_like=images)
-                torch.cuda.synchronize()
-                mb.capture()
-                ops.step_end()
-                run_f = lambda: mb.run_fwd(images, labels)      # noqa: E731
-                run_b = lambda: mb.run_bwd(None)                # noqa: E731
-            else:
-                holder = {}
-
-                def run_f():
-                    holder["loss"] = fwd(images, labels)[0]
-
-                def run_b():
-                    holder.pop("loss").backward()
-                    ops.join_side()
-                    ops.step_end()
-            marks = []
-            for it in range(iters + 2):
-                row = [clock()]
-                run_f(); row.append(clock())
-                run_b(); row.append(clock())
-                comm(); row.append(clock())
-                self.opt.step(prev_grad=self.prev_grad); row.append(clock())
-                if it >= 2:
-                    marks.append(row)
-            step_marks = None
-            if graphed:
-                step_marks = [clock()]
-                for _ in range(iters):
-                    self._graphed.graph.replay()
-                step_marks.append(clock())
-            if cuda:
-                torch.cuda.synchronize()
-            n = float(len(marks))
-            for i, k in enumerate(("fwd_ms", "bwd_ms", "allreduce_ms", "optimizer_ms")):
-                out[k] = sum(span(r[i], r[i + 1]) for r in marks) / n
-            if step_marks is not None:
-                out["step_ms"] = span(step_marks[0], step_marks[1]) / iters
-                out["exposed_comm_ms"] = max(0.0, out["step_ms"] - out["fwd_ms"] - out["bwd_ms"] - out["optimizer_ms"])
-            else:
-                out["step_ms"] = sum(span(r[0], r[4]) for r in marks) / n
-                out["exposed_comm_ms"] = out["allreduce_ms"]        # nothing overlaps on the eager / CPU path
-        finally:
-            if cuda:
-                torch.cuda.synchronize()
-            mb = None
-            for t, s in zip(state, snap):
-                t.copy_(s)
+        def restore():
             self.flat.begin_step()
-            if red is not None:
-                red.enabled = True
-                red.begin_step()
-        return out
+
+        return probe_step_regions(dev, self._state_tensors(), [self.reducer], self._graphed, fwd, comm,
+                                  lambda: self.opt.step(prev_grad=self.prev_grad), restore, images, labels, iters)
 
     def input_buffers(self):
         """Static (images, labels) buffers of the captured step, or None (eager mode / before capture)."""
@@ -320,6 +268,8 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         else:
             dev_s = time.time() - t_epoch
         s = eng.stats.read_and_reset()
+        if hasattr(eng.ar, "check_error"):
+            eng.ar.check_error()              # a rank that never arrived at a peer barrier is an error, not a hang
         if dev_idle is not None:
             rec.total_idle += float(dev_idle.item()) * 1e-9
             dev_idle.zero_()
@@ -329,9 +279,6 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         acc = 100.0 * s["correct"] / max(s["seen"], 1)
         if s["grad_div_n"] > 0:
             rec.grad_divs = [s["grad_div_sum"] / s["grad_div_n"]]
-        # reference split (Q8): compute = forward share, comm = backward+optimizer share of device time
-        rec.total_compute += dev_s * (1.0 / 3.0)
-        rec.total_comm += dev_s * (2.0 / 3.0)
         dev_s_max = allreduce_max_scalar(dev_s, rt.device)
         seen_all = s["seen"] * world
         ar_bytes = eng.allreduce_bytes_per_step()
@@ -351,6 +298,12 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
                         print(f"[probe] region breakdown unavailable: {e!r}", flush=True)
                     regions = {}
         ext.update({k: v for k, v in regions.items() if k != "step_ms"})
+        # reference columns (Q8: "compute_time" = forward, "comm_time" = backward + all-reduce + optimizer), filled from
+        # the device-timed regions — not a fixed ratio
+        comp_s, comm_s, src = split_compute_comm(dev_s, regions)
+        rec.total_compute += comp_s
+        rec.total_comm += comm_s
+        ext["split_source"] = src
         rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times, ext=ext)
         if rank == 0 and not cfg.quiet:
             print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "
@@ -370,6 +323,9 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         write_summary(logs_dir, f"summary_{cfg.sample_size}.json", {
             "strategy": "data", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
             "comm": rt.comm_backend, "allreduce": getattr(eng.ar, "name", None),
+            "allreduce_detail": eng.ar.describe() if hasattr(eng.ar, "describe") else None,
+            "fused_adam": eng.fused_adam, "bucket_algos": eng.reducer.algos if eng.reducer is not None else None,
+            "buckets": [[b.names[0], b.names[-1], b.end - b.start] for b in eng.flat.buckets],
             "graph": eng._graphed.graph is not None, "graph_error": eng._graphed.capture_error,
             "final": rec.rows[-1] if rec.rows else None})
     eng._graphed.graph = None

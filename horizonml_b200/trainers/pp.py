@@ -263,8 +263,15 @@ def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
                 rec.grad_divs = [s["grad_div_sum"] / s["grad_div_n"]]
         else:
             loss, acc = 0, 0
-        rec.total_compute += dev_s * 0.5
-        rec.total_comm += dev_s * 0.5
+        # reference columns: its layer script's "comm_time" is the time blocked in send/recv incl. waiting for the
+        # neighbour (layer_model_parallel_train.py:188-209) — here: the measured time this stage's compute stream was
+        # held up behind activation / gradient arrivals (exposed p2p + pipeline bubble); the rest is compute
+        p2p_total_ms = 0.0
+        if cfg.region_probe:
+            p2p_total_ms = eng.runner.p2p.take_time_ms() + (eng.overlapped.stall_ms() if eng.overlapped is not None else 0.0)
+        comm_s = min(p2p_total_ms / 1e3, dev_s)
+        rec.total_compute += dev_s - comm_s
+        rec.total_comm += comm_s
         dev_s_max = allreduce_max_scalar(dev_s, rt.device)
         n_img = nsteps * cfg.batch_size if nsteps else 0
         n_img = min(n_img, len(labels)) if not cfg.max_steps else n_img
@@ -278,9 +285,9 @@ def train_model_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         if cfg.region_probe:
             # time per step this stage's compute stream is blocked behind activation / gradient exchanges (includes
             # the pipeline bubble, like the reference's blocking send/recv "comm_time", layer_…:188-195,209)
-            p2p_total = eng.runner.p2p.take_time_ms() + (eng.overlapped.stall_ms() if eng.overlapped is not None else 0.0)
-            ext["p2p_ms"] = p2p_total / steps
+            ext["p2p_ms"] = p2p_total_ms / steps
             ext["exposed_comm_ms"] = ext["p2p_ms"]
+            ext["split_source"] = "device-timed stalls behind p2p arrivals"
         rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times,
                       avg_bandwidth=sent_total / steps, ext=ext)
         if eng.is_last and saver and not cfg.quiet:

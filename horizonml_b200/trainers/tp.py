@@ -24,7 +24,7 @@ from ..parallel.comm import make_grad_allreduce
 from ..parallel.dp import GradReducer
 from ..parallel.tp import TensorParallelResNet, TPComm
 from .common import (DeviceStats, FaultInjector, GraphedStep, Heartbeat, Runtime, allreduce_max_scalar,
-                     gpu_mem_mb, setup_runtime)
+                     gpu_mem_mb, probe_step_regions, setup_runtime, split_compute_comm)
 
 
 class TPEngine:
@@ -90,9 +90,56 @@ class TPEngine:
         self._graphed(images, labels)
         self.global_step += 1
 
+    def probe_regions(self, images, labels, iters: int = 10):
+        """Device-timed step regions (trainers/common.py ``probe_step_regions``).  Forward and backward contain the fused
+        GEMM+all-reduce / head kernels — the tensor-parallel traffic is *inside* those regions by construction —
+        ``allreduce_ms`` is the replicated-parameter gradient averaging, ``exposed_comm_ms`` what the overlapped step
+        costs beyond forward + backward + optimizer.  All ranks call it together."""
+        dev = self.rt.device
+        state = [self.flat_rep.master, self.flat_rep.grad, self.flat_shd.master, self.flat_shd.grad, self.opt_rep.m,
+                 self.opt_rep.v, self.opt_rep.step_t, self.opt_shd.m, self.opt_shd.v, self.opt_shd.step_t, self.stats.buf,
+                 self.stats.has_prev]
+        for fl in (self.flat_rep, self.flat_shd):
+            if fl.shadow is not None:
+                state.append(fl.shadow)
+        if self.prev_grad is not None:
+            state.append(self.prev_grad)
+        state += [b for b in self.model.buffers()]
+
+        def fwd(x, y):
+            if x.dtype == torch.uint8:
+                x = ops.stem_prepare(x.permute(0, 3, 1, 2), dtype=self.rt.dtype)
+            ops.step_begin(dev)
+            self.flat_rep.begin_step(); self.flat_shd.begin_step()
+            return self.model.forward_loss(x, y)
+
+        def comm():
+            if self.ar is not None:
+                for bk in self.flat_rep.buckets:
+                    self.ar.allreduce_avg_(self.flat_rep.grad[bk.start:bk.end])
+            if self.ar_shd is not None:
+                for bk in self.flat_shd.buckets:
+                    self.ar_shd.allreduce_avg_(self.flat_shd.grad[bk.start:bk.end])
+
+        def opt():
+            self.opt_rep.step(prev_grad=self.prev_grad)
+            self.opt_shd.step()
+
+        def restore():
+            self.flat_rep.begin_step(); self.flat_shd.begin_step()
+
+        return probe_step_regions(dev, state, [self.reducer], self._graphed, fwd, comm, opt, restore, images, labels, iters)
+
     def bytes_per_step(self) -> int:
         rep = sum(self.ar.wire_bytes(b.end - b.start) for b in self.flat_rep.buckets) if self.ar else 0
         return rep
+
+
+def _native_fallbacks(rt) -> dict:
+    if rt.backend != "native":
+        return {}
+    from ..ops import native_backend as nb
+    return dict(nb.FALLBACKS)
 
 
 def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
@@ -131,6 +178,7 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
     if not cfg.quiet:
         print(f"Worker {rank} is starting training...", flush=True)
     cuda = rt.device.type == "cuda"
+    probe_xy, regions = None, {}
     for epoch in range(start_epoch, cfg.epochs):
         t_epoch = time.time()
         t0 = time.time()
@@ -146,6 +194,8 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         for bi, (x, y) in enumerate(loader):
             if cfg.max_steps and bi >= cfg.max_steps:
                 break
+            if probe_xy is None or (x.shape[0] == cfg.batch_size and probe_xy[0].shape[0] != cfg.batch_size):
+                probe_xy = (x.clone(), y.clone())
             ts = time.time()
             rec.host.sample()
             fault.maybe_fail(eng.global_step)
@@ -174,14 +224,26 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
         acc = 100.0 * s["correct"] / max(s["seen"], 1)
         if s["grad_div_n"] > 0:
             rec.grad_divs = [s["grad_div_sum"] / s["grad_div_n"]]
-        rec.total_compute += dev_s / 3.0
-        rec.total_comm += dev_s * 2.0 / 3.0
         dev_s_max = allreduce_max_scalar(dev_s, rt.device)
+        if epoch == start_epoch and cfg.region_probe:
+            have = allreduce_max_scalar(0.0 if probe_xy is not None else 1.0, rt.device) == 0.0
+            if have:
+                try:
+                    regions = eng.probe_regions(*probe_xy)
+                except Exception as e:  # noqa: BLE001 — a diagnostics feature must never take the run down
+                    if rank == 0:
+                        print(f"[probe] region breakdown unavailable: {e!r}", flush=True)
+                    regions = {}
+        comp_s, comm_s, src = split_compute_comm(dev_s, regions)
+        rec.total_compute += comp_s
+        rec.total_comm += comm_s
         bytes_per_step = eng.bytes_per_step() + (tp_bytes / steps if eng._graphed.graph is None else 0)
         seen = s["seen"] * (mesh.dp if mesh is not None else 1)
         ext = {"images_per_sec": seen / dev_s_max if dev_s_max > 0 else 0, "steps": nsteps,
                "gpu_mem_MB": gpu_mem_mb(rt.device),
                "nvlink_GBps": bytes_per_step * nsteps / dev_s_max / 1e9 if dev_s_max > 0 else 0}
+        ext.update({k: v for k, v in regions.items() if k != "step_ms"})
+        ext["split_source"] = src
         if cuda:
             step_times = [dev_s / max(nsteps, 1)] * nsteps
         rec.end_epoch(epoch + 1, loss, acc, epoch_time, step_times, avg_bandwidth=bytes_per_step, ext=ext)
@@ -196,7 +258,14 @@ def train_tensor_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
     if rank == 0:
         write_summary(logs_dir, f"summary_{cfg.sample_size}.json", {
             "strategy": "tensor", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
-            "conv_split": eng.model.conv_split, "mesh": mesh.describe() if mesh is not None else None, "final": rec.rows[-1] if rec.rows else None})
+            "conv_split": eng.model.conv_split, "mesh": mesh.describe() if mesh is not None else None,
+            "fused_tp": eng.fused.describe() if eng.fused is not None else None,
+            "fused_tp_ops": eng.fused.ops if eng.fused is not None else None,
+            "library_collectives_in_step": eng.comm.library_collectives,
+            "native_fallbacks": _native_fallbacks(rt),
+            "replicated_grad_allreduce": getattr(eng.ar, "name", None),
+            "graph": eng._graphed.graph is not None, "graph_error": eng._graphed.capture_error,
+            "final": rec.rows[-1] if rec.rows else None})
     # a captured graph that contains NCCL kernels must be gone before the communicator is torn down
     eng._graphed.graph = None
     if cuda:

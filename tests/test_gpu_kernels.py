@@ -400,3 +400,62 @@ def test_cuda_graph_step(nb):
     assert eng._graphed.graph is not None, eng._graphed.capture_error
     assert s["steps"] == 8 and s["loss_sum"] == s["loss_sum"]
     assert s["loss_sum"] / 8 < 2.6        # memorising one batch: loss must drop below ln(10)+
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
+def test_allreduce_adam_fused_virtual_ranks(nb, world, algo):
+    """All-reduce with the Adam update fused into its final phase == all-reduce kernel followed by the Adam kernel
+    (same fp32 values feed the same arithmetic), over dead-block-compacted buckets, 3 optimizer steps,
+    step counter bumped by the last bucket only, divergence term accumulated across buckets."""
+    C = nb.C
+    n = 1 << 16
+    g = torch.Generator().manual_seed(13)
+    blocks = n // 64
+    live = torch.nonzero(torch.rand(blocks, generator=g) > 0.4).flatten().to(torch.int32).to(DEV)
+    halves = [(0, n // 2, None), (n // 2, n, None)]                     # two "buckets": second one is the last of the step
+    lv = live.cpu()
+    halves = [(lo, hi, (lv[(lv >= lo // 64) & (lv < hi // 64)] - lo // 64).to(torch.int32).to(DEV)) for lo, hi, _ in halves]
+
+    def fresh():
+        return {"p": [torch.randn(n, generator=torch.Generator().manual_seed(1)).to(DEV) for _ in range(world)],
+                "m": [torch.zeros(n, device=DEV) for _ in range(world)], "v": [torch.zeros(n, device=DEV) for _ in range(world)],
+                "sh": [torch.zeros(n, device=DEV, dtype=torch.bfloat16) for _ in range(world)],
+                "prev": [torch.zeros(n, device=DEV) for _ in range(world)], "diff": [torch.zeros((), device=DEV) for _ in range(world)],
+                "step": [torch.zeros(1, device=DEV) for _ in range(world)]}
+    A, B = fresh(), fresh()
+    comA = [C.PeerComm(r, world, 0, n * 2, 16) for r in range(world)]
+    comB = [C.PeerComm(r, world, 0, n * 2, 16) for r in range(world)]
+    C.PeerComm.link_local(comA); C.PeerComm.link_local(comB)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for it in range(3):
+        grads = [torch.randn(n, generator=g).to(DEV) for _ in range(world)]
+        gA, gB = [x.clone() for x in grads], [x.clone() for x in grads]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                for bi, (lo, hi, lb) in enumerate(halves):
+                    comA[r].allreduce_adam(gA[r][lo:hi], algo, True, 1.0 / world, lb, A["p"][r][lo:hi], A["m"][r][lo:hi],
+                                           A["v"][r][lo:hi], A["sh"][r][lo:hi], A["prev"][r][lo:hi], A["diff"][r], A["step"][r],
+                                           1e-3, 0.9, 0.999, 1e-8, bi == 1)
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                for bi, (lo, hi, lb) in enumerate(halves):
+                    comB[r].allreduce(gB[r][lo:hi], algo, True, 1.0 / world, lb)
+        torch.cuda.synchronize()
+        for r in range(world):
+            for bi, (lo, hi, lb) in enumerate(halves):
+                C.adam_step(B["p"][r][lo:hi], gB[r][lo:hi], B["m"][r][lo:hi], B["v"][r][lo:hi], B["sh"][r][lo:hi], B["step"][r],
+                            1e-3, 0.9, 0.999, 1e-8, 1.0, B["prev"][r][lo:hi], B["diff"][r], True, lb, bi == 0, 0)
+        torch.cuda.synchronize()
+        assert not any(c.error() for c in comA + comB)
+        for r in range(world):
+            assert A["step"][r].item() == it + 1 == B["step"][r].item()
+            for k in ("p", "m", "v", "sh", "prev"):
+                # same fp32 inputs, same formulas; only FMA contraction may differ between the two kernels
+                assert torch.allclose(A[k][r].float(), B[k][r].float(), rtol=1e-5, atol=1e-6 if k != "sh" else 1e-2), (k, r, it)
+                assert torch.equal(A[k][r], A[k][0]), "replicas diverged"
+            assert torch.equal(gA[r], gB[r])                                   # live blocks cleared, dead ones untouched
+            assert abs(A["diff"][r].item() - B["diff"][r].item()) <= 1e-4 * abs(B["diff"][r].item()) + 1e-6
+            A["diff"][r].zero_()          # (the stats kernel consumes and clears the accumulator once per step)
