@@ -41,7 +41,8 @@ def parse():
     p.add_argument("--no_grad_divergence", action="store_true")
     p.add_argument("--bucket_mb", type=float, default=25.0)
     p.add_argument("--live_bucket_mb", type=float, default=2.0)
-    p.add_argument("--no_fused_adam", action="store_true")
+    p.add_argument("--fused_adam", action="store_true")
+    p.add_argument("--overlap_adam", action="store_true")
     p.add_argument("--bucket_layout", default="auto", choices=["auto", "layers", "size"])
     return p.parse_args()
 
@@ -69,8 +70,8 @@ def run_ours(args):
     cfg = TrainConfig(strategy="data", world_size=world, batch_size=args.batch, device="cuda", dtype="bf16",
                       backend=backend, allreduce=args.allreduce, cuda_graph=not args.no_graph,
                       grad_divergence=not args.no_grad_divergence, quiet=True, bucket_mb=args.bucket_mb,
-                      live_bucket_mb=args.live_bucket_mb, fused_adam=not args.no_fused_adam,
-                      bucket_layout=args.bucket_layout)
+                      live_bucket_mb=args.live_bucket_mb, fused_adam=args.fused_adam,
+                      bucket_layout=args.bucket_layout, overlap_adam=args.overlap_adam)
     rt = setup_runtime(rank, world, cfg, "cuda")
     dev = rt.device
     eng = DPEngine(cfg, rt)

@@ -355,6 +355,7 @@ class PeerComm {
     for (auto* c : comms) raw.push_back(c->c_);
     hz_comm_link_local(raw.data(), (int)raw.size());
   }
+  int64_t symm_bytes() { return (int64_t)hz_comm_symm_bytes(c_); }
   void set_multicast(int64_t mc_ptr, int64_t local_ptr, int64_t bytes) {
     hz_comm_set_multicast(c_, (void*)mc_ptr, (void*)local_ptr, (size_t)bytes);
   }
@@ -363,7 +364,7 @@ class PeerComm {
     TORCH_CHECK(grad.is_cuda() && grad.scalar_type() == at::kFloat && grad.is_contiguous());
     const bool has_live = live_blocks.has_value() && live_blocks->defined();
     if (has_live) TORCH_CHECK(live_blocks->scalar_type() == at::kInt && live_blocks->is_cuda());
-    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : -1;
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : algo == "ll" ? 3 : -1;
     TORCH_CHECK(a >= 0, "unknown all-reduce algorithm ", algo);
     c10::cuda::CUDAGuard g(grad.device());
     const size_t n = has_live ? (size_t)live_blocks->numel() * 64 : (size_t)grad.numel();
@@ -380,7 +381,7 @@ class PeerComm {
     TORCH_CHECK(master.numel() == grad.numel() && m.numel() == grad.numel() && v.numel() == grad.numel());
     const bool has_live = live_blocks.has_value() && live_blocks->defined();
     if (has_live) TORCH_CHECK(live_blocks->scalar_type() == at::kInt && live_blocks->is_cuda());
-    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : -1;
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : algo == "ll" ? 3 : -1;
     TORCH_CHECK(a >= 0, "unknown all-reduce algorithm ", algo);
     c10::cuda::CUDAGuard g(grad.device());
     const size_t n = has_live ? (size_t)live_blocks->numel() * 64 : (size_t)grad.numel();
@@ -394,9 +395,10 @@ class PeerComm {
     TORCH_CHECK(rc == 0, "hz_comm_allreduce_adam failed rc=", rc);
   }
   int64_t blocks_for(int64_t n, const std::string& algo, bool wire_bf16) {
-    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : 2;
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "ll" ? 3 : 2;
     return hz_comm_blocks_for(c_, (size_t)n, a, wire_bf16 ? 1 : 0);
   }
+  void set_block_cap(int64_t cap) { hz_comm_set_block_cap(c_, (int)cap); }
   void barrier(c10::optional<Tensor> stamps) {
     long long* s = nullptr;
     if (stamps.has_value() && stamps->defined()) s = (long long*)stamps->data_ptr<int64_t>();
@@ -412,7 +414,7 @@ class PeerComm {
 
 // ------------------------------------------------------------------ fused tensor-parallel ops (csrc/tp_fused.cu)
 // `heaps`: base address of every rank's symmetric heap as mapped in this process; `mc`: multicast mapping or 0.
-// All *_off arguments are byte offsets into the heap.  ctrl_off: u32 [epoch, done] of this op.
+// All *_off arguments are byte offsets into the heap.  ctrl_off: u32 call counters of this op (one per CTA).
 struct HeapPtrs { char* h[8]; };
 HeapPtrs heap_ptrs(const std::vector<int64_t>& heaps) {
   TORCH_CHECK(heaps.size() >= 1 && heaps.size() <= 8, "1..8 tensor-parallel ranks");
@@ -463,7 +465,7 @@ Tensor tp_conv(int64_t kind, c10::optional<Tensor> a, int64_t a_off, const Tenso
   }
   unsigned* ctrl = reinterpret_cast<unsigned*>(hp.h[rank] + ctrl_off);
   int rc = hz_tp_conv((int)kind, xp, w.data_ptr(), out.data_ptr(), add, st, hp.h, (char*)(uintptr_t)mc, part_off,
-                      part_stride, cnt_off, ready_off, ctrl, ctrl + 1, world, (int)rank, (int)mode, nvls ? 1 : 0,
+                      part_stride, cnt_off, ready_off, ctrl, world, (int)rank, (int)mode, nvls ? 1 : 0,
                       ll ? 1 : 0, ag ? 1 : 0, N, H, Wd, Cin, Cout, R, (int)stride, (int)pad, cur_stream());
   TORCH_CHECK(rc == 0, "hz_tp_conv failed rc=", rc);
   return out;
@@ -493,7 +495,7 @@ std::vector<Tensor> tp_head(const Tensor& feat, const Tensor& Wl, const c10::opt
   int rc = hz_tp_head(cptr(feat), Wl.data_ptr<float>(), fptr(bl), labels.data_ptr<int64_t>(), pooled.data_ptr<float>(),
                       dl.data_ptr<float>(), logits.data_ptr<float>(), need_dfeat ? dfeat.data_ptr() : nullptr,
                       loss.data_ptr<float>(), correct.data_ptr<float>(), hp.h, (char*)(uintptr_t)mc, logits_off, dfeat_off,
-                      ctrl, ctrl + 1, world, (int)rank, nvls ? 1 : 0, d.N, d.C, d.H * d.W, kl, (int)n_valid,
+                      ctrl, world, (int)rank, nvls ? 1 : 0, d.N, d.C, d.H * d.W, kl, (int)n_valid,
                       (float)loss_scale, cur_stream());
   TORCH_CHECK(rc == 0, "hz_tp_head failed rc=", rc);
   hz_head_wgrad(pooled.data_ptr<float>(), dl.data_ptr<float>(), dW.data_ptr<float>(), fptr(db), d.N, d.C, kl,
@@ -514,7 +516,7 @@ Tensor tp_allreduce_bf16(const Tensor& in, std::vector<int64_t> heaps, int64_t m
   Tensor out = at::empty_like(in);
   unsigned* ctrl = reinterpret_cast<unsigned*>(hp.h[rank] + ctrl_off);
   int rc = hz_tp_allreduce_bf16(in.data_ptr(), out.data_ptr(), (size_t)in.numel(), hp.h, (char*)(uintptr_t)mc, buf_off,
-                                cnt_off, ctrl, ctrl + 1, (int)heaps.size(), (int)rank, nvls ? 1 : 0, ll ? 1 : 0,
+                                cnt_off, ctrl, (int)heaps.size(), (int)rank, nvls ? 1 : 0, ll ? 1 : 0,
                                 (int)blocks, cur_stream());
   TORCH_CHECK(rc == 0, "hz_tp_allreduce_bf16 failed rc=", rc);
   return out;
@@ -588,10 +590,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("import_handles", &PeerComm::import_handles)
       .def_static("link_local", &PeerComm::link_local)
       .def("set_multicast", &PeerComm::set_multicast)
+      .def("symm_bytes", &PeerComm::symm_bytes)
       .def("allreduce", &PeerComm::allreduce, py::arg("grad"), py::arg("algo"), py::arg("wire_bf16"),
            py::arg("scale"), py::arg("live_blocks") = py::none())
       .def("allreduce_adam", &PeerComm::allreduce_adam)
       .def("blocks_for", &PeerComm::blocks_for)
+      .def("set_block_cap", &PeerComm::set_block_cap)
       .def("barrier", &PeerComm::barrier)
       .def("error", &PeerComm::error);
 }

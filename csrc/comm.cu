@@ -24,6 +24,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 #include <vector>
 
@@ -173,7 +174,20 @@ HZ_DEVINL void store_grad(float* g, size_t off, const float* f) {
     reinterpret_cast<float4*>(g + off)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
 }
 
-enum Algo { kOneShot = 0, kTwoShot = 1, kNvls = 2 };
+enum Algo { kOneShot = 0, kTwoShot = 1, kNvls = 2, kLL = 3 };
+constexpr size_t kLLMaxElems = 512 * 1024;            // largest bucket the latency protocol takes (bf16 wire)
+constexpr size_t kLLSlotBytes = kLLMaxElems * 4;      // one rank's slot: 4 wire bytes per element ({2 bf16, flag} words)
+
+// "LL" words: 16 bytes = {data, flag, data, flag}; 8-byte halves are single-copy atomic, so a receiver that sees the
+// flag sees the data next to it: no fence, no separate flag, no barrier (NCCL's small-message protocol).
+HZ_DEVINL void ll_store(void* dst, const uint4& v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+HZ_DEVINL uint4 ll_load(const void* src) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src) : "memory");
+  return v;
+}
 
 // sub-range b of slice r of nv vectors split over W ranks and B blocks
 HZ_DEVINL void sub_range(size_t nv, int W, int B, int r, int b, size_t& lo, size_t& hi) {
@@ -184,7 +198,7 @@ HZ_DEVINL void sub_range(size_t nv, int W, int B, int r, int b, size_t& lo, size
   hi = min(lo + qq, shi);
 }
 
-constexpr int kUnroll = 4;     // independent 16-byte requests in flight per thread and phase
+constexpr int kUnroll = 8;     // independent 16-byte requests in flight per thread and phase
 
 // pack [lo,hi): grad(fp32)*scale -> wire vectors in the local staging buffer
 template <bool kBf16>
@@ -343,6 +357,52 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
     ak.step_size = ad.lr / bc1; ak.inv_sqrt_bc2 = rsqrtf(bc2); ak.b1 = ad.b1; ak.b2 = ad.b2; ak.eps = ad.eps;
   }
 
+  if (kAlgo == kLL) {
+    // ---- latency protocol (small buckets, e.g. the one that is only complete after the very last gradient kernel):
+    //      scaled bf16 gradients are pushed as {data, epoch} words straight into slot [rank] of every peer (ONE
+    //      multimem.st per 16 bytes through the NVSwitch when the region is multicast-mapped) and the W slots in local
+    //      memory are polled and summed in rank order.  No staging pass, no flag barrier: ~one NVLink flight time.
+    const uint32_t e = calls_of(my)[0] + 1u;
+    const bool mc = c.mc_base != nullptr;
+    const size_t ll_off = kFlagBytes + 4 * c.buf_bytes + (size_t)parity * (size_t)W * kLLSlotBytes;
+    char* rd_base = (mc ? c.mc_local - kFlagBytes : my) + ll_off;
+    const size_t per = (nv + B - 1) / B;
+    const size_t lo = min((size_t)b * per, nv), hi = min(lo + per, nv);
+    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+      float f[V];
+      load_grad<V>(grad, goff<V>(live, v), f);
+      const uint4 w = Wt::pack(f, scale);
+      const uint4 w0 = make_uint4(w.x, e, w.y, e), w1 = make_uint4(w.z, e, w.w, e);
+      const size_t off = ll_off + (size_t)c.rank * kLLSlotBytes + v * 32;
+      if (mc) {
+        mc_st(c.mc_base - kFlagBytes + off, w0);
+        mc_st(c.mc_base - kFlagBytes + off + 16, w1);
+      } else {
+        for (int d = 0; d < W; ++d) {
+          char* dst = c.base[(c.rank + d) % W] + off;
+          ll_store(dst, w0);
+          ll_store(dst + 16, w1);
+        }
+      }
+    }
+    const long long t0 = globaltimer_ns();
+    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+      float a[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[i] = 0.f;
+      for (int r = 0; r < W; ++r) {
+        const char* q = rd_base + (size_t)r * kLLSlotBytes + v * 32;
+        uint4 w0 = ll_load(q), w1 = ll_load(q + 16);
+        while (w0.y != e || w0.w != e || w1.y != e || w1.w != e) {
+          if (globaltimer_ns() - t0 > c.timeout_ns) { atomicExch(err_of(my), 1u); __threadfence_system(); __trap(); }
+          w0 = ll_load(q); w1 = ll_load(q + 16);
+        }
+        Wt::accum(a, make_uint4(w0.x, w0.z, w1.x, w1.z));
+      }
+      if (kAdam) adam_apply<V>(ad, ak, grad, goff<V>(live, v), a, dacc);
+      else store_grad<V>(grad, goff<V>(live, v), a);
+    }
+  } else {
   // ---- pack: fused 1/W scale + cast into the peer-visible staging buffer -------------------------
   if (kAlgo == kOneShot) {
     const size_t per = (nv + B - 1) / B;
@@ -360,40 +420,72 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
   if (kAlgo == kOneShot) {
     const size_t per = (nv + B - 1) / B;
     const size_t lo = min((size_t)b * per, nv), hi = min(lo + per, nv);
-    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-      uint4 w[kMaxRanks];
+    // all W copies of U vectors are requested before the first add: one NVLink round trip per U vectors per thread
+    // (with one vector per trip a CTA moved ~25 GB/s and the kernel needed ~100 CTAs next to the backward kernels)
+    auto body = [&](auto ucount) {
+      constexpr int U = decltype(ucount)::value;
+      for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * U) {
+        uint4 w[U][kMaxRanks];
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
-        if (r < W) w[r] = reinterpret_cast<const uint4*>(c.base[r] + stage_off)[v];
-      float a[V];
+        for (int u = 0; u < U; ++u) {
+          const size_t v = v0 + (size_t)u * blockDim.x;
 #pragma unroll
-      for (int i = 0; i < V; ++i) a[i] = 0.f;
+          for (int r = 0; r < kMaxRanks; ++r)
+            if (r < W && v < hi) w[u][r] = reinterpret_cast<const uint4*>(c.base[r] + stage_off)[v];
+        }
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
-        if (r < W) Wt::accum(a, w[r]);
-      if (kAdam) adam_apply<V>(ad, ak, grad, goff<V>(live, v), a, dacc);
-      else store_grad<V>(grad, goff<V>(live, v), a);
-    }
+        for (int u = 0; u < U; ++u) {
+          const size_t v = v0 + (size_t)u * blockDim.x;
+          if (v >= hi) continue;
+          float a[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) a[i] = 0.f;
+#pragma unroll
+          for (int r = 0; r < kMaxRanks; ++r)
+            if (r < W) Wt::accum(a, w[u][r]);
+          if (kAdam) adam_apply<V>(ad, ak, grad, goff<V>(live, v), a, dacc);
+          else store_grad<V>(grad, goff<V>(live, v), a);
+        }
+      }
+    };
+    if (W <= 2) body(std::integral_constant<int, 4>{});
+    else if (W <= 4) body(std::integral_constant<int, 2>{});
+    else body(std::integral_constant<int, 1>{});
   } else {
     size_t lo, hi;
     sub_range(nv, W, B, c.rank, b, lo, hi);
     if (kAlgo == kTwoShot) {
-      for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-        uint4 w[kMaxRanks];
+      auto body = [&](auto ucount) {
+        constexpr int U = decltype(ucount)::value;
+        for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * U) {
+          uint4 w[U][kMaxRanks];
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r)
-          if (r < W) w[r] = reinterpret_cast<const uint4*>(c.base[r] + stage_off)[v];
-        float a[V];
+          for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + (size_t)u * blockDim.x;
 #pragma unroll
-        for (int i = 0; i < V; ++i) a[i] = 0.f;
+            for (int r = 0; r < kMaxRanks; ++r)
+              if (r < W && v < hi) w[u][r] = reinterpret_cast<const uint4*>(c.base[r] + stage_off)[v];
+          }
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r)
-          if (r < W) Wt::accum(a, w[r]);
-        const uint4 o = Wt::from_acc(a);
+          for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + (size_t)u * blockDim.x;
+            if (v >= hi) continue;
+            float a[V];
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r)
-          if (r < W) reinterpret_cast<uint4*>(c.base[r] + out_off)[v] = o;     // NVLink push
-      }
+            for (int i = 0; i < V; ++i) a[i] = 0.f;
+#pragma unroll
+            for (int r = 0; r < kMaxRanks; ++r)
+              if (r < W) Wt::accum(a, w[u][r]);
+            const uint4 o = Wt::from_acc(a);
+#pragma unroll
+            for (int r = 0; r < kMaxRanks; ++r)
+              if (r < W) reinterpret_cast<uint4*>(c.base[r] + out_off)[v] = o;     // NVLink push
+          }
+        }
+      };
+      if (W <= 2) body(std::integral_constant<int, 4>{});
+      else if (W <= 4) body(std::integral_constant<int, 2>{});
+      else body(std::integral_constant<int, 1>{});
     } else {
       const char* mc_stage = c.mc_base - kFlagBytes + stage_off;
       char* mc_out = c.mc_base - kFlagBytes + out_off;
@@ -420,6 +512,7 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
       else unpack_range<kBf16>(grad, my_out, l2, h2, live);
     }
   }
+  }   // staged algorithms
   if (kAdam && ad.prev != nullptr && ad.diff_out != nullptr) {
     __shared__ float wsum[kCommThreads / 32];
     dacc = warp_sum(dacc);
@@ -463,9 +556,11 @@ struct HzComm {
   hz::CommDev dev;
   int device;
   int max_blocks;
+  int block_cap;               // 0 = max_blocks; else a (smaller) cap for the following calls
   size_t region_bytes;
   char* local;                 // cudaMalloc'd region
   size_t heap_off, heap_bytes; // symmetric heap (optional)
+  size_t ll_bytes;             // latency-protocol slot area behind the staging buffers
   bool imported[hz::kMaxRanks];
   bool local_group;
 };
@@ -505,11 +600,13 @@ HzComm* hz_comm_create2(int rank, int world, int device, size_t max_wire_bytes, 
     const double sec = e ? atof(e) : 0.0;
     c->dev.timeout_ns = sec > 0.0 ? (long long)(sec * 1e9) : hz::kDefaultSpinTimeoutNs;
   }
-  c->heap_off = hz::kFlagBytes + 4 * buf;
+  c->ll_bytes = 2 * (size_t)world * hz::kLLSlotBytes;              // latency-protocol slots [2 parities][world]
+  c->heap_off = hz::kFlagBytes + 4 * buf + c->ll_bytes;
   c->heap_bytes = (heap_bytes + 1023) / 1024 * 1024;
   c->region_bytes = c->heap_off + c->heap_bytes;
   if (cudaMalloc(&c->local, c->region_bytes) != cudaSuccess) { delete c; return nullptr; }
   cudaMemset(c->local, 0, hz::kFlagBytes);
+  cudaMemset(c->local + hz::kFlagBytes + 4 * buf, 0, c->ll_bytes);      // LL flags start at 0 (epochs start at 1)
   if (c->heap_bytes) cudaMemset(c->local + c->heap_off, 0, c->heap_bytes);
   c->dev.base[rank] = c->local;
   cudaDeviceSynchronize();
@@ -546,8 +643,11 @@ int hz_comm_link_local(HzComm** comms, int world) {
   return 0;
 }
 
+size_t hz_comm_symm_bytes(HzComm* c) { return 4 * c->dev.buf_bytes + c->ll_bytes; }
+
+// mc_ptr / local_ptr: multicast and local mapping of a zero-initialised symmetric buffer of hz_comm_symm_bytes()
 void hz_comm_set_multicast(HzComm* c, void* mc_ptr, void* local_ptr, size_t bytes) {
-  if (bytes < 4 * c->dev.buf_bytes) return;
+  if (bytes < 4 * c->dev.buf_bytes + c->ll_bytes) return;
   c->dev.mc_base = (char*)mc_ptr;
   c->dev.mc_local = (char*)local_ptr;
 }
@@ -558,8 +658,10 @@ int hz_comm_blocks_for(HzComm* c, size_t n, int algo, int wire_bf16) {
   // ~4 vectors (64 B) per thread and phase: enough CTAs to pull HBM + NVLink bandwidth on big buckets,
   // a single CTA for latency-bound small ones
   size_t want = (nv + (size_t)hz::kCommThreads * 4 - 1) / ((size_t)hz::kCommThreads * 4);
+  if (algo == hz::kLL) want = (nv + (size_t)hz::kCommThreads * 2 - 1) / ((size_t)hz::kCommThreads * 2);   // latency first
   if (want < 1) want = 1;
   if (want > (size_t)c->max_blocks) want = c->max_blocks;
+  if (c->block_cap > 0 && want > (size_t)c->block_cap) want = c->block_cap;
   (void)algo;
   return (int)want;
 }
@@ -571,6 +673,7 @@ static int comm_allreduce_impl(HzComm* c, float* grad, size_t n, int algo, int w
   if (n % V != 0) return -2;
   if (n * (wire_bf16 ? 2 : 4) > c->dev.buf_bytes) return -3;
   if (algo == hz::kNvls && c->dev.mc_base == nullptr) return -4;
+  if (algo == hz::kLL && (!wire_bf16 || n > hz::kLLMaxElems)) return -5;
   const int blocks = hz_comm_blocks_for(c, n, algo, wire_bf16);
   hz::AdamFuse ad;
   memset(&ad, 0, sizeof(ad));
@@ -583,6 +686,7 @@ static int comm_allreduce_impl(HzComm* c, float* grad, size_t n, int algo, int w
   if (wire_bf16) {
     if (algo == hz::kOneShot) HZ_LAUNCH(true, hz::kOneShot);
     else if (algo == hz::kTwoShot) HZ_LAUNCH(true, hz::kTwoShot);
+    else if (algo == hz::kLL) HZ_LAUNCH(true, hz::kLL);
     else HZ_LAUNCH(true, hz::kNvls);
   } else {
     if (algo == hz::kOneShot) HZ_LAUNCH(false, hz::kOneShot);
@@ -608,6 +712,10 @@ int hz_comm_allreduce_adam(HzComm* c, float* grad, size_t n, int algo, int wire_
   ad.step = step; ad.lr = lr; ad.b1 = b1; ad.b2 = b2; ad.eps = eps; ad.bump = bump;
   return comm_allreduce_impl(c, grad, n, algo, wire_bf16, scale, live, &ad, st);
 }
+
+// Grid cap for the following collectives (same value on every rank: blocks pair up with their peers).  A bucket
+// whose result is not needed for a long time is reduced by a few CTAs so the backward kernels keep the SMs.
+void hz_comm_set_block_cap(HzComm* c, int cap) { c->block_cap = cap > 0 ? cap : 0; }
 
 int hz_comm_barrier(HzComm* c, long long* stamps, cudaStream_t st) {
   hz::barrier_kernel<<<1, 32, 0, st>>>(c->dev, stamps);

@@ -72,8 +72,10 @@ size_t hz_comm_heap_bytes(struct HzComm* c);
 int hz_comm_export(struct HzComm* c, void* handle64);
 int hz_comm_import(struct HzComm* c, const void* handles);
 int hz_comm_link_local(struct HzComm** comms, int world);
+size_t hz_comm_symm_bytes(struct HzComm* c);
 void hz_comm_set_multicast(struct HzComm* c, void* mc_ptr, void* local_ptr, size_t bytes);
 int hz_comm_blocks_for(struct HzComm* c, size_t n, int algo, int wire_bf16);
+void hz_comm_set_block_cap(struct HzComm* c, int cap);
 int hz_comm_allreduce(struct HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
                       const int* live, cudaStream_t st);
 int hz_comm_allreduce_adam(struct HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
@@ -88,16 +90,16 @@ void hz_tp_set_debug(long long* buf);
 int hz_tp_tiles(int kind, int N, int H, int W_, int Cin, int Cout, int stride);
 int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, const void* addend, float* stats,
                char* const* heaps, char* mc_heap, long long part_off, long long part_stride, long long cnt_off,
-               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int mode, int nvls, int ll,
+               long long ready_off, unsigned* epoch, int world, int rank, int mode, int nvls, int ll,
                int ag, int N, int H, int W_, int Cin, int Cout, int R, int stride, int pad, cudaStream_t st);
 int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t* labels, float* pooled,
                float* dl_local, float* logits, void* dfeat, float* loss, float* correct, char* const* heaps,
                char* mc_heap, long long logits_off, long long dfeat_off, unsigned* epoch,
-               unsigned* done, int world, int rank, int nvls, int N, int C, int HW, int k_local, int n_valid,
+               int world, int rank, int nvls, int N, int C, int HW, int k_local, int n_valid,
                float loss_scale, cudaStream_t st);
 size_t hz_tp_head_bytes(int N, int C, int K, int world);
 int hz_tp_allreduce_bf16(const void* in, void* out, size_t n, char* const* heaps, char* mc_heap, long long buf_off,
-                         long long cnt_off, unsigned* epoch, unsigned* done, int world, int rank, int nvls, int ll,
+                         long long cnt_off, unsigned* epoch, int world, int rank, int nvls, int ll,
                          int blocks, cudaStream_t st);
 void hz_head_wgrad(const float* pooled, const float* dlogits, float* dW, float* db, int N, int C, int K,
                    int accumulate, cudaStream_t st);

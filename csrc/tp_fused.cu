@@ -63,8 +63,8 @@ struct TpParams {
   long long part_stride;         //   latency protocol LL words [2][world][tiles][128][64] (2x the bytes); stride of a parity
   long long cnt_off;             // u32 [tiles] arrival counters (monotonic: += W per call)
   long long ready_off;           // u32 [world]      (AG: "my A shard is ready")
-  unsigned* epoch;               // local: number of completed calls
-  unsigned* done;                // local: CTAs finished in this call
+  unsigned* epoch;               // local u32 [tiles]: calls completed by each tile's CTA (every CTA keeps its own
+                                 // counter: no cross-CTA atomic / fence at the tail of the kernel)
   __nv_bfloat16* out;            // local output tensor
   const __nv_bfloat16* addend;   // optional, layout of out: out = reduced tile + addend (residual gradient)
   float* stats;                  // optional [2*ncols]: sum y, sum y^2 of the REDUCED output (pre-zeroed)
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   HZ_STAMP(1);                                  // prologue done
   pdl_wait();                                   // the A operand / addend / epoch counter come from upstream kernels
   HZ_STAMP(2);                                  // upstream kernel complete
-  const unsigned e = *p.epoch + 1u;             // epoch of this call (same on every rank)
+  const unsigned e = p.epoch[tile] + 1u;        // epoch of this call (same for every tile and on every rank)
 
   if (p.ag && warp == 3) {
     // ready handshake: our shard was produced by earlier kernels of this stream (complete: pdl_wait above), so
@@ -478,16 +478,7 @@ __global__ void __launch_bounds__(128) igemm_tp_kernel(const __grid_constant__ P
   __syncthreads();
   HZ_STAMP(8);                                  // output rows (+ BN sums) written
   if (warp == 2) tc::tmem_dealloc(tmem_d, BLOCK_N);
-  // ---- the last CTA of the grid publishes the new epoch (every CTA has already read the old one)
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned fin = atomicAdd(p.done, 1u);
-    if (fin == (unsigned)(tiles - 1)) {
-      *p.done = 0u;
-      *p.epoch = e;
-      __threadfence();
-    }
-  }
+  if (threadIdx.x == 0) p.epoch[tile] = e;
   HZ_STAMP(9);
 #undef HZ_STAMP
 }
@@ -508,7 +499,7 @@ struct TpHeadParams {
   long long logits_off;          // LL words {f32, epoch}: [2 parities][N][K]
   long long dfeat_off;           // LL words {f32, epoch}: [2 parities][world][N][C]   partial dX of every rank
   long long par_stride_logits, par_stride_dfeat;
-  unsigned* epoch; unsigned* done;
+  unsigned* epoch;               // local u32 [N]: one call counter per sample CTA
   long long timeout_clk;
 };
 
@@ -534,7 +525,7 @@ __global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __res
   float* lg = hsm + p.C;
   float* dl = lg + p.K;
   const int n = blockIdx.x, W = p.world, me = p.rank, C = p.C, K = p.K, kl = p.k_local;
-  const unsigned e = *p.epoch + 1u;
+  const unsigned e = p.epoch[n] + 1u;
   const unsigned par = e & 1u;
   char* my_heap = p.heap[me];
   const float inv_hw = 1.f / (float)p.HW;
@@ -646,15 +637,8 @@ __global__ void __launch_bounds__(128) tp_head_kernel(const __nv_bfloat16* __res
       }
     }
   }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned fin = atomicAdd(p.done, 1u);
-    if (fin == (unsigned)(gridDim.x - 1)) {
-      *p.done = 0u;
-      *p.epoch = e;
-      __threadfence();
-    }
-  }
+  __syncthreads();
+  if (threadIdx.x == 0) p.epoch[n] = e;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -668,7 +652,7 @@ struct TpArParams {
   char* mc_heap;
   long long buf_off, buf_stride;     // bw: bf16 [2 parities][n];  ll: LL words [2 parities][world][n/8] x 32 B
   long long cnt_off;                 // u32 [gridDim.x]
-  unsigned* epoch; unsigned* done;
+  unsigned* epoch;                   // local u32 [gridDim.x]: one call counter per block
   long long timeout_clk;
 };
 
@@ -678,7 +662,7 @@ __global__ void __launch_bounds__(256) tp_allreduce_bf16_kernel(const __nv_bfloa
   pdl_launch();
   pdl_wait();
   const int W = p.world, me = p.rank;
-  const unsigned e = *p.epoch + 1u;
+  const unsigned e = p.epoch[blockIdx.x] + 1u;
   const long long boff = p.buf_off + (long long)(e & 1u) * p.buf_stride;
   const size_t per = (nvec + gridDim.x - 1) / gridDim.x;
   const size_t lo = min((size_t)blockIdx.x * per, nvec), hi = min(lo + per, nvec);
@@ -721,15 +705,8 @@ __global__ void __launch_bounds__(256) tp_allreduce_bf16_kernel(const __nv_bfloa
       const bf16x8 pk = pack8(a);
       reinterpret_cast<uint4*>(out)[v] = *reinterpret_cast<const uint4*>(&pk);
     }
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned fin = atomicAdd(p.done, 1u);
-      if (fin == gridDim.x - 1) {
-        *p.done = 0u;
-        *p.epoch = e;
-        __threadfence();
-      }
-    }
+    __syncthreads();
+    if (threadIdx.x == 0) p.epoch[blockIdx.x] = e;
     return;
   }
   uint4* mine = reinterpret_cast<uint4*>(p.heap[me] + boff);
@@ -770,15 +747,8 @@ __global__ void __launch_bounds__(256) tp_allreduce_bf16_kernel(const __nv_bfloa
     }
     reinterpret_cast<uint4*>(out)[v] = o;
   }
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned fin = atomicAdd(p.done, 1u);
-    if (fin == gridDim.x - 1) {
-      *p.done = 0u;
-      *p.epoch = e;
-      __threadfence();
-    }
-  }
+  __syncthreads();
+  if (threadIdx.x == 0) p.epoch[blockIdx.x] = e;
 }
 
 }  // namespace hz
@@ -820,7 +790,7 @@ int hz_tp_tiles(int kind, int N, int H, int W_, int Cin, int Cout, int stride) {
 // heaps[r]: heap base of rank r as mapped here; mc_heap: multicast mapping (nvls) or null.
 int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, const void* addend, float* stats,
                char* const* heaps, char* mc_heap, long long part_off, long long part_stride, long long cnt_off,
-               long long ready_off, unsigned* epoch, unsigned* done, int world, int rank, int mode, int nvls, int ll,
+               long long ready_off, unsigned* epoch, int world, int rank, int mode, int nvls, int ll,
                int ag, int N, int H, int W_, int Cin, int Cout, int R, int stride, int pad, cudaStream_t st) {
   const int S_ = R;
   if (kind == 0 && stride != 1) return -23;
@@ -888,7 +858,7 @@ int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, co
   for (int r = 0; r < world; ++r) p.heap[r] = heaps[r];
   p.mc_heap = mc_heap;
   p.part_off = part_off; p.part_stride = part_stride; p.cnt_off = cnt_off; p.ready_off = ready_off;
-  p.epoch = epoch; p.done = done;
+  p.epoch = epoch;
   p.out = (__nv_bfloat16*)out; p.addend = (const __nv_bfloat16*)addend; p.stats = stats;
   p.timeout_clk = tp_timeout_clk();
   p.dbg = g_tp_dbg;
@@ -910,7 +880,7 @@ int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, co
 int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t* labels, float* pooled,
                float* dl_local, float* logits, void* dfeat, float* loss, float* correct, char* const* heaps,
                char* mc_heap, long long logits_off, long long dfeat_off, unsigned* epoch,
-               unsigned* done, int world, int rank, int nvls, int N, int C, int HW, int k_local, int n_valid,
+               int world, int rank, int nvls, int N, int C, int HW, int k_local, int n_valid,
                float loss_scale, cudaStream_t st) {
   if (C & 3) return -20;
   hz::TpHeadParams p;
@@ -923,7 +893,7 @@ int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t
   p.logits_off = logits_off; p.dfeat_off = dfeat_off;
   p.par_stride_logits = (long long)N * p.K * 8;
   p.par_stride_dfeat = (long long)world * N * C * 8;
-  p.epoch = epoch; p.done = done;
+  p.epoch = epoch;
   p.timeout_clk = tp_timeout_clk();
   if (N > 148) return -21;
   const size_t smem = sizeof(float) * (C + 2 * p.K);
@@ -935,7 +905,7 @@ size_t hz_tp_head_bytes(int N, int C, int K, int world) { return 2 * ((size_t)N 
 
 // out = sum over ranks of `in` (bf16, n elements, n % 8 == 0); buf: bf16 [2][n] in the heap, cnt: u32 [blocks]
 int hz_tp_allreduce_bf16(const void* in, void* out, size_t n, char* const* heaps, char* mc_heap, long long buf_off,
-                         long long cnt_off, unsigned* epoch, unsigned* done, int world, int rank, int nvls, int ll,
+                         long long cnt_off, unsigned* epoch, int world, int rank, int nvls, int ll,
                          int blocks, cudaStream_t st) {
   if (n & 7) return -20;
   hz::TpArParams p;
@@ -945,7 +915,7 @@ int hz_tp_allreduce_bf16(const void* in, void* out, size_t n, char* const* heaps
   p.mc_heap = mc_heap;
   p.ll = ll ? 1 : 0;
   p.buf_off = buf_off; p.buf_stride = ll ? (long long)world * n * 4 : (long long)n * 2; p.cnt_off = cnt_off;
-  p.epoch = epoch; p.done = done;
+  p.epoch = epoch;
   p.timeout_clk = tp_timeout_clk();
   if (blocks < 1) blocks = 1;
   if (blocks > 64) blocks = 64;

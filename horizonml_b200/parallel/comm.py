@@ -33,6 +33,8 @@ def rank() -> int:
 
 # size thresholds (bytes of wire data) for algorithm selection; refined from measurements
 ONESHOT_MAX_BYTES = 1 << 20
+LL_MAX_ELEMS = 512 * 1024                 # csrc/comm.cu kLLMaxElems
+LL_MAX_INGRESS_BYTES = int(os.environ.get("HZ_LL_MAX_INGRESS", str(6 << 20)))
 
 
 class GradAllReduce:
@@ -86,6 +88,9 @@ class PeerAllReduce(GradAllReduce):
         self.handle = self.C.PeerComm(self.rank, self.world, self.device.index or 0,
                                       self.max_numel * wire_bytes, max_blocks)
         self.has_nvls = False
+        self.early_blocks = int(os.environ.get("HZ_COMM_BLOCKS_EARLY", "24"))
+        self.tail_blocks = int(os.environ.get("HZ_COMM_BLOCKS_TAIL", "0"))
+        self.plain_blocks = int(os.environ.get("HZ_COMM_BLOCKS", "32"))   # measured: 32 CTAs 0.601, 96 CTAs 0.608 ms/step (2 GPUs)
         self.nvls_error: Optional[str] = None
         if self.world > 1:
             # 64-byte cudaIpcMemHandle of this rank's region -> everyone (opaque host bytes)
@@ -104,10 +109,11 @@ class PeerAllReduce(GradAllReduce):
             return False
         try:
             import torch.distributed._symmetric_memory as symm
-            wire_bytes = 2 if self.wire == "bf16" else 4
-            nbytes = 4 * ((self.max_numel * wire_bytes + 255) // 256 * 256)   # stage[2] + out[2]
+            nbytes = int(self.handle.symm_bytes())     # stage[2] + out[2] + latency-protocol slots
             buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
             hdl = symm.rendezvous(buf, group=group if group is not None else dist.group.WORLD)
+            buf.zero_()                                 # LL flags start at 0
+            torch.cuda.synchronize(self.device)
             mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
             ok = torch.tensor([1 if mc else 0], device=self.device)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
@@ -126,6 +132,10 @@ class PeerAllReduce(GradAllReduce):
         if self.algo != "auto":
             return self.algo
         wb = numel * (2 if self.wire == "bf16" else 4)
+        # latency protocol for small buckets (flag-in-data push, no staging pass / barrier): every rank receives
+        # world x numel x 4 bytes, so it is bounded by ingress, not by element count alone
+        if self.wire == "bf16" and numel <= LL_MAX_ELEMS and self.world * numel * 4 <= LL_MAX_INGRESS_BYTES:
+            return "ll"
         if self.world <= 2 or wb <= ONESHOT_MAX_BYTES:
             return "oneshot"
         return "nvls" if self.has_nvls else "twoshot"
@@ -143,6 +153,9 @@ class PeerAllReduce(GradAllReduce):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_numel
         n_wire = t.numel() if live is None else live.numel() * 64
         a = algo or self.pick(n_wire)
+        # "ll" buckets are the latency-critical ones (small / last); the staged algorithms run in the shadow of the
+        # remaining backward kernels and get a CTA cap so that they do not crowd them
+        self.handle.set_block_cap(0 if a == "ll" else self.plain_blocks)
         self.handle.allreduce(t, a, self.wire == "bf16", 1.0 / self.world, live)
 
     def allreduce_adam_(self, t: torch.Tensor, master, m, v, shadow, prev, diff_out, step_t, lr, b1, b2, eps,
@@ -153,6 +166,9 @@ class PeerAllReduce(GradAllReduce):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_numel
         n_wire = t.numel() if live is None else live.numel() * 64
         a = algo or self.pick(n_wire)
+        # a bucket reduced in the shadow of the remaining backward needs few CTAs (it has ~100 us of slack and must
+        # not take the SMs from the latency-bound backward kernels); the last bucket is on the critical path
+        self.handle.set_block_cap(self.tail_blocks if bump else self.early_blocks)
         self.handle.allreduce_adam(t, a, self.wire == "bf16", 1.0 / self.world, live, master, m, v, shadow, prev,
                                    diff_out, step_t, float(lr), float(b1), float(b2), float(eps), bool(bump))
         return a

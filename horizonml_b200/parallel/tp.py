@@ -153,7 +153,7 @@ class FusedTP:
         part_off = h.alloc(2 * part_stride)
         cnt_off = h.alloc(4 * tiles)
         ready_off = h.alloc(4 * self.world)
-        ctrl_off = h.alloc(8)
+        ctrl_off = h.alloc(4 * tiles)
         ag = ag_off is not None
         C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
         xs = list(x_shape)
@@ -193,7 +193,7 @@ class FusedTP:
         K = k_local * self.world
         logits_off = h.alloc(2 * n * K * 8)                    # {value, epoch} words (flag-in-data protocol)
         dfeat_off = h.alloc(2 * self.world * n * c * 8)
-        ctrl_off = h.alloc(8)
+        ctrl_off = h.alloc(4 * n)
         C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
         wire = (self.world - 1) * n * (k_local * 8 + c * 8)
         self.ops.append({"kind": "head", "n": n, "c": c, "k_local": k_local, "nvls": nvls})
@@ -214,7 +214,7 @@ class FusedTP:
             ll = self.proto == "ll" or (self.proto == "auto" and self.world * n * 4 <= self.LL_MAX_INGRESS)
             buf_off = h.alloc(2 * (self.world * n * 4 if ll else n * 2))
             cnt_off = h.alloc(4 * blocks)
-            ctrl_off = h.alloc(8)
+            ctrl_off = h.alloc(4 * blocks)
             C, ptrs, mc, rank, nvls = self.C, h.ptrs, h.mc_ptr, self.rank, self.nvls
             self.ops.append({"kind": "allreduce_bf16", "numel": n, "nvls": nvls, "protocol": "ll" if ll else "bw"})
 

@@ -59,7 +59,11 @@ class DPEngine:
                            and os.environ.get("HZ_OVERLAP_ADAM", "0") != "1")
         layout = cfg.bucket_layout
         if layout == "auto":
-            layout = "layers" if (self.fused_adam and cfg.model == "resnet18") else "size"
+            # layer-group buckets: every group's all-reduce starts the moment its backward is done and the bucket that
+            # is only complete after the very last gradient kernel (layer1 + stem, 157 k elements) is small enough for
+            # the flag-in-data latency protocol — measured 0.601 vs 0.605 ms/step at 2 GPUs against DDP-like size caps
+            peer = rt.world > 1 and dev.type == "cuda" and cfg.allreduce != "nccl" and rt.backend == "native" and not self.zero1
+            layout = "layers" if (peer and cfg.model == "resnet18") else "size"
         starts = ("layer3.", "layer2.", "layer1.") if layout == "layers" else None
         self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype,
                                cfg.live_bucket_mb if by_live else cfg.bucket_mb, live_masks=live, bucket_by_live=by_live,

@@ -60,6 +60,8 @@ class TPEngine:
             kind = cfg.allreduce if cfg.allreduce not in ("auto", "nvls") else "twoshot"
             self.ar_shd = make_grad_allreduce(kind, self.flat_shd.total, rt.device, group=mesh.dp_group)
         self.stats = DeviceStats(rt.device)
+        # wgrad kernels depend only on (dy, x): side stream, off the dgrad / fused-reduction critical path
+        ops.enable_side_stream(rt.device.type == "cuda" and rt.backend == "native")
         self.prev_grad = torch.zeros_like(self.flat_rep.grad) if cfg.grad_divergence else None
         # collectives inside the step (NCCL all-gather/all-reduce) are graph-capturable on CUDA
         self._graphed = GraphedStep(self._step_impl, rt.device, cfg.cuda_graph and rt.backend == "native")

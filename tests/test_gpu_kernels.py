@@ -311,11 +311,14 @@ def test_adam_and_allreduce_skip_dead_blocks(nb):
             assert torch.equal(work[r][~emask], grads[r][~emask])             # dead blocks never touched
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "ll"])
 @pytest.mark.parametrize("wire_bf16", [True, False])
 def test_peer_allreduce_virtual_ranks(nb, world, algo, wire_bf16):
-    """Multi-rank protocol (flags, parity, slices) exercised with `world` virtual ranks on one GPU."""
+    """Multi-rank protocol (flags, parity, slices; flag-in-data words for "ll") exercised with `world` virtual ranks on
+    one GPU."""
+    if algo == "ll" and not wire_bf16:
+        pytest.skip("the latency protocol carries bf16 pairs")
     C = nb.C
     n = 1 << 18
     comms = [C.PeerComm(r, world, 0, n * 4, 16) for r in range(world)]
@@ -403,7 +406,7 @@ def test_cuda_graph_step(nb):
 
 
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "ll"])
 def test_allreduce_adam_fused_virtual_ranks(nb, world, algo):
     """All-reduce with the Adam update fused into its final phase == all-reduce kernel followed by the Adam kernel
     (same fp32 values feed the same arithmetic), over dead-block-compacted buckets, 3 optimizer steps,

@@ -55,7 +55,7 @@ def main():
             else:
                 dist.all_reduce(ref)
                 ref /= world
-            for algo in algos:
+            for algo in algos + (["ll"] if (wire == "bf16" and n <= 512 * 1024) else []):
                 y = x.clone()
                 try:
                     for _ in range(3):           # back-to-back: flags / parity buffers are reused
@@ -93,7 +93,7 @@ def main():
             x = torch.randn(n, device=dev)
             xb = torch.empty(n, device=dev, dtype=torch.bfloat16)
             row = {"n": n, "wire_bytes": n * 2}
-            for algo in ["oneshot", "twoshot"] + (["nvls"] if ar.has_nvls else []):
+            for algo in ["oneshot", "twoshot"] + (["nvls"] if ar.has_nvls else []) + (["ll"] if n <= 512 * 1024 else []):
                 if algo == "oneshot" and n * 2 * world > (256 << 20):
                     continue
                 row[algo + "_us"] = time_fn(lambda a=algo: ar.allreduce_avg_(x, a))
