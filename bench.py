@@ -261,7 +261,10 @@ def run_reference(args):
                  "NCCL_ASYNC_ERROR_HANDLING", "TORCH_NCCL_ASYNC_ERROR_HANDLING") or k.startswith("TORCHELASTIC_"):
             env.pop(k, None)
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    threads = max(1, ncpu // max(W, 1))          # torchrun exports OMP_NUM_THREADS=1; give every worker its share
+    # torchrun exports OMP_NUM_THREADS=1; give every worker its share of the cores instead — capped at 16: the
+    # reference's tiny CPU convs get *slower* beyond that (measured on the GPU box's 128 cores: 64 threads per worker
+    # 1.58 s/step at N=2, one thread 0.71 s/step on an 8-core box)
+    threads = max(1, min(16, ncpu // max(W, 1)))
     env["OMP_NUM_THREADS"] = env["MKL_NUM_THREADS"] = str(threads)
     # gloo picks its interface from the host name, which does not resolve inside the GPU box's container: every pair
     # connection then times out after 300 s (round 1: "no results" at N >= 2).  Loopback is all a one-node run needs.

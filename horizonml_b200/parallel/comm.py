@@ -147,15 +147,17 @@ class PeerAllReduce(GradAllReduce):
         return {"kind": "peer", "wire": self.wire, "algo": self.algo, "nvls": self.has_nvls, "nvls_error": self.nvls_error,
                 "max_blocks": self.max_blocks}
 
-    def allreduce_avg_(self, t: torch.Tensor, algo: Optional[str] = None, live: Optional[torch.Tensor] = None) -> None:
+    def allreduce_avg_(self, t: torch.Tensor, algo: Optional[str] = None, live: Optional[torch.Tensor] = None,
+                       background: bool = False) -> None:
         """``live``: int32 indices (relative to ``t``) of the 64-element blocks to reduce — the rest of ``t`` is
-        known to be identically zero on every rank (dead conv taps) and never touches the wire."""
+        known to be identically zero on every rank (dead conv taps) and never touches the wire.  ``background``: the
+        call runs in the shadow of other kernels (a gradient bucket during backward): cap its grid (HZ_COMM_BLOCKS)."""
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.max_numel
         n_wire = t.numel() if live is None else live.numel() * 64
         a = algo or self.pick(n_wire)
         # "ll" buckets are the latency-critical ones (small / last); the staged algorithms run in the shadow of the
         # remaining backward kernels and get a CTA cap so that they do not crowd them
-        self.handle.set_block_cap(0 if a == "ll" else self.plain_blocks)
+        self.handle.set_block_cap(self.plain_blocks if (background and a != "ll") else 0)
         self.handle.allreduce(t, a, self.wire == "bf16", 1.0 / self.world, live)
 
     def allreduce_adam_(self, t: torch.Tensor, master, m, v, shadow, prev, diff_out, step_t, lr, b1, b2, eps,

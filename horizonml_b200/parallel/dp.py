@@ -90,7 +90,12 @@ class GradReducer:
         if self.world > 1:
             live = self.flat.bucket_live[b] if hasattr(self.flat, "bucket_live") else None
             self.bytes_last_step += self.ar.wire_bytes(bk.end - bk.start if live is None else live.numel() * 64)
-            self.ar.allreduce_avg_(self.flat.grad[bk.start:bk.end], live=live)
+            if self.overlap and hasattr(self.ar, "plain_blocks"):
+                # every bucket but the last is reduced while backward still runs: few CTAs, the SMs stay with backward
+                self.ar.allreduce_avg_(self.flat.grad[bk.start:bk.end], live=live,
+                                       background=self._n_launched < len(self.flat.buckets) - 1)
+            else:
+                self.ar.allreduce_avg_(self.flat.grad[bk.start:bk.end], live=live)
         if self.post_bucket is not None:
             self.post_bucket(b, self._n_launched == 0)
         self._n_launched += 1

@@ -15,15 +15,19 @@ for tag in default size nccl; do
   case $tag in default) X="";; size) X="--bucket_layout size";; nccl) X="--bucket_layout size --allreduce nccl";; esac
   timeout 120 $R --nproc-per-node $N --master-port 2957$((RANDOM % 10)) bench.py --gpus $N --steps 200 --warmup 20 $X > gpurun_out/bench${N}_$tag.log 2>&1; echo "bench$N $tag: $(grep '"metric"' gpurun_out/bench${N}_$tag.log | tail -1 | cut -c1-230)"
 done
-timeout 200 python data_parallel_train.py --world_size $N --epochs 3 --sample_size 50000 --logs_dir gpurun_out/logs_dp$N > gpurun_out/dp$N.log 2>&1; grep -E "Epoch \[3|Error|completed in|Traceback" gpurun_out/dp$N.log | head -4
-timeout 200 python tensor_parallel_train.py --world_size $N --epochs 3 --sample_size 8192 --logs_dir gpurun_out/logs_tp$N > gpurun_out/tp$N.log 2>&1; grep -E "Epoch \[3|Error|completed in|Traceback" gpurun_out/tp$N.log | head -3
-timeout 200 python layer_model_parallel_train.py --world_size $PP --epochs 3 --sample_size 8192 --logs_dir gpurun_out/logs_pp$PP > gpurun_out/pp$PP.log 2>&1; grep -E "Epoch \[3|Error|completed in|Traceback|capture failed" gpurun_out/pp$PP.log | head -4
-timeout 200 python layer_model_parallel_train.py --world_size $PP --epochs 3 --sample_size 32768 --batch_size 512 --microbatches 8 --logs_dir gpurun_out/logs_pp${PP}_b512 > gpurun_out/pp${PP}_b512.log 2>&1; grep -E "Epoch \[3|Error|Traceback|capture failed" gpurun_out/pp${PP}_b512.log | head -3
-timeout 200 python layer_model_parallel_train.py --world_size $PP --epochs 3 --sample_size 32768 --batch_size 512 --microbatches 8 --no_pp_overlap --logs_dir gpurun_out/logs_pp${PP}_b512_blocking > gpurun_out/pp${PP}_b512_blocking.log 2>&1; grep -E "Epoch \[3|Error|Traceback" gpurun_out/pp${PP}_b512_blocking.log | head -3
-timeout 200 python data_parallel_train.py --world_size 1 --epochs 3 --sample_size 32768 --batch_size 512 --logs_dir gpurun_out/logs_dp1_b512 > gpurun_out/dp1_b512.log 2>&1; grep -E "Epoch \[3|Error|Traceback" gpurun_out/dp1_b512.log | head -3
+timeout 120 python data_parallel_train.py --world_size $N --epochs 3 --sample_size 50000 --logs_dir gpurun_out/logs_dp$N > gpurun_out/dp$N.log 2>&1; grep -E "Epoch \[3|Error|completed in|Traceback" gpurun_out/dp$N.log | head -4
+timeout 120 python tensor_parallel_train.py --world_size $N --epochs 3 --sample_size 8192 --logs_dir gpurun_out/logs_tp$N > gpurun_out/tp$N.log 2>&1; grep -E "Epoch \[3|Error|completed in|Traceback" gpurun_out/tp$N.log | head -3
+timeout 120 python layer_model_parallel_train.py --world_size $PP --epochs 3 --sample_size 8192 --logs_dir gpurun_out/logs_pp$PP > gpurun_out/pp$PP.log 2>&1; grep -E "Epoch \[3|Error|completed in|Traceback|capture failed" gpurun_out/pp$PP.log | head -4
+timeout 120 python layer_model_parallel_train.py --world_size $PP --epochs 3 --sample_size 32768 --batch_size 512 --microbatches 8 --logs_dir gpurun_out/logs_pp${PP}_b512 > gpurun_out/pp${PP}_b512.log 2>&1; grep -E "Epoch \[3|Error|Traceback|capture failed" gpurun_out/pp${PP}_b512.log | head -3
+[ "${LIGHT:-0}" = "1" ] || timeout 100 python layer_model_parallel_train.py --world_size $PP --epochs 3 --sample_size 32768 --batch_size 512 --microbatches 8 --no_pp_overlap --logs_dir gpurun_out/logs_pp${PP}_b512_blocking > gpurun_out/pp${PP}_b512_blocking.log 2>&1; grep -E "Epoch \[3|Error|Traceback" gpurun_out/pp${PP}_b512_blocking.log | head -3
+[ "${LIGHT:-0}" = "1" ] || timeout 100 python data_parallel_train.py --world_size 1 --epochs 3 --sample_size 32768 --batch_size 512 --logs_dir gpurun_out/logs_dp1_b512 > gpurun_out/dp1_b512.log 2>&1; grep -E "Epoch \[3|Error|Traceback" gpurun_out/dp1_b512.log | head -3
 if [ $N -ge 4 ]; then
-  timeout 200 python hybrid_parallel_train.py --world_size $N --dp_replicas 2 --inner layer --epochs 2 --sample_size 16384 --logs_dir gpurun_out/logs_hybrid_dp2pp$((N/2)) > gpurun_out/hybrid_pp$N.log 2>&1; grep -E "Epoch \[2|Error|completed in|Traceback" gpurun_out/hybrid_pp$N.log | head -3
-  timeout 200 python hybrid_parallel_train.py --world_size $N --dp_replicas 2 --inner tensor --epochs 2 --sample_size 16384 --logs_dir gpurun_out/logs_hybrid_dp2tp$((N/2)) > gpurun_out/hybrid_tp$N.log 2>&1; grep -E "Epoch \[2|Error|completed in|Traceback" gpurun_out/hybrid_tp$N.log | head -3
+  timeout 100 python hybrid_parallel_train.py --world_size $N --dp_replicas 2 --inner layer --epochs 2 --sample_size 16384 --logs_dir gpurun_out/logs_hybrid_dp2pp$((N/2)) > gpurun_out/hybrid_pp$N.log 2>&1; grep -E "Epoch \[2|Error|completed in|Traceback" gpurun_out/hybrid_pp$N.log | head -3
+  timeout 100 python hybrid_parallel_train.py --world_size $N --dp_replicas 2 --inner tensor --epochs 2 --sample_size 16384 --logs_dir gpurun_out/logs_hybrid_dp2tp$((N/2)) > gpurun_out/hybrid_tp$N.log 2>&1; grep -E "Epoch \[2|Error|completed in|Traceback" gpurun_out/hybrid_tp$N.log | head -3
+fi
+if [ $N -ge 8 ]; then
+  timeout 100 $R --nproc-per-node $N --master-port 29566 tools/trace_step_dist.py gpurun_out/trace${N}_default 2>&1 | grep "^{" | cut -c1-600
+  timeout 100 $R --nproc-per-node $N --master-port 29567 tools/trace_step_dist.py gpurun_out/trace${N}_size --size 2>&1 | grep "^{" | cut -c1-600
 fi
 if [ "${SWEEP:-0}" = "1" ]; then
   timeout 900 python main.py --sample_sizes 1000 10000 50000 --world_size $N --epochs 2 --output_dir gpurun_out/benchmark_results_${N}gpu > gpurun_out/main$N.log 2>&1; tail -3 gpurun_out/main$N.log
