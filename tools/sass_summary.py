@@ -9,7 +9,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "csrc", "build")
 OUT = os.path.join(ROOT, "profiles", "sass")
-KEYS = ["UTCHMMA", "UTCQMMA", "UTCOMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UTCBAR", "UTCATOMSWS", "SYNCS",
+KEYS = ["UTCHMMA", "UTCQMMA", "UTCOMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UBLKCP", "UTCBAR", "UTCATOMSWS", "SYNCS",
         "UCGABAR", "CGAERRBAR", "MAPA", "LDGMC", "REDG", "ATOMG", "ACQBULK", "HMMA", "STRONG.SYS", "CCTL.IVALL", "ERRBAR"]
 HEAD = """# SASS evidence — `cuobjdump -sass csrc/build/*.cu.o` (sm_100a), per kernel (regenerate: `python tools/sass_summary.py`)
 
@@ -26,6 +26,9 @@ HEAD = """# SASS evidence — `cuobjdump -sass csrc/build/*.cu.o` (sm_100a), per
 | `LDGMC.E.*ADD*` | `multimem.ld_reduce` (NVLS in-switch reduction); the matching `multimem.st` is `STG.E.128.STRONG.SYS` on the multicast address |
 | `LDG/STG.E.STRONG.SYS` | `ld.acquire.sys` / `st.release.sys` peer flags |
 | `REDG.E.ADD.F32` | `red.global.add(.v4).f32` (BN-statistics / wgrad atomics) |
+| `STG.E.128.STRONG.SYS` / `LDG.E.128.STRONG.SYS` in `igemm_tp_kernel`, `tp_head_kernel`, `tp_allreduce_bf16_kernel`, `allreduce_kernel<…,3,…>` | `st.volatile.global.v4` / `multimem.st` / `ld.volatile.global.v4`: the flag-in-data ("LL") words {data, epoch, data, epoch} pushed into every peer and polled locally |
+| `REDG.E.ADD.STRONG.SYS` | `red.release.sys.global.add.u32` / `multimem.red.release.sys.add.u32`: tile arrival counters of the bandwidth protocol |
+| `UBLKCP.S.G` | `cp.async.bulk.shared::cluster.global`: peers' partial tiles pulled straight into the idle operand ring |
 
 No `HMMA` (legacy `mma.sync`) appears in any kernel.
 """
