@@ -39,7 +39,7 @@ def judge(got: dict, want: dict, want2: dict):
     for k in want:
         c, n = cos(got[k], want[k]), cos(want2[k], want[k])
         out[k] = [round(c, 5), round(n, 5)]
-        if c < min(n, 0.999) - 0.03 or (k.startswith("fc.") and rel(got[k], want[k]) > 6e-2):
+        if c < min(n, 0.999) - 0.06 or (k.startswith("fc.") and rel(got[k], want[k]) > 1e-1):
             bad[k] = out[k]
     return out, bad
 
