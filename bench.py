@@ -212,6 +212,29 @@ def run_ours(args):
 
 
 # ================================================================================================
+def reference_env(base: dict, world: int):
+    """(environment, OpenMP threads per worker) for the reference's own launcher process: not a torchrun child (the
+    reference does its own rendezvous on localhost:<free port> and spawns its own workers), CPU only, loopback gloo."""
+    env = dict(base)
+    env["PYTHONPATH"] = os.path.join(ROOT, "tools", "ref_shim") + os.pathsep + env.get("PYTHONPATH", "")
+    for k in list(env):
+        if k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE",
+                 "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "GROUP_WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS",
+                 "NCCL_ASYNC_ERROR_HANDLING", "TORCH_NCCL_ASYNC_ERROR_HANDLING") or k.startswith("TORCHELASTIC_"):
+            env.pop(k, None)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1; give every worker its share of the cores instead — capped at 16: the
+    # reference's tiny CPU convs get *slower* beyond that (measured on the GPU box's 128 cores: 64 threads per worker
+    # 1.58 s/step at N=2, one thread 0.71 s/step on an 8-core box)
+    threads = max(1, min(16, ncpu // max(world, 1)))
+    env["OMP_NUM_THREADS"] = env["MKL_NUM_THREADS"] = str(threads)
+    # gloo picks its interface from the host name, which does not resolve inside the GPU box's container: every pair
+    # connection then times out after 300 s (round 1: "no results" at N >= 2).  Loopback is all a one-node run needs.
+    env.setdefault("GLOO_SOCKET_IFNAME", "lo")
+    env["CUDA_VISIBLE_DEVICES"] = ""     # the reference is CPU-only (README.md:14)
+    return env, threads
+
+
 def run_reference(args):
     """Unmodified reference (baseline/_ref/data_parallel_train.py) through its own public API
     ``run_data_parallel(world_size, epochs, sample_size)``: CPU + gloo, its own mp launcher — the reference has no
@@ -252,24 +275,7 @@ def run_reference(args):
         "    res.update(epoch_time=float(e2['epoch_time'].max()), epochs=int(df['epoch'].max()),\n"
         "               avg_step_time=float(e2['avg_step_time'].max()), workers=int(e2['worker'].nunique()))\n"
         "print('HZREF ' + json.dumps(res))\n")
-    env = dict(os.environ)
-    env["PYTHONPATH"] = os.path.join(ROOT, "tools", "ref_shim") + os.pathsep + env.get("PYTHONPATH", "")
-    # not a torchrun child: the reference does its own rendezvous (localhost:<free port>) and spawns its own workers
-    for k in list(env):
-        if k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "GROUP_RANK", "LOCAL_WORLD_SIZE",
-                 "ROLE_RANK", "ROLE_WORLD_SIZE", "ROLE_NAME", "GROUP_WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS",
-                 "NCCL_ASYNC_ERROR_HANDLING", "TORCH_NCCL_ASYNC_ERROR_HANDLING") or k.startswith("TORCHELASTIC_"):
-            env.pop(k, None)
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # torchrun exports OMP_NUM_THREADS=1; give every worker its share of the cores instead — capped at 16: the
-    # reference's tiny CPU convs get *slower* beyond that (measured on the GPU box's 128 cores: 64 threads per worker
-    # 1.58 s/step at N=2, one thread 0.71 s/step on an 8-core box)
-    threads = max(1, min(16, ncpu // max(W, 1)))
-    env["OMP_NUM_THREADS"] = env["MKL_NUM_THREADS"] = str(threads)
-    # gloo picks its interface from the host name, which does not resolve inside the GPU box's container: every pair
-    # connection then times out after 300 s (round 1: "no results" at N >= 2).  Loopback is all a one-node run needs.
-    env.setdefault("GLOO_SOCKET_IFNAME", "lo")
-    env["CUDA_VISIBLE_DEVICES"] = ""     # the reference is CPU-only (README.md:14)
+    env, threads = reference_env(dict(os.environ), W)
     t0 = time.time()
     try:
         r = subprocess.run([sys.executable, "-c", code], cwd=work, env=env, capture_output=True, text=True, timeout=840)

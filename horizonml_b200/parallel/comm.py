@@ -37,6 +37,23 @@ LL_MAX_ELEMS = 512 * 1024                 # csrc/comm.cu kLLMaxElems
 LL_MAX_INGRESS_BYTES = int(os.environ.get("HZ_LL_MAX_INGRESS", str(6 << 20)))
 
 
+def pick_allreduce_algo(numel: int, world: int, wire: str = "bf16", has_nvls: bool = False) -> str:
+    """Algorithm of the fused peer all-reduce for a bucket of ``numel`` wire elements (the rule behind
+    ``PeerAllReduce(algo="auto")``; measured crossover points in profiles/README.md):
+
+    * ``ll``      — flag-in-data push, no staging pass / barrier: small buckets.  Every rank receives
+      ``world x numel x 4`` bytes, so the bound is on ingress bytes as well as on the slot size;
+    * ``oneshot`` — everyone reads all copies: 2 ranks, or up to 1 MiB of wire data;
+    * ``nvls``    — in-switch reduction (``multimem.ld_reduce`` / ``multimem.st``) when the buffers are multicast-mapped;
+    * ``twoshot`` — reduce-scatter + all-gather over peer pointers otherwise."""
+    wb = numel * (2 if wire == "bf16" else 4)
+    if wire == "bf16" and numel <= LL_MAX_ELEMS and world * numel * 4 <= LL_MAX_INGRESS_BYTES:
+        return "ll"
+    if world <= 2 or wb <= ONESHOT_MAX_BYTES:
+        return "oneshot"
+    return "nvls" if has_nvls else "twoshot"
+
+
 class GradAllReduce:
     """In-place *averaging* all-reduce of a slice of the flat fp32 gradient buffer."""
 
@@ -131,14 +148,7 @@ class PeerAllReduce(GradAllReduce):
     def pick(self, numel: int) -> str:
         if self.algo != "auto":
             return self.algo
-        wb = numel * (2 if self.wire == "bf16" else 4)
-        # latency protocol for small buckets (flag-in-data push, no staging pass / barrier): every rank receives
-        # world x numel x 4 bytes, so it is bounded by ingress, not by element count alone
-        if self.wire == "bf16" and numel <= LL_MAX_ELEMS and self.world * numel * 4 <= LL_MAX_INGRESS_BYTES:
-            return "ll"
-        if self.world <= 2 or wb <= ONESHOT_MAX_BYTES:
-            return "oneshot"
-        return "nvls" if self.has_nvls else "twoshot"
+        return pick_allreduce_algo(numel, self.world, self.wire, self.has_nvls)
 
     def wire_bytes(self, numel: int) -> int:
         return numel * (2 if self.wire == "bf16" else 4)

@@ -350,6 +350,35 @@ class OverlappedPipelineRunner:
         self._sent_bwd: List[Optional[torch.cuda.Event]] = [None] * n     # slot's dx has left (backward may overwrite it)
 
     @staticmethod
+    def plan(stage: int, num_stages: int, num_micro: int, nslots: int) -> List[Tuple[str, int]]:
+        """The host-side enqueue order of ``run`` as a list of (op, micro-batch) with op in ``recv_fwd`` (posted, not
+        waited for), ``F``, ``send_fwd``, ``recv_bwd``, ``B``, ``send_bwd`` — the same rules as ``run`` (a receive is
+        posted as soon as the slot's previous owner's backward has been enqueued), without any device work.  For
+        tests, tracing and documentation."""
+        first, last = stage == 0, stage == num_stages - 1
+        out: List[Tuple[str, int]] = []
+        posted = b_enq = 0
+
+        def prefetch():
+            nonlocal posted
+            while not first and posted < num_micro and (posted < nslots or posted - nslots < b_enq):
+                out.append(("recv_fwd", posted))
+                posted += 1
+        prefetch()
+        for a, i in one_f_one_b(stage, num_stages, num_micro):
+            if a == "F":
+                out.append(("F", i))
+                if not last:
+                    out += [("send_fwd", i), ("recv_bwd", i)]
+            else:
+                out.append(("B", i))
+                b_enq += 1
+                if not first:
+                    out.append(("send_bwd", i))
+            prefetch()
+        return out
+
+    @staticmethod
     def _phys(t: torch.Tensor) -> torch.Tensor:
         """The dense NHWC storage view of a channels_last activation (what travels)."""
         return t.detach().permute(0, 2, 3, 1)

@@ -1,0 +1,144 @@
+"""CPU unit tests of the host-side logic added in round 2: layer-group gradient buckets, the all-reduce algorithm
+rule, the symmetric-heap allocator (virtual ranks), the fused-TP tile count, the overlapped 1F1B enqueue plan, the
+measured compute/comm split and the reference arm's environment."""
+import importlib.util
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_layer_group_buckets():
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.resnet import resnet18
+    m = resnet18(10, seed=0)
+    live = m.live_tap_masks(32)
+    fl = FlatParams(list(m.named_parameters()), "cpu", torch.float32, live_masks=live,
+                    bucket_starts=("layer3.", "layer2.", "layer1."))
+    assert len(fl.buckets) == 4
+    heads = [b.names[0] for b in fl.buckets]
+    assert heads[0].startswith("fc.") and heads[1].startswith("layer3.") and heads[2].startswith("layer2.") \
+        and heads[3].startswith("layer1.")
+    assert all(n.startswith(("fc.", "layer4.")) for n in fl.buckets[0].names)
+    assert fl.buckets[3].names[-1] == "conv1.weight"            # stem rides in the last (smallest) bucket
+    # contiguous cover of the flat buffer, gradient-ready order
+    assert fl.buckets[0].start == 0 and fl.buckets[-1].end == fl.total
+    assert all(a.end == b.start for a, b in zip(fl.buckets, fl.buckets[1:]))
+    sizes = [b.end - b.start if fl.bucket_live[b.index] is None else fl.bucket_live[b.index].numel() * 64 for b in fl.buckets]
+    assert sizes[3] == min(sizes) and sizes[3] < 200_000      # the bucket that is ready last is the smallest one
+    # every parameter belongs to exactly one bucket
+    assert sum(len(b.names) for b in fl.buckets) == len(fl.params)
+    for p in fl.params:
+        assert 0 <= fl.bucket_index(p) < 4
+
+
+def test_allreduce_algorithm_rule():
+    from horizonml_b200.parallel.comm import LL_MAX_ELEMS, pick_allreduce_algo as pick
+    tail, l2, l3 = 157_056, 524_288 + 1024, 2_100_000
+    for w in (2, 4, 8):
+        assert pick(tail, w, "bf16", True) == "ll"             # the last bucket always takes the latency protocol
+    assert pick(LL_MAX_ELEMS, 2, "bf16", False) == "ll" and pick(LL_MAX_ELEMS + 64, 2, "bf16", False) == "oneshot"
+    assert pick(l3, 2, "bf16", True) == "oneshot"                # two ranks: reading the peer's copy is the whole job
+    assert pick(l3, 8, "bf16", True) == "nvls" and pick(l3, 8, "bf16", False) == "twoshot"
+    assert pick(l2, 8, "bf16", True) == "nvls"
+    assert pick(300_000, 8, "bf16", True) == "oneshot"          # 8 x 300k x 4 B exceeds the ingress bound, 600 KB wire is small
+    assert pick(tail, 8, "fp32", True) == "oneshot"             # LL words carry bf16 pairs only
+    assert pick(16, 8, "bf16", False) == "ll"
+
+
+def test_symmetric_heap_virtual_ranks_cpu():
+    from horizonml_b200.parallel.symm import SymmHeap
+    heaps = SymmHeap.virtual(4, "cpu", 1 << 20)
+    assert [h.rank for h in heaps] == [0, 1, 2, 3] and all(h.world == 4 and not h.nvls for h in heaps)
+    assert all(h.ptrs == heaps[0].ptrs for h in heaps)          # everyone sees the same peer table
+    offs = [[h.alloc(1000), h.alloc(4096, align=4096), h.alloc(10)] for h in heaps]
+    assert all(o == offs[0] for o in offs), "allocation order defines the symmetric layout"
+    assert offs[0][0] % 1024 == 0 and offs[0][1] % 4096 == 0
+    t = heaps[1].tensor(offs[1][1], [2, 8, 2, 2], [32, 1, 16, 8], "bf16")     # channels_last [N,C,H,W] view
+    t.fill_(1.0)
+    raw = heaps[1].local[offs[1][1]: offs[1][1] + 128].view(torch.bfloat16)
+    assert float(raw.float().sum()) == 64.0 and float(heaps[0].local.float().sum()) == 0.0
+    with pytest.raises(MemoryError):
+        heaps[0].alloc(2 << 20)
+    assert heaps[0].describe()["provider"] == "local"
+
+
+def test_fused_tp_tile_counts():
+    """hz_tp_tiles (host code of csrc/tp_fused.cu): tiles = m-tiles x ceil(n_out / 64) x parity classes; the fused kernel
+    needs them co-resident (<= 148)."""
+    from horizonml_b200.ops import _ext
+    C = _ext.load(required=False)
+    if C is None:
+        pytest.skip("extension not built")
+    assert C.tp_tiles(0, [64, 32, 2, 2], 256, 1) == 2 * 4          # layer3 conv2 shard at W=8: 256 rows, 256 columns
+    assert C.tp_tiles(0, [64, 64, 1, 1], 512, 1) == 1 * 8          # layer4 conv2: 64 rows pad one 128-row tile
+    assert C.tp_tiles(1, [64, 128, 4, 4], 32, 2) == 2 * 2 * 4      # stride-2 dgrad: 4 parity classes of a 2x2 lattice
+    assert C.tp_tiles(1, [64, 256, 2, 2], 64, 2) == 1 * 4 * 4
+    assert C.tp_tiles(1, [64, 512, 1, 1], 64, 1) == 1 * 8
+    assert C.tp_tiles(0, [64, 32, 2, 2], 40, 1) == 2 * 1           # column counts round up to 64-wide tiles
+    assert C.tp_tiles(0, [4096, 64, 8, 8], 64, 1) == 2048          # reported; FusedTP.supported() rejects > 148
+
+
+def test_overlapped_pipeline_plan():
+    """Enqueue order of the overlapped 1F1B runner: every activation receive is posted before its forward and only
+    into a slot whose previous owner's backward has been enqueued; sends follow their producer; with the spare slot the
+    next receive is in flight while the stage computes."""
+    from horizonml_b200.parallel.pp import OverlappedPipelineRunner as R, one_f_one_b
+    for S in (2, 3, 4, 5):
+        for M in (1, 2, 4, 8):
+            for s in range(S):
+                ns = max(1, min(S - s + 1, M))
+                plan = R.plan(s, S, M, ns)
+                pos = {op: k for k, op in enumerate(plan)}
+                assert [op for op in plan if op[0] in "FB"] == one_f_one_b(s, S, M)
+                for i in range(M):
+                    if s > 0:
+                        assert pos[("recv_fwd", i)] < pos[("F", i)]
+                        if i >= ns:                                    # slot reuse: previous owner's backward first
+                            assert pos[("B", i - ns)] < pos[("recv_fwd", i)]
+                        assert pos[("send_bwd", i)] == pos[("B", i)] + 1
+                    else:
+                        assert ("recv_fwd", i) not in pos and ("send_bwd", i) not in pos
+                    if s < S - 1:
+                        assert pos[("send_fwd", i)] == pos[("F", i)] + 1 and pos[("recv_bwd", i)] < pos[("B", i)]
+                    else:
+                        assert ("send_fwd", i) not in pos and ("recv_bwd", i) not in pos
+                # the prefetch window exists: in steady state the next activation is already posted when F(i) is enqueued
+                if s > 0 and M > ns >= 2:
+                    i = ns - 1
+                    assert pos[("recv_fwd", i + 1)] < pos[("F", i + 1)]
+    # 4 stages, 4 micro-batches, first stage after the stem: 4 in flight + no spare needed (M == in-flight bound)
+    assert R.plan(1, 4, 4, 4)[:4] == [("recv_fwd", 0), ("recv_fwd", 1), ("recv_fwd", 2), ("recv_fwd", 3)]
+
+
+def test_split_compute_comm():
+    from horizonml_b200.trainers.common import split_compute_comm
+    c, m, src = split_compute_comm(10.0, {"fwd_ms": 0.25, "bwd_ms": 0.30, "optimizer_ms": 0.03, "exposed_comm_ms": 0.02,
+                                          "step_ms": 0.625})
+    assert abs(c - 4.0) < 1e-9 and abs(m - 6.0) < 1e-9 and src == "device-timed regions"
+    c, m, src = split_compute_comm(10.0, {})
+    assert (c, m) == (10.0, 0.0) and "unmeasured" in src
+    c, m, _ = split_compute_comm(2.0, {"fwd_ms": 0.2, "bwd_ms": 0.2})          # no step_ms: sum of the regions
+    assert abs(c - 1.0) < 1e-9 and abs(m - 1.0) < 1e-9
+
+
+def test_reference_arm_environment():
+    spec = importlib.util.spec_from_file_location("hz_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    base = {"RANK": "0", "WORLD_SIZE": "8", "LOCAL_RANK": "0", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29500",
+            "OMP_NUM_THREADS": "1", "TORCHELASTIC_RUN_ID": "x", "PATH": "/usr/bin", "PYTHONPATH": "/x"}
+    env, threads = bench.reference_env(base, 8)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        assert k not in env                                       # the reference does its own rendezvous
+    assert env["GLOO_SOCKET_IFNAME"] == "lo" and env["CUDA_VISIBLE_DEVICES"] == ""
+    assert env["OMP_NUM_THREADS"] == str(threads) and 1 <= threads <= 16
+    assert env["PYTHONPATH"].startswith(os.path.join(ROOT, "tools", "ref_shim")) and env["PATH"] == "/usr/bin"
+    assert "RANK" in base                                          # the caller's environment is not modified
