@@ -90,7 +90,13 @@ def _stable(w) -> bool:
     two kernels before any conv that reads it — the kernel may then request weight tiles before
     ``griddepcontrol.wait`` (programmatic dependent launch).  Anything else (casts, slices, padded copies) may have
     been produced by the immediately preceding kernel and is only read after the wait."""
-    return bool(getattr(w, "_hz_stable", False))
+    if not getattr(w, "_hz_stable", False):
+        return False
+    # Early launch is transitive (every kernel issues launch_dependents at its top), so in EAGER mode — warm-up steps,
+    # --no_cuda_graph, an off-size last batch — a conv of the next step could prefetch shadow weights while this step's
+    # Adam is still writing them.  Inside a captured graph the optimizer is always >= 2 kernels upstream of the first
+    # conv that reads a weight, within and across replays, so the prefetch is only enabled there (ADVICE r1).
+    return bool(w.is_cuda and torch.cuda.is_current_stream_capturing())
 
 
 def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):

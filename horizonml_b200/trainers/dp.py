@@ -313,7 +313,16 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
             print(f"Epoch [{epoch+1}/{cfg.epochs}], Loss: {loss:.4f}, Accuracy: {acc:.2f}%, "
                   f"Time: {epoch_time:.2f}s", flush=True)
         if cfg.profile and epoch == start_epoch and nsteps > 0:
+            # the profiled steps are real optimizer steps: snapshot the training state and put it back afterwards, so a
+            # profiled run trains (and checkpoints) exactly like an unprofiled one
+            state = eng._state_tensors()
+            snap, gs = [t.clone() for t in state], eng.global_step
             profile_steps(eng.step, x, y, f"{logs_dir}/profile_rank{rank}.json")
+            if cuda:
+                torch.cuda.synchronize()
+            for t, s_ in zip(state, snap):
+                t.copy_(s_)
+            eng.global_step = gs
         if cfg.save_dir and ((cfg.save_every and (epoch + 1) % cfg.save_every == 0) or epoch + 1 == cfg.epochs):
             # ZeRO-1: the moments are sharded — every rank takes part in gathering them, rank 0 writes the file
             optim_state = eng.opt.gather_state() if eng.zero1 else None
