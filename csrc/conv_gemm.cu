@@ -729,7 +729,7 @@ int pick_cluster_splits(int tiles, int k_total, int (*max_clusters)(int)) {
   if (off || tiles <= 0 || k_total < min_k) return 1;
   static const bool one_wave = [] { const char* e = getenv("HZ_CLUSTER_ONE_WAVE"); return !(e && e[0] == '0'); }();
   int s = 8;
-  while (s > 1 && (tiles * s > 148 || k_total / s < min_per || (one_wave && tiles > max_clusters(s)))) s >>= 1;
+  while (s > 1 && (tiles * s > hz_num_sms() || k_total / s < min_per || (one_wave && tiles > max_clusters(s)))) s >>= 1;
   return s;
 }
 

@@ -154,6 +154,16 @@ inline void input_taps(hz::TapList* tl, int R, int S, int stride, int pad, int H
 }
 
 
+// SM count of the current device (co-residency bound of kernels whose CTAs wait for each other / for peers)
+inline int num_sms() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
 template <typename K>
 inline bool set_smem(K kernel, int bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;

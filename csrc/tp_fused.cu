@@ -806,7 +806,7 @@ int hz_tp_conv(int kind, const void* const* x_ptrs, const void* w, void* out, co
   const int classes = (kind == 1 && stride == 2) ? 4 : 1;
   const int n_tiles = (Nn + 63) / 64;
   const int tiles = t.tiles * n_tiles * classes;
-  if (tiles > 148) return -21;                 // all CTAs must be co-resident (they spin on peers)
+  if (tiles > num_sms()) return -21;           // all CTAs must be co-resident (they spin on peers)
   if (mode == 2 && tiles < world) return -24;  // reduce-scatter: every rank must own a tile (keeps ranks in step)
   const int imgs_per_rank = ag ? N / world : N;
   if (ag && (kind != 0 || N % world || (t.BN > 1 && imgs_per_rank % t.BN))) return -22;
@@ -895,7 +895,7 @@ int hz_tp_head(const void* feat, const float* Wl, const float* bl, const int64_t
   p.par_stride_dfeat = (long long)world * N * C * 8;
   p.epoch = epoch;
   p.timeout_clk = tp_timeout_clk();
-  if (N > 148) return -21;
+  if (N > num_sms()) return -21;
   const size_t smem = sizeof(float) * (C + 2 * p.K);
   return hz::launch(hz::tp_head_kernel, dim3(N), dim3(128), smem, st, (const __nv_bfloat16*)feat, Wl, bl, labels,
                     pooled, dl_local, logits, (__nv_bfloat16*)dfeat, loss, correct, p) == cudaSuccess ? 0 : -1;

@@ -111,6 +111,9 @@ class FusedTP:
         self.group = group
         self.world, self.rank = self.heap.world, self.heap.rank
         self.nvls = self.heap.nvls
+        # CTAs of a fused kernel wait for their peers: the whole grid has to be resident at once
+        self.max_tiles = (torch.cuda.get_device_properties(self.device).multi_processor_count
+                          if self.device.type == "cuda" and torch.cuda.is_available() else 148)
         self.proto = os.environ.get("HZ_TP_PROTO", proto)      # auto | ll | bw
         self.bytes_moved = 0
         self.ops: List[dict] = []
@@ -126,7 +129,7 @@ class FusedTP:
         if cin % 8 or cout % 8 or (kind == 0 and stride != 1) or (stride == 2 and (h % 2 or w % 2)):
             return False
         t = self.tiles_for(kind, x_shape, cout, stride)
-        return t is not None and t <= 148
+        return t is not None and t <= self.max_tiles
 
     def _use_ll(self, tiles) -> bool:
         if self.proto in ("ll", "bw"):
@@ -143,7 +146,7 @@ class FusedTP:
         h = self.heap
         cout = w_shape[0]
         tiles = self.tiles_for(kind, x_shape, cout, stride)
-        if tiles is None or tiles > 148:
+        if tiles is None or tiles > self.max_tiles:
             raise ValueError(f"fused TP conv does not fit: {x_shape} -> {cout}, tiles={tiles}")
         m = {"none": 0, "allreduce": 1, "reduce_scatter": 2}[mode]
         if m == 2 and tiles < self.world:
@@ -429,7 +432,7 @@ class TensorParallelResNet(nn.Module):
             return None
         n, c = f.shape[0], f.shape[1]
         kl = self.fc_weight.shape[0]
-        if n > 148 or c % 4 or kl > 16 or kl * self.comm.world > 64 or self.fc_weight.dtype != torch.float32:
+        if n > fz.max_tiles or c % 4 or kl > 16 or kl * self.comm.world > 64 or self.fc_weight.dtype != torch.float32:
             return None
         key = (n, c)
         if key not in self._heads:

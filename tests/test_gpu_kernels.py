@@ -462,3 +462,35 @@ def test_allreduce_adam_fused_virtual_ranks(nb, world, algo):
             assert torch.equal(gA[r], gB[r])                                   # live blocks cleared, dead ones untouched
             assert abs(A["diff"][r].item() - B["diff"][r].item()) <= 1e-4 * abs(B["diff"][r].item()) + 1e-6
             A["diff"][r].zero_()          # (the stats kernel consumes and clears the accumulator once per step)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "ll"])
+def test_peer_allreduce_alternating_grid_sizes_with_skewed_rank(nb, world, algo):
+    """Back-to-back collectives of very different sizes (1 .. 16 blocks) on one communicator while one rank lags: the
+    staging / out / LL-slot parity comes from ONE per-communicator call counter, so a block that did not exist in the
+    previous (smaller) call cannot reuse that call's buffers while a slow peer still reads them (the
+    per-block counters of round 1 could)."""
+    C = nb.C
+    nmax = 1 << 18
+    comms = [C.PeerComm(r, world, 0, nmax * 4, 16) for r in range(world)]
+    C.PeerComm.link_local(comms)
+    g = torch.Generator().manual_seed(3)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    sizes = [nmax, 1024, 1 << 16, 64, nmax, 4096, 1 << 17, 64]
+    grads = {n: [torch.randn(n, generator=g).to(DEV) for _ in range(world)] for n in set(sizes)}
+    refs = {n: sum((x * (1.0 / world)).bfloat16().float() for x in grads[n]) for n in grads}
+    works = [[grads[n][r].clone() for n in sizes] for r in range(world)]
+    torch.cuda.synchronize()
+    for r in range(world):
+        with torch.cuda.stream(streams[r]):
+            for k, n in enumerate(sizes):
+                if k % world == r:
+                    torch.cuda._sleep(1_500_000)            # this rank arrives ~0.8 ms late at call k
+                comms[r].allreduce(works[r][k], algo, True, 1.0 / world)
+    torch.cuda.synchronize()
+    assert not any(c.error() for c in comms)
+    for k, n in enumerate(sizes):
+        for r in range(world):
+            assert rel_err(works[r][k], refs[n]) < 1e-2, (k, n, r)
+            assert torch.equal(works[r][k], works[0][k])
