@@ -1,0 +1,138 @@
+"""Executable models of the peer-memory protocols (SURVEY §5.2 "race detection"): the buffer-reuse arguments of
+csrc/comm.cu and csrc/tp_fused.cu checked under randomly interleaved schedules on the CPU.
+
+The kernels synchronise GPUs with nothing but words in memory, so their safety arguments are about *which call may
+still be reading a buffer when a later call overwrites it*.  compute-sanitizer cannot see across processes, and a
+hazard window of a few hundred nanoseconds does not show up in functional tests; a small model that explores
+arbitrary rank / block skew does.  Two models:
+
+* ``simulate_ll``      — the flag-in-data ("LL") protocol of the gradient all-reduce's last bucket, the fused
+  tensor-parallel GEMM+all-reduce, the TP head and the small bf16 all-reduce: every call pushes {data, epoch} words into
+  slot ``[parity][me]`` of every rank and polls its own slots.  Claim: with two parities a word is never overwritten
+  while a reader of an earlier call still waits for it, and no schedule deadlocks; with ONE buffer it is overwritten —
+  the model finds that.
+* ``simulate_staged``  — the staged (pack → block barrier → reduce) one-shot all-reduce with grids of different size
+  back to back.  Claim: taking the buffer parity from ONE per-communicator call counter is
+  safe; the round-1 scheme (a counter per block index) lets a block that did not exist in the previous, smaller call
+  reuse that call's parity and overwrite a region a slow peer is still reading — the model reproduces that hazard.
+
+Both return the number of schedules (out of ``trials``) in which a violation was observed.  Stores of one phase land in
+any order (GPU stores are unordered without fences); the kernels of one rank run in stream order; blocks of one kernel
+run concurrently; the scheduler is uniformly random over everything that can make a step."""
+from __future__ import annotations
+
+import random
+from typing import Dict, List, Sequence
+
+
+# ----------------------------------------------------------------------------------------------------------
+# flag-in-data protocol
+# ----------------------------------------------------------------------------------------------------------
+def simulate_ll(world: int = 3, calls: int = 6, words: int = 3, parities: int = 2, trials: int = 200, seed: int = 0,
+                max_steps: int = 200_000) -> int:
+    """Violation = a rank polling for epoch ``e`` finds a NEWER epoch in the word (its data was overwritten before it
+    was read — the real kernel would spin until its timeout), reads a payload that does not belong to ``e``, or the
+    system stops making progress."""
+    rng = random.Random(seed)
+    bad = 0
+    for _ in range(trials):
+        slots = [[[[(0, 0)] * words for _ in range(world)] for _ in range(parities)] for _ in range(world)]   # [dst][par][src][w]
+        state = [{"call": 1, "stores": [(d, w) for d in range(world) for w in range(words)], "reads": None} for _ in range(world)]
+        live = list(range(world))
+        violated, steps = False, 0
+        while live and not violated:
+            steps += 1
+            if steps > max_steps:
+                violated = True                              # nobody can finish: deadlock
+                break
+            r = rng.choice(live)
+            st = state[r]
+            e = st["call"]
+            par = e % parities
+            if st["stores"]:
+                dst, w = st["stores"].pop(rng.randrange(len(st["stores"])))
+                slots[dst][par][r][w] = (e, e)               # {epoch, payload} travel in one atomic word
+                if not st["stores"]:
+                    st["reads"] = [(s, w2) for s in range(world) for w2 in range(words)]
+                continue
+            s, w = st["reads"][0]
+            ep, payload = slots[r][par][s][w]
+            if ep > e or (ep == e and payload != e):
+                violated = True
+            elif ep == e:                                    # the poll succeeds (else: keep spinning)
+                st["reads"].pop(0)
+                if not st["reads"]:
+                    st["call"] += 1
+                    if st["call"] > calls:
+                        live.remove(r)
+                    else:
+                        st["stores"] = [(d, w2) for d in range(world) for w2 in range(words)]
+        bad += 1 if violated else 0
+    return bad
+
+
+# ----------------------------------------------------------------------------------------------------------
+# staged all-reduce with varying grid sizes
+# ----------------------------------------------------------------------------------------------------------
+def _make_blocks(grid: int, region: int, parity_of) -> List[Dict]:
+    per = (region + grid - 1) // grid
+    blocks = []
+    for b in range(grid):
+        lo, hi = min(b * per, region), min(b * per + per, region)
+        blocks.append({"id": b, "range": list(range(lo, hi)), "parity": parity_of(b), "phase": "pack",
+                       "todo": list(range(lo, hi))})
+    return blocks
+
+
+def simulate_staged(grids: Sequence[int], world: int = 2, region: int = 12, per_block_parity: bool = False,
+                    trials: int = 300, seed: int = 0) -> int:
+    """One-shot flavour: in call ``k`` (grid ``grids[k]``) block ``b`` of every rank packs its share of ``region`` words
+    into the rank's ``stage[parity]``, meets block ``b`` of every peer at a barrier, then reads the same share from every
+    peer's ``stage[parity]`` — no trailing barrier.  Violation = a block reads a word that was not written by the call
+    it belongs to."""
+    rng = random.Random(seed)
+    bad = 0
+    ncalls, gmax = len(grids), max(grids)
+    for _ in range(trials):
+        stage = [[[-1] * region for _ in range(2)] for _ in range(world)]            # stage[rank][parity][word] = call id
+        calls_done = [0] * world                                                     # ONE counter per communicator
+        block_calls = [[0] * gmax for _ in range(world)]                             # round 1: one counter per block index
+        arrived = [[[False] * world for _ in range(gmax)] for _ in range(ncalls)]    # barrier flags [call][block][rank]
+        cur = [0] * world
+
+        def parity_fn(r):
+            return (lambda b: block_calls[r][b] & 1) if per_block_parity else (lambda b: calls_done[r] & 1)
+
+        blocks = [_make_blocks(grids[0], region, parity_fn(r)) for r in range(world)]
+        violated = False
+        while not violated and any(c < ncalls for c in cur):
+            r = rng.choice([q for q in range(world) if cur[q] < ncalls])
+            k = cur[r]
+            b = rng.choice([x for x in blocks[r] if x["phase"] != "done"])
+            if b["phase"] == "pack":
+                if b["todo"]:
+                    w = b["todo"].pop(rng.randrange(len(b["todo"])))
+                    stage[r][b["parity"]][w] = k
+                if not b["todo"]:
+                    arrived[k][b["id"]][r] = True                                    # flag published after the block's stores
+                    b["phase"] = "barrier"
+            elif b["phase"] == "barrier":
+                if all(arrived[k][b["id"]]):
+                    b["phase"], b["todo"] = "read", [(s, w) for s in range(world) for w in b["range"]]
+                    if not b["todo"]:
+                        b["phase"] = "done"
+                        block_calls[r][b["id"]] += 1
+            else:
+                s, w = b["todo"].pop(rng.randrange(len(b["todo"])))
+                if stage[s][b["parity"]][w] != k:
+                    violated = True
+                if not b["todo"]:
+                    b["phase"] = "done"
+                    block_calls[r][b["id"]] += 1
+            if all(x["phase"] == "done" for x in blocks[r]):                         # kernel complete: the next call may start
+                calls_done[r] += 1
+                cur[r] += 1
+                if cur[r] < ncalls:
+                    blocks[r] = _make_blocks(grids[cur[r]], region, parity_fn(r))
+        bad += 1 if violated else 0
+    return bad

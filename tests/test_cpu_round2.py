@@ -142,3 +142,21 @@ def test_reference_arm_environment():
     assert env["OMP_NUM_THREADS"] == str(threads) and 1 <= threads <= 16
     assert env["PYTHONPATH"].startswith(os.path.join(ROOT, "tools", "ref_shim")) and env["PATH"] == "/usr/bin"
     assert "RANK" in base                                          # the caller's environment is not modified
+
+
+def test_protocol_models_buffer_reuse():
+    """The buffer-reuse arguments of the peer-memory kernels under random rank / block skew (utils/protocol_model.py):
+    the shipped schemes never let a call overwrite what an earlier call still reads; the schemes they replaced do."""
+    from horizonml_b200.utils.protocol_model import simulate_ll, simulate_staged
+    # flag-in-data protocol: two parity slots are enough (every call is an all-to-all dependency) ...
+    assert simulate_ll(world=3, calls=6, words=3, parities=2, trials=150, seed=1) == 0
+    assert simulate_ll(world=8, calls=4, words=2, parities=2, trials=30, seed=2) == 0
+    # ... one buffer is not: the checker has teeth
+    assert simulate_ll(world=3, calls=6, words=3, parities=1, trials=150, seed=1) > 100
+    # staged all-reduce, grids of different size back to back (1 .. 4 blocks): per-communicator parity is safe,
+    # round 1's per-block parity is the hazard the advisor described
+    grids = [1, 3, 3, 1, 4, 2, 4, 4]
+    assert simulate_staged(grids, world=2, per_block_parity=False, trials=200, seed=3) == 0
+    assert simulate_staged(grids, world=4, per_block_parity=False, trials=60, seed=4) == 0
+    assert simulate_staged(grids, world=2, per_block_parity=True, trials=200, seed=3) > 50
+    assert simulate_staged([3, 3, 3, 3], world=2, per_block_parity=True, trials=100, seed=5) == 0   # equal grids were always fine
