@@ -1,42 +1,163 @@
-"""MobileNetV2 — only reachable through the legacy container entrypoint (reference train.py:60-68,
-``MODEL_TYPE=mobilenet``).  It is a library model (torchvision graph, cuDNN/ATen kernels under
-autocast) adapted to the engine's ``forward_loss`` contract; the hand-written kernel path is
-ResNet-18, the model every benchmarked reference script uses."""
+"""MobileNetV2 on the framework's op set (reference: ``torchvision.models.mobilenet_v2`` behind the legacy container
+entrypoint, train.py:60-68, ``MODEL_TYPE=mobilenet``).
+
+Parameter / buffer names and shapes are torchvision's (``features.N.conv.M…``, ``classifier.1.*``), so state dicts are
+interchangeable.  What runs where:
+
+* every **1×1 convolution** (expand, project, the 320→1280 head conv — ~95 % of the model's FLOPs) goes through
+  ``ops.conv_bn_act``: conv → BatchNorm(batch stats) → [+residual] → [ReLU], i.e. on a B200 the tcgen05 implicit-GEMM
+  kernels (channel counts only need to be multiples of 8: the TMA zero-fill rule introduced for tensor-parallel
+  shards) with the BN statistics in the conv epilogue and gradients written straight into the flat buckets.  ReLU6 is
+  ReLU (fused) followed by a clamp.  BatchNorm kernels take the native path where the channel count is 8·2^k and the
+  PyTorch-op path otherwise (counted in ``native_backend.FALLBACKS``);
+* the **depthwise 3×3 convolutions** and the 3-channel stem run on PyTorch ops (cuDNN on GPUs) with plain autograd — a
+  depthwise tcgen05 kernel makes no sense (K = 9) and a hand-written SIMT one is not written yet; their gradients reach
+  the flat store through ``FlatParams``' autograd bridge;
+* the classifier (dropout → avg-pool → FC → CE) is ``ops.head_loss``.
+
+ResNet-18 stays the benchmarked model (every reference trainer uses it); this makes ``MODEL_TYPE=mobilenet`` a real
+model on the same engine (flat parameters, fused Adam, fused all-reduce) instead of a torchvision + autocast adapter."""
 from __future__ import annotations
 
-from typing import Optional
+from typing import List, Optional
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
+from .resnet import BNP, ConvW
 
-class LibraryModelAdapter(nn.Module):
-    def __init__(self, net: nn.Module, num_classes: int):
+# (expand ratio t, output channels c, repeats n, stride s) — torchvision.models.mobilenetv2
+_SETTING = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
+
+
+class DWConvW(nn.Module):
+    """Depthwise 3×3 weight [C, 1, 3, 3] (torchvision's ``Conv2d(C, C, 3, groups=C)``)."""
+
+    def __init__(self, c: int, stride: int):
         super().__init__()
-        self.net, self.num_classes = net, num_classes
+        w = torch.empty(c, 1, 3, 3)
+        nn.init.kaiming_normal_(w, mode="fan_out")
+        self.weight = nn.Parameter(w)
+        self.stride, self.c = stride, c
+
+
+def _relu6_cap(x):
+    return torch.clamp(x, max=6.0)
+
+
+def _pw(x, conv: ConvW, bn: BNP, relu6: bool, residual=None, training=True):
+    """1×1 conv → BN → [+residual] → [ReLU6] on the fused op (native tcgen05 path on GPUs)."""
+    y = ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, stride=1, pad=0,
+                        relu=relu6, residual=residual, momentum=bn.momentum, eps=bn.eps, training=training)
+    return _relu6_cap(y) if relu6 else y
+
+
+def _dw(x, conv: nn.Module, bn: BNP, training=True, groups: Optional[int] = None, pad: int = 1):
+    """k×k conv (depthwise, or the dense 3-channel stem) → BN → ReLU6 with PyTorch ops / plain autograd."""
+    w = conv.weight.to(x.dtype)                                  # differentiable cast: the gradient reaches the fp32 master
+    y = F.conv2d(x, w, None, conv.stride, pad, 1, groups if groups is not None else 1)
+    y = F.batch_norm(y.to(torch.promote_types(y.dtype, torch.float32)), bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                     training, bn.momentum, bn.eps)
+    return F.relu6(y).to(x.dtype).contiguous(memory_format=torch.channels_last)
+
+
+class _CNA(nn.Sequential):
+    """torchvision's Conv2dNormActivation as a parameter container: [0] conv weight holder, [1] BN."""
+
+    def __init__(self, conv: nn.Module, bn: BNP):
+        super().__init__(conv, bn)
+
+
+class InvertedResidual(nn.Module):
+    def __init__(self, inp: int, oup: int, stride: int, t: int):
+        super().__init__()
+        hidden = inp * t
+        self.use_res = stride == 1 and inp == oup
+        self.expand = t != 1
+        layers: List[nn.Module] = []
+        if self.expand:
+            layers.append(_CNA(ConvW(inp, hidden, 1, 1, 0), BNP(hidden)))
+        layers.append(_CNA(DWConvW(hidden, stride), BNP(hidden)))
+        layers.append(ConvW(hidden, oup, 1, 1, 0))
+        layers.append(BNP(oup))
+        self.conv = nn.Sequential(*layers)
 
     def forward(self, x):
-        return self.net(x)
+        t = self.training
+        i = 0
+        y = x
+        if self.expand:
+            y = _pw(y, self.conv[0][0], self.conv[0][1], True, training=t)
+            i = 1
+        y = _dw(y, self.conv[i][0], self.conv[i][1], t, groups=self.conv[i][0].c)
+        return _pw(y, self.conv[i + 1], self.conv[i + 2], False, residual=x if self.use_res else None, training=t)
+
+
+class _StemConv(nn.Module):
+    def __init__(self):
+        super().__init__()
+        w = torch.empty(32, 3, 3, 3)
+        nn.init.kaiming_normal_(w, mode="fan_out")
+        self.weight = nn.Parameter(w)
+        self.stride = 2
+
+
+class MobileNetV2(nn.Module):
+    def __init__(self, num_classes: int = 10, dropout: float = 0.2):
+        super().__init__()
+        feats: List[nn.Module] = [_CNA(_StemConv(), BNP(32))]
+        inp = 32
+        for t, c, n, s in _SETTING:
+            for i in range(n):
+                feats.append(InvertedResidual(inp, c, s if i == 0 else 1, t))
+                inp = c
+        feats.append(_CNA(ConvW(inp, 1280, 1, 1, 0), BNP(1280)))
+        self.features = nn.Sequential(*feats)
+        fc = nn.Linear(1280, num_classes)
+        nn.init.normal_(fc.weight, 0, 0.01)
+        nn.init.zeros_(fc.bias)
+        self.classifier = nn.Sequential(nn.Dropout(dropout), fc)
+        self.num_classes, self.dropout = num_classes, dropout
+        for m in self.modules():                                  # torchvision init: BN weight 1 / bias 0 (BNP default)
+            if isinstance(m, ConvW):
+                nn.init.kaiming_normal_(m.weight.data, mode="fan_out")
+
+    def feature_map(self, x):
+        t = self.training
+        x = x.contiguous(memory_format=torch.channels_last)
+        y = _dw(x, self.features[0][0], self.features[0][1], t, groups=1)
+        for blk in list(self.features)[1:-1]:
+            y = blk(y)
+        return _pw(y, self.features[-1][0], self.features[-1][1], True, training=t)
+
+    def _pooled(self, x):
+        fm = self.feature_map(x)
+        f = fm.to(torch.promote_types(fm.dtype, torch.float32)).mean(dim=(2, 3))
+        if self.training and self.dropout > 0:
+            f = F.dropout(f, self.dropout, True)
+        return f
+
+    def forward(self, x):
+        """images → logits [N, num_classes]"""
+        f = self._pooled(x)
+        fc = self.classifier[1]
+        return F.linear(f, fc.weight.to(f.dtype), fc.bias.to(f.dtype))
 
     def forward_loss(self, x, labels, loss_scale: float = 1.0, stats_out: Optional[dict] = None):
-        if x.is_cuda:
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                logits = self.net(x.float())
-        else:
-            logits = self.net(x.float())
-        logits = logits.float()
-        loss = F.cross_entropy(logits, labels) * loss_scale
-        correct = (logits.argmax(1) == labels).sum().float()
-        return loss, correct
+        f = self._pooled(x)
+        fc = self.classifier[1]
+        feat = f.to(x.dtype if x.dtype != torch.uint8 else torch.float32).view(f.shape[0], f.shape[1], 1, 1)
+        feat = feat.contiguous(memory_format=torch.channels_last)
+        return ops.head_loss(feat, fc.weight, fc.bias, labels, loss_scale, n_valid=self.num_classes, stats_out=stats_out)
 
 
-def mobilenet_v2(num_classes: int = 10, seed: Optional[int] = None) -> LibraryModelAdapter:
-    import torchvision
+def mobilenet_v2(num_classes: int = 10, seed: Optional[int] = None, dropout: float = 0.2) -> MobileNetV2:
     if seed is not None:
         st = torch.random.get_rng_state()
         torch.manual_seed(seed)
-    net = torchvision.models.mobilenet_v2(weights=None, num_classes=num_classes)
+    m = MobileNetV2(num_classes, dropout)
     if seed is not None:
         torch.random.set_rng_state(st)
-    return LibraryModelAdapter(net, num_classes)
+    return m

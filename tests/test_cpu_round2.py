@@ -160,3 +160,63 @@ def test_protocol_models_buffer_reuse():
     assert simulate_staged(grids, world=4, per_block_parity=False, trials=60, seed=4) == 0
     assert simulate_staged(grids, world=2, per_block_parity=True, trials=200, seed=3) > 50
     assert simulate_staged([3, 3, 3, 3], world=2, per_block_parity=True, trials=100, seed=5) == 0   # equal grids were always fine
+
+
+def test_mobilenet_v2_matches_torchvision():
+    """MobileNetV2 on the framework's op set (legacy MODEL_TYPE=mobilenet path): torchvision's names / shapes /
+    buffers, identical logits in eval mode, same loss and gradients in train mode (dropout off) — gradients compared by
+    cosine: a project-BN bias that feeds another conv+BN has a mathematically zero gradient, i.e. pure rounding noise in
+    both implementations."""
+    import torchvision
+    import torch.nn.functional as F
+    from horizonml_b200 import ops
+    from horizonml_b200.models.mobilenet import mobilenet_v2
+    ops.set_backend("torch")
+    torch.manual_seed(0)
+    ref = torchvision.models.mobilenet_v2(weights=None, num_classes=10)
+    ref.classifier[0].p = 0.0
+    mine = mobilenet_v2(10, seed=1, dropout=0.0)
+    assert [(n, tuple(p.shape)) for n, p in ref.named_parameters()] == [(n, tuple(p.shape)) for n, p in mine.named_parameters()]
+    assert [(n, tuple(b.shape)) for n, b in ref.named_buffers()] == [(n, tuple(b.shape)) for n, b in mine.named_buffers()]
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(32, 3, 32, 32)
+    y = torch.randint(0, 10, (32,))
+    ref.eval(); mine.eval()
+    with torch.no_grad():
+        assert torch.allclose(ref(x), mine(x), atol=1e-5)
+    ref.train(); mine.train()
+    lr = F.cross_entropy(ref(x), y)
+    lr.backward()
+    lm, correct = mine.forward_loss(x.contiguous(memory_format=torch.channels_last), y)
+    lm.backward()
+    assert abs(lr.item() - lm.item()) < 1e-4 and 0 <= correct.item() <= 32
+    gr = dict(ref.named_parameters())
+    for n, p in mine.named_parameters():
+        assert p.grad is not None, n
+        if p.dim() == 4 or n.startswith("classifier") or (p.dim() == 1 and n.endswith(".weight")):
+            c = F.cosine_similarity(p.grad.flatten(), gr[n].grad.flatten(), dim=0).item()
+            assert c > 0.999, (n, c)
+
+
+def test_mobilenet_trains_through_the_dp_engine():
+    """Flat parameter store + fused Adam + the autograd bridge (depthwise / stem parameters get plain ``.grad``s, the
+    1x1 convs write straight into the flat buckets) on the CPU path: a few steps on one batch must fit it."""
+    from horizonml_b200 import ops
+    from horizonml_b200.config import TrainConfig
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.dp import DPEngine
+    ops.set_backend("torch")
+    cfg = TrainConfig(strategy="data", world_size=1, batch_size=16, device="cpu", dtype="fp32", backend="torch",
+                      model="mobilenet", quiet=True, cuda_graph=False)
+    eng = DPEngine(cfg, Runtime(0, 1, torch.device("cpu"), torch.float32, "torch", "none"))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(16, 3, 32, 32, generator=g).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), generator=g)
+    losses, prev = [], 0.0
+    for _ in range(6):
+        eng.step(x, y)
+        cur = eng.stats.buf[0].item()
+        losses.append(cur - prev)
+        prev = cur
+    assert len(eng.flat.params) == 158
+    assert losses[-1] < 0.5 * losses[0], losses
