@@ -17,6 +17,9 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
     config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
     config.addinivalue_line("markers", "slow: multi-process CPU tests")
+    config.addinivalue_line("markers", "late: GPU test (or parameter set) written after the round's GPU budget was spent, i.e. "
+                                       "never executed on hardware by the author — collected last, so that under "
+                                       "`-x` a failure there cannot hide the hardware-verified tests")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -28,3 +31,5 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
         if "multigpu" in item.keywords and ngpu < 2:
             item.add_marker(pytest.mark.skip(reason="needs >= 2 GPUs"))
+    # stable partition: everything hardware-verified first, the `late` items after it (see the marker's description)
+    items.sort(key=lambda it: 1 if "late" in it.keywords else 0)

@@ -311,8 +311,11 @@ def test_adam_and_allreduce_skip_dead_blocks(nb):
             assert torch.equal(work[r][~emask], grads[r][~emask])             # dead blocks never touched
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "ll"])
+_LATE = pytest.mark.late      # parameter sets / tests added after the last 1-GPU run of this file (tests/conftest.py)
+
+
+@pytest.mark.parametrize("world", [2, 4, pytest.param(8, marks=_LATE)])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", pytest.param("ll", marks=_LATE)])
 @pytest.mark.parametrize("wire_bf16", [True, False])
 def test_peer_allreduce_virtual_ranks(nb, world, algo, wire_bf16):
     """Multi-rank protocol (flags, parity, slices; flag-in-data words for "ll") exercised with `world` virtual ranks on
@@ -406,7 +409,7 @@ def test_cuda_graph_step(nb):
 
 
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "ll"])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", pytest.param("ll", marks=_LATE)])
 def test_allreduce_adam_fused_virtual_ranks(nb, world, algo):
     """All-reduce with the Adam update fused into its final phase == all-reduce kernel followed by the Adam kernel
     (same fp32 values feed the same arithmetic), over dead-block-compacted buckets, 3 optimizer steps,
@@ -464,6 +467,7 @@ def test_allreduce_adam_fused_virtual_ranks(nb, world, algo):
             A["diff"][r].zero_()          # (the stats kernel consumes and clears the accumulator once per step)
 
 
+@pytest.mark.late
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("algo", ["oneshot", "twoshot", "ll"])
 def test_peer_allreduce_alternating_grid_sizes_with_skewed_rank(nb, world, algo):
