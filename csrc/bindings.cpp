@@ -55,8 +55,8 @@ Tensor channel_sums(const Tensor& y) {
 
 std::vector<Tensor> bn_act_fwd(const Tensor& y, const Tensor& sums, const Tensor& gamma, const Tensor& beta,
                                const c10::optional<Tensor>& rmean, const c10::optional<Tensor>& rvar,
-                               double momentum, double eps, const c10::optional<Tensor>& residual, bool relu,
-                               bool training) {
+                               double momentum, double eps, const c10::optional<Tensor>& residual, int64_t relu,
+                               bool training) {   // relu: 0 none, 1 ReLU, 2 ReLU6
   check_cl(y, "y");
   c10::cuda::CUDAGuard g(y.device());
   auto d = dims_of(y);
@@ -67,13 +67,13 @@ std::vector<Tensor> bn_act_fwd(const Tensor& y, const Tensor& sums, const Tensor
   if (residual.has_value() && residual->defined()) { check_cl(*residual, "residual"); res = residual->data_ptr(); }
   hz_bn_act_fwd(cptr(y), sums.data_ptr<float>(), gamma.data_ptr<float>(), beta.data_ptr<float>(), res,
                 out.data_ptr(), mean.data_ptr<float>(), invstd.data_ptr<float>(), fptr(rmean), fptr(rvar),
-                d.N * d.H * d.W, d.C, (float)eps, (float)momentum, relu ? 1 : 0, training ? 1 : 0, cur_stream());
+                d.N * d.H * d.W, d.C, (float)eps, (float)momentum, (int)relu, training ? 1 : 0, cur_stream());
   return {out, mean, invstd};
 }
 
 // writes dgamma/dbeta straight into their gradient slots
 std::vector<Tensor> bn_act_bwd(const Tensor& dout, const Tensor& out, const Tensor& yraw, const Tensor& mean,
-                               const Tensor& invstd, const Tensor& gamma, bool relu, bool has_res,
+                               const Tensor& invstd, const Tensor& gamma, int64_t relu, bool has_res,
                                Tensor dgamma, Tensor dbeta, bool acc_gamma, bool acc_beta,
                                c10::optional<Tensor> zeroed_scratch) {
   check_cl(dout, "dout"); check_cl(yraw, "yraw");
@@ -87,7 +87,7 @@ std::vector<Tensor> bn_act_bwd(const Tensor& dout, const Tensor& out, const Tens
   hz_bn_act_bwd(cptr(dout), cptr(out), cptr(yraw), mean.data_ptr<float>(), invstd.data_ptr<float>(),
                 gamma.data_ptr<float>(), scratch.data_ptr<float>(), dy.data_ptr(),
                 has_res ? dres.data_ptr() : nullptr, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
-                acc_gamma ? 1 : 0, acc_beta ? 1 : 0, d.N * d.H * d.W, d.C, relu ? 1 : 0,
+                acc_gamma ? 1 : 0, acc_beta ? 1 : 0, d.N * d.H * d.W, d.C, (int)relu,
                 pre ? (scratch.numel() >= 2 * d.C + 32 ? 2 : 1) : 0, cur_stream());
   return {dy, dres};
 }
@@ -151,6 +151,61 @@ std::vector<Tensor> stem_pack(const Tensor& x, const Tensor& w2d, int64_t R, int
     hz_pad_rows(cptr(w2d), wp.data_ptr(), (int)w2d.size(0), (int)w2d.size(1), (int)Kp, cur_stream());
   }
   return {A, wp};
+}
+
+// ------------------------------------------------------------------ depthwise 3x3 convolution (csrc/depthwise.cu)
+// w: bf16 [C,1,3,3] (C*9 contiguous elements); stats_pre: optional pre-zeroed [2,C] fp32 slice of the statistics arena
+void check_dw_weight(const Tensor& w, int C) {
+  TORCH_CHECK(w.is_cuda() && w.scalar_type() == at::kBFloat16 && w.numel() == (int64_t)C * 9 && w.dim() == 4 &&
+              w.size(0) == C && w.stride(0) == 9 && w.stride(2) == 3 && w.stride(3) == 1,
+              "depthwise weight must be bf16 [C,1,3,3] with C*9 contiguous elements");
+}
+std::vector<Tensor> dwconv_fwd(const Tensor& x, const Tensor& w, int64_t stride, bool want_stats,
+                               c10::optional<Tensor> stats_pre) {
+  check_cl(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  auto d = dims_of(x);
+  check_dw_weight(w, d.C);
+  TORCH_CHECK(hz_dwconv_ok(d.N, d.H, d.W, d.C, (int)stride), "dwconv_fwd: unsupported shape");
+  const int Ho = (d.H - 1) / (int)stride + 1, Wo = (d.W - 1) / (int)stride + 1;
+  Tensor y = empty_cl(x, d.N, d.C, Ho, Wo);
+  Tensor stats;
+  const bool pre = want_stats && stats_pre.has_value() && stats_pre->defined();
+  if (want_stats) stats = pre ? *stats_pre : at::empty({2, d.C}, x.options().dtype(at::kFloat));
+  if (pre) TORCH_CHECK(stats.numel() == 2 * d.C && stats.scalar_type() == at::kFloat && stats.is_contiguous());
+  int rc = hz_dwconv_fwd(cptr(x), cptr(w), y.data_ptr(), want_stats ? stats.data_ptr<float>() : nullptr, pre ? 1 : 0,
+                         d.N, d.H, d.W, d.C, (int)stride, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_dwconv_fwd failed rc=", rc);
+  return {y, stats};
+}
+
+Tensor dwconv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride) {
+  check_cl(dy, "dy");
+  c10::cuda::CUDAGuard g(dy.device());
+  const int N = (int)x_shape[0], Cc = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
+  check_dw_weight(w, Cc);
+  TORCH_CHECK(hz_dwconv_ok(N, H, W, Cc, (int)stride), "dwconv_dgrad: unsupported shape");
+  TORCH_CHECK(dy.size(0) == N && dy.size(1) == Cc && dy.size(2) == (H - 1) / stride + 1 && dy.size(3) == (W - 1) / stride + 1,
+              "dwconv_dgrad: dy does not match x_shape / stride");
+  Tensor dx = empty_cl(dy, N, Cc, H, W);
+  int rc = hz_dwconv_dgrad(cptr(dy), cptr(w), dx.data_ptr(), N, H, W, Cc, (int)stride, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_dwconv_dgrad failed rc=", rc);
+  return dx;
+}
+
+// dW (fp32 [C,1,3,3], C*9 contiguous: a view of the flat gradient bucket) written or accumulated in place
+void dwconv_wgrad(const Tensor& dy, const Tensor& x, Tensor dw, int64_t stride, bool accumulate, bool prezeroed) {
+  check_cl(dy, "dy"); check_cl(x, "x");
+  c10::cuda::CUDAGuard g(x.device());
+  auto d = dims_of(x);
+  TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.numel() == (int64_t)d.C * 9 && dw.dim() == 4 &&
+              dw.stride(0) == 9 && dw.stride(2) == 3 && dw.stride(3) == 1, "dwconv_wgrad: dw must be fp32 [C,1,3,3], C*9 contiguous");
+  TORCH_CHECK(hz_dwconv_ok(d.N, d.H, d.W, d.C, (int)stride), "dwconv_wgrad: unsupported shape");
+  TORCH_CHECK(dy.size(0) == d.N && dy.size(1) == d.C && dy.size(2) == (d.H - 1) / stride + 1 &&
+              dy.size(3) == (d.W - 1) / stride + 1, "dwconv_wgrad: dy does not match x / stride");
+  int rc = hz_dwconv_wgrad(cptr(dy), cptr(x), dw.data_ptr<float>(), d.N, d.H, d.W, d.C, (int)stride, accumulate ? 1 : 0,
+                           prezeroed ? 1 : 0, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_dwconv_wgrad failed rc=", rc);
 }
 
 Tensor pad_rows(const Tensor& w2d, int64_t Kp) {
@@ -548,6 +603,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("u8_normalize", &u8_normalize);
   m.def("im2col_small", &im2col_small);
   m.def("pad_rows", &pad_rows);
+  m.def("dwconv_ok", [](int64_t N, int64_t H, int64_t W, int64_t C, int64_t stride) {
+    return hz_dwconv_ok((int)N, (int)H, (int)W, (int)C, (int)stride) != 0; });
+  m.def("dwconv_fwd", &dwconv_fwd);
+  m.def("dwconv_dgrad", &dwconv_dgrad);
+  m.def("dwconv_wgrad", &dwconv_wgrad);
   m.def("conv_set_debug", [](c10::optional<Tensor> buf) {
     if (buf.has_value() && buf->defined()) {
       TORCH_CHECK(buf->is_cuda() && buf->scalar_type() == at::kLong && buf->is_contiguous());

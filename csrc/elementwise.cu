@@ -13,7 +13,10 @@ namespace hz {
 // ------------------------------------------------------------------------------------------------
 // per-channel reductions over rows: block = (C/8 channel-vectors) x (256/(C/8) row lanes)
 // ------------------------------------------------------------------------------------------------
-template <bool kBwd>
+// kGen: any channel count that is a multiple of 8 (the row-lane split leaves 256 % (C/8) threads idle) and the
+// ReLU6 mask (relu == 2) — MobileNetV2's 24/96/144/160/320/...-channel layers; the default instantiation is the
+// ResNet one (C/8 a power of two, plain ReLU).
+template <bool kBwd, bool kGen = false>
 __global__ void __launch_bounds__(256) channel_reduce_kernel(
     const __nv_bfloat16* __restrict__ a,      // fwd: y_raw           bwd: dout
     const __nv_bfloat16* __restrict__ outp,   // bwd: bn output (ReLU mask), may be null
@@ -35,6 +38,8 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mu[i] = mean[vec * 8 + i]; is[i] = invstd[vec * 8 + i]; }
   }
+  const bool active = !kGen || rl < rlanes;
+  if (active) {
   for (int r = blockIdx.x * rlanes + rl; r < M; r += gridDim.x * rlanes) {
     const size_t off = (size_t)r * C + vec * 8;
     float f[8];
@@ -48,8 +53,13 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
       if (relu) {
         float o[8];
         unpack8(ld8(outp + off), o);
+        if (kGen && relu == 2) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = o[i] > 0.f ? f[i] : 0.f;
+          for (int i = 0; i < 8; ++i) f[i] = (o[i] > 0.f && o[i] < 6.f) ? f[i] : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = o[i] > 0.f ? f[i] : 0.f;
+        }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * (y[i] - mu[i]) * is[i]; }
@@ -58,6 +68,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
   float* mine = red + ((size_t)rl * nvec + vec) * 16;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
+  }
   __syncthreads();
   // nvec*16 outputs, each summed over rlanes
   for (int o = threadIdx.x; o < nvec * 16; o += 256) {
@@ -73,6 +84,7 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(
 // BN apply (+ residual) (+ ReLU); every CTA derives scale/shift from the sums in smem,
 // CTA 0 publishes mean / invstd / running statistics.
 // ------------------------------------------------------------------------------------------------
+template <bool kGen = false>     // kGen: relu == 2 clamps at 6 (ReLU6)
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(
     const __nv_bfloat16* __restrict__ y, const float* __restrict__ sums,
     const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -128,12 +140,17 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(
     if (relu) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+      if (kGen && relu == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fminf(f[i], 6.f);
+      }
     }
     st8(out + v * 8, pack8(f));
   }
 }
 
 // dy_raw = γ·invstd·(g − Σg/M − x̂·Σ(g·x̂)/M), g = dout·[out>0];  dres = g;  CTA0: dγ, dβ
+template <bool kGen = false>     // kGen: relu == 2 is the ReLU6 mask (0 < out < 6)
 __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ outp,
     const __nv_bfloat16* __restrict__ yraw, const float* __restrict__ mean,
@@ -170,8 +187,13 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
     if (relu) {
       float o[8];
       unpack8(ld8(outp + v * 8), o);
+      if (kGen && relu == 2) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+        for (int i = 0; i < 8; ++i) g[i] = (o[i] > 0.f && o[i] < 6.f) ? g[i] : 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+      }
     }
     if (dres != nullptr) st8(dres + v * 8, pack8(g));
     float d[8];
@@ -782,15 +804,23 @@ inline int reduce_grid(int M, int C) {
 
 extern "C" {
 
+// 1: the default (ResNet) instantiations serve this channel count; 2: the generic ones do (any multiple of 8)
 int hz_channel_ok(int C) {
   if (C < 8 || C > 2048 || (C & 7)) return 0;
   const int nvec = C >> 3;
-  return (nvec & (nvec - 1)) == 0 && nvec <= 256;
+  return (nvec & (nvec - 1)) == 0 ? 1 : 2;
 }
+namespace {
+inline bool bn_generic(int C, int relu) { return relu == 2 || hz_channel_ok(C) == 2; }
+}  // namespace
 
 void hz_channel_sums(const void* y, float* sums, int M, int C, cudaStream_t st) {
   hz::zero_f32(sums, (size_t)2 * C, st);
   const size_t smem = sizeof(float) * 256 * 16;
+  if (bn_generic(C, 0))
+    hz::launch(hz::channel_reduce_kernel<false, true>, dim3(reduce_grid(M, C)), dim3(256), smem, st,
+        (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0);
+  else
   hz::launch(hz::channel_reduce_kernel<false>, dim3(reduce_grid(M, C)), dim3(256), smem, st, 
       (const __nv_bfloat16*)y, nullptr, nullptr, nullptr, nullptr, sums, M, C, 0);
 }
@@ -800,7 +830,12 @@ void hz_bn_act_fwd(const void* y, const float* sums, const float* gamma, const f
                    float* rvar, int M, int C, float eps, float momentum, int relu, int training,
                    cudaStream_t st) {
   const size_t smem = sizeof(float) * 2 * C;
-  hz::launch(hz::bn_act_fwd_kernel, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st, 
+  if (relu == 2)
+    hz::launch(hz::bn_act_fwd_kernel<true>, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st,
+        (const __nv_bfloat16*)y, sums, gamma, beta, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out,
+        mean, invstd, rmean, rvar, M, C, eps, momentum, relu, training);
+  else
+  hz::launch(hz::bn_act_fwd_kernel<false>, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st, 
       (const __nv_bfloat16*)y, sums, gamma, beta, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out,
       mean, invstd, rmean, rvar, M, C, eps, momentum, relu, training);
 }
@@ -809,7 +844,8 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
                    const float* invstd, const float* gamma, float* sums_scratch, void* dy, void* dres,
                    float* dgamma, float* dbeta, int acc_gamma, int acc_beta, int M, int C, int relu,
                    int scratch_is_zero, cudaStream_t st) {
-  if (scratch_is_zero == 2) {
+  const bool gen = bn_generic(C, relu);
+  if (scratch_is_zero == 2 && !gen) {
     // arena slice [2C sums | 32-float pad holding the barrier counter], all zero: one fused kernel
     int grid = grid_for((size_t)M * (C / 8), 256, 148);
     size_t smem = sizeof(float) * 256 * 16;
@@ -822,11 +858,21 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
   }
   if (!scratch_is_zero) hz::zero_f32(sums_scratch, (size_t)2 * C, st);
   const size_t smem_r = sizeof(float) * 256 * 16;
+  const size_t smem = sizeof(float) * 5 * C;
+  if (gen) {
+    hz::launch(hz::channel_reduce_kernel<true, true>, dim3(reduce_grid(M, C)), dim3(256), smem_r, st,
+        (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
+        sums_scratch, M, C, relu);
+    hz::launch(hz::bn_act_bwd_apply_kernel<true>, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st,
+        (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
+        gamma, sums_scratch, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta, acc_gamma, acc_beta,
+        M, C, relu);
+    return;
+  }
   hz::launch(hz::channel_reduce_kernel<true>, dim3(reduce_grid(M, C)), dim3(256), smem_r, st, 
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
       sums_scratch, M, C, relu);
-  const size_t smem = sizeof(float) * 5 * C;
-  hz::launch(hz::bn_act_bwd_apply_kernel, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st, 
+  hz::launch(hz::bn_act_bwd_apply_kernel<false>, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st, 
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
       gamma, sums_scratch, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta, acc_gamma, acc_beta,
       M, C, relu);

@@ -37,6 +37,14 @@ void hz_grad_diff(const float* g, float* prev, float* out, size_t n, cudaStream_
 void hz_stats_update(float* stats, float* has_prev, const float* loss, const float* correct, float batch,
                      float* diff_sq, cudaStream_t st);
 
+// ---- depthwise.cu (3x3 depthwise convolution, pad 1, stride 1|2; x/y NHWC bf16, w bf16 [C][3][3], dw fp32 [C][3][3])
+int hz_dwconv_ok(int N, int H, int W, int C, int stride);
+int hz_dwconv_fwd(const void* x, const void* w, void* y, float* stats, int stats_is_zero, int N, int H, int W, int C,
+                  int stride, cudaStream_t st);
+int hz_dwconv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int stride, cudaStream_t st);
+int hz_dwconv_wgrad(const void* dy, const void* x, float* dwt, int N, int H, int W, int C, int stride, int accumulate,
+                    int prezeroed, cudaStream_t st);
+
 // ---- conv_gemm.cu (tcgen05 implicit GEMM)
 int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
 void hz_cluster_capacity(int out[4]);

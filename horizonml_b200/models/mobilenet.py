@@ -2,21 +2,24 @@
 entrypoint, train.py:60-68, ``MODEL_TYPE=mobilenet``).
 
 Parameter / buffer names and shapes are torchvision's (``features.N.conv.M…``, ``classifier.1.*``), so state dicts are
-interchangeable.  What runs where:
+interchangeable.  What runs where on a B200 (``ops.set_backend("native")``):
 
 * every **1×1 convolution** (expand, project, the 320→1280 head conv — ~95 % of the model's FLOPs) goes through
-  ``ops.conv_bn_act``: conv → BatchNorm(batch stats) → [+residual] → [ReLU], i.e. on a B200 the tcgen05 implicit-GEMM
-  kernels (channel counts only need to be multiples of 8: the TMA zero-fill rule introduced for tensor-parallel
-  shards) with the BN statistics in the conv epilogue and gradients written straight into the flat buckets.  ReLU6 is
-  ReLU (fused) followed by a clamp.  BatchNorm kernels take the native path where the channel count is 8·2^k and the
-  PyTorch-op path otherwise (counted in ``native_backend.FALLBACKS``);
-* the **depthwise 3×3 convolutions** and the 3-channel stem run on PyTorch ops (cuDNN on GPUs) with plain autograd — a
-  depthwise tcgen05 kernel makes no sense (K = 9) and a hand-written SIMT one is not written yet; their gradients reach
-  the flat store through ``FlatParams``' autograd bridge;
-* the classifier (dropout → avg-pool → FC → CE) is ``ops.head_loss``.
+  ``ops.conv_bn_act``: the tcgen05 implicit-GEMM kernels (channel counts only need to be multiples of 8: the TMA
+  zero-fill rule introduced for tensor-parallel shards) with the BN statistics in the conv epilogue and gradients
+  written straight into the flat buckets;
+* the **depthwise 3×3 convolutions** go through ``ops.dwconv_bn_act`` → ``csrc/depthwise.cu``: a depthwise conv has
+  K = 9 and no cross-channel reuse, so it is a register-resident SIMT stencil (8 channels per thread), not a tensor-core
+  GEMM; forward leaves the BN sums in its epilogue, the weight gradient lands in the flat bucket;
+* the **3-channel stem** (3×3 / stride 2 → 32) is im2col → the same tcgen05 GEMM (like ResNet's 7×7 stem);
+* BatchNorm + **ReLU6** (+ the residual add of the stride-1 blocks) are the ``bn_act`` kernels in their generic
+  instantiation (any channel count that is a multiple of 8; activation code 2 clamps at 6 and masks the gradient to
+  0 < y < 6);
+* the classifier (dropout → avg-pool → FC → CE) is ``ops.head_loss``; dropout on the pooled 1280-vector is a PyTorch op.
 
-ResNet-18 stays the benchmarked model (every reference trainer uses it); this makes ``MODEL_TYPE=mobilenet`` a real
-model on the same engine (flat parameters, fused Adam, fused all-reduce) instead of a torchvision + autocast adapter."""
+On CPU / gloo the same graph runs on the PyTorch-op backend (the oracle the kernels are tested against).  ResNet-18
+stays the benchmarked model (every reference trainer uses it); this makes ``MODEL_TYPE=mobilenet`` a real model on the
+same engine (flat parameters, fused Adam, fused all-reduce) instead of a torchvision + autocast adapter."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -26,7 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .resnet import BNP, ConvW
+from .resnet import BNP, ConvW, _FUSE_RESADD
 
 # (expand ratio t, output channels c, repeats n, stride s) — torchvision.models.mobilenetv2
 _SETTING = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
@@ -43,24 +46,23 @@ class DWConvW(nn.Module):
         self.stride, self.c = stride, c
 
 
-def _relu6_cap(x):
-    return torch.clamp(x, max=6.0)
-
-
-def _pw(x, conv: ConvW, bn: BNP, relu6: bool, residual=None, training=True):
+def _pw(x, conv: ConvW, bn: BNP, relu6: bool, residual=None, training=True, in_link=None, res_link=None):
     """1×1 conv → BN → [+residual] → [ReLU6] on the fused op (native tcgen05 path on GPUs)."""
-    y = ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, stride=1, pad=0,
-                        relu=relu6, residual=residual, momentum=bn.momentum, eps=bn.eps, training=training)
-    return _relu6_cap(y) if relu6 else y
+    return ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, stride=1, pad=0,
+                           relu=2 if relu6 else 0, residual=residual, momentum=bn.momentum, eps=bn.eps,
+                           training=training, in_link=in_link, res_link=res_link)
 
 
-def _dw(x, conv: nn.Module, bn: BNP, training=True, groups: Optional[int] = None, pad: int = 1):
-    """k×k conv (depthwise, or the dense 3-channel stem) → BN → ReLU6 with PyTorch ops / plain autograd."""
-    w = conv.weight.to(x.dtype)                                  # differentiable cast: the gradient reaches the fp32 master
-    y = F.conv2d(x, w, None, conv.stride, pad, 1, groups if groups is not None else 1)
-    y = F.batch_norm(y.to(torch.promote_types(y.dtype, torch.float32)), bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                     training, bn.momentum, bn.eps)
-    return F.relu6(y).to(x.dtype).contiguous(memory_format=torch.channels_last)
+def _dw(x, conv: nn.Module, bn: BNP, training=True):
+    """depthwise 3×3 conv → BN → ReLU6 (csrc/depthwise.cu + the generic bn_act kernels on GPUs)."""
+    return ops.dwconv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, stride=conv.stride,
+                             act=2, momentum=bn.momentum, eps=bn.eps, training=training)
+
+
+def _stem(x, conv: nn.Module, bn: BNP, training=True):
+    """dense 3×3 / stride-2 conv over the 3 input channels → BN → ReLU6 (im2col + tcgen05 GEMM on GPUs)."""
+    return ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, stride=conv.stride,
+                           pad=1, relu=2, momentum=bn.momentum, eps=bn.eps, training=training)
 
 
 class _CNA(nn.Sequential):
@@ -88,11 +90,16 @@ class InvertedResidual(nn.Module):
         t = self.training
         i = 0
         y = x
+        # a residual block's input feeds the expand conv and the skip connection: the skip gradient is added inside the
+        # expand conv's dgrad epilogue (ops.GradLink, as in ResNet's BasicBlock) instead of by an accumulation kernel
+        link = (ops.GradLink(2) if (_FUSE_RESADD and self.use_res and self.expand and t and torch.is_grad_enabled()
+                                    and x.requires_grad) else None)
         if self.expand:
-            y = _pw(y, self.conv[0][0], self.conv[0][1], True, training=t)
+            y = _pw(y, self.conv[0][0], self.conv[0][1], True, training=t, in_link=link)
             i = 1
-        y = _dw(y, self.conv[i][0], self.conv[i][1], t, groups=self.conv[i][0].c)
-        return _pw(y, self.conv[i + 1], self.conv[i + 2], False, residual=x if self.use_res else None, training=t)
+        y = _dw(y, self.conv[i][0], self.conv[i][1], t)
+        return _pw(y, self.conv[i + 1], self.conv[i + 2], False, residual=x if self.use_res else None, training=t,
+                   res_link=link)
 
 
 class _StemConv(nn.Module):
@@ -127,7 +134,7 @@ class MobileNetV2(nn.Module):
     def feature_map(self, x):
         t = self.training
         x = x.contiguous(memory_format=torch.channels_last)
-        y = _dw(x, self.features[0][0], self.features[0][1], t, groups=1)
+        y = _stem(x, self.features[0][0], self.features[0][1], t)
         for blk in list(self.features)[1:-1]:
             y = blk(y)
         return _pw(y, self.features[-1][0], self.features[-1][1], True, training=t)
@@ -146,8 +153,12 @@ class MobileNetV2(nn.Module):
         return F.linear(f, fc.weight.to(f.dtype), fc.bias.to(f.dtype))
 
     def forward_loss(self, x, labels, loss_scale: float = 1.0, stats_out: Optional[dict] = None):
-        f = self._pooled(x)
         fc = self.classifier[1]
+        if not (self.training and self.dropout > 0):
+            # no dropout between pool and FC: the head kernel does avg-pool → FC → CE (+ backward) itself
+            return ops.head_loss(self.feature_map(x), fc.weight, fc.bias, labels, loss_scale, n_valid=self.num_classes,
+                                 stats_out=stats_out)
+        f = self._pooled(x)
         feat = f.to(x.dtype if x.dtype != torch.uint8 else torch.float32).view(f.shape[0], f.shape[1], 1, 1)
         feat = feat.contiguous(memory_format=torch.channels_last)
         return ops.head_loss(feat, fc.weight, fc.bias, labels, loss_scale, n_valid=self.num_classes, stats_out=stats_out)

@@ -22,9 +22,9 @@ _CSRC = os.path.join(_ROOT, "csrc")
 _PKG = os.path.join(_ROOT, "horizonml_b200")
 _SO = os.path.join(_PKG, "_C.so")
 _BUILD = os.path.join(_CSRC, "build")
-_CU = ["elementwise.cu", "comm.cu", "conv_gemm.cu", "tp_fused.cu"]
+_CU = ["elementwise.cu", "depthwise.cu", "comm.cu", "conv_gemm.cu", "tp_fused.cu"]
 _CPP = ["bindings.cpp"]
-_HDRS = ["common.cuh", "tc05.cuh", "igemm_common.cuh", "launchers.h"]
+_HDRS = ["common.cuh", "tc05.cuh", "igemm_common.cuh", "dw_core.cuh", "launchers.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -235,7 +235,7 @@ def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True,
     """``post_conv`` / ``post_dgrad`` are the tensor-parallel reduction points (row-parallel conv
     output, column-parallel conv input-gradient); they take and return a tensor.  ``conv_fn(x, w, want_stats) ->
     (y, sums | None)`` / ``dgrad_fn(dy, w, addend) -> dx`` replace conv + reduction (+ BN statistics pass / residual
-    gradient add) by ONE fused GEMM+collective kernel."""
+    gradient add) by ONE fused GEMM+collective kernel.  ``relu``: False/0 none, True/1 ReLU, 2 ReLU6."""
     if not training or not torch.is_grad_enabled():
         be = _be(x)
         if conv_fn is not None:
@@ -250,6 +250,60 @@ def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True,
         return out
     return _ConvBNAct.apply(x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
                             momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link, res_link)
+
+
+# ----------------------------------------------------------------------------------------------
+# depthwise 3×3 conv (pad 1, stride 1|2) + BN + ReLU6 — MobileNetV2's middle layer (train.py:60-68)
+# ----------------------------------------------------------------------------------------------
+
+class _DWConvBNAct(torch.autograd.Function):
+    """Same contract as ``_ConvBNAct`` for a depthwise convolution: BN statistics from the conv kernel's epilogue,
+    weight gradient written in place into ``weight.main_grad`` (the flat bucket), reducer hooks fired per parameter."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, rmean, rvar, stride, act, momentum, eps, training):
+        be = _be(x)
+        w = compute_weight(weight, x.dtype)
+        y_raw, sums = be.dwconv_fwd(x, w, stride, training)
+        out, mean, invstd = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar, momentum, eps, None,
+                                          act, training)
+        ctx.save_for_backward(x, y_raw, out, mean, invstd)
+        ctx.params = (weight, gamma, beta)
+        ctx.cfg = (stride, act, training)
+        ctx.x_needs_grad = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y_raw, out, mean, invstd = ctx.saved_tensors
+        weight, gamma, beta = ctx.params
+        stride, act, training = ctx.cfg
+        if not training:
+            raise RuntimeError("dwconv_bn_act backward requires training=True")
+        be = _be(x)
+        dout = dout.contiguous(memory_format=torch.channels_last)
+        tg, ag = grad_target(gamma)
+        tb, ab = grad_target(beta)
+        dy, _, _, _ = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), act, False,
+                                    _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab))
+        grad_written(gamma)
+        grad_written(beta)
+        dx = be.dwconv_dgrad(dy, compute_weight(weight, x.dtype), x.shape, stride) if ctx.x_needs_grad else None
+        tgt, acc = grad_target(weight)
+        be.dwconv_wgrad(dy, x, stride, tgt, acc, bool(getattr(weight, "_zeroed", False)))
+        grad_written(weight)
+        return (dx,) + (None,) * 10
+
+
+def dwconv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, act=2, momentum=0.1, eps=1e-5, training=True):
+    """Depthwise 3×3 conv (``weight`` [C,1,3,3], pad 1) → BatchNorm → activation (0 none | 1 ReLU | 2 ReLU6)."""
+    if not training or not torch.is_grad_enabled():
+        be = _be(x)
+        y_raw, sums = be.dwconv_fwd(x, compute_weight(weight, x.dtype), stride, training)
+        out, _, _ = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar, momentum, eps, None, act,
+                                  training)
+        return out
+    return _DWConvBNAct.apply(x, weight, gamma, beta, rmean, rvar, int(stride), int(act), momentum, eps, training)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,9 +1,10 @@
 """Native op backend: every function launches hand-written sm_100a kernels from ``csrc/``.
 
 Same signatures as ``torch_backend``.  Convolutions run on the tcgen05/TMEM/TMA implicit-GEMM
-kernels; the 3-channel 7×7/2 stem goes im2col → the same GEMM kernel (TMA needs ≥16-byte rows);
-shapes the tiles cannot express (channels not a multiple of 64, odd spatial sizes) are routed to
-the PyTorch oracle and counted in ``FALLBACKS`` — ``HZ_STRICT_NATIVE=1`` turns that into an error.
+kernels; RGB stems (ResNet 7×7/2, MobileNetV2 3×3/2) go im2col → the same GEMM kernel (TMA needs ≥16-byte rows);
+depthwise 3×3 convolutions run on the SIMT kernels of ``csrc/depthwise.cu``; shapes the tiles cannot express
+(channels not a multiple of 8, odd spatial sizes under stride 2) are routed to the PyTorch oracle and counted in
+``FALLBACKS`` — ``HZ_STRICT_NATIVE=1`` turns that into an error.
 """
 from __future__ import annotations
 
@@ -81,7 +82,16 @@ def _conv_ok(x_shape, w_shape, stride, pad) -> bool:
 
 
 def _is_stem(x_shape, w_shape) -> bool:
-    return x_shape[1] < 8 and w_shape[0] % 64 == 0 and w_shape[1] * w_shape[2] * w_shape[3] <= STEM_KP
+    """A dense conv over fewer than 8 input channels (RGB stems: ResNet 7x7/2 -> 64, MobileNetV2 3x3/2 -> 32): im2col
+    to [M, Kp] + the 1x1 tcgen05 GEMM."""
+    return x_shape[1] < 8 and w_shape[0] % 8 == 0 and w_shape[1] * w_shape[2] * w_shape[3] <= STEM_KP
+
+
+def _stem_kp(w_shape) -> int:
+    """Padded K of the im2col matrix: 192 for the 7x7x3 = 147 stem (the one-launch stem_pack kernel), else the next
+    multiple of 64 (one k-block of the GEMM per 64)."""
+    k = w_shape[1] * w_shape[2] * w_shape[3]
+    return STEM_KP if k == 147 else (k + 63) // 64 * 64
 
 
 # ------------------------------------------------------------------------------------------------
@@ -113,12 +123,13 @@ def conv_fwd(x, w, stride: int, pad: int, want_stats: bool):
             w2d = w.permute(0, 2, 3, 1).reshape(cout, -1)
             if not w2d.is_contiguous():
                 w2d = w2d.contiguous()
-            A, wp = C.stem_pack(x, w2d, r, stride, pad, STEM_KP)                # [N*Ho*Wo, 192], [Cout, 192]: one launch
+            kp = _stem_kp(w.shape)
+            A, wp = C.stem_pack(x, w2d, r, stride, pad, kp)       # [N*Ho*Wo, Kp], [Cout, Kp] (7x7x3: one launch)
             _STEM_CACHE["key"], _STEM_CACHE["A"] = (x.data_ptr(), x._version, tuple(x.shape)), A
-            LAUNCHES["stem_im2col"] += 1
+            LAUNCHES["stem_im2col"] += 1 if kp == STEM_KP else 2
             LAUNCHES["conv_fwd"] += 1
             pre = ARENA.take(2, cout, x.device) if want_stats else None
-            y2, stats = C.conv_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0, want_stats, pre,
+            y2, stats = C.conv_fwd(A.view(-1, kp, 1, 1), wp.view(cout, kp, 1, 1), 1, 0, want_stats, pre,
                                   False)          # wp was produced by the kernel right before: no early weight prefetch
             y = y2.reshape(n, ho, wo, cout).permute(0, 3, 1, 2)
             return y, (stats if want_stats else None)
@@ -139,7 +150,7 @@ def conv_bn_act_fwd(x, w, stride: int, pad: int, gamma, beta, rmean, rvar, momen
     in the statistics arena, a device-wide barrier makes them final, and every CTA normalises the tile it still
     holds in shared memory.  Returns (y_raw, out, mean, invstd), or None when not applicable (caller runs the
     conv and BN kernels separately)."""
-    if not (_FUSE_BN and _bf16_cl(x) and w.dtype == torch.bfloat16 and C.channel_ok(w.shape[0])):
+    if not (_FUSE_BN and int(relu) < 2 and _bf16_cl(x) and w.dtype == torch.bfloat16 and C.channel_ok(w.shape[0]) == 1):
         return None
     if residual is not None and not _bf16_cl(residual):
         return None
@@ -161,11 +172,12 @@ def conv_bn_act_fwd(x, w, stride: int, pad: int, gamma, beta, rmean, rvar, momen
     w2d = w.permute(0, 2, 3, 1).reshape(cout, -1)
     if not w2d.is_contiguous():
         w2d = w2d.contiguous()
-    A, wp = C.stem_pack(x, w2d, r, stride, pad, STEM_KP)
+    kp = _stem_kp(w.shape)
+    A, wp = C.stem_pack(x, w2d, r, stride, pad, kp)
     _STEM_CACHE["key"], _STEM_CACHE["A"] = (x.data_ptr(), x._version, tuple(x.shape)), A
     LAUNCHES["stem_im2col"] += 1
     res2 = residual.permute(0, 2, 3, 1).reshape(-1, cout, 1, 1) if residual is not None else None
-    y2, o2, mean, invstd = C.conv_bn_act_fwd(A.view(-1, STEM_KP, 1, 1), wp.view(cout, STEM_KP, 1, 1), 1, 0,
+    y2, o2, mean, invstd = C.conv_bn_act_fwd(A.view(-1, kp, 1, 1), wp.view(cout, kp, 1, 1), 1, 0,
                                              scratch.view(-1), gamma, beta, rmean, rvar, momentum, eps, res2, relu,
                                              False)
     return (y2.reshape(n, ho, wo, cout).permute(0, 3, 1, 2), o2.reshape(n, ho, wo, cout).permute(0, 3, 1, 2),
@@ -181,7 +193,7 @@ def bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual, r
             sums = torch.empty(2, y_raw.shape[1], dtype=torch.float32, device=y_raw.device)
         LAUNCHES["bn_act_fwd"] += 1
         out, mean, invstd = C.bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual,
-                                         relu, training)
+                                         int(relu), training)        # 0 none | 1 ReLU | 2 ReLU6
         return out, mean, invstd
     _fallback("bn_act_fwd", f"{tuple(y_raw.shape)} {y_raw.dtype}")
     return _tb.bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual, relu, training)
@@ -201,7 +213,7 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma
         # room for the counter the binding runs the reduce and apply kernels separately
         scratch = ARENA.take(1, 2 * c + (32 if _BN_BWD_FUSED else 0), y_raw.device)
         LAUNCHES["bn_act_bwd"] -= 1 if (scratch is not None and _BN_BWD_FUSED) else 0
-        dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dg, db, ag, ab,
+        dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, int(relu), has_residual, dg, db, ag, ab,
                                 scratch)
         return dy, dg, db, (dres if has_residual else None)
     _fallback("bn_act_bwd", f"{tuple(y_raw.shape)}")
@@ -236,18 +248,53 @@ def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, ac
             C.conv_wgrad(dy, x, out_grad, r, stride, pad, accumulate, prezeroed, 0, 0)
             return
         if _is_stem(x.shape, w_shape):
-            if _STEM_CACHE["key"] == (x.data_ptr(), x._version, tuple(x.shape)):
+            kp = _stem_kp(w_shape)
+            if _STEM_CACHE["key"] == (x.data_ptr(), x._version, tuple(x.shape)) and _STEM_CACHE["A"].shape[1] == kp:
                 A = _STEM_CACHE["A"]            # the forward's im2col matrix is still alive
             else:
-                A = C.im2col_small(x, r, stride, pad, STEM_KP)
+                A = C.im2col_small(x, r, stride, pad, kp)
                 LAUNCHES["stem_im2col"] += 1
             n, _, ho, wo = dy.shape
             dy2 = dy.permute(0, 2, 3, 1).reshape(-1, cout, 1, 1)     # [M, Cout,1,1] (NHWC rows)
             LAUNCHES["conv_wgrad"] += 1
-            C.conv_wgrad(dy2, A.view(-1, STEM_KP, 1, 1), out_grad, 1, 1, 0, accumulate, prezeroed, cin * r * s, cin * r * s)
+            C.conv_wgrad(dy2, A.view(-1, kp, 1, 1), out_grad, 1, 1, 0, accumulate, prezeroed, cin * r * s, cin * r * s)
             return
     _fallback("conv_wgrad", f"x={tuple(x.shape)} w={tuple(w_shape)}")
     _tb.conv_wgrad(dy, x, w_shape, stride, pad, out_grad, accumulate)
+
+
+# ---- depthwise 3x3 convolution, pad 1 (csrc/depthwise.cu): weight [C, 1, 3, 3]
+def _dw_ok(x_shape, stride) -> bool:
+    n, c, h, w = x_shape
+    return bool(C.dwconv_ok(n, h, w, c, stride))
+
+
+def dwconv_fwd(x, w, stride: int, want_stats: bool):
+    if _bf16_cl(x) and w.dtype == torch.bfloat16 and _dw_ok(x.shape, stride):
+        LAUNCHES["dwconv_fwd"] += 1
+        pre = ARENA.take(2, x.shape[1], x.device) if want_stats else None
+        y, stats = C.dwconv_fwd(x, w, stride, want_stats, pre)
+        return y, (stats if want_stats else None)
+    _fallback("dwconv_fwd", f"x={tuple(x.shape)} {x.dtype} s={stride}")
+    return _tb.dwconv_fwd(x, w, stride, want_stats)
+
+
+def dwconv_dgrad(dy, w, x_shape, stride: int):
+    if _bf16_cl(dy) and w.dtype == torch.bfloat16 and _dw_ok(tuple(x_shape), stride):
+        LAUNCHES["dwconv_dgrad"] += 1
+        return C.dwconv_dgrad(dy, w, list(x_shape), stride)
+    _fallback("dwconv_dgrad", f"x={tuple(x_shape)}")
+    return _tb.dwconv_dgrad(dy, w, x_shape, stride)
+
+
+def dwconv_wgrad(dy, x, stride: int, out_grad: torch.Tensor, accumulate: bool, prezeroed: bool = False):
+    if (_bf16_cl(dy) and _bf16_cl(x) and _dw_ok(x.shape, stride) and out_grad.is_cuda and out_grad.dtype == torch.float32
+            and out_grad.dim() == 4 and out_grad.stride(0) == 9 and out_grad.stride(2) == 3 and out_grad.stride(3) == 1):
+        LAUNCHES["dwconv_wgrad"] += 1
+        C.dwconv_wgrad(dy, x, out_grad, stride, accumulate, prezeroed)
+        return
+    _fallback("dwconv_wgrad", f"x={tuple(x.shape)}")
+    _tb.dwconv_wgrad(dy, x, stride, out_grad, accumulate, prezeroed)
 
 
 def maxpool_fwd(x, want_aux: bool = False):

@@ -56,6 +56,8 @@ def bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum: float, eps: floa
         out = out + residual.float()
     if relu:
         out = out.clamp_min(0.0)
+        if int(relu) == 2:                 # ReLU6 (MobileNetV2)
+            out = out.clamp_max(6.0)
     return _cl(out.to(y_raw.dtype)), mean, invstd
 
 
@@ -79,7 +81,8 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: 
     cnt = y_raw.numel() // C
     g = dout.float()
     if relu:
-        g = g * (out > 0).to(g.dtype)
+        mask = (out > 0) if int(relu) != 2 else ((out > 0) & (out < 6))
+        g = g * mask.to(g.dtype)
     dres = _cl(g.to(dout.dtype)) if has_residual else None
     xhat = (y_raw.float() - mean.view(1, C, 1, 1)) * invstd.view(1, C, 1, 1)
     dbeta = g.sum(dim=(0, 2, 3))
@@ -109,6 +112,34 @@ def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, ac
         dy, x, dy.new_empty(w_shape), None, [stride, stride], [pad, pad], [1, 1], False,
         [0, 0], 1, [False, True, False])
     gw = gw.float()
+    if accumulate:
+        out_grad.add_(gw)
+    else:
+        out_grad.copy_(gw)
+
+
+# ---- depthwise 3x3 convolution, pad 1 (MobileNetV2): weight [C, 1, 3, 3]
+def dwconv_fwd(x, w, stride: int, want_stats: bool):
+    y = _cl(F.conv2d(x, w.to(x.dtype), None, stride, 1, 1, x.shape[1]))
+    if not want_stats:
+        return y, None
+    yf = y.float()
+    return y, torch.stack([yf.sum(dim=(0, 2, 3)), (yf * yf).sum(dim=(0, 2, 3))])
+
+
+def dwconv_dgrad(dy, w, x_shape, stride: int):
+    dx, _, _ = torch.ops.aten.convolution_backward(
+        dy, dy.new_empty(x_shape), w.to(dy.dtype), None, [stride, stride], [1, 1], [1, 1], False,
+        [0, 0], x_shape[1], [True, False, False])
+    return _cl(dx)
+
+
+def dwconv_wgrad(dy, x, stride: int, out_grad: torch.Tensor, accumulate: bool, prezeroed: bool = False):
+    c = x.shape[1]
+    _, gw, _ = torch.ops.aten.convolution_backward(
+        dy, x, dy.new_empty((c, 1, 3, 3)), None, [stride, stride], [1, 1], [1, 1], False,
+        [0, 0], c, [False, True, False])
+    gw = gw.float().view_as(out_grad)
     if accumulate:
         out_grad.add_(gw)
     else:
