@@ -449,6 +449,29 @@ class PeerComm {
                                     cur_stream());
     TORCH_CHECK(rc == 0, "hz_comm_allreduce_adam failed rc=", rc);
   }
+  // ZeRO-1 step of one bucket in one kernel (csrc/comm.cu zero1_kernel): grad / master / shadow are the bucket's
+  // slices of the flat buffers, m / v / prev this rank's shards (zero1_shard(n_wire) elements)
+  void zero1_step(Tensor grad, double scale, c10::optional<Tensor> live_blocks, Tensor master, Tensor m, Tensor v,
+                  Tensor shadow, c10::optional<Tensor> prev, c10::optional<Tensor> diff_out, Tensor step, double lr,
+                  double b1, double b2, double eps, bool bump) {
+    TORCH_CHECK(grad.is_cuda() && grad.scalar_type() == at::kFloat && grad.is_contiguous());
+    TORCH_CHECK(master.scalar_type() == at::kFloat && master.numel() == grad.numel() && master.is_contiguous());
+    TORCH_CHECK(shadow.scalar_type() == at::kBFloat16 && shadow.numel() == grad.numel() && shadow.is_contiguous());
+    const bool has_live = live_blocks.has_value() && live_blocks->defined();
+    if (has_live) TORCH_CHECK(live_blocks->scalar_type() == at::kInt && live_blocks->is_cuda());
+    const size_t n = has_live ? (size_t)live_blocks->numel() * 64 : (size_t)grad.numel();
+    const int64_t shard = (int64_t)hz_comm_zero1_shard(n, world_);
+    TORCH_CHECK(m.scalar_type() == at::kFloat && v.scalar_type() == at::kFloat && m.numel() == shard && v.numel() == shard &&
+                m.is_contiguous() && v.is_contiguous(), "zero1_step: moment shards must have ", shard, " elements");
+    if (prev.has_value() && prev->defined()) TORCH_CHECK(prev->scalar_type() == at::kFloat && prev->numel() == shard);
+    c10::cuda::CUDAGuard g(grad.device());
+    int rc = hz_comm_zero1_step(c_, grad.data_ptr<float>(), n, (float)scale, has_live ? live_blocks->data_ptr<int>() : nullptr,
+                                master.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(), shadow.data_ptr(),
+                                fptr(prev), fptr(diff_out), step.data_ptr<float>(), (float)lr, (float)b1, (float)b2,
+                                (float)eps, bump ? 1 : 0, cur_stream());
+    TORCH_CHECK(rc == 0, "hz_comm_zero1_step failed rc=", rc);
+  }
+  int64_t zero1_shard(int64_t n_wire) { return (int64_t)hz_comm_zero1_shard((size_t)n_wire, world_); }
   int64_t blocks_for(int64_t n, const std::string& algo, bool wire_bf16) {
     int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "ll" ? 3 : 2;
     return hz_comm_blocks_for(c_, (size_t)n, a, wire_bf16 ? 1 : 0);
@@ -654,6 +677,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("allreduce", &PeerComm::allreduce, py::arg("grad"), py::arg("algo"), py::arg("wire_bf16"),
            py::arg("scale"), py::arg("live_blocks") = py::none())
       .def("allreduce_adam", &PeerComm::allreduce_adam)
+      .def("zero1_step", &PeerComm::zero1_step)
+      .def("zero1_shard", &PeerComm::zero1_shard)
       .def("blocks_for", &PeerComm::blocks_for)
       .def("set_block_cap", &PeerComm::set_block_cap)
       .def("barrier", &PeerComm::barrier)

@@ -537,6 +537,187 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(CommDev c, floa
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ZeRO-1 (optimizer-state sharding) step of one gradient bucket as ONE kernel: the two-shot all-reduce with the
+// optimizer in the middle.  Rank r owns slice r of the bucket's wire vectors — fp32 master values and both Adam
+// moments exist only there (m, v: 2·P/W floats per rank instead of 2·P):
+//     pack    : every slice of grad(fp32)·(1/W) -> bf16 into the local staging buffer, gradient cleared in the same pass
+//     barrier
+//     own slice: sum the W staged copies in rank order (fp32), Adam on the owned master slice and moment shards,
+//                new parameters -> bf16 -> pushed into the `out` buffer of EVERY rank (NVLink stores)
+//     barrier
+//     unpack  : out -> the local bf16 parameter shadow the compute kernels read (all slices)
+// Wire traffic is that of a bf16 all-reduce (gradients in, bf16 parameters out); the optimizer costs 1/W of the
+// replicated pass and there is no separate reduce-scatter / all-gather / shadow-refresh kernel (the NCCL formulation in
+// parallel/zero.py is the baseline).  The reference replicates its optimizer state (SURVEY §2.3 "ZeRO: NO").
+// The gradient-divergence term sum (g - g_prev)^2 is accumulated per slice and exchanged through per-(rank, block)
+// slots next to the flags, so every rank logs the whole-gradient value without an extra collective.
+struct ZeroFuse {
+  float* p;                        // fp32 master, the bucket's slice of the flat buffer (authoritative on the owner only)
+  float* m; float* v;              // this rank's moment shards of the bucket: [ceil(nv / W) * 8]
+  __nv_bfloat16* shadow;           // bf16 parameters, the bucket's slice of the flat shadow
+  float* prev; float* diff_out;    // optional: previous reduced gradient of the own slice (shard-sized) / accumulator [1]
+  float* step;                     // as AdamFuse
+  float lr, b1, b2, eps;
+  int bump;
+};
+constexpr int kZeroMaxBlocks = 64;
+HZ_DEVINL float* zdiff_of(char* base) { return reinterpret_cast<float*>(base + 53248); }   // [2][kMaxRanks][kZeroMaxBlocks]
+
+__global__ void __launch_bounds__(kCommThreads) zero1_kernel(CommDev c, float* __restrict__ grad, size_t n, float scale,
+                                                             const int* __restrict__ live, const ZeroFuse z) {
+  using Wt = Wire<true>;
+  constexpr int V = Wt::kVec;
+  __shared__ uint32_t s_epoch;
+  __shared__ float wsum[kCommThreads / 32];
+  const int W = c.world, B = gridDim.x, b = blockIdx.x;
+  const size_t nv = n / V;
+  char* my = c.base[c.rank];
+  const uint32_t parity = calls_of(my)[0] & 1u;        // per-communicator call counter, see allreduce_kernel
+  const size_t stage_off = kFlagBytes + (size_t)parity * c.buf_bytes;
+  const size_t out_off = kFlagBytes + (size_t)(2 + parity) * c.buf_bytes;
+  uint4* my_stage = reinterpret_cast<uint4*>(my + stage_off);
+  AdamCoef ak;
+  {
+    const float t = z.step[0] + 1.f;
+    const float bc1 = 1.f - __powf(z.b1, t), bc2 = 1.f - __powf(z.b2, t);
+    ak.step_size = z.lr / bc1; ak.inv_sqrt_bc2 = rsqrtf(bc2); ak.b1 = z.b1; ak.b2 = z.b2; ak.eps = z.eps;
+  }
+
+  // ---- pack all slices, clear the gradient (producers only ever accumulate into it)
+  for (int r = 0; r < W; ++r) {
+    size_t lo, hi;
+    sub_range(nv, W, B, r, b, lo, hi);
+    for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * 4) {
+      float f[4][V];
+      size_t off[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t v = v0 + (size_t)u * blockDim.x;
+        if (v < hi) { off[u] = goff<V>(live, v); load_grad<V>(grad, off[u], f[u]); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const size_t v = v0 + (size_t)u * blockDim.x;
+        if (v < hi) {
+          my_stage[v] = Wt::pack(f[u], scale);
+          reinterpret_cast<float4*>(grad + off[u])[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(grad + off[u])[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+  }
+  peer_block_barrier(c, &s_epoch);
+
+  // ---- own slice: reduce, Adam on the shard, push the new bf16 parameters to every rank
+  float dacc = 0.f;
+  {
+    size_t lo, hi;
+    sub_range(nv, W, B, c.rank, b, lo, hi);
+    const size_t q = (nv + W - 1) / W;
+    const size_t slice_lo = min((size_t)c.rank * q, nv);
+    for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+      uint4 w[kMaxRanks];
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < W) w[r] = reinterpret_cast<const uint4*>(c.base[r] + stage_off)[v];
+      float a[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < W) Wt::accum(a, w[r]);                                   // rank order: identical on every rank
+      const size_t off = goff<V>(live, v);                                // element offset in the bucket
+      const size_t so = (v - slice_lo) * V;                               // element offset in the shard
+      float pn[V];
+#pragma unroll
+      for (int h = 0; h < V / 4; ++h) {
+        float4 pp = *reinterpret_cast<float4*>(z.p + off + 4 * h);
+        float4 mm = *reinterpret_cast<float4*>(z.m + so + 4 * h);
+        float4 vv = *reinterpret_cast<float4*>(z.v + so + 4 * h);
+        float* P = &pp.x; float* Mo = &mm.x; float* Vv = &vv.x;
+        const float* G = a + 4 * h;
+        if (z.prev != nullptr) {
+          const float4 pr = *reinterpret_cast<const float4*>(z.prev + so + 4 * h);
+          const float dx = G[0] - pr.x, dy = G[1] - pr.y, dz = G[2] - pr.z, dw = G[3] - pr.w;
+          dacc += dx * dx + dy * dy + dz * dz + dw * dw;
+          *reinterpret_cast<float4*>(z.prev + so + 4 * h) = make_float4(G[0], G[1], G[2], G[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gr = G[j];
+          Mo[j] = ak.b1 * Mo[j] + (1.f - ak.b1) * gr;
+          Vv[j] = ak.b2 * Vv[j] + (1.f - ak.b2) * gr * gr;
+          const float denom = sqrtf(Vv[j]) * ak.inv_sqrt_bc2 + ak.eps;
+          P[j] -= ak.step_size * Mo[j] / denom;
+          pn[4 * h + j] = P[j];
+        }
+        *reinterpret_cast<float4*>(z.p + off + 4 * h) = pp;
+        *reinterpret_cast<float4*>(z.m + so + 4 * h) = mm;
+        *reinterpret_cast<float4*>(z.v + so + 4 * h) = vv;
+      }
+      const uint4 o = Wt::from_acc(pn);
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < W) reinterpret_cast<uint4*>(c.base[r] + out_off)[v] = o;   // NVLink push (own copy included)
+    }
+  }
+  const bool want_diff = z.prev != nullptr && z.diff_out != nullptr;
+  if (want_diff) {
+    dacc = warp_sum(dacc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = dacc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float tt = threadIdx.x < kCommThreads / 32 ? wsum[threadIdx.x] : 0.f;
+      tt = warp_sum(tt);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < W) zdiff_of(c.base[r])[((size_t)parity * kMaxRanks + c.rank) * kZeroMaxBlocks + b] = tt;
+      }
+    }
+  }
+  peer_block_barrier(c, &s_epoch);
+
+  // ---- unpack: every rank's new parameters -> the local bf16 shadow
+  {
+    const uint4* my_out = reinterpret_cast<const uint4*>(my + out_off);
+    for (int r = 0; r < W; ++r) {
+      size_t lo, hi;
+      sub_range(nv, W, B, r, b, lo, hi);
+      for (size_t v0 = lo + threadIdx.x; v0 < hi; v0 += (size_t)blockDim.x * 4) {
+        uint4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const size_t v = v0 + (size_t)u * blockDim.x;
+          if (v < hi) w[u] = my_out[v];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const size_t v = v0 + (size_t)u * blockDim.x;
+          if (v < hi) *reinterpret_cast<uint4*>(z.shadow + goff<V>(live, v)) = w[u];
+        }
+      }
+    }
+  }
+  if (want_diff && threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int r = 0; r < W; ++r) tot += zdiff_of(my)[((size_t)parity * kMaxRanks + r) * kZeroMaxBlocks + b];
+    atomicAdd(z.diff_out, tot);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    uint32_t* ticket = calls_of(my) + 1;
+    if (atomicAdd(ticket, 1u) == (uint32_t)(B - 1)) {      // last block of this call
+      *ticket = 0u;
+      calls_of(my)[0] += 1u;
+      if (z.bump) z.step[0] += 1.f;
+      __threadfence();
+    }
+  }
+}
+
 __global__ void barrier_kernel(CommDev c, long long* stamp_ns) {
   __shared__ uint32_t s_epoch;
   const long long t0 = globaltimer_ns();
@@ -711,6 +892,25 @@ int hz_comm_allreduce_adam(HzComm* c, float* grad, size_t n, int algo, int wire_
   ad.p = p; ad.m = m; ad.v = v; ad.shadow = (__nv_bfloat16*)shadow; ad.prev = prev; ad.diff_out = diff_out;
   ad.step = step; ad.lr = lr; ad.b1 = b1; ad.b2 = b2; ad.eps = eps; ad.bump = bump;
   return comm_allreduce_impl(c, grad, n, algo, wire_bf16, scale, live, &ad, st);
+}
+
+// ZeRO-1 step of one bucket (zero1_kernel): n wire elements (all of the bucket, or 64 per live block), bf16 wire and
+// bf16 parameter shadow only.  m / v / prev are THIS rank's shards: hz_comm_zero1_shard(n, world) elements each.
+size_t hz_comm_zero1_shard(size_t n, int world) { return ((n / 8 + (size_t)world - 1) / (size_t)world) * 8; }
+
+int hz_comm_zero1_step(HzComm* c, float* grad, size_t n, float scale, const int* live, float* p, float* m, float* v,
+                       void* shadow, float* prev, float* diff_out, float* step, float lr, float b1, float b2, float eps,
+                       int bump, cudaStream_t st) {
+  if (n % 8 != 0) return -2;
+  if (n * 2 > c->dev.buf_bytes) return -3;
+  if (shadow == nullptr || p == nullptr || m == nullptr || v == nullptr || step == nullptr) return -6;
+  int blocks = hz_comm_blocks_for(c, n, hz::kTwoShot, 1);
+  if (blocks > hz::kZeroMaxBlocks) blocks = hz::kZeroMaxBlocks;
+  hz::ZeroFuse z;
+  z.p = p; z.m = m; z.v = v; z.shadow = (__nv_bfloat16*)shadow; z.prev = prev; z.diff_out = diff_out; z.step = step;
+  z.lr = lr; z.b1 = b1; z.b2 = b2; z.eps = eps; z.bump = bump;
+  hz::zero1_kernel<<<blocks, hz::kCommThreads, 0, st>>>(c->dev, grad, n, scale, live, z);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // Grid cap for the following collectives (same value on every rank: blocks pair up with their peers).  A bucket

@@ -89,6 +89,10 @@ int hz_comm_allreduce(struct HzComm* c, float* grad, size_t n, int algo, int wir
 int hz_comm_allreduce_adam(struct HzComm* c, float* grad, size_t n, int algo, int wire_bf16, float scale,
                            const int* live, float* p, float* m, float* v, void* shadow, float* prev, float* diff_out,
                            float* step, float lr, float b1, float b2, float eps, int bump, cudaStream_t st);
+size_t hz_comm_zero1_shard(size_t n, int world);
+int hz_comm_zero1_step(struct HzComm* c, float* grad, size_t n, float scale, const int* live, float* p, float* m, float* v,
+                       void* shadow, float* prev, float* diff_out, float* step, float lr, float b1, float b2, float eps,
+                       int bump, cudaStream_t st);
 int hz_comm_barrier(struct HzComm* c, long long* stamps, cudaStream_t st);
 int hz_comm_error(struct HzComm* c);
 void hz_comm_destroy(struct HzComm* c);

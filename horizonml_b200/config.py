@@ -38,6 +38,9 @@ class TrainConfig:
     bucket_mb: float = 25.0           # DDP-like bucket cap (MiB); reference uses DDP default 25
     overlap: bool = True              # overlap bucket all-reduce with backward
     zero1: bool = False               # ZeRO-1: shard Adam's moments over the data-parallel group (parallel/zero.py)
+    zero1_impl: str = "auto"          # fused: one peer-memory kernel per bucket (csrc/comm.cu zero1_kernel; on CPU its
+                                      # torch.distributed plumbing form) | nccl: reduce-scatter + Adam + all-gather |
+                                      # auto: fused where the peer kernels run (CUDA, native backend, bf16), else nccl
     overlap_adam: bool = False        # bucket-wise Adam right behind each bucket's all-reduce (measured: no gain on B200)
     fused_adam: bool = False          # world > 1, peer all-reduce: Adam applied inside the bucket's all-reduce kernel
                                       # (measured on B200: 0.620 vs 0.601 ms/step at 2 GPUs — the update inside the comm
@@ -113,6 +116,8 @@ def add_train_flags(p: argparse.ArgumentParser, strategy: str) -> argparse.Argum
                    help='apply Adam inside each bucket\'s all-reduce kernel instead of a separate pass')
     g.add_argument('--bucket_layout', default=d.bucket_layout, choices=["auto", "layers", "size"])
     g.add_argument('--zero1', action='store_true', help='shard the optimizer state over the data-parallel ranks')
+    g.add_argument('--zero1_impl', default=d.zero1_impl, choices=["auto", "fused", "nccl"],
+                   help='ZeRO-1 implementation: one fused peer-memory kernel per bucket, or NCCL reduce-scatter/all-gather')
     g.add_argument('--bucket_by_live', action='store_true')
     g.add_argument('--live_bucket_mb', type=float, default=d.live_bucket_mb)
     g.add_argument('--microbatches', type=int, default=d.microbatches)

@@ -53,6 +53,11 @@ class DPEngine:
         live = self.model.live_tap_masks(32) if (cfg.skip_dead_taps and hasattr(self.model, "live_tap_masks")) else None
         by_live = live is not None and (bool(cfg.bucket_by_live) or os.environ.get("HZ_BUCKET_LIVE", "0") == "1")
         self.zero1 = bool(cfg.zero1) and rt.world > 1
+        # ZeRO-1 as ONE peer-memory kernel per bucket (reduce -> Adam on the owned shard -> bf16 parameter push) where
+        # the peer kernels run; "fused" on CPU selects the same sharding on torch.distributed (tests / plumbing)
+        peer_ok = (rt.world > 1 and dev.type == "cuda" and cfg.allreduce != "nccl" and rt.backend == "native"
+                   and rt.dtype == torch.bfloat16)
+        self.zero_fused = self.zero1 and (cfg.zero1_impl == "fused" or (cfg.zero1_impl == "auto" and peer_ok))
         # Adam inside the all-reduce kernel (csrc/comm.cu AdamFuse): peer kernels only, replicated optimizer state
         self.fused_adam = (bool(cfg.fused_adam) and rt.world > 1 and not self.zero1 and dev.type == "cuda"
                            and cfg.allreduce != "nccl" and rt.backend == "native" and not cfg.overlap_adam
@@ -62,7 +67,8 @@ class DPEngine:
             # layer-group buckets: every group's all-reduce starts the moment its backward is done and the bucket that
             # is only complete after the very last gradient kernel (layer1 + stem, 157 k elements) is small enough for
             # the flag-in-data latency protocol — measured 0.601 vs 0.605 ms/step at 2 GPUs against DDP-like size caps
-            peer = rt.world > 1 and dev.type == "cuda" and cfg.allreduce != "nccl" and rt.backend == "native" and not self.zero1
+            peer = (rt.world > 1 and dev.type == "cuda" and cfg.allreduce != "nccl" and rt.backend == "native"
+                    and (not self.zero1 or self.zero_fused))
             layout = "layers" if (peer and cfg.model == "resnet18") else "size"
         starts = ("layer3.", "layer2.", "layer1.") if layout == "layers" else None
         self.flat = FlatParams(list(self.model.named_parameters()), dev, rt.dtype,
@@ -74,30 +80,36 @@ class DPEngine:
                 if b.dtype.is_floating_point:
                     dist.broadcast(b, src=0)
             self.flat.sync_shadow()
-        if self.zero1:
+        kind = cfg.allreduce
+        self.ar = (make_grad_allreduce(kind, self.flat.total, dev)
+                   if (rt.world > 1 and (not self.zero1 or (self.zero_fused and peer_ok))) else None)
+        if self.zero_fused:
+            from ..parallel.zero import FusedShardedAdam
+            self.opt = FusedShardedAdam(self.flat, self.ar if hasattr(self.ar, "handle") else None, lr=cfg.lr,
+                                        with_prev=bool(cfg.grad_divergence))
+        elif self.zero1:
             from ..parallel.zero import ShardedFlatAdam
             self.opt = ShardedFlatAdam(self.flat, lr=cfg.lr)      # reduce-scatter + sharded Adam + all-gather
         else:
             self.opt = FlatAdam(self.flat, lr=cfg.lr)
-        kind = cfg.allreduce
-        self.ar = make_grad_allreduce(kind, self.flat.total, dev) if (rt.world > 1 and not self.zero1) else None
         self.stats = DeviceStats(dev)
         ops.enable_side_stream(dev.type == "cuda" and rt.backend == "native")
         self.prev_grad = None
-        if cfg.grad_divergence:
+        if cfg.grad_divergence and not self.zero_fused:         # (the fused ZeRO optimizer keeps its own shards of it)
             self.prev_grad = torch.zeros_like(self.opt.gshard if self.zero1 else self.flat.grad)
         # bucket-wise optimizer: Adam for a bucket runs right behind that bucket's all-reduce (or, on one GPU, as
         # soon as its gradients are final) and overlaps the rest of backward
         self.bucket_adam = (bool(cfg.overlap_adam) or os.environ.get("HZ_OVERLAP_ADAM", "0") == "1") and not self.zero1
-        self._diff_acc = torch.zeros((), dtype=torch.float32, device=dev) if self.prev_grad is not None else None
+        self._diff_acc = (torch.zeros((), dtype=torch.float32, device=dev)
+                          if (self.prev_grad is not None or (self.zero_fused and cfg.grad_divergence)) else None)
         self.fused_adam = self.fused_adam and hasattr(self.ar, "allreduce_adam_")
         if self.fused_adam and self._diff_acc is None and self.prev_grad is not None:
             self._diff_acc = torch.zeros((), dtype=torch.float32, device=dev)
         self.reducer = None
         if self.ar is not None or self.bucket_adam:
+            fused = self._fused_bucket if self.fused_adam else (self._zero_bucket if self.zero_fused else None)
             self.reducer = GradReducer(self.flat, self.ar, cfg.overlap,
-                                       post_bucket=self._adam_bucket if self.bucket_adam else None,
-                                       fused_bucket=self._fused_bucket if self.fused_adam else None)
+                                       post_bucket=self._adam_bucket if self.bucket_adam else None, fused_bucket=fused)
         self._graphed = GraphedStep(self._step_impl, dev, cfg.cuda_graph)
         self.global_step = 0
 
@@ -111,6 +123,10 @@ class DPEngine:
                                        self.prev_grad[sl] if self.prev_grad is not None else None,
                                        self._diff_acc if self.prev_grad is not None else None, o.step_t, o.lr,
                                        o.betas[0], o.betas[1], o.eps, bump=last, live=f.bucket_live[b])
+
+    def _zero_bucket(self, b: int, last: bool):
+        """One kernel: reduce bucket ``b`` over the ranks, Adam on the shard this rank owns, new bf16 parameters to all."""
+        return self.opt.step_bucket(b, last, self._diff_acc)
 
     def _adam_bucket(self, b: int, first: bool) -> None:
         self.opt.step_bucket(b, first, diff_out=self._diff_acc, prev_grad=self.prev_grad)
@@ -136,6 +152,12 @@ class DPEngine:
         with nvtx_range("optimizer"):
             if self.bucket_adam or self.fused_adam:
                 diff = self._diff_acc          # every bucket's Adam has been joined by reducer.finish()
+            elif self.zero_fused:
+                if self.reducer is None:       # plumbing path (no peer communicator): buckets in gradient-ready order
+                    nb_ = len(self.flat.buckets)
+                    for b in range(nb_):
+                        self.opt.step_bucket(b, b == nb_ - 1, self._diff_acc)
+                diff = self._diff_acc
             else:
                 diff = self.opt.step(prev_grad=self.prev_grad)
         self.stats.add_step(loss, correct, labels.shape[0], diff)
@@ -149,14 +171,19 @@ class DPEngine:
     # device-timed breakdown of the step (SURVEY §5.1 / §5.5 extended columns)
     # ------------------------------------------------------------------------------------------
     def _state_tensors(self) -> List[torch.Tensor]:
-        ts = [self.flat.master, self.flat.grad, self.opt.m, self.opt.v, self.opt.step_t, self.stats.buf,
-              self.stats.has_prev]
-        if self.zero1:
+        if self.zero_fused:
+            ts = [self.flat.master, self.flat.grad] + self.opt.state_tensors() + [self.stats.buf, self.stats.has_prev]
+        else:
+            ts = [self.flat.master, self.flat.grad, self.opt.m, self.opt.v, self.opt.step_t, self.stats.buf,
+                  self.stats.has_prev]
+        if self.zero1 and not self.zero_fused:
             ts.append(self.opt.gshard)
         if self.flat.shadow is not None:
             ts.append(self.flat.shadow)
         if self.prev_grad is not None:
             ts += [self.prev_grad, self._diff_acc]
+        elif self._diff_acc is not None:
+            ts.append(self._diff_acc)
         ts += [b for b in self.model.buffers()]
         return ts
 
@@ -173,6 +200,11 @@ class DPEngine:
             return self.model.forward_loss(x, y)
 
         def comm():
+            if self.zero_fused:                  # reduction and sharded optimizer are one kernel per bucket
+                nb_ = len(self.flat.buckets)
+                for b in range(nb_):
+                    self.opt.step_bucket(b, b == nb_ - 1, self._diff_acc)
+                return
             if self.ar is None:
                 return
             for bk in self.flat.buckets:
@@ -181,8 +213,9 @@ class DPEngine:
         def restore():
             self.flat.begin_step()
 
+        opt_step = (lambda: None) if self.zero_fused else (lambda: self.opt.step(prev_grad=self.prev_grad))
         return probe_step_regions(dev, self._state_tensors(), [self.reducer], self._graphed, fwd, comm,
-                                  lambda: self.opt.step(prev_grad=self.prev_grad), restore, images, labels, iters)
+                                  opt_step, restore, images, labels, iters)
 
     def input_buffers(self):
         """Static (images, labels) buffers of the captured step, or None (eager mode / before capture)."""
@@ -337,7 +370,10 @@ def train_data_parallel(rank: int, world: int, cfg: TrainConfig, device: str):
             "strategy": "data", "world_size": world, "backend": rt.backend, "dtype": str(rt.dtype),
             "comm": rt.comm_backend, "allreduce": getattr(eng.ar, "name", None),
             "allreduce_detail": eng.ar.describe() if hasattr(eng.ar, "describe") else None,
-            "fused_adam": eng.fused_adam, "bucket_algos": eng.reducer.algos if eng.reducer is not None else None,
+            "fused_adam": eng.fused_adam,
+            "zero1": ("fused-kernel" if getattr(eng.opt, "native", False) else "fused-dist") if eng.zero_fused
+                     else ("nccl" if eng.zero1 else None),
+            "bucket_algos": eng.reducer.algos if eng.reducer is not None else None,
             "buckets": [[b.names[0], b.names[-1], b.end - b.start] for b in eng.flat.buckets],
             "graph": eng._graphed.graph is not None, "graph_error": eng._graphed.capture_error,
             "final": rec.rows[-1] if rec.rows else None})

@@ -26,6 +26,10 @@ def test_zero1_sharded_optimizer_equivalence_gloo(tmp_path):
     run("zero1_equivalence", 2, find_free_port(), str(tmp_path))
 
 
+def test_zero1_per_bucket_fused_form_equivalence_gloo(tmp_path):
+    run("zero1_fused_equivalence", 2, find_free_port(), str(tmp_path))
+
+
 def test_pp_1f1b_equivalence_gloo(tmp_path):
     run("pp_equivalence", 3, find_free_port(), str(tmp_path))
 
