@@ -639,6 +639,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       hz_conv_set_debug(nullptr);
     }
   });
+  m.def("conv_set_persist", [](int64_t mode) { return (int64_t)hz_conv_set_persist((int)mode); });
   m.def("cluster_capacity", [] { int v[4]; hz_cluster_capacity(v); return std::vector<int64_t>{v[0], v[1], v[2], v[3]}; });
   m.def("conv_bn_act_fwd", &conv_bn_act_fwd);
   m.def("stem_pack", &stem_pack);

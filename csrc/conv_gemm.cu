@@ -497,6 +497,261 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
 }
 
 // ------------------------------------------------------------------------------------------------
+// Throughput variant of igemm_kernel for grids of many waves (large --batch_size): PERSISTENT CTAs, one per SM, that
+// walk a static tile schedule with the three pipelines of the canonical sm_100 GEMM —
+//     warp 0 (one lane)  TMA producer: runs ahead across tile boundaries (the operand ring never drains)
+//     warp 1 (one lane)  tcgen05.mma issuer into TWO TMEM accumulators (2 x BLOCK_N columns), alternating per tile
+//     warps 2..5         epilogue: tcgen05.ld -> bf16 -> dedicated staging tile -> coalesced stores (+ BN sums,
+//                        + residual-gradient addend); the accumulator is handed back (tmem_empty) as soon as it is in
+//                        registers, so the MMAs of tile i+1 run under the stores of tile i
+// One-tile-per-CTA pays barrier init + TMEM alloc + descriptor prefetch + pipeline fill + a serial epilogue per tile
+// (measured: MMA ~0.6 us of a ~4.5 us CTA at batch 4096, 14-16 % of the bf16 peak); here they are paid once per SM or
+// overlapped.  Same operands, taps, parity classes, masking and epilogue arithmetic as igemm_kernel (no split-K: there
+// are more tiles than SMs).  Dispatch: hz_conv_fwd / hz_conv_dgrad via use_persistent() — opt-in (HZ_CONV_PERSIST=1 |
+// auto) until its first hardware run has passed.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPersistThreads = 192;
+template <int BLOCK_N>
+struct PersistSmem {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kStagingLd = BLOCK_N + 8;
+  static constexpr int kStagingOff = kPipeBytes;                       // dedicated: the ring is busy with the next tile
+  static constexpr int kStagingBytes = kTileM * kStagingLd * 2;
+  static constexpr int kBarOff = kStagingOff + ((kStagingBytes + 1023) / 1024) * 1024;
+  static constexpr int kTotal = kBarOff + 256 + 1024;                  // + barriers + alignment slack
+};
+
+HZ_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps only
+
+template <int BLOCK_N, bool B_MN>
+__global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const __grid_constant__ AMaps amaps,
+                                                                           const __grid_constant__ CUtensorMap bmap,
+                                                                           const __grid_constant__ IgemmParams p,
+                                                                           const int m_tiles, const int n_tiles) {
+  using S = PersistSmem<BLOCK_N>;
+  static_assert(BLOCK_N == 64, "epilogue below assumes 8 vectors per row");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  __shared__ float stat_sm[4][2][BLOCK_N];
+
+  pdl_launch();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.num_classes * n_tiles * m_tiles;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) tc::prefetch_tmap(&amaps.m[i]);
+    tc::prefetch_tmap(&bmap);
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+  pdl_wait();
+
+  // tile t -> (class, n tile, m tile), m fastest: neighbouring CTAs share the weight tile and adjacent input rows
+  auto decode = [&](int t, int& cls, int& nt, int& mt) {
+    mt = t % m_tiles;
+    const int r = t / m_tiles;
+    nt = r % n_tiles;
+    cls = r / n_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int it = 0;                                                       // ring position, continues across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int cls, nt, mt;
+        decode(t, cls, nt, mt);
+        const TapList& taps = p.cls[cls];
+        const int n0 = (p.BN == 1) ? mt / p.tiles_per_img : mt * p.BN;
+        const int h0 = (p.BN == 1) ? (mt % p.tiles_per_img) * p.BH : 0;
+        const int k_total = taps.n * p.cblocks;
+        for (int k = 0; k < k_total; ++k, ++it) {
+          const int tp = k / p.cblocks, cb = k % p.cblocks;
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          uint8_t* sa = smem + s * S::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          tc::mbar_wait(&empty[s], ph ^ 1);
+          tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
+          tc::tma_load_4d(sa, &amaps.m[taps.map[tp]], &full[s], cb * kKBlock, taps.dw[tp], h0 + taps.dh[tp], n0);
+          if (!B_MN) {
+            tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[tp] + cb * kKBlock, nt * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tc::tma_load_2d(sb + j * 8192, &bmap, &full[s], taps.bk[tp] + nt * BLOCK_N + j * 64, cb * kKBlock);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = tc::make_idesc(kTileM, BLOCK_N, false, B_MN);
+      int it = 0, acc_it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int cls, nt, mt;
+        decode(t, cls, nt, mt);
+        const int k_total = p.cls[cls].n * p.cblocks;
+        if (k_total == 0) continue;                                     // a class without taps: no accumulator used
+        const int acc = acc_it & 1;
+        const uint32_t acc_ph = (acc_it >> 1) & 1;
+        ++acc_it;
+        tc::mbar_wait(&tmem_empty[acc], acc_ph ^ 1);                    // the epilogue has drained this accumulator
+        tc::fence_after_sync();
+        const uint32_t td = tmem_d + (uint32_t)(acc * BLOCK_N);
+        for (int k = 0; k < k_total; ++k, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          tc::mbar_wait(&full[s], ph);
+          tc::fence_after_sync();
+          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < kKBlock / 16; ++kk) {
+            const uint64_t da = tc::make_sdesc(sa + kk * 32, 16, 1024);
+            const uint64_t db = B_MN ? tc::make_sdesc(sb + kk * 2048, 8192, 1024)
+                                     : tc::make_sdesc(sb + kk * 32, 16, 1024);
+            tc::umma_f16(td, da, db, idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc::umma_commit(&empty[s]);
+        }
+        tc::umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 2..5 =====================
+    __nv_bfloat16* staging = reinterpret_cast<__nv_bfloat16*>(smem + S::kStagingOff);
+    const int et = threadIdx.x - 64;                       // 0..127
+    const int ew = warp - 2;                               // staging / statistics slot of this warp
+    const int lq = warp & 3;                               // TMEM lane quarter this warp may read (warp id mod 4)
+    const int row = lq * 32 + lane;                        // accumulator row held by this thread
+    constexpr int kVecPerRow = BLOCK_N / 8;
+    constexpr int kRowsPerPass = 128 / kVecPerRow;
+    constexpr int kPasses = kTileM / kRowsPerPass;
+    const int vec = et % kVecPerRow;
+    int acc_it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int cls, nt, mt;
+      decode(t, cls, nt, mt);
+      const int n0 = (p.BN == 1) ? mt / p.tiles_per_img : mt * p.BN;
+      const int h0 = (p.BN == 1) ? (mt % p.tiles_per_img) * p.BH : 0;
+      const int k_total = p.cls[cls].n * p.cblocks;
+      // output addresses of this thread's 8 rows x 8 channels (-1: row past the last image / column past the last channel)
+      long long offs[kPasses];
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int r0 = et / kVecPerRow + i * kRowsPerPass;
+        const int wi = r0 % p.BW;
+        const int hi = (r0 / p.BW) % p.BH;
+        const int n = n0 + r0 / (p.BW * p.BH);
+        offs[i] = (n >= p.n_images || nt * BLOCK_N + vec * 8 >= p.ncols)
+                      ? -1
+                      : (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride +
+                            (long long)wi * p.out_w_stride + p.cls_out_off[cls] + nt * BLOCK_N + vec * 8;
+      }
+      bf16x8 addv[kPasses];
+      if (p.addend != nullptr) {
+#pragma unroll
+        for (int i = 0; i < kPasses; ++i)
+          if (offs[i] >= 0) addv[i] = ld8(p.addend + offs[i]);
+      }
+      if (k_total > 0) {
+        const int acc = acc_it & 1;
+        const uint32_t acc_ph = (acc_it >> 1) & 1;
+        ++acc_it;
+        tc::mbar_wait(&tmem_full[acc], acc_ph);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld32(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), r);
+          tc::tmem_ld_wait();
+          __nv_bfloat16* dst = staging + row * S::kStagingLd + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[j + i]);
+            st8(dst + j, pack8(f));
+          }
+        }
+        // the accumulator is in registers / shared memory: give it back before the (long) global stores
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+      } else {
+        float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 8) st8(staging + row * S::kStagingLd + c0, pack8(z));
+      }
+      epi_bar_sync();                                      // the whole tile is staged
+      float ssum[8], ssq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < kPasses; ++i) {
+        const int r0 = et / kVecPerRow + i * kRowsPerPass;
+        const long long off = offs[i];
+        if (off < 0) continue;
+        bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
+        if (p.stats != nullptr) {
+          float f[8];
+          unpack8(v, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { ssum[j] += f[j]; ssq[j] += f[j] * f[j]; }
+        }
+        if (p.addend != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v.v[j] = __hadd2(v.v[j], addv[i].v[j]);
+        }
+        st8(p.out + off, v);
+      }
+      if (p.stats != nullptr) {
+        // lanes l, l^8, l^16, l^24 hold the same 8 columns (different rows): fold them, then the 4 warps through smem
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 8);
+          ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 8);
+          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
+          ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            stat_sm[ew][0][lane * 8 + j] = ssum[j];
+            stat_sm[ew][1][lane * 8 + j] = ssq[j];
+          }
+        }
+        epi_bar_sync();
+        const int col = et % BLOCK_N, which = et / BLOCK_N;
+        const float tot = stat_sm[0][which][col] + stat_sm[1][which][col] + stat_sm[2][which][col] + stat_sm[3][which][col];
+        if (nt * BLOCK_N + col < p.ncols) atomicAdd(&p.stats[which * p.ncols + nt * BLOCK_N + col], tot);
+      }
+      epi_bar_sync();                                      // staging (and stat_sm) may be overwritten by the next tile
+    }
+  }
+  __syncwarp();                                            // re-converge the single-lane role warps
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_d, 2 * BLOCK_N);
+}
+
+// ------------------------------------------------------------------------------------------------
 // wgrad
 // ------------------------------------------------------------------------------------------------
 struct WgradParams {
@@ -733,6 +988,30 @@ int pick_cluster_splits(int tiles, int k_total, int (*max_clusters)(int)) {
   return s;
 }
 
+// Persistent (throughput) kernel selection: 0 never (DEFAULT: the kernel was written after the round's GPU budget was
+// spent and has not run on hardware yet — tests/test_gpu_persist.py is its first execution), 1 always, -1 auto (grids
+// of >= HZ_CONV_PERSIST_WAVES x #SMs tiles).  HZ_CONV_PERSIST = 0 | 1 | auto sets the initial mode,
+// hz_conv_set_persist() changes it at run time (tests, tools/conv_roofline.py).
+int g_persist_mode = [] { const char* e = getenv("HZ_CONV_PERSIST"); return e ? (e[0] == '1' ? 1 : (e[0] == 'a' ? -1 : 0)) : 0; }();
+bool use_persistent(int total_tiles) {
+  static const int waves = [] { const char* e = getenv("HZ_CONV_PERSIST_WAVES"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
+  if (g_persist_mode == 0 || total_tiles <= 0) return false;
+  if (g_persist_mode == 1) return true;
+  return total_tiles >= waves * hz_num_sms();
+}
+template <bool B_MN>
+int launch_persistent(const hz::AMaps& am, const CUtensorMap& bm, hz::IgemmParams& p, int m_tiles, int n_tiles,
+                      cudaStream_t st) {
+  using SM = hz::PersistSmem<64>;
+  static bool attr = set_smem(hz::igemm_persist_kernel<64, B_MN>, SM::kTotal);
+  (void)attr;
+  p.splits = 1; p.cluster = 0; p.prefetch_b = 0; p.dbg = nullptr; p.ws = nullptr; p.sem = nullptr;
+  const int total = p.num_classes * n_tiles * m_tiles;
+  const int grid = total < hz_num_sms() ? total : hz_num_sms();
+  return hz::launch(hz::igemm_persist_kernel<64, B_MN>, dim3(grid), dim3(hz::kPersistThreads), SM::kTotal, st, am, bm, p,
+                    m_tiles, n_tiles) == cudaSuccess ? 0 : -1;
+}
+
 int prefetch_weights_enabled() {
   static const int on = [] { const char* e = getenv("HZ_PREFETCH_B"); return (e && e[0] == '0') ? 0 : 1; }();
   return on;
@@ -775,6 +1054,13 @@ int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride,
 // per-CTA phase stamps (16 x int64 per CTA) for the next forward / dgrad launches; nullptr switches them off
 void hz_conv_set_debug(long long* buf) { g_conv_dbg = buf; }
 
+// persistent-kernel selection for the following forward / dgrad launches: -1 auto, 0 never, 1 always; returns the old mode
+int hz_conv_set_persist(int mode) {
+  const int old = g_persist_mode;
+  g_persist_mode = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  return old;
+}
+
 // resident clusters of the forward conv kernel for cluster sizes 1,2,4,8 (diagnostics)
 void hz_cluster_capacity(int out[4]) {
   static bool attr = set_smem(hz::igemm_kernel<64, false>, hz::IgemmSmem<64>::kTotal);
@@ -811,6 +1097,8 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   p.addend = nullptr;
   p.stats = stats;
   if (stats && !stats_is_zero) hz::zero_f32(stats, (size_t)2 * Cout, st);
+  if (bn == nullptr && use_persistent(t.tiles * ((Cout + BLOCK_N - 1) / BLOCK_N)))
+    return launch_persistent<false>(am, bm, p, t.tiles, (Cout + BLOCK_N - 1) / BLOCK_N, st);
   {
     const SplitWs w = get_split_ws();
     const int tiles = t.tiles * ((Cout + BLOCK_N - 1) / BLOCK_N);
@@ -903,6 +1191,8 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
   p.out = (__nv_bfloat16*)dx;
   p.addend = (const __nv_bfloat16*)addend;
   p.stats = nullptr;
+  if (use_persistent(t.tiles * ((Cin + BLOCK_N - 1) / BLOCK_N) * p.num_classes))
+    return launch_persistent<true>(am, bm, p, t.tiles, (Cin + BLOCK_N - 1) / BLOCK_N, st);
   {
     const SplitWs w = get_split_ws();
     const int tiles = t.tiles * ((Cin + BLOCK_N - 1) / BLOCK_N) * p.num_classes;

@@ -32,4 +32,8 @@ def pytest_collection_modifyitems(config, items):
         if "multigpu" in item.keywords and ngpu < 2:
             item.add_marker(pytest.mark.skip(reason="needs >= 2 GPUs"))
     # stable partition: everything hardware-verified first, the `late` items after it (see the marker's description)
-    items.sort(key=lambda it: 1 if "late" in it.keywords else 0)
+    # (within the late tier: ascending `order` — the cases closest to verified code first, new tcgen05 code last)
+    def rank(it):
+        m = it.get_closest_marker("late")
+        return (0, 0) if m is None else (1, int(m.kwargs.get("order", 0)))
+    items.sort(key=rank)

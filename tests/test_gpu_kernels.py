@@ -467,7 +467,7 @@ def test_allreduce_adam_fused_virtual_ranks(nb, world, algo):
             A["diff"][r].zero_()          # (the stats kernel consumes and clears the accumulator once per step)
 
 
-@pytest.mark.late
+@pytest.mark.late(order=1)
 @pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("algo", ["oneshot", "twoshot", "ll"])
 def test_peer_allreduce_alternating_grid_sizes_with_skewed_rank(nb, world, algo):

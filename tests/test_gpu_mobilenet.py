@@ -8,7 +8,7 @@ tests); the depthwise index logic is additionally run on the CPU (csrc/tests/dw_
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.late]
+pytestmark = [pytest.mark.gpu, pytest.mark.late(order=2)]
 
 DEV = "cuda:0"
 

@@ -7,7 +7,7 @@ state layout is also exercised on CPU over gloo (tests/test_dist_cpu.py::test_ze
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.late]
+pytestmark = [pytest.mark.gpu, pytest.mark.late(order=3)]
 DEV = "cuda:0"
 
 

@@ -82,7 +82,7 @@ def test_strategy_equivalence_native_kernels(tmp_path, mode):
         assert res["graphed"] and res["overlapped"]
 
 
-@pytest.mark.late
+@pytest.mark.late(order=3)
 def test_zero1_fused_kernel_trains_on_gpus(tmp_path):
     """`data_parallel_train.py --zero1` on real peers: one zero1_kernel per bucket (no NCCL collective, no separate
     optimizer pass) must train like the replicated optimizer; the run summary records which implementation ran."""

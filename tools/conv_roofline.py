@@ -2,6 +2,9 @@
 shapes for growing batch sizes, next to cuDNN (torch.nn.functional / aten) on the same tensors — where the
 hand-written kernels sit against the measured bf16 peak once the problem is large enough to be compute-bound.
 Device-timed (CUDA events, after warm-up); a 256 MiB L2 flush between timed launches.
+With HZ_CONV_PERSIST=1 (or `auto`) the forward / dgrad columns are additionally measured on the persistent kernel
+(the plain columns are then the persistent kernel's, `fwd_default_us` / `dgrad_default_us` the one-tile-per-CTA
+kernel's; igemm_persist_kernel: one CTA per SM, two TMEM accumulators, epilogue under the next tile's MMAs).
 Usage: python tools/conv_roofline.py gpurun_out/conv_roofline.json [batches...]"""
 import json
 import os
@@ -66,6 +69,11 @@ for B in batches:
                  "dgrad": timed(lambda: nb.conv_dgrad(dy, w, x.shape, s, p)),
                  "wgrad": timed(lambda: nb.conv_wgrad(dy, x, w.shape, s, p, gv, False))}
             row["native_fallbacks"] = sum(nb.FALLBACKS.values()) - before
+            if os.environ.get("HZ_CONV_PERSIST", "0")[:1] in ("1", "a"):
+                nb.C.conv_set_persist(0)        # the columns above were taken in the requested mode: add the default kernel's
+                row["fwd_default_us"] = round(timed(lambda: nb.conv_fwd(x, w, s, p, True)), 2)
+                row["dgrad_default_us"] = round(timed(lambda: nb.conv_dgrad(dy, w, x.shape, s, p)), 2)
+                nb.C.conv_set_persist(1 if os.environ["HZ_CONV_PERSIST"][:1] == "1" else -1)
             c = {"fwd": timed(lambda: tb.conv_fwd(x, w, s, p, False)),
                  "dgrad": timed(lambda: tb.conv_dgrad(dy, w, x.shape, s, p)),
                  "wgrad": timed(lambda: tb.conv_wgrad(dy, x, w.shape, s, p, gref, False))}
