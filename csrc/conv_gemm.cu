@@ -1239,7 +1239,10 @@ int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W,
   p.n_tiles = (Cin + BLOCK_N - 1) / BLOCK_N;
   const int m_tiles = (Cout + 127) / 128;
   const int ctas = m_tiles * p.n_tiles * p.taps.n;
-  int splits = (72 + ctas - 1) / ctas;      // leave SMs for the concurrently running dgrad chain
+  // small problems: leave SMs for the concurrently running dgrad chain; in throughput mode (see use_persistent) a long
+  // pixel reduction is spread over two waves of CTAs instead
+  const int target = (g_persist_mode != 0 && p.kblocks >= 512) ? 2 * hz_num_sms() : 72;
+  int splits = (target + ctas - 1) / ctas;
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits > 32) splits = 32;
   if (splits < 1) splits = 1;

@@ -136,3 +136,131 @@ def simulate_staged(grids: Sequence[int], world: int = 2, region: int = 12, per_
                     blocks[r] = _make_blocks(grids[cur[r]], region, parity_fn(r))
         bad += 1 if violated else 0
     return bad
+
+
+# ----------------------------------------------------------------------------------------------------------
+# persistent convolution kernel: operand ring + two TMEM accumulators (csrc/conv_gemm.cu igemm_persist_kernel)
+# ----------------------------------------------------------------------------------------------------------
+class _MBar:
+    """mbarrier with phase parity: ``try_wait(P)`` is true iff the phase of parity P has completed, i.e. iff the phase
+    currently in progress has the other parity (a fresh barrier: phase 0 in progress, so parity 1 passes at once — the
+    "wait on parity^1" idiom of empty barriers).  A waiter that falls two phases behind would alias; the protocol has
+    to make that impossible, which is what the model checks."""
+
+    def __init__(self, count: int):
+        self.count, self.pending, self.phase = count, count, 0
+
+    def arrive(self) -> None:
+        self.pending -= 1
+        if self.pending == 0:
+            self.pending, self.phase = self.count, self.phase + 1
+
+    def try_wait(self, parity: int) -> bool:
+        return (self.phase & 1) != parity
+
+
+def simulate_persistent_pipeline(tile_k: Sequence[int], stages: int = 6, epi_warps: int = 4, trials: int = 200,
+                                 seed: int = 0, broken: str = "") -> int:
+    """One persistent CTA working through tiles with ``tile_k[i]`` k-iterations each (0 = a class without taps: no
+    accumulator is used, the epilogue stores zeros).  Three agents with exactly the kernel's index / parity formulas:
+
+    * producer : ring slot ``it % stages``, waits ``empty[s]`` on parity ``((it // stages) & 1) ^ 1``, fills, ``full[s]``
+      completes (TMA transaction);
+    * MMA      : per tile with k > 0 takes accumulator ``acc_it & 1``, waits ``tmem_empty[acc]`` on parity
+      ``((acc_it >> 1) & 1) ^ 1``, then per k waits ``full[s]`` on ``(it // stages) & 1``, consumes, commits
+      ``empty[s]``; after the last k commits ``tmem_full[acc]`` (tcgen05.commit arrives only when the MMAs are done);
+    * epilogue : ``epi_warps`` warps, each waits ``tmem_full[acc]`` on ``(acc_it >> 1) & 1``, reads the accumulator,
+      arrives on ``tmem_empty[acc]`` (count = epi_warps).
+
+    Violation = a slot filled before its previous content was consumed, an MMA reading a slot that does not hold the
+    (tile, k) it expects, an accumulator overwritten before every epilogue warp has read it, an epilogue warp reading an
+    accumulator that does not hold its tile, or no agent able to move before all tiles are done (deadlock).
+    ``broken``: "acc_parity" drops the ^1 of the MMA's tmem_empty wait, "one_acc" uses a single accumulator without
+    waiting — the model must catch both (sanity of the model itself).  Returns the number of violating schedules."""
+    rng = random.Random(seed)
+    bad = 0
+    for _ in range(trials):
+        full = [_MBar(1) for _ in range(stages)]
+        empty = [_MBar(1) for _ in range(stages)]
+        tfull = [_MBar(1) for _ in range(2)]
+        tempty = [_MBar(epi_warps) for _ in range(2)]
+        slot = [None] * stages                   # content tag (tile, k) or None = consumed / never filled
+        acc = [None, None]                       # {"tile": t, "k": n accumulated, "readers": set of warps}
+        violated = [False]
+
+        def producer():
+            it = 0
+            for t, kt in enumerate(tile_k):
+                for k in range(kt):
+                    s = it % stages
+                    while not empty[s].try_wait(((it // stages) & 1) ^ 1):
+                        yield False
+                    if slot[s] is not None:
+                        violated[0] = True       # overwrote operands the MMA has not consumed
+                    slot[s] = (t, k)
+                    full[s].arrive()             # TMA completes the transaction bytes
+                    it += 1
+                    yield True
+
+        def mma():
+            it = acc_it = 0
+            for t, kt in enumerate(tile_k):
+                if kt == 0:
+                    continue
+                a = 0 if broken == "one_acc" else (acc_it & 1)
+                par = (acc_it >> 1) & 1
+                acc_it += 1
+                if broken != "one_acc":
+                    while not tempty[a].try_wait(par if broken == "acc_parity" else par ^ 1):
+                        yield False
+                if acc[a] is not None and len(acc[a]["readers"]) < epi_warps:
+                    violated[0] = True           # accumulator overwritten while an epilogue warp still has to read it
+                acc[a] = {"tile": t, "k": 0, "readers": set()}
+                for k in range(kt):
+                    s = it % stages
+                    while not full[s].try_wait((it // stages) & 1):
+                        yield False
+                    if slot[s] != (t, k):
+                        violated[0] = True       # wrong operands under the tensor core
+                    slot[s] = None
+                    acc[a]["k"] += 1
+                    empty[s].arrive()            # tcgen05.commit -> empty[s]
+                    it += 1
+                    yield True
+                tfull[a].arrive()                # tcgen05.commit -> tmem_full[acc]
+                yield True
+
+        def epilogue(wid):
+            acc_it = 0
+            for t, kt in enumerate(tile_k):
+                if kt == 0:
+                    yield True                   # zeros from registers, no accumulator involved
+                    continue
+                a = 0 if broken == "one_acc" else (acc_it & 1)
+                par = (acc_it >> 1) & 1
+                acc_it += 1
+                while not tfull[a].try_wait(par):
+                    yield False
+                if acc[a] is None or acc[a]["tile"] != t or acc[a]["k"] != kt:
+                    violated[0] = True           # read an accumulator that is not (all of) this tile
+                else:
+                    acc[a]["readers"].add(wid)
+                tempty[a].arrive()
+                yield True
+
+        agents = [producer(), mma()] + [epilogue(w) for w in range(epi_warps)]
+        alive = list(range(len(agents)))
+        stuck = 0
+        while alive and not violated[0]:
+            i = rng.choice(alive)
+            try:
+                progressed = next(agents[i])
+            except StopIteration:
+                alive.remove(i)
+                stuck = 0
+                continue
+            stuck = 0 if progressed else stuck + 1
+            if stuck > 50 * len(agents) * (stages + 4):
+                violated[0] = True               # nobody can move: deadlock
+        bad += 1 if violated[0] else 0
+    return bad

@@ -220,3 +220,19 @@ def test_mobilenet_trains_through_the_dp_engine():
         prev = cur
     assert len(eng.flat.params) == 158
     assert losses[-1] < 0.5 * losses[0], losses
+
+
+def test_protocol_model_persistent_conv_pipeline():
+    """The three pipelines of the persistent convolution kernel (operand ring, two TMEM accumulators, epilogue warps —
+    csrc/conv_gemm.cu igemm_persist_kernel) with the kernel's own slot / parity formulas under random interleavings:
+    no slot or accumulator is overwritten before it is consumed, nobody reads the wrong tile, nothing deadlocks —
+    including tiles without any k-iteration (tap-less dgrad classes).  The model catches a dropped parity flip and a
+    single unguarded accumulator."""
+    from horizonml_b200.utils.protocol_model import simulate_persistent_pipeline as sim
+    assert sim([9] * 7, trials=150) == 0
+    assert sim([9, 0, 0, 9, 1, 18, 0, 3, 9], trials=150, seed=1) == 0
+    assert sim([1] * 40, trials=100, seed=2) == 0                  # ring wraps many times, accumulators alternate per k
+    assert sim([18] * 5, stages=2, trials=100, seed=3) == 0
+    assert sim([0, 0, 0], trials=10) == 0
+    assert sim([9] * 7, trials=50, broken="acc_parity") == 50
+    assert sim([2] * 7, trials=50, broken="one_acc") > 25

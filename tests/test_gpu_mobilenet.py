@@ -60,12 +60,12 @@ def test_depthwise_conv(nb, tb, cfg):
     tb.dwconv_wgrad(dy.float(), x.float(), s, ref, False)
     dw = torch.full((C, 1, 3, 3), 7.0, device=DEV)
     nb.dwconv_wgrad(dy, x, s, dw, False)                       # overwrite: stale contents must not survive
-    assert rel_err(dw, ref) < 2e-3
+    assert rel_err(dw, ref) < 1e-2
     nb.dwconv_wgrad(dy, x, s, dw, True)                        # accumulate
-    assert rel_err(dw, 2 * ref) < 2e-3
+    assert rel_err(dw, 2 * ref) < 1e-2
     dz = torch.zeros(C, 1, 3, 3, device=DEV)
     nb.dwconv_wgrad(dy, x, s, dz, False, True)                 # pre-zeroed by the optimizer pass: no clear kernel
-    assert rel_err(dz, ref) < 2e-3
+    assert rel_err(dz, ref) < 1e-2
     assert sum(nb.FALLBACKS.values()) == before, dict(nb.FALLBACKS)
 
 

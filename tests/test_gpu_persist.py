@@ -97,6 +97,19 @@ def test_persistent_dgrad(nb, tb, persist, cfg, with_addend):
     assert rel_err(dx, dx0) < 8e-3
 
 
+@pytest.mark.parametrize("cfg", [SHAPES[1], SHAPES[2], SHAPES[8]])
+def test_throughput_mode_wgrad_splits(nb, tb, persist, cfg):
+    """In throughput mode a long pixel reduction (>= 512 k-blocks of 64 pixels) is split over two waves of CTAs."""
+    x, w, dy, _ = _data(cfg, seed=3)
+    s, p = cfg[6], cfg[7]
+    Cout, Cin, R = cfg[4], cfg[1], cfg[5]
+    gv = torch.zeros(Cout, R, R, Cin, device=DEV).permute(0, 3, 1, 2)          # storage [Cout, R, S, Cin]
+    ref = torch.zeros(Cout, Cin, R, R, device=DEV)
+    nb.conv_wgrad(dy, x, w.shape, s, p, gv, False)
+    tb.conv_wgrad(dy.float(), x.float(), w.shape, s, p, ref, False)
+    assert rel_err(gv, ref) < 2e-2
+
+
 def test_persistent_kernel_in_a_training_step(nb, persist):
     """ResNet-18 forward + backward + Adam at batch 64 with every forward / dgrad convolution on the persistent kernel:
     loss and gradient must match the default kernels' (same seed, same data), and training must make progress."""
