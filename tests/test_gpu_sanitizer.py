@@ -1,0 +1,45 @@
+"""compute-sanitizer over the kernel numerics tests: the GPU test run itself executes ``memcheck`` on the
+hardware-verified SIMT kernels (BatchNorm forward / backward, max-pool, classifier head, fused Adam) and on one tcgen05 /
+TMA convolution, and requires ``ERROR SUMMARY: 0 errors`` — so every GPU test log carries a sanitizer verdict
+(`tools/sanitize.sh` runs the full memcheck / synccheck / racecheck passes by hand).
+
+`late`: written after the round's GPU budget was spent.  The sanitizer slows kernels 10-50x and python start-up under it
+takes a minute, so the selection is small and a run that does not finish inside its time box is a skip, not a failure."""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _memcheck(selection: str, files, budget_s: int):
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    env = dict(os.environ, HZ_PDL="0")          # plain stream order: the sanitizer serialises kernels anyway
+    cmd = [exe, "--tool", "memcheck", "--error-exitcode", "9", "--launch-timeout", "120", sys.executable, "-m", "pytest",
+           *files, "-q", "-x", "-m", "gpu and not late", "-k", selection, "-p", "no:cacheprovider"]
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=budget_s)
+    except subprocess.TimeoutExpired:
+        pytest.skip(f"compute-sanitizer run did not finish within {budget_s} s")
+    out = r.stdout + r.stderr
+    if "ERROR SUMMARY" not in out:
+        pytest.skip("compute-sanitizer produced no summary (tool could not attach?): " + out[-400:].replace("\n", " | "))
+    assert "ERROR SUMMARY: 0 errors" in out and r.returncode == 0, out[-3000:]
+    assert " passed" in out, out[-1500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.late(order=5)
+def test_memcheck_clean_on_elementwise_kernels():
+    _memcheck("test_bn_act or test_maxpool or test_head or test_adam_and_graddiff", ["tests/test_gpu_kernels.py"], 420)
+
+
+@pytest.mark.gpu
+@pytest.mark.late(order=10)
+def test_memcheck_clean_on_a_tcgen05_convolution():
+    _memcheck("(test_conv_fwd_tcgen05 or test_conv_dgrad or test_conv_wgrad_tcgen05) and cfg0", ["tests/test_gpu_kernels.py"], 420)
