@@ -513,9 +513,10 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
 constexpr int kPersistThreads = 192;
 template <int BLOCK_N>
 struct PersistSmem {
+  static constexpr int kNumStages = BLOCK_N == 64 ? 6 : 5;             // 24 KB / 32 KB operand stages
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kPipeBytes = kNumStages * kStageBytes;
   static constexpr int kStagingLd = BLOCK_N + 8;
   static constexpr int kStagingOff = kPipeBytes;                       // dedicated: the ring is busy with the next tile
   static constexpr int kStagingBytes = kTileM * kStagingLd * 2;
@@ -525,21 +526,25 @@ struct PersistSmem {
 
 HZ_DEVINL void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps only
 
+// BLOCK_N = 64 | 128 output columns per tile (128: the activation tile is fetched once per 128 output channels instead
+// of once per 64 — layers with >= 128 output channels); the epilogue works in 64-column halves either way.
 template <int BLOCK_N, bool B_MN>
 __global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const __grid_constant__ AMaps amaps,
                                                                            const __grid_constant__ CUtensorMap bmap,
                                                                            const __grid_constant__ IgemmParams p,
                                                                            const int m_tiles, const int n_tiles) {
   using S = PersistSmem<BLOCK_N>;
-  static_assert(BLOCK_N == 64, "epilogue below assumes 8 vectors per row");
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128, "epilogue below works in 64-column halves");
+  constexpr int NS = S::kNumStages;
+  constexpr int kHalves = BLOCK_N / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
-  uint64_t* empty = full + kStages;
-  uint64_t* tmem_full = empty + kStages;          // [2]
+  uint64_t* empty = full + NS;
+  uint64_t* tmem_full = empty + NS;               // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  __shared__ float stat_sm[4][2][BLOCK_N];
+  __shared__ float stat_sm[4][2][64];
 
   pdl_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -547,7 +552,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) tc::prefetch_tmap(&amaps.m[i]);
     tc::prefetch_tmap(&bmap);
-    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NS; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 4); }
     tc::fence_barrier_init();
   }
@@ -582,18 +587,18 @@ __global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const
         const int k_total = taps.n * p.cblocks;
         for (int k = 0; k < k_total; ++k, ++it) {
           const int tp = k / p.cblocks, cb = k % p.cblocks;
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
           uint8_t* sa = smem + s * S::kStageBytes;
           uint8_t* sb = sa + kABytes;
           tc::mbar_wait(&empty[s], ph ^ 1);
           tc::mbar_arrive_expect_tx(&full[s], S::kStageBytes);
           tc::tma_load_4d(sa, &amaps.m[taps.map[tp]], &full[s], cb * kKBlock, taps.dw[tp], h0 + taps.dh[tp], n0);
           if (!B_MN) {
-            tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[tp] + cb * kKBlock, nt * BLOCK_N);
+            tc::tma_load_2d(sb, &bmap, &full[s], taps.bk[tp] + cb * kKBlock, nt * BLOCK_N);      // box: 64 k x BLOCK_N rows
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
+            for (int j = 0; j < BLOCK_N / 64; ++j)                                               // 64-column MN atoms
               tc::tma_load_2d(sb + j * 8192, &bmap, &full[s], taps.bk[tp] + nt * BLOCK_N + j * 64, cb * kKBlock);
           }
         }
@@ -616,8 +621,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const
         tc::fence_after_sync();
         const uint32_t td = tmem_d + (uint32_t)(acc * BLOCK_N);
         for (int k = 0; k < k_total; ++k, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
           tc::mbar_wait(&full[s], ph);
           tc::fence_after_sync();
           const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
@@ -638,10 +643,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const
     // ===================== epilogue: warps 2..5 =====================
     __nv_bfloat16* staging = reinterpret_cast<__nv_bfloat16*>(smem + S::kStagingOff);
     const int et = threadIdx.x - 64;                       // 0..127
-    const int ew = warp - 2;                               // staging / statistics slot of this warp
+    const int ew = warp - 2;                               // statistics slot of this warp
     const int lq = warp & 3;                               // TMEM lane quarter this warp may read (warp id mod 4)
     const int row = lq * 32 + lane;                        // accumulator row held by this thread
-    constexpr int kVecPerRow = BLOCK_N / 8;
+    constexpr int kVecPerRow = 8;                          // per 64-column half
     constexpr int kRowsPerPass = 128 / kVecPerRow;
     constexpr int kPasses = kTileM / kRowsPerPass;
     const int vec = et % kVecPerRow;
@@ -652,24 +657,17 @@ __global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const
       const int n0 = (p.BN == 1) ? mt / p.tiles_per_img : mt * p.BN;
       const int h0 = (p.BN == 1) ? (mt % p.tiles_per_img) * p.BH : 0;
       const int k_total = p.cls[cls].n * p.cblocks;
-      // output addresses of this thread's 8 rows x 8 channels (-1: row past the last image / column past the last channel)
-      long long offs[kPasses];
+      // element offset of (row, column 0) for this thread's 8 rows; -1: row past the last image
+      long long rowoff[kPasses];
 #pragma unroll
       for (int i = 0; i < kPasses; ++i) {
         const int r0 = et / kVecPerRow + i * kRowsPerPass;
         const int wi = r0 % p.BW;
         const int hi = (r0 / p.BW) % p.BH;
         const int n = n0 + r0 / (p.BW * p.BH);
-        offs[i] = (n >= p.n_images || nt * BLOCK_N + vec * 8 >= p.ncols)
-                      ? -1
-                      : (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride +
-                            (long long)wi * p.out_w_stride + p.cls_out_off[cls] + nt * BLOCK_N + vec * 8;
-      }
-      bf16x8 addv[kPasses];
-      if (p.addend != nullptr) {
-#pragma unroll
-        for (int i = 0; i < kPasses; ++i)
-          if (offs[i] >= 0) addv[i] = ld8(p.addend + offs[i]);
+        rowoff[i] = n >= p.n_images ? -1
+                                    : (long long)n * p.out_n_stride + (long long)(h0 + hi) * p.out_h_stride +
+                                          (long long)wi * p.out_w_stride + p.cls_out_off[cls];
       }
       if (k_total > 0) {
         const int acc = acc_it & 1;
@@ -691,7 +689,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const
             st8(dst + j, pack8(f));
           }
         }
-        // the accumulator is in registers / shared memory: give it back before the (long) global stores
+        // the accumulator is in shared memory: give it back before the (long) global stores
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
@@ -700,49 +698,60 @@ __global__ void __launch_bounds__(kPersistThreads, 1) igemm_persist_kernel(const
         for (int c0 = 0; c0 < BLOCK_N; c0 += 8) st8(staging + row * S::kStagingLd + c0, pack8(z));
       }
       epi_bar_sync();                                      // the whole tile is staged
-      float ssum[8], ssq[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
-#pragma unroll
-      for (int i = 0; i < kPasses; ++i) {
-        const int r0 = et / kVecPerRow + i * kRowsPerPass;
-        const long long off = offs[i];
-        if (off < 0) continue;
-        bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
-        if (p.stats != nullptr) {
-          float f[8];
-          unpack8(v, f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { ssum[j] += f[j]; ssq[j] += f[j] * f[j]; }
-        }
+#pragma unroll 1
+      for (int half = 0; half < kHalves; ++half) {
+        const int cbase = nt * BLOCK_N + half * 64;        // first output column of this half
+        const bool col_ok = cbase + vec * 8 < p.ncols;     // columns past the last channel are not stored
+        bf16x8 addv[kPasses];
         if (p.addend != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v.v[j] = __hadd2(v.v[j], addv[i].v[j]);
+          for (int i = 0; i < kPasses; ++i)
+            if (rowoff[i] >= 0 && col_ok) addv[i] = ld8(p.addend + rowoff[i] + cbase + vec * 8);
         }
-        st8(p.out + off, v);
-      }
-      if (p.stats != nullptr) {
-        // lanes l, l^8, l^16, l^24 hold the same 8 columns (different rows): fold them, then the 4 warps through smem
+        float ssum[8], ssq[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 8);
-          ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 8);
-          ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
-          ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 16);
+        for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPasses; ++i) {
+          const int r0 = et / kVecPerRow + i * kRowsPerPass;
+          if (rowoff[i] < 0 || !col_ok) continue;          // zero-filled rows add nothing to the sums
+          bf16x8 v = ld8(staging + r0 * S::kStagingLd + half * 64 + vec * 8);
+          if (p.stats != nullptr) {
+            float f[8];
+            unpack8(v, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ssum[j] += f[j]; ssq[j] += f[j] * f[j]; }
+          }
+          if (p.addend != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v.v[j] = __hadd2(v.v[j], addv[i].v[j]);
+          }
+          st8(p.out + rowoff[i] + cbase + vec * 8, v);
         }
-        if (lane < 8) {
+        if (p.stats != nullptr) {
+          // lanes l, l^8, l^16, l^24 hold the same 8 columns (different rows): fold them, then the 4 warps through smem
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            stat_sm[ew][0][lane * 8 + j] = ssum[j];
-            stat_sm[ew][1][lane * 8 + j] = ssq[j];
+            ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 8);
+            ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 8);
+            ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
+            ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 16);
           }
+          if (lane < 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              stat_sm[ew][0][lane * 8 + j] = ssum[j];
+              stat_sm[ew][1][lane * 8 + j] = ssq[j];
+            }
+          }
+          epi_bar_sync();
+          const int col = et % 64, which = et / 64;        // 128 threads = 64 columns x {sum, sum of squares}
+          const float tot = stat_sm[0][which][col] + stat_sm[1][which][col] + stat_sm[2][which][col] + stat_sm[3][which][col];
+          if (cbase + col < p.ncols) atomicAdd(&p.stats[which * p.ncols + cbase + col], tot);
+          epi_bar_sync();                                  // stat_sm is rewritten by the next half / tile
         }
-        epi_bar_sync();
-        const int col = et % BLOCK_N, which = et / BLOCK_N;
-        const float tot = stat_sm[0][which][col] + stat_sm[1][which][col] + stat_sm[2][which][col] + stat_sm[3][which][col];
-        if (nt * BLOCK_N + col < p.ncols) atomicAdd(&p.stats[which * p.ncols + nt * BLOCK_N + col], tot);
       }
-      epi_bar_sync();                                      // staging (and stat_sm) may be overwritten by the next tile
+      epi_bar_sync();                                      // staging may be overwritten by the next tile
     }
   }
   __syncwarp();                                            // re-converge the single-lane role warps
@@ -996,20 +1005,26 @@ int g_persist_mode = [] { const char* e = getenv("HZ_CONV_PERSIST"); return e ? 
 bool use_persistent(int total_tiles) {
   static const int waves = [] { const char* e = getenv("HZ_CONV_PERSIST_WAVES"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
   if (g_persist_mode == 0 || total_tiles <= 0) return false;
-  if (g_persist_mode == 1) return true;
+  if (g_persist_mode >= 1) return true;
   return total_tiles >= waves * hz_num_sms();
 }
-template <bool B_MN>
-int launch_persistent(const hz::AMaps& am, const CUtensorMap& bm, hz::IgemmParams& p, int m_tiles, int n_tiles,
-                      cudaStream_t st) {
-  using SM = hz::PersistSmem<64>;
-  static bool attr = set_smem(hz::igemm_persist_kernel<64, B_MN>, SM::kTotal);
+template <int BLOCK_N, bool B_MN>
+int launch_persistent_n(const hz::AMaps& am, const CUtensorMap& bm, hz::IgemmParams& p, int m_tiles, cudaStream_t st) {
+  using SM = hz::PersistSmem<BLOCK_N>;
+  static bool attr = set_smem(hz::igemm_persist_kernel<BLOCK_N, B_MN>, SM::kTotal);
   (void)attr;
   p.splits = 1; p.cluster = 0; p.prefetch_b = 0; p.dbg = nullptr; p.ws = nullptr; p.sem = nullptr;
+  const int n_tiles = (p.ncols + BLOCK_N - 1) / BLOCK_N;
   const int total = p.num_classes * n_tiles * m_tiles;
   const int grid = total < hz_num_sms() ? total : hz_num_sms();
-  return hz::launch(hz::igemm_persist_kernel<64, B_MN>, dim3(grid), dim3(hz::kPersistThreads), SM::kTotal, st, am, bm, p,
-                    m_tiles, n_tiles) == cudaSuccess ? 0 : -1;
+  return hz::launch(hz::igemm_persist_kernel<BLOCK_N, B_MN>, dim3(grid), dim3(hz::kPersistThreads), SM::kTotal, st, am, bm,
+                    p, m_tiles, n_tiles) == cudaSuccess ? 0 : -1;
+}
+// 128-column tiles when the output has >= 128 channels in whole 128-column tiles (mode 2 / HZ_CONV_PERSIST_N=64 pin 64)
+bool persist_wide(int ncols) {
+  static const int pin = [] { const char* e = getenv("HZ_CONV_PERSIST_N"); return e ? atoi(e) : 0; }();
+  if (pin == 64 || g_persist_mode == 2) return false;
+  return ncols >= 128 && ncols % 128 == 0;
 }
 
 int prefetch_weights_enabled() {
@@ -1054,10 +1069,11 @@ int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride,
 // per-CTA phase stamps (16 x int64 per CTA) for the next forward / dgrad launches; nullptr switches them off
 void hz_conv_set_debug(long long* buf) { g_conv_dbg = buf; }
 
-// persistent-kernel selection for the following forward / dgrad launches: -1 auto, 0 never, 1 always; returns the old mode
+// persistent-kernel selection for the following forward / dgrad launches: -1 auto, 0 never, 1 always (128-column tiles
+// where the channel count allows), 2 always with 64-column tiles only; returns the old mode
 int hz_conv_set_persist(int mode) {
   const int old = g_persist_mode;
-  g_persist_mode = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  g_persist_mode = mode < 0 ? -1 : (mode > 2 ? 1 : mode);
   return old;
 }
 
@@ -1097,8 +1113,14 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
   p.addend = nullptr;
   p.stats = stats;
   if (stats && !stats_is_zero) hz::zero_f32(stats, (size_t)2 * Cout, st);
-  if (bn == nullptr && use_persistent(t.tiles * ((Cout + BLOCK_N - 1) / BLOCK_N)))
-    return launch_persistent<false>(am, bm, p, t.tiles, (Cout + BLOCK_N - 1) / BLOCK_N, st);
+  if (bn == nullptr && use_persistent(t.tiles * ((Cout + BLOCK_N - 1) / BLOCK_N))) {
+    if (persist_wide(Cout)) {
+      CUtensorMap bm2;      // weight box of 128 rows (output channels)
+      if (!make_map2(&bm2, w, (long long)R * S_ * Cin, Cout, (long long)R * S_ * Cin, 64, 128)) return -12;
+      return launch_persistent_n<128, false>(am, bm2, p, t.tiles, st);
+    }
+    return launch_persistent_n<64, false>(am, bm, p, t.tiles, st);
+  }
   {
     const SplitWs w = get_split_ws();
     const int tiles = t.tiles * ((Cout + BLOCK_N - 1) / BLOCK_N);
@@ -1192,7 +1214,8 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
   p.addend = (const __nv_bfloat16*)addend;
   p.stats = nullptr;
   if (use_persistent(t.tiles * ((Cin + BLOCK_N - 1) / BLOCK_N) * p.num_classes))
-    return launch_persistent<true>(am, bm, p, t.tiles, (Cin + BLOCK_N - 1) / BLOCK_N, st);
+    return persist_wide(Cin) ? launch_persistent_n<128, true>(am, bm, p, t.tiles, st)      // same 64 x 64 weight boxes,
+                             : launch_persistent_n<64, true>(am, bm, p, t.tiles, st);      // two MN atoms per stage
   {
     const SplitWs w = get_split_ws();
     const int tiles = t.tiles * ((Cin + BLOCK_N - 1) / BLOCK_N) * p.num_classes;

@@ -34,10 +34,11 @@ def tb():
     return torch_backend
 
 
-@pytest.fixture()
-def persist(nb):
-    old = nb.C.conv_set_persist(1)
-    yield
+@pytest.fixture(params=[1, 2], ids=["wide", "n64"])
+def persist(nb, request):
+    """1: 128-column tiles where the channel count is a multiple of 128 (else 64), 2: 64-column tiles everywhere."""
+    old = nb.C.conv_set_persist(request.param)
+    yield request.param
     nb.C.conv_set_persist(old)
 
 
@@ -78,7 +79,7 @@ def test_persistent_forward(nb, tb, persist, cfg):
     assert none is None and torch.equal(y, y2)                     # deterministic, with and without the BN sums
     nb.C.conv_set_persist(0)                                       # the hardware-verified kernel on the same operands
     y0, st0 = nb.conv_fwd(x, w, s, p, True)
-    nb.C.conv_set_persist(1)
+    nb.C.conv_set_persist(persist)
     assert rel_err(y, y0) < 8e-3 and rel_err(stats, st0) < 5e-3    # (cluster split-K there may reorder the fp32 sum: 1 bf16 ulp)
 
 
@@ -93,7 +94,7 @@ def test_persistent_dgrad(nb, tb, persist, cfg, with_addend):
     assert rel_err(dx, ref) < 2e-2
     nb.C.conv_set_persist(0)
     dx0 = nb.conv_dgrad(dy, w, x.shape, s, p, a)
-    nb.C.conv_set_persist(1)
+    nb.C.conv_set_persist(persist)
     assert rel_err(dx, dx0) < 8e-3
 
 
@@ -122,7 +123,7 @@ def test_persistent_kernel_in_a_training_step(nb, persist):
     res = {}
     try:
         ops.set_backend("native")
-        for mode in (1, 0):
+        for mode in (persist, 0):
             nb.C.conv_set_persist(mode)
             model = resnet18(10, seed=0).to(DEV).train()
             flat = FlatParams(list(model.named_parameters()), DEV, torch.bfloat16)
@@ -141,7 +142,7 @@ def test_persistent_kernel_in_a_training_step(nb, persist):
             res[("loss", mode)] = losses
     finally:
         ops.set_backend("torch")
-    l1, l0 = res[("loss", 1)], res[("loss", 0)]
+    l1, l0 = res[("loss", persist)], res[("loss", 0)]
     assert all(v == v for v in l1) and abs(l1[0] - l0[0]) < 2e-2 * max(1.0, abs(l0[0])) and l1[-1] < l1[0]
-    cos = torch.nn.functional.cosine_similarity(res[1].flatten(), res[0].flatten(), dim=0).item()
+    cos = torch.nn.functional.cosine_similarity(res[persist].flatten(), res[0].flatten(), dim=0).item()
     assert cos > 0.9, cos          # (two runs of the SAME kernels differ by cos 0.95-0.99: fp32 atomics reorder)
