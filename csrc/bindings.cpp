@@ -419,7 +419,7 @@ class PeerComm {
     TORCH_CHECK(grad.is_cuda() && grad.scalar_type() == at::kFloat && grad.is_contiguous());
     const bool has_live = live_blocks.has_value() && live_blocks->defined();
     if (has_live) TORCH_CHECK(live_blocks->scalar_type() == at::kInt && live_blocks->is_cuda());
-    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : algo == "ll" ? 3 : -1;
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : algo == "ll" ? 3 : algo == "bulk" ? 4 : -1;
     TORCH_CHECK(a >= 0, "unknown all-reduce algorithm ", algo);
     c10::cuda::CUDAGuard g(grad.device());
     const size_t n = has_live ? (size_t)live_blocks->numel() * 64 : (size_t)grad.numel();
@@ -436,7 +436,7 @@ class PeerComm {
     TORCH_CHECK(master.numel() == grad.numel() && m.numel() == grad.numel() && v.numel() == grad.numel());
     const bool has_live = live_blocks.has_value() && live_blocks->defined();
     if (has_live) TORCH_CHECK(live_blocks->scalar_type() == at::kInt && live_blocks->is_cuda());
-    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : algo == "ll" ? 3 : -1;
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "nvls" ? 2 : algo == "ll" ? 3 : algo == "bulk" ? 4 : -1;
     TORCH_CHECK(a >= 0, "unknown all-reduce algorithm ", algo);
     c10::cuda::CUDAGuard g(grad.device());
     const size_t n = has_live ? (size_t)live_blocks->numel() * 64 : (size_t)grad.numel();
@@ -473,7 +473,7 @@ class PeerComm {
   }
   int64_t zero1_shard(int64_t n_wire) { return (int64_t)hz_comm_zero1_shard((size_t)n_wire, world_); }
   int64_t blocks_for(int64_t n, const std::string& algo, bool wire_bf16) {
-    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "ll" ? 3 : 2;
+    int a = algo == "oneshot" ? 0 : algo == "twoshot" ? 1 : algo == "ll" ? 3 : algo == "bulk" ? 4 : 2;
     return hz_comm_blocks_for(c_, (size_t)n, a, wire_bf16 ? 1 : 0);
   }
   void set_block_cap(int64_t cap) { hz_comm_set_block_cap(c_, (int)cap); }

@@ -21,6 +21,7 @@
 // parameters: no gradient round trip through HBM, no separate optimizer kernel waiting for "all buckets".
 #include "common.cuh"
 #include "launchers.h"
+#include "tc05.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -174,7 +175,7 @@ HZ_DEVINL void store_grad(float* g, size_t off, const float* f) {
     reinterpret_cast<float4*>(g + off)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
 }
 
-enum Algo { kOneShot = 0, kTwoShot = 1, kNvls = 2, kLL = 3 };
+enum Algo { kOneShot = 0, kTwoShot = 1, kNvls = 2, kLL = 3, kBulk = 4 };
 constexpr size_t kLLMaxElems = 512 * 1024;            // largest bucket the latency protocol takes (bf16 wire)
 constexpr size_t kLLSlotBytes = kLLMaxElems * 4;      // one rank's slot: 4 wire bytes per element ({2 bf16, flag} words)
 
@@ -718,6 +719,95 @@ __global__ void __launch_bounds__(kCommThreads) zero1_kernel(CommDev c, float* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-shot all-reduce whose reduce phase PULLS with bulk async copies (algo "bulk"): instead of every thread loading one
+// 16-byte vector from each peer into registers (~32 KB in flight per CTA: the staged kernels need ~100 CTAs to fill
+// NVLink, and lose bandwidth under the 32-CTA background cap), one elected thread streams 8 KB chunks of all W peers'
+// staging buffers into a 3-deep shared-memory ring with cp.async.bulk (completion on an mbarrier, W x 8 KB per stage:
+// up to 192 KB in flight per CTA), and the CTA sums from shared memory in rank order.  Same pack / flag barrier /
+// parity / ticket protocol and the same arithmetic (bit-identical results) as allreduce_kernel<.., kOneShot, false>.
+// The copy engine path is the one the fused tensor-parallel kernels' pull uses (csrc/tp_fused.cu, measured there).
+// Selected explicitly (`--allreduce peer-bulk` / PeerComm.allreduce(.., "bulk", ..)); not part of the auto rule yet:
+// written after the round's GPU budget was spent, untimed.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBulkChunkVec = 512;          // 16-byte vectors per peer and ring stage (8 KB) = one per thread
+constexpr int kBulkStages = 3;
+HZ_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kCommThreads) allreduce_bulk_kernel(CommDev c, float* __restrict__ grad, size_t n,
+                                                                      float scale, const int* __restrict__ live) {
+  using Wt = Wire<kBf16>;
+  constexpr int V = Wt::kVec;
+  static_assert(kBulkChunkVec == kCommThreads, "one vector per thread and chunk");
+  extern __shared__ __align__(128) uint8_t bulk_ring[];          // [kBulkStages][W][kBulkChunkVec] uint4
+  __shared__ uint32_t s_epoch;
+  __shared__ __align__(8) uint64_t full[kBulkStages], empty[kBulkStages];
+  const int W = c.world, B = gridDim.x, b = blockIdx.x;
+  const size_t nv = n / V;
+  char* my = c.base[c.rank];
+  const uint32_t parity = calls_of(my)[0] & 1u;
+  const size_t stage_off = kFlagBytes + (size_t)parity * c.buf_bytes;
+  uint4* my_stage = reinterpret_cast<uint4*>(my + stage_off);
+  uint4* ring = reinterpret_cast<uint4*>(bulk_ring);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBulkStages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], kCommThreads / 32); }
+    tc::fence_barrier_init();
+  }
+  const size_t per = (nv + B - 1) / B;
+  const size_t lo = min((size_t)b * per, nv), hi = min(lo + per, nv);
+  pack_range<kBf16>(grad, my_stage, lo, hi, scale, live);
+  peer_block_barrier(c, &s_epoch);                       // (its __syncthreads also publish the mbarrier inits)
+
+  const int nchunks = (int)((hi - lo + kBulkChunkVec - 1) / kBulkChunkVec);
+  auto issue = [&](int ck) {                             // thread 0: request chunk ck of every peer into ring slot ck % S
+    const int s = ck % kBulkStages;
+    const uint32_t ph = (ck / kBulkStages) & 1;
+    const size_t v0 = lo + (size_t)ck * kBulkChunkVec;
+    const uint32_t bytes = (uint32_t)(min((size_t)kBulkChunkVec, hi - v0) * 16);
+    tc::mbar_wait(&empty[s], ph ^ 1);                    // every warp is done with the previous content of the slot
+    tc::mbar_arrive_expect_tx(&full[s], (uint32_t)W * bytes);
+    for (int d = 0; d < W; ++d) {
+      const int r = (c.rank + d) % W;                    // own copy first, peers staggered
+      bulk_g2s(ring + ((size_t)s * W + r) * kBulkChunkVec, c.base[r] + stage_off + v0 * 16, bytes, &full[s]);
+    }
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");     // the peers' staging stores (seen through the flag barrier) -> async proxy
+    for (int ck = 0; ck < kBulkStages - 1 && ck < nchunks; ++ck) issue(ck);
+  }
+  for (int ck = 0; ck < nchunks; ++ck) {
+    if (threadIdx.x == 0 && ck + kBulkStages - 1 < nchunks) issue(ck + kBulkStages - 1);
+    __syncwarp();
+    const int s = ck % kBulkStages;
+    const uint32_t ph = (ck / kBulkStages) & 1;
+    tc::mbar_wait(&full[s], ph);
+    const size_t v = lo + (size_t)ck * kBulkChunkVec + threadIdx.x;
+    if (v < hi) {
+      float a[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[i] = 0.f;
+      for (int r = 0; r < W; ++r) Wt::accum(a, ring[((size_t)s * W + r) * kBulkChunkVec + threadIdx.x]);   // rank order
+      store_grad<V>(grad, goff<V>(live, v), a);
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) tc::mbar_arrive(&empty[s]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    uint32_t* ticket = calls_of(my) + 1;
+    if (atomicAdd(ticket, 1u) == (uint32_t)(B - 1)) {      // last block of this call
+      *ticket = 0u;
+      calls_of(my)[0] += 1u;
+      __threadfence();
+    }
+  }
+}
+
 __global__ void barrier_kernel(CommDev c, long long* stamp_ns) {
   __shared__ uint32_t s_epoch;
   const long long t0 = globaltimer_ns();
@@ -856,6 +946,20 @@ static int comm_allreduce_impl(HzComm* c, float* grad, size_t n, int algo, int w
   if (algo == hz::kNvls && c->dev.mc_base == nullptr) return -4;
   if (algo == hz::kLL && (!wire_bf16 || n > hz::kLLMaxElems)) return -5;
   const int blocks = hz_comm_blocks_for(c, n, algo, wire_bf16);
+  if (algo == hz::kBulk) {
+    if (adam) return -7;                                   // plain reduction only
+    const size_t smem = (size_t)hz::kBulkStages * c->dev.world * hz::kBulkChunkVec * 16;
+    static bool attr = [] {
+      return cudaFuncSetAttribute(hz::allreduce_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  hz::kBulkStages * hz::kMaxRanks * hz::kBulkChunkVec * 16) == cudaSuccess &&
+             cudaFuncSetAttribute(hz::allreduce_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  hz::kBulkStages * hz::kMaxRanks * hz::kBulkChunkVec * 16) == cudaSuccess;
+    }();
+    if (!attr) return -8;
+    if (wire_bf16) hz::allreduce_bulk_kernel<true><<<blocks, hz::kCommThreads, smem, st>>>(c->dev, grad, n, scale, live);
+    else hz::allreduce_bulk_kernel<false><<<blocks, hz::kCommThreads, smem, st>>>(c->dev, grad, n, scale, live);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  }
   hz::AdamFuse ad;
   memset(&ad, 0, sizeof(ad));
   if (adam) ad = *adam;

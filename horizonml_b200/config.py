@@ -34,7 +34,7 @@ class TrainConfig:
     dtype: str = "auto"               # auto (bf16 on cuda, fp32 on cpu) | bf16 | fp32
     backend: str = "auto"             # op backend: auto | native | torch
     comm: str = "auto"                # process-group backend: auto | nccl | gloo
-    allreduce: str = "auto"           # auto | oneshot | twoshot | nvls | nccl
+    allreduce: str = "auto"           # auto | oneshot | twoshot | nvls | ll | bulk (one-shot with cp.async.bulk pulls) | nccl
     bucket_mb: float = 25.0           # DDP-like bucket cap (MiB); reference uses DDP default 25
     overlap: bool = True              # overlap bucket all-reduce with backward
     zero1: bool = False               # ZeRO-1: shard Adam's moments over the data-parallel group (parallel/zero.py)
@@ -108,7 +108,7 @@ def add_train_flags(p: argparse.ArgumentParser, strategy: str) -> argparse.Argum
                    help="op backend: hand-written sm_100a kernels or the PyTorch oracle")
     g.add_argument('--comm', default=d.comm, choices=["auto", "nccl", "gloo"])
     g.add_argument('--allreduce', default=d.allreduce,
-                   choices=["auto", "oneshot", "twoshot", "nvls", "nccl"])
+                   choices=["auto", "oneshot", "twoshot", "nvls", "ll", "bulk", "nccl"])
     g.add_argument('--bucket_mb', type=float, default=d.bucket_mb)
     g.add_argument('--no_overlap', dest='overlap', action='store_false')
     g.add_argument('--overlap_adam', action='store_true')
