@@ -264,3 +264,66 @@ def simulate_persistent_pipeline(tile_k: Sequence[int], stages: int = 6, epi_war
                 violated[0] = True               # nobody can move: deadlock
         bad += 1 if violated[0] else 0
     return bad
+
+
+def simulate_bulk_ring(nchunks: int = 11, stages: int = 3, warps: int = 16, trials: int = 200, seed: int = 0,
+                       prefetch: int = -1) -> int:
+    """The shared-memory ring of the bulk-copy all-reduce (csrc/comm.cu allreduce_bulk_kernel): lane 0 of warp 0 both
+    issues the copies (chunk ``ck + stages - 1`` at the top of iteration ``ck``, after waiting ``empty[slot]`` on parity
+    ``((ck' // stages) & 1) ^ 1``) and consumes like every other warp (wait ``full[slot]`` on ``(ck // stages) & 1``, sum,
+    arrive on ``empty[slot]``, count = warps).  Violation = a slot refilled before every warp has consumed it, a warp
+    summing a slot that does not hold its chunk, or a deadlock (the issuing warp waiting for itself).
+    ``prefetch`` overrides the distance (``stages`` instead of ``stages - 1`` makes warp 0 wait for its own arrival:
+    the model must report the deadlock)."""
+    rng = random.Random(seed)
+    dist_ = stages - 1 if prefetch < 0 else prefetch
+    bad = 0
+    for _ in range(trials):
+        full = [_MBar(1) for _ in range(stages)]
+        empty = [_MBar(warps) for _ in range(stages)]
+        slot = [None] * stages                  # {"chunk": ck, "readers": set()}
+        violated = [False]
+
+        def issue(ck):
+            s = ck % stages
+            while not empty[s].try_wait(((ck // stages) & 1) ^ 1):
+                yield False
+            if slot[s] is not None and len(slot[s]["readers"]) < warps:
+                violated[0] = True
+            slot[s] = {"chunk": ck, "readers": set()}
+            full[s].arrive()                    # the copies land, complete_tx flips the phase
+            yield True
+
+        def warp(wid):
+            if wid == 0:
+                for ck in range(min(dist_, nchunks)):
+                    yield from issue(ck)
+            for ck in range(nchunks):
+                if wid == 0 and ck + dist_ < nchunks:
+                    yield from issue(ck + dist_)
+                s = ck % stages
+                while not full[s].try_wait((ck // stages) & 1):
+                    yield False
+                if slot[s] is None or slot[s]["chunk"] != ck:
+                    violated[0] = True
+                else:
+                    slot[s]["readers"].add(wid)
+                empty[s].arrive()
+                yield True
+
+        agents = [warp(w) for w in range(warps)]
+        alive = list(range(warps))
+        stuck = 0
+        while alive and not violated[0]:
+            i = rng.choice(alive)
+            try:
+                progressed = next(agents[i])
+            except StopIteration:
+                alive.remove(i)
+                stuck = 0
+                continue
+            stuck = 0 if progressed else stuck + 1
+            if stuck > 200 * warps:
+                violated[0] = True
+        bad += 1 if violated[0] else 0
+    return bad

@@ -236,3 +236,13 @@ def test_protocol_model_persistent_conv_pipeline():
     assert sim([0, 0, 0], trials=10) == 0
     assert sim([9] * 7, trials=50, broken="acc_parity") == 50
     assert sim([2] * 7, trials=50, broken="one_acc") > 25
+
+
+def test_protocol_model_bulk_allreduce_ring():
+    """The 3-stage shared-memory ring of the bulk-copy all-reduce, where the issuing lane is also a consumer: no slot is
+    refilled before all 16 warps have summed it, nobody sums the wrong chunk, no deadlock; a prefetch distance of a full
+    ring (the issuer waiting for its own warp's arrival) is reported as the deadlock it is."""
+    from horizonml_b200.utils.protocol_model import simulate_bulk_ring as sim
+    assert sim(11, trials=100) == 0 and sim(1, trials=10) == 0 and sim(3, trials=30) == 0
+    assert sim(40, stages=3, warps=4, trials=60, seed=1) == 0
+    assert sim(11, trials=20, prefetch=3) == 20
