@@ -792,6 +792,20 @@ inline int grid_for(size_t work_items, int block, int cap = 148 * 8) {
   if (g > (size_t)cap) g = cap;
   return (int)g;
 }
+// head_wgrad_kernel stages dlogits[N][16] in shared memory: beyond N = 640 that exceeds the 48 KB a kernel gets without
+// opting in (a --batch_size 1024 step used to fail at this launch)
+inline bool head_wgrad_smem_ok(size_t bytes) {
+  if (bytes <= 48 * 1024) return true;
+  static size_t granted = 0;
+  if (bytes <= granted) return true;
+  if (bytes > 200 * 1024) return false;
+  if (cudaFuncSetAttribute(hz::head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  granted = bytes;
+  return true;
+}
 inline int reduce_grid(int M, int C) {
   const int rlanes = 256 / (C / 8);
   int g = (M + rlanes - 1) / rlanes;
@@ -940,6 +954,7 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
                                                dlogits, logits, (__nv_bfloat16*)dfeat, loss, correct, N,
                                                C, HW, K, n_valid, loss_scale, w_in_smem);
   dim3 grid((C + 31) / 32, (K + 15) / 16);
+  head_wgrad_smem_ok(sizeof(float) * (N * 16 + 4 * 32 * 16));
   hz::launch(hz::head_wgrad_kernel, dim3(grid), dim3(128), sizeof(float) * (N * 16 + 4 * 32 * 16), st, pooled, dlogits, dW, db, N, C, K,
                                                                                   accumulate);
 }
@@ -948,6 +963,7 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
 void hz_head_wgrad(const float* pooled, const float* dlogits, float* dW, float* db, int N, int C, int K,
                    int accumulate, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (K + 15) / 16);
+  head_wgrad_smem_ok(sizeof(float) * (N * 16 + 4 * 32 * 16));
   hz::launch(hz::head_wgrad_kernel, dim3(grid), dim3(128), sizeof(float) * (N * 16 + 4 * 32 * 16), st, pooled, dlogits,
              dW, db, N, C, K, accumulate);
 }

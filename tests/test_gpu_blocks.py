@@ -83,3 +83,23 @@ def test_resnet_basic_block_native_vs_oracle(cin, cout, stride, hw):
 def test_mobilenet_inverted_residual_native_vs_oracle(inp, oup, stride, t, hw):
     from horizonml_b200.models.mobilenet import InvertedResidual
     _compare(lambda: InvertedResidual(inp, oup, stride, t), inp, hw, (oup, (hw - 1) // stride + 1))
+
+
+@pytest.mark.parametrize("n", [640, 1024, 2048])
+def test_head_beyond_48k_of_shared_memory(n):
+    """The classifier head's weight-gradient kernel stages dlogits[N][16] in shared memory: above N = 640 it needs the
+    opt-in dynamic shared-memory size (a --batch_size 1024 step failed at this launch before)."""
+    from horizonml_b200.ops import native_backend as nb
+    from horizonml_b200.ops import torch_backend as tb
+    g = torch.Generator().manual_seed(5)
+    f = cl(torch.randn(n, 512, 1, 1, generator=g).to(DEV).bfloat16())
+    W = (torch.randn(16, 512, generator=g) * 0.05).to(DEV)
+    b = (torch.randn(16, generator=g) * 0.1).to(DEV)
+    lab = torch.randint(0, 10, (n,), generator=g).to(DEV)
+    dW, db = torch.zeros(16, 512, device=DEV), torch.zeros(16, device=DEV)
+    dW2, db2 = torch.zeros_like(dW), torch.zeros_like(db)
+    l, c, df, lg = nb.head_fwd_bwd(f, W, b, lab, 1.0, 10, dW, db, False, True)
+    l2, c2, df2, lg2 = tb.head_fwd_bwd(f, W, b, lab, 1.0, 10, dW2, db2, False, True)
+    torch.cuda.synchronize()
+    assert abs(l.item() - l2.item()) < 1e-3 * max(1, abs(l2.item())) and c.item() == c2.item()
+    assert rel_err(df, df2) < 1e-2 and rel_err(dW, dW2) < 1e-3 and rel_err(db, db2) < 1e-3

@@ -5,7 +5,8 @@ recipe of tools/conv_roofline.py / bench.py.  Nothing here can fail the run: eve
 measure (or why not) and the test itself only asserts that it produced a report.
 
 * persistent vs one-tile-per-CTA convolution kernel vs cuDNN at batch 4096 (TFLOP/s, fraction of the measured bf16 peak)
-* MobileNetV2 and ResNet-18 training step through the DP engine on one GPU (ms/step, images/s)"""
+* MobileNetV2 and ResNet-18 training step through the DP engine on one GPU (ms/step, images/s)
+* `bench.py --batch 512` with the one-tile-per-CTA kernels and with the persistent kernels (HZ_CONV_PERSIST=1)"""
 import json
 import os
 import warnings
@@ -116,4 +117,24 @@ def test_round_end_perf_report():
                 _report("step", {"model": model, "error": repr(e)[:300]})
     finally:
         ops.set_backend("torch")
+    # ---- the public benchmark at a throughput-bound batch size, one-tile-per-CTA kernels vs persistent kernels
+    import subprocess
+    import sys
+    del flush
+    torch.cuda.empty_cache()
+    for tag, env_extra in (("b512_latency_kernels", {"HZ_CONV_PERSIST": "0"}), ("b512_persistent_kernels", {"HZ_CONV_PERSIST": "1"})):
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--batch", "512", "--steps", "30",
+                                "--warmup", "5"], cwd=ROOT, env=dict(os.environ, **env_extra), capture_output=True, text=True,
+                               timeout=120)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{") and '"metric"' in ln]
+            if line:
+                d = json.loads(line[-1])
+                _report("bench", {"variant": tag, "images_per_s": d["value"], "ms_per_step": d["ms_per_step"],
+                                  "fallbacks": d.get("native_fallbacks"), "cuda_graph": d["config"].get("cuda_graph")})
+                sections += 1
+            else:
+                _report("bench", {"variant": tag, "error": (r.stderr or r.stdout)[-300:]})
+        except Exception as e:  # noqa: BLE001
+            _report("bench", {"variant": tag, "error": repr(e)[:200]})
     assert sections >= 0
