@@ -953,19 +953,21 @@ void hz_head_fwd_bwd(const void* feat, const float* W, const float* bias, const 
   hz::launch(hz::head_sample_kernel, dim3(N), dim3(128), smem, st, (const __nv_bfloat16*)feat, W, bias, labels, pooled,
                                                dlogits, logits, (__nv_bfloat16*)dfeat, loss, correct, N,
                                                C, HW, K, n_valid, loss_scale, w_in_smem);
-  dim3 grid((C + 31) / 32, (K + 15) / 16);
-  head_wgrad_smem_ok(sizeof(float) * (N * 16 + 4 * 32 * 16));
-  hz::launch(hz::head_wgrad_kernel, dim3(grid), dim3(128), sizeof(float) * (N * 16 + 4 * 32 * 16), st, pooled, dlogits, dW, db, N, C, K,
-                                                                                  accumulate);
+  hz_head_wgrad(pooled, dlogits, dW, db, N, C, K, accumulate, st);
 }
 
 // dW[k,c] (+)= sum_n dlogits[n,k] * pooled[n,c], db[k] (+)= sum_n dlogits[n,k]   (tensor-parallel head: local shard)
 void hz_head_wgrad(const float* pooled, const float* dlogits, float* dW, float* db, int N, int C, int K,
                    int accumulate, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (K + 15) / 16);
-  head_wgrad_smem_ok(sizeof(float) * (N * 16 + 4 * 32 * 16));
-  hz::launch(hz::head_wgrad_kernel, dim3(grid), dim3(128), sizeof(float) * (N * 16 + 4 * 32 * 16), st, pooled, dlogits,
-             dW, db, N, C, K, accumulate);
+  constexpr int kChunk = 2048;                       // samples per launch: dlogits[chunk][16] must fit in shared memory
+  for (int n0 = 0; n0 < N; n0 += kChunk) {
+    const int nn = N - n0 < kChunk ? N - n0 : kChunk;
+    const size_t smem = sizeof(float) * ((size_t)nn * 16 + 4 * 32 * 16);
+    head_wgrad_smem_ok(smem);
+    hz::launch(hz::head_wgrad_kernel, dim3(grid), dim3(128), smem, st, pooled + (size_t)n0 * C, dlogits + (size_t)n0 * K,
+               dW, db, nn, C, K, (accumulate || n0 > 0) ? 1 : 0);
+  }
 }
 
 void hz_adam(float* p, float* g, float* m, float* v, void* shadow, float* step, float* prev, float* diff_out,

@@ -85,7 +85,7 @@ def test_mobilenet_inverted_residual_native_vs_oracle(inp, oup, stride, t, hw):
     _compare(lambda: InvertedResidual(inp, oup, stride, t), inp, hw, (oup, (hw - 1) // stride + 1))
 
 
-@pytest.mark.parametrize("n", [640, 1024, 2048])
+@pytest.mark.parametrize("n", [640, 1024, 2048, 5000])        # 5000: three launches of <= 2048 samples
 def test_head_beyond_48k_of_shared_memory(n):
     """The classifier head's weight-gradient kernel stages dlogits[N][16] in shared memory: above N = 640 it needs the
     opt-in dynamic shared-memory size (a --batch_size 1024 step failed at this launch before)."""
