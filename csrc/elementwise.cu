@@ -796,7 +796,10 @@ inline int grid_for(size_t work_items, int block, int cap = 148 * 8) {
 // opting in (a --batch_size 1024 step used to fail at this launch)
 inline bool head_wgrad_smem_ok(size_t bytes) {
   if (bytes <= 48 * 1024) return true;
-  static size_t granted = 0;
+  static size_t granted_on[16] = {0};                 // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& granted = granted_on[dev & 15];
   if (bytes <= granted) return true;
   if (bytes > 200 * 1024) return false;
   if (cudaFuncSetAttribute(hz::head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
