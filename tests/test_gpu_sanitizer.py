@@ -16,8 +16,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _memcheck(selection: str, files, budget_s: int):
-    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+def _memcheck(selection: str, files, budget_s: int, exe: str = ""):
+    exe = exe or shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
     if not os.path.exists(exe):
         pytest.skip("compute-sanitizer not installed")
     # plain stream order (the sanitizer serialises kernels anyway); lazy module loading: with the eager loading the
@@ -25,14 +25,22 @@ def _memcheck(selection: str, files, budget_s: int):
     env = dict(os.environ, HZ_PDL="0", CUDA_MODULE_LOADING="LAZY")
     cmd = [exe, "--tool", "memcheck", "--error-exitcode", "9", "--launch-timeout", "60", sys.executable, "-m", "pytest",
            *files, "-q", "-x", "-m", "gpu and not late", "-k", selection, "-p", "no:cacheprovider"]
+    import signal
+    proc = subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                            start_new_session=True)           # own process group: tool + target die together
     try:
-        r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=budget_s)
+        out, _ = proc.communicate(timeout=budget_s)
     except subprocess.TimeoutExpired:
+        try:
+            os.killpg(proc.pid, signal.SIGKILL)
+        except OSError:
+            pass
+        proc.communicate()
         pytest.skip(f"compute-sanitizer run did not finish within {budget_s} s")
-    out = r.stdout + r.stderr
+    rc = proc.returncode
     if "ERROR SUMMARY" not in out:
         pytest.skip("compute-sanitizer produced no summary (tool could not attach?): " + out[-400:].replace("\n", " | "))
-    assert "ERROR SUMMARY: 0 errors" in out and r.returncode == 0, out[-3000:]
+    assert "ERROR SUMMARY: 0 errors" in out and rc == 0, out[-3000:]
     assert " passed" in out, out[-1500:]
 
 
