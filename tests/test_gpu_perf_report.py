@@ -94,11 +94,12 @@ def test_round_end_perf_report():
         g = torch.Generator().manual_seed(0)
         xs = torch.randint(0, 256, (64, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
         ys = torch.randint(0, 10, (64,), generator=g).to(DEV)
-        for model in ("resnet18", "mobilenet"):
+        for model, be in (("resnet18", "native"), ("mobilenet", "native"), ("mobilenet", "torch")):
             try:
+                ops.set_backend(be)          # "torch": the same engine on PyTorch ops (cuDNN / ATen kernels) for scale
                 cfg = TrainConfig(strategy="data", world_size=1, batch_size=64, device="cuda", dtype="bf16",
-                                  backend="native", model=model, quiet=True)
-                eng = DPEngine(cfg, Runtime(0, 1, torch.device(DEV), torch.bfloat16, "native", "none"))
+                                  backend=be, model=model, quiet=True)
+                eng = DPEngine(cfg, Runtime(0, 1, torch.device(DEV), torch.bfloat16, be, "none"))
                 for _ in range(6):
                     eng.step(xs, ys)
                 torch.cuda.synchronize()
@@ -109,12 +110,12 @@ def test_round_end_perf_report():
                     a.record(); eng.step(xs, ys); b.record()
                 torch.cuda.synchronize()
                 ms = sum(a.elapsed_time(b) for a, b in evs) / K
-                _report("step", {"model": model, "batch": 64, "ms_per_step": round(ms, 4), "images_per_s": round(64 / ms * 1e3),
+                _report("step", {"model": model, "backend": be, "batch": 64, "ms_per_step": round(ms, 4), "images_per_s": round(64 / ms * 1e3),
                                  "graph": eng._graphed.graph is not None, "fallbacks": dict(nb.FALLBACKS)})
                 eng._graphed.graph = None
                 sections += 1
             except Exception as e:  # noqa: BLE001
-                _report("step", {"model": model, "error": repr(e)[:300]})
+                _report("step", {"model": model, "backend": be, "error": repr(e)[:300]})
     finally:
         ops.set_backend("torch")
     # ---- the public benchmark at a throughput-bound batch size, one-tile-per-CTA kernels vs persistent kernels
