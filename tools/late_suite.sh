@@ -1,0 +1,13 @@
+#!/bin/bash
+# First hardware run of everything written after round 2's GPU budget was spent (one GPU, ~6 min):
+#   1. the `late` test tier as ordinary (gating) tests, most certain first      -> gpurun_out/late_tier.log
+#   2. the HZPERF report lines (persistent vs latency conv kernel vs cuDNN, MobileNetV2 / ResNet-18 step times,
+#      bench.py --batch 512 with both kernel families)                            -> gpurun_out/hzperf.txt
+#   3. conv roofline with the persistent kernels next to the one-tile-per-CTA kernels -> gpurun_out/conv_roofline_persist.json
+# Usage: gpurun --timeout 900 -- bash tools/late_suite.sh
+mkdir -p gpurun_out
+HZ_LATE_STRICT=1 timeout 700 python -m pytest tests -m "gpu and late and not multigpu" -q -rA -W default 2>&1 | tee gpurun_out/late_tier.log | tail -40
+grep -h "HZPERF" gpurun_out/late_tier.log | sed 's/.*HZPERF/HZPERF/' | sort -u > gpurun_out/hzperf.txt
+cat gpurun_out/hzperf.txt
+HZ_CONV_PERSIST=1 timeout 300 python tools/conv_roofline.py gpurun_out/conv_roofline_persist.json 512 4096 > gpurun_out/conv_roofline_persist.log 2>&1
+tail -8 gpurun_out/conv_roofline_persist.log | cut -c1-400
