@@ -1,12 +1,17 @@
 """ZeRO-1: optimizer-state sharding over the data-parallel group.
 
-The reference replicates Adam's state on every worker (SURVEY §2.3 "ZeRO / FSDP / optimizer sharding: NO"); here the
-flat parameter store makes the sharded variant a few lines: the flat gradient buffer is reduce-scattered (each rank
-receives the average of ITS contiguous 1/W slice), the fused Adam kernel runs on that slice only (moments exist only
-for it: 2·P/W floats instead of 2·P), and the updated fp32 master slice is all-gathered; the bf16 shadow is refreshed
-from it.  Collectives go through ``torch.distributed`` (NCCL on GPUs; on gloo, which has no reduce-scatter, an
-all-reduce + slice) — this is the baseline formulation of the path; folding the Adam update between the two halves
-of the two-shot peer all-reduce kernel (csrc/comm.cu) is the fused variant the design points to.
+The reference replicates Adam's state on every worker (SURVEY §2.3 "ZeRO / FSDP / optimizer sharding: NO").  Two
+implementations on top of the flat parameter store:
+
+* ``FusedShardedAdam`` — per gradient bucket ONE peer-memory kernel (``csrc/comm.cu`` ``zero1_kernel``): the two-shot
+  all-reduce with the optimizer in the middle.  Every rank packs its bucket (1/W scale, bf16), the owner of each slice sums
+  the W copies, applies Adam to its fp32 master slice and its moment shards (2·P/W floats instead of 2·P) and pushes the new
+  bf16 parameters into every rank's shadow over NVLink.  Launched by the gradient reducer as buckets complete, i.e.
+  overlapped with backward inside the step's CUDA graph; no library collective.  Default for ``--zero1`` where the peer
+  kernels run (CUDA, native backend, bf16).  On CPU / gloo the same class runs the same sharding on ``torch.distributed``.
+* ``ShardedFlatAdam`` — the baseline formulation: the whole flat gradient buffer is reduce-scattered (NCCL; on gloo an
+  all-reduce + slice), the fused Adam kernel runs on the rank's contiguous 1/W slice, the fp32 master slice is all-gathered
+  and the bf16 shadow refreshed (``--zero1_impl nccl``).
 """
 from __future__ import annotations
 
