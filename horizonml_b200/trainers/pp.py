@@ -34,6 +34,11 @@ class PPEngine:
     group (fused peer all-reduce on GPUs) between the 1F1B schedule and the optimizer pass."""
 
     def __init__(self, cfg: TrainConfig, rt: Runtime, mesh=None):
+        if cfg.model != "resnet18":
+            # the reference's pipeline script partitions torchvision's ResNet-18 and nothing else; MobileNetV2 is the
+            # legacy container path's second model (train.py MODEL_TYPE) and runs on the data-parallel engine
+            raise ValueError(f"--model {cfg.model}: the pipeline strategy partitions ResNet-18 only "
+                             "(use data_parallel_train.py / train.py for mobilenet)")
         self.cfg, self.rt, self.mesh = cfg, rt, mesh
         S, s = (mesh.pp, mesh.coord.pp) if mesh is not None else (rt.world, rt.rank)
         self.S, self.s = S, s

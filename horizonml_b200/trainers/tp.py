@@ -34,6 +34,11 @@ class TPEngine:
     the rank's data-parallel group."""
 
     def __init__(self, cfg: TrainConfig, rt: Runtime, mesh=None):
+        if cfg.model != "resnet18":
+            # the reference's tensor-parallel script partitions torchvision's ResNet-18 and nothing else; MobileNetV2 is the
+            # legacy container path's second model (train.py MODEL_TYPE) and runs on the data-parallel engine
+            raise ValueError(f"--model {cfg.model}: the tensor-parallel strategy partitions ResNet-18 only "
+                             "(use data_parallel_train.py / train.py for mobilenet)")
         self.cfg, self.rt, self.mesh = cfg, rt, mesh
         fused = None
         tp_group = mesh.tp_group if mesh is not None else None
