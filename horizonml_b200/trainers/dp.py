@@ -81,17 +81,18 @@ class DPEngine:
                     dist.broadcast(b, src=0)
             self.flat.sync_shadow()
         kind = cfg.allreduce
-        self.ar = (make_grad_allreduce(kind, self.flat.total, dev)
-                   if (rt.world > 1 and (not self.zero1 or (self.zero_fused and peer_ok))) else None)
         if self.zero_fused:
             from ..parallel.zero import FusedShardedAdam
+            self.ar = make_grad_allreduce(kind, self.flat.total, dev) if peer_ok else None   # the kernel's communicator
             self.opt = FusedShardedAdam(self.flat, self.ar if hasattr(self.ar, "handle") else None, lr=cfg.lr,
                                         with_prev=bool(cfg.grad_divergence))
         elif self.zero1:
             from ..parallel.zero import ShardedFlatAdam
             self.opt = ShardedFlatAdam(self.flat, lr=cfg.lr)      # reduce-scatter + sharded Adam + all-gather
+            self.ar = None
         else:
             self.opt = FlatAdam(self.flat, lr=cfg.lr)
+            self.ar = make_grad_allreduce(kind, self.flat.total, dev) if rt.world > 1 else None
         self.stats = DeviceStats(dev)
         ops.enable_side_stream(dev.type == "cuda" and rt.backend == "native")
         self.prev_grad = None
