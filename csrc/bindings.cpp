@@ -75,7 +75,8 @@ std::vector<Tensor> bn_act_fwd(const Tensor& y, const Tensor& sums, const Tensor
 std::vector<Tensor> bn_act_bwd(const Tensor& dout, const Tensor& out, const Tensor& yraw, const Tensor& mean,
                                const Tensor& invstd, const Tensor& gamma, int64_t relu, bool has_res,
                                Tensor dgamma, Tensor dbeta, bool acc_gamma, bool acc_beta,
-                               c10::optional<Tensor> zeroed_scratch) {
+                               c10::optional<Tensor> zeroed_scratch, bool sums_ready) {
+  // sums_ready: `zeroed_scratch` already holds the final (sum g, sum g*xhat) — left there by conv_dgrad_bnbwd
   check_cl(dout, "dout"); check_cl(yraw, "yraw");
   c10::cuda::CUDAGuard g(dout.device());
   auto d = dims_of(yraw);
@@ -88,7 +89,7 @@ std::vector<Tensor> bn_act_bwd(const Tensor& dout, const Tensor& out, const Tens
                 gamma.data_ptr<float>(), scratch.data_ptr<float>(), dy.data_ptr(),
                 has_res ? dres.data_ptr() : nullptr, dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
                 acc_gamma ? 1 : 0, acc_beta ? 1 : 0, d.N * d.H * d.W, d.C, (int)relu,
-                pre ? (scratch.numel() >= 2 * d.C + 32 ? 2 : 1) : 0, cur_stream());
+                (sums_ready && pre) ? 3 : (pre ? (scratch.numel() >= 2 * d.C + 32 ? 2 : 1) : 0), cur_stream());
   return {dy, dres};
 }
 
@@ -343,6 +344,41 @@ std::vector<Tensor> conv_bn_act_fwd(const Tensor& x, const Tensor& w, int64_t st
 }
 
 // addend (optional, same shape/layout as dx): dx = dgrad(dy, w) + addend, fused into the epilogue
+// dgrad + the BatchNorm-backward sums of the layer that produced the conv's input (see HzBnBwd): returns {dx, sums[2,Cin]}
+std::vector<Tensor> conv_dgrad_bnbwd(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride,
+                                     int64_t pad, c10::optional<Tensor> addend, bool weights_stable,
+                                     c10::optional<Tensor> bn_out, const Tensor& bn_yraw, const Tensor& bn_mean,
+                                     const Tensor& bn_invstd, c10::optional<Tensor> sums_pre) {
+  check_cl(dy, "dy"); check_cl(w, "w"); check_cl(bn_yraw, "bn_yraw");
+  c10::cuda::CUDAGuard g(dy.device());
+  const int N = (int)x_shape[0], Cin = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
+  Tensor dx = empty_cl(dy, N, Cin, H, W);
+  TORCH_CHECK(bn_yraw.sizes() == dx.sizes() && bn_mean.numel() == Cin && bn_invstd.numel() == Cin &&
+              bn_mean.scalar_type() == at::kFloat && bn_invstd.scalar_type() == at::kFloat, "conv_dgrad_bnbwd: BN operand mismatch");
+  const void* add = nullptr;
+  if (addend.has_value() && addend->defined()) {
+    check_cl(*addend, "addend");
+    TORCH_CHECK(addend->sizes() == dx.sizes() && addend->scalar_type() == dx.scalar_type(), "dgrad addend mismatch");
+    add = addend->data_ptr();
+  }
+  const void* bo = nullptr;
+  if (bn_out.has_value() && bn_out->defined()) {
+    check_cl(*bn_out, "bn_out");
+    TORCH_CHECK(bn_out->sizes() == dx.sizes(), "conv_dgrad_bnbwd: bn_out shape");
+    bo = bn_out->data_ptr();
+  }
+  const bool pre = sums_pre.has_value() && sums_pre->defined();
+  Tensor sums = pre ? *sums_pre : at::empty({2, Cin}, dy.options().dtype(at::kFloat));
+  TORCH_CHECK(sums.numel() >= 2 * Cin && sums.scalar_type() == at::kFloat && sums.is_contiguous());
+  HzBnBwd b;
+  b.out = bo; b.yraw = bn_yraw.data_ptr(); b.mean = bn_mean.data_ptr<float>(); b.invstd = bn_invstd.data_ptr<float>();
+  b.sums = sums.data_ptr<float>(); b.sums_is_zero = pre ? 1 : 0;
+  int rc = hz_conv_dgrad_bnbwd(cptr(dy), cptr(w), dx.data_ptr(), add, N, H, W, Cin, (int)w.size(0), (int)w.size(2),
+                               (int)stride, (int)pad, weights_stable ? 1 : 0, &b, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_conv_dgrad_bnbwd failed rc=", rc);
+  return {dx, sums};
+}
+
 Tensor conv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride, int64_t pad,
                   c10::optional<Tensor> addend, bool weights_stable) {
   check_cl(dy, "dy"); check_cl(w, "w");
@@ -650,6 +686,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_supported", &conv_supported);
   m.def("conv_fwd", &conv_fwd);
   m.def("conv_dgrad", &conv_dgrad);
+  m.def("conv_dgrad_bnbwd", &conv_dgrad_bnbwd);
   m.def("conv_wgrad", &conv_wgrad);
   m.def("tp_set_debug", [](c10::optional<Tensor> buf) {
     if (buf.has_value() && buf->defined()) {

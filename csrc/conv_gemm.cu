@@ -62,6 +62,12 @@ struct IgemmParams {
   float bn_inv_count, bn_unbias, bn_eps, bn_momentum;
   int bn_relu;
   long long* dbg;                // optional: per-CTA clock64 stamps of the kernel's phases (tools/conv_timeline.py)
+  // ---- dgrad only (kBnBwd instantiation): this dgrad's output IS the upstream gradient of the producing layer's
+  //      BatchNorm, so its backward sums  (sum g, sum g*xhat),  g = dx * [bn_out > 0],  are taken from the registers
+  //      that store dx (into `stats`, pre-zeroed) — the separate channel_reduce pass over dx / out / y_raw disappears
+  const __nv_bfloat16* bnb_out;  // the producing layer's BN output (ReLU mask), same layout as `out`; null = no ReLU
+  const __nv_bfloat16* bnb_yraw; // the producing layer's raw conv output
+  const float* bnb_mean; const float* bnb_invstd;     // [ncols]
 };
 
 HZ_DEVINL unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -105,7 +111,7 @@ HZ_DEVINL void cluster_reduce_rows(uint32_t red_base, int row_lo, __nv_bfloat16*
   }
 }
 
-template <int BLOCK_N, bool B_MN>
+template <int BLOCK_N, bool B_MN, bool kBnBwd = false>
 __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMaps amaps,
                                                     const __grid_constant__ CUtensorMap bmap,
                                                     const __grid_constant__ IgemmParams p) {
@@ -391,13 +397,22 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
   for (int j = 0; j < 8; ++j) ssum[j] = ssq[j] = 0.f;
   {
     const int vec = threadIdx.x % kVecPerRow;
+    float bmu[8], bis[8];
+    if (kBnBwd) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = nt * BLOCK_N + vec * 8 + j;
+        bmu[j] = c < p.ncols ? p.bnb_mean[c] : 0.f;
+        bis[j] = c < p.ncols ? p.bnb_invstd[c] : 0.f;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < kPasses; ++i) {
       const int r0 = row_lo + threadIdx.x / kVecPerRow + i * kRowsPerPass;
       const long long off = offs[i];
       if (off < 0) continue;              // rows past the last image are zero-filled: they add nothing to the sums
       bf16x8 v = ld8(staging + r0 * S::kStagingLd + vec * 8);
-      if (p.stats != nullptr) {
+      if (!kBnBwd && p.stats != nullptr) {
         float f[8];
         unpack8(v, f);
 #pragma unroll
@@ -406,6 +421,21 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
       if (p.addend != nullptr) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) v.v[j] = __hadd2(v.v[j], addv[i].v[j]);  // bf16 + bf16 -> bf16, as the separate add did
+      }
+      if (kBnBwd) {
+        // BatchNorm-backward sums of the layer that produced this conv's input, from the bf16 values being stored
+        // (exactly what channel_reduce_kernel<true> would read back): g = dx * [out > 0], xhat = (y - mean) * invstd
+        float g[8], y[8];
+        unpack8(v, g);
+        unpack8(ld8(p.bnb_yraw + off), y);
+        if (p.bnb_out != nullptr) {
+          float o[8];
+          unpack8(ld8(p.bnb_out + off), o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ssum[j] += g[j]; ssq[j] += g[j] * (y[j] - bmu[j]) * bis[j]; }
       }
       st8(p.out + off, v);
     }
@@ -1161,9 +1191,12 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
                             p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;
 }
 
-// dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w)
-int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout, int R,
-                  int stride, int pad, int weights_stable, cudaStream_t st) {
+}  // extern "C"
+
+namespace {
+// dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w);  bnb: also the BatchNorm-backward sums of the layer that produced x
+int conv_dgrad_impl(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout, int R,
+                    int stride, int pad, int weights_stable, const HzBnBwd* bnb, cudaStream_t st) {
   const int S_ = R;
   const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S_) / stride + 1;
   // output lattice per class: stride 1 -> (H,W); stride 2 -> (H/2,W/2) == (Ho,Wo)
@@ -1213,7 +1246,15 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
   p.out = (__nv_bfloat16*)dx;
   p.addend = (const __nv_bfloat16*)addend;
   p.stats = nullptr;
-  if (use_persistent(t.tiles * ((Cin + BLOCK_N - 1) / BLOCK_N) * p.num_classes))
+  if (bnb != nullptr) {
+    if (bnb->sums == nullptr || bnb->yraw == nullptr || bnb->mean == nullptr || bnb->invstd == nullptr) return -15;
+    if (!bnb->sums_is_zero) hz::zero_f32(bnb->sums, (size_t)2 * Cin, st);
+    p.stats = bnb->sums;
+    p.bnb_out = (const __nv_bfloat16*)bnb->out;
+    p.bnb_yraw = (const __nv_bfloat16*)bnb->yraw;
+    p.bnb_mean = bnb->mean; p.bnb_invstd = bnb->invstd;
+  }
+  if (bnb == nullptr && use_persistent(t.tiles * ((Cin + BLOCK_N - 1) / BLOCK_N) * p.num_classes))
     return persist_wide(Cin) ? launch_persistent_n<128, true>(am, bm, p, t.tiles, st)      // same 64 x 64 weight boxes,
                              : launch_persistent_n<64, true>(am, bm, p, t.tiles, st);      // two MN atoms per stage
   {
@@ -1234,8 +1275,29 @@ int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, i
   p.dbg = g_conv_dbg;
   using SM = hz::IgemmSmem<BLOCK_N>;
   dim3 grid(t.tiles, (Cin + BLOCK_N - 1) / BLOCK_N, p.num_classes * p.splits);
+  if (bnb != nullptr) {
+    static bool attr2 = set_smem(hz::igemm_kernel<64, true, true>, hz::IgemmSmem<64>::kTotal);
+    (void)attr2;
+    return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, true, true>, grid, dim3(128), SM::kTotal, st,
+                              p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;
+  }
   return hz::launch_cluster(hz::igemm_kernel<BLOCK_N, true>, grid, dim3(128), SM::kTotal, st,
                             p.cluster ? (unsigned)p.splits : 1u, am, bm, p) == cudaSuccess ? 0 : -1;
+}
+}  // namespace
+
+extern "C" {
+
+int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout, int R,
+                  int stride, int pad, int weights_stable, cudaStream_t st) {
+  return conv_dgrad_impl(dy, w, dx, addend, N, H, W, Cin, Cout, R, stride, pad, weights_stable, nullptr, st);
+}
+
+// dgrad whose epilogue also leaves the BatchNorm-backward sums of the layer that produced x (see IgemmParams::bnb_*)
+int hz_conv_dgrad_bnbwd(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout,
+                        int R, int stride, int pad, int weights_stable, const HzBnBwd* bnb, cudaStream_t st) {
+  if (bnb == nullptr) return -15;
+  return conv_dgrad_impl(dy, w, dx, addend, N, H, W, Cin, Cout, R, stride, pad, weights_stable, bnb, st);
 }
 
 // dw[Cout, R*S*Cin (ld_out)] (+)= dy^T * x_taps.   ld_out / n_valid allow the padded stem (Cin=192 -> 147)

@@ -873,9 +873,22 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
         acc_gamma, acc_beta, M, C, relu);
     return;
   }
-  if (!scratch_is_zero) hz::zero_f32(sums_scratch, (size_t)2 * C, st);
   const size_t smem_r = sizeof(float) * 256 * 16;
   const size_t smem = sizeof(float) * 5 * C;
+  if (scratch_is_zero == 3) {
+    // the sums are already final: the dgrad kernel that produced `dout` took them in its epilogue
+    // (hz_conv_dgrad_bnbwd) — only the apply pass is left
+    if (gen)
+      hz::launch(hz::bn_act_bwd_apply_kernel<true>, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st,
+          (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
+          gamma, sums_scratch, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta, acc_gamma, acc_beta, M, C, relu);
+    else
+      hz::launch(hz::bn_act_bwd_apply_kernel<false>, dim3(grid_for((size_t)M * (C / 8), 256, 148 * 4)), dim3(256), smem, st,
+          (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
+          gamma, sums_scratch, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta, acc_gamma, acc_beta, M, C, relu);
+    return;
+  }
+  if (!scratch_is_zero) hz::zero_f32(sums_scratch, (size_t)2 * C, st);
   if (gen) {
     hz::launch(hz::channel_reduce_kernel<true, true>, dim3(reduce_grid(M, C)), dim3(256), smem_r, st,
         (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,

@@ -67,6 +67,17 @@ int hz_conv_fwd(const void* x, const void* w, void* y, float* stats, int stats_i
                 cudaStream_t st);
 int hz_conv_dgrad(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout, int R,
                   int stride, int pad, int weights_stable, cudaStream_t st);
+// BatchNorm-backward sums (sum g, sum g*xhat; g = dx * [out > 0]) of the layer that produced the conv's input, taken in
+// the dgrad epilogue: `out` (null = no ReLU) / `yraw` are that layer's BN output / raw conv output (layout of dx),
+// mean / invstd its saved statistics [Cin], sums [2*Cin] fp32 (sums_is_zero: already cleared)
+struct HzBnBwd {
+  const void* out; const void* yraw;
+  const float* mean; const float* invstd;
+  float* sums;
+  int sums_is_zero;
+};
+int hz_conv_dgrad_bnbwd(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout,
+                        int R, int stride, int pad, int weights_stable, const struct HzBnBwd* bnb, cudaStream_t st);
 int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,
                   int stride, int pad, int accumulate, int prezeroed, long long ld_out, int n_valid,
                   cudaStream_t st);

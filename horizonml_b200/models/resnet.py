@@ -47,15 +47,21 @@ class BNP(nn.Module):
         self.momentum, self.eps = 0.1, 1e-5
 
 
-def _cba(x, conv: ConvW, bn: BNP, relu: bool, residual=None, training=True, in_link=None, res_link=None):
+def _cba(x, conv: ConvW, bn: BNP, relu: bool, residual=None, training=True, in_link=None, res_link=None,
+         bn_src=None, bn_dst=None):
     return ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                            stride=conv.stride, pad=conv.pad, relu=relu, residual=residual,
-                           momentum=bn.momentum, eps=bn.eps, training=training, in_link=in_link, res_link=res_link)
+                           momentum=bn.momentum, eps=bn.eps, training=training, in_link=in_link, res_link=res_link,
+                           bn_src=bn_src, bn_dst=bn_dst)
 
 
 # the block input feeds two branches; their gradients are summed inside the later dgrad kernel's epilogue
 # (ops.GradLink) instead of by a separate accumulation kernel.  HZ_FUSE_RESADD=0 restores plain autograd.
 _FUSE_RESADD = os.environ.get("HZ_FUSE_RESADD", "1") != "0"
+# bn1's backward sums (Σg, Σg·x̂) taken in the epilogue of conv2's dgrad kernel, whose output IS bn1's upstream gradient
+# (ops.BNBackLink): one reduction kernel less per block.  Off by default: written after the round's GPU budget was
+# spent, first hardware run in tests/test_gpu_blocks.py; HZ_BN_BWD_IN_DGRAD=1 enables it.
+_BN_BWD_IN_DGRAD = os.environ.get("HZ_BN_BWD_IN_DGRAD", "0") == "1"
 
 
 class BasicBlock(nn.Module):
@@ -74,12 +80,13 @@ class BasicBlock(nn.Module):
     def forward(self, x):
         t = self.training
         link = ops.GradLink(2) if (_FUSE_RESADD and t and torch.is_grad_enabled() and x.requires_grad) else None
+        bl = ops.BNBackLink() if (_BN_BWD_IN_DGRAD and t and torch.is_grad_enabled()) else None
         if self.downsample is not None:
             idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t, in_link=link)
-            y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link)
-            return _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t)
-        y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link)
-        return _cba(y, self.conv2, self.bn2, relu=True, residual=x, training=t, res_link=link)
+            y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link, bn_dst=bl)
+            return _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t, bn_src=bl)
+        y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link, bn_dst=bl)
+        return _cba(y, self.conv2, self.bn2, relu=True, residual=x, training=t, res_link=link, bn_src=bl)
 
 
 class Stem(nn.Module):

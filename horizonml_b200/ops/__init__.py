@@ -3,7 +3,7 @@
 from .functional import (  # noqa: F401
     set_backend, get_backend, conv_bn_act, dwconv_bn_act, maxpool3x3s2, head_loss, head_logits,
     adam_step, grad_diff_sq, stem_prepare, compute_weight, grad_target, grad_written,
-    enable_side_stream, join_side, step_begin, step_end, stats_update, GradLink, backward,
+    enable_side_stream, join_side, step_begin, step_end, stats_update, GradLink, BNBackLink, backward,
 )
 
 

@@ -141,15 +141,34 @@ class GradLink:
         return None
 
 
+class BNBackLink:
+    """Hand-off between a producer ``conv_bn_act`` (passed as ``bn_dst``) and the ONE op that consumes its output
+    (passed as ``bn_src``): the consumer's input gradient *is* the producer's BatchNorm upstream gradient, so the
+    consumer's dgrad kernel takes the producer's BN-backward sums (Σg, Σg·x̂) in its epilogue and the producer's
+    backward skips its reduction pass over dout / out / y_raw (one kernel less per layer pair).  Only used on the
+    native backend, for activations none / ReLU, when the consumer's dgrad output is the complete gradient of the
+    producer's output (no other consumer)."""
+    __slots__ = ("out", "y_raw", "mean", "invstd", "act", "sums")
+
+    def __init__(self):
+        self.out = self.y_raw = self.mean = self.invstd = self.sums = None
+        self.act = 0
+
+    def clear(self):
+        self.out = self.y_raw = self.mean = self.invstd = self.sums = None
+
+
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
-                momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link=None, res_link=None):
+                momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link=None, res_link=None,
+                bn_src=None, bn_dst=None):
         be = _be(x)
         w = compute_weight(weight, x.dtype)
         ctx.post_dgrad = post_dgrad
         ctx.dgrad_fn = dgrad_fn
         ctx.in_link, ctx.res_link = in_link, res_link
+        ctx.bn_src, ctx.bn_dst = bn_src, bn_dst
         fused = None
         if conv_fn is None and post_conv is None and training and hasattr(be, "conv_bn_act_fwd"):
             # one kernel: conv + BN statistics + device-wide barrier + normalise / residual / ReLU
@@ -170,6 +189,9 @@ class _ConvBNAct(torch.autograd.Function):
         ctx.params = (weight, gamma, beta)
         ctx.cfg = (stride, pad, relu, residual is not None, training)
         ctx.x_needs_grad = x.requires_grad
+        if bn_dst is not None:             # what the consumer's dgrad epilogue needs to take this BN's backward sums
+            bn_dst.out, bn_dst.y_raw, bn_dst.mean, bn_dst.invstd, bn_dst.act = out, y_raw, mean, invstd, int(relu)
+            bn_dst.sums = None
         return out
 
     @staticmethod
@@ -183,8 +205,17 @@ class _ConvBNAct(torch.autograd.Function):
         dout = dout.contiguous(memory_format=torch.channels_last)
         tg, ag = grad_target(gamma)
         tb, ab = grad_target(beta)
-        dy, _, _, dres = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), relu, has_res,
-                                       _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab))
+        pre_sums = None
+        if ctx.bn_dst is not None:
+            # the consumer's dgrad kernel produced `dout` AND this BN's backward sums (only if `dout` is its tensor)
+            pre_sums = ctx.bn_dst.sums if (ctx.bn_dst.sums is not None and not has_res) else None
+            ctx.bn_dst.clear()
+        if pre_sums is not None:
+            dy, _, _, dres = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), relu, has_res,
+                                           _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab), sums=pre_sums)
+        else:
+            dy, _, _, dres = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), relu, has_res,
+                                           _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab))
         grad_written(gamma)
         grad_written(beta)
         w = compute_weight(weight, x.dtype)
@@ -205,7 +236,17 @@ class _ConvBNAct(torch.autograd.Function):
         if ctx.x_needs_grad:
             link = ctx.in_link
             addend = link.take() if link is not None else None
-            if ctx.dgrad_fn is not None:                      # fused dgrad GEMM + all-reduce (+ residual-gradient addend)
+            src = ctx.bn_src
+            fused_bn = None
+            if (src is not None and src.out is not None and ctx.dgrad_fn is None and ctx.post_dgrad is None and link is None
+                    and hasattr(be, "conv_dgrad_bnbwd") and src.out.data_ptr() == x.data_ptr()):
+                # x is the producer's BN output and this op is its only consumer: take the producer's BN-backward
+                # sums in this dgrad's epilogue (None = shape / activation not covered: plain dgrad below)
+                fused_bn = be.conv_dgrad_bnbwd(dy, w, x.shape, stride, pad, addend, src.out, src.y_raw, src.mean,
+                                               src.invstd, src.act)
+            if fused_bn is not None:
+                dx, src.sums = fused_bn
+            elif ctx.dgrad_fn is not None:                    # fused dgrad GEMM + all-reduce (+ residual-gradient addend)
                 dx = ctx.dgrad_fn(dy, w, addend)
             else:
                 if ctx.post_dgrad is None:
@@ -226,16 +267,18 @@ class _ConvBNAct(torch.autograd.Function):
         else:
             be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc, zeroed)
             grad_written(weight)
-        return (dx, None, None, None, dres) + (None,) * 14
+        return (dx, None, None, None, dres) + (None,) * 16
 
 
 def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True, residual=None,
                 momentum=0.1, eps=1e-5, training=True, post_conv=None, post_dgrad=None,
-                conv_fn=None, dgrad_fn=None, in_link=None, res_link=None):
+                conv_fn=None, dgrad_fn=None, in_link=None, res_link=None, bn_src=None, bn_dst=None):
     """``post_conv`` / ``post_dgrad`` are the tensor-parallel reduction points (row-parallel conv
     output, column-parallel conv input-gradient); they take and return a tensor.  ``conv_fn(x, w, want_stats) ->
     (y, sums | None)`` / ``dgrad_fn(dy, w, addend) -> dx`` replace conv + reduction (+ BN statistics pass / residual
-    gradient add) by ONE fused GEMM+collective kernel.  ``relu``: False/0 none, True/1 ReLU, 2 ReLU6."""
+    gradient add) by ONE fused GEMM+collective kernel.  ``relu``: False/0 none, True/1 ReLU, 2 ReLU6.
+    ``bn_dst`` / ``bn_src``: a ``BNBackLink`` shared by a producer (``bn_dst``) and the single consumer of its output
+    (``bn_src``): the consumer's dgrad kernel takes the producer's BatchNorm-backward sums in its epilogue."""
     if not training or not torch.is_grad_enabled():
         be = _be(x)
         if conv_fn is not None:
@@ -249,7 +292,8 @@ def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True,
                                   momentum, eps, residual, relu, training)
         return out
     return _ConvBNAct.apply(x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
-                            momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link, res_link)
+                            momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link, res_link,
+                            bn_src, bn_dst)
 
 
 # ----------------------------------------------------------------------------------------------

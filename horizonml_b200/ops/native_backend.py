@@ -199,7 +199,20 @@ def bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual, r
     return _tb.bn_act_fwd(y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual, relu, training)
 
 
-def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot=None, dbeta_slot=None):
+def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot=None, dbeta_slot=None, sums=None):
+    """``sums``: the final [2, C] (Σg, Σg·x̂) left by ``conv_dgrad_bnbwd`` in the epilogue of the dgrad kernel that
+    produced ``dout`` — the reduce pass is skipped, only the apply kernel runs."""
+    if sums is not None and _bf16_cl(y_raw) and C.channel_ok(y_raw.shape[1]):
+        c = y_raw.shape[1]
+        if dgamma_slot is None:
+            dg = torch.empty(c, dtype=torch.float32, device=y_raw.device)
+            db = torch.empty(c, dtype=torch.float32, device=y_raw.device)
+            ag = ab = False
+        else:
+            dg, ag, db, ab = dgamma_slot.t, dgamma_slot.acc, dbeta_slot.t, dbeta_slot.acc
+        LAUNCHES["bn_act_bwd"] += 1
+        dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, int(relu), has_residual, dg, db, ag, ab, sums, True)
+        return dy, dg, db, (dres if has_residual else None)
     if _bf16_cl(y_raw) and C.channel_ok(y_raw.shape[1]):
         c = y_raw.shape[1]
         if dgamma_slot is None:
@@ -214,7 +227,7 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma
         scratch = ARENA.take(1, 2 * c + (32 if _BN_BWD_FUSED else 0), y_raw.device)
         LAUNCHES["bn_act_bwd"] -= 1 if (scratch is not None and _BN_BWD_FUSED) else 0
         dy, dres = C.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, int(relu), has_residual, dg, db, ag, ab,
-                                scratch)
+                                scratch, False)
         return dy, dg, db, (dres if has_residual else None)
     _fallback("bn_act_bwd", f"{tuple(y_raw.shape)}")
     return _tb.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot, dbeta_slot)
@@ -230,6 +243,23 @@ def conv_dgrad(dy, w, x_shape, stride: int, pad: int, addend=None):
         return C.conv_dgrad(dy, w, list(x_shape), stride, pad, addend, _stable(w))
     _fallback("conv_dgrad", f"x={tuple(x_shape)} w={tuple(w.shape)}")
     return _tb.conv_dgrad(dy, w, x_shape, stride, pad, addend)
+
+
+def conv_dgrad_bnbwd(dy, w, x_shape, stride: int, pad: int, addend, bn_out, bn_yraw, bn_mean, bn_invstd, relu):
+    """conv_dgrad whose epilogue also takes the BatchNorm-backward sums of the layer that produced the conv's input
+    (``bn_out`` / ``bn_yraw`` / statistics of that layer; ``relu`` its activation: only none / ReLU are fused).
+    Returns (dx, sums[2, Cin]) or None when the fused form does not apply (caller runs the plain dgrad)."""
+    if not (_bf16_cl(dy) and w.dtype == torch.bfloat16 and _conv_ok(tuple(x_shape), w.shape, stride, pad)
+            and int(relu) in (0, 1) and _bf16_cl(bn_yraw) and tuple(bn_yraw.shape) == tuple(x_shape)
+            and C.channel_ok(x_shape[1]) and bn_mean.dtype == torch.float32 and bn_invstd.dtype == torch.float32):
+        return None
+    if addend is not None and not (_bf16_cl(addend) and tuple(addend.shape) == tuple(x_shape)):
+        return None
+    LAUNCHES["conv_dgrad"] += 1
+    pre = ARENA.take(2, x_shape[1], dy.device)
+    dx, sums = C.conv_dgrad_bnbwd(dy, w, list(x_shape), stride, pad, addend, _stable(w), bn_out if int(relu) else None,
+                                  bn_yraw, bn_mean, bn_invstd, pre)
+    return dx, sums
 
 
 def _flat_dw_ok(out_grad: torch.Tensor, w_shape) -> bool:

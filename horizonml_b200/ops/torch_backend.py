@@ -74,7 +74,7 @@ class GradSlot:
 
 
 def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: bool,
-               dgamma_slot=None, dbeta_slot=None):
+               dgamma_slot=None, dbeta_slot=None, sums=None):
     """Backward of bn_act_fwd (training mode). Returns (dy_raw, dgamma, dbeta, dres); when slots are
     given dγ/dβ are also written (or accumulated) into them."""
     C = y_raw.shape[1]
@@ -85,8 +85,11 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: 
         g = g * mask.to(g.dtype)
     dres = _cl(g.to(dout.dtype)) if has_residual else None
     xhat = (y_raw.float() - mean.view(1, C, 1, 1)) * invstd.view(1, C, 1, 1)
-    dbeta = g.sum(dim=(0, 2, 3))
-    dgamma = (g * xhat).sum(dim=(0, 2, 3))
+    if sums is not None:                   # (Σg, Σg·x̂) handed over by conv_dgrad_bnbwd of the consuming layer
+        dbeta, dgamma = sums[0].float(), sums[1].float()
+    else:
+        dbeta = g.sum(dim=(0, 2, 3))
+        dgamma = (g * xhat).sum(dim=(0, 2, 3))
     k = (gamma.float() * invstd).view(1, C, 1, 1)
     dy = k * (g - (dbeta / cnt).view(1, C, 1, 1) - xhat * (dgamma / cnt).view(1, C, 1, 1))
     if dgamma_slot is not None:
@@ -102,6 +105,21 @@ def conv_dgrad(dy, w, x_shape, stride: int, pad: int, addend=None):
     if addend is not None:
         dx = dx + addend.to(dx.dtype)
     return _cl(dx)
+
+
+def conv_dgrad_bnbwd(dy, w, x_shape, stride: int, pad: int, addend, bn_out, bn_yraw, bn_mean, bn_invstd, relu):
+    """Oracle of the native dgrad-with-BN-backward-sums kernel: (dx, [Σg, Σg·x̂]) with g = dx·[bn_out > 0] and
+    x̂ = (bn_yraw − mean)·invstd, the sums taken from dx rounded to its storage dtype (what the separate reduction pass
+    would read back)."""
+    if int(relu) not in (0, 1):
+        return None
+    dx = conv_dgrad(dy, w, x_shape, stride, pad, addend)
+    C = x_shape[1]
+    g = dx.float()
+    if int(relu):
+        g = g * (bn_out > 0).to(g.dtype)
+    xhat = (bn_yraw.float() - bn_mean.view(1, C, 1, 1)) * bn_invstd.view(1, C, 1, 1)
+    return dx, torch.stack([g.sum(dim=(0, 2, 3)), (g * xhat).sum(dim=(0, 2, 3))])
 
 
 def conv_wgrad(dy, x, w_shape, stride: int, pad: int, out_grad: torch.Tensor, accumulate: bool,

@@ -87,7 +87,10 @@ def test_native_binding_signatures_for_mobilenet_ops():
         "dwconv_dgrad": lambda: C.dwconv_dgrad(x, w, [2, 16, 4, 4], 1),
         "dwconv_wgrad": lambda: C.dwconv_wgrad(x, x, torch.zeros(16, 1, 3, 3), 1, False, True),
         "bn_act_fwd": lambda: C.bn_act_fwd(x, torch.zeros(2, 16), f, f, f, f, 0.1, 1e-5, None, 2, True),
-        "bn_act_bwd": lambda: C.bn_act_bwd(x, x, x, f, f, f, 2, False, f, f, False, False, None),
+        "bn_act_bwd": lambda: C.bn_act_bwd(x, x, x, f, f, f, 2, False, f, f, False, False, None, False),
+        "bn_act_bwd(sums)": lambda: C.bn_act_bwd(x, x, x, f, f, f, 1, False, f, f, False, False, torch.zeros(2, 16), True),
+        "conv_dgrad_bnbwd": lambda: C.conv_dgrad_bnbwd(x, torch.zeros(16, 16, 3, 3, dtype=torch.bfloat16).contiguous(
+            memory_format=torch.channels_last), [2, 16, 4, 4], 1, 1, None, False, x, x, f, f, None),
     }
     for name, fn in calls.items():
         with pytest.raises(RuntimeError, match="CUDA tensor"):

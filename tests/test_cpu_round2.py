@@ -246,3 +246,37 @@ def test_protocol_model_bulk_allreduce_ring():
     assert sim(11, trials=100) == 0 and sim(1, trials=10) == 0 and sim(3, trials=30) == 0
     assert sim(40, stages=3, warps=4, trials=60, seed=1) == 0
     assert sim(11, trials=20, prefetch=3) == 20
+
+
+def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
+    """ops.BNBackLink: with HZ_BN_BWD_IN_DGRAD the BasicBlock's conv2 dgrad returns bn1's backward sums and bn1's backward
+    skips its own reduction — the block's output, input gradient and every parameter gradient must not change (PyTorch-op
+    backend: the oracle of the fused dgrad kernel; identity and downsample blocks)."""
+    import horizonml_b200.models.resnet as R
+    from horizonml_b200 import ops
+    from horizonml_b200.ops import torch_backend as tb
+    ops.set_backend("torch")
+    calls = {"n": 0}
+    orig = tb.conv_dgrad_bnbwd
+
+    def counted(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+    tb.conv_dgrad_bnbwd = counted
+    try:
+        for cin, cout, stride in ((16, 16, 1), (16, 32, 2)):
+            res = []
+            for flag in (False, True):
+                R._BN_BWD_IN_DGRAD = flag
+                torch.manual_seed(3)
+                blk = R.BasicBlock(cin, cout, stride).train()
+                x = torch.randn(4, cin, 8, 8).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+                y = blk(x)
+                y.backward(torch.randn(y.shape, generator=torch.Generator().manual_seed(1)))
+                res.append([y.detach(), x.grad] + [p.grad for p in blk.parameters()])
+            for a, b in zip(*res):
+                assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+        assert calls["n"] == 2                       # one fused dgrad per block, only with the flag on
+    finally:
+        tb.conv_dgrad_bnbwd = orig
+        R._BN_BWD_IN_DGRAD = False

@@ -103,3 +103,73 @@ def test_head_beyond_48k_of_shared_memory(n):
     torch.cuda.synchronize()
     assert abs(l.item() - l2.item()) < 1e-3 * max(1, abs(l2.item())) and c.item() == c2.item()
     assert rel_err(df, df2) < 1e-2 and rel_err(dW, dW2) < 1e-3 and rel_err(db, db2) < 1e-3
+
+
+# ---- BatchNorm-backward sums taken in the consumer's dgrad epilogue (ops.BNBackLink, HZ_BN_BWD_IN_DGRAD) --------------
+DGRAD_SHAPES = [  # N, Cin, H, W, Cout, R, stride, pad
+    (64, 64, 8, 8, 64, 3, 1, 1), (64, 64, 8, 8, 128, 3, 2, 1), (64, 128, 4, 4, 128, 3, 1, 1), (64, 256, 2, 2, 256, 3, 1, 1),
+    (64, 512, 1, 1, 512, 3, 1, 1), (64, 64, 8, 8, 128, 1, 2, 0), (16, 64, 8, 8, 64, 3, 1, 1), (64, 32, 4, 4, 96, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("cfg", DGRAD_SHAPES)
+@pytest.mark.parametrize("relu,with_addend", [(1, False), (0, False), (1, True)])
+def test_dgrad_with_bn_backward_sums(cfg, relu, with_addend):
+    """conv_dgrad_bnbwd == plain dgrad (bit-identical dx) + the sums the separate channel-reduce kernel would produce."""
+    from horizonml_b200.ops import native_backend as nb
+    from horizonml_b200.ops import torch_backend as tb
+    N, Cin, H, W, Cout, R, s, p = cfg
+    g = torch.Generator().manual_seed(9)
+    w = cl((torch.randn(Cout, Cin, R, R, generator=g) / (Cin * R * R) ** 0.5).to(DEV).bfloat16())
+    Ho, Wo = (H + 2 * p - R) // s + 1, (W + 2 * p - R) // s + 1
+    dy = cl((torch.randn(N, Cout, Ho, Wo, generator=g) * 0.5).to(DEV).bfloat16())
+    add = cl((torch.randn(N, Cin, H, W, generator=g) * 0.5).to(DEV).bfloat16()) if with_addend else None
+    y_raw = cl(torch.randn(N, Cin, H, W, generator=g).to(DEV).bfloat16())            # the producing layer's tensors
+    mean, invstd = torch.randn(Cin, generator=g).to(DEV) * 0.1, (torch.rand(Cin, generator=g) + 0.5).to(DEV)
+    out = cl(torch.randn(N, Cin, H, W, generator=g).to(DEV).bfloat16())               # ~half of it <= 0: the ReLU mask
+    nb.step_begin(DEV)
+    got = nb.conv_dgrad_bnbwd(dy, w, (N, Cin, H, W), s, p, add, out, y_raw, mean, invstd, relu)
+    assert got is not None
+    dx, sums = got
+    dx0 = nb.conv_dgrad(dy, w, (N, Cin, H, W), s, p, add)
+    nb.step_end()
+    assert torch.equal(dx, dx0)
+    # reference sums from the stored bf16 dx, exactly what bn_act_bwd's reduction kernel computes
+    gg = dx.float() * ((out > 0).float() if relu else 1.0)
+    xhat = (y_raw.float() - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+    ref = torch.stack([gg.sum(dim=(0, 2, 3)), (gg * xhat).sum(dim=(0, 2, 3))])
+    assert rel_err(sums.view(2, -1), ref) < 1e-3
+    # and the apply pass fed with them == the two-kernel BN backward
+    gamma = (torch.rand(Cin, generator=g) + 0.5).to(DEV)
+    a = nb.bn_act_bwd(dx, out, y_raw, mean, invstd, gamma, relu, False, sums=sums)
+    b = nb.bn_act_bwd(dx, out, y_raw, mean, invstd, gamma, relu, False)
+    assert rel_err(a[0], b[0]) < 2e-3 and rel_err(a[1], b[1]) < 1e-3 and rel_err(a[2], b[2]) < 1e-3
+
+
+@pytest.mark.parametrize("cin,cout,stride,hw", [(64, 64, 1, 8), (64, 128, 2, 8), (128, 256, 2, 4), (256, 256, 1, 2),
+                                                (512, 512, 1, 1)])
+def test_basic_block_with_bn_sums_in_dgrad(cin, cout, stride, hw):
+    """HZ_BN_BWD_IN_DGRAD on the native backend: same block output / gradients as with the separate reduction kernel,
+    one bn_act_bwd launch less."""
+    import horizonml_b200.models.resnet as R
+    from horizonml_b200 import ops
+    from horizonml_b200.ops import native_backend as nb
+    g = torch.Generator().manual_seed(7)
+    x0 = cl(torch.randn(64, cin, hw, hw, generator=g).to(DEV).bfloat16())
+    dy = cl((torch.randn(64, cout, hw // stride, hw // stride, generator=g) * 0.1).to(DEV).bfloat16())
+    res, launches = {}, {}
+    try:
+        for flag in (False, True):
+            R._BN_BWD_IN_DGRAD = flag
+            before = nb.LAUNCHES["bn_act_bwd"]
+            res[flag] = _run(lambda: R.BasicBlock(cin, cout, stride), x0, dy, "native")
+            launches[flag] = nb.LAUNCHES["bn_act_bwd"] - before
+    finally:
+        R._BN_BWD_IN_DGRAD = False
+        ops.set_backend("torch")
+    assert launches[True] == launches[False] - 1, launches
+    (y0, dx0, g0), (y1, dx1, g1) = res[False], res[True]
+    assert torch.equal(y0, y1) and rel_err(dx1, dx0) < 1e-2
+    for n in g0:
+        if g0[n].abs().max().item() > 1e-6:
+            assert rel_err(g1[n], g0[n]) < 2e-2, (n, rel_err(g1[n], g0[n]))

@@ -6,7 +6,8 @@ measure (or why not) and the test itself only asserts that it produced a report.
 
 * persistent vs one-tile-per-CTA convolution kernel vs cuDNN at batch 4096 (TFLOP/s, fraction of the measured bf16 peak)
 * MobileNetV2 and ResNet-18 training step through the DP engine on one GPU (ms/step, images/s)
-* `bench.py --batch 512` with the one-tile-per-CTA kernels and with the persistent kernels (HZ_CONV_PERSIST=1)"""
+* `bench.py` at batch 64 with and without the BatchNorm-backward sums taken in the dgrad epilogue (HZ_BN_BWD_IN_DGRAD=1),
+  and at batch 512 with the one-tile-per-CTA kernels and with the persistent kernels (HZ_CONV_PERSIST=1)"""
 import json
 import os
 import warnings
@@ -89,15 +90,20 @@ def test_round_end_perf_report():
     import subprocess
     import sys
     torch.cuda.empty_cache()
-    for tag, env_extra in (("b512_latency_kernels", {"HZ_CONV_PERSIST": "0"}), ("b512_persistent_kernels", {"HZ_CONV_PERSIST": "1"})):
+    variants = (("b64_default", 64, 100, {}),
+                ("b64_bn_backward_sums_in_dgrad", 64, 100, {"HZ_BN_BWD_IN_DGRAD": "1"}),     # 8 reduction kernels less per step
+                ("b512_latency_kernels", 512, 30, {"HZ_CONV_PERSIST": "0"}),
+                ("b512_persistent_kernels", 512, 30, {"HZ_CONV_PERSIST": "1"}))
+    for tag, batch, steps, env_extra in variants:
         try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--batch", "512", "--steps", "30",
-                                "--warmup", "5"], cwd=ROOT, env=dict(os.environ, **env_extra), capture_output=True, text=True,
-                               timeout=120)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--batch", str(batch), "--steps",
+                                str(steps), "--warmup", "10"], cwd=ROOT, env=dict(os.environ, **env_extra), capture_output=True,
+                               text=True, timeout=120)
             line = [ln for ln in r.stdout.splitlines() if ln.startswith("{") and '"metric"' in ln]
             if line:
                 d = json.loads(line[-1])
                 _report("bench", {"variant": tag, "images_per_s": d["value"], "ms_per_step": d["ms_per_step"],
+                                  "launches_per_step": d.get("launches_per_step"),
                                   "fallbacks": d.get("native_fallbacks"), "cuda_graph": d["config"].get("cuda_graph")})
                 sections += 1
             else:
