@@ -47,8 +47,8 @@ def _memcheck(selection: str, files, budget_s: int, exe: str = ""):
 @pytest.mark.gpu
 @pytest.mark.late(order=5)
 def test_memcheck_clean_on_elementwise_kernels():
-    """BatchNorm forward + backward (reduce, apply), max-pool forward / backward, the classifier head: ~100 s box."""
-    _memcheck("test_bn_act and 64-16 or test_maxpool or test_head and 1", ["tests/test_gpu_kernels.py"], 100)
+    """BatchNorm forward + backward (reduce, apply), max-pool forward / backward, the classifier head: 75 s box."""
+    _memcheck("test_bn_act and 64-16 or test_maxpool or test_head and 1", ["tests/test_gpu_kernels.py"], 75)
 
 
 @pytest.mark.gpu
