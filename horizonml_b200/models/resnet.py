@@ -58,8 +58,9 @@ def _cba(x, conv: ConvW, bn: BNP, relu: bool, residual=None, training=True, in_l
 # the block input feeds two branches; their gradients are summed inside the later dgrad kernel's epilogue
 # (ops.GradLink) instead of by a separate accumulation kernel.  HZ_FUSE_RESADD=0 restores plain autograd.
 _FUSE_RESADD = os.environ.get("HZ_FUSE_RESADD", "1") != "0"
-# bn1's backward sums (Σg, Σg·x̂) taken in the epilogue of conv2's dgrad kernel, whose output IS bn1's upstream gradient
-# (ops.BNBackLink): one reduction kernel less per block.  Off by default: written after the round's GPU budget was
+# BatchNorm-backward sums (Σg, Σg·x̂) taken in the epilogue of the dgrad kernel whose output IS that BatchNorm's upstream
+# gradient (ops.BNBackLink): bn1 <- conv2's dgrad inside a block, the previous block's bn2 <- whichever of conv1 /
+# downsample runs last (it folds the other shares in): 15 of the 20 reduction kernels of a step disappear.  Off by default: written after the round's GPU budget was
 # spent, first hardware run in tests/test_gpu_blocks.py; HZ_BN_BWD_IN_DGRAD=1 enables it.
 _BN_BWD_IN_DGRAD = os.environ.get("HZ_BN_BWD_IN_DGRAD", "0") == "1"
 
@@ -80,13 +81,22 @@ class BasicBlock(nn.Module):
     def forward(self, x):
         t = self.training
         link = ops.GradLink(2) if (_FUSE_RESADD and t and torch.is_grad_enabled() and x.requires_grad) else None
-        bl = ops.BNBackLink() if (_BN_BWD_IN_DGRAD and t and torch.is_grad_enabled()) else None
+        fuse = _BN_BWD_IN_DGRAD and t and torch.is_grad_enabled()
+        bl = ops.BNBackLink() if fuse else None                       # bn1 -> conv2 (only consumer)
+        # the previous block's bn2 -> this block's consumers of x (their gradient shares meet in `link`); this block's
+        # bn2 -> the next block, handed over on the output tensor
+        prev = getattr(x, "_hz_bn_back", None) if (fuse and link is not None) else None
+        nxt = ops.BNBackLink(single=False) if fuse else None
         if self.downsample is not None:
-            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t, in_link=link)
-            y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link, bn_dst=bl)
-            return _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t, bn_src=bl)
-        y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link, bn_dst=bl)
-        return _cba(y, self.conv2, self.bn2, relu=True, residual=x, training=t, res_link=link, bn_src=bl)
+            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t, in_link=link, bn_src=prev)
+            y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link, bn_dst=bl, bn_src=prev)
+            out = _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t, bn_src=bl, bn_dst=nxt)
+        else:
+            y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link, bn_dst=bl, bn_src=prev)
+            out = _cba(y, self.conv2, self.bn2, relu=True, residual=x, training=t, res_link=link, bn_src=bl, bn_dst=nxt)
+        if nxt is not None:
+            out._hz_bn_back = nxt
+        return out
 
 
 class Stem(nn.Module):

@@ -147,12 +147,16 @@ class BNBackLink:
     consumer's dgrad kernel takes the producer's BN-backward sums (Σg, Σg·x̂) in its epilogue and the producer's
     backward skips its reduction pass over dout / out / y_raw (one kernel less per layer pair).  Only used on the
     native backend, for activations none / ReLU, when the consumer's dgrad output is the complete gradient of the
-    producer's output (no other consumer)."""
-    __slots__ = ("out", "y_raw", "mean", "invstd", "act", "sums")
+    producer's output: either the consumer is the only one (``single=True``, e.g. conv1 -> conv2 inside a block), or the
+    producer's output feeds several ops whose gradients meet in a ``GradLink`` — then the op that runs last (it folds
+    the parked shares into its dgrad epilogue) sees the total and takes the sums (``single=False``: a block's bn2 ->
+    the next block's conv1 / downsample / skip connection)."""
+    __slots__ = ("out", "y_raw", "mean", "invstd", "act", "sums", "single")
 
-    def __init__(self):
+    def __init__(self, single: bool = True):
         self.out = self.y_raw = self.mean = self.invstd = self.sums = None
         self.act = 0
+        self.single = single
 
     def clear(self):
         self.out = self.y_raw = self.mean = self.invstd = self.sums = None
@@ -208,7 +212,7 @@ class _ConvBNAct(torch.autograd.Function):
         pre_sums = None
         if ctx.bn_dst is not None:
             # the consumer's dgrad kernel produced `dout` AND this BN's backward sums (only if `dout` is its tensor)
-            pre_sums = ctx.bn_dst.sums if (ctx.bn_dst.sums is not None and not has_res) else None
+            pre_sums = ctx.bn_dst.sums
             ctx.bn_dst.clear()
         if pre_sums is not None:
             dy, _, _, dres = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), relu, has_res,
@@ -238,10 +242,13 @@ class _ConvBNAct(torch.autograd.Function):
             addend = link.take() if link is not None else None
             src = ctx.bn_src
             fused_bn = None
-            if (src is not None and src.out is not None and ctx.dgrad_fn is None and ctx.post_dgrad is None and link is None
-                    and hasattr(be, "conv_dgrad_bnbwd") and src.out.data_ptr() == x.data_ptr()):
-                # x is the producer's BN output and this op is its only consumer: take the producer's BN-backward
-                # sums in this dgrad's epilogue (None = shape / activation not covered: plain dgrad below)
+            total_here = (link is None and src is not None and src.single) or (link is not None and link.k == link.n - 1)
+            if (src is not None and src.out is not None and src.sums is None and ctx.dgrad_fn is None
+                    and ctx.post_dgrad is None and total_here and hasattr(be, "conv_dgrad_bnbwd")
+                    and src.out.data_ptr() == x.data_ptr()):
+                # x is the producer's BN output and this dgrad's result (with the parked shares of x's other consumers
+                # folded into its epilogue) is the complete gradient of x: take the producer's BN-backward sums here
+                # (None = shape / activation not covered: plain dgrad below)
                 fused_bn = be.conv_dgrad_bnbwd(dy, w, x.shape, stride, pad, addend, src.out, src.y_raw, src.mean,
                                                src.invstd, src.act)
             if fused_bn is not None:

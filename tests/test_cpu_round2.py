@@ -277,6 +277,20 @@ def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
             for a, b in zip(*res):
                 assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
         assert calls["n"] == 2                       # one fused dgrad per block, only with the flag on
+        # a stack of blocks: the previous block's bn2 gets its sums from whichever consumer of the block output runs last
+        calls["n"] = 0
+        res = []
+        for flag in (False, True):
+            R._BN_BWD_IN_DGRAD = flag
+            torch.manual_seed(5)
+            net = torch.nn.Sequential(R.BasicBlock(16, 16, 1), R.BasicBlock(16, 32, 2), R.BasicBlock(32, 32, 1)).train()
+            x = torch.randn(4, 16, 8, 8).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            y = net(x)
+            y.backward(torch.randn(y.shape, generator=torch.Generator().manual_seed(2)))
+            res.append([y.detach(), x.grad] + [p.grad for p in net.parameters()])
+        for a, b in zip(*res):
+            assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+        assert calls["n"] == 5                       # 3 x (bn1 <- conv2) + 2 x (previous bn2 <- next block)
     finally:
         tb.conv_dgrad_bnbwd = orig
         R._BN_BWD_IN_DGRAD = False

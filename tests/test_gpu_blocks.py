@@ -173,3 +173,47 @@ def test_basic_block_with_bn_sums_in_dgrad(cin, cout, stride, hw):
     for n in g0:
         if g0[n].abs().max().item() > 1e-6:
             assert rel_err(g1[n], g0[n]) < 2e-2, (n, rel_err(g1[n], g0[n]))
+
+
+def test_resnet18_step_with_bn_sums_in_dgrad():
+    """Whole model: 15 of the 20 BatchNorm-backward reduction kernels are gone (bn1 of every block and bn2 of every block
+    but the last take their sums from a dgrad epilogue), the first-step loss is unchanged, gradients agree with the
+    two-kernel path to the run-to-run noise of the fp32 atomics, and training still makes progress."""
+    import horizonml_b200.models.resnet as R
+    from horizonml_b200 import ops
+    from horizonml_b200.models.flat import FlatAdam, FlatParams
+    from horizonml_b200.ops import native_backend as nb
+    g = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (64, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+    labels = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    res = {}
+    try:
+        ops.set_backend("native")
+        for flag in (False, True):
+            R._BN_BWD_IN_DGRAD = flag
+            model = R.resnet18(10, seed=0).to(DEV).train()
+            flat = FlatParams(list(model.named_parameters()), DEV, torch.bfloat16)
+            opt = FlatAdam(flat, lr=1e-3)
+            losses = []
+            for it in range(3):
+                x = ops.stem_prepare(images.permute(0, 3, 1, 2), dtype=torch.bfloat16)
+                ops.step_begin(DEV)
+                flat.begin_step()
+                before = nb.LAUNCHES["bn_act_bwd"]
+                loss, _ = model.forward_loss(x, labels)
+                loss.backward()
+                ops.join_side()
+                ops.step_end()
+                if it == 0:
+                    res[flag] = (flat.grad.clone(), nb.LAUNCHES["bn_act_bwd"] - before)
+                opt.step()
+                losses.append(float(loss.detach()))
+            res[("loss", flag)] = losses
+    finally:
+        R._BN_BWD_IN_DGRAD = False
+        ops.set_backend("torch")
+    assert res[False][1] == 40 and res[True][1] == 25, (res[False][1], res[True][1])
+    l0, l1 = res[("loss", False)], res[("loss", True)]
+    assert l0[0] == l1[0] and all(v == v for v in l1) and l1[-1] < l1[0], (l0, l1)
+    cos = torch.nn.functional.cosine_similarity(res[False][0].flatten(), res[True][0].flatten(), dim=0).item()
+    assert cos > 0.9, cos
