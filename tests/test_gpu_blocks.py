@@ -214,6 +214,6 @@ def test_resnet18_step_with_bn_sums_in_dgrad():
         ops.set_backend("torch")
     assert res[False][1] == 40 and res[True][1] == 25, (res[False][1], res[True][1])
     l0, l1 = res[("loss", False)], res[("loss", True)]
-    assert l0[0] == l1[0] and all(v == v for v in l1) and l1[-1] < l1[0], (l0, l1)
+    assert abs(l0[0] - l1[0]) < 1e-3 and all(v == v for v in l1) and l1[-1] < l1[0], (l0, l1)   # (loss: fp32 atomics)
     cos = torch.nn.functional.cosine_similarity(res[False][0].flatten(), res[True][0].flatten(), dim=0).item()
     assert cos > 0.9, cos
