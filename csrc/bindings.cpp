@@ -114,6 +114,32 @@ Tensor maxpool_bwd(const Tensor& dy, const Tensor& idx, std::vector<int64_t> x_s
   return dx;
 }
 
+// max-pool backward + the BatchNorm-backward sums of the layer feeding the pool: {dx, sums[2,C]}
+std::vector<Tensor> maxpool_bwd_bn(const Tensor& dy, const Tensor& idx, std::vector<int64_t> x_shape,
+                                   c10::optional<Tensor> bn_out, const Tensor& bn_yraw, const Tensor& bn_mean,
+                                   const Tensor& bn_invstd, c10::optional<Tensor> sums_pre) {
+  check_cl(dy, "dy"); check_cl(bn_yraw, "bn_yraw");
+  c10::cuda::CUDAGuard g(dy.device());
+  const int N = (int)x_shape[0], Cc = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
+  Tensor dx = empty_cl(dy, N, Cc, H, W);
+  TORCH_CHECK(bn_yraw.sizes() == dx.sizes() && bn_mean.numel() == Cc && bn_invstd.numel() == Cc &&
+              bn_mean.scalar_type() == at::kFloat && bn_invstd.scalar_type() == at::kFloat, "maxpool_bwd_bn: BN operand mismatch");
+  const void* bo = nullptr;
+  if (bn_out.has_value() && bn_out->defined()) {
+    check_cl(*bn_out, "bn_out");
+    TORCH_CHECK(bn_out->sizes() == dx.sizes(), "maxpool_bwd_bn: bn_out shape");
+    bo = bn_out->data_ptr();
+  }
+  const bool pre = sums_pre.has_value() && sums_pre->defined();
+  Tensor sums = pre ? *sums_pre : at::empty({2, Cc}, dy.options().dtype(at::kFloat));
+  TORCH_CHECK(sums.numel() >= 2 * Cc && sums.scalar_type() == at::kFloat && sums.is_contiguous());
+  int rc = hz_maxpool_bwd_bn(cptr(dy), idx.data_ptr(), dx.data_ptr(), bo, bn_yraw.data_ptr(), bn_mean.data_ptr<float>(),
+                             bn_invstd.data_ptr<float>(), sums.data_ptr<float>(), pre ? 1 : 0, bo != nullptr ? 1 : 0, N, H, W, Cc,
+                             cur_stream());
+  TORCH_CHECK(rc == 0, "hz_maxpool_bwd_bn: shape not covered");
+  return {dx, sums};
+}
+
 // uint8 NHWC-physical (logical NCHW channels_last view) -> normalised bf16, same layout
 Tensor u8_normalize(const Tensor& img, double mean, double std) {
   TORCH_CHECK(img.is_cuda() && img.scalar_type() == at::kByte);
@@ -659,6 +685,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_act_bwd", &bn_act_bwd);
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("maxpool_bwd_bn", &maxpool_bwd_bn);
   m.def("u8_normalize", &u8_normalize);
   m.def("im2col_small", &im2col_small);
   m.def("pad_rows", &pad_rows);

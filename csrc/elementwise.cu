@@ -400,6 +400,78 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// max-pool backward that also takes the BatchNorm-backward sums of the layer feeding the pool (the stem's bn1: the pool
+// is the only consumer of its output, so dx IS that BatchNorm's upstream gradient): sums[0:C] += sum g,
+// sums[C:2C] += sum g*xhat with g = dx * [bn_out > 0] from the bf16 values being stored — the separate reduction pass
+// over dx / out / y_raw (the largest one of the step: 64 x 16 x 16 x 64) disappears.  Thread layout of the reductions
+// (C/8 channel vectors x 256/(C/8) row lanes, C/8 a power of two), pixel math of maxpool_bwd_kernel.
+__global__ void __launch_bounds__(256) maxpool_bwd_bn_kernel(
+    const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx, __nv_bfloat16* __restrict__ dx,
+    const __nv_bfloat16* __restrict__ bn_out, const __nv_bfloat16* __restrict__ bn_yraw,
+    const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums, int relu,
+    int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();
+  extern __shared__ float red[];              // [rlanes][nvec][16]
+  const int nvec = C >> 3;
+  const int rlanes = 256 / nvec;
+  const int cv = threadIdx.x % nvec, rl = threadIdx.x / nvec;
+  float s[8], q[8], mu[8], is[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = q[i] = 0.f; mu[i] = mean[cv * 8 + i]; is[i] = invstd[cv * 8 + i]; }
+  const int P = N * H * W;
+  for (int p = blockIdx.x * rlanes + rl; p < P; p += gridDim.x * rlanes) {
+    const int w = p % W;
+    const int t = p / W;
+    const int h = t % H;
+    const int n = t / H;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int ho = h / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho >= Ho) continue;
+      const int r = h - (ho * 2 - 1);
+      for (int wo = w / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo >= Wo) continue;
+        const int me = r * 3 + (w - (wo * 2 - 1));
+        const size_t oo = (((size_t)n * Ho + ho) * Wo + wo) * C + cv * 8;
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + oo);
+        float gv[8];
+        unpack8(ld8(dy + oo), gv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int a = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xFF;
+          acc[i] += (a == me) ? gv[i] : 0.f;
+        }
+      }
+    }
+    const size_t off = (size_t)p * C + cv * 8;
+    const bf16x8 v = pack8(acc);
+    st8(dx + off, v);
+    float g[8], y[8];
+    unpack8(v, g);                                   // the rounded values a separate pass would read back
+    unpack8(ld8(bn_yraw + off), y);
+    if (relu) {
+      float o[8];
+      unpack8(ld8(bn_out + off), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += g[i]; q[i] += g[i] * (y[i] - mu[i]) * is[i]; }
+  }
+  float* mine = red + ((size_t)rl * nvec + cv) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
+  __syncthreads();
+  for (int o = threadIdx.x; o < nvec * 16; o += 256) {
+    const int v = o >> 4, j = o & 15;
+    float tt = 0.f;
+    for (int k = 0; k < rlanes; ++k) tt += red[((size_t)k * nvec + v) * 16 + j];
+    atomicAdd(&sums[(j >> 3) * C + v * 8 + (j & 7)], tt);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // stem: uint8 NHWC -> normalised bf16 NHWC;  small-Cin im2col -> A[M, Kp] (K = (r,s,c), zero padded)
 // ------------------------------------------------------------------------------------------------
@@ -918,6 +990,24 @@ void hz_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   hz::launch(hz::maxpool_bwd_kernel, dim3(grid_for((size_t)N * H * W * (C / 8), 256)), dim3(256), 0, st, 
       (const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
+}
+
+// max-pool backward + BatchNorm-backward sums of the layer that feeds the pool (see maxpool_bwd_bn_kernel); C/8 must be a
+// power of two; sums [2C] fp32 (sums_is_zero: already cleared).  Returns 0, or -1 when the shape is not covered.
+int hz_maxpool_bwd_bn(const void* dy, const void* idx, void* dx, const void* bn_out, const void* bn_yraw, const float* mean,
+                      const float* invstd, float* sums, int sums_is_zero, int relu, int N, int H, int W, int C,
+                      cudaStream_t st) {
+  if (hz_channel_ok(C) != 1 || (long long)N * H * W >= (1ll << 31) || (relu && bn_out == nullptr)) return -1;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  if (!sums_is_zero) hz::zero_f32(sums, (size_t)2 * C, st);
+  const int rlanes = 256 / (C / 8);
+  int grid = (N * H * W + rlanes - 1) / rlanes;
+  grid = (grid + 1) / 2;                                  // >= 2 pixels per lane
+  if (grid < 1) grid = 1;
+  if (grid > 148 * 4) grid = 148 * 4;
+  return hz::launch(hz::maxpool_bwd_bn_kernel, dim3(grid), dim3(256), sizeof(float) * 256 * 16, st,
+                    (const __nv_bfloat16*)dy, (const uint8_t*)idx, (__nv_bfloat16*)dx, (const __nv_bfloat16*)bn_out,
+                    (const __nv_bfloat16*)bn_yraw, mean, invstd, sums, relu, N, H, W, C, Ho, Wo) == cudaSuccess ? 0 : -1;
 }
 
 void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std, cudaStream_t st) {

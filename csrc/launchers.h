@@ -20,6 +20,9 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
                    int scratch_is_zero, cudaStream_t st);
 void hz_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, cudaStream_t st);
 void hz_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, cudaStream_t st);
+int hz_maxpool_bwd_bn(const void* dy, const void* idx, void* dx, const void* bn_out, const void* bn_yraw, const float* mean,
+                      const float* invstd, float* sums, int sums_is_zero, int relu, int N, int H, int W, int C,
+                      cudaStream_t st);
 void hz_u8_normalize(const void* in, void* out, size_t n, float mean, float std, cudaStream_t st);
 void hz_im2col_small(const void* x, void* A, int N, int H, int W, int Cin, int R, int S, int stride, int pad,
                      int Ho, int Wo, int Kp, cudaStream_t st);

@@ -108,8 +108,10 @@ class Stem(nn.Module):
 
     def forward(self, x):
         p = self._p
-        y = _cba(x, p.conv1, p.bn1, relu=True, training=p.training)
-        return ops.maxpool3x3s2(y)
+        # bn1's output has one consumer, the pool: its backward kernel also takes bn1's backward sums (ops.BNBackLink)
+        bl = ops.BNBackLink() if (_BN_BWD_IN_DGRAD and p.training and torch.is_grad_enabled()) else None
+        y = _cba(x, p.conv1, p.bn1, relu=True, training=p.training, bn_dst=bl)
+        return ops.maxpool3x3s2(y, bn_src=bl)
 
 
 class ResNet18(nn.Module):

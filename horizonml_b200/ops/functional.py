@@ -363,20 +363,32 @@ def dwconv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, act=2, momentum
 
 class _MaxPool(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, bn_src=None):
         ctx.be = _be(x)
+        ctx.bn_src = bn_src
+        ctx.x_ptr = x.data_ptr()
         y, ctx.aux = ctx.be.maxpool_fwd(x, True)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        return ctx.be.maxpool_bwd(dy.contiguous(memory_format=torch.channels_last), ctx.aux)
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        src = ctx.bn_src
+        if (src is not None and src.out is not None and src.sums is None and src.single and hasattr(ctx.be, "maxpool_bwd_bn")
+                and src.out.data_ptr() == ctx.x_ptr):
+            # the pool is the only consumer of the producing layer's BN output: take that BatchNorm's backward sums here
+            fused = ctx.be.maxpool_bwd_bn(dy, ctx.aux, src.out, src.y_raw, src.mean, src.invstd, src.act)
+            if fused is not None:
+                dx, src.sums = fused
+                return dx, None
+        return ctx.be.maxpool_bwd(dy, ctx.aux), None
 
 
-def maxpool3x3s2(x):
+def maxpool3x3s2(x, bn_src=None):
+    """``bn_src``: the ``BNBackLink`` of the conv_bn_act that produced ``x`` when this pool is its only consumer."""
     if not x.requires_grad or not torch.is_grad_enabled():
         return _be(x).maxpool_fwd(x, False)[0]
-    return _MaxPool.apply(x)
+    return _MaxPool.apply(x, bn_src)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -343,6 +343,19 @@ def maxpool_bwd(dy, aux):
     return _tb.maxpool_bwd(dy, aux)
 
 
+def maxpool_bwd_bn(dy, aux, bn_out, bn_yraw, bn_mean, bn_invstd, relu):
+    """max-pool backward whose kernel also takes the BatchNorm-backward sums of the layer that feeds the pool (its output
+    has no other consumer).  Returns (dx, sums[2, C]) or None when the fused form does not apply."""
+    if not (isinstance(aux, tuple) and aux and isinstance(aux[0], str) and aux[0] == "native" and _bf16_cl(dy)
+            and int(relu) in (0, 1) and _bf16_cl(bn_yraw) and tuple(bn_yraw.shape) == tuple(aux[2])
+            and C.channel_ok(aux[2][1]) == 1 and bn_mean.dtype == torch.float32 and bn_invstd.dtype == torch.float32):
+        return None
+    LAUNCHES["maxpool"] += 1
+    pre = ARENA.take(2, aux[2][1], dy.device)
+    dx, sums = C.maxpool_bwd_bn(dy, aux[1], list(aux[2]), bn_out if int(relu) else None, bn_yraw, bn_mean, bn_invstd, pre)
+    return dx, sums
+
+
 def head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out, db_out, accumulate, need_dfeat=True):
     if (_bf16_cl(feat) and fc_w.dtype == torch.float32 and fc_w.is_contiguous() and fc_w.shape[0] <= 64
             and dw_out.is_contiguous()):

@@ -179,6 +179,19 @@ def maxpool_bwd(dy, aux):
     return _cl(dx)
 
 
+def maxpool_bwd_bn(dy, aux, bn_out, bn_yraw, bn_mean, bn_invstd, relu):
+    """Oracle of the native max-pool-backward-with-BN-sums kernel: (dx, [Σg, Σg·x̂])."""
+    if int(relu) not in (0, 1):
+        return None
+    dx = maxpool_bwd(dy, aux)
+    C = dx.shape[1]
+    g = dx.float()
+    if int(relu):
+        g = g * (bn_out > 0).to(g.dtype)
+    xhat = (bn_yraw.float() - bn_mean.view(1, C, 1, 1)) * bn_invstd.view(1, C, 1, 1)
+    return dx, torch.stack([g.sum(dim=(0, 2, 3)), (g * xhat).sum(dim=(0, 2, 3))])
+
+
 def head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale: float, n_valid: int,
                  dw_out, db_out, accumulate: bool, need_dfeat: bool = True):
     """global-avg-pool → FC → softmax cross-entropy, forward AND backward in one op.

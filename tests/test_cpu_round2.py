@@ -291,6 +291,30 @@ def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
         for a, b in zip(*res):
             assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
         assert calls["n"] == 5                       # 3 x (bn1 <- conv2) + 2 x (previous bn2 <- next block)
+        # the whole model: 8 + 7 dgrad hand-offs and the stem's bn1 <- max-pool backward; loss and gradients unchanged
+        pool_calls = {"n": 0}
+        orig_pool = tb.maxpool_bwd_bn
+
+        def counted_pool(*a, **k):
+            pool_calls["n"] += 1
+            return orig_pool(*a, **k)
+        tb.maxpool_bwd_bn = counted_pool
+        try:
+            calls["n"] = 0
+            res = []
+            xb = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(4)).contiguous(memory_format=torch.channels_last)
+            yb = torch.tensor([1, 3, 5, 7])
+            for flag in (False, True):
+                R._BN_BWD_IN_DGRAD = flag
+                model = R.resnet18(10, seed=0).train()
+                loss, _ = model.forward_loss(xb, yb)
+                loss.backward()
+                res.append([loss.detach()] + [p.grad for p in model.parameters()])
+            for a, b in zip(*res):
+                assert torch.allclose(a, b, atol=2e-5, rtol=1e-4), (a - b).abs().max()
+            assert calls["n"] == 15 and pool_calls["n"] == 1
+        finally:
+            tb.maxpool_bwd_bn = orig_pool
     finally:
         tb.conv_dgrad_bnbwd = orig
         R._BN_BWD_IN_DGRAD = False

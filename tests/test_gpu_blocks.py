@@ -176,8 +176,8 @@ def test_basic_block_with_bn_sums_in_dgrad(cin, cout, stride, hw):
 
 
 def test_resnet18_step_with_bn_sums_in_dgrad():
-    """Whole model: 15 of the 20 BatchNorm-backward reduction kernels are gone (bn1 of every block and bn2 of every block
-    but the last take their sums from a dgrad epilogue), the first-step loss is unchanged, gradients agree with the
+    """Whole model: 16 of the 20 BatchNorm-backward reduction kernels are gone (bn1 of every block and bn2 of every block
+    but the last take their sums from a dgrad epilogue, the stem's bn1 from the max-pool backward kernel), the first-step loss is unchanged, gradients agree with the
     two-kernel path to the run-to-run noise of the fp32 atomics, and training still makes progress."""
     import horizonml_b200.models.resnet as R
     from horizonml_b200 import ops
@@ -212,8 +212,30 @@ def test_resnet18_step_with_bn_sums_in_dgrad():
     finally:
         R._BN_BWD_IN_DGRAD = False
         ops.set_backend("torch")
-    assert res[False][1] == 40 and res[True][1] == 25, (res[False][1], res[True][1])
+    assert res[False][1] == 40 and res[True][1] == 24, (res[False][1], res[True][1])    # 15 dgrad hand-offs + the pool's
     l0, l1 = res[("loss", False)], res[("loss", True)]
     assert abs(l0[0] - l1[0]) < 1e-3 and all(v == v for v in l1) and l1[-1] < l1[0], (l0, l1)   # (loss: fp32 atomics)
     cos = torch.nn.functional.cosine_similarity(res[False][0].flatten(), res[True][0].flatten(), dim=0).item()
     assert cos > 0.9, cos
+
+
+@pytest.mark.parametrize("relu", [1, 0])
+def test_maxpool_backward_with_bn_sums(relu):
+    """maxpool_bwd_bn == max-pool backward (bit-identical dx) + the sums the reduction kernel would produce."""
+    from horizonml_b200.ops import native_backend as nb
+    g = torch.Generator().manual_seed(4)
+    x = cl(torch.randn(64, 64, 16, 16, generator=g).to(DEV).bfloat16())                 # = the stem's BN output
+    y_raw = cl(torch.randn(64, 64, 16, 16, generator=g).to(DEV).bfloat16())
+    mean, invstd = torch.randn(64, generator=g).to(DEV) * 0.1, (torch.rand(64, generator=g) + 0.5).to(DEV)
+    y, aux = nb.maxpool_fwd(x, True)
+    dy = cl(torch.randn(64, 64, 8, 8, generator=g).to(DEV).bfloat16())
+    nb.step_begin(DEV)
+    got = nb.maxpool_bwd_bn(dy, aux, x, y_raw, mean, invstd, relu)
+    nb.step_end()
+    assert got is not None
+    dx, sums = got
+    assert torch.equal(dx, nb.maxpool_bwd(dy, aux))
+    gg = dx.float() * ((x > 0).float() if relu else 1.0)
+    xhat = (y_raw.float() - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+    ref = torch.stack([gg.sum(dim=(0, 2, 3)), (gg * xhat).sum(dim=(0, 2, 3))])
+    assert rel_err(sums.view(2, -1), ref) < 1e-3
