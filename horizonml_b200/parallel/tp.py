@@ -30,6 +30,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from .. import ops
+from ..models import resnet as _resnet
 from ..models.resnet import BNP, BasicBlock, ConvW, ResNet18, _cba
 from ..ops.functional import grad_target, grad_written
 
@@ -389,12 +390,15 @@ class TPBasicBlock(nn.Module):
             res_link = None
         c1, b1, c2, b2 = self.conv1, self.bn1, self.conv2, self.bn2
         fwd2, dg1 = self._fused_ops(x)
+        # conv2 is row-parallel: its dgrad is a plain local kernel whose output (the local channel shard) is exactly bn1's
+        # upstream gradient — with HZ_BN_BWD_IN_DGRAD it also takes bn1's backward sums (ops.BNBackLink, models/resnet.py)
+        bl = ops.BNBackLink() if (_resnet._BN_BWD_IN_DGRAD and t and torch.is_grad_enabled()) else None
         y = ops.conv_bn_act(x, c1.weight, b1.weight, b1.bias, b1.running_mean, b1.running_var,
                             stride=c1.stride, pad=1, relu=True, training=t,
-                            post_dgrad=self.comm.all_reduce_sum, dgrad_fn=dg1, in_link=link)
+                            post_dgrad=self.comm.all_reduce_sum, dgrad_fn=dg1, in_link=link, bn_dst=bl)
         return ops.conv_bn_act(y, c2.weight, b2.weight, b2.bias, b2.running_mean, b2.running_var,
                                stride=1, pad=1, relu=True, residual=idt, training=t,
-                               post_conv=self.comm.all_reduce_sum, conv_fn=fwd2, res_link=res_link)
+                               post_conv=self.comm.all_reduce_sum, conv_fn=fwd2, res_link=res_link, bn_src=bl)
 
 
 class TensorParallelResNet(nn.Module):

@@ -44,6 +44,9 @@ def run(fn, world, port, out_dir):
 def _entry(fn, rank, world, port, out_dir):
     try:
         _init(rank, world, port)
+        if os.environ.get("HZ_BN_BWD_IN_DGRAD") == "1":       # the flag is read at import: make sure the workers have it
+            import horizonml_b200.models.resnet as _R
+            assert _R._BN_BWD_IN_DGRAD
         globals()[fn](rank, world, out_dir)
         dist.barrier()
         dist.destroy_process_group()

@@ -34,6 +34,16 @@ def test_pp_1f1b_equivalence_gloo(tmp_path):
     run("pp_equivalence", 3, find_free_port(), str(tmp_path))
 
 
+def test_equivalences_hold_with_bn_backward_sums_hand_off(tmp_path, monkeypatch):
+    """HZ_BN_BWD_IN_DGRAD=1 (BatchNorm-backward sums handed over by the consuming dgrad / max-pool backward,
+    ops.BNBackLink) must not change any strategy's gradients: pipeline micro-batches (links per micro-batch, stage
+    boundaries without a producer) and tensor-parallel blocks (bn1 <- the row-parallel conv2's local dgrad) against the
+    same dense references as above, on the PyTorch-op oracle of the fused kernels."""
+    monkeypatch.setenv("HZ_BN_BWD_IN_DGRAD", "1")          # read at import by the spawned workers
+    run("pp_equivalence", 3, find_free_port(), str(tmp_path))
+    run("tp_equivalence", 2, find_free_port(), str(tmp_path))
+
+
 def test_hybrid_dp_pp_mesh_equivalence_gloo(tmp_path):
     run("hybrid_dp_pp_equivalence", 4, find_free_port(), str(tmp_path))
 
