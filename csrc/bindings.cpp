@@ -374,7 +374,7 @@ std::vector<Tensor> conv_bn_act_fwd(const Tensor& x, const Tensor& w, int64_t st
 std::vector<Tensor> conv_dgrad_bnbwd(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride,
                                      int64_t pad, c10::optional<Tensor> addend, bool weights_stable,
                                      c10::optional<Tensor> bn_out, const Tensor& bn_yraw, const Tensor& bn_mean,
-                                     const Tensor& bn_invstd, c10::optional<Tensor> sums_pre) {
+                                     const Tensor& bn_invstd, c10::optional<Tensor> sums_pre, bool cap6) {
   check_cl(dy, "dy"); check_cl(w, "w"); check_cl(bn_yraw, "bn_yraw");
   c10::cuda::CUDAGuard g(dy.device());
   const int N = (int)x_shape[0], Cin = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
@@ -399,6 +399,7 @@ std::vector<Tensor> conv_dgrad_bnbwd(const Tensor& dy, const Tensor& w, std::vec
   HzBnBwd b;
   b.out = bo; b.yraw = bn_yraw.data_ptr(); b.mean = bn_mean.data_ptr<float>(); b.invstd = bn_invstd.data_ptr<float>();
   b.sums = sums.data_ptr<float>(); b.sums_is_zero = pre ? 1 : 0;
+  b.cap6 = cap6 ? 1 : 0;
   int rc = hz_conv_dgrad_bnbwd(cptr(dy), cptr(w), dx.data_ptr(), add, N, H, W, Cin, (int)w.size(0), (int)w.size(2),
                                (int)stride, (int)pad, weights_stable ? 1 : 0, &b, cur_stream());
   TORCH_CHECK(rc == 0, "hz_conv_dgrad_bnbwd failed rc=", rc);

@@ -68,6 +68,7 @@ struct IgemmParams {
   const __nv_bfloat16* bnb_out;  // the producing layer's BN output (ReLU mask), same layout as `out`; null = no ReLU
   const __nv_bfloat16* bnb_yraw; // the producing layer's raw conv output
   const float* bnb_mean; const float* bnb_invstd;     // [ncols]
+  int bnb_cap6;                  // the producing layer's activation is ReLU6: the mask is 0 < out < 6
 };
 
 HZ_DEVINL unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -431,8 +432,13 @@ __global__ void __launch_bounds__(128) igemm_kernel(const __grid_constant__ AMap
         if (p.bnb_out != nullptr) {
           float o[8];
           unpack8(ld8(p.bnb_out + off), o);
+          if (p.bnb_cap6) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+            for (int j = 0; j < 8; ++j) g[j] = (o[j] > 0.f && o[j] < 6.f) ? g[j] : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+          }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) { ssum[j] += g[j]; ssq[j] += g[j] * (y[j] - bmu[j]) * bis[j]; }
@@ -1253,6 +1259,7 @@ int conv_dgrad_impl(const void* dy, const void* w, void* dx, const void* addend,
     p.bnb_out = (const __nv_bfloat16*)bnb->out;
     p.bnb_yraw = (const __nv_bfloat16*)bnb->yraw;
     p.bnb_mean = bnb->mean; p.bnb_invstd = bnb->invstd;
+    p.bnb_cap6 = bnb->cap6;
   }
   if (bnb == nullptr && use_persistent(t.tiles * ((Cin + BLOCK_N - 1) / BLOCK_N) * p.num_classes))
     return persist_wide(Cin) ? launch_persistent_n<128, true>(am, bm, p, t.tiles, st)      // same 64 x 64 weight boxes,

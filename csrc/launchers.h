@@ -78,6 +78,7 @@ struct HzBnBwd {
   const float* mean; const float* invstd;
   float* sums;
   int sums_is_zero;
+  int cap6;                      // the producing layer's activation is ReLU6 (mask 0 < out < 6) instead of ReLU
 };
 int hz_conv_dgrad_bnbwd(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout,
                         int R, int stride, int pad, int weights_stable, const struct HzBnBwd* bnb, cudaStream_t st);

@@ -29,6 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from . import resnet as _resnet
 from .resnet import BNP, ConvW, _FUSE_RESADD
 
 # (expand ratio t, output channels c, repeats n, stride s) — torchvision.models.mobilenetv2
@@ -46,17 +47,18 @@ class DWConvW(nn.Module):
         self.stride, self.c = stride, c
 
 
-def _pw(x, conv: ConvW, bn: BNP, relu6: bool, residual=None, training=True, in_link=None, res_link=None):
+def _pw(x, conv: ConvW, bn: BNP, relu6: bool, residual=None, training=True, in_link=None, res_link=None,
+        bn_src=None, bn_dst=None):
     """1×1 conv → BN → [+residual] → [ReLU6] on the fused op (native tcgen05 path on GPUs)."""
     return ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, stride=1, pad=0,
                            relu=2 if relu6 else 0, residual=residual, momentum=bn.momentum, eps=bn.eps,
-                           training=training, in_link=in_link, res_link=res_link)
+                           training=training, in_link=in_link, res_link=res_link, bn_src=bn_src, bn_dst=bn_dst)
 
 
-def _dw(x, conv: nn.Module, bn: BNP, training=True):
+def _dw(x, conv: nn.Module, bn: BNP, training=True, bn_dst=None):
     """depthwise 3×3 conv → BN → ReLU6 (csrc/depthwise.cu + the generic bn_act kernels on GPUs)."""
     return ops.dwconv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, stride=conv.stride,
-                             act=2, momentum=bn.momentum, eps=bn.eps, training=training)
+                             act=2, momentum=bn.momentum, eps=bn.eps, training=training, bn_dst=bn_dst)
 
 
 def _stem(x, conv: nn.Module, bn: BNP, training=True):
@@ -94,12 +96,23 @@ class InvertedResidual(nn.Module):
         # expand conv's dgrad epilogue (ops.GradLink, as in ResNet's BasicBlock) instead of by an accumulation kernel
         link = (ops.GradLink(2) if (_FUSE_RESADD and self.use_res and self.expand and t and torch.is_grad_enabled()
                                     and x.requires_grad) else None)
+        # BatchNorm-backward sums handed over by the consuming 1×1 conv's dgrad kernel (ops.BNBackLink, HZ_BN_BWD_IN_DGRAD):
+        #   the depthwise BN  <- the project conv (its only consumer);
+        #   the previous block's project BN <- this block's expand conv, which sees the complete gradient of x either as
+        #   x's only consumer (no skip connection) or by folding the skip share in through `link`
+        fuse = _resnet._BN_BWD_IN_DGRAD and t and torch.is_grad_enabled()
+        prev = getattr(x, "_hz_bn_back", None) if (fuse and self.expand and (not self.use_res or link is not None)) else None
+        mid = ops.BNBackLink() if fuse else None
+        nxt = ops.BNBackLink() if fuse else None
         if self.expand:
-            y = _pw(y, self.conv[0][0], self.conv[0][1], True, training=t, in_link=link)
+            y = _pw(y, self.conv[0][0], self.conv[0][1], True, training=t, in_link=link, bn_src=prev)
             i = 1
-        y = _dw(y, self.conv[i][0], self.conv[i][1], t)
-        return _pw(y, self.conv[i + 1], self.conv[i + 2], False, residual=x if self.use_res else None, training=t,
-                   res_link=link)
+        y = _dw(y, self.conv[i][0], self.conv[i][1], t, bn_dst=mid)
+        out = _pw(y, self.conv[i + 1], self.conv[i + 2], False, residual=x if self.use_res else None, training=t,
+                  res_link=link, bn_src=mid, bn_dst=nxt)
+        if nxt is not None:
+            out._hz_bn_back = nxt
+        return out
 
 
 class _StemConv(nn.Module):
@@ -137,7 +150,8 @@ class MobileNetV2(nn.Module):
         y = _stem(x, self.features[0][0], self.features[0][1], t)
         for blk in list(self.features)[1:-1]:
             y = blk(y)
-        return _pw(y, self.features[-1][0], self.features[-1][1], True, training=t)
+        prev = getattr(y, "_hz_bn_back", None) if (_resnet._BN_BWD_IN_DGRAD and t and torch.is_grad_enabled()) else None
+        return _pw(y, self.features[-1][0], self.features[-1][1], True, training=t, bn_src=prev)
 
     def _pooled(self, x):
         fm = self.feature_map(x)

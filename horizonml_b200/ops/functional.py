@@ -312,7 +312,7 @@ class _DWConvBNAct(torch.autograd.Function):
     weight gradient written in place into ``weight.main_grad`` (the flat bucket), reducer hooks fired per parameter."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, rmean, rvar, stride, act, momentum, eps, training):
+    def forward(ctx, x, weight, gamma, beta, rmean, rvar, stride, act, momentum, eps, training, bn_dst=None):
         be = _be(x)
         w = compute_weight(weight, x.dtype)
         y_raw, sums = be.dwconv_fwd(x, w, stride, training)
@@ -322,6 +322,10 @@ class _DWConvBNAct(torch.autograd.Function):
         ctx.params = (weight, gamma, beta)
         ctx.cfg = (stride, act, training)
         ctx.x_needs_grad = x.requires_grad
+        ctx.bn_dst = bn_dst
+        if bn_dst is not None:             # the consuming 1×1 conv's dgrad may take this BN's backward sums (BNBackLink)
+            bn_dst.out, bn_dst.y_raw, bn_dst.mean, bn_dst.invstd, bn_dst.act = out, y_raw, mean, invstd, int(act)
+            bn_dst.sums = None
         return out
 
     @staticmethod
@@ -335,18 +339,27 @@ class _DWConvBNAct(torch.autograd.Function):
         dout = dout.contiguous(memory_format=torch.channels_last)
         tg, ag = grad_target(gamma)
         tb, ab = grad_target(beta)
-        dy, _, _, _ = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), act, False,
-                                    _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab))
+        pre_sums = None
+        if ctx.bn_dst is not None:
+            pre_sums = ctx.bn_dst.sums
+            ctx.bn_dst.clear()
+        if pre_sums is not None:
+            dy, _, _, _ = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), act, False,
+                                        _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab), sums=pre_sums)
+        else:
+            dy, _, _, _ = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), act, False,
+                                        _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab))
         grad_written(gamma)
         grad_written(beta)
         dx = be.dwconv_dgrad(dy, compute_weight(weight, x.dtype), x.shape, stride) if ctx.x_needs_grad else None
         tgt, acc = grad_target(weight)
         be.dwconv_wgrad(dy, x, stride, tgt, acc, bool(getattr(weight, "_zeroed", False)))
         grad_written(weight)
-        return (dx,) + (None,) * 10
+        return (dx,) + (None,) * 11
 
 
-def dwconv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, act=2, momentum=0.1, eps=1e-5, training=True):
+def dwconv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, act=2, momentum=0.1, eps=1e-5, training=True,
+                  bn_dst=None):
     """Depthwise 3×3 conv (``weight`` [C,1,3,3], pad 1) → BatchNorm → activation (0 none | 1 ReLU | 2 ReLU6)."""
     if not training or not torch.is_grad_enabled():
         be = _be(x)
@@ -354,7 +367,7 @@ def dwconv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, act=2, momentum
         out, _, _ = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar, momentum, eps, None, act,
                                   training)
         return out
-    return _DWConvBNAct.apply(x, weight, gamma, beta, rmean, rvar, int(stride), int(act), momentum, eps, training)
+    return _DWConvBNAct.apply(x, weight, gamma, beta, rmean, rvar, int(stride), int(act), momentum, eps, training, bn_dst)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -247,10 +247,10 @@ def conv_dgrad(dy, w, x_shape, stride: int, pad: int, addend=None):
 
 def conv_dgrad_bnbwd(dy, w, x_shape, stride: int, pad: int, addend, bn_out, bn_yraw, bn_mean, bn_invstd, relu):
     """conv_dgrad whose epilogue also takes the BatchNorm-backward sums of the layer that produced the conv's input
-    (``bn_out`` / ``bn_yraw`` / statistics of that layer; ``relu`` its activation: only none / ReLU are fused).
+    (``bn_out`` / ``bn_yraw`` / statistics of that layer; ``relu`` its activation code: 0 none, 1 ReLU, 2 ReLU6).
     Returns (dx, sums[2, Cin]) or None when the fused form does not apply (caller runs the plain dgrad)."""
     if not (_bf16_cl(dy) and w.dtype == torch.bfloat16 and _conv_ok(tuple(x_shape), w.shape, stride, pad)
-            and int(relu) in (0, 1) and _bf16_cl(bn_yraw) and tuple(bn_yraw.shape) == tuple(x_shape)
+            and int(relu) in (0, 1, 2) and _bf16_cl(bn_yraw) and tuple(bn_yraw.shape) == tuple(x_shape)
             and C.channel_ok(x_shape[1]) and bn_mean.dtype == torch.float32 and bn_invstd.dtype == torch.float32):
         return None
     if addend is not None and not (_bf16_cl(addend) and tuple(addend.shape) == tuple(x_shape)):
@@ -258,7 +258,7 @@ def conv_dgrad_bnbwd(dy, w, x_shape, stride: int, pad: int, addend, bn_out, bn_y
     LAUNCHES["conv_dgrad"] += 1
     pre = ARENA.take(2, x_shape[1], dy.device)
     dx, sums = C.conv_dgrad_bnbwd(dy, w, list(x_shape), stride, pad, addend, _stable(w), bn_out if int(relu) else None,
-                                  bn_yraw, bn_mean, bn_invstd, pre)
+                                  bn_yraw, bn_mean, bn_invstd, pre, int(relu) == 2)
     return dx, sums
 
 

@@ -111,13 +111,13 @@ def conv_dgrad_bnbwd(dy, w, x_shape, stride: int, pad: int, addend, bn_out, bn_y
     """Oracle of the native dgrad-with-BN-backward-sums kernel: (dx, [Σg, Σg·x̂]) with g = dx·[bn_out > 0] and
     x̂ = (bn_yraw − mean)·invstd, the sums taken from dx rounded to its storage dtype (what the separate reduction pass
     would read back)."""
-    if int(relu) not in (0, 1):
+    if int(relu) not in (0, 1, 2):
         return None
     dx = conv_dgrad(dy, w, x_shape, stride, pad, addend)
     C = x_shape[1]
     g = dx.float()
     if int(relu):
-        g = g * (bn_out > 0).to(g.dtype)
+        g = g * ((bn_out > 0) if int(relu) == 1 else ((bn_out > 0) & (bn_out < 6))).to(g.dtype)
     xhat = (bn_yraw.float() - bn_mean.view(1, C, 1, 1)) * bn_invstd.view(1, C, 1, 1)
     return dx, torch.stack([g.sum(dim=(0, 2, 3)), (g * xhat).sum(dim=(0, 2, 3))])
 

@@ -90,7 +90,7 @@ def test_native_binding_signatures_for_mobilenet_ops():
         "bn_act_bwd": lambda: C.bn_act_bwd(x, x, x, f, f, f, 2, False, f, f, False, False, None, False),
         "bn_act_bwd(sums)": lambda: C.bn_act_bwd(x, x, x, f, f, f, 1, False, f, f, False, False, torch.zeros(2, 16), True),
         "conv_dgrad_bnbwd": lambda: C.conv_dgrad_bnbwd(x, torch.zeros(16, 16, 3, 3, dtype=torch.bfloat16).contiguous(
-            memory_format=torch.channels_last), [2, 16, 4, 4], 1, 1, None, False, x, x, f, f, None),
+            memory_format=torch.channels_last), [2, 16, 4, 4], 1, 1, None, False, x, x, f, f, None, False),
     }
     for name, fn in calls.items():
         with pytest.raises(RuntimeError, match="CUDA tensor"):
@@ -98,3 +98,37 @@ def test_native_binding_signatures_for_mobilenet_ops():
     assert C.dwconv_ok(64, 16, 16, 96, 2) and not C.dwconv_ok(64, 16, 16, 12, 1) and not C.dwconv_ok(64, 16, 16, 16, 3)
     # 1: default BatchNorm instantiation (C/8 a power of two), 2: generic one, 0: not a multiple of 8
     assert [C.channel_ok(c) for c in (64, 24, 1280, 12)] == [1, 2, 2, 0]
+
+
+def test_mobilenet_bn_backward_sums_hand_off_matches_plain_backward():
+    """HZ_BN_BWD_IN_DGRAD on MobileNetV2 (PyTorch-op oracle of the fused dgrad): every depthwise BN gets its backward sums
+    from the project conv's dgrad, every project BN from the next expand conv's (or the head conv's) dgrad — 17 + 17
+    hand-offs, ReLU6 masks and skip connections included — and loss / gradients do not change."""
+    import horizonml_b200.models.resnet as R
+    from horizonml_b200 import ops
+    from horizonml_b200.models.mobilenet import mobilenet_v2
+    from horizonml_b200.ops import torch_backend as tb
+    ops.set_backend("torch")
+    calls = {"n": 0}
+    orig = tb.conv_dgrad_bnbwd
+
+    def counted(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+    tb.conv_dgrad_bnbwd = counted
+    try:
+        xb = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(4)).contiguous(memory_format=torch.channels_last)
+        yb = torch.randint(0, 10, (8,), generator=torch.Generator().manual_seed(5))
+        res = []
+        for flag in (False, True):
+            R._BN_BWD_IN_DGRAD = flag
+            model = mobilenet_v2(10, seed=0, dropout=0.0).train()
+            loss, _ = model.forward_loss(xb, yb)
+            loss.backward()
+            res.append([loss.detach()] + [p.grad for p in model.parameters()])
+        for a, b in zip(*res):
+            assert torch.allclose(a, b, atol=5e-5, rtol=1e-3), (a - b).abs().max()
+        assert calls["n"] == 34, calls
+    finally:
+        tb.conv_dgrad_bnbwd = orig
+        R._BN_BWD_IN_DGRAD = False

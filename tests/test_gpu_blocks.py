@@ -113,7 +113,7 @@ DGRAD_SHAPES = [  # N, Cin, H, W, Cout, R, stride, pad
 
 
 @pytest.mark.parametrize("cfg", DGRAD_SHAPES)
-@pytest.mark.parametrize("relu,with_addend", [(1, False), (0, False), (1, True)])
+@pytest.mark.parametrize("relu,with_addend", [(1, False), (0, False), (1, True), (2, False)])
 def test_dgrad_with_bn_backward_sums(cfg, relu, with_addend):
     """conv_dgrad_bnbwd == plain dgrad (bit-identical dx) + the sums the separate channel-reduce kernel would produce."""
     from horizonml_b200.ops import native_backend as nb
@@ -126,7 +126,7 @@ def test_dgrad_with_bn_backward_sums(cfg, relu, with_addend):
     add = cl((torch.randn(N, Cin, H, W, generator=g) * 0.5).to(DEV).bfloat16()) if with_addend else None
     y_raw = cl(torch.randn(N, Cin, H, W, generator=g).to(DEV).bfloat16())            # the producing layer's tensors
     mean, invstd = torch.randn(Cin, generator=g).to(DEV) * 0.1, (torch.rand(Cin, generator=g) + 0.5).to(DEV)
-    out = cl(torch.randn(N, Cin, H, W, generator=g).to(DEV).bfloat16())               # ~half of it <= 0: the ReLU mask
+    out = cl((torch.randn(N, Cin, H, W, generator=g) * 4).to(DEV).bfloat16())         # ~half <= 0, ~7 % >= 6: both masks
     nb.step_begin(DEV)
     got = nb.conv_dgrad_bnbwd(dy, w, (N, Cin, H, W), s, p, add, out, y_raw, mean, invstd, relu)
     assert got is not None
@@ -135,7 +135,8 @@ def test_dgrad_with_bn_backward_sums(cfg, relu, with_addend):
     nb.step_end()
     assert torch.equal(dx, dx0)
     # reference sums from the stored bf16 dx, exactly what bn_act_bwd's reduction kernel computes
-    gg = dx.float() * ((out > 0).float() if relu else 1.0)
+    mask = 1.0 if relu == 0 else ((out > 0).float() if relu == 1 else ((out > 0) & (out < 6)).float())
+    gg = dx.float() * mask
     xhat = (y_raw.float() - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
     ref = torch.stack([gg.sum(dim=(0, 2, 3)), (gg * xhat).sum(dim=(0, 2, 3))])
     assert rel_err(sums.view(2, -1), ref) < 1e-3
@@ -239,3 +240,36 @@ def test_maxpool_backward_with_bn_sums(relu):
     xhat = (y_raw.float() - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
     ref = torch.stack([gg.sum(dim=(0, 2, 3)), (gg * xhat).sum(dim=(0, 2, 3))])
     assert rel_err(sums.view(2, -1), ref) < 1e-3
+
+
+@pytest.mark.parametrize("inp,oup,stride,t,hw", [(24, 24, 1, 6, 8), (24, 32, 2, 6, 8), (96, 160, 2, 6, 2)])
+def test_mobilenet_blocks_with_bn_sums_in_dgrad(inp, oup, stride, t, hw):
+    """A stack of two inverted-residual blocks with HZ_BN_BWD_IN_DGRAD on the native backend: the depthwise BatchNorms (ReLU6
+    mask, channel counts that are not powers of two) get their sums from the project convs' dgrad kernels, the first
+    block's project BN from the second block's expand conv (skip share folded in): fewer bn_act_bwd launches, same
+    gradients as the separate reduction kernels."""
+    import horizonml_b200.models.resnet as R
+    from horizonml_b200 import ops
+    from horizonml_b200.models.mobilenet import InvertedResidual
+    from horizonml_b200.ops import native_backend as nb
+    g = torch.Generator().manual_seed(7)
+    x0 = cl(torch.randn(64, inp, hw, hw, generator=g).to(DEV).bfloat16())
+    ho = (hw - 1) // stride + 1
+    dy = cl((torch.randn(64, oup, ho, ho, generator=g) * 0.1).to(DEV).bfloat16())
+    mk = lambda: torch.nn.Sequential(InvertedResidual(inp, oup, stride, t), InvertedResidual(oup, oup, 1, t))     # noqa: E731
+    res, launches = {}, {}
+    try:
+        for flag in (False, True):
+            R._BN_BWD_IN_DGRAD = flag
+            before = nb.LAUNCHES["bn_act_bwd"]
+            res[flag] = _run(mk, x0, dy, "native")
+            launches[flag] = nb.LAUNCHES["bn_act_bwd"] - before
+    finally:
+        R._BN_BWD_IN_DGRAD = False
+        ops.set_backend("torch")
+    assert launches[True] == launches[False] - 3, launches          # 2 depthwise BNs + the first block's project BN
+    (y0, dx0, g0), (y1, dx1, g1) = res[False], res[True]
+    assert rel_err(y1, y0) < 1e-2 and rel_err(dx1, dx0) < 3e-2
+    for n in g0:
+        if g0[n].abs().max().item() > 1e-6:
+            assert rel_err(g1[n], g0[n]) < 3e-2, (n, rel_err(g1[n], g0[n]))
