@@ -6,7 +6,7 @@ measure (or why not) and the test itself only asserts that it produced a report.
 
 * persistent vs one-tile-per-CTA convolution kernel vs cuDNN at batch 4096 (TFLOP/s, fraction of the measured bf16 peak)
 * MobileNetV2 and ResNet-18 training step through the DP engine on one GPU (ms/step, images/s)
-* `bench.py` at batch 64 with and without the BatchNorm-backward sums taken in the dgrad epilogue (HZ_BN_BWD_IN_DGRAD=1)"""
+  each with and without the BatchNorm-backward sums taken in the dgrad / pool-backward kernels (HZ_BN_BWD_IN_DGRAD)"""
 import json
 import os
 import warnings
@@ -61,14 +61,22 @@ def test_round_end_perf_report():
         g = torch.Generator().manual_seed(0)
         xs = torch.randint(0, 256, (64, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
         ys = torch.randint(0, 10, (64,), generator=g).to(DEV)
-        for model, be in (("resnet18", "native"), ("mobilenet", "native"), ("mobilenet", "torch")):
+        import horizonml_b200.models.resnet as R
+        # (model, op backend, BatchNorm-backward sums taken in the dgrad / pool-backward kernels: HZ_BN_BWD_IN_DGRAD)
+        for model, be, hand_off in (("resnet18", "native", False), ("mobilenet", "native", False), ("mobilenet", "torch", False),
+                                    ("resnet18", "native", True), ("mobilenet", "native", True)):     # (least certain last)
             try:
                 ops.set_backend(be)          # "torch": the same engine on PyTorch ops (cuDNN / ATen kernels) for scale
+                R._BN_BWD_IN_DGRAD = hand_off
                 cfg = TrainConfig(strategy="data", world_size=1, batch_size=64, device="cuda", dtype="bf16",
                                   backend=be, model=model, quiet=True)
                 eng = DPEngine(cfg, Runtime(0, 1, torch.device(DEV), torch.bfloat16, be, "none"))
-                for _ in range(6):
+                launches = None
+                for i in range(6):
+                    before = sum(nb.LAUNCHES.values())
                     eng.step(xs, ys)
+                    if i == 1:
+                        launches = sum(nb.LAUNCHES.values()) - before        # (an eager warm-up step: python-side launches)
                 torch.cuda.synchronize()
                 K = 30
                 evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -77,37 +85,18 @@ def test_round_end_perf_report():
                     a.record(); eng.step(xs, ys); b.record()
                 torch.cuda.synchronize()
                 ms = sum(a.elapsed_time(b) for a, b in evs) / K
-                _report("step", {"model": model, "backend": be, "batch": 64, "ms_per_step": round(ms, 4), "images_per_s": round(64 / ms * 1e3),
-                                 "graph": eng._graphed.graph is not None, "fallbacks": dict(nb.FALLBACKS)})
+                _report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "batch": 64,
+                                 "ms_per_step": round(ms, 4), "images_per_s": round(64 / ms * 1e3),
+                                 "launches_per_step": launches, "graph": eng._graphed.graph is not None,
+                                 "fallbacks": dict(nb.FALLBACKS)})
                 eng._graphed.graph = None
                 sections += 1
             except Exception as e:  # noqa: BLE001
-                _report("step", {"model": model, "backend": be, "error": repr(e)[:300]})
+                _report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "error": repr(e)[:300]})
+            finally:
+                R._BN_BWD_IN_DGRAD = False
     finally:
         ops.set_backend("torch")
-    # ---- the public benchmark at a throughput-bound batch size, one-tile-per-CTA kernels vs persistent kernels
-    import subprocess
-    import sys
-    torch.cuda.empty_cache()
-    variants = (("b64_default", 64, 100, {}),
-                ("b64_bn_backward_sums_in_dgrad", 64, 100, {"HZ_BN_BWD_IN_DGRAD": "1"}))     # 8 reduction kernels less per step
-    #      # (tools/late_suite.sh adds the batch-512 pair: latency vs persistent kernels)
-    for tag, batch, steps, env_extra in variants:
-        try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--batch", str(batch), "--steps",
-                                str(steps), "--warmup", "10"], cwd=ROOT, env=dict(os.environ, **env_extra), capture_output=True,
-                               text=True, timeout=120)
-            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{") and '"metric"' in ln]
-            if line:
-                d = json.loads(line[-1])
-                _report("bench", {"variant": tag, "images_per_s": d["value"], "ms_per_step": d["ms_per_step"],
-                                  "launches_per_step": d.get("launches_per_step"),
-                                  "fallbacks": d.get("native_fallbacks"), "cuda_graph": d["config"].get("cuda_graph")})
-                sections += 1
-            else:
-                _report("bench", {"variant": tag, "error": (r.stderr or r.stdout)[-300:]})
-        except Exception as e:  # noqa: BLE001
-            _report("bench", {"variant": tag, "error": repr(e)[:200]})
     # ---- convolution kernels at batch 4096 (last: the persistent kernel is the least certain code of the tier —
     #      if it traps, everything above has already been reported)
     try:
