@@ -220,6 +220,37 @@ Tensor dwconv_dgrad(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_sh
   return dx;
 }
 
+// depthwise dgrad + the BatchNorm-backward sums of the layer that produced the conv's input: {dx, sums[2,C]}
+std::vector<Tensor> dwconv_dgrad_bnbwd(const Tensor& dy, const Tensor& w, std::vector<int64_t> x_shape, int64_t stride,
+                                       c10::optional<Tensor> bn_out, const Tensor& bn_yraw, const Tensor& bn_mean,
+                                       const Tensor& bn_invstd, c10::optional<Tensor> sums_pre, bool cap6) {
+  check_cl(dy, "dy"); check_cl(bn_yraw, "bn_yraw");
+  c10::cuda::CUDAGuard g(dy.device());
+  const int N = (int)x_shape[0], Cc = (int)x_shape[1], H = (int)x_shape[2], W = (int)x_shape[3];
+  check_dw_weight(w, Cc);
+  TORCH_CHECK(hz_dwconv_ok(N, H, W, Cc, (int)stride), "dwconv_dgrad_bnbwd: unsupported shape");
+  TORCH_CHECK(dy.size(0) == N && dy.size(1) == Cc && dy.size(2) == (H - 1) / stride + 1 && dy.size(3) == (W - 1) / stride + 1,
+              "dwconv_dgrad_bnbwd: dy does not match x_shape / stride");
+  Tensor dx = empty_cl(dy, N, Cc, H, W);
+  TORCH_CHECK(bn_yraw.sizes() == dx.sizes() && bn_mean.numel() == Cc && bn_invstd.numel() == Cc &&
+              bn_mean.scalar_type() == at::kFloat && bn_invstd.scalar_type() == at::kFloat, "dwconv_dgrad_bnbwd: BN operand mismatch");
+  const void* bo = nullptr;
+  if (bn_out.has_value() && bn_out->defined()) {
+    check_cl(*bn_out, "bn_out");
+    TORCH_CHECK(bn_out->sizes() == dx.sizes(), "dwconv_dgrad_bnbwd: bn_out shape");
+    bo = bn_out->data_ptr();
+  }
+  const bool pre = sums_pre.has_value() && sums_pre->defined();
+  Tensor sums = pre ? *sums_pre : at::empty({2, Cc}, dy.options().dtype(at::kFloat));
+  TORCH_CHECK(sums.numel() >= 2 * Cc && sums.scalar_type() == at::kFloat && sums.is_contiguous());
+  HzBnBwd b;
+  b.out = bo; b.yraw = bn_yraw.data_ptr(); b.mean = bn_mean.data_ptr<float>(); b.invstd = bn_invstd.data_ptr<float>();
+  b.sums = sums.data_ptr<float>(); b.sums_is_zero = pre ? 1 : 0; b.cap6 = cap6 ? 1 : 0;
+  int rc = hz_dwconv_dgrad_bnbwd(cptr(dy), cptr(w), dx.data_ptr(), N, H, W, Cc, (int)stride, &b, cur_stream());
+  TORCH_CHECK(rc == 0, "hz_dwconv_dgrad_bnbwd failed rc=", rc);
+  return {dx, sums};
+}
+
 // dW (fp32 [C,1,3,3], C*9 contiguous: a view of the flat gradient bucket) written or accumulated in place
 void dwconv_wgrad(const Tensor& dy, const Tensor& x, Tensor dw, int64_t stride, bool accumulate, bool prezeroed) {
   check_cl(dy, "dy"); check_cl(x, "x");
@@ -694,6 +725,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     return hz_dwconv_ok((int)N, (int)H, (int)W, (int)C, (int)stride) != 0; });
   m.def("dwconv_fwd", &dwconv_fwd);
   m.def("dwconv_dgrad", &dwconv_dgrad);
+  m.def("dwconv_dgrad_bnbwd", &dwconv_dgrad_bnbwd);
   m.def("dwconv_wgrad", &dwconv_wgrad);
   m.def("conv_set_debug", [](c10::optional<Tensor> buf) {
     if (buf.has_value() && buf->defined()) {

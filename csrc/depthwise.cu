@@ -59,21 +59,69 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const __nv_bfloat16* __
   }
 }
 
+// the producing layer's BatchNorm (the expand conv's, whose only consumer is this depthwise conv): its backward sums
+// (sum g, sum g*xhat), g = dx * mask(out), are taken from the registers that store dx (see conv_gemm.cu kBnBwd)
+struct DwBnBwd {
+  const __nv_bfloat16* out;      // BN output (activation mask); null = no activation
+  const __nv_bfloat16* yraw;
+  const float* mean; const float* invstd;
+  float* sums;                   // [2C], pre-zeroed
+  int cap6;                      // ReLU6 mask (0 < out < 6) instead of ReLU
+};
+
 // dx = dwconv_transposed(dy, w)
+template <bool kBn>
 __global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const __nv_bfloat16* __restrict__ dy,
                                                            const __nv_bfloat16* __restrict__ w,
-                                                           __nv_bfloat16* __restrict__ dx, const Geo g) {
+                                                           __nv_bfloat16* __restrict__ dx, const Geo g, const DwBnBwd b) {
   pdl_launch();
   pdl_wait();
+  extern __shared__ float red[];                 // kBn: [rlanes][nvec][16]
   const Lane l = dw::make_lane(threadIdx.x, g.C);
   const int Q = g.N * g.H * g.W;
-  if (!l.active) return;
-  float wr[9][8];
-  dw::load_taps(w, l.cv, wr);
-  for (int p = blockIdx.x * l.rlanes + l.rl; p < Q; p += gridDim.x * l.rlanes) {
-    float acc[8];
-    dw::dgrad_pixel(g, dy, p, l.cv, wr, acc);
-    dw::store8(dx + (size_t)p * g.C + l.cv * 8, acc);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (l.active) {
+    float wr[9][8];
+    dw::load_taps(w, l.cv, wr);
+    float mu[8], is[8];
+    if (kBn) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mu[i] = b.mean[l.cv * 8 + i]; is[i] = b.invstd[l.cv * 8 + i]; }
+    }
+    for (int p = blockIdx.x * l.rlanes + l.rl; p < Q; p += gridDim.x * l.rlanes) {
+      float acc[8];
+      dw::dgrad_pixel(g, dy, p, l.cv, wr, acc);
+      const size_t off = (size_t)p * g.C + l.cv * 8;
+      dw::store8(dx + off, acc);                   // (acc now holds the bf16-rounded values)
+      if (kBn) {
+        float y[8];
+        dw::load8(b.yraw + off, y);
+        if (b.out != nullptr) {
+          float o[8];
+          dw::load8(b.out + off, o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = (o[i] > 0.f && (!b.cap6 || o[i] < 6.f)) ? acc[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += acc[i]; q[i] += acc[i] * (y[i] - mu[i]) * is[i]; }
+      }
+    }
+  }
+  if (kBn) {
+    if (l.active) {
+      float* mine = red + ((size_t)l.rl * l.nvec + l.cv) * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < l.nvec * 16; o += 256) {
+      const int v = o >> 4, j = o & 15;
+      float t = 0.f;
+      for (int k = 0; k < l.rlanes; ++k) t += red[((size_t)k * l.nvec + v) * 16 + j];
+      atomicAdd(&b.sums[(j >> 3) * g.C + v * 8 + (j & 7)], t);
+    }
   }
 }
 
@@ -155,8 +203,23 @@ int hz_dwconv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W
   if (!hz_dwconv_ok(N, H, W, C, stride)) return -1;
   const hz::dw::Geo g = hz::dw::make_geo(N, H, W, C, stride);
   const int grid = rows_grid(g.N * g.H * g.W, C, 2, 148 * 4);
-  return hz::launch(hz::dwconv_dgrad_kernel, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dy,
-                    (const __nv_bfloat16*)w, (__nv_bfloat16*)dx, g) == cudaSuccess ? 0 : -2;
+  hz::DwBnBwd b{};
+  return hz::launch(hz::dwconv_dgrad_kernel<false>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dy,
+                    (const __nv_bfloat16*)w, (__nv_bfloat16*)dx, g, b) == cudaSuccess ? 0 : -2;
+}
+
+// depthwise dgrad that also takes the BatchNorm-backward sums of the layer producing the conv's input (struct HzBnBwd)
+int hz_dwconv_dgrad_bnbwd(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int stride,
+                          const struct HzBnBwd* bnb, cudaStream_t st) {
+  if (!hz_dwconv_ok(N, H, W, C, stride) || bnb == nullptr || bnb->sums == nullptr || bnb->yraw == nullptr) return -1;
+  const hz::dw::Geo g = hz::dw::make_geo(N, H, W, C, stride);
+  const int grid = rows_grid(g.N * g.H * g.W, C, 2, 148 * 4);
+  if (!bnb->sums_is_zero) hz::zero_f32(bnb->sums, (size_t)2 * C, st);
+  hz::DwBnBwd b;
+  b.out = (const __nv_bfloat16*)bnb->out; b.yraw = (const __nv_bfloat16*)bnb->yraw;
+  b.mean = bnb->mean; b.invstd = bnb->invstd; b.sums = bnb->sums; b.cap6 = bnb->cap6;
+  return hz::launch(hz::dwconv_dgrad_kernel<true>, dim3(grid), dim3(256), sizeof(float) * 256 * 16, st,
+                    (const __nv_bfloat16*)dy, (const __nv_bfloat16*)w, (__nv_bfloat16*)dx, g, b) == cudaSuccess ? 0 : -2;
 }
 
 // dw: fp32 [C][3][3]; accumulate = add to what is there; otherwise the buffer is cleared first unless `prezeroed`

@@ -82,6 +82,8 @@ struct HzBnBwd {
 };
 int hz_conv_dgrad_bnbwd(const void* dy, const void* w, void* dx, const void* addend, int N, int H, int W, int Cin, int Cout,
                         int R, int stride, int pad, int weights_stable, const struct HzBnBwd* bnb, cudaStream_t st);
+int hz_dwconv_dgrad_bnbwd(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int stride,
+                          const struct HzBnBwd* bnb, cudaStream_t st);      // depthwise.cu
 int hz_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int R,
                   int stride, int pad, int accumulate, int prezeroed, long long ld_out, int n_valid,
                   cudaStream_t st);

@@ -55,10 +55,10 @@ def _pw(x, conv: ConvW, bn: BNP, relu6: bool, residual=None, training=True, in_l
                            training=training, in_link=in_link, res_link=res_link, bn_src=bn_src, bn_dst=bn_dst)
 
 
-def _dw(x, conv: nn.Module, bn: BNP, training=True, bn_dst=None):
+def _dw(x, conv: nn.Module, bn: BNP, training=True, bn_dst=None, bn_src=None):
     """depthwise 3×3 conv → BN → ReLU6 (csrc/depthwise.cu + the generic bn_act kernels on GPUs)."""
     return ops.dwconv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, stride=conv.stride,
-                             act=2, momentum=bn.momentum, eps=bn.eps, training=training, bn_dst=bn_dst)
+                             act=2, momentum=bn.momentum, eps=bn.eps, training=training, bn_dst=bn_dst, bn_src=bn_src)
 
 
 def _stem(x, conv: nn.Module, bn: BNP, training=True):
@@ -97,17 +97,18 @@ class InvertedResidual(nn.Module):
         link = (ops.GradLink(2) if (_FUSE_RESADD and self.use_res and self.expand and t and torch.is_grad_enabled()
                                     and x.requires_grad) else None)
         # BatchNorm-backward sums handed over by the consuming 1×1 conv's dgrad kernel (ops.BNBackLink, HZ_BN_BWD_IN_DGRAD):
-        #   the depthwise BN  <- the project conv (its only consumer);
+        #   the expand BN <- the depthwise conv's dgrad kernel, the depthwise BN <- the project conv (only consumers);
         #   the previous block's project BN <- this block's expand conv, which sees the complete gradient of x either as
         #   x's only consumer (no skip connection) or by folding the skip share in through `link`
         fuse = _resnet._BN_BWD_IN_DGRAD and t and torch.is_grad_enabled()
         prev = getattr(x, "_hz_bn_back", None) if (fuse and self.expand and (not self.use_res or link is not None)) else None
+        exp = ops.BNBackLink() if (fuse and self.expand) else None       # the expand BN <- the depthwise conv's dgrad
         mid = ops.BNBackLink() if fuse else None
         nxt = ops.BNBackLink() if fuse else None
         if self.expand:
-            y = _pw(y, self.conv[0][0], self.conv[0][1], True, training=t, in_link=link, bn_src=prev)
+            y = _pw(y, self.conv[0][0], self.conv[0][1], True, training=t, in_link=link, bn_src=prev, bn_dst=exp)
             i = 1
-        y = _dw(y, self.conv[i][0], self.conv[i][1], t, bn_dst=mid)
+        y = _dw(y, self.conv[i][0], self.conv[i][1], t, bn_dst=mid, bn_src=exp)
         out = _pw(y, self.conv[i + 1], self.conv[i + 2], False, residual=x if self.use_res else None, training=t,
                   res_link=link, bn_src=mid, bn_dst=nxt)
         if nxt is not None:

@@ -312,8 +312,9 @@ class _DWConvBNAct(torch.autograd.Function):
     weight gradient written in place into ``weight.main_grad`` (the flat bucket), reducer hooks fired per parameter."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, rmean, rvar, stride, act, momentum, eps, training, bn_dst=None):
+    def forward(ctx, x, weight, gamma, beta, rmean, rvar, stride, act, momentum, eps, training, bn_dst=None, bn_src=None):
         be = _be(x)
+        ctx.bn_src = bn_src
         w = compute_weight(weight, x.dtype)
         y_raw, sums = be.dwconv_fwd(x, w, stride, training)
         out, mean, invstd = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar, momentum, eps, None,
@@ -351,15 +352,27 @@ class _DWConvBNAct(torch.autograd.Function):
                                         _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab))
         grad_written(gamma)
         grad_written(beta)
-        dx = be.dwconv_dgrad(dy, compute_weight(weight, x.dtype), x.shape, stride) if ctx.x_needs_grad else None
+        dx = None
+        if ctx.x_needs_grad:
+            src = ctx.bn_src
+            fused = None
+            if (src is not None and src.out is not None and src.sums is None and src.single
+                    and hasattr(be, "dwconv_dgrad_bnbwd") and src.out.data_ptr() == x.data_ptr()):
+                # x is the producing layer's BN output and this depthwise conv its only consumer (BNBackLink)
+                fused = be.dwconv_dgrad_bnbwd(dy, compute_weight(weight, x.dtype), x.shape, stride, src.out, src.y_raw,
+                                              src.mean, src.invstd, src.act)
+            if fused is not None:
+                dx, src.sums = fused
+            else:
+                dx = be.dwconv_dgrad(dy, compute_weight(weight, x.dtype), x.shape, stride)
         tgt, acc = grad_target(weight)
         be.dwconv_wgrad(dy, x, stride, tgt, acc, bool(getattr(weight, "_zeroed", False)))
         grad_written(weight)
-        return (dx,) + (None,) * 11
+        return (dx,) + (None,) * 12
 
 
 def dwconv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, act=2, momentum=0.1, eps=1e-5, training=True,
-                  bn_dst=None):
+                  bn_dst=None, bn_src=None):
     """Depthwise 3×3 conv (``weight`` [C,1,3,3], pad 1) → BatchNorm → activation (0 none | 1 ReLU | 2 ReLU6)."""
     if not training or not torch.is_grad_enabled():
         be = _be(x)
@@ -367,7 +380,8 @@ def dwconv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, act=2, momentum
         out, _, _ = be.bn_act_fwd(y_raw, sums, gamma.detach(), beta.detach(), rmean, rvar, momentum, eps, None, act,
                                   training)
         return out
-    return _DWConvBNAct.apply(x, weight, gamma, beta, rmean, rvar, int(stride), int(act), momentum, eps, training, bn_dst)
+    return _DWConvBNAct.apply(x, weight, gamma, beta, rmean, rvar, int(stride), int(act), momentum, eps, training, bn_dst,
+                              bn_src)
 
 
 # ----------------------------------------------------------------------------------------------

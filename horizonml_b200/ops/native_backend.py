@@ -317,6 +317,20 @@ def dwconv_dgrad(dy, w, x_shape, stride: int):
     return _tb.dwconv_dgrad(dy, w, x_shape, stride)
 
 
+def dwconv_dgrad_bnbwd(dy, w, x_shape, stride: int, bn_out, bn_yraw, bn_mean, bn_invstd, relu):
+    """Depthwise dgrad whose kernel also takes the BatchNorm-backward sums of the layer that produced the conv's input
+    (activation code 0 / 1 / 2).  Returns (dx, sums[2, C]) or None when the fused form does not apply."""
+    if not (_bf16_cl(dy) and w.dtype == torch.bfloat16 and _dw_ok(tuple(x_shape), stride) and int(relu) in (0, 1, 2)
+            and _bf16_cl(bn_yraw) and tuple(bn_yraw.shape) == tuple(x_shape) and bn_mean.dtype == torch.float32
+            and bn_invstd.dtype == torch.float32):
+        return None
+    LAUNCHES["dwconv_dgrad"] += 1
+    pre = ARENA.take(2, x_shape[1], dy.device)
+    dx, sums = C.dwconv_dgrad_bnbwd(dy, w, list(x_shape), stride, bn_out if int(relu) else None, bn_yraw, bn_mean,
+                                    bn_invstd, pre, int(relu) == 2)
+    return dx, sums
+
+
 def dwconv_wgrad(dy, x, stride: int, out_grad: torch.Tensor, accumulate: bool, prezeroed: bool = False):
     if (_bf16_cl(dy) and _bf16_cl(x) and _dw_ok(x.shape, stride) and out_grad.is_cuda and out_grad.dtype == torch.float32
             and out_grad.dim() == 4 and out_grad.stride(0) == 9 and out_grad.stride(2) == 3 and out_grad.stride(3) == 1):

@@ -152,6 +152,19 @@ def dwconv_dgrad(dy, w, x_shape, stride: int):
     return _cl(dx)
 
 
+def dwconv_dgrad_bnbwd(dy, w, x_shape, stride: int, bn_out, bn_yraw, bn_mean, bn_invstd, relu):
+    """Oracle of the native depthwise-dgrad-with-BN-backward-sums kernel: (dx, [Σg, Σg·x̂])."""
+    if int(relu) not in (0, 1, 2):
+        return None
+    dx = dwconv_dgrad(dy, w, x_shape, stride)
+    C = x_shape[1]
+    g = dx.float()
+    if int(relu):
+        g = g * ((bn_out > 0) if int(relu) == 1 else ((bn_out > 0) & (bn_out < 6))).to(g.dtype)
+    xhat = (bn_yraw.float() - bn_mean.view(1, C, 1, 1)) * bn_invstd.view(1, C, 1, 1)
+    return dx, torch.stack([g.sum(dim=(0, 2, 3)), (g * xhat).sum(dim=(0, 2, 3))])
+
+
 def dwconv_wgrad(dy, x, stride: int, out_grad: torch.Tensor, accumulate: bool, prezeroed: bool = False):
     c = x.shape[1]
     _, gw, _ = torch.ops.aten.convolution_backward(

@@ -86,6 +86,7 @@ def test_native_binding_signatures_for_mobilenet_ops():
         "dwconv_fwd": lambda: C.dwconv_fwd(x, w, 1, True, None),
         "dwconv_dgrad": lambda: C.dwconv_dgrad(x, w, [2, 16, 4, 4], 1),
         "dwconv_wgrad": lambda: C.dwconv_wgrad(x, x, torch.zeros(16, 1, 3, 3), 1, False, True),
+        "dwconv_dgrad_bnbwd": lambda: C.dwconv_dgrad_bnbwd(x, w, [2, 16, 4, 4], 1, x, x, f, f, None, True),
         "bn_act_fwd": lambda: C.bn_act_fwd(x, torch.zeros(2, 16), f, f, f, f, 0.1, 1e-5, None, 2, True),
         "bn_act_bwd": lambda: C.bn_act_bwd(x, x, x, f, f, f, 2, False, f, f, False, False, None, False),
         "bn_act_bwd(sums)": lambda: C.bn_act_bwd(x, x, x, f, f, f, 1, False, f, f, False, False, torch.zeros(2, 16), True),
@@ -102,8 +103,9 @@ def test_native_binding_signatures_for_mobilenet_ops():
 
 def test_mobilenet_bn_backward_sums_hand_off_matches_plain_backward():
     """HZ_BN_BWD_IN_DGRAD on MobileNetV2 (PyTorch-op oracle of the fused dgrad): every depthwise BN gets its backward sums
-    from the project conv's dgrad, every project BN from the next expand conv's (or the head conv's) dgrad — 17 + 17
-    hand-offs, ReLU6 masks and skip connections included — and loss / gradients do not change."""
+    from the project conv's dgrad, every project BN from the next expand conv's (or the head conv's) dgrad, every expand
+    BN from the depthwise conv's dgrad — 17 + 17 + 16 hand-offs (50 of 52 BatchNorms), ReLU6 masks and skip connections
+    included — and loss / gradients do not change."""
     import horizonml_b200.models.resnet as R
     from horizonml_b200 import ops
     from horizonml_b200.models.mobilenet import mobilenet_v2
@@ -116,6 +118,13 @@ def test_mobilenet_bn_backward_sums_hand_off_matches_plain_backward():
         calls["n"] += 1
         return orig(*a, **k)
     tb.conv_dgrad_bnbwd = counted
+    dw_calls = {"n": 0}
+    orig_dw = tb.dwconv_dgrad_bnbwd
+
+    def counted_dw(*a, **k):
+        dw_calls["n"] += 1
+        return orig_dw(*a, **k)
+    tb.dwconv_dgrad_bnbwd = counted_dw
     try:
         xb = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(4)).contiguous(memory_format=torch.channels_last)
         yb = torch.randint(0, 10, (8,), generator=torch.Generator().manual_seed(5))
@@ -128,7 +137,8 @@ def test_mobilenet_bn_backward_sums_hand_off_matches_plain_backward():
             res.append([loss.detach()] + [p.grad for p in model.parameters()])
         for a, b in zip(*res):
             assert torch.allclose(a, b, atol=5e-5, rtol=1e-3), (a - b).abs().max()
-        assert calls["n"] == 34, calls
+        assert calls["n"] == 34 and dw_calls["n"] == 16, (calls, dw_calls)      # + the 16 expand BNs <- depthwise dgrad
     finally:
         tb.conv_dgrad_bnbwd = orig
+        tb.dwconv_dgrad_bnbwd = orig_dw
         R._BN_BWD_IN_DGRAD = False

@@ -245,9 +245,9 @@ def test_maxpool_backward_with_bn_sums(relu):
 @pytest.mark.parametrize("inp,oup,stride,t,hw", [(24, 24, 1, 6, 8), (24, 32, 2, 6, 8), (96, 160, 2, 6, 2)])
 def test_mobilenet_blocks_with_bn_sums_in_dgrad(inp, oup, stride, t, hw):
     """A stack of two inverted-residual blocks with HZ_BN_BWD_IN_DGRAD on the native backend: the depthwise BatchNorms (ReLU6
-    mask, channel counts that are not powers of two) get their sums from the project convs' dgrad kernels, the first
-    block's project BN from the second block's expand conv (skip share folded in): fewer bn_act_bwd launches, same
-    gradients as the separate reduction kernels."""
+    mask, channel counts that are not powers of two) get their sums from the project convs' dgrad kernels, the expand
+    BatchNorms from the depthwise convs' dgrad kernels, the first block's project BN from the second block's expand conv
+    (skip share folded in): fewer bn_act_bwd launches, same gradients as the separate reduction kernels."""
     import horizonml_b200.models.resnet as R
     from horizonml_b200 import ops
     from horizonml_b200.models.mobilenet import InvertedResidual
@@ -267,9 +267,34 @@ def test_mobilenet_blocks_with_bn_sums_in_dgrad(inp, oup, stride, t, hw):
     finally:
         R._BN_BWD_IN_DGRAD = False
         ops.set_backend("torch")
-    assert launches[True] == launches[False] - 3, launches          # 2 depthwise BNs + the first block's project BN
+    assert launches[True] == launches[False] - 5, launches          # 2 expand BNs + 2 depthwise BNs + the first block's project BN
     (y0, dx0, g0), (y1, dx1, g1) = res[False], res[True]
     assert rel_err(y1, y0) < 1e-2 and rel_err(dx1, dx0) < 3e-2
     for n in g0:
         if g0[n].abs().max().item() > 1e-6:
             assert rel_err(g1[n], g0[n]) < 3e-2, (n, rel_err(g1[n], g0[n]))
+
+
+@pytest.mark.parametrize("N,C,H,stride", [(64, 96, 16, 2), (64, 144, 8, 1), (64, 576, 2, 1), (64, 960, 1, 1), (3, 24, 7, 2)])
+@pytest.mark.parametrize("act", [2, 1, 0])
+def test_depthwise_dgrad_with_bn_backward_sums(N, C, H, stride, act):
+    """dwconv_dgrad_bnbwd == depthwise dgrad (bit-identical dx) + the producing BatchNorm's backward sums (ReLU6 mask)."""
+    from horizonml_b200.ops import native_backend as nb
+    g = torch.Generator().manual_seed(12)
+    w = (torch.randn(C, 1, 3, 3, generator=g) / 3).to(DEV).bfloat16()
+    Ho = (H - 1) // stride + 1
+    dy = cl((torch.randn(N, C, Ho, Ho, generator=g) * 0.5).to(DEV).bfloat16())
+    y_raw = cl(torch.randn(N, C, H, H, generator=g).to(DEV).bfloat16())
+    out = cl((torch.randn(N, C, H, H, generator=g) * 4).to(DEV).bfloat16())
+    mean, invstd = torch.randn(C, generator=g).to(DEV) * 0.1, (torch.rand(C, generator=g) + 0.5).to(DEV)
+    nb.step_begin(DEV)
+    got = nb.dwconv_dgrad_bnbwd(dy, w, (N, C, H, H), stride, out, y_raw, mean, invstd, act)
+    nb.step_end()
+    assert got is not None
+    dx, sums = got
+    assert torch.equal(dx, nb.dwconv_dgrad(dy, w, (N, C, H, H), stride))
+    mask = 1.0 if act == 0 else ((out > 0).float() if act == 1 else ((out > 0) & (out < 6)).float())
+    gg = dx.float() * mask
+    xhat = (y_raw.float() - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+    ref = torch.stack([gg.sum(dim=(0, 2, 3)), (gg * xhat).sum(dim=(0, 2, 3))])
+    assert rel_err(sums.view(2, -1), ref) < 1e-3
