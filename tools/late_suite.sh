@@ -4,9 +4,10 @@
 #   2. the HZPERF report lines (persistent vs latency conv kernel vs cuDNN, MobileNetV2 / ResNet-18 step times,
 #      bench.py --batch 512 with both kernel families)                            -> gpurun_out/hzperf.txt
 #   3. conv roofline with the persistent kernels next to the one-tile-per-CTA kernels -> gpurun_out/conv_roofline_persist.json
+#   4. the HZPERF ncu lines come from tests/test_gpu_ncu_report.py (Nsight Compute over one eager step, per-kernel shares)
 # Usage: gpurun --timeout 900 -- bash tools/late_suite.sh
 mkdir -p gpurun_out
-HZ_LATE_STRICT=1 timeout 700 python -m pytest tests -m "gpu and late and not multigpu" -q -rA -W default 2>&1 | tee gpurun_out/late_tier.log | tail -40
+HZ_LATE_STRICT=1 HZ_LATE_BUDGET_S=3600 timeout 800 python -m pytest tests -m "gpu and late and not multigpu" -q -rA -W default 2>&1 | tee gpurun_out/late_tier.log | tail -40
 grep -h "HZPERF" gpurun_out/late_tier.log | sed 's/.*HZPERF/HZPERF/' | sort -u > gpurun_out/hzperf.txt
 cat gpurun_out/hzperf.txt
 for v in 0 1; do HZ_BN_BWD_IN_DGRAD=$v timeout 120 python bench.py --gpus 1 --steps 200 --warmup 20 2>/dev/null | tail -1 | cut -c1-300 | sed "s/^/b64 HZ_BN_BWD_IN_DGRAD=$v: /"; done | tee -a gpurun_out/hzperf.txt
