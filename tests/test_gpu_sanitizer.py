@@ -45,14 +45,14 @@ def _memcheck(selection: str, files, budget_s: int, exe: str = ""):
 
 
 @pytest.mark.gpu
-@pytest.mark.late(order=5)
+@pytest.mark.late(order=13)
 def test_memcheck_clean_on_elementwise_kernels():
     """BatchNorm forward + backward (reduce, apply), max-pool forward / backward, the classifier head: 75 s box."""
     _memcheck("test_bn_act and 64-16 or test_maxpool or test_head and 1", ["tests/test_gpu_kernels.py"], 75)
 
 
 @pytest.mark.gpu
-@pytest.mark.late(order=10)
+@pytest.mark.late(order=14)
 @pytest.mark.skipif(os.environ.get("HZ_TEST_SANITIZER", "0") != "1", reason="set HZ_TEST_SANITIZER=1 (several minutes)")
 def test_memcheck_clean_on_a_tcgen05_convolution():
     _memcheck("(test_conv_fwd_tcgen05 or test_conv_dgrad or test_conv_wgrad_tcgen05) and cfg0", ["tests/test_gpu_kernels.py"], 600)
