@@ -1,0 +1,144 @@
+"""Device-timed measurements of the code written after round 2's last GPU session, one section per process so that a
+kernel that traps cannot take the other sections' numbers with it.  Every result is printed at once as a line
+``HZPERF <tag> <json>`` (tests/test_gpu_perf_report.py republishes them in the test log, tools/late_suite.sh collects them).
+
+    python tools/perf_probe.py steps      # ResNet-18 / MobileNetV2 training step through the DP engine (native, + PyTorch ops)
+    python tools/perf_probe.py handoff    # the same steps with the BatchNorm-backward sums taken in dgrad / pool-backward kernels
+    python tools/perf_probe.py conv       # batch-4096 convolutions: one-tile-per-CTA kernel, cuDNN, then the persistent kernels
+
+CUDA events after warm-up, synchronised on both sides, a 256 MiB L2-flush write between timed launches."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from horizonml_b200 import ops  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def report(tag, payload):
+    print("HZPERF " + tag + " " + json.dumps(payload), flush=True)
+
+
+def cl(t):
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def timed(fn, flush, iters=8):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / iters * 1e3          # us
+
+
+def steps(variants):
+    import horizonml_b200.models.resnet as R
+    from horizonml_b200.config import TrainConfig
+    from horizonml_b200.ops import native_backend as nb
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.dp import DPEngine
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    g = torch.Generator().manual_seed(0)
+    xs = torch.randint(0, 256, (64, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+    ys = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    for model, be, hand_off in variants:
+        try:
+            ops.set_backend(be)          # "torch": the same engine on PyTorch ops (cuDNN / ATen kernels) for scale
+            R._BN_BWD_IN_DGRAD = hand_off
+            cfg = TrainConfig(strategy="data", world_size=1, batch_size=64, device="cuda", dtype="bf16", backend=be,
+                              model=model, quiet=True)
+            eng = DPEngine(cfg, Runtime(0, 1, torch.device(DEV), torch.bfloat16, be, "none"))
+            launches = None
+            for i in range(6):
+                before = sum(nb.LAUNCHES.values())
+                eng.step(xs, ys)
+                if i == 1:
+                    launches = sum(nb.LAUNCHES.values()) - before        # (an eager warm-up step: python-side launches)
+            torch.cuda.synchronize()
+            K = 30
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            for a, b in evs:
+                flush.fill_(1)
+                a.record(); eng.step(xs, ys); b.record()
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in evs) / K
+            report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "batch": 64, "ms_per_step": round(ms, 4),
+                            "images_per_s": round(64 / ms * 1e3), "launches_per_step": launches,
+                            "graph": eng._graphed.graph is not None, "fallbacks": dict(nb.FALLBACKS)})
+            eng._graphed.graph = None
+        except Exception as e:  # noqa: BLE001
+            report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "error": repr(e)[:300]})
+        finally:
+            R._BN_BWD_IN_DGRAD = False
+
+
+def conv():
+    from horizonml_b200.ops import native_backend as nb
+    from horizonml_b200.ops import torch_backend as tb
+    ops.set_backend("native")
+    peak = 1433.5
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+    except Exception:  # noqa: BLE001
+        pass
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    B = 4096
+    data = []
+    for name, cin, h, cout in (("layer1", 64, 8, 64), ("layer2", 128, 4, 128), ("layer3", 256, 2, 256)):
+        g = torch.Generator().manual_seed(1)
+        x = cl((torch.randn(B, cin, h, h, generator=g) * 0.5).to(DEV).bfloat16())
+        w = cl((torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(DEV).bfloat16())
+        dy = cl((torch.randn(B, cout, h, h, generator=g) * 0.5).to(DEV).bfloat16())
+        data.append((name, x, w, dy, 2.0 * B * h * h * cout * cin * 9))
+
+    def kernels(mode, tag):
+        for name, x, w, dy, flops in data:
+            row = {"layer": name, "batch": B, "kernel": tag, "gflop": round(flops / 1e9, 1)}
+            try:
+                nb.C.conv_set_persist(mode)
+                tf = timed(lambda: nb.conv_fwd(x, w, 1, 1, True), flush)
+                td = timed(lambda: nb.conv_dgrad(dy, w, x.shape, 1, 1), flush)
+                row.update(fwd_us=round(tf, 1), fwd_tflops=round(flops / tf / 1e6, 1), dgrad_us=round(td, 1),
+                           dgrad_tflops=round(flops / td / 1e6, 1), fwd_frac_of_peak=round(flops / tf / 1e6 / peak, 3),
+                           peak_tflops=peak)
+            except Exception as e:  # noqa: BLE001
+                row["error"] = repr(e)[:200]
+            finally:
+                nb.C.conv_set_persist(0)
+            report("conv", row)
+    kernels(0, "one_tile_per_cta")
+    for name, x, w, dy, flops in data:
+        row = {"layer": name, "batch": B, "kernel": "cudnn"}
+        try:
+            tf = timed(lambda: tb.conv_fwd(x, w, 1, 1, False), flush)
+            td = timed(lambda: tb.conv_dgrad(dy, w, x.shape, 1, 1), flush)
+            row.update(fwd_us=round(tf, 1), fwd_tflops=round(flops / tf / 1e6, 1), dgrad_us=round(td, 1),
+                       dgrad_tflops=round(flops / td / 1e6, 1))
+        except Exception as e:  # noqa: BLE001
+            row["error"] = repr(e)[:200]
+        report("conv", row)
+    kernels(2, "persistent_n64")           # (the uncertain kernels last: everything above is already printed)
+    kernels(1, "persistent_wide")
+
+
+if __name__ == "__main__":
+    section = sys.argv[1] if len(sys.argv) > 1 else "steps"
+    if section == "steps":
+        steps([("resnet18", "native", False), ("mobilenet", "native", False), ("mobilenet", "torch", False)])
+    elif section == "handoff":
+        steps([("resnet18", "native", True), ("mobilenet", "native", True)])
+    elif section == "conv":
+        conv()
+    else:
+        raise SystemExit(f"unknown section {section}")
