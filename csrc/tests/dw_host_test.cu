@@ -108,7 +108,17 @@ int main() {
       {5, 2, 2, 576, 2, 1},  {2, 6, 6, 192, 1, 64},
   };
   for (const Case& c : cases) run(c);
+  // random geometries: any batch, odd / even extents, every channel-vector count class (power of two or not), both strides
+  unsigned s = 12345u;
+  auto rnd = [&](int lo, int hi) { s = s * 1664525u + 1013904223u; return lo + (int)((s >> 8) % (unsigned)(hi - lo + 1)); };
+  int n_random = 0;
+  for (int i = 0; i < 60; ++i) {
+    Case c;
+    c.N = rnd(1, 5); c.H = rnd(1, 9); c.W = rnd(1, 9); c.C = 8 * rnd(1, 40); c.stride = rnd(1, 2); c.grid = rnd(1, 9);
+    run(c);
+    ++n_random;
+  }
   if (fails) { fprintf(stderr, "%d check(s) failed\n", fails); return 1; }
-  printf("host depthwise logic ok (%zu cases)\n", sizeof(cases) / sizeof(cases[0]));
+  printf("host depthwise logic ok (%zu cases + %d random)\n", sizeof(cases) / sizeof(cases[0]), n_random);
   return 0;
 }
