@@ -318,3 +318,37 @@ def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
     finally:
         tb.conv_dgrad_bnbwd = orig
         R._BN_BWD_IN_DGRAD = False
+
+
+def test_late_tier_harness(tmp_path):
+    """tests/conftest.py: `late` tests are collected after everything else in ascending `order`, reported as XPASS / XFAIL
+    (so they cannot turn the run red or stop it under -x), become ordinary tests with HZ_LATE_STRICT=1, and are skipped
+    once the session's wall-clock budget is used up."""
+    import shutil
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = tmp_path / "t"
+    d.mkdir()
+    shutil.copy(os.path.join(root, "tests", "conftest.py"), d / "conftest.py")
+    (d / "test_demo.py").write_text(
+        "import time, pytest\n"
+        "@pytest.mark.late(order=5)\ndef test_l5(): assert False\n"
+        "@pytest.mark.late\ndef test_l0(): assert True\n"
+        "def test_plain(): time.sleep(0.3)\n"
+        "@pytest.mark.late(order=2)\ndef test_l2(): assert True\n")
+
+    def run(env_extra, *args):
+        env = dict(os.environ, **env_extra)
+        env.pop("HZ_LATE_STRICT", None) if "HZ_LATE_STRICT" not in env_extra else None
+        return subprocess.run([sys.executable, "-m", "pytest", str(d), "-q", "-x", "-p", "no:cacheprovider", *args], cwd=str(d),
+                              env=env, capture_output=True, text=True, timeout=120)
+    r = run({}, "--collect-only")
+    order = [ln.split("::")[1].strip() for ln in r.stdout.splitlines() if "::test_" in ln]
+    assert order == ["test_plain", "test_l0", "test_l2", "test_l5"], r.stdout
+    r = run({})
+    assert r.returncode == 0 and "1 passed" in r.stdout and "2 xpassed" in r.stdout and "1 xfailed" in r.stdout, r.stdout
+    r = run({"HZ_LATE_STRICT": "1"})
+    assert r.returncode != 0 and "1 failed" in r.stdout and "3 passed" in r.stdout, r.stdout
+    r = run({"HZ_LATE_BUDGET_S": "0.1"})
+    assert r.returncode == 0 and "1 passed" in r.stdout and "3 skipped" in r.stdout, r.stdout
