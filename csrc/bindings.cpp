@@ -93,6 +93,33 @@ std::vector<Tensor> bn_act_bwd(const Tensor& dout, const Tensor& out, const Tens
   return {dy, dres};
 }
 
+// bn_act_bwd of a layer with a residual branch that ends in a BatchNorm without activation: {dy, dres, res_sums[2,C]}
+std::vector<Tensor> bn_act_bwd_res(const Tensor& dout, const Tensor& out, const Tensor& yraw, const Tensor& mean,
+                                   const Tensor& invstd, const Tensor& gamma, int64_t relu, Tensor dgamma, Tensor dbeta,
+                                   bool acc_gamma, bool acc_beta, c10::optional<Tensor> zeroed_scratch, bool sums_ready,
+                                   const Tensor& res_yraw, const Tensor& res_mean, const Tensor& res_invstd,
+                                   c10::optional<Tensor> res_sums_pre) {
+  check_cl(dout, "dout"); check_cl(yraw, "yraw"); check_cl(res_yraw, "res_yraw");
+  c10::cuda::CUDAGuard g(dout.device());
+  auto d = dims_of(yraw);
+  TORCH_CHECK(res_yraw.sizes() == yraw.sizes() && res_mean.numel() == d.C && res_invstd.numel() == d.C &&
+              res_mean.scalar_type() == at::kFloat && res_invstd.scalar_type() == at::kFloat, "bn_act_bwd_res: operand mismatch");
+  Tensor dy = at::empty_like(yraw), dres = at::empty_like(yraw);
+  const bool pre = zeroed_scratch.has_value() && zeroed_scratch->defined();
+  Tensor scratch = pre ? *zeroed_scratch : at::empty({2, d.C}, yraw.options().dtype(at::kFloat));
+  const bool rpre = res_sums_pre.has_value() && res_sums_pre->defined();
+  Tensor rs = rpre ? *res_sums_pre : at::empty({2, d.C}, yraw.options().dtype(at::kFloat));
+  TORCH_CHECK(rs.numel() >= 2 * d.C && rs.scalar_type() == at::kFloat && rs.is_contiguous());
+  int rc = hz_bn_act_bwd_res(cptr(dout), cptr(out), cptr(yraw), mean.data_ptr<float>(), invstd.data_ptr<float>(),
+                             gamma.data_ptr<float>(), scratch.data_ptr<float>(), dy.data_ptr(), dres.data_ptr(),
+                             dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), acc_gamma ? 1 : 0, acc_beta ? 1 : 0,
+                             d.N * d.H * d.W, d.C, (int)relu, (sums_ready && pre) ? 3 : (pre ? 1 : 0), res_yraw.data_ptr(),
+                             res_mean.data_ptr<float>(), res_invstd.data_ptr<float>(), rs.data_ptr<float>(), rpre ? 1 : 0,
+                             cur_stream());
+  TORCH_CHECK(rc == 0, "hz_bn_act_bwd_res: shape / activation not covered");
+  return {dy, dres, rs};
+}
+
 std::vector<Tensor> maxpool_fwd(const Tensor& x, bool want_idx) {
   check_cl(x, "x");
   c10::cuda::CUDAGuard g(x.device());
@@ -715,6 +742,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("channel_sums", &channel_sums);
   m.def("bn_act_fwd", &bn_act_fwd);
   m.def("bn_act_bwd", &bn_act_bwd);
+  m.def("bn_act_bwd_res", &bn_act_bwd_res);
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
   m.def("maxpool_bwd_bn", &maxpool_bwd_bn);

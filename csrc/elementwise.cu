@@ -207,6 +207,83 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(
   }
 }
 
+// BN-backward apply of a layer whose output had a residual added (a BasicBlock's bn2 with a downsample branch) that also
+// takes the backward sums of the BatchNorm producing that residual (the downsample BN: no activation, and this kernel's
+// `dres` is its only upstream gradient): res_sums[0:C] += sum dres, res_sums[C:2C] += sum dres * xhat_res, from the
+// bf16 values being stored — the downsample BN's own reduction pass disappears (ops.BNBackLink, HZ_BN_BWD_IN_DGRAD).
+// Row-lane thread layout of the reductions (C/8 a power of two); arithmetic of bn_act_bwd_apply_kernel.
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_res_kernel(
+    const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ outp,
+    const __nv_bfloat16* __restrict__ yraw, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma,
+    const float* __restrict__ sums, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dres,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, int acc_gamma, int acc_beta,
+    int M, int C, int relu, const __nv_bfloat16* __restrict__ res_yraw, const float* __restrict__ res_mean,
+    const float* __restrict__ res_invstd, float* __restrict__ res_sums) {
+  pdl_launch();
+  pdl_wait();
+  extern __shared__ float sm[];   // k[C], a[C], b[C], mu[C], is[C], red[256 * 16]
+  float *k = sm, *a = sm + C, *b = sm + 2 * C, *mu = sm + 3 * C, *is = sm + 4 * C, *red = sm + 5 * C;
+  const float inv_cnt = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float i_s = invstd[c];
+    k[c] = gamma[c] * i_s;
+    a[c] = sums[c] * inv_cnt;
+    b[c] = sums[C + c] * inv_cnt;
+    mu[c] = mean[c];
+    is[c] = i_s;
+    if (blockIdx.x == 0) {
+      if (dgamma != nullptr) dgamma[c] = (acc_gamma ? dgamma[c] : 0.f) + sums[C + c];
+      if (dbeta != nullptr) dbeta[c] = (acc_beta ? dbeta[c] : 0.f) + sums[c];
+    }
+  }
+  __syncthreads();
+  const int nvec = C >> 3;
+  const int rlanes = 256 / nvec;
+  const int cv = threadIdx.x % nvec, rl = threadIdx.x / nvec;
+  const int c0 = cv * 8;
+  float rmu[8], ris[8], s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { rmu[i] = res_mean[c0 + i]; ris[i] = res_invstd[c0 + i]; s[i] = q[i] = 0.f; }
+  for (int p = blockIdx.x * rlanes + rl; p < M; p += gridDim.x * rlanes) {
+    const size_t off = (size_t)p * C + c0;
+    float g[8], y[8];
+    unpack8(ld8(dout + off), g);
+    unpack8(ld8(yraw + off), y);
+    if (relu) {
+      float o[8];
+      unpack8(ld8(outp + off), o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+    }
+    const bf16x8 gv = pack8(g);
+    st8(dres + off, gv);
+    float gr[8], yr[8];
+    unpack8(gv, gr);                                  // the rounded values the downsample BN's reduction would read
+    unpack8(ld8(res_yraw + off), yr);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += gr[i]; q[i] += gr[i] * (yr[i] - rmu[i]) * ris[i]; }
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      const float xh = (y[i] - mu[c]) * is[c];
+      d[i] = k[c] * (g[i] - a[c] - xh * b[c]);
+    }
+    st8(dy + off, pack8(d));
+  }
+  float* mine = red + ((size_t)rl * nvec + cv) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = s[i]; mine[8 + i] = q[i]; }
+  __syncthreads();
+  for (int o = threadIdx.x; o < nvec * 16; o += 256) {
+    const int v = o >> 4, j = o & 15;
+    float t = 0.f;
+    for (int kk = 0; kk < rlanes; ++kk) t += red[((size_t)kk * nvec + v) * 16 + j];
+    atomicAdd(&res_sums[(j >> 3) * C + v * 8 + (j & 7)], t);
+  }
+}
+
 // Single-kernel BN backward: per-channel reduction -> device-wide barrier -> apply.
 // grid <= #SMs so all CTAs are co-resident (the barrier spins); sums[2C] and the barrier counter come
 // pre-zeroed from the statistics arena.
@@ -978,6 +1055,34 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
       gamma, sums_scratch, (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta, acc_gamma, acc_beta,
       M, C, relu);
+}
+
+// hz_bn_act_bwd for a layer with a residual whose producer is a BatchNorm without activation (the downsample branch):
+// also leaves that BatchNorm's backward sums in res_sums [2C] (see bn_act_bwd_apply_res_kernel).  scratch_is_zero as in
+// hz_bn_act_bwd (3: the own sums are already final).  Returns -1 when the shape / activation is not covered.
+int hz_bn_act_bwd_res(const void* dout, const void* outp, const void* yraw, const float* mean, const float* invstd,
+                      const float* gamma, float* sums_scratch, void* dy, void* dres, float* dgamma, float* dbeta,
+                      int acc_gamma, int acc_beta, int M, int C, int relu, int scratch_is_zero, const void* res_yraw,
+                      const float* res_mean, const float* res_invstd, float* res_sums, int res_sums_is_zero,
+                      cudaStream_t st) {
+  if (hz_channel_ok(C) != 1 || relu == 2 || dres == nullptr || res_yraw == nullptr || res_sums == nullptr) return -1;
+  if (scratch_is_zero != 3) {
+    if (!scratch_is_zero) hz::zero_f32(sums_scratch, (size_t)2 * C, st);
+    hz::launch(hz::channel_reduce_kernel<true>, dim3(reduce_grid(M, C)), dim3(256), sizeof(float) * 256 * 16, st,
+        (const __nv_bfloat16*)dout, (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd,
+        sums_scratch, M, C, relu);
+  }
+  if (!res_sums_is_zero) hz::zero_f32(res_sums, (size_t)2 * C, st);
+  const int rlanes = 256 / (C / 8);
+  int grid = (M + rlanes - 1) / rlanes;
+  grid = (grid + 1) / 2;
+  if (grid < 1) grid = 1;
+  if (grid > 148 * 4) grid = 148 * 4;
+  const size_t smem = sizeof(float) * ((size_t)5 * C + 256 * 16);
+  return hz::launch(hz::bn_act_bwd_apply_res_kernel, dim3(grid), dim3(256), smem, st, (const __nv_bfloat16*)dout,
+                    (const __nv_bfloat16*)outp, (const __nv_bfloat16*)yraw, mean, invstd, gamma, sums_scratch,
+                    (__nv_bfloat16*)dy, (__nv_bfloat16*)dres, dgamma, dbeta, acc_gamma, acc_beta, M, C, relu,
+                    (const __nv_bfloat16*)res_yraw, res_mean, res_invstd, res_sums) == cudaSuccess ? 0 : -1;
 }
 
 void hz_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, cudaStream_t st) {

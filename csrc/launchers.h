@@ -18,6 +18,11 @@ void hz_bn_act_bwd(const void* dout, const void* outp, const void* yraw, const f
                    const float* invstd, const float* gamma, float* sums_scratch, void* dy, void* dres,
                    float* dgamma, float* dbeta, int acc_gamma, int acc_beta, int M, int C, int relu,
                    int scratch_is_zero, cudaStream_t st);
+int hz_bn_act_bwd_res(const void* dout, const void* outp, const void* yraw, const float* mean, const float* invstd,
+                      const float* gamma, float* sums_scratch, void* dy, void* dres, float* dgamma, float* dbeta,
+                      int acc_gamma, int acc_beta, int M, int C, int relu, int scratch_is_zero, const void* res_yraw,
+                      const float* res_mean, const float* res_invstd, float* res_sums, int res_sums_is_zero,
+                      cudaStream_t st);
 void hz_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C, cudaStream_t st);
 void hz_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, cudaStream_t st);
 int hz_maxpool_bwd_bn(const void* dy, const void* idx, void* dx, const void* bn_out, const void* bn_yraw, const float* mean,

@@ -48,11 +48,11 @@ class BNP(nn.Module):
 
 
 def _cba(x, conv: ConvW, bn: BNP, relu: bool, residual=None, training=True, in_link=None, res_link=None,
-         bn_src=None, bn_dst=None):
+         bn_src=None, bn_dst=None, res_bn_src=None):
     return ops.conv_bn_act(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                            stride=conv.stride, pad=conv.pad, relu=relu, residual=residual,
                            momentum=bn.momentum, eps=bn.eps, training=training, in_link=in_link, res_link=res_link,
-                           bn_src=bn_src, bn_dst=bn_dst)
+                           bn_src=bn_src, bn_dst=bn_dst, res_bn_src=res_bn_src)
 
 
 # the block input feeds two branches; their gradients are summed inside the later dgrad kernel's epilogue
@@ -60,8 +60,10 @@ def _cba(x, conv: ConvW, bn: BNP, relu: bool, residual=None, training=True, in_l
 _FUSE_RESADD = os.environ.get("HZ_FUSE_RESADD", "1") != "0"
 # BatchNorm-backward sums (Σg, Σg·x̂) taken in the epilogue of the dgrad kernel whose output IS that BatchNorm's upstream
 # gradient (ops.BNBackLink): bn1 <- conv2's dgrad inside a block, the previous block's bn2 <- whichever of conv1 /
-# downsample runs last (it folds the other shares in): 15 of the 20 reduction kernels of a step disappear.  Off by default: written after the round's GPU budget was
-# spent, first hardware run in tests/test_gpu_blocks.py; HZ_BN_BWD_IN_DGRAD=1 enables it.
+# downsample runs last (it folds the other shares in), the stem's bn1 <- the pool's backward kernel, a downsample BN <- the
+# block's bn2 apply kernel (which stores its upstream gradient): 19 of the 20 reduction kernels of a step disappear (the
+# last block's bn2 gets its gradient from the head kernel).  Off by default: written after the round's GPU budget was
+# spent, first hardware run in tests/test_gpu_bn_handoff.py; HZ_BN_BWD_IN_DGRAD=1 enables it.
 _BN_BWD_IN_DGRAD = os.environ.get("HZ_BN_BWD_IN_DGRAD", "0") == "1"
 
 
@@ -88,9 +90,12 @@ class BasicBlock(nn.Module):
         prev = getattr(x, "_hz_bn_back", None) if (fuse and link is not None) else None
         nxt = ops.BNBackLink(single=False) if fuse else None
         if self.downsample is not None:
-            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t, in_link=link, bn_src=prev)
+            dsl = ops.BNBackLink() if fuse else None                  # downsample BN -> bn2's residual add (only consumer)
+            idt = _cba(x, self.downsample[0], self.downsample[1], relu=False, training=t, in_link=link, bn_src=prev,
+                       bn_dst=dsl)
             y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link, bn_dst=bl, bn_src=prev)
-            out = _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t, bn_src=bl, bn_dst=nxt)
+            out = _cba(y, self.conv2, self.bn2, relu=True, residual=idt, training=t, bn_src=bl, bn_dst=nxt,
+                       res_bn_src=dsl)
         else:
             y = _cba(x, self.conv1, self.bn1, relu=True, training=t, in_link=link, bn_dst=bl, bn_src=prev)
             out = _cba(y, self.conv2, self.bn2, relu=True, residual=x, training=t, res_link=link, bn_src=bl, bn_dst=nxt)

@@ -166,13 +166,15 @@ class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
                 momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link=None, res_link=None,
-                bn_src=None, bn_dst=None):
+                bn_src=None, bn_dst=None, res_bn_src=None):
         be = _be(x)
         w = compute_weight(weight, x.dtype)
         ctx.post_dgrad = post_dgrad
         ctx.dgrad_fn = dgrad_fn
         ctx.in_link, ctx.res_link = in_link, res_link
         ctx.bn_src, ctx.bn_dst = bn_src, bn_dst
+        ctx.res_bn_src = res_bn_src
+        ctx.res_ptr = residual.data_ptr() if (residual is not None and res_bn_src is not None) else None
         fused = None
         if conv_fn is None and post_conv is None and training and hasattr(be, "conv_bn_act_fwd"):
             # one kernel: conv + BN statistics + device-wide barrier + normalise / residual / ReLU
@@ -214,7 +216,18 @@ class _ConvBNAct(torch.autograd.Function):
             # the consumer's dgrad kernel produced `dout` AND this BN's backward sums (only if `dout` is its tensor)
             pre_sums = ctx.bn_dst.sums
             ctx.bn_dst.clear()
-        if pre_sums is not None:
+        rsrc = ctx.res_bn_src
+        with_res = None
+        if (has_res and rsrc is not None and rsrc.out is not None and rsrc.sums is None and rsrc.single
+                and rsrc.act == 0 and ctx.res_link is None and rsrc.out.data_ptr() == ctx.res_ptr
+                and hasattr(be, "bn_act_bwd_res")):
+            # the residual is the output of a BatchNorm without activation and this op is its only consumer: the apply
+            # kernel stores that BatchNorm's upstream gradient (dres) and takes its backward sums on the way
+            with_res = be.bn_act_bwd_res(dout, out, y_raw, mean, invstd, gamma.detach(), relu, _tb.GradSlot(tg, ag),
+                                         _tb.GradSlot(tb, ab), pre_sums, rsrc.y_raw, rsrc.mean, rsrc.invstd)
+        if with_res is not None:
+            dy, dres, rsrc.sums = with_res
+        elif pre_sums is not None:
             dy, _, _, dres = be.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma.detach(), relu, has_res,
                                            _tb.GradSlot(tg, ag), _tb.GradSlot(tb, ab), sums=pre_sums)
         else:
@@ -274,18 +287,20 @@ class _ConvBNAct(torch.autograd.Function):
         else:
             be.conv_wgrad(dy, x, weight.shape, stride, pad, tgt, acc, zeroed)
             grad_written(weight)
-        return (dx, None, None, None, dres) + (None,) * 16
+        return (dx, None, None, None, dres) + (None,) * 17
 
 
 def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True, residual=None,
                 momentum=0.1, eps=1e-5, training=True, post_conv=None, post_dgrad=None,
-                conv_fn=None, dgrad_fn=None, in_link=None, res_link=None, bn_src=None, bn_dst=None):
+                conv_fn=None, dgrad_fn=None, in_link=None, res_link=None, bn_src=None, bn_dst=None, res_bn_src=None):
     """``post_conv`` / ``post_dgrad`` are the tensor-parallel reduction points (row-parallel conv
     output, column-parallel conv input-gradient); they take and return a tensor.  ``conv_fn(x, w, want_stats) ->
     (y, sums | None)`` / ``dgrad_fn(dy, w, addend) -> dx`` replace conv + reduction (+ BN statistics pass / residual
     gradient add) by ONE fused GEMM+collective kernel.  ``relu``: False/0 none, True/1 ReLU, 2 ReLU6.
     ``bn_dst`` / ``bn_src``: a ``BNBackLink`` shared by a producer (``bn_dst``) and the single consumer of its output
-    (``bn_src``): the consumer's dgrad kernel takes the producer's BatchNorm-backward sums in its epilogue."""
+    (``bn_src``): the consumer's dgrad kernel takes the producer's BatchNorm-backward sums in its epilogue.
+    ``res_bn_src``: the ``bn_dst`` link of the op that produced ``residual`` (a BatchNorm without activation whose only
+    consumer is this op): this op's BN-backward apply kernel takes that BatchNorm's backward sums."""
     if not training or not torch.is_grad_enabled():
         be = _be(x)
         if conv_fn is not None:
@@ -300,7 +315,7 @@ def conv_bn_act(x, weight, gamma, beta, rmean, rvar, stride=1, pad=1, relu=True,
         return out
     return _ConvBNAct.apply(x, weight, gamma, beta, residual, rmean, rvar, stride, pad, relu,
                             momentum, eps, training, post_conv, post_dgrad, conv_fn, dgrad_fn, in_link, res_link,
-                            bn_src, bn_dst)
+                            bn_src, bn_dst, res_bn_src)
 
 
 # ----------------------------------------------------------------------------------------------

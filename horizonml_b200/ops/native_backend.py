@@ -233,6 +233,31 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma
     return _tb.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_residual, dgamma_slot, dbeta_slot)
 
 
+def bn_act_bwd_res(dout, out, y_raw, mean, invstd, gamma, relu, dgamma_slot, dbeta_slot, sums, res_yraw, res_mean,
+                   res_invstd):
+    """bn_act_bwd of a layer whose residual comes from a BatchNorm without activation (a BasicBlock's downsample
+    branch): the apply kernel also takes that BatchNorm's backward sums from the residual gradient it stores.
+    ``sums``: this layer's own final sums if its consumer's dgrad already took them.  Returns (dy, dres, res_sums) or
+    None when the shape / activation is not covered (caller runs the plain bn_act_bwd)."""
+    c = y_raw.shape[1]
+    if not (_bf16_cl(y_raw) and _bf16_cl(res_yraw) and tuple(res_yraw.shape) == tuple(y_raw.shape)
+            and C.channel_ok(c) == 1 and int(relu) in (0, 1) and dgamma_slot is not None
+            and res_mean.dtype == torch.float32 and res_invstd.dtype == torch.float32):
+        return None
+    dg, ag, db, ab = dgamma_slot.t, dgamma_slot.acc, dbeta_slot.t, dbeta_slot.acc
+    pre = ARENA.take(2, c, y_raw.device)
+    if sums is not None:
+        LAUNCHES["bn_act_bwd"] += 1
+        dy, dres, rs = C.bn_act_bwd_res(dout, out, y_raw, mean, invstd, gamma, int(relu), dg, db, ag, ab, sums, True,
+                                        res_yraw, res_mean, res_invstd, pre)
+    else:
+        LAUNCHES["bn_act_bwd"] += 2
+        scratch = ARENA.take(1, 2 * c, y_raw.device)
+        dy, dres, rs = C.bn_act_bwd_res(dout, out, y_raw, mean, invstd, gamma, int(relu), dg, db, ag, ab, scratch, False,
+                                        res_yraw, res_mean, res_invstd, pre)
+    return dy, dres, rs
+
+
 def conv_dgrad(dy, w, x_shape, stride: int, pad: int, addend=None):
     """``addend``: bf16 channels_last tensor of x's shape added in the kernel epilogue (the residual-branch
     gradient), replacing autograd's separate accumulation kernel."""

@@ -98,6 +98,20 @@ def bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu: bool, has_residual: 
     return _cl(dy.to(y_raw.dtype)), dgamma, dbeta, dres
 
 
+def bn_act_bwd_res(dout, out, y_raw, mean, invstd, gamma, relu, dgamma_slot, dbeta_slot, sums, res_yraw, res_mean,
+                   res_invstd):
+    """Oracle of the native apply-with-residual-BN-sums kernel: bn_act_bwd of a layer with a residual whose producer
+    is a BatchNorm without activation, plus that BatchNorm's backward sums [Σ dres, Σ dres·x̂_res] taken from dres
+    rounded to its storage dtype.  Returns (dy, dres, res_sums) or None (activation not covered)."""
+    if int(relu) not in (0, 1):
+        return None
+    dy, _, _, dres = bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, True, dgamma_slot, dbeta_slot, sums=sums)
+    C = y_raw.shape[1]
+    g = dres.float()
+    xhat = (res_yraw.float() - res_mean.view(1, C, 1, 1)) * res_invstd.view(1, C, 1, 1)
+    return dy, dres, torch.stack([g.sum(dim=(0, 2, 3)), (g * xhat).sum(dim=(0, 2, 3))])
+
+
 def conv_dgrad(dy, w, x_shape, stride: int, pad: int, addend=None):
     dx, _, _ = torch.ops.aten.convolution_backward(
         dy, dy.new_empty(x_shape), w.to(dy.dtype), None, [stride, stride], [pad, pad], [1, 1], False,

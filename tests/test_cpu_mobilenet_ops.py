@@ -90,6 +90,10 @@ def test_native_binding_signatures_for_mobilenet_ops():
         "bn_act_fwd": lambda: C.bn_act_fwd(x, torch.zeros(2, 16), f, f, f, f, 0.1, 1e-5, None, 2, True),
         "bn_act_bwd": lambda: C.bn_act_bwd(x, x, x, f, f, f, 2, False, f, f, False, False, None, False),
         "bn_act_bwd(sums)": lambda: C.bn_act_bwd(x, x, x, f, f, f, 1, False, f, f, False, False, torch.zeros(2, 16), True),
+        "bn_act_bwd_res": lambda: C.bn_act_bwd_res(x, x, x, f, f, f, 1, f, f, False, False, torch.zeros(2, 16), True,
+                                                   x, f, f, torch.zeros(2, 16)),
+        "bn_act_bwd_res(no scratch)": lambda: C.bn_act_bwd_res(x, x, x, f, f, f, 0, f, f, True, True, None, False,
+                                                               x, f, f, None),
         "conv_dgrad_bnbwd": lambda: C.conv_dgrad_bnbwd(x, torch.zeros(16, 16, 3, 3, dtype=torch.bfloat16).contiguous(
             memory_format=torch.channels_last), [2, 16, 4, 4], 1, 1, None, False, x, x, f, f, None, False),
     }

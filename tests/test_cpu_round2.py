@@ -263,6 +263,13 @@ def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
         calls["n"] += 1
         return orig(*a, **k)
     tb.conv_dgrad_bnbwd = counted
+    res_calls = {"n": 0}
+    orig_res = tb.bn_act_bwd_res
+
+    def counted_res(*a, **k):
+        res_calls["n"] += 1
+        return orig_res(*a, **k)
+    tb.bn_act_bwd_res = counted_res
     try:
         for cin, cout, stride in ((16, 16, 1), (16, 32, 2)):
             res = []
@@ -277,6 +284,7 @@ def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
             for a, b in zip(*res):
                 assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
         assert calls["n"] == 2                       # one fused dgrad per block, only with the flag on
+        assert res_calls["n"] == 1                   # the downsample BN's sums from bn2's apply (downsample block only)
         # a stack of blocks: the previous block's bn2 gets its sums from whichever consumer of the block output runs last
         calls["n"] = 0
         res = []
@@ -291,7 +299,9 @@ def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
         for a, b in zip(*res):
             assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
         assert calls["n"] == 5                       # 3 x (bn1 <- conv2) + 2 x (previous bn2 <- next block)
-        # the whole model: 8 + 7 dgrad hand-offs and the stem's bn1 <- max-pool backward; loss and gradients unchanged
+        assert res_calls["n"] == 2
+        # the whole model: 8 + 7 dgrad hand-offs, the stem's bn1 <- max-pool backward, 3 downsample BNs <- bn2's apply;
+        # loss and gradients unchanged
         pool_calls = {"n": 0}
         orig_pool = tb.maxpool_bwd_bn
 
@@ -312,11 +322,12 @@ def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
                 res.append([loss.detach()] + [p.grad for p in model.parameters()])
             for a, b in zip(*res):
                 assert torch.allclose(a, b, atol=2e-5, rtol=1e-4), (a - b).abs().max()
-            assert calls["n"] == 15 and pool_calls["n"] == 1
+            assert calls["n"] == 15 and pool_calls["n"] == 1 and res_calls["n"] == 2 + 3
         finally:
             tb.maxpool_bwd_bn = orig_pool
     finally:
         tb.conv_dgrad_bnbwd = orig
+        tb.bn_act_bwd_res = orig_res
         R._BN_BWD_IN_DGRAD = False
 
 

@@ -74,7 +74,8 @@ def test_basic_block_with_bn_sums_in_dgrad(cin, cout, stride, hw):
     finally:
         R._BN_BWD_IN_DGRAD = False
         ops.set_backend("torch")
-    assert launches[True] == launches[False] - 1, launches
+    # bn1 <- conv2's dgrad; with a downsample branch also its BN <- bn2's apply kernel
+    assert launches[True] == launches[False] - (2 if (stride != 1 or cin != cout) else 1), launches
     (y0, dx0, g0), (y1, dx1, g1) = res[False], res[True]
     assert rel_err(y1, y0) < 1e-2 and rel_err(dx1, dx0) < 2e-2       # (BN statistics: fp32 atomics, last-bit noise)
     for n in g0:
@@ -83,8 +84,9 @@ def test_basic_block_with_bn_sums_in_dgrad(cin, cout, stride, hw):
 
 
 def test_resnet18_step_with_bn_sums_in_dgrad():
-    """Whole model: 16 of the 20 BatchNorm-backward reduction kernels are gone (bn1 of every block and bn2 of every block
-    but the last take their sums from a dgrad epilogue, the stem's bn1 from the max-pool backward kernel), the first-step loss is unchanged, gradients agree with the
+    """Whole model: 19 of the 20 BatchNorm-backward reduction kernels are gone (bn1 of every block and bn2 of every block
+    but the last take their sums from a dgrad epilogue, the stem's bn1 from the max-pool backward kernel, the three
+    downsample BNs from their block's bn2 apply kernel), the first-step loss is unchanged, gradients agree with the
     two-kernel path to the run-to-run noise of the fp32 atomics, and training still makes progress."""
     import horizonml_b200.models.resnet as R
     from horizonml_b200 import ops
@@ -119,11 +121,49 @@ def test_resnet18_step_with_bn_sums_in_dgrad():
     finally:
         R._BN_BWD_IN_DGRAD = False
         ops.set_backend("torch")
-    assert res[False][1] == 40 and res[True][1] == 24, (res[False][1], res[True][1])    # 15 dgrad hand-offs + the pool's
+    # 15 dgrad hand-offs + the pool's + 3 downsample BNs
+    assert res[False][1] == 40 and res[True][1] == 21, (res[False][1], res[True][1])
     l0, l1 = res[("loss", False)], res[("loss", True)]
     assert abs(l0[0] - l1[0]) < 1e-3 and all(v == v for v in l1) and l1[-1] < l1[0], (l0, l1)   # (loss: fp32 atomics)
     cos = torch.nn.functional.cosine_similarity(res[False][0].flatten(), res[True][0].flatten(), dim=0).item()
     assert cos > 0.9, cos
+
+
+@pytest.mark.parametrize("N,C,H", [(64, 128, 4), (64, 256, 2), (64, 512, 1), (64, 64, 8), (5, 128, 3)])
+@pytest.mark.parametrize("relu,own_ready", [(1, False), (1, True), (0, False)])
+def test_bn_backward_apply_with_residual_bn_sums(N, C, H, relu, own_ready):
+    """bn_act_bwd_res == bn_act_bwd (dy, dres, dgamma, dbeta) + the backward sums of the BatchNorm that produced the
+    residual, taken from the stored dres; with and without this layer's own sums already final."""
+    from horizonml_b200.ops import native_backend as nb
+    from horizonml_b200.ops import torch_backend as tb
+    g = torch.Generator().manual_seed(21)
+    mk = lambda scale=1.0: cl((torch.randn(N, C, H, H, generator=g) * scale).to(DEV).bfloat16())      # noqa: E731
+    dout, out, y_raw, res_yraw = mk(0.5), mk(), mk(), mk()
+    vec = lambda: (torch.randn(C, generator=g).to(DEV) * 0.1, (torch.rand(C, generator=g) + 0.5).to(DEV))   # noqa: E731
+    (mean, invstd), (rmean, rinvstd) = vec(), vec()
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV)
+    slots = lambda: (tb.GradSlot(torch.zeros(C, device=DEV), False), tb.GradSlot(torch.zeros(C, device=DEV), False))  # noqa: E731
+    s0, s1 = slots(), slots()
+    dy0, _, _, dres0 = nb.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, True, *s0)
+    own = None
+    if own_ready:
+        gg = dout.float() * ((out > 0).float() if relu else 1.0)
+        xh = (y_raw.float() - mean.view(1, -1, 1, 1)) * invstd.view(1, -1, 1, 1)
+        own = torch.stack([gg.sum(dim=(0, 2, 3)), (gg * xh).sum(dim=(0, 2, 3))]).contiguous()
+    nb.step_begin(DEV)
+    got = nb.bn_act_bwd_res(dout, out, y_raw, mean, invstd, gamma, relu, *s1, own, res_yraw, rmean, rinvstd)
+    nb.step_end()
+    assert got is not None
+    dy1, dres1, rs = got
+    assert torch.equal(dres1, dres0)
+    assert rel_err(dy1, dy0) < 2e-3 and rel_err(s1[0].t, s0[0].t) < 1e-3 and rel_err(s1[1].t, s0[1].t) < 1e-3
+    gr = dres0.float()
+    xhat = (res_yraw.float() - rmean.view(1, -1, 1, 1)) * rinvstd.view(1, -1, 1, 1)
+    ref = torch.stack([gr.sum(dim=(0, 2, 3)), (gr * xhat).sum(dim=(0, 2, 3))])
+    assert rel_err(rs.view(2, -1), ref) < 1e-3
+    # outside a step (no pre-zeroed arena): the launcher zeroes its own scratch
+    got2 = nb.bn_act_bwd_res(dout, out, y_raw, mean, invstd, gamma, relu, *slots(), own, res_yraw, rmean, rinvstd)
+    assert rel_err(got2[2].view(2, -1), ref) < 1e-3 and rel_err(got2[0], dy0) < 2e-3
 
 
 @pytest.mark.parametrize("relu", [1, 0])
