@@ -772,6 +772,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("grad_diff_sq", &grad_diff_sq);
   m.def("stats_update", &stats_update);
   m.def("conv_supported", &conv_supported);
+  m.def("conv_shape_ok", [](int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int64_t R, int64_t stride,
+                            int64_t pad) {
+    return hz_conv_shape_ok((int)N, (int)H, (int)W, (int)Cin, (int)Cout, (int)R, (int)stride, (int)pad) != 0;
+  });
   m.def("conv_fwd", &conv_fwd);
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_dgrad_bnbwd", &conv_dgrad_bnbwd);

@@ -1087,7 +1087,8 @@ int pick_splits(int tiles, int k_total) {
 
 extern "C" {
 
-int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad) {
+// the shape rules of hz_conv_supported alone (host-only: also answers on a machine without a CUDA driver)
+int hz_conv_shape_ok(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad) {
   // channel counts only need 16-byte rows (TMA): a 64-wide box over a narrower tensor is zero-filled, surplus output
   // columns are masked in the epilogue — tensor-parallel shards (256/8 = 32 channels) stay on these kernels
   if ((Cin & 7) || (Cout & 7) || Cin < 8 || Cout < 8) return 0;
@@ -1099,7 +1100,11 @@ int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride,
   if (!pick_tile(128, N, Ho, Wo, &t)) return 0;
   if (!pick_tile(64, N, Ho, Wo, &t)) return 0;
   if (!pick_tile(128, N, H, W, &t) && stride == 1) return 0;
-  return get_encode() != nullptr;
+  return 1;
+}
+
+int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad) {
+  return hz_conv_shape_ok(N, H, W, Cin, Cout, R, stride, pad) && get_encode() != nullptr;
 }
 
 // per-CTA phase stamps (16 x int64 per CTA) for the next forward / dgrad launches; nullptr switches them off

@@ -55,6 +55,7 @@ int hz_dwconv_wgrad(const void* dy, const void* x, float* dwt, int N, int H, int
 
 // ---- conv_gemm.cu (tcgen05 implicit GEMM)
 int hz_conv_supported(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
+int hz_conv_shape_ok(int N, int H, int W, int Cin, int Cout, int R, int stride, int pad);
 void hz_cluster_capacity(int out[4]);
 void hz_conv_set_debug(long long* buf);
 int hz_conv_set_persist(int mode);      // persistent (throughput) conv kernel: -1 auto by grid size, 0 never, 1 always

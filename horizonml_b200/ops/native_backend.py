@@ -71,8 +71,14 @@ def _fallback(name: str, why: str):
         raise RuntimeError(f"native backend fallback in {name}: {why}")
 
 
+def _dev(t: torch.Tensor) -> bool:
+    """Tensor lives where the kernels run (one seam: tests/test_cpu_native_plumbing.py drives this module on CPU
+    tensors against a shim of the extension)."""
+    return t.is_cuda
+
+
 def _bf16_cl(t: torch.Tensor) -> bool:
-    return t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 4
+    return _dev(t) and t.dtype == torch.bfloat16 and t.dim() == 4
 
 
 def _conv_ok(x_shape, w_shape, stride, pad) -> bool:
@@ -290,7 +296,7 @@ def conv_dgrad_bnbwd(dy, w, x_shape, stride: int, pad: int, addend, bn_out, bn_y
 def _flat_dw_ok(out_grad: torch.Tensor, w_shape) -> bool:
     """out_grad must be the [Cout,R,S,Cin]-physical fp32 view (what FlatParams hands out)."""
     cout, cin, r, s = w_shape
-    return (out_grad.dtype == torch.float32 and out_grad.is_cuda and
+    return (out_grad.dtype == torch.float32 and _dev(out_grad) and
             out_grad.permute(0, 2, 3, 1).is_contiguous())
 
 
@@ -357,7 +363,7 @@ def dwconv_dgrad_bnbwd(dy, w, x_shape, stride: int, bn_out, bn_yraw, bn_mean, bn
 
 
 def dwconv_wgrad(dy, x, stride: int, out_grad: torch.Tensor, accumulate: bool, prezeroed: bool = False):
-    if (_bf16_cl(dy) and _bf16_cl(x) and _dw_ok(x.shape, stride) and out_grad.is_cuda and out_grad.dtype == torch.float32
+    if (_bf16_cl(dy) and _bf16_cl(x) and _dw_ok(x.shape, stride) and _dev(out_grad) and out_grad.dtype == torch.float32
             and out_grad.dim() == 4 and out_grad.stride(0) == 9 and out_grad.stride(2) == 3 and out_grad.stride(3) == 1):
         LAUNCHES["dwconv_wgrad"] += 1
         C.dwconv_wgrad(dy, x, out_grad, stride, accumulate, prezeroed)
@@ -412,7 +418,7 @@ def linear_fwd(x2d, w, b):
 
 def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.0, prev=None, zero_grad=False,
               live_blocks=None, diff_out=None, bump=True, max_ctas=0):
-    if master.is_cuda and master.numel() % 4 == 0 and (shadow is None or shadow.dtype == torch.bfloat16):
+    if _dev(master) and master.numel() % 4 == 0 and (shadow is None or shadow.dtype == torch.bfloat16):
         LAUNCHES["adam"] += 2 if bump else 1
         diff = diff_out
         if diff is None and prev is not None:
@@ -426,21 +432,21 @@ def adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale=1.
 
 
 def grad_diff_sq(grad, prev):
-    if grad.is_cuda and grad.numel() % 4 == 0:
+    if _dev(grad) and grad.numel() % 4 == 0:
         LAUNCHES["grad_diff"] += 1
         return C.grad_diff_sq(grad, prev)
     return _tb.grad_diff_sq(grad, prev)
 
 
 def stem_prepare(images, mean, std, dtype):
-    if images.is_cuda and images.dtype == torch.uint8 and dtype == torch.bfloat16:
+    if _dev(images) and images.dtype == torch.uint8 and dtype == torch.bfloat16:
         LAUNCHES["u8_normalize"] += 1
         return C.u8_normalize(images, mean, std)
     return _tb.stem_prepare(images, mean, std, dtype)
 
 
 def stats_update(stats, has_prev, loss, correct, batch, diff_sq):
-    if stats.is_cuda and loss.dtype == torch.float32 and correct.dtype == torch.float32:
+    if _dev(stats) and loss.dtype == torch.float32 and correct.dtype == torch.float32:
         LAUNCHES["stats"] += 1
         C.stats_update(stats, has_prev, loss.detach(), correct.detach(), float(batch), diff_sq)
         return

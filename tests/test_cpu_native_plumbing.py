@@ -1,0 +1,292 @@
+"""The native backend's Python layer, driven on CPU tensors against a shim of the CUDA extension.
+
+No kernel can run here, but everything between the model and the kernel launch can: ``ops/functional.py`` →
+``ops/native_backend.py`` → the pybind argument lists of ``csrc/bindings.cpp``.  Every call the native backend makes is
+(1) forwarded to the REAL binding with the CPU tensors — pybind must accept the argument list (no TypeError) and the
+binding must then stop at its device check — and (2) answered by an emulation of the kernel built from the PyTorch-op
+oracle, honouring the binding's buffer contract (statistics accumulated into the pre-zeroed arena slice, gradients
+written / accumulated in place into the flat bucket views).  A whole ResNet-18 / MobileNetV2 training step through that
+path must then reproduce the PyTorch-op backend's loss and gradients with no fallback: a mis-ordered argument, a
+missing return value, a wrong activation code, a hand-off link feeding the wrong layer or a stale arena slice shows up
+here instead of on the first GPU run (native_backend.py was edited after the round's last GPU access)."""
+import os
+from collections import Counter
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from horizonml_b200.ops import _ext
+from horizonml_b200.ops import torch_backend as tb
+
+BF16 = torch.bfloat16
+
+
+class ShimC:
+    """Stands in for horizonml_b200._C: real pybind signature check + oracle emulation per binding."""
+
+    def __init__(self, real):
+        self._real = real
+        self.calls = Counter()
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        if name == "conv_supported":             # the real one also asks for the CUDA driver's tensor-map encoder
+            return self._real.conv_shape_ok
+        real = getattr(self._real, name)         # AttributeError = the backend calls a binding that does not exist
+        emu = getattr(self, "_emu_" + name, None)
+
+        def call(*args):
+            self.calls[name] += 1
+            try:
+                out = real(*args)
+            except TypeError as e:                # pybind rejected the argument list
+                raise AssertionError(f"C.{name}: argument list rejected by the binding: {str(e)[:400]}") from None
+            except RuntimeError as e:
+                msg = str(e)
+                assert "CUDA tensor" in msg or "is_cuda" in msg, f"C.{name} failed before its device check: {msg[:300]}"
+                assert emu is not None, f"no emulation for C.{name}"
+                return emu(*args)
+            assert emu is None, f"C.{name} accepted CPU tensors"      # pure host helpers only (channel_ok, ...)
+            return out
+        return call
+
+    # ---- convolution
+    @staticmethod
+    def _stats_out(sums, pre):
+        if pre is None:
+            return sums
+        pre.view(2, -1).add_(sums)                # the kernels accumulate into the pre-zeroed arena slice
+        return pre
+
+    def _emu_conv_fwd(self, x, w, stride, pad, want_stats, pre, stable):
+        y, sums = tb.conv_fwd(x, w, stride, pad, want_stats)
+        return y, (self._stats_out(sums, pre) if want_stats else None)
+
+    @staticmethod
+    def _im2col(x, r, stride, pad, kp):
+        cols = F.unfold(x.float(), r, padding=pad, stride=stride)                 # [N, Cin*r*r, L], K order (cin, r, s)
+        n, k, L = cols.shape
+        cin = x.shape[1]
+        A = cols.view(n, cin, r, r, L).permute(0, 4, 2, 3, 1).reshape(n * L, r * r * cin)   # K order (r, s, cin)
+        return F.pad(A, (0, kp - k)).to(x.dtype).contiguous()
+
+    def _emu_stem_pack(self, x, w2d, r, stride, pad, kp):
+        return self._im2col(x, r, stride, pad, kp), F.pad(w2d, (0, kp - w2d.shape[1])).contiguous()
+
+    def _emu_im2col_small(self, x, r, stride, pad, kp):
+        return self._im2col(x, r, stride, pad, kp)
+
+    def _emu_conv_dgrad(self, dy, w, x_shape, stride, pad, addend, stable):
+        return tb.conv_dgrad(dy, w, x_shape, stride, pad, addend)
+
+    def _emu_conv_dgrad_bnbwd(self, dy, w, x_shape, stride, pad, addend, stable, bn_out, bn_yraw, mean, invstd, pre, cap6):
+        assert not (cap6 and bn_out is None)
+        relu = 2 if cap6 else (1 if bn_out is not None else 0)
+        dx, sums = tb.conv_dgrad_bnbwd(dy, w, x_shape, stride, pad, addend, bn_out, bn_yraw, mean, invstd, relu)
+        return dx, self._stats_out(sums, pre)
+
+    def _emu_conv_wgrad(self, dy, x, out_grad, r, stride, pad, accumulate, prezeroed, k_valid, k_ld):
+        if k_valid == 0:
+            gw = torch.ops.aten.convolution_backward(dy, x, dy.new_empty(out_grad.shape), None, [stride, stride], [pad, pad],
+                                                     [1, 1], False, [0, 0], 1, [False, True, False])[1].float()
+        else:                                      # stem: dy [M, Cout, 1, 1], im2col matrix [M, Kp, 1, 1]
+            cout, cin, R, S = out_grad.shape
+            assert k_valid == cin * R * S == k_ld
+            m = dy.shape[0]
+            g2 = dy.reshape(m, cout).float().t() @ x.reshape(m, -1).float()[:, :k_valid]       # K order (r, s, cin)
+            gw = g2.view(cout, R, S, cin).permute(0, 3, 1, 2)
+        if accumulate or prezeroed:                # prezeroed: the kernel adds into a buffer it is told is zero
+            out_grad.add_(gw)
+        else:
+            out_grad.copy_(gw)
+
+    # ---- depthwise
+    def _emu_dwconv_fwd(self, x, w, stride, want_stats, pre):
+        y, sums = tb.dwconv_fwd(x, w, stride, want_stats)
+        return y, (self._stats_out(sums, pre) if want_stats else None)
+
+    def _emu_dwconv_dgrad(self, dy, w, x_shape, stride):
+        return tb.dwconv_dgrad(dy, w, x_shape, stride)
+
+    def _emu_dwconv_dgrad_bnbwd(self, dy, w, x_shape, stride, bn_out, bn_yraw, mean, invstd, pre, cap6):
+        relu = 2 if cap6 else (1 if bn_out is not None else 0)
+        dx, sums = tb.dwconv_dgrad_bnbwd(dy, w, x_shape, stride, bn_out, bn_yraw, mean, invstd, relu)
+        return dx, self._stats_out(sums, pre)
+
+    def _emu_dwconv_wgrad(self, dy, x, out_grad, stride, accumulate, prezeroed):
+        tb.dwconv_wgrad(dy, x, stride, out_grad, accumulate or prezeroed)
+
+    # ---- BatchNorm
+    def _emu_channel_sums(self, y):
+        yf = y.float()
+        return torch.stack([yf.sum(dim=(0, 2, 3)), (yf * yf).sum(dim=(0, 2, 3))])
+
+    def _emu_bn_act_fwd(self, y_raw, sums, gamma, beta, rmean, rvar, momentum, eps, residual, relu, training):
+        assert relu in (0, 1, 2) and isinstance(relu, int)
+        return tb.bn_act_fwd(y_raw, sums.view(2, -1) if training else None, gamma, beta, rmean, rvar, momentum, eps,
+                             residual, relu, training)
+
+    def _emu_bn_act_bwd(self, dout, out, y_raw, mean, invstd, gamma, relu, has_res, dg, db, ag, ab, scratch, sums_ready):
+        c = y_raw.shape[1]
+        if sums_ready:
+            assert scratch is not None
+        elif scratch is not None:
+            assert float(scratch.abs().sum()) == 0.0, "BN-backward scratch handed over as zeroed is not zero"
+        dy, _, _, dres = tb.bn_act_bwd(dout, out, y_raw, mean, invstd, gamma, relu, has_res, tb.GradSlot(dg, ag),
+                                       tb.GradSlot(db, ab), sums=scratch.reshape(-1)[:2 * c].view(2, c) if sums_ready else None)
+        return dy, dres
+
+    def _emu_bn_act_bwd_res(self, dout, out, y_raw, mean, invstd, gamma, relu, dg, db, ag, ab, scratch, sums_ready,
+                            res_yraw, res_mean, res_invstd, pre):
+        c = y_raw.shape[1]
+        dy, dres, rs = tb.bn_act_bwd_res(dout, out, y_raw, mean, invstd, gamma, relu, tb.GradSlot(dg, ag), tb.GradSlot(db, ab),
+                                         scratch.reshape(-1)[:2 * c].view(2, c) if sums_ready else None, res_yraw,
+                                         res_mean, res_invstd)
+        return dy, dres, self._stats_out(rs, pre)
+
+    # ---- pooling / head / optimizer / bookkeeping
+    def _emu_maxpool_fwd(self, x, want_idx):
+        y, aux = tb.maxpool_fwd(x, want_idx)
+        return y, (aux[0] if want_idx else None)
+
+    def _emu_maxpool_bwd(self, dy, idx, shape):
+        return tb.maxpool_bwd(dy, (idx, tuple(shape)))
+
+    def _emu_maxpool_bwd_bn(self, dy, idx, shape, bn_out, bn_yraw, mean, invstd, pre):
+        dx, sums = tb.maxpool_bwd_bn(dy, (idx, tuple(shape)), bn_out, bn_yraw, mean, invstd, 1 if bn_out is not None else 0)
+        return dx, self._stats_out(sums, pre)
+
+    def _emu_head_fwd_bwd(self, feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out, db_out, accumulate, need_dfeat, scratch):
+        return tb.head_fwd_bwd(feat, fc_w, fc_b, labels, loss_scale, n_valid, dw_out, db_out, accumulate, need_dfeat)
+
+    def _emu_adam_step(self, master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, diff, zero_grad,
+                       live_blocks, bump, max_ctas):
+        tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad, live_blocks, diff,
+                     bump, max_ctas)
+
+    def _emu_grad_diff_sq(self, grad, prev):
+        return tb.grad_diff_sq(grad, prev)
+
+    def _emu_u8_normalize(self, images, mean, std):
+        return tb.stem_prepare(images, mean, std, BF16)
+
+    def _emu_stats_update(self, stats, has_prev, loss, correct, batch, diff_sq):
+        tb.stats_update(stats, has_prev, loss, correct, batch, diff_sq)
+
+
+@pytest.fixture
+def shim(monkeypatch):
+    real = _ext.load(required=False)
+    if real is None:
+        pytest.skip("extension not built")
+    import horizonml_b200.ops.native_backend as nb
+    from horizonml_b200.ops import functional as fn
+    s = ShimC(real)
+    monkeypatch.setattr(nb, "C", s)
+    monkeypatch.setattr(nb, "_dev", lambda t: True)
+    monkeypatch.setattr(nb, "_STRICT", True)                      # any fallback raises
+    state = {"native": False}
+    monkeypatch.setattr(fn, "_be", lambda t: nb if state["native"] else tb)
+    return s, nb, state
+
+
+def _train_steps(make_model, images, labels, nb, state, native, steps=2):
+    """`steps` optimizer steps of model.forward_loss through FlatParams / FlatAdam; returns (losses, first-step flat
+    gradient, final master parameters)."""
+    from horizonml_b200 import ops
+    from horizonml_b200.models.flat import FlatAdam, FlatParams
+    state["native"] = native
+    torch.manual_seed(11)                       # MobileNetV2's classifier dropout draws the same mask in both runs
+    dev = torch.device("cpu")
+    model = make_model().train()
+    with torch.no_grad():                       # wide BatchNorm outputs: plenty of activations beyond ReLU6's cap, so a
+        for n, p in model.named_parameters():   # wrong activation code anywhere changes the gradients visibly
+            if p.dim() == 1 and n.endswith("weight"):
+                p.mul_(4.0)
+    flat = FlatParams(list(model.named_parameters()), dev, BF16)
+    opt = FlatAdam(flat, lr=1e-3)
+    losses, g0 = [], None
+    for it in range(steps):
+        x = ops.stem_prepare(images.permute(0, 3, 1, 2), dtype=BF16)
+        if native:
+            nb.step_begin(dev)
+        flat.begin_step()
+        loss, _ = model.forward_loss(x, labels)
+        loss.backward()
+        ops.join_side()
+        if native:
+            nb.step_end()
+        if it == 0:
+            g0 = flat.grad.clone()
+        opt.step()
+        losses.append(float(loss.detach()))
+    return losses, g0, flat.master.clone()
+
+
+def _close(a, b, tol):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)) < tol
+
+
+@pytest.mark.parametrize("handoff", [False, True])
+def test_resnet18_step_through_the_native_backend_on_a_shim(shim, handoff):
+    import horizonml_b200.models.resnet as R
+    s, nb, state = shim
+    g = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (16, 32, 32, 3), dtype=torch.uint8, generator=g)
+    labels = torch.randint(0, 10, (16,), generator=g)
+    old = R._BN_BWD_IN_DGRAD
+    try:
+        R._BN_BWD_IN_DGRAD = False
+        ref = _train_steps(lambda: R.resnet18(10, seed=0), images, labels, nb, state, native=False)
+        R._BN_BWD_IN_DGRAD = handoff
+        before = Counter(nb.LAUNCHES)
+        got = _train_steps(lambda: R.resnet18(10, seed=0), images, labels, nb, state, native=True)
+    finally:
+        R._BN_BWD_IN_DGRAD = old
+        state["native"] = False
+    assert not nb.FALLBACKS or sum(nb.FALLBACKS.values()) == 0, dict(nb.FALLBACKS)
+    assert abs(got[0][0] - ref[0][0]) < 2e-3 and abs(got[0][1] - ref[0][1]) < 5e-2, (got[0], ref[0])
+    assert _close(got[1], ref[1], 2e-2), "first-step gradient differs from the PyTorch-op backend"
+    assert _close(got[2], ref[2], 5e-2)           # (Adam's first steps are sign-like: near-zero gradients may flip)
+    per_step = {k: (nb.LAUNCHES[k] - before[k]) // 2 for k in nb.LAUNCHES}
+    # 20 convs (the stem through im2col + the 1x1 GEMM), 20 BatchNorms, pool, head, optimizer: every op went through a binding
+    assert s.calls["conv_fwd"] == 2 * 20 and s.calls["stem_pack"] == 2 and s.calls["conv_wgrad"] == 2 * 20
+    assert s.calls["im2col_small"] == 0                      # the forward's im2col matrix is reused by the stem's wgrad
+    assert s.calls["bn_act_fwd"] == 2 * 20 and s.calls["head_fwd_bwd"] == 2 and s.calls["adam_step"] >= 2
+    assert s.calls["u8_normalize"] == 2 and s.calls["maxpool_fwd"] == 2
+    if handoff:
+        assert s.calls["conv_dgrad_bnbwd"] == 2 * 15 and s.calls["maxpool_bwd_bn"] == 2 and s.calls["bn_act_bwd_res"] == 2 * 3
+        assert s.calls["conv_dgrad"] == 2 * (19 - 15) and s.calls["bn_act_bwd"] == 2 * (20 - 3) and s.calls["maxpool_bwd"] == 0
+        assert per_step["bn_act_bwd"] == 40 - 19
+    else:
+        assert s.calls["conv_dgrad"] == 2 * 19 and s.calls["bn_act_bwd"] == 2 * 20 and per_step["bn_act_bwd"] == 40
+        assert s.calls["conv_dgrad_bnbwd"] == 0 and s.calls["bn_act_bwd_res"] == 0 and s.calls["maxpool_bwd"] == 2
+
+
+@pytest.mark.parametrize("handoff", [False, True])
+def test_mobilenet_step_through_the_native_backend_on_a_shim(shim, handoff):
+    import horizonml_b200.models.resnet as R
+    from horizonml_b200.models.mobilenet import mobilenet_v2
+    s, nb, state = shim
+    g = torch.Generator().manual_seed(1)
+    images = torch.randint(0, 256, (8, 32, 32, 3), dtype=torch.uint8, generator=g)
+    labels = torch.randint(0, 10, (8,), generator=g)
+    old = R._BN_BWD_IN_DGRAD
+    try:
+        R._BN_BWD_IN_DGRAD = False
+        ref = _train_steps(lambda: mobilenet_v2(10, seed=0), images, labels, nb, state, native=False, steps=1)
+        R._BN_BWD_IN_DGRAD = handoff
+        got = _train_steps(lambda: mobilenet_v2(10, seed=0), images, labels, nb, state, native=True, steps=1)
+    finally:
+        R._BN_BWD_IN_DGRAD = old
+        state["native"] = False
+    assert sum(nb.FALLBACKS.values()) == 0, dict(nb.FALLBACKS)
+    assert abs(got[0][0] - ref[0][0]) < 5e-3, (got[0], ref[0])
+    assert _close(got[1], ref[1], 3e-2)
+    assert s.calls["dwconv_fwd"] == 17 and s.calls["dwconv_wgrad"] == 17 and s.calls["bn_act_fwd"] == 52
+    if handoff:
+        assert s.calls["dwconv_dgrad_bnbwd"] == 16 and s.calls["conv_dgrad_bnbwd"] == 34
+    else:
+        assert s.calls["dwconv_dgrad"] == 17 and s.calls["dwconv_dgrad_bnbwd"] == 0 and s.calls["conv_dgrad_bnbwd"] == 0
