@@ -7,7 +7,8 @@ can fail the run: every section reports what it could measure, or why not.
 
 * steps   — ResNet-18 and MobileNetV2 training step through the DP engine on one GPU (ms/step, images/s, launches/step)
 * handoff — the same steps with the BatchNorm-backward sums taken in the dgrad / pool-backward kernels (HZ_BN_BWD_IN_DGRAD)
-* conv    — batch-4096 convolutions: one-tile-per-CTA kernel vs cuDNN vs the persistent kernels (TFLOP/s, fraction of peak)"""
+* conv    — batch-4096 convolutions: one-tile-per-CTA kernel vs cuDNN vs the persistent kernels (TFLOP/s, fraction of peak)
+* bigbatch — ResNet-18 training step at batch 2048: default kernels, PyTorch ops, persistent kernels chosen by the wave rule"""
 import os
 import signal
 import subprocess
@@ -20,7 +21,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.late(order=11)]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("section,budget_s", [("steps", 90), ("handoff", 80), ("conv", 80)])
+@pytest.mark.parametrize("section,budget_s", [("steps", 90), ("handoff", 80), ("conv", 80), ("bigbatch", 90)])
 def test_round_end_perf_report(section, budget_s):
     proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "perf_probe.py"), section], cwd=ROOT,
                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)

@@ -5,6 +5,7 @@ kernel that traps cannot take the other sections' numbers with it.  Every result
     python tools/perf_probe.py steps      # ResNet-18 / MobileNetV2 training step through the DP engine (native, + PyTorch ops)
     python tools/perf_probe.py handoff    # the same steps with the BatchNorm-backward sums taken in dgrad / pool-backward kernels
     python tools/perf_probe.py conv       # batch-4096 convolutions: one-tile-per-CTA kernel, cuDNN, then the persistent kernels
+    python tools/perf_probe.py bigbatch   # ResNet-18 step at batch 2048: default kernels, PyTorch ops, persistent kernels (auto)
 
 CUDA events after warm-up, synchronised on both sides, a 256 MiB L2-flush write between timed launches."""
 import json
@@ -42,7 +43,7 @@ def timed(fn, flush, iters=8):
     return tot / iters * 1e3          # us
 
 
-def steps(variants):
+def steps(variants, batch=64, persist=0, timed_steps=30):
     import horizonml_b200.models.resnet as R
     from horizonml_b200.config import TrainConfig
     from horizonml_b200.ops import native_backend as nb
@@ -50,13 +51,15 @@ def steps(variants):
     from horizonml_b200.trainers.dp import DPEngine
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     g = torch.Generator().manual_seed(0)
-    xs = torch.randint(0, 256, (64, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
-    ys = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    xs = torch.randint(0, 256, (batch, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
+    ys = torch.randint(0, 10, (batch,), generator=g).to(DEV)
     for model, be, hand_off in variants:
         try:
             ops.set_backend(be)          # "torch": the same engine on PyTorch ops (cuDNN / ATen kernels) for scale
             R._BN_BWD_IN_DGRAD = hand_off
-            cfg = TrainConfig(strategy="data", world_size=1, batch_size=64, device="cuda", dtype="bf16", backend=be,
+            if be == "native":
+                nb.C.conv_set_persist(persist)      # baked into the captured graph: set before the engine's first step
+            cfg = TrainConfig(strategy="data", world_size=1, batch_size=batch, device="cuda", dtype="bf16", backend=be,
                               model=model, quiet=True)
             eng = DPEngine(cfg, Runtime(0, 1, torch.device(DEV), torch.bfloat16, be, "none"))
             launches = None
@@ -66,21 +69,25 @@ def steps(variants):
                 if i == 1:
                     launches = sum(nb.LAUNCHES.values()) - before        # (an eager warm-up step: python-side launches)
             torch.cuda.synchronize()
-            K = 30
+            K = timed_steps
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
             for a, b in evs:
                 flush.fill_(1)
                 a.record(); eng.step(xs, ys); b.record()
             torch.cuda.synchronize()
             ms = sum(a.elapsed_time(b) for a, b in evs) / K
-            report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "batch": 64, "ms_per_step": round(ms, 4),
-                            "images_per_s": round(64 / ms * 1e3), "launches_per_step": launches,
+            report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "batch": batch,
+                            "conv_persist_mode": persist, "ms_per_step": round(ms, 4),
+                            "images_per_s": round(batch / ms * 1e3), "launches_per_step": launches,
                             "graph": eng._graphed.graph is not None, "fallbacks": dict(nb.FALLBACKS)})
             eng._graphed.graph = None
         except Exception as e:  # noqa: BLE001
-            report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "error": repr(e)[:300]})
+            report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "batch": batch,
+                            "conv_persist_mode": persist, "error": repr(e)[:300]})
         finally:
             R._BN_BWD_IN_DGRAD = False
+            if be == "native":
+                nb.C.conv_set_persist(0)
 
 
 def conv():
@@ -140,5 +147,11 @@ if __name__ == "__main__":
         steps([("resnet18", "native", True), ("mobilenet", "native", True)])
     elif section == "conv":
         conv()
+    elif section == "bigbatch":
+        # the throughput regime (many waves of tiles per conv): one-tile-per-CTA kernels, then the persistent kernels
+        # where the dispatcher's wave rule picks them (mode -1 = auto), then the same on PyTorch ops for scale
+        steps([("resnet18", "native", False)], batch=2048, persist=0, timed_steps=10)
+        steps([("resnet18", "torch", False)], batch=2048, timed_steps=10)
+        steps([("resnet18", "native", False)], batch=2048, persist=-1, timed_steps=10)
     else:
         raise SystemExit(f"unknown section {section}")
