@@ -45,7 +45,8 @@ class ShimC:
                 raise AssertionError(f"C.{name}: argument list rejected by the binding: {str(e)[:400]}") from None
             except RuntimeError as e:
                 msg = str(e)
-                assert "CUDA tensor" in msg or "is_cuda" in msg, f"C.{name} failed before its device check: {msg[:300]}"
+                assert "CUDA tensor" in msg or "is_cuda" in msg or "non-CUDA DeviceType" in msg, \
+                    f"C.{name} failed before its device check: {msg[:300]}"
                 assert emu is not None, f"no emulation for C.{name}"
                 return emu(*args)
             assert emu is None, f"C.{name} accepted CPU tensors"      # pure host helpers only (channel_ok, ...)
@@ -290,3 +291,38 @@ def test_mobilenet_step_through_the_native_backend_on_a_shim(shim, handoff):
         assert s.calls["dwconv_dgrad_bnbwd"] == 16 and s.calls["conv_dgrad_bnbwd"] == 34
     else:
         assert s.calls["dwconv_dgrad"] == 17 and s.calls["dwconv_dgrad_bnbwd"] == 0 and s.calls["conv_dgrad_bnbwd"] == 0
+
+
+def test_dp_engine_steps_through_the_native_backend_on_a_shim(shim, monkeypatch):
+    """The data-parallel engine itself (trainers/dp.py: stem preparation, statistics arena per step, flat-bucket
+    gradients, fused Adam with the gradient-divergence bookkeeping, on-device step statistics) on the shimmed native
+    backend: same loss curve and parameters as the engine on the PyTorch-op backend."""
+    from horizonml_b200.config import TrainConfig
+    from horizonml_b200.ops import functional as fn
+    from horizonml_b200.trainers.common import Runtime
+    from horizonml_b200.trainers.dp import DPEngine
+    s, nb, state = shim
+    dev = torch.device("cpu")
+    monkeypatch.setattr(fn, "step_begin", lambda device=None: nb.step_begin(dev) if state["native"] else None)
+    monkeypatch.setattr(fn, "step_end", lambda: nb.step_end() if state["native"] else None)
+    g = torch.Generator().manual_seed(3)
+    xs = torch.randint(0, 256, (16, 32, 32, 3), dtype=torch.uint8, generator=g)
+    ys = torch.randint(0, 10, (16,), generator=g)
+    res = {}
+    for native in (False, True):
+        state["native"] = native
+        be = "native" if native else "torch"
+        cfg = TrainConfig(strategy="data", world_size=1, batch_size=16, device="cpu", dtype="bf16", backend=be,
+                          model="resnet18", quiet=True, cuda_graph=False)
+        eng = DPEngine(cfg, Runtime(0, 1, dev, BF16, be, "none"))
+        for _ in range(3):
+            eng.step(xs, ys)
+        res[native] = (eng.stats.buf.clone(), eng.flat.master.clone())
+    state["native"] = False
+    assert sum(nb.FALLBACKS.values()) == 0, dict(nb.FALLBACKS)
+    assert s.calls["stats_update"] == 3 and s.calls["u8_normalize"] == 3 and s.calls["adam_step"] >= 3
+    (st0, m0), (st1, m1) = res[False], res[True]
+    assert abs(float(st0[0] - st1[0])) < 0.1 * abs(float(st0[0])) and float(st0[2]) == float(st1[2]) == 48.0   # Σ loss, samples
+    assert float(st1[4]) == 2.0 and float(st1[3]) > 0           # gradient divergence accumulated over steps 2 and 3
+    assert abs(float(st1[3] - st0[3])) < 0.2 * float(st0[3])
+    assert _close(m1, m0, 5e-2)
