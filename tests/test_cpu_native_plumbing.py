@@ -326,3 +326,34 @@ def test_dp_engine_steps_through_the_native_backend_on_a_shim(shim, monkeypatch)
     assert float(st1[4]) == 2.0 and float(st1[3]) > 0           # gradient divergence accumulated over steps 2 and 3
     assert abs(float(st1[3] - st0[3])) < 0.2 * float(st0[3])
     assert _close(m1, m0, 5e-2)
+
+
+@pytest.mark.parametrize("model_name", ["resnet18", "mobilenet"])
+def test_eval_forward_through_the_native_backend_on_a_shim(shim, model_name):
+    """Inference path (running statistics, no autograd): conv / depthwise conv / BN-apply / pool bindings called with
+    training=False, logits equal to the PyTorch-op backend's."""
+    import horizonml_b200.models.resnet as R
+    from horizonml_b200 import ops
+    from horizonml_b200.models.flat import FlatParams
+    from horizonml_b200.models.mobilenet import mobilenet_v2
+    s, nb, state = shim
+    g = torch.Generator().manual_seed(5)
+    images = torch.randint(0, 256, (8, 32, 32, 3), dtype=torch.uint8, generator=g)
+    out = {}
+    for native in (False, True):
+        state["native"] = native
+        model = (R.resnet18(10, seed=0) if model_name == "resnet18" else mobilenet_v2(10, seed=0)).eval()
+        with torch.no_grad():
+            for n, b in model.named_buffers():            # non-trivial running statistics
+                if n.endswith("running_mean"):
+                    b.copy_(torch.linspace(-0.2, 0.2, b.numel()))
+                elif n.endswith("running_var"):
+                    b.copy_(torch.linspace(0.5, 1.5, b.numel()))
+        FlatParams(list(model.named_parameters()), torch.device("cpu"), BF16)
+        with torch.no_grad():
+            x = ops.stem_prepare(images.permute(0, 3, 1, 2), dtype=BF16)
+            out[native] = model(x).float()
+    state["native"] = False
+    assert sum(nb.FALLBACKS.values()) == 0, dict(nb.FALLBACKS)
+    assert s.calls["bn_act_fwd"] == (20 if model_name == "resnet18" else 52) and s.calls["channel_sums"] == 0
+    assert out[True].shape == (8, 10) and _close(out[True], out[False], 2e-2), (out[True] - out[False]).abs().max()
