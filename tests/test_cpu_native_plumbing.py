@@ -293,7 +293,8 @@ def test_mobilenet_step_through_the_native_backend_on_a_shim(shim, handoff):
         assert s.calls["dwconv_dgrad"] == 17 and s.calls["dwconv_dgrad_bnbwd"] == 0 and s.calls["conv_dgrad_bnbwd"] == 0
 
 
-def test_dp_engine_steps_through_the_native_backend_on_a_shim(shim, monkeypatch):
+@pytest.mark.parametrize("model_name", ["resnet18", "mobilenet"])
+def test_dp_engine_steps_through_the_native_backend_on_a_shim(shim, monkeypatch, model_name):
     """The data-parallel engine itself (trainers/dp.py: stem preparation, statistics arena per step, flat-bucket
     gradients, fused Adam with the gradient-divergence bookkeeping, on-device step statistics) on the shimmed native
     backend: same loss curve and parameters as the engine on the PyTorch-op backend."""
@@ -313,7 +314,8 @@ def test_dp_engine_steps_through_the_native_backend_on_a_shim(shim, monkeypatch)
         state["native"] = native
         be = "native" if native else "torch"
         cfg = TrainConfig(strategy="data", world_size=1, batch_size=16, device="cpu", dtype="bf16", backend=be,
-                          model="resnet18", quiet=True, cuda_graph=False)
+                          model=model_name, quiet=True, cuda_graph=False)
+        torch.manual_seed(9)                                 # (MobileNetV2's dropout mask)
         eng = DPEngine(cfg, Runtime(0, 1, dev, BF16, be, "none"))
         for _ in range(3):
             eng.step(xs, ys)
