@@ -13,7 +13,15 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+_REAL_OUT_FD = [None]
+
+
 def pytest_configure(config):
+    if _REAL_OUT_FD[0] is None:
+        try:
+            _REAL_OUT_FD[0] = os.dup(1)        # (output capture is suspended here: this is the real stdout — the
+        except OSError:                        #  watchdog below has to write while fd 1 points into a capture file)
+            pass
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
     config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
     config.addinivalue_line("markers", "slow: multi-process CPU tests")
@@ -34,10 +42,110 @@ def pytest_sessionstart(session):
     _SESSION_T0[0] = time.time()
 
 
-def pytest_runtest_setup(item):
+_EXIT = {"status": None, "late_ran": False}
+# ---- watchdog of the late tier: a kernel that never ran on hardware and spins forever (a mismatched barrier — the mbarrier
+# and peer-flag waits are bounded and trap) would block this process inside a CUDA call until an outer harness kills the
+# whole run, verdict of the verified tier included.  A thread watches the running late test; past its limit it prints the
+# outcome so far and leaves with the status the verified tier has earned.
+_LATE_TEST_LIMIT_S = float(os.environ.get("HZ_LATE_TEST_LIMIT_S", "200"))
+_WATCH = {"node": None, "t0": 0.0, "limit": 0.0, "thread": None, "counts": {}, "verified_failed": 0}
+
+
+def _watchdog_loop():
     import time
-    if "late" in item.keywords and _SESSION_T0[0] is not None and time.time() - _SESSION_T0[0] > _LATE_BUDGET_S:
-        pytest.skip(f"late tier: session time budget of {_LATE_BUDGET_S:.0f} s used up (HZ_LATE_BUDGET_S)")
+    while True:
+        time.sleep(0.5)
+        node, t0, limit = _WATCH["node"], _WATCH["t0"], _WATCH["limit"]
+        if node is None or time.time() - t0 <= limit:
+            continue
+        status = 1 if _WATCH["verified_failed"] else 0
+        c = _WATCH["counts"]
+        line = ", ".join(f"{v} {k}" for k, v in sorted(c.items()) if v)
+        msg = (f"\nlate tier: {node} has not returned after {limit:.0f} s — a kernel that had never run on hardware is "
+               f"presumably spinning.  Outcome up to this test: {line or 'nothing run'}.  Leaving with exit status {status} "
+               "(decided by the hardware-verified tests, all of which had finished).\n")
+        try:
+            if _REAL_OUT_FD[0] is not None:
+                os.write(_REAL_OUT_FD[0], msg.encode())
+            else:
+                sys.__stdout__.write(msg)
+                sys.__stdout__.flush()
+        finally:
+            os._exit(status)
+
+
+def pytest_runtest_setup(item):
+    import threading
+    import time
+    if "late" in item.keywords:
+        if _SESSION_T0[0] is not None and time.time() - _SESSION_T0[0] > _LATE_BUDGET_S:
+            pytest.skip(f"late tier: session time budget of {_LATE_BUDGET_S:.0f} s used up (HZ_LATE_BUDGET_S)")
+        _EXIT["late_ran"] = True
+        m = item.get_closest_marker("late")
+        _WATCH["limit"] = float(m.kwargs.get("limit_s", _LATE_TEST_LIMIT_S)) if m is not None else _LATE_TEST_LIMIT_S
+        _WATCH["t0"] = time.time()
+        _WATCH["node"] = item.nodeid
+        if _WATCH["thread"] is None:
+            _WATCH["thread"] = threading.Thread(target=_watchdog_loop, name="late-tier-watchdog", daemon=True)
+            _WATCH["thread"].start()
+
+
+def pytest_runtest_teardown(item, nextitem):
+    _WATCH["node"] = None
+
+
+def pytest_runtest_logreport(report):
+    if report.when == "call" or (report.when == "setup" and report.outcome != "passed"):
+        key = report.outcome
+        if hasattr(report, "wasxfail"):
+            key = "xpassed" if report.outcome == "passed" else "xfailed"
+        _WATCH["counts"][key] = _WATCH["counts"].get(key, 0) + 1
+        if key == "failed":
+            _WATCH["verified_failed"] += 1
+
+
+def pytest_sessionfinish(session, exitstatus):
+    _WATCH["node"] = None
+    _EXIT["status"] = int(exitstatus)
+
+
+def _cuda_context_broken() -> bool:
+    if os.environ.get("HZ_LATE_FORCE_HARD_EXIT", "0") == "1":          # (test hook of tests/test_cpu_round2.py)
+        return True
+    try:
+        import torch
+        if not torch.cuda.is_available() or not torch.cuda.is_initialized():
+            return False
+        torch.cuda.synchronize()
+        return False
+    except Exception:  # noqa: BLE001  (a sticky error: illegal address / trap raised by a kernel of the late tier)
+        return True
+
+
+@pytest.hookimpl(trylast=True)
+def pytest_unconfigure(config):
+    """A late-tier kernel that faults leaves a sticky CUDA error behind: the remaining late tests then fail fast (XFAIL),
+    but the interpreter's teardown (allocator, events, graphs freeing device objects in a dead context) can abort the
+    process AFTER pytest has printed its verdict, turning the exit code of a green verified tier into SIGABRT.  In that
+    one situation leave without teardown, with the exit status pytest has just computed."""
+    if not _EXIT["late_ran"] or _EXIT["status"] is None or not _cuda_context_broken():
+        return
+    tr = config.pluginmanager.get_plugin("terminalreporter")
+    msg = ("late tier: a kernel that had never run on hardware left the CUDA context unusable; leaving without interpreter "
+           f"teardown, exit status {_EXIT['status']} as computed from the test outcomes")
+    try:
+        if tr is not None:
+            tr.write_line(msg)
+            tr.flush()
+        else:
+            sys.stdout.write(msg + "\n")
+        for f in (sys.stdout, sys.stderr, sys.__stdout__, sys.__stderr__):      # os._exit drops unflushed buffers
+            try:
+                f.flush()
+            except Exception:  # noqa: BLE001
+                pass
+    finally:
+        os._exit(_EXIT["status"])
 
 
 def pytest_collection_modifyitems(config, items):

@@ -363,3 +363,33 @@ def test_late_tier_harness(tmp_path):
     assert r.returncode != 0 and "1 failed" in r.stdout and "3 passed" in r.stdout, r.stdout
     r = run({"HZ_LATE_BUDGET_S": "0.1"})
     assert r.returncode == 0 and "1 passed" in r.stdout and "3 skipped" in r.stdout, r.stdout
+    # a late kernel that leaves the CUDA context unusable: the process leaves without interpreter teardown, with the
+    # status and the complete summary pytest has produced (stdout is a pipe here: nothing may be lost in a buffer)
+    r = run({"HZ_LATE_FORCE_HARD_EXIT": "1"})
+    assert r.returncode == 0 and "2 xpassed" in r.stdout and "1 xfailed" in r.stdout and "without interpreter teardown" in r.stdout, r.stdout
+    r = run({"HZ_LATE_FORCE_HARD_EXIT": "1", "HZ_LATE_STRICT": "1"})
+    assert r.returncode == 1 and "1 failed" in r.stdout and "without interpreter teardown" in r.stdout, r.stdout
+    # a late test that never returns (a spinning kernel): the watchdog reports the outcome so far and leaves with the
+    # status of the verified tier — 0 when it was green, 1 when one of its tests had failed
+    (d / "test_demo.py").write_text(
+        "import time, pytest\n"
+        "def test_plain(): pass\n"
+        "@pytest.mark.late\ndef test_l0(): assert True\n"
+        "@pytest.mark.late(order=3)\ndef test_hang(): time.sleep(60)\n"
+        "@pytest.mark.late(order=4)\ndef test_after(): pass\n")
+    r = run({"HZ_LATE_TEST_LIMIT_S": "1"})
+    assert r.returncode == 0 and "test_hang has not returned" in r.stdout and "1 passed" in r.stdout and "1 xpassed" in r.stdout, \
+        (r.returncode, r.stdout, r.stderr)
+    (d / "test_demo.py").write_text(
+        "import time, pytest\n"
+        "def test_plain(): assert False\n"
+        "@pytest.mark.late(order=3)\ndef test_hang(): time.sleep(60)\n")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(d), "-q", "-p", "no:cacheprovider"], cwd=str(d),
+                       env=dict(os.environ, HZ_LATE_TEST_LIMIT_S="1"), capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "test_hang has not returned" in r.stdout and "1 failed" in r.stdout, (r.returncode, r.stdout)
+    # a per-test limit on the marker overrides the default
+    (d / "test_demo.py").write_text(
+        "import time, pytest\n"
+        "@pytest.mark.late(order=3, limit_s=30)\ndef test_slow(): time.sleep(3)\n")
+    r = run({"HZ_LATE_TEST_LIMIT_S": "1"})
+    assert r.returncode == 0 and "1 xpassed" in r.stdout and "has not returned" not in r.stdout, r.stdout

@@ -52,7 +52,7 @@ def test_memcheck_clean_on_elementwise_kernels():
 
 
 @pytest.mark.gpu
-@pytest.mark.late(order=14)
+@pytest.mark.late(order=14, limit_s=700)
 @pytest.mark.skipif(os.environ.get("HZ_TEST_SANITIZER", "0") != "1", reason="set HZ_TEST_SANITIZER=1 (several minutes)")
 def test_memcheck_clean_on_a_tcgen05_convolution():
     _memcheck("(test_conv_fwd_tcgen05 or test_conv_dgrad or test_conv_wgrad_tcgen05) and cfg0", ["tests/test_gpu_kernels.py"], 600)
