@@ -76,9 +76,12 @@ def steps(variants, batch=64, persist=0, timed_steps=30):
                 a.record(); eng.step(xs, ys); b.record()
             torch.cuda.synchronize()
             ms = sum(a.elapsed_time(b) for a, b in evs) / K
+            st = eng.stats.buf.float().cpu()           # [sum of losses, correct, samples, ...] over all steps run above
             report("step", {"model": model, "backend": be, "bn_sums_in_dgrad": hand_off, "batch": batch,
                             "conv_persist_mode": persist, "ms_per_step": round(ms, 4),
                             "images_per_s": round(batch / ms * 1e3), "launches_per_step": launches,
+                            "mean_loss": round(float(st[0] / max(float(st[5]), 1.0)), 4),
+                            "train_acc": round(float(st[1] / max(float(st[2]), 1.0)), 4),
                             "graph": eng._graphed.graph is not None, "fallbacks": dict(nb.FALLBACKS)})
             eng._graphed.graph = None
         except Exception as e:  # noqa: BLE001
@@ -114,6 +117,16 @@ def conv():
             row = {"layer": name, "batch": B, "kernel": tag, "gflop": round(flops / 1e9, 1)}
             try:
                 nb.C.conv_set_persist(mode)
+                if mode != 0:                      # numerics next to the timing: same operands through the default kernels
+                    y1, s1 = nb.conv_fwd(x, w, 1, 1, True)
+                    d1 = nb.conv_dgrad(dy, w, x.shape, 1, 1)
+                    nb.C.conv_set_persist(0)
+                    y0, s0 = nb.conv_fwd(x, w, 1, 1, True)
+                    d0 = nb.conv_dgrad(dy, w, x.shape, 1, 1)
+                    nb.C.conv_set_persist(mode)
+                    rel = lambda a, b: float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))   # noqa: E731
+                    row.update(fwd_rel_err_vs_default=round(rel(y1, y0), 6), dgrad_rel_err_vs_default=round(rel(d1, d0), 6),
+                               bn_sums_rel_err_vs_default=round(rel(s1.view(-1), s0.view(-1)), 6))
                 tf = timed(lambda: nb.conv_fwd(x, w, 1, 1, True), flush)
                 td = timed(lambda: nb.conv_dgrad(dy, w, x.shape, 1, 1), flush)
                 row.update(fwd_us=round(tf, 1), fwd_tflops=round(flops / tf / 1e6, 1), dgrad_us=round(td, 1),
