@@ -8,7 +8,9 @@ import sys
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+# `late`: these wrappers have never been executed as pytest items (every recorded GPU test run was on a 1-GPU box, where the
+# module is skipped); the programs they start were run by hand at 2 / 4 / 8 GPUs (tools/run_gpu_suite.sh, profiles/r2/).
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu, pytest.mark.late(order=5, limit_s=650)]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
