@@ -393,3 +393,9 @@ def test_late_tier_harness(tmp_path):
         "@pytest.mark.late(order=3, limit_s=30)\ndef test_slow(): time.sleep(3)\n")
     r = run({"HZ_LATE_TEST_LIMIT_S": "1"})
     assert r.returncode == 0 and "1 xpassed" in r.stdout and "has not returned" not in r.stdout, r.stdout
+    # measurements published by late tests as HZPERF warnings are repeated as plain lines in a section of their own
+    (d / "test_demo.py").write_text(
+        "import warnings, pytest\n"
+        "@pytest.mark.late(order=11)\ndef test_report(): warnings.warn('HZPERF step {\"ms\": 0.5}', UserWarning)\n")
+    r = run({})
+    assert r.returncode == 0 and "HZPERF: device-timed measurements" in r.stdout and '\nHZPERF step {"ms": 0.5}' in r.stdout, r.stdout
