@@ -1,6 +1,6 @@
 """Pipeline and tensor-parallel engines on the shimmed native backend — run as a script by
 tests/test_cpu_native_plumbing.py (own processes: gloo process group of WORLD ranks, one spawned process per rank).
-    python tests/helpers_shim_engines.py pp|tp WORLD [handoff]
+    python tests/helpers_shim_engines.py dp|dpz|pp|tp WORLD [handoff]
 Prints one JSON line per rank: per-backend step statistics, fallbacks, calls per binding."""
 import json
 import os
@@ -43,13 +43,21 @@ def worker(rank: int, world: int, port: int, which: str, handoff: bool, q):
         R._BN_BWD_IN_DGRAD = handoff and native
         be = "native" if native else "torch"
         kw = dict(world_size=world, batch_size=16, device="cpu", dtype="bf16", backend=be, quiet=True, cuda_graph=False)
-        if which == "pp":
+        if which in ("dp", "dpz"):
+            from horizonml_b200.trainers.dp import DPEngine
+            xs_r, ys_r = xs[rank::world], ys[rank::world]                # this rank's shard of the batch
+            kw["batch_size"] = xs_r.shape[0]
+            cfg = TrainConfig(strategy="data", zero1=(which == "dpz"), zero1_impl="fused", **kw)
+            eng = DPEngine(cfg, Runtime(rank, world, dev, BF16, be, "gloo"))
+            for _ in range(2):
+                eng.step(xs_r, ys_r)
+        elif which == "pp":
             from horizonml_b200.trainers.pp import PPEngine
             eng = PPEngine(TrainConfig(strategy="layer", microbatches=4, **kw), Runtime(rank, world, dev, BF16, be, "gloo"))
         else:
             from horizonml_b200.trainers.tp import TPEngine
             eng = TPEngine(TrainConfig(strategy="tensor", **kw), Runtime(rank, world, dev, BF16, be, "gloo"))
-        for _ in range(2):
+        for _ in range(2 if which in ("pp", "tp") else 0):
             eng.step(xs, ys)
         out[be] = [float(v) for v in eng.stats.buf.tolist()]
         dist.barrier()

@@ -361,10 +361,11 @@ def test_eval_forward_through_the_native_backend_on_a_shim(shim, model_name):
     assert out[True].shape == (8, 10) and _close(out[True], out[False], 2e-2), (out[True] - out[False]).abs().max()
 
 
-@pytest.mark.parametrize("which,world,handoff", [("pp", 1, False), ("pp", 2, True), ("tp", 1, True), ("tp", 2, False),
-                                                 ("tp", 2, True)])
-def test_pipeline_and_tensor_parallel_engines_on_a_shim(which, world, handoff):
-    """trainers/pp.py (1F1B runner, 4 micro-batches, activations / gradients over gloo p2p at two stages) and trainers/tp.py
+@pytest.mark.parametrize("which,world,handoff", [("dp", 2, False), ("dpz", 2, True), ("pp", 1, False), ("pp", 2, True),
+                                                 ("tp", 1, True), ("tp", 2, False), ("tp", 2, True)])
+def test_parallel_engines_on_a_shim(which, world, handoff):
+    """trainers/dp.py at two ranks (bucketed gradient all-reduce over gloo; `dpz`: ZeRO-1 in its torch.distributed form),
+    trainers/pp.py (1F1B runner, 4 micro-batches, activations / gradients over gloo p2p at two stages) and trainers/tp.py
     (channel-split layer3/4 blocks and the tensor-parallel head on their non-fused paths: 128- / 256-channel shards at
     world 2) with every op on the shimmed native backend, one process per rank: same step statistics (loss, correct,
     samples, gradient divergence) as the same engine on the PyTorch-op backend, no fallback — with and without the
@@ -390,7 +391,7 @@ def test_pipeline_and_tensor_parallel_engines_on_a_shim(which, world, handoff):
     t, n = last["torch"], last["native"]
     assert abs(t[0] - n[0]) < 0.02 * abs(t[0]) and t[1:3] == n[1:3] and t[4:] == n[4:], (t, n)     # loss; correct, samples; counts
     assert abs(t[3] - n[3]) < 0.1 * max(t[3], 1e-6), (t, n)                                       # gradient divergence
-    layers = 20 * passes * (world if which == "tp" else 1)      # PP: the 20 convs are spread over the stages
+    layers = 20 * passes * (1 if which == "pp" else world)      # PP: the 20 convs are spread over the stages
     assert total["conv_fwd"] == layers and total["conv_wgrad"] == layers and total["bn_act_fwd"] == layers, total
     if handoff:
         assert total.get("conv_dgrad_bnbwd", 0) >= 8 * passes, total
