@@ -7,6 +7,7 @@ can fail the run: every section reports what it could measure, or why not.
 
 * steps   — ResNet-18 and MobileNetV2 training step through the DP engine on one GPU (ms/step, images/s, launches/step)
 * handoff — the same steps with the BatchNorm-backward sums taken in the dgrad / pool-backward kernels (HZ_BN_BWD_IN_DGRAD)
+* bench   — bench.py --gpus 1 (its own timing rules and e2e arm) on the default path and with the hand-offs
 * conv    — batch-4096 convolutions: one-tile-per-CTA kernel vs cuDNN vs the persistent kernels (TFLOP/s, fraction of peak)
 * bigbatch — ResNet-18 training step at batch 2048: default kernels, PyTorch ops, persistent kernels chosen by the wave rule"""
 import os
@@ -21,7 +22,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.late(order=11)]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("section,budget_s", [("steps", 90), ("handoff", 80), ("conv", 80), ("bigbatch", 90)])
+@pytest.mark.parametrize("section,budget_s", [("steps", 90), ("handoff", 80), ("bench", 120), ("conv", 80), ("bigbatch", 90)])
 def test_round_end_perf_report(section, budget_s):
     proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "perf_probe.py"), section], cwd=ROOT,
                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)

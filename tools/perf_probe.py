@@ -5,6 +5,7 @@ kernel that traps cannot take the other sections' numbers with it.  Every result
     python tools/perf_probe.py steps      # ResNet-18 / MobileNetV2 training step through the DP engine (native, + PyTorch ops)
     python tools/perf_probe.py handoff    # the same steps with the BatchNorm-backward sums taken in dgrad / pool-backward kernels
     python tools/perf_probe.py conv       # batch-4096 convolutions: one-tile-per-CTA kernel, cuDNN, then the persistent kernels
+    python tools/perf_probe.py bench      # bench.py --gpus 1 on the default path and with HZ_BN_BWD_IN_DGRAD=1
     python tools/perf_probe.py bigbatch   # ResNet-18 step at batch 2048: default kernels, PyTorch ops, persistent kernels (auto)
 
 CUDA events after warm-up, synchronised on both sides, a 256 MiB L2-flush write between timed launches."""
@@ -152,6 +153,27 @@ def conv():
     kernels(1, "persistent_wide")
 
 
+def bench_ab():
+    """bench.py itself (its timing rules: warm-up, L2 flush, device events, clock sampling, e2e arm) on the default path
+    and with the BatchNorm hand-offs: the A/B in the judged harness."""
+    import subprocess
+    for flag in ("0", "1"):
+        row = {"HZ_BN_BWD_IN_DGRAD": int(flag)}
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--gpus", "1", "--steps", "100", "--warmup", "10"],
+                               cwd=ROOT, env=dict(os.environ, HZ_BN_BWD_IN_DGRAD=flag), capture_output=True, text=True, timeout=100)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{") and '"metric"' in ln]
+            if r.returncode != 0 or not line:
+                row["error"] = (r.stderr or r.stdout)[-300:].replace("\n", " | ")
+            else:
+                d = json.loads(line[-1])
+                row.update(images_per_s=d.get("value"), ms_per_step=d.get("ms_per_step"), gpu_launches=d.get("gpu_launches"),
+                           e2e_images_per_s=(d.get("e2e") or {}).get("value"), clocks=d.get("clocks"), steps=d.get("steps"))
+        except Exception as e:  # noqa: BLE001
+            row["error"] = repr(e)[:300]
+        report("bench", row)
+
+
 if __name__ == "__main__":
     section = sys.argv[1] if len(sys.argv) > 1 else "steps"
     if section == "steps":
@@ -160,6 +182,8 @@ if __name__ == "__main__":
         steps([("resnet18", "native", True), ("mobilenet", "native", True)])
     elif section == "conv":
         conv()
+    elif section == "bench":
+        bench_ab()
     elif section == "bigbatch":
         # the throughput regime (many waves of tiles per conv): one-tile-per-CTA kernels, then the persistent kernels
         # where the dispatcher's wave rule picks them (mode -1 = auto), then the same on PyTorch ops for scale
