@@ -34,7 +34,7 @@ def pytest_configure(config):
 _SESSION_T0 = [None]
 # wall-clock budget of the whole test session after which the remaining `late` tests are skipped (they are informational;
 # a run that an outer harness kills for taking too long would lose the verified tier's summary line as well)
-_LATE_BUDGET_S = float(os.environ.get("HZ_LATE_BUDGET_S", "420"))
+_LATE_BUDGET_S = float(os.environ.get("HZ_LATE_BUDGET_S", "300"))
 
 
 def pytest_sessionstart(session):
@@ -47,7 +47,7 @@ _EXIT = {"status": None, "late_ran": False}
 # and peer-flag waits are bounded and trap) would block this process inside a CUDA call until an outer harness kills the
 # whole run, verdict of the verified tier included.  A thread watches the running late test; past its limit it prints the
 # outcome so far and leaves with the status the verified tier has earned.
-_LATE_TEST_LIMIT_S = float(os.environ.get("HZ_LATE_TEST_LIMIT_S", "200"))
+_LATE_TEST_LIMIT_S = float(os.environ.get("HZ_LATE_TEST_LIMIT_S", "150"))
 _WATCH = {"node": None, "t0": 0.0, "limit": 0.0, "thread": None, "counts": {}, "verified_failed": 0}
 
 

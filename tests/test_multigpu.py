@@ -10,7 +10,7 @@ import torch
 
 # `late`: these wrappers have never been executed as pytest items (every recorded GPU test run was on a 1-GPU box, where the
 # module is skipped); the programs they start were run by hand at 2 / 4 / 8 GPUs (tools/run_gpu_suite.sh, profiles/r2/).
-pytestmark = [pytest.mark.gpu, pytest.mark.multigpu, pytest.mark.late(order=5, limit_s=650)]
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu, pytest.mark.late(order=15, limit_s=650)]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -65,7 +65,7 @@ def test_hybrid_mesh_on_gpus(tmp_path):
     assert float(last["loss"].iloc[0]) < 0.5 and float(last["accuracy"].iloc[0]) > 85.0
 
 
-@pytest.mark.late(order=5, limit_s=650)      # (the tool was run by hand at 2/4/8 GPUs — profiles/r2/equiv_*.json —, this wrapper never)
+@pytest.mark.late(order=15, limit_s=650)     # (the tool was run by hand at 2/4/8 GPUs — profiles/r2/equiv_*.json —, this wrapper never)
 @pytest.mark.parametrize("mode", ["dp", "pp"])
 def test_strategy_equivalence_native_kernels(tmp_path, mode):
     """DP(W) == mean of the shard gradients, PP(S stages, 4 micro-batches, graphed + overlapped 1F1B) == the dense model
@@ -85,7 +85,7 @@ def test_strategy_equivalence_native_kernels(tmp_path, mode):
         assert res["graphed"] and res["overlapped"]
 
 
-@pytest.mark.late(order=3, limit_s=650)
+@pytest.mark.late(order=15, limit_s=650)
 def test_zero1_fused_kernel_trains_on_gpus(tmp_path):
     """`data_parallel_train.py --zero1` on real peers: one zero1_kernel per bucket (no NCCL collective, no separate
     optimizer pass) must train like the replicated optimizer; the run summary records which implementation ran."""
