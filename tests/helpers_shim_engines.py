@@ -77,12 +77,22 @@ def main(which: str, world: int, handoff: bool):
     procs = [ctx.Process(target=worker, args=(r, world, port, which, handoff, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=540) for _ in procs]
+    import queue
+    import time
+    res, t0 = [], time.time()
+    while len(res) < world and time.time() - t0 < 540:
+        try:
+            res.append(q.get(timeout=2))
+        except queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):          # a rank died: do not wait for its result
+                break
     for p in procs:
-        p.join(60)
+        p.join(30)
+        if p.is_alive():
+            p.terminate()
     for o in sorted(res, key=lambda o: o["rank"]):
         print("SHIM_ENGINE " + json.dumps(o), flush=True)
-    return 0 if all(p.exitcode == 0 for p in procs) else 1
+    return 0 if (len(res) == world and all(p.exitcode == 0 for p in procs)) else 1
 
 
 if __name__ == "__main__":
