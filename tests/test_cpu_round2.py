@@ -399,3 +399,25 @@ def test_late_tier_harness(tmp_path):
         "@pytest.mark.late(order=11)\ndef test_report(): warnings.warn('HZPERF step {\"ms\": 0.5}', UserWarning)\n")
     r = run({})
     assert r.returncode == 0 and "HZPERF: device-timed measurements" in r.stdout and '\nHZPERF step {"ms": 0.5}' in r.stdout, r.stdout
+
+
+def test_late_gpu_tests_dry_run():
+    """The GPU test modules written after the last GPU access have never been executed: run their CODE here, on CPU, with
+    the extension replaced by the shim of tests/test_cpu_native_plumbing.py (HZ_GPU_TESTS_DRYRUN=1, tests/conftest.py) —
+    every helper, parametrisation, tuple unpacking, launch-count and fallback assertion runs, numerics are the oracle's.  A
+    typo in one of these tests would otherwise turn the only hardware run it gets into an XFAIL that says nothing about
+    the kernel."""
+    import subprocess
+    import sys
+    from horizonml_b200.ops import _ext
+    if _ext.load(required=False) is None:
+        pytest.skip("extension not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = ["tests/test_gpu_bn_handoff.py", "tests/test_gpu_blocks.py", "tests/test_gpu_mobilenet.py", "tests/test_gpu_persist.py"]
+    env = dict(os.environ, HZ_GPU_TESTS_DRYRUN="1", HZ_LATE_STRICT="1", HZ_LATE_BUDGET_S="3600", HZ_LATE_TEST_LIMIT_S="600")
+    r = subprocess.run([sys.executable, "-m", "pytest", *files, "-q", "-p", "no:cacheprovider"], cwd=root, env=env,
+                       capture_output=True, text=True, timeout=1500)
+    tail = r.stdout[-1500:]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail and "error" not in tail.lower(), tail + r.stderr[-1500:]
+    n = int(tail.rsplit(" passed", 1)[0].split()[-1])
+    assert n >= 200, tail
