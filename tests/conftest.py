@@ -131,6 +131,8 @@ def pytest_terminal_summary(terminalreporter, exitstatus, config):
 def _cuda_context_broken() -> bool:
     if os.environ.get("HZ_LATE_FORCE_HARD_EXIT", "0") == "1":          # (test hook of tests/test_cpu_round2.py)
         return True
+    if "torch" not in sys.modules:         # nothing in this process can have touched a device
+        return False
     try:
         import torch
         if not torch.cuda.is_available() or not torch.cuda.is_initialized():
@@ -192,9 +194,11 @@ def _install_dryrun_shim():
 
 
 def pytest_collection_modifyitems(config, items):
-    import torch
-    has_gpu = torch.cuda.is_available()
-    ngpu = torch.cuda.device_count() if has_gpu else 0
+    has_gpu, ngpu = False, 0
+    if _DRYRUN or any("gpu" in item.keywords or "multigpu" in item.keywords for item in items):
+        import torch                       # (only when a collected test can need a device: the import costs seconds)
+        has_gpu = torch.cuda.is_available()
+        ngpu = torch.cuda.device_count() if has_gpu else 0
     if _DRYRUN and not has_gpu:
         _install_dryrun_shim()
         for mod in list(sys.modules.values()):                 # (helpers imported from other test modules too)
