@@ -193,7 +193,7 @@ def shim(monkeypatch):
     return s, nb, state
 
 
-def _train_steps(make_model, images, labels, nb, state, native, steps=2):
+def _train_steps(make_model, images, labels, nb, state, native, steps=2, arena=True):
     """`steps` optimizer steps of model.forward_loss through FlatParams / FlatAdam; returns (losses, first-step flat
     gradient, final master parameters)."""
     from horizonml_b200 import ops
@@ -211,13 +211,13 @@ def _train_steps(make_model, images, labels, nb, state, native, steps=2):
     losses, g0 = [], None
     for it in range(steps):
         x = ops.stem_prepare(images.permute(0, 3, 1, 2), dtype=BF16)
-        if native:
+        if native and arena:
             nb.step_begin(dev)
         flat.begin_step()
         loss, _ = model.forward_loss(x, labels)
         loss.backward()
         ops.join_side()
-        if native:
+        if native and arena:
             nb.step_end()
         if it == 0:
             g0 = flat.grad.clone()
@@ -397,3 +397,20 @@ def test_parallel_engines_on_a_shim(which, world, handoff):
         assert total.get("conv_dgrad_bnbwd", 0) >= 8 * passes, total
     else:
         assert total.get("conv_dgrad_bnbwd", 0) == 0 and total.get("bn_act_bwd_res", 0) == 0, total
+
+
+def test_smoke_sequence_without_the_statistics_arena_on_a_shim(shim):
+    """__graft_entry__.smoke() steps the model without ops.step_begin(): no pre-zeroed statistics arena, every binding gets
+    None for its scratch / pre-zeroed buffers and has to allocate and clear its own — same gradients as with the arena."""
+    import horizonml_b200.models.resnet as R
+    s, nb, state = shim
+    g = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (16, 32, 32, 3), dtype=torch.uint8, generator=g)
+    labels = torch.randint(0, 10, (16,), generator=g)
+    try:
+        ref = _train_steps(lambda: R.resnet18(10, seed=0), images, labels, nb, state, native=False)
+        got = _train_steps(lambda: R.resnet18(10, seed=0), images, labels, nb, state, native=True, arena=False)
+    finally:
+        state["native"] = False
+    assert sum(nb.FALLBACKS.values()) == 0 and not nb.ARENA.active
+    assert abs(got[0][0] - ref[0][0]) < 2e-3 and _close(got[1], ref[1], 2e-2) and _close(got[2], ref[2], 5e-2)
