@@ -421,3 +421,72 @@ def test_late_gpu_tests_dry_run():
     assert r.returncode == 0 and " passed" in tail and "failed" not in tail and "error" not in tail.lower(), tail + r.stderr[-1500:]
     n = int(tail.rsplit(" passed", 1)[0].split()[-1])
     assert n >= 200, tail
+
+
+@pytest.mark.parametrize("knows_tensor_metric", [True, False])
+def test_ncu_report_against_a_fake_ncu(tmp_path, monkeypatch, knows_tensor_metric):
+    """tests/test_gpu_ncu_report.py end to end with a stand-in `ncu` on PATH that prints a raw-page CSV (header, units row,
+    one row per launch): aggregation per kernel, time-weighted utilisations, the HZPERF lines — and the fallback to the
+    base metric list when the profiler refuses the optional tensor-pipe metric."""
+    import json
+    import stat
+    import sys
+    import warnings
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_gpu_ncu_report as T
+    fake = tmp_path / "ncu"
+    fake.write_text(f"""#!{sys.executable}
+import sys
+metrics = sys.argv[sys.argv.index("--metrics") + 1].split(",")
+if {not knows_tensor_metric!r} and any("pipe_tensor" in m for m in metrics):
+    print("==ERROR== Failed to find metric sm__pipe_tensor_cycles_active"); sys.exit(1)
+print("==PROF== Connected to process 1")
+cols = ["ID", "Process ID", "Process Name", "Host Name", "Kernel Name", "Context", "Stream", "Block Size", "Grid Size", "Device", "CC"] + metrics
+print(",".join('"%s"' % c for c in cols))
+print(",".join('""' for _ in cols))
+kern = [("void hz::igemm_kernel<64, false, false>(hz::AMaps)", 4000.0), ("hz::bn_act_fwd_kernel<false>(const __nv_bfloat16*)", 1500.0),
+        ("void hz::igemm_kernel<64, false, false>(hz::AMaps)", 6000.0)] * 20
+for i, (k, ns) in enumerate(kern):
+    vals = []
+    for m in metrics:
+        vals.append({{"gpu__time_duration.sum": ns, "launch__registers_per_thread": 96}}.get(m, 10.0 + (i % 3)))
+    row = [str(i), "1", "python", "box", k, "1", "7", "(128, 1, 1)", "(64, 1, 1)", "0", "10.0"] + ["%.1f" % v for v in vals]
+    print(",".join('"%s"' % c for c in row))
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        T.test_ncu_profile_of_one_training_step()
+    lines = [str(w.message) for w in rec if str(w.message).startswith("HZPERF ncu")]
+    total = json.loads([ln for ln in lines if ln.startswith("HZPERF ncu_total ")][0].split(" ", 2)[2])
+    assert total["kernels"] == 60 and total["distinct"] == 2 and abs(total["sum_of_durations_us"] - 230.0) < 0.5
+    rows = [json.loads(ln.split(" ", 2)[2]) for ln in lines if ln.startswith("HZPERF ncu ")]
+    conv = [r for r in rows if r["kernel"].startswith("igemm_kernel")][0]
+    assert conv["launches"] == 40 and abs(conv["share"] - 200.0 / 230.0) < 1e-3 and conv["regs"] == 96
+    assert (conv["tensor_pipe_pct"] is not None) == knows_tensor_metric
+
+
+def test_ncu_summary_tool_reads_a_raw_page_csv(tmp_path):
+    """tools/ncu_summary.py (the offline reader of .ncu-rep captures, `ncu -i … --page raw --csv`): CSV on stdin, units row
+    honoured (durations in µs, traffic in Mbyte), markdown table written."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cols = ["ID", "Kernel Name", "gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "launch__registers_per_thread", "dram__bytes_read.sum", "dram__bytes_write.sum"]
+    lines = ["==PROF== noise", ",".join(f'"{c}"' for c in cols), '"","","usecond","%","register/thread","Mbyte","Mbyte"']
+    for i in range(6):
+        k = "void hz::wgrad_kernel<64>(CUtensorMap)" if i % 2 else "hz::adam_kernel<true, false>(float*)"
+        lines.append(",".join(f'"{v}"' for v in [i, k, "2.5" if i % 2 else "1.0", "40.0", "128", "1.5", "0.5"]))
+    out = tmp_path / "t.md"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), "-", "--out", str(out)], input="\n".join(lines),
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    recs = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert recs[0]["launches"] == 6 and recs[0]["distinct_kernels"] == 2 and abs(recs[0]["sum_of_durations_us"] - 10.5) < 1e-6
+    top = recs[1]
+    assert top["kernel"] == "wgrad_kernel<64>" and top["launches"] == 3 and abs(top["us"] - 7.5) < 1e-6 and top["regs"] == 128
+    assert abs(top["dram_MB"] - 6.0) < 1e-6 and top["sm_pct"] == 40.0 and top["tensor_pipe_pct"] is None
+    assert "| `wgrad_kernel<64>` | 3 | 7.5 |" in out.read_text()
