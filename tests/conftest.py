@@ -34,7 +34,7 @@ def pytest_configure(config):
 _SESSION_T0 = [None]
 # wall-clock budget of the whole test session after which the remaining `late` tests are skipped (they are informational;
 # a run that an outer harness kills for taking too long would lose the verified tier's summary line as well)
-_LATE_BUDGET_S = float(os.environ.get("HZ_LATE_BUDGET_S", "330"))
+_LATE_BUDGET_S = float(os.environ.get("HZ_LATE_BUDGET_S", "360"))
 
 
 def pytest_sessionstart(session):

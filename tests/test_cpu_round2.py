@@ -490,3 +490,34 @@ def test_ncu_summary_tool_reads_a_raw_page_csv(tmp_path):
     assert top["kernel"] == "wgrad_kernel<64>" and top["launches"] == 3 and abs(top["us"] - 7.5) < 1e-6 and top["regs"] == 128
     assert abs(top["dram_MB"] - 6.0) < 1e-6 and top["sm_pct"] == 40.0 and top["tensor_pipe_pct"] is None
     assert "| `wgrad_kernel<64>` | 3 | 7.5 |" in out.read_text()
+
+
+def test_sanitizer_report_against_a_fake_tool(tmp_path, monkeypatch):
+    """tests/test_gpu_sanitizer.py with a stand-in compute-sanitizer on PATH: summary parsing, the HZPERF line, and a
+    non-zero error summary failing the test."""
+    import json
+    import stat
+    import sys
+    import warnings
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import test_gpu_sanitizer as T
+    fake = tmp_path / "compute-sanitizer"
+
+    def install(errors):
+        fake.write_text(f"#!{sys.executable}\nimport sys\nprint('========= COMPUTE-SANITIZER')\nprint('...                [100%]')\n"
+                        f"print('3 passed, 140 deselected in 21.0s')\nprint('========= ERROR SUMMARY: {errors} errors')\n"
+                        f"sys.exit({9 if errors else 0})\n")
+        fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    install(0)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        T.test_memcheck_clean_on_elementwise_kernels()
+    line = [str(w.message) for w in rec if str(w.message).startswith("HZPERF sanitizer ")][0]
+    d = json.loads(line.split(" ", 2)[2])
+    assert d["error_summaries"] == [0] and d["tests_passed_under_the_tool"] == 3 and d["exit_code"] == 0
+    install(2)
+    with pytest.raises(AssertionError):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            T.test_memcheck_clean_on_elementwise_kernels()

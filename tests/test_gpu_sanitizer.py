@@ -40,12 +40,20 @@ def _memcheck(selection: str, files, budget_s: int, exe: str = ""):
     rc = proc.returncode
     if "ERROR SUMMARY" not in out:
         pytest.skip("compute-sanitizer produced no summary (tool could not attach?): " + out[-400:].replace("\n", " | "))
+    import json
+    import re
+    import warnings
+    summ = re.findall(r"ERROR SUMMARY: (\d+) error", out)
+    ran = re.findall(r"(\d+) passed", out)
+    warnings.warn("HZPERF sanitizer " + json.dumps({
+        "tool": "compute-sanitizer memcheck", "selection": selection, "error_summaries": [int(x) for x in summ],
+        "tests_passed_under_the_tool": int(ran[-1]) if ran else 0, "exit_code": rc}), UserWarning)
     assert "ERROR SUMMARY: 0 errors" in out and rc == 0, out[-3000:]
     assert " passed" in out, out[-1500:]
 
 
 @pytest.mark.gpu
-@pytest.mark.late(order=13)
+@pytest.mark.late(order=10, limit_s=120)     # right after the numerics tests and the ncu report: hardware-verified kernels only
 def test_memcheck_clean_on_elementwise_kernels():
     """BatchNorm forward + backward (reduce, apply), max-pool forward / backward, the classifier head: 75 s box."""
     _memcheck("test_bn_act and 64-16 or test_maxpool or test_head and 1", ["tests/test_gpu_kernels.py"], 75)
