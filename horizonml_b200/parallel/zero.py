@@ -103,6 +103,11 @@ class ShardedFlatAdam:
         self.lr = sd.get("lr", self.lr)
 
 
+def _peer_device(device: torch.device) -> bool:
+    """the peer-memory kernels run there (seam for the CPU dry run of the GPU tests, tests/conftest.py)"""
+    return device.type == "cuda"
+
+
 class FusedShardedAdam:
     """ZeRO-1 on the peer-memory kernel (``csrc/comm.cu`` ``zero1_kernel``): per gradient bucket ONE kernel reduces the
     bucket over the ranks, applies Adam to the slice this rank owns (moment shards, fp32 master authoritative on the
@@ -124,7 +129,7 @@ class FusedShardedAdam:
         ready = dist.is_available() and dist.is_initialized()
         self.world = ar.world if ar is not None else (dist.get_world_size(group) if ready else 1)
         self.rank = ar.rank if ar is not None else (dist.get_rank(group) if ready else 0)
-        self.native = ar is not None and hasattr(ar, "handle") and flat.device.type == "cuda" and flat.shadow is not None
+        self.native = ar is not None and hasattr(ar, "handle") and _peer_device(flat.device) and flat.shadow is not None
         dev, W = flat.device, self.world
         self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.early_blocks = early_blocks

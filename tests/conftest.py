@@ -191,6 +191,15 @@ def _install_dryrun_shim():
     fn._be = lambda t: nb if fn._state["backend"] == "native" else tb
     fn.step_begin = ops.step_begin = lambda device=None: nb.step_begin(cpu) if fn._state["backend"] == "native" else None
     torch.cuda.synchronize = lambda *a, **k: None
+    import contextlib
+    import horizonml_b200.parallel.zero as zero
+    zero._peer_device = lambda device: True
+
+    class _NoStream:                                   # virtual-rank tests give every rank a stream of its own
+        def synchronize(self):
+            pass
+    torch.cuda.Stream = lambda *a, **k: _NoStream()
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
 
 
 def pytest_collection_modifyitems(config, items):

@@ -34,6 +34,9 @@ class ShimC:
             raise AttributeError(name)
         if name == "conv_supported":             # the real one also asks for the CUDA driver's tensor-map encoder
             return self._real.conv_shape_ok
+        if name == "PeerComm":                   # peer-memory communicator: emulated ranks of one process (see FakePeerComm)
+            FakePeerComm._real = self._real.PeerComm
+            return FakePeerComm
         real = getattr(self._real, name)         # AttributeError = the backend calls a binding that does not exist
         emu = getattr(self, "_emu_" + name, None)
 
@@ -164,8 +167,21 @@ class ShimC:
 
     def _emu_adam_step(self, master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, diff, zero_grad,
                        live_blocks, bump, max_ctas):
-        tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad, live_blocks, diff,
-                     bump, max_ctas)
+        if live_blocks is None:
+            tb.adam_step(master, grad, m, v, shadow, step_t, lr, b1, b2, eps, grad_scale, prev, zero_grad, live_blocks, diff,
+                         bump, max_ctas)
+            return
+        # dead-block elision: the kernel only visits the listed 64-element blocks (gather, update, scatter)
+        idx = _wire_index(live_blocks, master.numel())
+        parts = [t[idx].contiguous() if t is not None else None for t in (master, grad, m, v, prev)]
+        sh = shadow[idx].contiguous() if shadow is not None else None
+        tb.adam_step(parts[0], parts[1], parts[2], parts[3], sh, step_t, lr, b1, b2, eps, grad_scale, parts[4], zero_grad, None,
+                     diff, bump, max_ctas)
+        for dst, src in zip((master, grad, m, v, prev), parts):
+            if dst is not None:
+                dst[idx] = src
+        if shadow is not None:
+            shadow[idx] = sh
 
     def _emu_grad_diff_sq(self, grad, prev):
         return tb.grad_diff_sq(grad, prev)
@@ -175,6 +191,119 @@ class ShimC:
 
     def _emu_stats_update(self, stats, has_prev, loss, correct, batch, diff_sq):
         tb.stats_update(stats, has_prev, loss, correct, batch, diff_sq)
+
+
+def _wire_index(live, n):
+    """element offsets, in wire order, of a bucket with dead-block compaction (`live`: int32 indices of 64-element blocks)"""
+    if live is None:
+        return torch.arange(n)
+    return (live.long()[:, None] * 64 + torch.arange(64)[None, :]).reshape(-1)
+
+
+class FakePeerComm:
+    """Emulation of horizonml_b200._C.PeerComm for ranks that live in ONE process (the virtual-rank tests): the k-th
+    collective of a group completes when the last rank has issued its k-th call (every rank queues its calls in order, like
+    kernels on its stream) — the tests issue every rank's call before they look at any
+    result, as they must on a GPU (the kernels of the early ranks spin until the late ones arrive).  Arithmetic follows
+    the kernels' contract (csrc/comm.cu): wire = bf16(grad * scale) or fp32, summed in rank order in fp32; two-shot and
+    NVLS round the sum to the wire type for their second hop; ZeRO-1: rank r owns wire vectors [r*q, (r+1)*q), q =
+    ceil(nv / W)."""
+    _real = None
+
+    def __init__(self, rank, world, device, max_wire_bytes, max_blocks, heap_bytes=0):
+        try:                                       # the real constructor must accept the argument list
+            FakePeerComm._real(rank, world, device, max_wire_bytes, max_blocks, heap_bytes)
+        except TypeError as e:
+            raise AssertionError(f"C.PeerComm: argument list rejected by the binding: {e}") from None
+        except RuntimeError:
+            pass                                   # (no device to create the communicator on)
+        self.rank, self.world, self.max_wire_bytes = rank, world, max_wire_bytes
+        self.group, self.queue, self.cap = None, [], 0      # queue: this rank's issued, not yet completed collectives (stream order)
+
+    @staticmethod
+    def link_local(comms):
+        assert sorted(c.rank for c in comms) == list(range(len(comms))) and all(c.world == len(comms) for c in comms)
+        for c in comms:
+            c.group = sorted(comms, key=lambda x: x.rank)
+
+    def set_block_cap(self, cap):
+        self.cap = int(cap)
+
+    def error(self):
+        return 0
+
+    def zero1_shard(self, n_wire):
+        return ((n_wire // 8 + self.world - 1) // self.world) * 8
+
+    def blocks_for(self, n, algo, wire_bf16):
+        return 1
+
+    def _arrive(self, kind, payload):
+        assert self.group is not None, "communicator not linked"
+        self.queue.append((kind, payload))
+        while all(c.queue for c in self.group):            # the k-th collective of every rank has been issued: run it
+            heads = [c.queue.pop(0) for c in self.group]
+            assert len({h[0] for h in heads}) == 1, "ranks issued different collectives: " + str([h[0] for h in heads])
+            getattr(FakePeerComm, "_do_" + heads[0][0])(self.group, [h[1] for h in heads])
+
+    def allreduce(self, grad, algo, wire_bf16, scale, live_blocks=None):
+        assert algo in ("oneshot", "twoshot", "nvls", "ll", "bulk") and grad.dtype == torch.float32
+        n = live_blocks.numel() * 64 if live_blocks is not None else grad.numel()
+        assert n % (8 if wire_bf16 else 4) == 0 and n * (2 if wire_bf16 else 4) <= self.max_wire_bytes
+        self._arrive("allreduce", (grad, algo, wire_bf16, scale, live_blocks))
+
+    @staticmethod
+    def _do_allreduce(group, calls):
+        _, algo, wire_bf16, scale, live = calls[0]
+        idx = _wire_index(live, calls[0][0].numel())
+        total = torch.zeros(idx.numel())
+        for g, *_ in calls:                        # rank order
+            w = g[idx] * scale
+            total += w.bfloat16().float() if wire_bf16 else w
+        if algo in ("twoshot", "nvls") and wire_bf16:
+            total = total.bfloat16().float()       # the reduced slice travels as bf16 on the second hop
+        for g, *_ in calls:
+            g[idx] = total
+
+    def zero1_step(self, grad, scale, live_blocks, master, m, v, shadow, prev, diff_out, step, lr, b1, b2, eps, bump):
+        n = live_blocks.numel() * 64 if live_blocks is not None else grad.numel()
+        shard = self.zero1_shard(n)
+        assert m.numel() == shard == v.numel() and (prev is None or prev.numel() == shard) and shadow.dtype == BF16
+        self._arrive("zero1", (grad, scale, live_blocks, master, m, v, shadow, prev, diff_out, step, lr, b1, b2, eps, bump))
+
+    @staticmethod
+    def _do_zero1(group, calls):
+        W = len(group)
+        grad0, scale, live = calls[0][0], calls[0][1], calls[0][2]
+        idx = _wire_index(live, grad0.numel())
+        n = idx.numel()
+        total = torch.zeros(n)
+        for c in calls:
+            total += (c[0][idx] * scale).bfloat16().float()
+            c[0][idx] = 0.0                        # the pack pass clears the gradient
+        q = ((n // 8 + W - 1) // W) * 8
+        new_params = torch.empty(n)
+        diffs = []
+        for r, c in enumerate(calls):
+            _, _, _, master, m, v, shadow, prev, diff_out, step, lr, b1, b2, eps, bump = c
+            lo, hi = min(r * q, n), min(r * q + q, n)
+            own, k = idx[lo:hi], hi - lo
+            g = total[lo:hi]
+            if prev is not None and diff_out is not None:
+                diffs.append(((g - prev[:k]) ** 2).sum())
+                prev[:k] = g
+            t = float(step[0]) + 1.0
+            m[:k] = b1 * m[:k] + (1 - b1) * g
+            v[:k] = b2 * v[:k] + (1 - b2) * g * g
+            denom = v[:k].sqrt() / (1 - b2 ** t) ** 0.5 + eps
+            master[own] = master[own] - (lr / (1 - b1 ** t)) * m[:k] / denom
+            new_params[lo:hi] = master[own]
+        for c in calls:
+            c[6][idx] = new_params.to(BF16)        # every rank's shadow gets every slice
+            if c[7] is not None and c[8] is not None:
+                c[8].add_(sum(diffs))
+            if c[14]:
+                c[9].add_(1.0)
 
 
 @pytest.fixture
