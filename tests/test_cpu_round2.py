@@ -524,3 +524,29 @@ def test_sanitizer_report_against_a_fake_tool(tmp_path, monkeypatch):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             T.test_memcheck_clean_on_elementwise_kernels()
+
+
+@pytest.mark.parametrize("section,tags", [("handoff", ["step", "step"]), ("conv", ["conv"] * 12), ("bigbatch", ["step"] * 3)])
+def test_perf_probe_dry_run(section, tags):
+    """tools/perf_probe.py — the script behind the HZPERF lines of the round-end GPU test run — has never been executed
+    on a GPU: run its sections here on CPU tensors (HZ_PROBE_DRYRUN=1: extension shim, tiny shapes, host clock) and
+    require one well-formed line per measurement and no error field.  (The `bench` section starts bench.py, which needs a
+    device; `steps` is the same function as `handoff`.)"""
+    import json
+    import subprocess
+    import sys
+    from horizonml_b200.ops import _ext
+    if _ext.load(required=False) is None:
+        pytest.skip("extension not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "perf_probe.py"), section], cwd=root,
+                       env=dict(os.environ, HZ_PROBE_DRYRUN="1"), capture_output=True, text=True, timeout=900)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("HZPERF ")]
+    assert r.returncode == 0 and [ln.split(" ", 2)[1] for ln in lines] == tags, (r.stdout[-1500:], r.stderr[-2500:])
+    for ln in lines:
+        d = json.loads(ln.split(" ", 2)[2])
+        assert "error" not in d, d
+        if section != "conv":
+            assert d["ms_per_step"] > 0 and d["fallbacks"] == {} and (d["backend"] == "torch" or d["launches_per_step"] > 100), d
+        elif d["kernel"].startswith("persistent"):
+            assert d["fwd_rel_err_vs_default"] == 0.0 and d["dgrad_rel_err_vs_default"] == 0.0, d

@@ -20,6 +20,32 @@ sys.path.insert(0, ROOT)
 from horizonml_b200 import ops  # noqa: E402
 
 DEV = "cuda:0"
+# HZ_PROBE_DRYRUN=1 (tests/test_cpu_round2.py::test_perf_probe_dry_run): the same code paths on CPU tensors with the extension
+# replaced by the test shim — tiny shapes, host clock instead of CUDA events; checks this script, not the kernels
+DRYRUN = os.environ.get("HZ_PROBE_DRYRUN", "0") == "1"
+SCALE = 1
+if DRYRUN:
+    DEV, SCALE = "cpu", 64
+    os.environ["HZ_GPU_TESTS_DRYRUN"] = "1"
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import conftest as _conftest
+    _conftest._install_dryrun_shim()
+
+
+class _HostEvent:
+    def __init__(self, enable_timing=True):
+        self.t = 0.0
+
+    def record(self):
+        import time
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+def Event():
+    return _HostEvent() if DRYRUN else torch.cuda.Event(enable_timing=True)
 
 
 def report(tag, payload):
@@ -37,7 +63,7 @@ def timed(fn, flush, iters=8):
     tot = 0.0
     for _ in range(iters):
         flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, b = Event(), Event()
         a.record(); fn(); b.record()
         torch.cuda.synchronize()
         tot += a.elapsed_time(b)
@@ -50,7 +76,8 @@ def steps(variants, batch=64, persist=0, timed_steps=30):
     from horizonml_b200.ops import native_backend as nb
     from horizonml_b200.trainers.common import Runtime
     from horizonml_b200.trainers.dp import DPEngine
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    flush = torch.empty((256 << 20) // (SCALE * SCALE), dtype=torch.uint8, device=DEV)
+    batch = max(8, batch // SCALE) if DRYRUN else batch
     g = torch.Generator().manual_seed(0)
     xs = torch.randint(0, 256, (batch, 32, 32, 3), dtype=torch.uint8, generator=g).to(DEV)
     ys = torch.randint(0, 10, (batch,), generator=g).to(DEV)
@@ -60,8 +87,8 @@ def steps(variants, batch=64, persist=0, timed_steps=30):
             R._BN_BWD_IN_DGRAD = hand_off
             if be == "native":
                 nb.C.conv_set_persist(persist)      # baked into the captured graph: set before the engine's first step
-            cfg = TrainConfig(strategy="data", world_size=1, batch_size=batch, device="cuda", dtype="bf16", backend=be,
-                              model=model, quiet=True)
+            cfg = TrainConfig(strategy="data", world_size=1, batch_size=batch, device="cpu" if DRYRUN else "cuda", dtype="bf16",
+                              backend=be, model=model, quiet=True, cuda_graph=not DRYRUN)
             eng = DPEngine(cfg, Runtime(0, 1, torch.device(DEV), torch.bfloat16, be, "none"))
             launches = None
             for i in range(6):
@@ -70,8 +97,8 @@ def steps(variants, batch=64, persist=0, timed_steps=30):
                 if i == 1:
                     launches = sum(nb.LAUNCHES.values()) - before        # (an eager warm-up step: python-side launches)
             torch.cuda.synchronize()
-            K = timed_steps
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+            K = 2 if DRYRUN else timed_steps
+            evs = [(Event(), Event()) for _ in range(K)]
             for a, b in evs:
                 flush.fill_(1)
                 a.record(); eng.step(xs, ys); b.record()
@@ -103,8 +130,8 @@ def conv():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
     except Exception:  # noqa: BLE001
         pass
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
-    B = 4096
+    flush = torch.empty((256 << 20) // (SCALE * SCALE), dtype=torch.uint8, device=DEV)
+    B = 4096 // SCALE
     data = []
     for name, cin, h, cout in (("layer1", 64, 8, 64), ("layer2", 128, 4, 128), ("layer3", 256, 2, 256)):
         g = torch.Generator().manual_seed(1)
