@@ -15,7 +15,7 @@ import warnings
 
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.late(order=10, limit_s=230)]
+pytestmark = [pytest.mark.gpu, pytest.mark.late(order=10, limit_s=190)]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_summary  # noqa: E402  (the aggregation is shared with the offline tool)
@@ -49,9 +49,9 @@ def test_ncu_profile_of_one_training_step():
     if not os.path.exists(exe):
         pytest.skip("ncu not installed")
     t0 = time.time()
-    res = _ncu(exe, METRICS + [TENSOR], 100)
+    res = _ncu(exe, METRICS + [TENSOR], 80)
     if res is not None and res[0].find('"ID"') < 0 and time.time() - t0 < 30:
-        res = _ncu(exe, METRICS, 100)           # refused quickly (a metric name this ncu does not know): base list
+        res = _ncu(exe, METRICS, 80)           # refused quickly (a metric name this ncu does not know): base list
     if res is None:
         pytest.skip("ncu run did not finish within its time box")
     out, err = res

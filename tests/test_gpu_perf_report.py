@@ -22,7 +22,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.late(order=11)]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("section,budget_s", [("steps", 90), ("handoff", 80), ("bench", 120), ("conv", 80), ("bigbatch", 90)])
+@pytest.mark.parametrize("section,budget_s", [("steps", 70), ("handoff", 60), ("bench", 90), ("conv", 60), ("bigbatch", 70)])
 def test_round_end_perf_report(section, budget_s):
     proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "perf_probe.py"), section], cwd=ROOT,
                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
