@@ -25,6 +25,10 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
     config.addinivalue_line("markers", "multigpu: needs >= 2 CUDA devices")
     config.addinivalue_line("markers", "slow: multi-process CPU tests")
+    config.addinivalue_line("markers", "deep: long CPU-side verification of the test infrastructure / never-executed code (dry runs, "
+                                       "engine shims at two ranks): collected after the other CPU tests and skipped once the "
+                                       "session has run for HZ_DEEP_BUDGET_S (420 s) — on a slow machine the CPU tier then "
+                                       "takes no longer than it did before these checks existed")
     config.addinivalue_line("markers", "late: GPU test (or parameter set) written after the round's GPU budget was spent, i.e. "
                                        "never executed on hardware by the author — collected last and reported as "
                                        "XPASS / XFAIL (HZ_LATE_STRICT=1: ordinary tests), so the verified tier decides "
@@ -74,9 +78,14 @@ def _watchdog_loop():
             os._exit(status)
 
 
+_DEEP_BUDGET_S = float(os.environ.get("HZ_DEEP_BUDGET_S", "420"))
+
+
 def pytest_runtest_setup(item):
     import threading
     import time
+    if "deep" in item.keywords and _SESSION_T0[0] is not None and time.time() - _SESSION_T0[0] > _DEEP_BUDGET_S:
+        pytest.skip(f"deep CPU checks: session time budget of {_DEEP_BUDGET_S:.0f} s used up (HZ_DEEP_BUDGET_S)")
     if "late" in item.keywords:
         if _SESSION_T0[0] is not None and time.time() - _SESSION_T0[0] > _LATE_BUDGET_S:
             pytest.skip(f"late tier: session time budget of {_LATE_BUDGET_S:.0f} s used up (HZ_LATE_BUDGET_S)")
@@ -222,7 +231,9 @@ def pytest_collection_modifyitems(config, items):
     # (within the late tier: ascending `order` — the cases closest to verified code first, new tcgen05 code last)
     def rank(it):
         m = it.get_closest_marker("late")
-        return (0, 0) if m is None else (1, int(m.kwargs.get("order", 0)))
+        if m is None:
+            return (0, 1 if "deep" in it.keywords else 0)
+        return (1, int(m.kwargs.get("order", 0)))
     items.sort(key=rank)
     # The late tier has never run on hardware, so its outcome is information, not a gate: a pass is reported as XPASS, a
     # failure as XFAIL, and the exit code reflects the hardware-verified tests only.  HZ_LATE_STRICT=1 (the next

@@ -490,6 +490,7 @@ def test_eval_forward_through_the_native_backend_on_a_shim(shim, model_name):
     assert out[True].shape == (8, 10) and _close(out[True], out[False], 2e-2), (out[True] - out[False]).abs().max()
 
 
+@pytest.mark.deep
 @pytest.mark.parametrize("which,world,handoff", [("dp", 2, False), ("dpz", 2, True), ("pp", 2, True), ("tp", 2, False),
                                                  ("tp", 2, True)])
 def test_parallel_engines_on_a_shim(which, world, handoff):

@@ -331,6 +331,7 @@ def test_bn_backward_sums_handed_over_by_the_consumers_dgrad():
         R._BN_BWD_IN_DGRAD = False
 
 
+@pytest.mark.deep
 def test_late_tier_harness(tmp_path):
     """tests/conftest.py: `late` tests are collected after everything else in ascending `order`, reported as XPASS / XFAIL
     (so they cannot turn the run red or stop it under -x), become ordinary tests with HZ_LATE_STRICT=1, and are skipped
@@ -401,6 +402,7 @@ def test_late_tier_harness(tmp_path):
     assert r.returncode == 0 and "HZPERF: device-timed measurements" in r.stdout and '\nHZPERF step {"ms": 0.5}' in r.stdout, r.stdout
 
 
+@pytest.mark.deep
 def test_late_gpu_tests_dry_run():
     """The GPU test modules written after the last GPU access have never been executed: run their CODE here, on CPU, with
     the extension replaced by the shim of tests/test_cpu_native_plumbing.py (HZ_GPU_TESTS_DRYRUN=1, tests/conftest.py) —
@@ -526,6 +528,7 @@ def test_sanitizer_report_against_a_fake_tool(tmp_path, monkeypatch):
             T.test_memcheck_clean_on_elementwise_kernels()
 
 
+@pytest.mark.deep
 @pytest.mark.parametrize("section,tags", [("handoff", ["step", "step"]), ("conv", ["conv"] * 12), ("bigbatch", ["step"] * 3)])
 def test_perf_probe_dry_run(section, tags):
     """tools/perf_probe.py — the script behind the HZPERF lines of the round-end GPU test run — has never been executed
